@@ -1,0 +1,137 @@
+"""CPU tests of the oracle itself: (1) the restated algorithm vs the reference's functions run
+verbatim (only where /root/reference exists), (2) the restated diffusers U-Net vs the in-repo
+DDPM U-Net (`src/models/ddpm/diffusion.py`) through a weight mapping, (3) the oracle vs the
+committed golden vectors (runs everywhere), (4) an absolute anchor: dense-Jacobian svdvals."""
+import contextlib
+import io
+import os
+import types
+
+import pytest
+import torch
+
+from oracle import pullback_oracle as PO
+from oracle import reference_shim as RS
+from oracle import unet_torch as UT
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(not RS.available(), reason="/root/reference not on this machine")
+
+
+def _quiet(fn, *a, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,op,bi", [("sd_tiny", "mid", 0), ("sd_tiny", "up", 1),
+                                        ("sd_tiny_lin", "mid", 0), ("uncond_tiny", "mid", 0)])
+def test_restatement_matches_verbatim_reference(name, op, bi):
+    m = RS.bind(UT.build_unet(name))
+    x, t, ctx = UT.synthetic_inputs(name)
+    k, iters = 3, 4
+    torch.manual_seed(0)
+    with torch.no_grad():
+        if ctx is not None:
+            u, s, vT = _quiet(m.local_encoder_pullback_zt, x, t, ctx, op=op, block_idx=bi, pca_rank=k,
+                              chunk_size=5, min_iter=iters, max_iter=iters, convergence_threshold=0.)
+        else:
+            u, s, vT = _quiet(m.local_encoder_pullback_xt, x, t, op=op, block_idx=bi, pca_rank=k,
+                              chunk_size=2, min_iter=iters, max_iter=iters, convergence_threshold=0.)
+    torch.manual_seed(0)
+    u2, s2, vT2 = PO.local_encoder_pullback(m, x, t, ctx, op, bi, k, iters, iters, 0.)
+    assert torch.allclose(s, s2, rtol=1e-5)
+    rep = PO.parity_report(s2, vT2, s, vT, u2, u)
+    assert rep["subspace"] > 0.9999 and min(rep["cos"]) > 0.9999 and min(rep["u_cos"]) > 0.9999
+
+
+@needs_ref
+def test_restated_unet2dmodel_matches_inrepo_ddpm():
+    """Maps the weights of the reference's in-repo DDPM (the only U-Net source in the reference)
+    onto the restated diffusers UNet2DModel and compares get_h at ('mid',0)."""
+    PullBackDDPM, _ = RS.load_ddpm()
+    ns = types.SimpleNamespace
+    cfg = ns(model=ns(ch=32, out_ch=3, ch_mult=[1, 1, 2, 2], num_res_blocks=2, attn_resolutions=[8],
+                      dropout=0.0, in_channels=3, resamp_with_conv=True),
+             data=ns(image_size=32))
+    torch.manual_seed(3)
+    ddpm = PullBackDDPM(ns(config=cfg, device="cpu", dtype=torch.float32)).eval()
+    m = UT.build_unet("uncond_tiny")
+    sd = {}
+    src = ddpm.state_dict()
+
+    def cp(dst, s_, lin=False):
+        for suf in ("weight", "bias"):
+            w = src[f"{s_}.{suf}"]
+            if lin and suf == "weight":
+                w = w.reshape(w.shape[0], w.shape[1])
+            sd[f"{dst}.{suf}"] = w
+
+    cp("time_embedding.linear_1", "temb.dense.0"); cp("time_embedding.linear_2", "temb.dense.1")
+    cp("conv_in", "conv_in")
+
+    def res(dst, s_):
+        for a, b in [("norm1", "norm1"), ("conv1", "conv1"), ("time_emb_proj", "temb_proj"),
+                     ("norm2", "norm2"), ("conv2", "conv2")]:
+            cp(f"{dst}.{a}", f"{s_}.{b}")
+        if f"{s_}.nin_shortcut.weight" in src:
+            cp(f"{dst}.conv_shortcut", f"{s_}.nin_shortcut")
+
+    def att(dst, s_):
+        for a, b in [("group_norm", "norm"), ("query", "q"), ("key", "k"), ("value", "v"),
+                     ("proj_attn", "proj_out")]:
+            cp(f"{dst}.{a}", f"{s_}.{b}", lin=a != "group_norm")
+
+    for i in range(4):
+        for j in range(2):
+            res(f"down_blocks.{i}.resnets.{j}", f"down.{i}.block.{j}")
+            if i == 2:
+                att(f"down_blocks.{i}.attentions.{j}", f"down.{i}.attn.{j}")
+        if i != 3:
+            cp(f"down_blocks.{i}.downsamplers.0.conv", f"down.{i}.downsample.conv")
+    res("mid_block.resnets.0", "mid.block_1"); att("mid_block.attentions.0", "mid.attn_1")
+    res("mid_block.resnets.1", "mid.block_2")
+    missing = m.load_state_dict(sd, strict=True)
+    x, t, _ = UT.synthetic_inputs("uncond_tiny")
+    with torch.no_grad():
+        h_ref = ddpm.get_h(x, t, op="mid", block_idx=0)
+        h = PO.get_h_uncond(m, x, t, "mid", 0)
+    assert h.shape == h_ref.shape
+    assert torch.allclose(h, h_ref, rtol=1e-4, atol=1e-5), float((h - h_ref).abs().max())
+
+
+@pytest.mark.parametrize("name,op,bi", [("sd_tiny", "mid", 0)])
+def test_oracle_matches_dense_jacobian(name, op, bi):
+    """Absolute anchor: top singular value of the dense Jacobian."""
+    m = UT.build_unet(name)
+    x, t, ctx = UT.synthetic_inputs(name)
+    f = PO.make_h_fn(m, t, ctx, op, bi)
+    J = torch.autograd.functional.jacobian(lambda z: f(z).reshape(-1), x).reshape(-1, x.numel())
+    sv = torch.linalg.svdvals(J.double())
+    torch.manual_seed(0)
+    u, s, vT = PO.local_encoder_pullback(m, x, t, ctx, op, bi, 3, 40, 40, 0.)
+    assert abs(float(s[0]) - float(sv[0])) / float(sv[0]) < 1e-3
+    assert torch.allclose(u.norm(dim=0), s, rtol=2e-2)      # ||u_i|| ~= s_i (one half-step apart)
+    assert torch.allclose(vT @ vT.T, torch.eye(3), atol=1e-5)
+
+
+def _golden_files():
+    if not os.path.isdir(GOLDEN):
+        return []
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt"))
+
+
+@pytest.mark.parametrize("fname", _golden_files())
+def test_oracle_reproduces_golden(fname):
+    """Golden vectors were produced by the reference's verbatim functions
+    (scripts/make_golden.py); the oracle must reproduce them on this machine."""
+    g = torch.load(os.path.join(GOLDEN, fname))
+    if g["n_params"] > 60e6:
+        pytest.skip("full-size golden: covered by the gpu parity test")
+    m = UT.build_unet(g["config"], build_up=g["op"] == "up")
+    x, t, ctx = UT.synthetic_inputs(g["config"])
+    u, s, vT = PO.local_encoder_pullback(m, x, t, ctx, g["op"], g["block_idx"], g["k"],
+                                         g["iters"], g["iters"], 0., v0=g["v0"])
+    rep = PO.parity_report(s, vT, g["s"], g["vT"])
+    assert rep["s_rel_max"] < 1e-4, rep
+    assert rep["subspace"] > 0.9995 and rep["cos_min_gapped"] > 0.995, rep
