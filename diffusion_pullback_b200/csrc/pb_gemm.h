@@ -1,0 +1,40 @@
+// Segmented (implicit-)GEMM descriptor shared by the engine and the backends.
+//
+//   D[b,h][m,n] = alpha * sum_seg sum_k A_seg[b,h][m,k] * B_seg[b,h][n,k]  + bias[n] + beta * R[b,h][m,n]
+//
+// All matrices are fp32, K-major (row-major [rows][K]); the contraction runs on the tcgen05 tensor
+// cores as TF32 with fp32 accumulation in TMEM.
+//
+//  * plain mode: A is [M][K] with leading dimension lda and two batch strides (b = tangent index,
+//    h = attention head); a stride of 0 broadcasts the operand over that batch dimension.
+//  * conv mode (3x3, stride 1, pad 1, NHWC): A is the activation tensor [nb][H][W][C] (pixel stride lda);
+//    M = nb*H*W rows; K runs over 9 taps x C channels and B is the packed filter [N][9*C]
+//    (tap-major, channel fastest).  Padding is produced by TMA out-of-bounds zero fill.
+#pragma once
+#include <cstdint>
+
+struct PbGemmSeg {
+  const float* A; long lda, sAb, sAh;
+  const float* B; long ldb, sBb, sBh;
+  int K;
+};
+
+struct PbGemm {
+  int M, N;
+  int nseg;
+  PbGemmSeg seg[2];
+  float* D; long ldd, sDb, sDh;
+  const float* R; long ldr, sRb, sRh;   // optional residual (may alias D element-for-element)
+  const float* bias;                     // optional [N]
+  float alpha, beta;
+  int nb, nh;                            // batch extents (plain mode); conv mode: nb images, nh = 1
+  int conv;                              // 0 plain, 1 = 3x3/s1/p1 NHWC implicit GEMM
+  int H, W;                              // conv mode spatial extent
+  int round_tf32;                        // round the stored result to TF32 (RNA) for a GEMM-only consumer
+};
+
+static inline PbGemm pb_gemm_init() {
+  PbGemm g{};
+  g.nseg = 1; g.alpha = 1.f; g.beta = 0.f; g.nb = 1; g.nh = 1;
+  return g;
+}

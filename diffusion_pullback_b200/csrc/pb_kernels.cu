@@ -1,0 +1,974 @@
+// Hand-written sm_100a kernels for everything on the pullback hot path that is not a contraction:
+// GroupNorm/LayerNorm/SiLU/GEGLU/softmax forward + their tangent (JVP) and cotangent (VJP)
+// linearisations around the cached primal, layout moves, stride-2 im2col, tiny direct convs, the
+// time embedding and the weight packers.  All HBM-bound: 128-bit accesses along the channel axis,
+// grids sized to cover 148 SMs, reductions by warp shuffles.  See pb_kernels.h for semantics.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <algorithm>
+
+#include "pb_kernels.h"
+
+const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st);
+
+namespace {
+
+constexpr int kSMs = 148;
+
+inline const char* cuda_err(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+inline const char* last_err() { return cuda_err(cudaGetLastError()); }
+inline cudaStream_t S(pb_stream st) { return static_cast<cudaStream_t>(st); }
+inline unsigned grid_for(long work, int block, int per_sm = 8) {
+  long g = (work + block - 1) / block;
+  return (unsigned)std::max<long>(1, std::min<long>(g, (long)kSMs * per_sm));
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float maybe_round(float x, int r) { return r ? rna_tf32(x) : x; }
+__device__ __forceinline__ float4 maybe_round4(float4 v, int r) {
+  if (r) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoidf_(x); }
+__device__ __forceinline__ float silu_d(float x) { float s = sigmoidf_(x); return s * (1.f + x * (1.f - s)); }
+__device__ __forceinline__ float gelu_f(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_d(float g) {
+  return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// data movement
+// ------------------------------------------------------------------------------------------------
+__global__ void copy2d_v4(float* __restrict__ dst, long ldd, const float* __restrict__ src, long lds, long rows,
+                          int cols4, float beta) {
+  const long total = rows * cols4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols4; const int c = int(i % cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
+    float4* d = reinterpret_cast<float4*>(dst + r * ldd + c);
+    if (beta != 0.f) { float4 o = *d; v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w; }
+    *d = v;
+  }
+}
+__global__ void copy2d_s(float* __restrict__ dst, long ldd, const float* __restrict__ src, long lds, long rows,
+                         int cols, float beta) {
+  const long total = rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols; const int c = int(i % cols);
+    float v = src[r * lds + c];
+    float* d = dst + r * ldd + c;
+    *d = beta != 0.f ? v + beta * *d : v;
+  }
+}
+
+// src [nb][R][C] -> dst [nb][C][ldd]
+__global__ void transpose_k(float* __restrict__ dst, long ldd, const float* __restrict__ src, int R, int C, float beta,
+                            int rnd) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* s = src + (long)b * R * C;
+  float* d = dst + (long)b * C * ldd;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? s[(long)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) {
+      float v = tile[threadIdx.x][i];
+      float* p = d + (long)c * ldd + r;
+      if (beta != 0.f) v += beta * *p;
+      *p = maybe_round(v, rnd);
+    }
+  }
+}
+
+__global__ void upsample2x_k(const float4* __restrict__ x, int nb, int H, int W, int C4, float4* __restrict__ y,
+                             int rnd) {
+  const long total = (long)nb * 4 * H * W * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C4); t /= C4;
+    const int ox = int(t % (2 * W)); t /= 2 * W;
+    const int oy = int(t % (2 * H)); t /= 2 * H;
+    const int b = int(t);
+    y[i] = maybe_round4(x[(((long)b * H + oy / 2) * W + ox / 2) * C4 + c], rnd);
+  }
+}
+__global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, int W, int C4, float4* __restrict__ gx,
+                                 float beta) {
+  const long total = (long)nb * H * W * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C4); t /= C4;
+    const int x = int(t % W); t /= W;
+    const int y = int(t % H); t /= H;
+    const int b = int(t);
+    float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float4 v = gy[(((long)b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C4 + c];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    if (beta != 0.f) { const float4 o = gx[i]; a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
+    gx[i] = a;
+  }
+}
+__global__ void round_tf32_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = rna_tf32(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stride-2 3x3 conv helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void im2col_s2_k(const float4* __restrict__ x, int nb, int H, int W, int C4, int pad, int Ho, int Wo,
+                            float4* __restrict__ col, int rnd) {
+  const long total = (long)nb * Ho * Wo * 9 * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C4); t /= C4;
+    const int tap = int(t % 9); t /= 9;
+    const int ox = int(t % Wo); t /= Wo;
+    const int oy = int(t % Ho); t /= Ho;
+    const int b = int(t);
+    const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long)b * H + iy) * W + ix) * C4 + c];
+    col[i] = maybe_round4(v, rnd);
+  }
+}
+__global__ void col2im_s2_k(const float4* __restrict__ col, int nb, int H, int W, int C4, int pad, int Ho, int Wo,
+                            float4* __restrict__ gx, float beta) {
+  const long total = (long)nb * H * W * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C4); t /= C4;
+    const int ix = int(t % W); t /= W;
+    const int iy = int(t % H); t /= H;
+    const int b = int(t);
+    float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = iy + pad - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ix + pad - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        const float4 v = col[((((long)b * Ho + oy) * Wo + ox) * 9 + ky * 3 + kx) * C4 + c];
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+    }
+    if (beta != 0.f) { const float4 o = gx[i]; a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
+    gx[i] = a;
+  }
+}
+
+// thread per output element; for tiny Cin (conv_in)
+__global__ void conv3x3_direct_thin_in(const float* __restrict__ x, int nb, int H, int W, int Cin,
+                                       const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                       float* __restrict__ y, float beta) {
+  const long total = (long)nb * H * W * Cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int co = int(t % Cout); t /= Cout;
+    const int px = int(t % W); t /= W;
+    const int py = int(t % H); t /= H;
+    const int b = int(t);
+    float acc = bias ? bias[co] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const float* xp = x + (((long)b * H + iy) * W + ix) * Cin;
+      const float* wp = w + ((long)co * 9 + tap) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xp[ci], wp[ci], acc);
+    }
+    y[i] = beta != 0.f ? acc + beta * y[i] : acc;
+  }
+}
+// warp per output pixel, lanes split Cin; for tiny Cout (transpose of conv_in)
+template <int MAXCO>
+__global__ void conv3x3_direct_thin_out(const float* __restrict__ x, int nb, int H, int W, int Cin,
+                                        const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                                        float* __restrict__ y, float beta) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long total = (long)nb * H * W;
+  for (long pix = warp; pix < total; pix += nwarps) {
+    long t = pix;
+    const int px = int(t % W); t /= W;
+    const int py = int(t % H); t /= H;
+    const int b = int(t);
+    float acc[MAXCO];
+#pragma unroll
+    for (int co = 0; co < MAXCO; ++co) acc[co] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const float* xp = x + (((long)b * H + iy) * W + ix) * Cin;
+      for (int ci = lane; ci < Cin; ci += 32) {
+        const float xv = xp[ci];
+#pragma unroll
+        for (int co = 0; co < MAXCO; ++co)
+          if (co < Cout) acc[co] = fmaf(xv, w[((long)co * 9 + tap) * Cin + ci], acc[co]);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < MAXCO; ++co) {
+      if (co < Cout) {
+        float v = warp_sum(acc[co]);
+        if (lane == 0) {
+          if (bias) v += bias[co];
+          float* p = y + pix * Cout + co;
+          *p = beta != 0.f ? v + beta * *p : v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+// Per-(image, channel) sums over a chunk of pixels.  Threads own fixed channel quads so partials
+// live in registers; pixel lanes are combined through shared memory, chunks through atomics.
+//   MODE 0 (fwd):  s1 = sum (x - pivot_c), s2 = sum (x - pivot_c)^2,  pivot_c = x[b][0][c]
+//   MODE 1 (jvp):  u = t                    ; s1 = sum u, s2 = sum xhat*u
+//   MODE 2 (vjp):  u = t * act'(y) * gamma  ; s1 = sum u, s2 = sum xhat*u
+struct GnGeom { int TP, QPT, R; };   // threads per pixel row, quads per thread, pixel lanes
+static GnGeom gn_geom(int C) {
+  const int Q = C / 4;
+  int TP = 1;
+  for (int d = 1; d <= Q && d <= 256; ++d)
+    if (Q % d == 0) TP = d;
+  GnGeom g;
+  g.TP = TP; g.QPT = Q / TP; g.R = std::max(1, 256 / TP);
+  return g;
+}
+constexpr int GN_MAX_QPT = 8;
+
+template <int MODE>
+__global__ void gn_sums_k(const float* __restrict__ xp, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ gamma, const float* __restrict__ beta_, int HW, int C, int G,
+                          int silu, const float* __restrict__ t, int TP, int QPT, int R, int pix_per_block,
+                          float* __restrict__ sums /* [nb][C][2] */) {
+  extern __shared__ float sh[];                 // [R][C][2]
+  const int b = blockIdx.y;
+  const int tp = threadIdx.x % TP, pl = threadIdx.x / TP;
+  const int cpg = C / G;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(HW, p0 + pix_per_block);
+  const float* xb = MODE == 0 ? xp + (long)b * HW * C : xp;       // primal is a single image in lin modes
+  const float* tb = MODE == 0 ? nullptr : t + (long)b * HW * C;
+  const float* mb = MODE == 0 ? nullptr : mean;
+  const float* rb = MODE == 0 ? nullptr : rstd;
+  float a1[GN_MAX_QPT][4], a2[GN_MAX_QPT][4];
+#pragma unroll
+  for (int j = 0; j < GN_MAX_QPT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a1[j][e] = 0.f; a2[j][e] = 0.f; }
+  for (int pix = p0 + pl; pix < p1; pix += R) {
+#pragma unroll
+    for (int j = 0; j < GN_MAX_QPT; ++j) {
+      if (j >= QPT) break;
+      const int c = 4 * (tp + j * TP);
+      const float4 xv = *reinterpret_cast<const float4*>(xb + (long)pix * C + c);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (MODE == 0) {
+        const float4 pv = *reinterpret_cast<const float4*>(xb + c);
+        const float ps[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float d = xs[e] - ps[e]; a1[j][e] += d; a2[j][e] = fmaf(d, d, a2[j][e]); }
+      } else {
+        const float4 tv = *reinterpret_cast<const float4*>(tb + (long)pix * C + c);
+        const float ts[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int g = (c + e) / cpg;
+          const float xh = (xs[e] - mb[g]) * rb[g];
+          float u = ts[e];
+          if (MODE == 2) {
+            const float ga = gamma[c + e];
+            u *= silu ? ga * silu_d(fmaf(ga, xh, beta_[c + e])) : ga;
+          }
+          a1[j][e] += u; a2[j][e] = fmaf(xh, u, a2[j][e]);
+        }
+      }
+    }
+  }
+  // combine pixel lanes
+#pragma unroll
+  for (int j = 0; j < GN_MAX_QPT; ++j) {
+    if (j >= QPT) break;
+    const int c = 4 * (tp + j * TP);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      sh[((long)pl * C + c + e) * 2 + 0] = a1[j][e];
+      sh[((long)pl * C + c + e) * 2 + 1] = a2[j][e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s += sh[(long)r * C * 2 + i];
+    atomicAdd(sums + (long)b * C * 2 + i, s);
+  }
+}
+
+__global__ void gn_finalize_fwd_k(const float* __restrict__ x, const float* __restrict__ sums, int HW, int C, int G,
+                                  float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  const int cpg = C / G;
+  const double n = HW;
+  double msum = 0.0;
+  for (int i = 0; i < cpg; ++i) {
+    const int c = g * cpg + i;
+    msum += (double)x[(long)b * HW * C + c] + (double)sums[((long)b * C + c) * 2] / n;
+  }
+  const double mg = msum / cpg;
+  double m2 = 0.0;
+  for (int i = 0; i < cpg; ++i) {
+    const int c = g * cpg + i;
+    const double s1 = sums[((long)b * C + c) * 2], s2 = sums[((long)b * C + c) * 2 + 1];
+    const double mc = (double)x[(long)b * HW * C + c] + s1 / n;
+    m2 += (s2 - s1 * s1 / n) + n * (mc - mg) * (mc - mg);
+  }
+  const double var = m2 / (n * cpg);
+  mean[b * G + g] = (float)mg;
+  rstd[b * G + g] = (float)(1.0 / sqrt(var + (double)eps));
+}
+// tmp[b][g] = (mean_g(u), mean_g(xhat*u))
+__global__ void gn_finalize_lin_k(const float* __restrict__ sums, int HW, int C, int G, float* __restrict__ tmp) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  const int cpg = C / G;
+  double s1 = 0, s2 = 0;
+  for (int i = 0; i < cpg; ++i) {
+    s1 += sums[((long)b * C + g * cpg + i) * 2];
+    s2 += sums[((long)b * C + g * cpg + i) * 2 + 1];
+  }
+  const double n = (double)HW * cpg;
+  tmp[((long)b * G + g) * 2] = (float)(s1 / n);
+  tmp[((long)b * G + g) * 2 + 1] = (float)(s2 / n);
+}
+
+__global__ void gn_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
+                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                               const float* __restrict__ beta_, long total4, int HW, int C, int G, int silu, int rnd,
+                               float* __restrict__ y) {
+  const int C4 = C / 4, cpg = C / G;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int c = int(i % C4) * 4;
+    const int b = int(i / ((long)HW * C4));
+    const float4 xv = reinterpret_cast<const float4*>(x)[i];
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (c + e) / cpg;
+      float v = fmaf(gamma[c + e], (xs[e] - mean[b * G + g]) * rstd[b * G + g], beta_[c + e]);
+      if (silu) v = silu_f(v);
+      o[e] = maybe_round(v, rnd);
+    }
+    reinterpret_cast<float4*>(y)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+template <int MODE>
+__global__ void gn_apply_lin_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                               const float* __restrict__ beta_, const float* __restrict__ tmp, long total4, int HW,
+                               int C, int G, int silu, const float* __restrict__ t, float* __restrict__ out, float acc,
+                               int rnd) {
+  const int C4 = C / 4, cpg = C / G;
+  const long per_img4 = (long)HW * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int c = int(i % C4) * 4;
+    const int b = int(i / per_img4);
+    const float4 xv = reinterpret_cast<const float4*>(xp)[i % per_img4];
+    const float4 tv = reinterpret_cast<const float4*>(t)[i];
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float ts[4] = {tv.x, tv.y, tv.z, tv.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (c + e) / cpg;
+      const float rs = rstd[g];
+      const float xh = (xs[e] - mean[g]) * rs;
+      const float m1 = tmp[((long)b * G + g) * 2], m2 = tmp[((long)b * G + g) * 2 + 1];
+      const float ga = gamma[c + e];
+      const float f = silu ? ga * silu_d(fmaf(ga, xh, beta_[c + e])) : ga;
+      float v;
+      if (MODE == 0) v = f * rs * (ts[e] - m1 - xh * m2);
+      else v = rs * (ts[e] * f - m1 - xh * m2);
+      o[e] = v;
+    }
+    float4* op = reinterpret_cast<float4*>(out) + i;
+    if (acc != 0.f) { const float4 p = *op; o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
+    *op = maybe_round4(make_float4(o[0], o[1], o[2], o[3]), rnd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per token row
+// ------------------------------------------------------------------------------------------------
+__global__ void ln_fwd_k(const float* __restrict__ x, long rows, int C, const float* __restrict__ gamma,
+                         const float* __restrict__ beta_, float eps, float* __restrict__ y, float* __restrict__ mean,
+                         float* __restrict__ rstd, int rnd) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long r = warp; r < rows; r += nw) {
+    const float* xr = x + r * C;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) { const float4 v = *reinterpret_cast<const float4*>(xr + c); s += v.x + v.y + v.z + v.w; }
+    const float m = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      q += (v.x - m) * (v.x - m) + (v.y - m) * (v.y - m) + (v.z - m) * (v.z - m) + (v.w - m) * (v.w - m);
+    }
+    const float rs = rsqrtf(warp_sum(q) / C + eps);
+    if (lane == 0) { mean[r] = m; rstd[r] = rs; }
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 bb = *reinterpret_cast<const float4*>(beta_ + c);
+      float4 o = make_float4(fmaf(g.x, (v.x - m) * rs, bb.x), fmaf(g.y, (v.y - m) * rs, bb.y),
+                             fmaf(g.z, (v.z - m) * rs, bb.z), fmaf(g.w, (v.w - m) * rs, bb.w));
+      *reinterpret_cast<float4*>(y + r * C + c) = maybe_round4(o, rnd);
+    }
+  }
+}
+template <int MODE>
+__global__ void ln_lin_k(const float* __restrict__ xp, const float* __restrict__ mean, const float* __restrict__ rstd,
+                         const float* __restrict__ gamma, long rows_p, int C, const float* __restrict__ t, long rows,
+                         float* __restrict__ out, float acc, int rnd) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long r = warp; r < rows; r += nw) {
+    const long rp = r % rows_p;
+    const float* xr = xp + rp * C;
+    const float* tr = t + r * C;
+    const float m = mean[rp], rs = rstd[rp];
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      float4 tv = *reinterpret_cast<const float4*>(tr + c);
+      if (MODE == 1) { const float4 g = *reinterpret_cast<const float4*>(gamma + c); tv.x *= g.x; tv.y *= g.y; tv.z *= g.z; tv.w *= g.w; }
+      s1 += tv.x + tv.y + tv.z + tv.w;
+      s2 += (xv.x - m) * rs * tv.x + (xv.y - m) * rs * tv.y + (xv.z - m) * rs * tv.z + (xv.w - m) * rs * tv.w;
+    }
+    const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const float4 tv = *reinterpret_cast<const float4*>(tr + c);
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {tv.x, tv.y, tv.z, tv.w}, gs[4] = {g.x, g.y, g.z, g.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (xs[e] - m) * rs;
+        o[e] = MODE == 0 ? gs[e] * rs * (ts[e] - m1 - xh * m2) : rs * (ts[e] * gs[e] - m1 - xh * m2);
+      }
+      float4* op = reinterpret_cast<float4*>(out + r * C + c);
+      if (acc != 0.f) { const float4 p = *op; o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
+      *op = maybe_round4(make_float4(o[0], o[1], o[2], o[3]), rnd);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU
+// ------------------------------------------------------------------------------------------------
+__global__ void geglu_fwd_k(const float* __restrict__ h, long rows, int F, float* __restrict__ y, int rnd) {
+  const int F4 = F / 4;
+  const long total = rows * F4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / F4; const int c = int(i % F4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(h + r * 2 * F + c);
+    const float4 g = *reinterpret_cast<const float4*>(h + r * 2 * F + F + c);
+    float4 o = make_float4(a.x * gelu_f(g.x), a.y * gelu_f(g.y), a.z * gelu_f(g.z), a.w * gelu_f(g.w));
+    *reinterpret_cast<float4*>(y + r * F + c) = maybe_round4(o, rnd);
+  }
+}
+__global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ dh, long rows, int F,
+                            float* __restrict__ dy, int rnd) {
+  const int F4 = F / 4;
+  const long total = rows * F4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / F4; const int c = int(i % F4) * 4;
+    const long rp = r % rows_p;
+    const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
+    const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
+    const float4 da = *reinterpret_cast<const float4*>(dh + r * 2 * F + c);
+    const float4 dg = *reinterpret_cast<const float4*>(dh + r * 2 * F + F + c);
+    float4 o = make_float4(da.x * gelu_f(g.x) + a.x * gelu_d(g.x) * dg.x, da.y * gelu_f(g.y) + a.y * gelu_d(g.y) * dg.y,
+                           da.z * gelu_f(g.z) + a.z * gelu_d(g.z) * dg.z, da.w * gelu_f(g.w) + a.w * gelu_d(g.w) * dg.w);
+    *reinterpret_cast<float4*>(dy + r * F + c) = maybe_round4(o, rnd);
+  }
+}
+__global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ gy, long rows, int F,
+                            float* __restrict__ gh, int rnd) {
+  const int F4 = F / 4;
+  const long total = rows * F4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / F4; const int c = int(i % F4) * 4;
+    const long rp = r % rows_p;
+    const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
+    const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
+    const float4 y = *reinterpret_cast<const float4*>(gy + r * F + c);
+    float4 ga = make_float4(y.x * gelu_f(g.x), y.y * gelu_f(g.y), y.z * gelu_f(g.z), y.w * gelu_f(g.w));
+    float4 gg = make_float4(y.x * a.x * gelu_d(g.x), y.y * a.y * gelu_d(g.y), y.z * a.z * gelu_d(g.z),
+                            y.w * a.w * gelu_d(g.w));
+    *reinterpret_cast<float4*>(gh + r * 2 * F + c) = maybe_round4(ga, rnd);
+    *reinterpret_cast<float4*>(gh + r * 2 * F + F + c) = maybe_round4(gg, rnd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// softmax (rows of attention scores).  NT threads cooperate on one row; up to 4 float4 per thread
+// are cached in registers so HBM is touched once per element, longer rows are re-read.
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ float row_reduce_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if (NT == 32) return v;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < NT / 32) ? sh[l] : 0.f;
+  return warp_sum(t);
+}
+template <int NT>
+__device__ __forceinline__ float row_reduce_max(float v, float* sh) {
+  v = warp_max(v);
+  if (NT == 32) return v;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < NT / 32) ? sh[l] : -INFINITY;
+  return warp_max(t);
+}
+
+// NT == 32: one warp per row, blockDim = 256 (8 rows per block); NT == 256: one block per row.
+template <int NT>
+__global__ void softmax_fwd_k(float* __restrict__ Sm, long rows, int cols, long ld, int rnd) {
+  __shared__ float sh[8];
+  const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  const long row0 = NT == 32 ? (blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5)) : blockIdx.x;
+  const long rstep = NT == 32 ? (long)gridDim.x * (blockDim.x >> 5) : gridDim.x;
+  for (long r = row0; r < rows; r += rstep) {
+    float* p = Sm + r * ld;
+    float mx = -INFINITY;
+    for (int c = tid; c < cols; c += NT) mx = fmaxf(mx, p[c]);
+    mx = row_reduce_max<NT>(mx, sh);
+    float s = 0.f;
+    for (int c = tid; c < cols; c += NT) s += __expf(p[c] - mx);
+    s = row_reduce_sum<NT>(s, sh);
+    const float inv = 1.f / s;
+    for (int c = tid; c < cols; c += NT) p[c] = maybe_round(__expf(p[c] - mx) * inv, rnd);
+    for (int c = cols + tid; c < ld; c += NT) p[c] = 0.f;
+  }
+}
+
+template <int NT>
+__global__ void softmax_lin_k(const float* __restrict__ P, long rows_p, float* __restrict__ dS, long rows, int cols,
+                              long ld, int rnd) {
+  __shared__ float sh[8];
+  const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
+  const long row0 = NT == 32 ? (blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5)) : blockIdx.x;
+  const long rstep = NT == 32 ? (long)gridDim.x * (blockDim.x >> 5) : gridDim.x;
+  const int cols4 = (cols + 3) / 4;               // ld % 4 == 0 and ld >= cols, so float4 loads stay in the row
+  for (long r = row0; r < rows; r += rstep) {
+    const float4* pp = reinterpret_cast<const float4*>(P + (r % rows_p) * ld);
+    float4* dp = reinterpret_cast<float4*>(dS + r * ld);
+    float4 pc[4], dc[4];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c4 = tid + j * NT;
+      if (c4 < cols4) {
+        pc[j] = pp[c4]; dc[j] = dp[c4];
+        const int c = c4 * 4;
+        if (c + 3 < cols) dot += pc[j].x * dc[j].x + pc[j].y * dc[j].y + pc[j].z * dc[j].z + pc[j].w * dc[j].w;
+        else {
+          dot += pc[j].x * dc[j].x;
+          if (c + 1 < cols) dot += pc[j].y * dc[j].y;
+          if (c + 2 < cols) dot += pc[j].z * dc[j].z;
+        }
+      }
+    }
+    for (int c4 = tid + 4 * NT; c4 < cols4; c4 += NT) {      // long rows: uncached tail
+      const float4 a = pp[c4], b = dp[c4];
+      const int c = c4 * 4;
+      dot += a.x * b.x;
+      if (c + 1 < cols) dot += a.y * b.y;
+      if (c + 2 < cols) dot += a.z * b.z;
+      if (c + 3 < cols) dot += a.w * b.w;
+    }
+    dot = row_reduce_sum<NT>(dot, sh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c4 = tid + j * NT;
+      if (c4 < cols4) {
+        float4 o = make_float4(pc[j].x * (dc[j].x - dot), pc[j].y * (dc[j].y - dot), pc[j].z * (dc[j].z - dot),
+                               pc[j].w * (dc[j].w - dot));
+        dp[c4] = maybe_round4(o, rnd);
+      }
+    }
+    for (int c4 = tid + 4 * NT; c4 < cols4; c4 += NT) {
+      const float4 a = pp[c4], b = dp[c4];
+      dp[c4] = maybe_round4(make_float4(a.x * (b.x - dot), a.y * (b.y - dot), a.z * (b.z - dot), a.w * (b.w - dot)), rnd);
+    }
+  }
+}
+
+__global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float* __restrict__ o, long ldo, int nb,
+                             int N, int H, int d, float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const long total = (long)nb * H * N;
+  for (long w = warp; w < total; w += nw) {
+    long t = w;
+    const int i = int(t % N); t /= N;
+    const int h = int(t % H); t /= H;
+    const int b = int(t);
+    const float* g = go + ((long)b * N + i) * ldg + h * d;
+    const float* oo = o + (long)i * ldo + h * d;
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s = fmaf(g[c], oo[c], s);
+    s = warp_sum(s);
+    if (lane == 0) delta[w] = s;
+  }
+}
+__global__ void attn_ds_k(const float* __restrict__ P, float* __restrict__ dP, const float* __restrict__ delta,
+                          float scale, int nb, int H, int rows, int cols, long ld, int col_mode, int rnd) {
+  const long ld4 = ld / 4;
+  const long per_b = (long)H * rows * ld4;
+  const long total = (long)nb * per_b;
+  const int ndelta = col_mode ? cols : rows;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = int(i % ld4) * 4;
+    const long rr = i / ld4;                  // (b*H + h)*rows + r
+    const int r = int(rr % rows);
+    const long bh = rr / rows;
+    const float4 p = reinterpret_cast<const float4*>(P)[i % per_b];
+    float4 v = reinterpret_cast<float4*>(dP)[i];
+    const float* dl = delta + bh * ndelta;
+    float d0, d1, d2, d3;
+    if (col_mode) {
+      d0 = c < cols ? dl[c] : 0.f; d1 = c + 1 < cols ? dl[c + 1] : 0.f;
+      d2 = c + 2 < cols ? dl[c + 2] : 0.f; d3 = c + 3 < cols ? dl[c + 3] : 0.f;
+    } else {
+      d0 = d1 = d2 = d3 = dl[r];
+    }
+    v.x = scale * p.x * (v.x - d0); v.y = scale * p.y * (v.y - d1);
+    v.z = scale * p.z * (v.z - d2); v.w = scale * p.w * (v.w - d3);
+    reinterpret_cast<float4*>(dP)[i] = maybe_round4(v, rnd);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// time embedding / gemv / packing
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_k(float t, int dim, int flip, float shift, float* __restrict__ out) {
+  const int half = dim / 2;
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float e = expf(-logf(10000.f) * (float)j / ((float)half - shift));
+    const float a = t * e;
+    const float s = sinf(a), c = cosf(a);
+    if (flip) { out[j] = c; out[half + j] = s; } else { out[j] = s; out[half + j] = c; }
+  }
+}
+__global__ void gemv_k(const float* __restrict__ Wm, const float* __restrict__ x, const float* __restrict__ bias,
+                       int N, int K, int silu_in, int silu_out, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < N; n += nw) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float xv = x[k];
+      if (silu_in) xv = silu_f(xv);
+      s = fmaf(Wm[(long)n * K + k], xv, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (bias) s += bias[n];
+      y[n] = silu_out ? silu_f(s) : s;
+    }
+  }
+}
+__global__ void pack_conv3x3_k(const float* __restrict__ w, int Co, int Ci, float* __restrict__ fwd,
+                               float* __restrict__ bwd, int rnd) {
+  const long total = (long)Co * Ci * 9;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int tap = int(t % 9); t /= 9;
+    const int ci = int(t % Ci); t /= Ci;
+    const int co = int(t);
+    const float v = maybe_round(w[i], rnd);
+    if (fwd) fwd[((long)co * 9 + tap) * Ci + ci] = v;
+    if (bwd) bwd[((long)ci * 9 + (8 - tap)) * Co + co] = v;
+  }
+}
+
+}  // namespace
+
+// ==================================================================================================
+// C entry points
+// ==================================================================================================
+#define CHECK_ALIGN4(v, what) \
+  if ((v) % 4) return what " must be a multiple of 4"
+
+PBK pbk_backend_name() { return "cuda-sm100a"; }
+PBK pbk_memset0(void* p, size_t bytes, pb_stream st) { return cuda_err(cudaMemsetAsync(p, 0, bytes, S(st))); }
+PBK pbk_copy(void* dst, const void* src, size_t bytes, pb_stream st) {
+  return cuda_err(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, S(st)));
+}
+PBK pbk_download(void* host_dst, const void* src, size_t bytes, pb_stream st) {
+  cudaError_t e = cudaMemcpyAsync(host_dst, src, bytes, cudaMemcpyDeviceToHost, S(st));
+  if (e != cudaSuccess) return cuda_err(e);
+  return cuda_err(cudaStreamSynchronize(S(st)));
+}
+PBK pbk_upload(void* dst, const void* host_src, size_t bytes, pb_stream st) {
+  cudaError_t e = cudaMemcpyAsync(dst, host_src, bytes, cudaMemcpyHostToDevice, S(st));
+  if (e != cudaSuccess) return cuda_err(e);
+  return cuda_err(cudaStreamSynchronize(S(st)));
+}
+PBK pbk_sync(pb_stream st) { return cuda_err(cudaStreamSynchronize(S(st))); }
+
+PBK pbk_gemm(const PbGemm* g, pb_stream st) { return pb_gemm_launch(*g, S(st)); }
+
+PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
+                       float* y, float beta, pb_stream st) {
+  if (Cout <= 8 && Cin >= 32) {
+    const long pix = (long)nb * H * W;
+    conv3x3_direct_thin_out<8><<<grid_for(pix * 32, 256), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
+  } else {
+    const long total = (long)nb * H * W * Cout;
+    conv3x3_direct_thin_in<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
+  }
+  return last_err();
+}
+PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* col, int round_tf32,
+                  pb_stream st) {
+  CHECK_ALIGN4(C, "im2col: C");
+  const long total = (long)nb * Ho * Wo * 9 * (C / 4);
+  im2col_s2_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(x), nb, H, W, C / 4, pad_lo,
+                                                          Ho, Wo, reinterpret_cast<float4*>(col), round_tf32);
+  return last_err();
+}
+PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* gx, float beta,
+                  pb_stream st) {
+  CHECK_ALIGN4(C, "col2im: C");
+  const long total = (long)nb * H * W * (C / 4);
+  col2im_s2_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(col), nb, H, W, C / 4, pad_lo,
+                                                          Ho, Wo, reinterpret_cast<float4*>(gx), beta);
+  return last_err();
+}
+
+PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, pb_stream st) {
+  if (rows <= 0 || cols <= 0) return nullptr;
+  const bool v4 = (cols % 4 == 0) && (ldd % 4 == 0) && (lds % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  if (v4) copy2d_v4<<<grid_for(rows * (cols / 4), 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols / 4, beta);
+  else copy2d_s<<<grid_for(rows * cols, 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols, beta);
+  return last_err();
+}
+PBK pbk_transpose(float* dst, long ldd, const float* src, int nb, int R, int C, float beta, int round_tf32,
+                  pb_stream st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32, nb), block(32, 8);
+  transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, src, R, C, beta, round_tf32);
+  return last_err();
+}
+PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int round_tf32, pb_stream st) {
+  CHECK_ALIGN4(C, "upsample: C");
+  const long total = (long)nb * 4 * H * W * (C / 4);
+  upsample2x_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(x), nb, H, W, C / 4,
+                                                           reinterpret_cast<float4*>(y), round_tf32);
+  return last_err();
+}
+PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, pb_stream st) {
+  CHECK_ALIGN4(C, "upsample_vjp: C");
+  const long total = (long)nb * H * W * (C / 4);
+  upsample2x_vjp_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(gy), nb, H, W, C / 4,
+                                                               reinterpret_cast<float4*>(gx), beta);
+  return last_err();
+}
+PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {
+  round_tf32_k<<<grid_for((long)n, 256, 16), 256, 0, S(st)>>>(dst, src, n);
+  return last_err();
+}
+
+// ---- GroupNorm ----
+static const char* gn_launch_sums(int mode, const float* xp, const float* mean, const float* rstd, const float* gamma,
+                                  const float* beta, int HW, int C, int G, int silu, const float* t, int nb,
+                                  float* sums, cudaStream_t st) {
+  if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
+  const GnGeom g = gn_geom(C);
+  if (g.QPT > GN_MAX_QPT) return "groupnorm: channel count not supported (too many quads per thread)";
+  const int block = g.TP * g.R;
+  const size_t shmem = (size_t)g.R * C * 2 * sizeof(float);
+  // enough blocks to cover the machine, but at least R pixels each
+  int chunks = std::max(1, std::min((HW + g.R - 1) / g.R, (kSMs * 4 + nb - 1) / nb));
+  const int ppb = (HW + chunks - 1) / chunks;
+  chunks = (HW + ppb - 1) / ppb;
+  dim3 grid(chunks, nb);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)nb * C * 2 * sizeof(float), st);
+  if (e != cudaSuccess) return cuda_err(e);
+  if (shmem > 48 * 1024) {
+    if (mode == 0) cudaFuncSetAttribute(gn_sums_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+    if (mode == 1) cudaFuncSetAttribute(gn_sums_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+    if (mode == 2) cudaFuncSetAttribute(gn_sums_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
+  }
+  if (mode == 0) gn_sums_k<0><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
+  else if (mode == 1) gn_sums_k<1><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
+  else gn_sums_k<2><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
+  return last_err();
+}
+
+PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float* tmp,
+                 pb_stream st) {
+  if (G > 1024) return "groupnorm: too many groups";
+  if (const char* e = gn_launch_sums(0, x, nullptr, nullptr, nullptr, nullptr, HW, C, G, 0, nullptr, nb, tmp, S(st)))
+    return e;
+  gn_finalize_fwd_k<<<nb, ((G + 31) / 32) * 32, 0, S(st)>>>(x, tmp, HW, C, G, eps, mean, rstd);
+  return last_err();
+}
+PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int nb,
+                 int HW, int C, int G, int silu, int round_tf32, float* y, pb_stream st) {
+  const long total4 = (long)nb * HW * (C / 4);
+  gn_apply_fwd_k<<<grid_for(total4, 256, 16), 256, 0, S(st)>>>(x, mean, rstd, gamma, beta, total4, HW, C, G, silu,
+                                                              round_tf32, y);
+  return last_err();
+}
+PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
+               int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
+               float* tmp, pb_stream st) {
+  float* sums = tmp;                                  // [nb][C][2]
+  tmp = tmp + (size_t)nb * C * 2;                     // [nb][G][2]
+  if (const char* e = gn_launch_sums(mode ? 2 : 1, xp, mean, rstd, gamma, beta, HW, C, G, silu, t, nb, sums, S(st)))
+    return e;
+  gn_finalize_lin_k<<<nb, ((G + 31) / 32) * 32, 0, S(st)>>>(sums, HW, C, G, tmp);
+  const long total4 = (long)nb * HW * (C / 4);
+  if (mode == 0)
+    gn_apply_lin_k<0><<<grid_for(total4, 256, 16), 256, 0, S(st)>>>(xp, mean, rstd, gamma, beta, tmp, total4, HW, C, G,
+                                                                   silu, t, out, acc, round_tf32);
+  else
+    gn_apply_lin_k<1><<<grid_for(total4, 256, 16), 256, 0, S(st)>>>(xp, mean, rstd, gamma, beta, tmp, total4, HW, C, G,
+                                                                   silu, t, out, acc, round_tf32);
+  return last_err();
+}
+
+// ---- LayerNorm ----
+PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float* beta, float eps, float* y,
+               float* mean, float* rstd, int round_tf32, pb_stream st) {
+  CHECK_ALIGN4(C, "layernorm: C");
+  ln_fwd_k<<<grid_for(rows * 32, 256, 8), 256, 0, S(st)>>>(x, rows, C, gamma, beta, eps, y, mean, rstd, round_tf32);
+  return last_err();
+}
+PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
+               const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st) {
+  CHECK_ALIGN4(C, "layernorm: C");
+  const long rows = rows_p * nb;
+  if (mode == 0) ln_lin_k<0><<<grid_for(rows * 32, 256, 8), 256, 0, S(st)>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, round_tf32);
+  else ln_lin_k<1><<<grid_for(rows * 32, 256, 8), 256, 0, S(st)>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, round_tf32);
+  return last_err();
+}
+
+// ---- GEGLU ----
+PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st) {
+  CHECK_ALIGN4(F, "geglu: F");
+  geglu_fwd_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(h, rows, F, y, round_tf32);
+  return last_err();
+}
+PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
+                  pb_stream st) {
+  CHECK_ALIGN4(F, "geglu: F");
+  const long rows = rows_p * nb;
+  geglu_jvp_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32);
+  return last_err();
+}
+PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
+                  pb_stream st) {
+  CHECK_ALIGN4(F, "geglu: F");
+  const long rows = rows_p * nb;
+  geglu_vjp_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32);
+  return last_err();
+}
+
+// ---- softmax ----
+PBK pbk_softmax_fwd(float* Sm, long rows, int cols, long ld, int round_tf32, pb_stream st) {
+  if (cols <= 512) softmax_fwd_k<32><<<grid_for(rows, 8, 16), 256, 0, S(st)>>>(Sm, rows, cols, ld, round_tf32);
+  else softmax_fwd_k<256><<<(unsigned)std::min<long>(rows, kSMs * 16), 256, 0, S(st)>>>(Sm, rows, cols, ld, round_tf32);
+  return last_err();
+}
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32,
+                    pb_stream st) {
+  CHECK_ALIGN4(ld, "softmax_lin: ld");
+  const long rows = rows_p * nb;
+  if (cols <= 512) softmax_lin_k<32><<<grid_for(rows, 8, 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32);
+  else softmax_lin_k<256><<<(unsigned)std::min<long>(rows, kSMs * 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32);
+  return last_err();
+}
+PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
+                   pb_stream st) {
+  const long total = (long)nb * H * N;
+  attn_delta_k<<<grid_for(total * 32, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta);
+  return last_err();
+}
+PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
+                int col_mode, int round_tf32, pb_stream st) {
+  CHECK_ALIGN4(ld, "attn_ds: ld");
+  const long total = (long)nb * H * rows * (ld / 4);
+  attn_ds_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(P, dP, delta, scale, nb, H, rows, cols, ld, col_mode, round_tf32);
+  return last_err();
+}
+
+// ---- time embedding / gemv / packing ----
+PBK pbk_timestep_embedding(float t, int dim, int flip_sin_to_cos, float freq_shift, float* out, pb_stream st) {
+  timestep_embedding_k<<<1, 256, 0, S(st)>>>(t, dim, flip_sin_to_cos, freq_shift, out);
+  return last_err();
+}
+PBK pbk_gemv(const float* Wm, const float* x, const float* bias, int N, int K, int silu_in, int silu_out, float* y,
+             pb_stream st) {
+  gemv_k<<<grid_for((long)N * 32, 256, 8), 256, 0, S(st)>>>(Wm, x, bias, N, K, silu_in, silu_out, y);
+  return last_err();
+}
+PBK pbk_pack_conv3x3(const float* w, int Co, int Ci, float* fwd, float* bwd, int round_tf32, pb_stream st) {
+  pack_conv3x3_k<<<grid_for((long)Co * Ci * 9, 256, 16), 256, 0, S(st)>>>(w, Co, Ci, fwd, bwd, round_tf32);
+  return last_err();
+}

@@ -1,0 +1,106 @@
+// Leaf-kernel interface between the engine (pb_engine.cpp, device-agnostic host C++) and the
+// kernel library.  The product library implements every pbk_* as hand-written sm_100a CUDA
+// (pb_kernels.cu, pb_gemm_sm100.cu, pb_ortho.cu).  tests/hostsim/ provides a plain-C++ double of
+// the same symbols so the engine's sequencing logic can be unit-tested without a GPU; that double
+// is test infrastructure only and is never linked into, or reachable from, the product library.
+//
+// Conventions: fp32, activations are [batch][pixels-or-tokens][channels] (NHWC), `st` is a
+// cudaStream_t, every call is stream-ordered and returns nullptr or a static error string.
+// "xp" arguments are PRIMAL tensors cached once per (x_t, t, prompt); "t"/"g" arguments carry the
+// nb tangent (JVP) or cotangent (VJP) directions packed on the batch axis.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "pb_gemm.h"
+
+typedef void* pb_stream;
+#define PBK extern "C" const char*
+
+// ---- memory ----
+PBK pbk_memset0(void* p, size_t bytes, pb_stream st);
+PBK pbk_copy(void* dst, const void* src, size_t bytes, pb_stream st);            // device -> device
+PBK pbk_download(void* host_dst, const void* src, size_t bytes, pb_stream st);   // blocking
+PBK pbk_upload(void* dst, const void* host_src, size_t bytes, pb_stream st);     // blocking
+PBK pbk_sync(pb_stream st);
+PBK pbk_backend_name();
+
+// ---- contraction ----
+PBK pbk_gemm(const PbGemm* g, pb_stream st);
+// direct 3x3/s1/p1 conv for tiny channel counts (conv_in and its transpose); w is [Cout][9][Cin]
+PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
+                       float* y, float beta, pb_stream st);
+// stride-2 3x3 conv as im2col + GEMM; input row = 2*o + tap - pad_lo (pad_lo 1: SD, 0: DDPM (0,1,0,1) pad)
+PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* col, int round_tf32,
+                  pb_stream st);
+PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* gx, float beta,
+                  pb_stream st);
+
+// ---- data movement ----
+// dst[r][c] = src[r][c] + beta * dst[r][c]   (channel-slice copies: concat / split / residual fan-in)
+PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, pb_stream st);
+// src [nb][R][C] -> dst [nb][C][ldd] (ldd >= R); dst = src^T + beta * dst
+PBK pbk_transpose(float* dst, long ldd, const float* src, int nb, int R, int C, float beta, int round_tf32,
+                  pb_stream st);
+PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int round_tf32, pb_stream st);
+PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, pb_stream st);
+PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
+
+// ---- GroupNorm (+ optional SiLU) ----
+// tmp: nb*C*2 floats of scratch
+PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float* tmp,
+                 pb_stream st);
+PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int nb,
+                 int HW, int C, int G, int silu, int round_tf32, float* y, pb_stream st);
+// Linearisation of y = act(gamma * xhat + beta) around the cached primal xp (one image, [HW][C]).
+//   mode 0 (JVP): out = act'(.) * gamma * rstd * (t - mean_g(t) - xhat * mean_g(xhat * t))
+//   mode 1 (VJP): g = t * act'(.) * gamma ; out = rstd * (g - mean_g(g) - xhat * mean_g(xhat * g))
+// out = result + acc * out.  tmp: nb*(C+G)*2 floats of scratch.
+PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
+               int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
+               float* tmp, pb_stream st);
+
+// ---- LayerNorm over the channel axis ----
+PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float* beta, float eps, float* y,
+               float* mean, float* rstd, int round_tf32, pb_stream st);
+PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
+               const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st);
+
+// ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
+PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st);
+PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
+                  pb_stream st);
+PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
+                  pb_stream st);
+
+// ---- softmax pieces (attention probabilities are materialised per (head, query) row) ----
+PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int round_tf32, pb_stream st);
+// dS <- P * (dS - rowsum(P * dS)); P has rows_p rows and is broadcast over the nb tangents
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32,
+                    pb_stream st);
+// delta[b][h][i] = sum_c go[b][i][h*d + c] * o[i][h*d + c]
+PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
+                   pb_stream st);
+// dP[b][h][r][c] <- scale * P[h][r][c] * (dP[b][h][r][c] - (col_mode ? delta[b][h][c] : delta[b][h][r]))
+PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
+                int col_mode, int round_tf32, pb_stream st);
+
+// ---- time embedding (primal only) ----
+PBK pbk_timestep_embedding(float t, int dim, int flip_sin_to_cos, float freq_shift, float* out, pb_stream st);
+// y = act_out(W[N][K] . act_in(x) + bias); act flags: 1 = SiLU
+PBK pbk_gemv(const float* Wm, const float* x, const float* bias, int N, int K, int silu_in, int silu_out, float* y,
+             pb_stream st);
+
+// ---- weight packing (one-time) ----
+// w [Co][Ci][3][3] (PyTorch) -> fwd [Co][9][Ci], bwd [Ci][9][Co] with taps flipped (transpose conv)
+PBK pbk_pack_conv3x3(const float* w, int Co, int Ci, float* fwd, float* bwd, int round_tf32, pb_stream st);
+
+// ---- subspace re-orthonormalisation (replaces torch.linalg.svd of the k x n_in matrix) ----
+// G = W W^T, M = W Vprev^T  (fp64 accumulation), W/Vprev: [k][n]
+PBK pbk_gram2(const float* Wm, const float* Vprev, int k, long n, double* G, double* M, pb_stream st);
+// Jacobi eigen-decomposition of G (one warp, fp64): sv[i] = lambda_i^(1/4) descending (the reference returns
+// sqrt of svdvals(W) = sqrt(sqrt(eig))), Rm[i][j] = sign_i * X[j][i] / sqrt(lambda_i), sign from M.
+PBK pbk_jacobi(const double* G, const double* M, int k, float* Rm, float* sv, pb_stream st);
+// V = Rm W ; metrics[0] += sum (V - Vprev)^2 ; metrics[1] += #{|V - Vprev| > atol + rtol*|V|}
+PBK pbk_rotate(const float* Wm, const float* Rm, const float* Vprev, int k, long n, float atol, float rtol, float* V,
+               float* metrics, pb_stream st);

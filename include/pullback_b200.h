@@ -1,0 +1,115 @@
+/* pullback_b200 -- C ABI of the B200-native pullback hot path.
+ *
+ * Drop-in boundary for the one hot path of enkeejunior1/Diffusion-Pullback:
+ *   local_encoder_pullback_zt   (reference src/utils/utils.py:722-816, bound at utils.py:333)
+ *   local_encoder_pullback_xt   (reference src/utils/utils.py:165-249, bound at utils.py:104)
+ *   get_h / get_h_uncond        (reference src/utils/utils.py:438-527 / :114-163, bound at :326 / :103)
+ * The reference is pure Python; these entry points are what a ctypes binding for that path binds
+ * (see INTEGRATION.md for the stub).  Plain pointers and sizes only, no torch / C++ types.
+ *
+ * Memory: the library never allocates user-visible device memory.  The caller allocates three
+ * device regions whose sizes the library reports after pb_plan(): the packed-weight region, the
+ * primal cache and the tangent workspace.  All calls are ordered on the cudaStream_t passed in
+ * (as void*); only pb_pullback() synchronises (once per iteration after min_iter, to evaluate the
+ * reference's early-exit test).  One handle per (device, U-Net); not thread-safe per handle.
+ *
+ * Every function returns 0 on success or a negative pb_status; pb_last_error() gives the text.
+ */
+#ifndef PULLBACK_B200_H
+#define PULLBACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_handle pb_handle;
+
+enum pb_status { PB_OK = 0, PB_EINVAL = -1, PB_ESTATE = -2, PB_ECUDA = -3, PB_EMISSING = -4 };
+
+enum pb_unet_kind {
+  PB_UNET_COND = 0,   /* diffusers UNet2DConditionModel (Stable Diffusion): get_h, utils.py:438-527   */
+  PB_UNET_UNCOND = 1  /* diffusers UNet2DModel (DDPM CelebA-HQ ...): get_h_uncond, utils.py:114-163   */
+};
+enum pb_op { PB_OP_MID = 0, PB_OP_UP = 1 }; /* `op='down'` raises in the reference  */
+
+#define PB_MAX_LEVELS 8
+
+/* Architecture of the U-Net whose x_t -> h map is linearised (diffusers 0.11.0 config subset). */
+typedef struct pb_unet_cfg {
+  int32_t kind;                              /* pb_unet_kind */
+  int32_t in_channels;
+  int32_t n_levels;                          /* len(block_out_channels) */
+  int32_t block_out_channels[PB_MAX_LEVELS];
+  int32_t down_has_attn[PB_MAX_LEVELS];      /* CrossAttnDownBlock2D / AttnDownBlock2D */
+  int32_t up_has_attn[PB_MAX_LEVELS];        /* CrossAttnUpBlock2D (COND only) */
+  int32_t heads[PB_MAX_LEVELS];              /* attention heads per level (SD 1.x: 8; SD 2.x: 5,10,20,20; DDPM: 1) */
+  int32_t layers_per_block;
+  int32_t cross_attention_dim;               /* COND only */
+  int32_t norm_num_groups;
+  float norm_eps;                            /* resnet GroupNorm eps (transformer GroupNorm uses 1e-6, LayerNorm 1e-5) */
+  int32_t flip_sin_to_cos;
+  float freq_shift;
+  int32_t downsample_padding;                /* 1: symmetric pad (SD); 0: (0,1,0,1) pad (DDPM) */
+} pb_unet_cfg;
+
+/* One named parameter in PyTorch layout, resident on the device (a state_dict entry). */
+typedef struct pb_tensor_desc {
+  const char* name;                          /* diffusers state_dict key, e.g. "mid_block.resnets.0.conv1.weight" */
+  const float* data;                         /* device pointer, contiguous fp32 */
+  int32_t ndim;
+  int64_t shape[4];
+} pb_tensor_desc;
+
+typedef struct pb_sizes {
+  size_t packed_weight_bytes;                /* both conv/linear layouts, TF32-rounded */
+  size_t primal_cache_bytes;                 /* linearisation cache for one (x_t, t, prompt) */
+  size_t workspace_bytes;                    /* k_max tangents/cotangents + scratch */
+  int64_t n_in, n_out;                       /* numel(x_t), numel(h) */
+  int32_t out_channels, out_h, out_w;
+} pb_sizes;
+
+typedef struct pb_iter_info {
+  int32_t iters_done;
+  int32_t converged;                         /* reference early-exit fired (allclose && i > min_iter) */
+  float last_dist;                           /* || V_i - V_{i-1} ||_2  (the reference's printed metric) */
+} pb_iter_info;
+
+int pb_create(const pb_unet_cfg* cfg, pb_handle** out);
+void pb_destroy(pb_handle* h);
+const char* pb_last_error(const pb_handle* h);
+const char* pb_backend(void);                /* "cuda-sm100a" for the product library */
+
+/* Fix the problem geometry: latent H x W, truncation point (op, block_idx), largest rank, text length. */
+int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int32_t block_idx, int32_t k_max,
+            int32_t ctx_len, pb_sizes* sizes);
+
+/* Repack the state_dict once into `packed` (size pb_sizes.packed_weight_bytes). */
+int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n, void* packed, void* stream);
+
+/* Primal pass at (x_t [C,H,W] NCHW, t, ctx [ctx_len, cross_attention_dim] or NULL): fills the linearisation
+ * cache.  `primal_cache` / `workspace` are the caller's regions.  Optionally returns h (NCHW) in h_out. */
+int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx, void* primal_cache, void* workspace,
+                 float* h_out, void* stream);
+
+/* U[k][n_out] = J V,  V: [k][n_in]   (both NCHW-flattened rows; replaces the jacfwd call, utils.py:766-775) */
+int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream);
+/* W[k][n_in] = U^T J, U: [k][n_out]  (replaces autograd.functional.jacobian, utils.py:790-797) */
+int pb_vjp(pb_handle* h, const float* U, int32_t k, float* W, void* stream);
+/* (s, V) from W as torch.linalg.svd would give (utils.py:799): V rows orthonormal, s = sqrt(svdvals(W)),
+ * descending.  Vprev (may be NULL) fixes the row signs and feeds metrics[0]=||V-Vprev||^2, metrics[1]=#violations
+ * of allclose(atol,rtol=1e-5).  All device pointers; metrics may be NULL. */
+int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t k, float atol, float* V, float* s,
+                      float* metrics, void* stream);
+
+/* The whole loop of utils.py:756-808: V0 [k][n_in] -> u [k][n_out] (the reference returns its transpose view),
+ * s [k], vT [k][n_in].  Device pointers; info is host memory. */
+int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u,
+                float* s, float* vT, pb_iter_info* info, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PULLBACK_B200_H */
