@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- pullback JVP-iters/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one synthetic problem: the primal pass at (x_t, t, prompt) plus the full
+subspace iteration of `local_encoder_pullback_zt` (BASELINE.json configs[1]: SD-v1.5 512^2, mid-block_0, pca_rank 5,
+50 power iterations, edit_t = 0.7 T; random-init weights, synthetic 4x64x64 latent).  One JVP-iter = k JVP columns +
+k VJP columns + re-orthonormalisation; value = (ranks x steps x iterations) / seconds.
+
+  value     : inputs (x_t, ctx, V0) resident in HBM before the timed region, device-timed with CUDA events, max over ranks
+  e2e       : the same steps through the C-ABI host entry pb_pullback_host (pinned HOST buffers in and out)
+  roofline  : algorithmic flops of one iteration (2 k F_tan) / measured iteration time, against the measured
+              dense bf16 peak of MEASURED_PEAKS.json (the MMA kind used is TF32, nominally half that peak)
+  cpu_baseline (N = 1, rank 0): the oracle port of the reference algorithm on torch-CPU, one iteration
+  --impl reference: the reference's CPU path (oracle port) alone, on the same config / metric
+
+Multi-GPU: independent problems are sharded over ranks (weak scaling, no data-path collective); one NCCL all-gather of the
+singular values / vectors of every solved problem closes the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name: (model config, op, block_idx, k, iterations, F_tan GF, primal GF)
+WORKLOADS = {
+    "sd15_mid_k5_i50": ("sd15", "mid", 0, 5, 50, 309.1, 261.4),
+    "sd15_up1_k5_i50": ("sd15", "up", 1, 5, 50, 486.5, 438.7),
+    "sd15_mid_k16_i50": ("sd15", "mid", 0, 16, 50, 309.1, 261.4),
+    "sd21_768_mid_k5_i50": ("sd21_768", "mid", 0, 5, 50, 971.1, 724.8),
+    "celebahq_mid_k2_i10": ("celebahq", "mid", 0, 2, 10, 135.3, 135.2),
+    "sd_small_mid_k5_i50": ("sd_small", "mid", 0, 5, 50, 0.0, 0.0),
+}
+METRIC, UNIT = "pullback JVP-iters/sec", "iters/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [c.strip() for c in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_iteration(model_name, op, bi, k_s, iters=1, threads=None):
+    """ORACLE LEG (test infrastructure used as the CPU baseline): the reference algorithm (utils.py:722-816 restated in
+    oracle/pullback_oracle.py) on torch-CPU fp32 with all host threads.  Returns seconds per subspace iteration at rank k_s."""
+    from oracle import pullback_oracle as PO
+    from oracle import unet_torch as UT
+    torch.set_num_threads(threads or os.cpu_count())
+    m = UT.build_unet(model_name, build_up=(op == "up"))
+    x, t, ctx = UT.synthetic_inputs(model_name)
+    torch.manual_seed(0)
+    v0 = PO.initial_subspace(x.numel(), k_s)
+    t0 = time.perf_counter()
+    PO.local_encoder_pullback(m, x, t, ctx, op, bi, k_s, iters, iters, 0.0, v0=v0)
+    return (time.perf_counter() - t0) / iters
+
+
+def run_reference(args, wl):
+    model_name, op, bi, k, iters, f_tan, f_primal = WORKLOADS[wl]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pullback_oracle as PO
+    from oracle import unet_torch as UT
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    m = UT.build_unet(model_name, build_up=(op == "up"))
+    x, t, ctx = UT.synthetic_inputs(model_name)
+    f = PO.make_h_fn(m, t, ctx, op, bi)
+
+    def iteration(k_s, seed):
+        torch.manual_seed(seed)
+        v0 = PO.initial_subspace(x.numel(), k_s)
+        t0 = time.perf_counter()
+        PO.local_encoder_pullback(m, x, t, ctx, op, bi, k_s, 1, 1, 0.0, v0=v0)
+        return time.perf_counter() - t0
+
+    t_col = iteration(1, 0)                                  # probe (also warms the thread pool)
+    budget = 200.0
+    k_s = 1
+    for cand in (k, 2, 1):
+        if cand <= k and (args.steps + args.warmup) * cand * t_col <= budget:
+            k_s = cand
+            break
+    for i in range(args.warmup):
+        iteration(k_s, 100 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        iteration(k_s, 200 + i)
+    dt = (time.perf_counter() - t0) / args.steps
+    per_iter = dt * (k / k_s)                                # reference cost per iteration is linear in k (k dual forwards + k backwards)
+    value = 1.0 / per_iter
+    sample = (f"each step = ONE subspace iteration (1 of {iters}) at rank {k_s} of {k} on the full {model_name} {op}-{bi} problem"
+              + ("" if k_s == k else f", scaled x{k}/{k_s} to rank {k}"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "model": model_name, "op": op, "block_idx": bi, "pca_rank": k, "power_iters": iters,
+                       "device": "host CPU (torch-cpu autograd, oracle port of the reference algorithm)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+    import diffusion_pullback_b200 as PB
+    from diffusion_pullback_b200 import synthetic as SY
+    model_name, op, bi, k, iters, f_tan, f_primal = WORKLOADS[wl]
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, args.warmup
+    unet = SY.SyntheticUNet(model_name, upto=(op, bi), device=dev)
+    cfg = PB.unet_config(unet)
+    size, ctx_len = unet.config["sample_size"], unet.config["ctx_len"]
+    eng = PB.PullbackEngine(cfg, size, size, op, bi, k, ctx_len, dev)
+    eng.bind(unet.state_dict())
+    unet._sd = None                                          # packed copy lives in the engine now
+    torch.cuda.empty_cache()
+    _, t, ctx = SY.synthetic_inputs(model_name)
+    tval = float(t)
+    # one independent problem per (rank, step): synthetic x_t and the reference's randn + QR start (utils.py:750-752)
+    xs, v0s = [], []
+    for i in range(K + Wm):
+        g = torch.Generator().manual_seed(1234 + 1000 * i + rank)
+        xs.append(torch.randn(1, cfg["in_channels"], size, size, generator=g))
+        g2 = torch.Generator().manual_seed(i * world + rank)
+        q, _ = torch.linalg.qr(torch.randn(eng.n_in, k, generator=g2))
+        v0s.append(q.T.contiguous())
+    xd = [x.to(dev) for x in xs]
+    v0d = [v.to(dev) for v in v0s]
+    ctxd = ctx.to(dev) if ctx is not None else None
+    results = []
+
+    def step(i):
+        eng.set_point(xd[i], tval, ctxd)
+        u, s, vT, info = eng.pullback(v0d[i], iters, iters, 0.0)
+        return s, vT
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(Wm, Wm + K):
+        results.append(step(i))
+    payload = torch.cat([torch.cat([s, vT.reshape(-1)]) for s, vT in results])
+    if world > 1:
+        gathered = [torch.empty_like(payload) for _ in range(world)]
+        dist.all_gather(gathered, payload)                   # the single collective: singular values + vectors of every problem
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = eng.launches - l0
+    if world > 1:
+        tmax = torch.tensor([ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax)
+    secs = ms / 1e3
+    value = world * K * iters / secs
+
+    # ---- e2e: the C-ABI host entry with pinned host buffers, H2D / D2H inside the timed region ----
+    xh = [x.contiguous().pin_memory() for x in xs]
+    v0h = [v.pin_memory() for v in v0s]
+    ctxh = ctx.contiguous().pin_memory() if ctx is not None else None
+    out = (torch.empty(k, eng.n_out).pin_memory(), torch.empty(k).pin_memory(), torch.empty(k, eng.n_in).pin_memory())
+    for i in range(min(Wm, 1)):
+        eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Wm, Wm + K):
+        eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax)
+    h2d = 4 * (eng.n_in + (ctx.numel() if ctx is not None else 0) + k * eng.n_in)
+    d2h = 4 * (k * eng.n_out + k + k * eng.n_in)
+
+    if rank == 0:
+        peak_tf, peak_hbm, peak_src = peaks()
+        flops_iter = 2.0 * k * f_tan * 1e9
+        step_flops = flops_iter * iters + f_primal * 1e9
+        achieved = step_flops * K / secs / 1e12 if f_tan else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,
+                           "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K,
+                           "parallelism": f"problem-sharded x{world}", "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
+                           "column_iters_per_s": value * k},
+                "clocks": clocks,
+                "e2e": {"value": world * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                             "note": "algorithmic flops of one step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; "
+                                     "dominant kernel gemm_tf32_kernel (tcgen05 kind::tf32, nominal peak = half of bf16); peak = " + peak_src}}
+        if world == 1 and not args.no_cpu_baseline:
+            k_s = k
+            sec_iter = cpu_reference_iteration(model_name, op, bi, k_s)
+            line["cpu_baseline"] = {"value": 1.0 / sec_iter, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"1 of {iters} subspace iterations at rank {k_s} on the full {model_name} {op}-{bi} problem "
+                                              f"(oracle port of utils.py:722-816, torch-cpu fp32, {sec_iter:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args, args.workload)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3                                   # timing rule: W >= 3
+        run_ours(args, args.workload)
+
+
+if __name__ == "__main__":
+    main()

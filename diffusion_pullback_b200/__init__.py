@@ -1,0 +1,5 @@
+"""pullback_b200 -- B200-native (sm_100a) implementation of Diffusion-Pullback's
+`local_encoder_pullback_zt/xt` hot path.  See DESIGN.md."""
+from .api import (get_h, get_h_uncond, local_encoder_pullback_xt, local_encoder_pullback_zt,  # noqa: F401
+                  patch_unet, refresh_weights)
+from .engine import PullbackEngine, unet_config  # noqa: F401

@@ -1,0 +1,116 @@
+"""ctypes loader for libpullback_b200.so.  Fails loudly when the CUDA library is missing: there is
+no fallback path (the product is the sm_100a library)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpullback_b200.so")
+
+PB_MAX_LEVELS = 8
+
+
+class PbUnetCfg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("in_channels", C.c_int32), ("n_levels", C.c_int32),
+                ("block_out_channels", C.c_int32 * PB_MAX_LEVELS),
+                ("down_has_attn", C.c_int32 * PB_MAX_LEVELS),
+                ("up_has_attn", C.c_int32 * PB_MAX_LEVELS),
+                ("heads", C.c_int32 * PB_MAX_LEVELS),
+                ("layers_per_block", C.c_int32), ("cross_attention_dim", C.c_int32),
+                ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float),
+                ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float),
+                ("downsample_padding", C.c_int32)]
+
+
+class PbTensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * 4)]
+
+
+class PbSizes(C.Structure):
+    _fields_ = [("packed_weight_bytes", C.c_size_t), ("primal_cache_bytes", C.c_size_t),
+                ("workspace_bytes", C.c_size_t), ("n_in", C.c_int64), ("n_out", C.c_int64),
+                ("out_channels", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32)]
+
+
+class PbIterInfo(C.Structure):
+    _fields_ = [("iters_done", C.c_int32), ("converged", C.c_int32), ("last_dist", C.c_float)]
+
+
+class PbGemmSeg(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_long), ("sAb", C.c_long), ("sAh", C.c_long),
+                ("B", C.c_void_p), ("ldb", C.c_long), ("sBb", C.c_long), ("sBh", C.c_long),
+                ("K", C.c_int)]
+
+
+class PbGemm(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("nseg", C.c_int), ("seg", PbGemmSeg * 2),
+                ("D", C.c_void_p), ("ldd", C.c_long), ("sDb", C.c_long), ("sDh", C.c_long),
+                ("R", C.c_void_p), ("ldr", C.c_long), ("sRb", C.c_long), ("sRh", C.c_long),
+                ("bias", C.c_void_p), ("alpha", C.c_float), ("beta", C.c_float),
+                ("nb", C.c_int), ("nh", C.c_int), ("conv", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("round_tf32", C.c_int), ("precise", C.c_int)]
+
+
+_lib = None
+_raw = None
+
+
+def raw() -> C.CDLL:
+    global _raw
+    if _raw is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m diffusion_pullback_b200.build` "
+                "(there is no CPU or PyTorch fallback for the pullback hot path)")
+        _raw = C.CDLL(LIB_PATH)
+    return _raw
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = raw()
+        _declare(_lib)
+        if _lib.pb_backend().decode() != "cuda-sm100a":
+            raise RuntimeError("libpullback_b200.so is not the sm_100a product library")
+    return _lib
+
+
+def _declare(L):
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.pb_backend.restype = C.c_char_p
+    L.pb_backend.argtypes = []
+    L.pb_last_error.restype = C.c_char_p
+    L.pb_last_error.argtypes = [vp]
+    L.pb_create.argtypes = [C.POINTER(PbUnetCfg), C.POINTER(vp)]
+    L.pb_destroy.argtypes = [vp]
+    L.pb_destroy.restype = None
+    L.pb_plan.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.POINTER(PbSizes)]
+    L.pb_bind_weights.argtypes = [vp, C.POINTER(PbTensorDesc), i32, vp, vp]
+    L.pb_set_point.argtypes = [vp, vp, f32, vp, vp, vp, vp, vp]
+    L.pb_jvp.argtypes = [vp, vp, i32, vp, vp]
+    L.pb_vjp.argtypes = [vp, vp, i32, vp, vp]
+    L.pb_orthonormalize.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, vp]
+    L.pb_pullback.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp, C.POINTER(PbIterInfo), vp]
+    L.pb_pullback_host.argtypes = [vp, vp, f32, vp, vp, i32, i32, i32, f32, vp, vp, vp,
+                                   C.POINTER(PbIterInfo), vp]
+    L.pb_kernel_launches.argtypes = [vp]
+    L.pb_kernel_launches.restype = C.c_int64
+    L.pb_weight_count.argtypes = [vp]
+    L.pb_weight_count.restype = C.c_int
+    L.pb_weight_info.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(i32), C.POINTER(i64)]
+    L.pb_weight_info.restype = C.c_int
+    L.pb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    L.pb_set_option.restype = C.c_int
+    for name in ("pb_create", "pb_plan", "pb_bind_weights", "pb_set_point", "pb_jvp", "pb_vjp",
+                 "pb_orthonormalize", "pb_pullback", "pb_pullback_host"):
+        getattr(L, name).restype = C.c_int
+
+
+def leaf(name):
+    """A pbk_* leaf kernel entry (tests only): returns an error string or None."""
+    f = getattr(raw(), name)
+    f.restype = C.c_char_p
+    return f

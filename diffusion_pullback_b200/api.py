@@ -1,0 +1,114 @@
+"""Drop-in replacements for the reference's monkey-patched U-Net methods
+(`/root/reference/src/utils/utils.py`): same names, same positional/keyword signatures, same return
+contract, bindable with `types.MethodType` exactly like `utils.py:103-104`, `:326`, `:333` do:
+
+    unet.get_h                     <- get_h / get_h_uncond          (utils.py:438-527 / :114-163)
+    unet.local_encoder_pullback_zt <- local_encoder_pullback_zt     (utils.py:722-816)
+    unet.local_encoder_pullback_xt <- local_encoder_pullback_xt     (utils.py:165-249)
+
+`patch_unet(unet)` performs the three bindings.  All arithmetic runs in libpullback_b200.so (sm_100a
+CUDA); there is no PyTorch / CPU fallback -- a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import time
+import types
+
+import torch
+
+from .engine import PullbackEngine, unet_config
+
+
+def _engine_for(unet, sample, op, block_idx, k, ctx_len) -> PullbackEngine:
+    if sample.device.type != "cuda":
+        raise RuntimeError("diffusion_pullback_b200 runs on a CUDA (sm_100a) device only; got a "
+                           f"{sample.device.type} tensor (no CPU fallback exists)")
+    cache = unet.__dict__.setdefault("_pb200_engines", {})
+    key = (sample.device.index, sample.shape[2], sample.shape[3], op, block_idx, ctx_len)
+    eng = cache.get(key)
+    if eng is None or eng.k_max < k:
+        cfg = unet_config(unet)
+        if sample.shape[1] != cfg["in_channels"]:
+            raise ValueError("sample has the wrong number of channels")
+        eng = PullbackEngine(cfg, sample.shape[2], sample.shape[3], op, block_idx, max(k, 1), ctx_len, sample.device)
+        eng.bind(unet.state_dict())
+        cache[key] = eng
+    return eng
+
+
+def refresh_weights(unet):
+    """Re-pack weights after the module's parameters changed (engines cache a packed copy)."""
+    for eng in unet.__dict__.get("_pb200_engines", {}).values():
+        eng.bind(unet.state_dict())
+
+
+def _timestep(t):
+    return float(t.reshape(-1)[0]) if torch.is_tensor(t) else float(t)
+
+
+def get_h(self, sample=None, timestep=None, encoder_hidden_states=None, op=None, block_idx=None, verbose=False):
+    """`utils.py:438-527`: the truncated U-Net forward; batch 1 (the pullback's use of it)."""
+    if sample.shape[0] != 1:
+        raise ValueError("diffusion_pullback_b200.get_h evaluates one latent at a time")
+    ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+    eng = _engine_for(self, sample, op, block_idx, 1, ctx_len)
+    return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
+
+
+def get_h_uncond(self, x=None, t=None, op=None, block_idx=None, verbose=False):
+    """`utils.py:114-163`; only ('mid', 0) is valid, anything else raises ValueError like the reference."""
+    if x.shape[0] != 1:
+        raise ValueError("diffusion_pullback_b200.get_h evaluates one latent at a time")
+    eng = _engine_for(self, x, op, block_idx, 1, 0)
+    return eng.set_point(x, _timestep(t), None, want_h=True)
+
+
+def _pullback(self, sample, timestep, ctx, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info):
+    time_s = time.time()
+    k = int(pca_rank)
+    ctx_len = ctx.shape[1] if ctx is not None else 0
+    eng = _engine_for(self, sample, op, block_idx, k, ctx_len)
+    n_in = sample[0].numel()
+    if v0 is None:
+        # identical RNG consumption and V0 to the reference (utils.py:750-752 / :193-195)
+        vT = torch.randn(n_in, k, device=sample.device, dtype=torch.float)
+        vT, _ = torch.linalg.qr(vT)
+        v0 = vT.T.contiguous()
+    eng.set_point(sample, _timestep(timestep), ctx)
+    u, s, vT, info = eng.pullback(v0, min_iter, max_iter, convergence_threshold)
+    print(f"power method : {info.iters_done - 1}-th step convergence : ", info.last_dist)
+    if info.converged:
+        print("reach convergence threshold : ", info.last_dist)
+    print("power method runtime ==", time.time() - time_s)
+    u = u.T                                    # [n_out, k] view, like the reference's `.view(k, n_out).T`
+    if return_info:
+        return u, s, vT, dict(iters_done=info.iters_done, converged=bool(info.converged), last_dist=info.last_dist)
+    return u, s, vT
+
+
+@torch.no_grad()
+def local_encoder_pullback_zt(self, sample, timestep, encoder_hidden_states=None, op=None, block_idx=None,
+                              pca_rank=50, chunk_size=25, min_iter=10, max_iter=100, convergence_threshold=1e-3,
+                              v0=None, return_info=False):
+    """`utils.py:722-816`.  `chunk_size` bounds memory in the reference and does not change results; the
+    k tangents always ride the batch axis of one pass here.  Returns (u [n_out,k], s [k], vT [k,n_in])."""
+    return _pullback(self, sample, timestep, encoder_hidden_states, op, block_idx, pca_rank, min_iter, max_iter,
+                     convergence_threshold, v0, return_info)
+
+
+@torch.no_grad()
+def local_encoder_pullback_xt(self, x, t, op=None, block_idx=None, pca_rank=50, chunk_size=25, min_iter=10, max_iter=100,
+                              convergence_threshold=1e-3, v0=None, return_info=False):
+    """`utils.py:165-249` (unconditional `UNet2DModel`)."""
+    return _pullback(self, x, t, None, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info)
+
+
+def patch_unet(unet):
+    """The monkey-patch of `utils.py:103-104` (uncond) / `:326`, `:333` (Stable Diffusion)."""
+    if hasattr(unet, "up_blocks") and unet_config(unet)["kind"] == 0:
+        unet.get_h = types.MethodType(get_h, unet)
+        unet.local_encoder_pullback_zt = types.MethodType(local_encoder_pullback_zt, unet)
+    else:
+        unet.get_h = types.MethodType(get_h_uncond, unet)
+        unet.local_encoder_pullback_xt = types.MethodType(local_encoder_pullback_xt, unet)
+    return unet

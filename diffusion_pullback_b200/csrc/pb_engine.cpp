@@ -1,0 +1,1049 @@
+// pb_engine -- host side of the pullback hot path behind the C ABI of include/pullback_b200.h.
+//
+// The truncated U-Net x_t -> h of the reference's get_h / get_h_uncond (src/utils/utils.py:438-527,
+// :114-163; module semantics: diffusers 0.11.0) is planned ONCE into a flat op list over NHWC
+// activations.  Three interpreters walk that list:
+//   primal : runs the network at (x_t, t, ctx) and caches the linearisation (activations, norm statistics,
+//            attention probabilities and the transposed operand copies the tcgen05 GEMM needs)
+//   jvp    : pushes k tangents (packed on the batch axis) forward   U = J V     (replaces utils.py:766-775)
+//   vjp    : pulls  k cotangents backward through the transposed ops W = U^T J  (replaces utils.py:790-797)
+// and pb_pullback() runs the reference's subspace iteration (utils.py:756-808) on top of them, one CUDA
+// graph replay per iteration, re-orthonormalising on the device (pb_ortho.cu).
+//
+// This file is device-agnostic: it only sequences the leaf kernels declared in pb_kernels.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "pb_kernels.h"
+#include "pullback_b200.h"
+
+#define PB_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+inline int round4(int v) { return (v + 3) / 4 * 4; }
+
+// ---------------------------------------------------------------------------------------------
+// plan data structures
+// ---------------------------------------------------------------------------------------------
+struct Val {                 // one activation tensor, [rows][C] per image (NHWC / token layout)
+  long rows; int C;
+  size_t p_off;              // primal copy in the primal cache (bytes)
+  size_t t_off;              // k_max tangents / cotangents in the workspace (bytes)
+  bool ginit;                // vjp bookkeeping: cotangent buffer already holds a contribution
+};
+
+enum WKind { WK_VEC, WK_RAW, WK_LIN, WK_CONV3, WK_CONV3_S2 };
+struct WSpec {
+  WKind kind;
+  std::vector<std::string> names;   // sources, concatenated along the output dimension
+  int out, in;                      // total rows, columns (conv: Co, Ci)
+  size_t fwd_off, bwd_off;          // bytes in the packed region
+};
+
+enum OpKind { OP_IN, OP_CONV_DIRECT, OP_GN, OP_LN, OP_GEMM, OP_CONCAT, OP_IM2COL, OP_UPSAMPLE, OP_GEGLU, OP_ATTN, OP_OUT };
+struct Op {
+  OpKind kind;
+  int x = -1, x2 = -1, y = -1, res = -1;
+  int H = 0, W = 0;
+  int w = -1, bias = -1, gamma = -1, beta = -1, temb_w = -1, temb_b = -1;
+  size_t bias_eff_off = 0, mean_off = 0, rstd_off = 0;
+  float eps = 0.f; int silu = 0, groups = 0;
+  int conv = 0;                     // OP_GEMM: 1 = 3x3 / s1 / p1 implicit GEMM
+  int pad_lo = 0, Ho = 0, Wo = 0;   // OP_IM2COL
+  // OP_ATTN
+  int heads = 0, d = 0, cross = 0, Nq = 0, Nk = 0, ldk = 0, ldq = 0, kv = -1;
+  float scale = 0.f;
+  size_t P_off = 0, Pt_off = 0, Qt_off = 0, Kt_off = 0, Vt_off = 0;
+};
+
+}  // namespace
+
+struct pb_handle {
+  pb_unet_cfg cfg{};
+  bool planned = false, bound = false, point = false;
+  int H = 0, W = 0, op = 0, block_idx = 0, kmax = 0, ctx_len = 0;
+  std::vector<Val> vals;
+  std::vector<WSpec> wspecs;
+  std::vector<Op> ops;
+  std::map<std::string, int> windex;
+  pb_sizes sizes{};
+  size_t cache_top = 0, work_top = 0, packed_top = 0;
+  // fixed primal-cache / workspace slots (byte offsets)
+  size_t c_temb = 0, c_sin = 0, c_e1 = 0, c_ctx = 0;
+  size_t w_s1 = 0, w_s2 = 0, w_s3 = 0, w_delta = 0, w_gn = 0;
+  size_t w_V = 0, w_Vprev = 0, w_W = 0, w_U = 0, w_G = 0, w_M = 0, w_R = 0, w_sv = 0, w_met = 0, w_x = 0;
+  size_t n_s1 = 0, n_s2 = 0, n_s3 = 0, n_delta = 0, n_gn = 0;   // floats per tangent
+  char* packed = nullptr; char* cache = nullptr; char* work = nullptr;
+  int in_val = -1, out_val = -1;
+  long n_in = 0, n_out = 0;
+  // numerics policy (DESIGN.md "precision"): producers RNA-round GEMM operands to TF32 (rnd_*); GEMMs run one TF32
+  // pass (0), error-compensated 3xTF32 (1) or split-weight 2xTF32 (2)
+  int rnd_p = 1, rnd_t = 1, rnd_w = 1;      // primal activations / tangents / packed weights
+  int prec_p = 0, prec_t = 0, prec_a = 0;   // primal GEMMs / tangent weight GEMMs / tangent attention GEMMs
+  int rnd = 1;                              // rounding flag of the pass being interpreted
+  std::string err;
+  long launches = 0;
+  // CUDA graph of one iteration (jvp + vjp + orthonormalise)
+  void* graph = nullptr; int graph_k = 0; float graph_tol = 0.f; int use_graph = 1; bool warm = false;
+  const float* graph_u = nullptr; const float* graph_s = nullptr; long graph_nodes = 0;
+
+  float* P(int v) const { return reinterpret_cast<float*>(cache + vals[v].p_off); }
+  float* T(int v) const { return reinterpret_cast<float*>(work + vals[v].t_off); }
+  float* CP(size_t off) const { return reinterpret_cast<float*>(cache + off); }
+  float* WP(size_t off) const { return reinterpret_cast<float*>(work + off); }
+  float* Wf(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].fwd_off); }
+  float* Wb(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].bwd_off); }
+};
+
+namespace {
+
+int fail(pb_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// planner
+// ---------------------------------------------------------------------------------------------
+struct Planner {
+  pb_handle* h;
+  std::string error;
+
+  size_t cache_alloc(size_t floats) { size_t o = h->cache_top; h->cache_top = align_up(o + floats * 4); return o; }
+  size_t work_alloc(size_t floats) { size_t o = h->work_top; h->work_top = align_up(o + floats * 4); return o; }
+
+  int val(long rows, int C) {
+    Val v{rows, C, 0, 0, false};
+    v.p_off = cache_alloc((size_t)rows * C);
+    v.t_off = work_alloc((size_t)rows * C * h->kmax);
+    h->vals.push_back(v);
+    return (int)h->vals.size() - 1;
+  }
+  int weight(WKind kind, std::vector<std::string> names, int out, int in) {
+    std::string key = names[0] + "#" + std::to_string((int)kind) + "#" + std::to_string(names.size());
+    auto it = h->windex.find(key);
+    if (it != h->windex.end()) return it->second;
+    WSpec s{kind, std::move(names), out, in, 0, 0};
+    size_t n = 0;
+    switch (kind) {
+      case WK_VEC: n = (size_t)out; break;
+      case WK_RAW: case WK_LIN: n = (size_t)out * in; break;
+      case WK_CONV3: case WK_CONV3_S2: n = (size_t)out * in * 9; break;
+    }
+    s.fwd_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 4);
+    if (kind == WK_LIN || kind == WK_CONV3 || kind == WK_CONV3_S2) {
+      s.bwd_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 4);
+    }
+    h->wspecs.push_back(s);
+    h->windex[key] = (int)h->wspecs.size() - 1;
+    return (int)h->wspecs.size() - 1;
+  }
+  int vec(const std::string& name, int n) { return weight(WK_VEC, {name}, n, 1); }
+
+  Op& push(OpKind k) { h->ops.emplace_back(); h->ops.back().kind = k; return h->ops.back(); }
+
+  int gn(int x, const std::string& p, float eps, int silu) {
+    const Val& vx = h->vals[x];
+    const int G = h->cfg.norm_num_groups;
+    if (vx.C % G || vx.C % 4) { error = "GroupNorm channels must divide into groups and be a multiple of 4"; return -1; }
+    int y = val(vx.rows, vx.C);
+    Op& o = push(OP_GN);
+    o.x = x; o.y = y; o.eps = eps; o.silu = silu; o.groups = G;
+    o.gamma = vec(p + ".weight", h->vals[x].C); o.beta = vec(p + ".bias", h->vals[x].C);
+    o.mean_off = cache_alloc(G); o.rstd_off = cache_alloc(G);
+    h->n_gn = std::max(h->n_gn, (size_t)(h->vals[x].C + G) * 2);
+    return y;
+  }
+  int ln(int x, const std::string& p) {
+    int y = val(h->vals[x].rows, h->vals[x].C);
+    Op& o = push(OP_LN);
+    o.x = x; o.y = y; o.eps = 1e-5f;
+    o.gamma = vec(p + ".weight", h->vals[x].C); o.beta = vec(p + ".bias", h->vals[x].C);
+    o.mean_off = cache_alloc(h->vals[x].rows); o.rstd_off = cache_alloc(h->vals[x].rows);
+    return y;
+  }
+  // y = x W^T (+ bias) (+ res);  names: weight sources concatenated along the output dimension
+  int linear(int x, std::vector<std::string> wnames, std::vector<std::string> bnames, int out, int res = -1) {
+    const int in = h->vals[x].C;
+    int y = val(h->vals[x].rows, out);
+    Op& o = push(OP_GEMM);
+    o.x = x; o.y = y; o.res = res;
+    o.w = weight(WK_LIN, std::move(wnames), out, in);
+    if (!bnames.empty()) o.bias = weight(WK_VEC, std::move(bnames), out, 1);
+    return y;
+  }
+  int conv3(int x, const std::string& p, int out, int H, int W, int res = -1, const std::string& temb = "") {
+    const int in = h->vals[x].C;
+    if (in % 32) { error = "3x3 conv input channels must be a multiple of 32 (" + p + ")"; return -1; }
+    int y = val(h->vals[x].rows, out);
+    Op& o = push(OP_GEMM);
+    o.x = x; o.y = y; o.res = res; o.conv = 1; o.H = H; o.W = W;
+    o.w = weight(WK_CONV3, {p + ".weight"}, out, in);
+    o.bias = vec(p + ".bias", out);
+    if (!temb.empty()) {
+      const int ted = h->cfg.block_out_channels[0] * 4;
+      o.temb_w = weight(WK_RAW, {temb + ".weight"}, out, ted);
+      o.temb_b = vec(temb + ".bias", out);
+      o.bias_eff_off = cache_alloc(out);
+    }
+    return y;
+  }
+  int resnet(int x, int Cout, int H, int W, const std::string& p) {
+    const int Cin = h->vals[x].C;
+    int a = gn(x, p + ".norm1", h->cfg.norm_eps, 1); if (a < 0) return -1;
+    int h1 = conv3(a, p + ".conv1", Cout, H, W, -1, p + ".time_emb_proj"); if (h1 < 0) return -1;
+    int b = gn(h1, p + ".norm2", h->cfg.norm_eps, 1); if (b < 0) return -1;
+    int sc = x;
+    if (Cin != Cout) sc = linear(x, {p + ".conv_shortcut.weight"}, {p + ".conv_shortcut.bias"}, Cout);
+    return conv3(b, p + ".conv2", Cout, H, W, sc);
+  }
+  // attention core; self: qkv is the fused [N][3C] projection; cross: q is [N][C], kv the cached [Nk][2C] text projection
+  int attn(int q, int heads, int C, int cross, int Nk, int kv) {
+    const long N = h->vals[q].rows;
+    int y = val(N, C);
+    Op& o = push(OP_ATTN);
+    o.x = q; o.y = y; o.heads = heads; o.d = C / heads; o.cross = cross; o.Nq = (int)N; o.Nk = Nk; o.kv = kv;
+    o.ldk = round4(Nk); o.ldq = round4((int)N);
+    o.scale = 1.0f / std::sqrt((float)o.d);
+    if (C % heads || o.d % 4) { error = "attention head dim must be a multiple of 4"; return -1; }
+    o.P_off = cache_alloc((size_t)heads * N * o.ldk);
+    o.Vt_off = cache_alloc((size_t)C * o.ldk);
+    o.Kt_off = cache_alloc((size_t)C * o.ldk);
+    if (!cross) {
+      o.Pt_off = cache_alloc((size_t)heads * Nk * o.ldq);
+      o.Qt_off = cache_alloc((size_t)C * o.ldq);
+    }
+    h->n_s1 = std::max(h->n_s1, (size_t)heads * N * o.ldk);
+    if (!cross) h->n_s2 = std::max(h->n_s2, (size_t)heads * Nk * o.ldq);
+    h->n_s3 = std::max(h->n_s3, (size_t)C * std::max(o.ldk, o.ldq));
+    h->n_delta = std::max(h->n_delta, (size_t)heads * N);
+    return y;
+  }
+  int transformer(int x, int heads, int H, int W, const std::string& p) {
+    const int C = h->vals[x].C;
+    const std::string tb = p + ".transformer_blocks.0";
+    int n0 = gn(x, p + ".norm", 1e-6f, 0); if (n0 < 0) return -1;
+    int t0 = linear(n0, {p + ".proj_in.weight"}, {p + ".proj_in.bias"}, C);
+    int l1 = ln(t0, tb + ".norm1");
+    int qkv = linear(l1, {tb + ".attn1.to_q.weight", tb + ".attn1.to_k.weight", tb + ".attn1.to_v.weight"}, {}, 3 * C);
+    int o1 = attn(qkv, heads, C, 0, H * W, -1); if (o1 < 0) return -1;
+    int t1 = linear(o1, {tb + ".attn1.to_out.0.weight"}, {tb + ".attn1.to_out.0.bias"}, C, t0);
+    int l2 = ln(t1, tb + ".norm2");
+    int q2 = linear(l2, {tb + ".attn2.to_q.weight"}, {}, C);
+    // text keys / values: a primal-only GEMM on ctx, recorded as a weight pair and a cache slot
+    int kvw = weight(WK_LIN, {tb + ".attn2.to_k.weight", tb + ".attn2.to_v.weight"}, 2 * C, h->cfg.cross_attention_dim);
+    size_t kv_off = cache_alloc((size_t)h->ctx_len * 2 * C);
+    int o2 = attn(q2, heads, C, 1, h->ctx_len, kvw); if (o2 < 0) return -1;
+    h->ops.back().bias_eff_off = kv_off;     // OP_ATTN (cross): location of the [Nk][2C] text projection
+    int t2 = linear(o2, {tb + ".attn2.to_out.0.weight"}, {tb + ".attn2.to_out.0.bias"}, C, t1);
+    int l3 = ln(t2, tb + ".norm3");
+    int f1 = linear(l3, {tb + ".ff.net.0.proj.weight"}, {tb + ".ff.net.0.proj.bias"}, 8 * C);
+    int gg = val(h->vals[f1].rows, 4 * C);
+    { Op& o = push(OP_GEGLU); o.x = f1; o.y = gg; }
+    int t3 = linear(gg, {tb + ".ff.net.2.weight"}, {tb + ".ff.net.2.bias"}, C, t2);
+    return linear(t3, {p + ".proj_out.weight"}, {p + ".proj_out.bias"}, C, x);
+  }
+  // diffusers 0.11.0 AttentionBlock (UNet2DModel)
+  int attn_block(int x, int heads, int H, int W, const std::string& p) {
+    const int C = h->vals[x].C;
+    int n0 = gn(x, p + ".group_norm", h->cfg.norm_eps, 0); if (n0 < 0) return -1;
+    int qkv = linear(n0, {p + ".query.weight", p + ".key.weight", p + ".value.weight"},
+                     {p + ".query.bias", p + ".key.bias", p + ".value.bias"}, 3 * C);
+    int o1 = attn(qkv, heads, C, 0, H * W, -1); if (o1 < 0) return -1;
+    return linear(o1, {p + ".proj_attn.weight"}, {p + ".proj_attn.bias"}, C, x);
+  }
+  int downsample(int x, int H, int W, const std::string& p) {
+    const int C = h->vals[x].C;
+    const int pad = h->cfg.downsample_padding ? 1 : 0;
+    const int Ho = pad ? (H + 2 - 3) / 2 + 1 : (H + 1 - 3) / 2 + 1;
+    const int Wo = pad ? (W + 2 - 3) / 2 + 1 : (W + 1 - 3) / 2 + 1;
+    int col = val((long)Ho * Wo, 9 * C);
+    { Op& o = push(OP_IM2COL); o.x = x; o.y = col; o.H = H; o.W = W; o.Ho = Ho; o.Wo = Wo; o.pad_lo = pad; }
+    int y = val((long)Ho * Wo, C);
+    Op& o = push(OP_GEMM);
+    o.x = col; o.y = y;
+    o.w = weight(WK_CONV3_S2, {p + ".conv.weight"}, C, C);
+    o.bias = vec(p + ".conv.bias", C);
+    return y;
+  }
+  int upsample(int x, int H, int W, const std::string& p) {
+    const int C = h->vals[x].C;
+    int up = val(4L * H * W, C);
+    { Op& o = push(OP_UPSAMPLE); o.x = x; o.y = up; o.H = H; o.W = W; }
+    return conv3(up, p + ".conv", C, 2 * H, 2 * W);
+  }
+  int concat(int a, int b) {
+    int y = val(h->vals[a].rows, h->vals[a].C + h->vals[b].C);
+    Op& o = push(OP_CONCAT); o.x = a; o.x2 = b; o.y = y;
+    return y;
+  }
+
+  bool build() {
+    const pb_unet_cfg& c = h->cfg;
+    const int L = c.n_levels;
+    int H = h->H, W = h->W;
+    const bool cond = c.kind == PB_UNET_COND;
+    int x0 = val((long)H * W, c.in_channels);
+    { Op& o = push(OP_IN); o.y = x0; o.H = H; o.W = W; }
+    h->in_val = x0;
+    int x = val((long)H * W, c.block_out_channels[0]);
+    {
+      Op& o = push(OP_CONV_DIRECT);
+      o.x = x0; o.y = x; o.H = H; o.W = W;
+      o.w = weight(WK_CONV3, {"conv_in.weight"}, c.block_out_channels[0], c.in_channels);
+      o.bias = vec("conv_in.bias", c.block_out_channels[0]);
+    }
+    const int ted = c.block_out_channels[0] * 4;
+    weight(WK_RAW, {"time_embedding.linear_1.weight"}, ted, c.block_out_channels[0]);
+    vec("time_embedding.linear_1.bias", ted);
+    weight(WK_RAW, {"time_embedding.linear_2.weight"}, ted, ted);
+    vec("time_embedding.linear_2.bias", ted);
+    struct Skip { int v, H, W; };
+    std::vector<Skip> skips{{x, H, W}};
+    for (int i = 0; i < L; ++i) {
+      const std::string bp = "down_blocks." + std::to_string(i);
+      for (int j = 0; j < c.layers_per_block; ++j) {
+        x = resnet(x, c.block_out_channels[i], H, W, bp + ".resnets." + std::to_string(j));
+        if (x < 0) return false;
+        if (c.down_has_attn[i]) {
+          const std::string ap = bp + ".attentions." + std::to_string(j);
+          x = cond ? transformer(x, c.heads[i], H, W, ap) : attn_block(x, c.heads[i], H, W, ap);
+          if (x < 0) return false;
+        }
+        skips.push_back({x, H, W});
+      }
+      if (i != L - 1) {
+        x = downsample(x, H, W, bp + ".downsamplers.0");
+        H = h->ops[h->ops.size() - 2].Ho;        // the OP_IM2COL emitted just before the GEMM
+        W = h->ops[h->ops.size() - 2].Wo;
+        skips.push_back({x, H, W});
+      }
+    }
+    const int Cm = c.block_out_channels[L - 1];
+    x = resnet(x, Cm, H, W, "mid_block.resnets.0"); if (x < 0) return false;
+    x = cond ? transformer(x, c.heads[L - 1], H, W, "mid_block.attentions.0")
+             : attn_block(x, c.heads[L - 1], H, W, "mid_block.attentions.0");
+    if (x < 0) return false;
+    x = resnet(x, Cm, H, W, "mid_block.resnets.1"); if (x < 0) return false;
+    if (h->op == PB_OP_UP) {
+      if (!cond) { error = "(op, block_idx) is not valid: get_h_uncond supports ('mid', 0) only"; return false; }
+      for (int i = 0; i <= h->block_idx; ++i) {
+        const std::string bp = "up_blocks." + std::to_string(i);
+        const int out_ch = c.block_out_channels[L - 1 - i];
+        for (int j = 0; j <= c.layers_per_block; ++j) {
+          Skip s = skips.back(); skips.pop_back();
+          if (s.H != H || s.W != W) { error = "internal: skip geometry mismatch"; return false; }
+          int cat = concat(x, s.v);
+          x = resnet(cat, out_ch, H, W, bp + ".resnets." + std::to_string(j)); if (x < 0) return false;
+          if (c.up_has_attn[i]) {
+            x = transformer(x, c.heads[L - 1 - i], H, W, bp + ".attentions." + std::to_string(j));
+            if (x < 0) return false;
+          }
+        }
+        if (i != L - 1) { x = upsample(x, H, W, bp + ".upsamplers.0"); if (x < 0) return false; H *= 2; W *= 2; }
+      }
+    }
+    { Op& o = push(OP_OUT); o.x = x; o.H = H; o.W = W; }
+    h->out_val = x;
+    h->sizes.out_channels = h->vals[x].C; h->sizes.out_h = H; h->sizes.out_w = W;
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// interpreters
+// ---------------------------------------------------------------------------------------------
+#define CK(call)                                                      \
+  do {                                                                \
+    const char* e__ = (call);                                         \
+    ++h->launches;                                                    \
+    if (e__) return fail(h, PB_ECUDA, std::string(#call ": ") + e__); \
+  } while (0)
+
+PbGemm plain_gemm(const float* A, long lda, long M, const float* B, long ldb, int N, int K, float* D, long ldd) {
+  PbGemm g = pb_gemm_init();
+  g.M = (int)M; g.N = N;
+  g.seg[0].A = A; g.seg[0].lda = lda; g.seg[0].B = B; g.seg[0].ldb = ldb; g.seg[0].K = K;
+  g.D = D; g.ldd = ldd;
+  return g;
+}
+
+// y = x (*) W (+ bias) (+ res), nb images; mode 0 primal, 1 jvp
+int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
+  const Val& vx = h->vals[o.x]; const Val& vy = h->vals[o.y];
+  const float* A = primal ? h->P(o.x) : h->T(o.x);
+  float* D = primal ? h->P(o.y) : h->T(o.y);
+  PbGemm g = plain_gemm(A, vx.C, vx.rows * nb, h->Wf(o.w), o.conv ? 9L * vx.C : vx.C, vy.C, vx.C, D, vy.C);
+  if (o.conv) { g.conv = 1; g.H = o.H; g.W = o.W; g.nb = nb; }
+  if (primal && o.bias >= 0) g.bias = o.temb_w >= 0 ? h->CP(o.bias_eff_off) : h->Wf(o.bias);
+  if (o.res >= 0) { g.R = primal ? h->P(o.res) : h->T(o.res); g.ldr = vy.C; g.beta = 1.f; }
+  g.round_tf32 = h->rnd;
+  g.precise = primal ? h->prec_p : h->prec_t;
+  CK(pbk_gemm(&g, st));
+  return PB_OK;
+}
+// gx (+)= gy (*) W^T ; gres (+)= gy
+int run_gemm_bwd(pb_handle* h, const Op& o, int nb, pb_stream st) {
+  Val& vx = h->vals[o.x]; const Val& vy = h->vals[o.y];
+  PbGemm g = plain_gemm(h->T(o.y), vy.C, vy.rows * nb, h->Wb(o.w), o.conv ? 9L * vy.C : vy.C, vx.C, vy.C, h->T(o.x), vx.C);
+  if (o.conv) { g.conv = 1; g.H = o.H; g.W = o.W; g.nb = nb; }
+  if (vx.ginit) { g.R = h->T(o.x); g.ldr = vx.C; g.beta = 1.f; }
+  g.round_tf32 = h->rnd;
+  g.precise = h->prec_t;
+  CK(pbk_gemm(&g, st));
+  vx.ginit = true;
+  if (o.res >= 0) {
+    Val& vr = h->vals[o.res];
+    CK(pbk_copy2d(h->T(o.res), vr.C, h->T(o.y), vy.C, vy.rows * nb, vy.C, vr.ginit ? 1.f : 0.f, h->rnd, st));
+    vr.ginit = true;
+  }
+  return PB_OK;
+}
+
+struct AttnPtrs { const float *Q, *K, *V; long ld; };   // primal operands, row stride
+
+int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
+  const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
+  const float *Q, *K, *V; long ldq_, ldkv;
+  if (o.cross) {
+    // text keys / values: kv = ctx [Nk][ctx_dim] x Wkv^T -> [Nk][2C]
+    float* kv = h->CP(o.bias_eff_off);
+    PbGemm g = plain_gemm(ctx, h->cfg.cross_attention_dim, Nk, h->Wf(o.kv), h->cfg.cross_attention_dim, 2 * C,
+                          h->cfg.cross_attention_dim, kv, 2 * C);
+    g.round_tf32 = h->rnd;
+    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+    Q = h->P(o.x); ldq_ = C; K = kv; V = kv + C; ldkv = 2 * C;
+  } else {
+    Q = h->P(o.x); K = Q + C; V = Q + 2 * C; ldq_ = ldkv = 3 * C;
+  }
+  float* P = h->CP(o.P_off);
+  {
+    PbGemm g = plain_gemm(Q, ldq_, N, K, ldkv, Nk, d, P, ldk);
+    g.seg[0].sAh = d; g.seg[0].sBh = d; g.sDh = (long)N * ldk; g.nh = hd; g.alpha = o.scale;
+    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+  }
+  CK(pbk_softmax_fwd(P, (long)hd * N, Nk, ldk, h->rnd, st));
+  float* Vt = h->CP(o.Vt_off); float* Kt = h->CP(o.Kt_off);
+  CK(pbk_transpose(Vt, ldk, 0, (long)d * ldk, V, ldkv, 0, d, 1, hd, Nk, d, 0.f, h->rnd, st));
+  CK(pbk_transpose(Kt, ldk, 0, (long)d * ldk, K, ldkv, 0, d, 1, hd, Nk, d, 0.f, h->rnd, st));
+  if (!o.cross) {
+    CK(pbk_transpose(h->CP(o.Qt_off), o.ldq, 0, (long)d * o.ldq, Q, ldq_, 0, d, 1, hd, N, d, 0.f, h->rnd, st));
+    CK(pbk_transpose(h->CP(o.Pt_off), o.ldq, 0, (long)Nk * o.ldq, P, ldk, 0, (long)N * ldk, 1, hd, N, Nk, 0.f, h->rnd, st));
+  }
+  {
+    PbGemm g = plain_gemm(P, ldk, N, Vt, ldk, d, Nk, h->P(o.y), C);
+    g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk; g.sDh = d; g.nh = hd; g.round_tf32 = h->rnd;
+    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+  }
+  return PB_OK;
+}
+
+int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
+  const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
+  float* P = h->CP(o.P_off); float* Vt = h->CP(o.Vt_off);
+  float* dS = h->WP(h->w_s1);
+  const long sS = (long)hd * N * ldk;
+  if (o.cross) {
+    const float* kv = h->CP(o.bias_eff_off);
+    PbGemm g = plain_gemm(h->T(o.x), C, N, kv, 2 * C, Nk, d, dS, ldk);
+    g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
+    g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  } else {
+    const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
+    PbGemm g = plain_gemm(dqkv, 3 * C, N, qkv + C, 3 * C, Nk, d, dS, ldk);       // dQ K^T
+    g.seg[0].sAb = (long)N * 3 * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
+    g.nseg = 2;                                                                    // + Q dK^T
+    g.seg[1].A = qkv; g.seg[1].lda = 3 * C; g.seg[1].sAb = 0; g.seg[1].sAh = d;
+    g.seg[1].B = dqkv + C; g.seg[1].ldb = 3 * C; g.seg[1].sBb = (long)N * 3 * C; g.seg[1].sBh = d; g.seg[1].K = d;
+    g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  CK(pbk_softmax_lin(P, (long)hd * N, dS, nb, Nk, ldk, h->rnd, st));
+  PbGemm g = plain_gemm(dS, ldk, N, Vt, ldk, d, Nk, h->T(o.y), C);                // dP V
+  g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
+  g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
+  if (!o.cross) {                                                                  // + P dV
+    float* dVt = h->WP(h->w_s3);
+    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, h->T(o.x) + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f,
+                     h->rnd, st));
+    g.nseg = 2;
+    g.seg[1].A = P; g.seg[1].lda = ldk; g.seg[1].sAb = 0; g.seg[1].sAh = (long)N * ldk;
+    g.seg[1].B = dVt; g.seg[1].ldb = ldk; g.seg[1].sBb = (long)C * ldk; g.seg[1].sBh = (long)d * ldk; g.seg[1].K = Nk;
+  }
+  g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  return PB_OK;
+}
+
+int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
+  const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk, ldq = o.ldq;
+  float* P = h->CP(o.P_off); float* Kt = h->CP(o.Kt_off);
+  const float* gO = h->T(o.y);
+  float* gS = h->WP(h->w_s1);
+  const long sS = (long)hd * N * ldk;
+  const float* V; long ldkv;
+  if (o.cross) { V = h->CP(o.bias_eff_off) + C; ldkv = 2 * C; } else { V = h->P(o.x) + 2 * C; ldkv = 3 * C; }
+  {                                                                                // dP = gO V^T
+    PbGemm g = plain_gemm(gO, C, N, V, ldkv, Nk, d, gS, ldk);
+    g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
+    g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  CK(pbk_softmax_lin(P, (long)hd * N, gS, nb, Nk, ldk, h->rnd, st));              // gS = P o (dP - rowsum(P o dP))
+  const long ldx = o.cross ? C : 3 * C;
+  float* gx = h->T(o.x);
+  {                                                                                // gQ = scale gS K
+    PbGemm g = plain_gemm(gS, ldk, N, Kt, ldk, d, Nk, gx, ldx);
+    g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  h->vals[o.x].ginit = true;
+  if (o.cross) return PB_OK;
+  // keys / values need the query index contracted: work on the transposed score matrix
+  float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
+  float* gSt = h->WP(h->w_s2); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
+  const long sSt = (long)hd * Nk * ldq;
+  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));
+  {                                                                                // dP^T = V gO^T
+    PbGemm g = plain_gemm(V, ldkv, Nk, gO, C, N, d, gSt, ldq);
+    g.seg[0].sAh = d; g.seg[0].sBb = (long)N * C; g.seg[0].sBh = d;
+    g.sDb = sSt; g.sDh = (long)Nk * ldq; g.nb = nb; g.nh = hd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  CK(pbk_attn_ds(Pt, gSt, delta, 1.f, nb, hd, Nk, N, ldq, 1, h->rnd, st));        // gS^T = P^T o (dP^T - delta_i)
+  {                                                                                // gK = scale gS^T Q
+    PbGemm g = plain_gemm(gSt, ldq, Nk, Qt, ldq, d, N, gx + C, ldx);
+    g.seg[0].sAb = sSt; g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBh = (long)d * ldq;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
+  {                                                                                // gV = P^T gO
+    PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, ldx);
+    g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  }
+  return PB_OK;
+}
+
+int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h_out, pb_stream st) {
+  h->rnd = h->rnd_p;
+  const pb_unet_cfg& c = h->cfg;
+  const int c0 = c.block_out_channels[0], ted = 4 * c0;
+  auto W = [&](const char* name, WKind kind, int n) { return h->Wf(h->windex.at(std::string(name) + "#" + std::to_string((int)kind) + "#" + std::to_string(n))); };
+  CK(pbk_timestep_embedding(t, c0, c.flip_sin_to_cos, c.freq_shift, h->CP(h->c_sin), st));
+  CK(pbk_gemv(W("time_embedding.linear_1.weight", WK_RAW, 1), h->CP(h->c_sin), W("time_embedding.linear_1.bias", WK_VEC, 1), ted, c0,
+              0, 1, h->CP(h->c_e1), st));
+  CK(pbk_gemv(W("time_embedding.linear_2.weight", WK_RAW, 1), h->CP(h->c_e1), W("time_embedding.linear_2.bias", WK_VEC, 1), ted, ted,
+              0, 0, h->CP(h->c_temb), st));
+  const float* ctx_r = nullptr;
+  if (c.kind == PB_UNET_COND) {
+    if (!ctx) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
+    const size_t nctx = (size_t)h->ctx_len * c.cross_attention_dim;
+    if (h->rnd) CK(pbk_round_tf32(h->CP(h->c_ctx), ctx, nctx, st));
+    else CK(pbk_copy(h->CP(h->c_ctx), ctx, nctx * 4, st));
+    ctx_r = h->CP(h->c_ctx);
+  }
+  for (const Op& o : h->ops) {
+    switch (o.kind) {
+      case OP_IN: {
+        const Val& v = h->vals[o.y];
+        CK(pbk_transpose(h->P(o.y), v.C, 0, 0, x, v.rows, 0, 0, 1, 1, v.C, (int)v.rows, 0.f, 0, st));
+        break;
+      }
+      case OP_CONV_DIRECT:
+        CK(pbk_conv3x3_direct(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), h->Wf(o.bias), h->vals[o.y].C, h->P(o.y), 0.f, st));
+        break;
+      case OP_GN: {
+        const Val& v = h->vals[o.x];
+        CK(pbk_gn_stats(h->P(o.x), 1, (int)v.rows, v.C, o.groups, o.eps, h->CP(o.mean_off), h->CP(o.rstd_off), h->WP(h->w_gn), st));
+        CK(pbk_gn_apply(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), 1, (int)v.rows, v.C,
+                        o.groups, o.silu, h->rnd, h->P(o.y), st));
+        break;
+      }
+      case OP_LN: {
+        const Val& v = h->vals[o.x];
+        CK(pbk_ln_fwd(h->P(o.x), v.rows, v.C, h->Wf(o.gamma), h->Wf(o.beta), o.eps, h->P(o.y), h->CP(o.mean_off), h->CP(o.rstd_off),
+                      h->rnd, st));
+        break;
+      }
+      case OP_GEMM: {
+        if (o.temb_w >= 0) {   // bias_eff = conv bias + time_emb_proj(SiLU(temb))
+          const int Co = h->vals[o.y].C;
+          CK(pbk_gemv(h->Wf(o.temb_w), h->CP(h->c_temb), h->Wf(o.temb_b), Co, ted, 1, 0, h->CP(o.bias_eff_off), st));
+          CK(pbk_copy2d(h->CP(o.bias_eff_off), Co, h->Wf(o.bias), Co, 1, Co, 1.f, 0, st));
+        }
+        if (int e = run_gemm_fwd(h, o, 1, true, st)) return e;
+        break;
+      }
+      case OP_CONCAT: {
+        const Val& a = h->vals[o.x]; const Val& b = h->vals[o.x2]; const Val& y = h->vals[o.y];
+        CK(pbk_copy2d(h->P(o.y), y.C, h->P(o.x), a.C, a.rows, a.C, 0.f, 0, st));
+        CK(pbk_copy2d(h->P(o.y) + a.C, y.C, h->P(o.x2), b.C, b.rows, b.C, 0.f, 0, st));
+        break;
+      }
+      case OP_IM2COL:
+        CK(pbk_im2col_s2(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->P(o.y), h->rnd, st));
+        break;
+      case OP_UPSAMPLE:
+        CK(pbk_upsample2x(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, h->P(o.y), h->rnd, st));
+        break;
+      case OP_GEGLU:
+        CK(pbk_geglu_fwd(h->P(o.x), h->vals[o.x].rows, h->vals[o.y].C, h->P(o.y), h->rnd, st));
+        break;
+      case OP_ATTN:
+        if (int e = run_attn_primal(h, o, ctx_r, st)) return e;
+        break;
+      case OP_OUT:
+        if (h_out) {
+          const Val& v = h->vals[o.x];
+          CK(pbk_transpose(h_out, v.rows, 0, 0, h->P(o.x), v.C, 0, 0, 1, 1, (int)v.rows, v.C, 0.f, 0, st));
+        }
+        break;
+    }
+  }
+  return PB_OK;
+}
+
+int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
+  h->rnd = h->rnd_t;
+  for (const Op& o : h->ops) {
+    switch (o.kind) {
+      case OP_IN: {
+        const Val& v = h->vals[o.y];
+        CK(pbk_transpose(h->T(o.y), v.C, v.rows * v.C, 0, V, v.rows, v.rows * v.C, 0, nb, 1, v.C, (int)v.rows, 0.f, 0, st));
+        break;
+      }
+      case OP_CONV_DIRECT:
+        CK(pbk_conv3x3_direct(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), nullptr, h->vals[o.y].C, h->T(o.y), 0.f, st));
+        break;
+      case OP_GN: {
+        const Val& v = h->vals[o.x];
+        CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
+                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->rnd, h->WP(h->w_gn), st));
+        break;
+      }
+      case OP_LN: {
+        const Val& v = h->vals[o.x];
+        CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.x), nb, 0, h->T(o.y), 0.f,
+                      h->rnd, st));
+        break;
+      }
+      case OP_GEMM:
+        if (int e = run_gemm_fwd(h, o, nb, false, st)) return e;
+        break;
+      case OP_CONCAT: {
+        const Val& a = h->vals[o.x]; const Val& b = h->vals[o.x2]; const Val& y = h->vals[o.y];
+        CK(pbk_copy2d(h->T(o.y), y.C, h->T(o.x), a.C, a.rows * nb, a.C, 0.f, 0, st));
+        CK(pbk_copy2d(h->T(o.y) + a.C, y.C, h->T(o.x2), b.C, b.rows * nb, b.C, 0.f, 0, st));
+        break;
+      }
+      case OP_IM2COL:
+        CK(pbk_im2col_s2(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->T(o.y), h->rnd, st));
+        break;
+      case OP_UPSAMPLE:
+        CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->rnd, st));
+        break;
+      case OP_GEGLU:
+        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->rnd, st));
+        break;
+      case OP_ATTN:
+        if (int e = run_attn_jvp(h, o, nb, st)) return e;
+        break;
+      case OP_OUT: {
+        const Val& v = h->vals[o.x];
+        CK(pbk_transpose(U, v.rows, v.rows * v.C, 0, h->T(o.x), v.C, v.rows * v.C, 0, nb, 1, (int)v.rows, v.C, 0.f, 0, st));
+        break;
+      }
+    }
+  }
+  return PB_OK;
+}
+
+int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
+  h->rnd = h->rnd_t;
+  for (Val& v : h->vals) v.ginit = false;
+  for (size_t i = h->ops.size(); i-- > 0;) {
+    const Op& o = h->ops[i];
+    if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
+    switch (o.kind) {
+      case OP_OUT: {
+        Val& v = h->vals[o.x];
+        CK(pbk_transpose(h->T(o.x), v.C, v.rows * v.C, 0, U, v.rows, v.rows * v.C, 0, nb, 1, v.C, (int)v.rows, 0.f, h->rnd, st));
+        v.ginit = true;
+        break;
+      }
+      case OP_ATTN:
+        if (int e = run_attn_vjp(h, o, nb, st)) return e;
+        break;
+      case OP_GEGLU:
+        if (h->vals[o.x].ginit) return fail(h, PB_ESTATE, "internal: GEGLU input has several consumers");
+        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->rnd, st));
+        h->vals[o.x].ginit = true;
+        break;
+      case OP_UPSAMPLE: {
+        Val& v = h->vals[o.x];
+        CK(pbk_upsample2x_vjp(h->T(o.y), nb, o.H, o.W, v.C, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, st));
+        v.ginit = true;
+        break;
+      }
+      case OP_IM2COL: {
+        Val& v = h->vals[o.x];
+        CK(pbk_col2im_s2(h->T(o.y), nb, o.H, o.W, v.C, o.pad_lo, o.Ho, o.Wo, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, st));
+        v.ginit = true;
+        break;
+      }
+      case OP_CONCAT: {
+        Val& a = h->vals[o.x]; Val& b = h->vals[o.x2]; const Val& y = h->vals[o.y];
+        CK(pbk_copy2d(h->T(o.x), a.C, h->T(o.y), y.C, a.rows * nb, a.C, a.ginit ? 1.f : 0.f, h->rnd, st));
+        CK(pbk_copy2d(h->T(o.x2), b.C, h->T(o.y) + a.C, y.C, b.rows * nb, b.C, b.ginit ? 1.f : 0.f, h->rnd, st));
+        a.ginit = b.ginit = true;
+        break;
+      }
+      case OP_GEMM:
+        if (int e = run_gemm_bwd(h, o, nb, st)) return e;
+        break;
+      case OP_LN: {
+        Val& v = h->vals[o.x];
+        CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.y), nb, 1, h->T(o.x),
+                      v.ginit ? 1.f : 0.f, h->rnd, st));
+        v.ginit = true;
+        break;
+      }
+      case OP_GN: {
+        Val& v = h->vals[o.x];
+        CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
+                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, h->WP(h->w_gn), st));
+        v.ginit = true;
+        break;
+      }
+      case OP_CONV_DIRECT: {
+        Val& v = h->vals[o.x];
+        CK(pbk_conv3x3_direct(h->T(o.y), nb, o.H, o.W, h->vals[o.y].C, h->Wb(o.w), nullptr, v.C, h->T(o.x), 0.f, st));
+        v.ginit = true;
+        break;
+      }
+      case OP_IN: {
+        const Val& v = h->vals[o.y];
+        CK(pbk_transpose(Wout, v.rows, v.rows * v.C, 0, h->T(o.y), v.C, v.rows * v.C, 0, nb, 1, (int)v.rows, v.C, 0.f, 0, st));
+        break;
+      }
+    }
+  }
+  return PB_OK;
+}
+
+int run_ortho(pb_handle* h, const float* Wm, const float* Vprev, int k, float atol, float* V, float* s, float* metrics, pb_stream st) {
+  double* G = reinterpret_cast<double*>(h->work + h->w_G);
+  double* M = reinterpret_cast<double*>(h->work + h->w_M);
+  CK(pbk_gram2(Wm, Vprev, k, h->n_in, G, Vprev ? M : nullptr, st));
+  CK(pbk_jacobi(G, Vprev ? M : nullptr, k, h->WP(h->w_R), s, st));
+  CK(pbk_rotate(Wm, h->WP(h->w_R), Vprev, k, h->n_in, atol, 1e-5f, V, metrics, st));
+  return PB_OK;
+}
+
+int check_ready(pb_handle* h, int k, bool need_point) {
+  if (!h) return PB_EINVAL;
+  if (!h->planned) return fail(h, PB_ESTATE, "pb_plan has not been called");
+  if (!h->bound) return fail(h, PB_ESTATE, "pb_bind_weights has not been called");
+  if (need_point && !h->point) return fail(h, PB_ESTATE, "pb_set_point has not been called");
+  if (k < 1 || k > h->kmax) return fail(h, PB_EINVAL, "pca_rank must be in [1, k_max]");
+  return PB_OK;
+}
+
+void drop_graph(pb_handle* h) {
+  if (h->graph) { pbk_graph_destroy(h->graph); h->graph = nullptr; }
+}
+
+}  // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+PB_API const char* pb_backend(void) { return pbk_backend_name(); }
+
+PB_API const char* pb_last_error(const pb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+PB_API int pb_create(const pb_unet_cfg* cfg, pb_handle** out) {
+  if (!cfg || !out) return PB_EINVAL;
+  *out = nullptr;
+  if (cfg->n_levels < 1 || cfg->n_levels > PB_MAX_LEVELS || cfg->in_channels < 1 || cfg->layers_per_block < 1 ||
+      cfg->norm_num_groups < 1 || (cfg->kind != PB_UNET_COND && cfg->kind != PB_UNET_UNCOND))
+    return PB_EINVAL;
+  for (int i = 0; i < cfg->n_levels; ++i)
+    if (cfg->block_out_channels[i] < 4 || cfg->heads[i] < 1) return PB_EINVAL;
+  pb_handle* h = new pb_handle();
+  h->cfg = *cfg;
+  *out = h;
+  return PB_OK;
+}
+
+PB_API void pb_destroy(pb_handle* h) {
+  if (!h) return;
+  drop_graph(h);
+  delete h;
+}
+
+PB_API int64_t pb_kernel_launches(const pb_handle* h) { return h ? h->launches : 0; }
+
+// Enumerates the state_dict entries the planned path consumes (name + PyTorch shape), in plan order.
+PB_API int pb_weight_count(const pb_handle* h) {
+  if (!h || !h->planned) return 0;
+  int n = 0;
+  for (const WSpec& s : h->wspecs) n += (int)s.names.size();
+  return n;
+}
+PB_API int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t* ndim, int64_t* shape) {
+  if (!h || !h->planned || !name || !ndim || !shape) return PB_EINVAL;
+  for (const WSpec& s : h->wspecs) {
+    if (index >= (int)s.names.size()) { index -= (int)s.names.size(); continue; }
+    *name = s.names[index].c_str();
+    const int64_t rows = s.out / (int64_t)s.names.size();
+    shape[0] = rows; shape[1] = s.in; shape[2] = shape[3] = 3;
+    switch (s.kind) {
+      case WK_VEC: *ndim = 1; break;
+      case WK_RAW: case WK_LIN: *ndim = 2; break;
+      case WK_CONV3: case WK_CONV3_S2: *ndim = 4; break;
+    }
+    return PB_OK;
+  }
+  return PB_EINVAL;
+}
+
+PB_API int pb_set_option(pb_handle* h, const char* name, int value) {
+  if (!h || !name) return PB_EINVAL;
+  struct { const char* n; int* p; bool rebind; } opts[] = {
+      {"round_primal", &h->rnd_p, false}, {"round_tangent", &h->rnd_t, false}, {"round_weights", &h->rnd_w, true},
+      {"precise_primal", &h->prec_p, false}, {"precise_tangent", &h->prec_t, false}, {"precise_attn", &h->prec_a, false}};
+  for (auto& o : opts)
+    if (!strcmp(name, o.n)) {
+      *o.p = value; drop_graph(h); h->point = false;
+      if (o.rebind) h->bound = false;
+      return PB_OK;
+    }
+  if (!strcmp(name, "use_graph")) { h->use_graph = value ? 1 : 0; drop_graph(h); return PB_OK; }
+  return fail(h, PB_EINVAL, std::string("unknown option ") + name);
+}
+
+PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int32_t block_idx, int32_t k_max, int32_t ctx_len,
+                   pb_sizes* sizes) {
+  if (!h) return PB_EINVAL;
+  h->planned = h->bound = h->point = false;
+  drop_graph(h);
+  if (height < 1 || width < 1 || k_max < 1 || k_max > 64) return fail(h, PB_EINVAL, "bad geometry or k_max (1..64)");
+  // the reference raises ValueError for every other (op, block_idx) (utils.py:527, :158-163); op='down' is broken there
+  if (op == PB_OP_MID) { if (block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid"); }
+  else if (op == PB_OP_UP) {
+    if (h->cfg.kind != PB_UNET_COND || block_idx < 0 || block_idx >= h->cfg.n_levels) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
+  } else return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
+  if (h->cfg.kind == PB_UNET_COND && ctx_len < 1) return fail(h, PB_EINVAL, "ctx_len must be >= 1 for a conditional U-Net");
+  h->H = height; h->W = width; h->op = op; h->block_idx = block_idx; h->kmax = k_max; h->ctx_len = ctx_len;
+  h->vals.clear(); h->ops.clear(); h->wspecs.clear(); h->windex.clear();
+  h->cache_top = h->work_top = h->packed_top = 0;
+  h->n_s1 = h->n_s2 = h->n_s3 = h->n_delta = h->n_gn = 0;
+  h->sizes = pb_sizes{};
+  Planner p{h, ""};
+  const int c0 = h->cfg.block_out_channels[0];
+  h->c_sin = p.cache_alloc(c0); h->c_e1 = p.cache_alloc(4 * c0); h->c_temb = p.cache_alloc(4 * c0);
+  h->c_ctx = p.cache_alloc((size_t)std::max(1, ctx_len) * std::max(1, h->cfg.cross_attention_dim));
+  if (!p.build()) return fail(h, PB_EINVAL, p.error);
+  h->n_in = (long)h->cfg.in_channels * height * width;
+  h->n_out = h->vals[h->out_val].rows * h->vals[h->out_val].C;
+  const size_t K = k_max;
+  h->w_s1 = p.work_alloc(h->n_s1 * K); h->w_s2 = p.work_alloc(h->n_s2 * K); h->w_s3 = p.work_alloc(h->n_s3 * K);
+  h->w_delta = p.work_alloc(h->n_delta * K); h->w_gn = p.work_alloc(h->n_gn * K + 64);
+  h->w_V = p.work_alloc(K * h->n_in); h->w_Vprev = p.work_alloc(K * h->n_in); h->w_W = p.work_alloc(K * h->n_in);
+  h->w_U = p.work_alloc(K * h->n_out);
+  h->w_G = p.work_alloc(2 * K * K); h->w_M = p.work_alloc(2 * K * K); h->w_R = p.work_alloc(K * K);
+  h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4);
+  h->w_x = p.work_alloc((size_t)h->n_in);
+  h->sizes.packed_weight_bytes = h->packed_top; h->sizes.primal_cache_bytes = h->cache_top; h->sizes.workspace_bytes = h->work_top;
+  h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out;
+  if (sizes) *sizes = h->sizes;
+  h->planned = true;
+  return PB_OK;
+}
+
+PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n, void* packed, void* stream) {
+  if (!h || !table || !packed) return PB_EINVAL;
+  if (!h->planned) return fail(h, PB_ESTATE, "pb_plan has not been called");
+  h->bound = false; h->point = false;
+  drop_graph(h);
+  std::map<std::string, const pb_tensor_desc*> byname;
+  for (int i = 0; i < n; ++i) if (table[i].name) byname[table[i].name] = &table[i];
+  h->packed = static_cast<char*>(packed);
+  for (const WSpec& s : h->wspecs) {
+    int row = 0;
+    for (const std::string& name : s.names) {
+      auto it = byname.find(name);
+      if (it == byname.end()) return fail(h, PB_EMISSING, "state_dict entry missing: " + name);
+      const pb_tensor_desc& d = *it->second;
+      long numel = 1;
+      for (int a = 0; a < d.ndim; ++a) numel *= d.shape[a];
+      const long per_row = s.kind == WK_VEC ? 1 : (s.kind == WK_CONV3 || s.kind == WK_CONV3_S2) ? (long)s.in * 9 : s.in;
+      if (numel % per_row || (s.names.size() == 1 && numel != per_row * s.out))
+        return fail(h, PB_EINVAL, "unexpected shape for " + name);
+      const int rows = (int)(numel / per_row);
+      if (row + rows > s.out) return fail(h, PB_EINVAL, "unexpected shape for " + name);
+      float* fwd = reinterpret_cast<float*>(h->packed + s.fwd_off);
+      float* bwd = reinterpret_cast<float*>(h->packed + s.bwd_off);
+      switch (s.kind) {
+        case WK_VEC: case WK_RAW:
+          CK(pbk_copy(fwd + (size_t)row * per_row, d.data, (size_t)numel * 4, stream));
+          break;
+        case WK_LIN:
+          if (h->rnd_w) CK(pbk_round_tf32(fwd + (size_t)row * s.in, d.data, (size_t)numel, stream));
+          else CK(pbk_copy(fwd + (size_t)row * s.in, d.data, (size_t)numel * 4, stream));
+          CK(pbk_transpose(bwd + row, s.out, 0, 0, d.data, s.in, 0, 0, 1, 1, rows, s.in, 0.f, h->rnd_w, stream));
+          break;
+        case WK_CONV3:
+          // conv_in (thin direct kernel, fp32 FMA) keeps full precision
+          CK(pbk_pack_conv3x3(d.data, s.out, s.in, fwd, bwd, (s.in % 32 == 0) ? h->rnd_w : 0, stream));
+          break;
+        case WK_CONV3_S2:
+          CK(pbk_pack_conv3x3(d.data, s.out, s.in, fwd, nullptr, h->rnd_w, stream));
+          CK(pbk_transpose(bwd, s.out, 0, 0, fwd, 9L * s.in, 0, 0, 1, 1, s.out, 9 * s.in, 0.f, 0, stream));
+          break;
+      }
+      row += rows;
+    }
+    if (row != s.out) return fail(h, PB_EINVAL, "unexpected shape for " + s.names[0]);
+  }
+  h->bound = true;
+  return PB_OK;
+}
+
+PB_API int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx, void* primal_cache, void* workspace, float* h_out,
+                        void* stream) {
+  if (int e = check_ready(h, 1, false)) return e;
+  if (!x || !primal_cache || !workspace) return fail(h, PB_EINVAL, "null pointer");
+  h->point = false;
+  if (h->cache != primal_cache || h->work != workspace) drop_graph(h);
+  h->cache = static_cast<char*>(primal_cache); h->work = static_cast<char*>(workspace);
+  if (int e = run_primal(h, x, t, ctx, h_out, stream)) return e;
+  h->point = true;
+  return PB_OK;
+}
+
+PB_API int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream) {
+  if (int e = check_ready(h, k, true)) return e;
+  if (!V || !U) return fail(h, PB_EINVAL, "null pointer");
+  return run_jvp(h, V, k, U, stream);
+}
+
+PB_API int pb_vjp(pb_handle* h, const float* U, int32_t k, float* W, void* stream) {
+  if (int e = check_ready(h, k, true)) return e;
+  if (!U || !W) return fail(h, PB_EINVAL, "null pointer");
+  return run_vjp(h, U, k, W, stream);
+}
+
+PB_API int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t k, float atol, float* V, float* s, float* metrics,
+                             void* stream) {
+  if (int e = check_ready(h, k, true)) return e;
+  if (!W || !V || !s) return fail(h, PB_EINVAL, "null pointer");
+  return run_ortho(h, W, Vprev, k, atol, V, s, metrics, stream);
+}
+
+PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u, float* s,
+                       float* vT, pb_iter_info* info, void* stream) {
+  if (int e = check_ready(h, k, true)) return e;
+  if (!V0 || !u || !s || !vT) return fail(h, PB_EINVAL, "null pointer");
+  if (max_iter < 1) return fail(h, PB_EINVAL, "max_iter must be >= 1");
+  float* Va = h->WP(h->w_V); float* Vb = h->WP(h->w_Vprev);
+  float* Wm = h->WP(h->w_W); float* met = h->WP(h->w_met);
+  const size_t vbytes = (size_t)k * h->n_in * 4;
+  CK(pbk_copy(Vb, V0, vbytes, stream));
+  // One iteration (utils.py:758-799): Vprev = Vb -> U = J Vprev -> W = U^T J -> (s, Va) = svd(W); then Vb <- Va.
+  auto iteration = [&]() -> int {
+    if (int e = run_jvp(h, Vb, k, u, stream)) return e;
+    if (int e = run_vjp(h, u, k, Wm, stream)) return e;
+    if (int e = run_ortho(h, Wm, Vb, k, tol, Va, s, met, stream)) return e;
+    return PB_OK;
+  };
+  int done = 0, converged = 0;
+  float host_met[2] = {0.f, 0.f};
+  for (int i = 0; i < max_iter; ++i) {
+    bool replayed = false;
+    if (h->use_graph) {
+      if (h->graph && (h->graph_k != k || h->graph_tol != tol || h->graph_u != u || h->graph_s != s)) drop_graph(h);
+      if (!h->graph && h->warm) {     // the first iteration ever runs eagerly (one-time kernel attribute setup)
+        const char* e = pbk_graph_begin(stream);
+        if (!e) {
+          const long before = h->launches;
+          int rc = iteration();
+          long nodes = 0;
+          const char* e2 = pbk_graph_end(stream, &h->graph, &nodes);
+          h->launches = before;
+          if (rc) { drop_graph(h); return rc; }
+          if (e2) { drop_graph(h); return fail(h, PB_ECUDA, std::string("graph capture: ") + e2); }
+          h->graph_k = k; h->graph_tol = tol; h->graph_u = u; h->graph_s = s;
+          h->graph_nodes = nodes;
+        } else {
+          h->use_graph = 0;            // backend without graph support: launch directly
+        }
+      }
+      if (h->graph) {
+        const char* e = pbk_graph_launch(h->graph, stream);
+        if (e) return fail(h, PB_ECUDA, std::string("graph launch: ") + e);
+        h->launches += h->graph_nodes;
+        replayed = true;
+      }
+    }
+    if (!replayed) { if (int e = iteration()) return e; h->warm = true; }
+    ++done;
+    const bool last = (i + 1 == max_iter);
+    // the reference tests allclose(v_prev, v, atol) and i > min_iter after every iteration (utils.py:806-808)
+    if (i > min_iter || last) {
+      CK(pbk_download(host_met, met, sizeof host_met, stream));
+      if (i > min_iter && host_met[1] == 0.f) { converged = 1; }
+    }
+    if (converged || last) break;
+    CK(pbk_copy(Vb, Va, vbytes, stream));
+  }
+  CK(pbk_copy(vT, Va, vbytes, stream));
+  if (info) { info->iters_done = done; info->converged = converged; info->last_dist = std::sqrt(host_met[0]); }
+  return PB_OK;
+}
+
+// The same call with HOST buffers (what a host-language binding of the reference's method would hand over):
+// copies x_t / ctx / V0 in, runs the primal pass and the iteration, copies (u, s, vT) out.  Blocking.
+PB_API int pb_pullback_host(pb_handle* h, const float* x_host, float t, const float* ctx_host, const float* V0_host, int32_t k,
+                            int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
+                            pb_iter_info* info, void* stream) {
+  if (int e = check_ready(h, k, false)) return e;
+  if (!h->cache || !h->work) return fail(h, PB_ESTATE, "pb_set_point must have been called once to attach the cache / workspace");
+  if (!x_host || !V0_host || !u_host || !s_host || !vT_host) return fail(h, PB_EINVAL, "null pointer");
+  float* dx = h->WP(h->w_x);
+  float* dctx = nullptr;
+  CK(pbk_upload(dx, x_host, (size_t)h->n_in * 4, stream));
+  if (h->cfg.kind == PB_UNET_COND) {
+    if (!ctx_host) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
+    // staged in the S3 scratch (free until the first attention op runs; run_primal copies it into the cache first)
+    dctx = h->WP(h->w_s3);
+    if ((size_t)h->ctx_len * h->cfg.cross_attention_dim > h->n_s3 * (size_t)h->kmax)
+      return fail(h, PB_ESTATE, "internal: scratch too small for the text context");
+    CK(pbk_upload(dctx, ctx_host, (size_t)h->ctx_len * h->cfg.cross_attention_dim * 4, stream));
+  }
+  h->point = false;
+  if (int e = run_primal(h, dx, t, dctx, nullptr, stream)) return e;
+  h->point = true;
+  float* dV0 = h->WP(h->w_W);          // W is overwritten only after V0 has been copied to Vprev
+  CK(pbk_upload(dV0, V0_host, (size_t)k * h->n_in * 4, stream));
+  float* du = h->WP(h->w_U); float* ds = h->WP(h->w_sv);
+  float* dvT_slot = h->WP(h->w_Vprev); // Vprev is dead once the last iteration has produced V
+  if (int e = pb_pullback(h, dV0, k, min_iter, max_iter, tol, du, ds, dvT_slot, info, stream)) return e;
+  CK(pbk_download(u_host, du, (size_t)k * h->n_out * 4, stream));
+  CK(pbk_download(s_host, ds, (size_t)k * 4, stream));
+  CK(pbk_download(vT_host, dvT_slot, (size_t)k * h->n_in * 4, stream));
+  return PB_OK;
+}

@@ -31,6 +31,8 @@ struct PbGemm {
   int conv;                              // 0 plain, 1 = 3x3/s1/p1 NHWC implicit GEMM
   int H, W;                              // conv mode spatial extent
   int round_tf32;                        // round the stored result to TF32 (RNA) for a GEMM-only consumer
+  int precise;                           // 0: one TF32 pass; 1: error-compensated 3xTF32 (A and B split hi/lo);
+                                         // 2: B (weights) split hi/lo, A as given
 };
 
 static inline PbGemm pb_gemm_init() {

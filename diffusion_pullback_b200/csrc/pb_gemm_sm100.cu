@@ -395,7 +395,7 @@ static const char* launch_t(const Params& p, dim3 grid, cudaStream_t st) {
 
 }  // namespace pbgemm
 
-extern "C" void pb_gemm_set_tmap_tf32(int on) { pbgemm::g_tmap_dtype_tf32 = on; }
+extern "C" __attribute__((visibility("default"))) void pb_gemm_set_tmap_tf32(int on) { pbgemm::g_tmap_dtype_tf32 = on; }
 
 // Returns nullptr on success, else a static error string.  Stream-ordered, no host sync.
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {

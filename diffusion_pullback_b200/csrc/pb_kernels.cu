@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <algorithm>
+#include <vector>
 
 #include "pb_kernels.h"
 
@@ -56,38 +57,38 @@ __device__ __forceinline__ float gelu_d(float g) {
 // data movement
 // ------------------------------------------------------------------------------------------------
 __global__ void copy2d_v4(float* __restrict__ dst, long ldd, const float* __restrict__ src, long lds, long rows,
-                          int cols4, float beta) {
+                          int cols4, float beta, int rnd) {
   const long total = rows * cols4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / cols4; const int c = int(i % cols4) * 4;
     float4 v = *reinterpret_cast<const float4*>(src + r * lds + c);
     float4* d = reinterpret_cast<float4*>(dst + r * ldd + c);
     if (beta != 0.f) { float4 o = *d; v.x += beta * o.x; v.y += beta * o.y; v.z += beta * o.z; v.w += beta * o.w; }
-    *d = v;
+    *d = maybe_round4(v, rnd);
   }
 }
 __global__ void copy2d_s(float* __restrict__ dst, long ldd, const float* __restrict__ src, long lds, long rows,
-                         int cols, float beta) {
+                         int cols, float beta, int rnd) {
   const long total = rows * cols;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / cols; const int c = int(i % cols);
     float v = src[r * lds + c];
     float* d = dst + r * ldd + c;
-    *d = beta != 0.f ? v + beta * *d : v;
+    *d = maybe_round(beta != 0.f ? v + beta * *d : v, rnd);
   }
 }
 
-// src [nb][R][C] -> dst [nb][C][ldd]
-__global__ void transpose_k(float* __restrict__ dst, long ldd, const float* __restrict__ src, int R, int C, float beta,
-                            int rnd) {
+// src_(b,h) [R][lds] -> dst_(b,h) [C][ldd];  blockIdx.z = b * nh + h
+__global__ void transpose_k(float* __restrict__ dst, long ldd, long sbd, long shd, const float* __restrict__ src,
+                            long lds, long sbs, long shs, int nh, int R, int C, float beta, int rnd) {
   __shared__ float tile[32][33];
-  const int b = blockIdx.z;
+  const int b = blockIdx.z / nh, h = blockIdx.z % nh;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const float* s = src + (long)b * R * C;
-  float* d = dst + (long)b * C * ldd;
+  const float* s = src + (long)b * sbs + (long)h * shs;
+  float* d = dst + (long)b * sbd + (long)h * shd;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? s[(long)r * C + c] : 0.f;
+    tile[i][threadIdx.x] = (r < R && c < C) ? s[(long)r * lds + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -114,7 +115,7 @@ __global__ void upsample2x_k(const float4* __restrict__ x, int nb, int H, int W,
   }
 }
 __global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, int W, int C4, float4* __restrict__ gx,
-                                 float beta) {
+                                 float beta, int rnd) {
   const long total = (long)nb * H * W * C4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
@@ -131,7 +132,7 @@ __global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, i
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
       }
     if (beta != 0.f) { const float4 o = gx[i]; a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
-    gx[i] = a;
+    gx[i] = maybe_round4(a, rnd);
   }
 }
 __global__ void round_tf32_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
@@ -159,7 +160,7 @@ __global__ void im2col_s2_k(const float4* __restrict__ x, int nb, int H, int W, 
   }
 }
 __global__ void col2im_s2_k(const float4* __restrict__ col, int nb, int H, int W, int C4, int pad, int Ho, int Wo,
-                            float4* __restrict__ gx, float beta) {
+                            float4* __restrict__ gx, float beta, int rnd) {
   const long total = (long)nb * H * W * C4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
@@ -185,7 +186,7 @@ __global__ void col2im_s2_k(const float4* __restrict__ col, int nb, int H, int W
       }
     }
     if (beta != 0.f) { const float4 o = gx[i]; a.x += beta * o.x; a.y += beta * o.y; a.z += beta * o.z; a.w += beta * o.w; }
-    gx[i] = a;
+    gx[i] = maybe_round4(a, rnd);
   }
 }
 
@@ -770,6 +771,40 @@ PBK pbk_upload(void* dst, const void* host_src, size_t bytes, pb_stream st) {
 }
 PBK pbk_sync(pb_stream st) { return cuda_err(cudaStreamSynchronize(S(st))); }
 
+PBK pbk_graph_begin(pb_stream st) {
+  if (S(st) == nullptr || S(st) == cudaStreamLegacy) return "graph capture needs a non-default stream";
+  return cuda_err(cudaStreamBeginCapture(S(st), cudaStreamCaptureModeThreadLocal));
+}
+PBK pbk_graph_end(pb_stream st, void** graph_exec, long* kernel_nodes) {
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(S(st), &g);
+  if (e != cudaSuccess) { cudaGetLastError(); return cuda_err(e); }
+  size_t n = 0;
+  if (kernel_nodes) {
+    *kernel_nodes = 0;
+    if (cudaGraphGetNodes(g, nullptr, &n) == cudaSuccess && n) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      cudaGraphGetNodes(g, nodes.data(), &n);
+      for (size_t i = 0; i < n; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++*kernel_nodes;
+      }
+    }
+  }
+  cudaGraphExec_t ex = nullptr;
+  e = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return cuda_err(e);
+  *graph_exec = ex;
+  return nullptr;
+}
+PBK pbk_graph_launch(void* graph_exec, pb_stream st) {
+  return cuda_err(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), S(st)));
+}
+PBK pbk_graph_destroy(void* graph_exec) {
+  return cuda_err(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)));
+}
+
 PBK pbk_gemm(const PbGemm* g, pb_stream st) { return pb_gemm_launch(*g, S(st)); }
 
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
@@ -792,26 +827,28 @@ PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int H
   return last_err();
 }
 PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* gx, float beta,
-                  pb_stream st) {
+                  int round_tf32, pb_stream st) {
   CHECK_ALIGN4(C, "col2im: C");
   const long total = (long)nb * H * W * (C / 4);
   col2im_s2_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(col), nb, H, W, C / 4, pad_lo,
-                                                          Ho, Wo, reinterpret_cast<float4*>(gx), beta);
+                                                          Ho, Wo, reinterpret_cast<float4*>(gx), beta, round_tf32);
   return last_err();
 }
 
-PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, pb_stream st) {
+PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, int round_tf32,
+               pb_stream st) {
   if (rows <= 0 || cols <= 0) return nullptr;
   const bool v4 = (cols % 4 == 0) && (ldd % 4 == 0) && (lds % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
-  if (v4) copy2d_v4<<<grid_for(rows * (cols / 4), 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols / 4, beta);
-  else copy2d_s<<<grid_for(rows * cols, 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols, beta);
+  if (v4) copy2d_v4<<<grid_for(rows * (cols / 4), 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols / 4, beta, round_tf32);
+  else copy2d_s<<<grid_for(rows * cols, 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols, beta, round_tf32);
   return last_err();
 }
-PBK pbk_transpose(float* dst, long ldd, const float* src, int nb, int R, int C, float beta, int round_tf32,
-                  pb_stream st) {
-  dim3 grid((C + 31) / 32, (R + 31) / 32, nb), block(32, 8);
-  transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, src, R, C, beta, round_tf32);
+PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, long lds, long sbs, long shs, int nb,
+                  int nh, int R, int C, float beta, int round_tf32, pb_stream st) {
+  if ((long)nb * nh > 65535 || (R + 31) / 32 > 65535) return "transpose: batch / row extent too large";
+  dim3 grid((C + 31) / 32, (R + 31) / 32, nb * nh), block(32, 8);
+  transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, sbd, shd, src, lds, sbs, shs, nh, R, C, beta, round_tf32);
   return last_err();
 }
 PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int round_tf32, pb_stream st) {
@@ -821,11 +858,12 @@ PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int ro
                                                            reinterpret_cast<float4*>(y), round_tf32);
   return last_err();
 }
-PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, pb_stream st) {
+PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int round_tf32,
+                       pb_stream st) {
   CHECK_ALIGN4(C, "upsample_vjp: C");
   const long total = (long)nb * H * W * (C / 4);
   upsample2x_vjp_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(gy), nb, H, W, C / 4,
-                                                               reinterpret_cast<float4*>(gx), beta);
+                                                               reinterpret_cast<float4*>(gx), beta, round_tf32);
   return last_err();
 }
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {

@@ -15,7 +15,7 @@
 #include "pb_gemm.h"
 
 typedef void* pb_stream;
-#define PBK extern "C" const char*
+#define PBK extern "C" __attribute__((visibility("default"))) const char*
 
 // ---- memory ----
 PBK pbk_memset0(void* p, size_t bytes, pb_stream st);
@@ -24,6 +24,11 @@ PBK pbk_download(void* host_dst, const void* src, size_t bytes, pb_stream st);  
 PBK pbk_upload(void* dst, const void* host_src, size_t bytes, pb_stream st);     // blocking
 PBK pbk_sync(pb_stream st);
 PBK pbk_backend_name();
+// CUDA-graph capture of a launch sequence on `st` (must not be the legacy default stream)
+PBK pbk_graph_begin(pb_stream st);
+PBK pbk_graph_end(pb_stream st, void** graph_exec, long* kernel_nodes);
+PBK pbk_graph_launch(void* graph_exec, pb_stream st);
+PBK pbk_graph_destroy(void* graph_exec);
 
 // ---- contraction ----
 PBK pbk_gemm(const PbGemm* g, pb_stream st);
@@ -34,16 +39,19 @@ PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const floa
 PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* col, int round_tf32,
                   pb_stream st);
 PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* gx, float beta,
-                  pb_stream st);
+                  int round_tf32, pb_stream st);
 
 // ---- data movement ----
 // dst[r][c] = src[r][c] + beta * dst[r][c]   (channel-slice copies: concat / split / residual fan-in)
-PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, pb_stream st);
-// src [nb][R][C] -> dst [nb][C][ldd] (ldd >= R); dst = src^T + beta * dst
-PBK pbk_transpose(float* dst, long ldd, const float* src, int nb, int R, int C, float beta, int round_tf32,
-                  pb_stream st);
+PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, int round_tf32,
+               pb_stream st);
+// per batch (b, h): src_bh = src + b*sbs + h*shs is [R][lds] (first C columns used) -> dst_bh = dst + b*sbd + h*shd
+// is [C][ldd] (ldd >= R);  dst = src^T + beta * dst
+PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, long lds, long sbs, long shs, int nb,
+                  int nh, int R, int C, float beta, int round_tf32, pb_stream st);
 PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int round_tf32, pb_stream st);
-PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, pb_stream st);
+PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int round_tf32,
+                       pb_stream st);
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
 
 // ---- GroupNorm (+ optional SiLU) ----

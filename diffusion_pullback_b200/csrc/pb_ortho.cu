@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int kMaxK = 64;
-constexpr int kChunk = 512;     // columns of W staged per block
+constexpr int kChunkMax = 512;  // columns of W staged per block (shrinks for large k to fit shared memory)
 
 inline const char* last_err() {
   cudaError_t e = cudaGetLastError();
@@ -29,8 +29,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-__global__ void gram2_k(const float* __restrict__ Wm, const float* __restrict__ Vp, int k, long n, double* __restrict__ G,
-                        double* __restrict__ M) {
+__global__ void gram2_k(const float* __restrict__ Wm, const float* __restrict__ Vp, int k, long n, int kChunk,
+                        double* __restrict__ G, double* __restrict__ M) {
   extern __shared__ float sh[];                  // W tile [k][kChunk], V tile [k][kChunk]
   float* sw = sh;
   float* sv = sh + (size_t)k * kChunk;
@@ -173,17 +173,26 @@ PBK pbk_gram2(const float* Wm, const float* Vprev, int k, long n, double* G, dou
   cudaStream_t s = static_cast<cudaStream_t>(st);
   cudaMemsetAsync(G, 0, sizeof(double) * k * k, s);
   if (M) cudaMemsetAsync(M, 0, sizeof(double) * k * k, s);
+  int kChunk = std::min(kChunkMax, (96 * 1024 / (2 * k * 4)) / 32 * 32);
   const size_t shmem = (size_t)2 * k * kChunk * sizeof(float);
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(gram2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxK * kChunk * 4); attr = true; }
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gram2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr = true;
+  }
   const unsigned grid = (unsigned)std::max<long>(1, std::min<long>((n + kChunk - 1) / kChunk, 148 * 2));
-  gram2_k<<<grid, 256, shmem, s>>>(Wm, Vprev, k, n, G, M);
+  gram2_k<<<grid, 256, shmem, s>>>(Wm, Vprev, k, n, kChunk, G, M);
   return last_err();
 }
 PBK pbk_jacobi(const double* G, const double* M, int k, float* Rm, float* sv, pb_stream st) {
   if (k < 1 || k > kMaxK) return "ortho: pca_rank must be in [1, 64]";
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(jacobi_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxK * kMaxK * 8); attr = true; }
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxK * kMaxK * 8);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    attr = true;
+  }
   jacobi_k<<<1, 32, (size_t)2 * k * k * sizeof(double), static_cast<cudaStream_t>(st)>>>(G, M, k, Rm, sv);
   return last_err();
 }

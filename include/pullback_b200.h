@@ -109,6 +109,23 @@ int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t 
 int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u,
                 float* s, float* vT, pb_iter_info* info, void* stream);
 
+/* The same call with HOST buffers -- what a host-language binding of the reference's method hands over
+ * (x_t, t, encoder_hidden_states, V0 in; u, s, vT out): copies in, runs the primal pass (pb_set_point) and
+ * the iteration (pb_pullback) on the cache / workspace attached by an earlier pb_set_point, copies out.
+ * Blocking. */
+int pb_pullback_host(pb_handle* h, const float* x_host, float t, const float* ctx_host, const float* V0_host,
+                     int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host,
+                     float* vT_host, pb_iter_info* info, void* stream);
+
+/* After pb_plan(): the state_dict entries (diffusers key + PyTorch shape, ndim <= 4) the planned path consumes. */
+int pb_weight_count(const pb_handle* h);
+int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t* ndim, int64_t* shape);
+
+/* Diagnostics: kernels launched through this handle so far (graph replays count their kernel nodes);
+ * options: "use_graph" (default 1), "round_tf32" (default 1; re-bind weights after changing it). */
+int64_t pb_kernel_launches(const pb_handle* h);
+int pb_set_option(pb_handle* h, const char* name, int value);
+
 #ifdef __cplusplus
 }
 #endif

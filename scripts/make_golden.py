@@ -65,7 +65,7 @@ def run(case, out_dir):
     g = {"case": case, "config": cfg_name, "op": op, "block_idx": bi, "k": k, "iters": iters,
          "n_params": n_params, "v0": v0.clone(), "s": s.clone(), "vT": vT.clone().contiguous(),
          "n_out": u.shape[0], "u_norm": u.norm(dim=0).clone(),
-         "ref_seconds": dt, "ref_threads": torch.get_num_threads(), "torch": torch.__version__,
+         "ref_seconds": dt, "ref_threads": torch.get_num_threads(), "torch": str(torch.__version__),
          "ref_log": buf.getvalue()[-2000:]}
     u = u.contiguous()
     if u.numel() * 4 <= 4 << 20:

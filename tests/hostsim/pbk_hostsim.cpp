@@ -1,0 +1,446 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or reachable from the product library.
+//
+// A plain-C++ double of the leaf-kernel interface (csrc/pb_kernels.h) so that the HOST logic of the
+// engine (csrc/pb_engine.cpp: planning, weight packing, op sequencing, cotangent accumulation order,
+// workspace offsets, the iteration loop) can be unit-tested in the CPU-only authoring container
+// (`pytest -m "not gpu"`), where no CUDA kernel can run.  tests/hostsim/build.py links it with the
+// unmodified pb_engine.cpp into tests/hostsim/libpb_hostsim.so; pb_backend() of that library reports
+// "hostsim" and diffusion_pullback_b200._native refuses anything but "cuda-sm100a".
+// Semantics mirror the CUDA kernels, including TF32 operand truncation in the GEMM and RNA rounding.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pb_kernels.h"
+
+#include <cstdlib>
+namespace {
+// PB_HOSTSIM_EXACT=1: keep fp32 everywhere (separates engine-logic errors from TF32 effects)
+const bool kExact = std::getenv("PB_HOSTSIM_EXACT") != nullptr;
+inline float rna(float x) {
+  if (kExact) return x;
+  uint32_t u; memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & ~0x1fffu;
+  memcpy(&x, &u, 4); return x;
+}
+inline float trunc_tf32(float x) { if (kExact) return x; uint32_t u; memcpy(&u, &x, 4); u &= ~0x1fffu; memcpy(&x, &u, 4); return x; }
+inline float mr(float x, int r) { return r ? rna(x) : x; }
+inline float opA(float x, int precise) { return precise == 1 ? x : trunc_tf32(x); }
+inline float opB(float x, int precise) { return precise >= 1 ? x : trunc_tf32(x); }
+inline float sigm(float x) { return 1.f / (1.f + std::exp(-x)); }
+inline float silu_f(float x) { return x * sigm(x); }
+inline float silu_d(float x) { float s = sigm(x); return s * (1.f + x * (1.f - s)); }
+inline float gelu_f(float g) { return 0.5f * g * (1.f + std::erf(g * 0.70710678118654752f)); }
+inline float gelu_d(float g) { return 0.5f * (1.f + std::erf(g * 0.70710678118654752f)) + g * 0.3989422804014327f * std::exp(-0.5f * g * g); }
+}  // namespace
+
+PBK pbk_backend_name() { return "hostsim"; }
+PBK pbk_memset0(void* p, size_t bytes, pb_stream) { memset(p, 0, bytes); return nullptr; }
+PBK pbk_copy(void* dst, const void* src, size_t bytes, pb_stream) { memmove(dst, src, bytes); return nullptr; }
+PBK pbk_download(void* dst, const void* src, size_t bytes, pb_stream) { memmove(dst, src, bytes); return nullptr; }
+PBK pbk_upload(void* dst, const void* src, size_t bytes, pb_stream) { memmove(dst, src, bytes); return nullptr; }
+PBK pbk_sync(pb_stream) { return nullptr; }
+PBK pbk_graph_begin(pb_stream) { return "hostsim: no graphs"; }
+PBK pbk_graph_end(pb_stream, void**, long*) { return "hostsim: no graphs"; }
+PBK pbk_graph_launch(void*, pb_stream) { return "hostsim: no graphs"; }
+PBK pbk_graph_destroy(void*) { return nullptr; }
+
+PBK pbk_gemm(const PbGemm* gp, pb_stream) {
+  const PbGemm& g = *gp;
+  if (g.M <= 0 || g.N <= 0) return "gemm: empty problem";
+  if (g.conv) {
+    const PbGemmSeg& s = g.seg[0];
+    const int C = s.K, H = g.H, W = g.W;
+    if (C % 32) return "gemm: conv channels must be a multiple of 32";
+#pragma omp parallel for collapse(2) schedule(static)
+    for (long pix = 0; pix < (long)g.nb * H * W; ++pix)
+      for (int n = 0; n < g.N; ++n) {
+        const int x = pix % W, y = (pix / W) % H; const long b = pix / ((long)W * H);
+        double acc = 0.0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+          if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+          const float* a = s.A + ((b * H + iy) * W + ix) * s.lda;
+          const float* w = s.B + (long)n * s.ldb + (long)tap * C;
+          float part = 0.f;
+          for (int c = 0; c < C; ++c) part += opA(a[c], g.precise) * opB(w[c], g.precise);
+          acc += part;
+        }
+        float v = g.alpha * (float)acc;
+        if (g.bias) v += g.bias[n];
+        if (g.R) v += g.beta * g.R[pix * g.ldr + n];
+        g.D[pix * g.ldd + n] = mr(v, g.round_tf32);
+      }
+    return nullptr;
+  }
+  for (int b = 0; b < g.nb; ++b)
+    for (int h = 0; h < g.nh; ++h) {
+#pragma omp parallel for collapse(2) schedule(static)
+      for (int m = 0; m < g.M; ++m)
+        for (int n = 0; n < g.N; ++n) {
+          double acc = 0.0;
+          for (int si = 0; si < g.nseg; ++si) {
+            const PbGemmSeg& s = g.seg[si];
+            const float* a = s.A + b * s.sAb + h * s.sAh + (long)m * s.lda;
+            const float* w = s.B + b * s.sBb + h * s.sBh + (long)n * s.ldb;
+            float part = 0.f;
+            for (int k = 0; k < s.K; ++k) part += opA(a[k], g.precise) * opB(w[k], g.precise);
+            acc += part;
+          }
+          float v = g.alpha * (float)acc;
+          if (g.bias) v += g.bias[n];
+          if (g.R) v += g.beta * g.R[b * g.sRb + h * g.sRh + (long)m * g.ldr + n];
+          g.D[b * g.sDb + h * g.sDh + (long)m * g.ldd + n] = mr(v, g.round_tf32);
+        }
+    }
+  return nullptr;
+}
+
+PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout, float* y,
+                       float beta, pb_stream) {
+#pragma omp parallel for schedule(static)
+  for (long pix = 0; pix < (long)nb * H * W; ++pix) {
+    const int px = pix % W, py = (pix / W) % H; const long b = pix / ((long)W * H);
+    for (int co = 0; co < Cout; ++co) {
+      float acc = bias ? bias[co] : 0.f;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        const float* xp = x + ((b * H + iy) * W + ix) * Cin;
+        const float* wp = w + ((long)co * 9 + tap) * Cin;
+        for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * wp[ci];
+      }
+      float* p = y + pix * Cout + co;
+      *p = beta != 0.f ? acc + beta * *p : acc;
+    }
+  }
+  return nullptr;
+}
+PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad, int Ho, int Wo, float* col, int rnd, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (int oy = 0; oy < Ho; ++oy)
+      for (int ox = 0; ox < Wo; ++ox)
+        for (int tap = 0; tap < 9; ++tap) {
+          const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
+          float* d = col + ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
+          for (int c = 0; c < C; ++c)
+            d[c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? mr(x[((b * H + iy) * W + ix) * C + c], rnd) : 0.f;
+        }
+  return nullptr;
+}
+PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad, int Ho, int Wo, float* gx, float beta, int rnd,
+                  pb_stream) {
+  std::vector<float> acc((size_t)nb * H * W * C, 0.f);
+  for (long b = 0; b < nb; ++b)
+    for (int oy = 0; oy < Ho; ++oy)
+      for (int ox = 0; ox < Wo; ++ox)
+        for (int tap = 0; tap < 9; ++tap) {
+          const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
+          if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+          const float* s = col + ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
+          float* d = acc.data() + ((b * H + iy) * W + ix) * C;
+          for (int c = 0; c < C; ++c) d[c] += s[c];
+        }
+  for (size_t i = 0; i < acc.size(); ++i) gx[i] = mr(beta != 0.f ? acc[i] + beta * gx[i] : acc[i], rnd);
+  return nullptr;
+}
+PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, int rnd, pb_stream) {
+  for (long r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      float* d = dst + r * ldd + c;
+      const float v = src[r * lds + c];
+      *d = mr(beta != 0.f ? v + beta * *d : v, rnd);
+    }
+  return nullptr;
+}
+PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, long lds, long sbs, long shs, int nb, int nh,
+                  int R, int C, float beta, int rnd, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (long h = 0; h < nh; ++h) {
+      const float* s = src + b * sbs + h * shs;
+      float* d = dst + b * sbd + h * shd;
+      for (int r = 0; r < R; ++r)
+        for (int c = 0; c < C; ++c) {
+          float v = s[(long)r * lds + c];
+          float* p = d + (long)c * ldd + r;
+          if (beta != 0.f) v += beta * *p;
+          *p = mr(v, rnd);
+        }
+    }
+  return nullptr;
+}
+PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int rnd, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (int oy = 0; oy < 2 * H; ++oy)
+      for (int ox = 0; ox < 2 * W; ++ox)
+        for (int c = 0; c < C; ++c)
+          y[((b * 2 * H + oy) * 2 * W + ox) * C + c] = mr(x[((b * H + oy / 2) * W + ox / 2) * C + c], rnd);
+  return nullptr;
+}
+PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int rnd, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x)
+        for (int c = 0; c < C; ++c) {
+          float a = 0.f;
+          for (int dy = 0; dy < 2; ++dy)
+            for (int dx = 0; dx < 2; ++dx) a += gy[((b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C + c];
+          float* p = gx + ((b * H + y) * W + x) * C + c;
+          *p = mr(beta != 0.f ? a + beta * *p : a, rnd);
+        }
+  return nullptr;
+}
+PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream) {
+  for (size_t i = 0; i < n; ++i) dst[i] = rna(src[i]);
+  return nullptr;
+}
+
+PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float*, pb_stream) {
+  const int cpg = C / G;
+  for (int b = 0; b < nb; ++b)
+    for (int g = 0; g < G; ++g) {
+      double s = 0, q = 0;
+      for (int p = 0; p < HW; ++p)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) { const double v = x[((long)b * HW + p) * C + c]; s += v; q += v * v; }
+      const double n = (double)HW * cpg, m = s / n, var = q / n - m * m;
+      mean[b * G + g] = (float)m; rstd[b * G + g] = (float)(1.0 / std::sqrt(var + eps));
+    }
+  return nullptr;
+}
+PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int nb, int HW,
+                 int C, int G, int silu, int rnd, float* y, pb_stream) {
+  const int cpg = C / G;
+  for (long i = 0; i < (long)nb * HW * C; ++i) {
+    const int c = i % C; const long b = i / ((long)HW * C); const int g = c / cpg;
+    float v = gamma[c] * ((x[i] - mean[b * G + g]) * rstd[b * G + g]) + beta[c];
+    if (silu) v = silu_f(v);
+    y[i] = mr(v, rnd);
+  }
+  return nullptr;
+}
+PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW, int C, int G,
+               int silu, const float* t, int nb, int mode, float* out, float acc, int rnd, float*, pb_stream) {
+  const int cpg = C / G;
+  for (long b = 0; b < nb; ++b)
+    for (int g = 0; g < G; ++g) {
+      double s1 = 0, s2 = 0;
+      for (int p = 0; p < HW; ++p)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          const float xh = (xp[(long)p * C + c] - mean[g]) * rstd[g];
+          float u = t[(b * HW + p) * C + c];
+          if (mode == 1) u *= silu ? gamma[c] * silu_d(gamma[c] * xh + beta[c]) : gamma[c];
+          s1 += u; s2 += (double)xh * u;
+        }
+      const float m1 = (float)(s1 / ((double)HW * cpg)), m2 = (float)(s2 / ((double)HW * cpg));
+      for (int p = 0; p < HW; ++p)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          const float xh = (xp[(long)p * C + c] - mean[g]) * rstd[g];
+          const float f = silu ? gamma[c] * silu_d(gamma[c] * xh + beta[c]) : gamma[c];
+          const float tv = t[(b * HW + p) * C + c];
+          float v = mode == 0 ? f * rstd[g] * (tv - m1 - xh * m2) : rstd[g] * (tv * f - m1 - xh * m2);
+          float* o = out + (b * HW + p) * C + c;
+          if (acc != 0.f) v += acc * *o;
+          *o = mr(v, rnd);
+        }
+    }
+  return nullptr;
+}
+PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float* beta, float eps, float* y, float* mean,
+               float* rstd, int rnd, pb_stream) {
+  for (long r = 0; r < rows; ++r) {
+    double s = 0, q = 0;
+    for (int c = 0; c < C; ++c) s += x[r * C + c];
+    const double m = s / C;
+    for (int c = 0; c < C; ++c) q += (x[r * C + c] - m) * (x[r * C + c] - m);
+    const float rs = (float)(1.0 / std::sqrt(q / C + eps));
+    mean[r] = (float)m; rstd[r] = rs;
+    for (int c = 0; c < C; ++c) y[r * C + c] = mr(gamma[c] * ((x[r * C + c] - (float)m) * rs) + beta[c], rnd);
+  }
+  return nullptr;
+}
+PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C, const float* t,
+               int nb, int mode, float* out, float acc, int rnd, pb_stream) {
+  for (long r = 0; r < rows_p * nb; ++r) {
+    const long rp = r % rows_p;
+    double s1 = 0, s2 = 0;
+    for (int c = 0; c < C; ++c) {
+      const float xh = (xp[rp * C + c] - mean[rp]) * rstd[rp];
+      const float u = mode == 1 ? t[r * C + c] * gamma[c] : t[r * C + c];
+      s1 += u; s2 += (double)xh * u;
+    }
+    const float m1 = (float)(s1 / C), m2 = (float)(s2 / C);
+    for (int c = 0; c < C; ++c) {
+      const float xh = (xp[rp * C + c] - mean[rp]) * rstd[rp];
+      float v = mode == 0 ? gamma[c] * rstd[rp] * (t[r * C + c] - m1 - xh * m2) : rstd[rp] * (t[r * C + c] * gamma[c] - m1 - xh * m2);
+      float* o = out + r * C + c;
+      if (acc != 0.f) v += acc * *o;
+      *o = mr(v, rnd);
+    }
+  }
+  return nullptr;
+}
+PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int rnd, pb_stream) {
+  for (long r = 0; r < rows; ++r)
+    for (int c = 0; c < F; ++c) y[r * F + c] = mr(h[r * 2 * F + c] * gelu_f(h[r * 2 * F + F + c]), rnd);
+  return nullptr;
+}
+PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int rnd, pb_stream) {
+  for (long r = 0; r < rows_p * nb; ++r) {
+    const long rp = r % rows_p;
+    for (int c = 0; c < F; ++c) {
+      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c];
+      dy[r * F + c] = mr(dh[r * 2 * F + c] * gelu_f(g) + a * gelu_d(g) * dh[r * 2 * F + F + c], rnd);
+    }
+  }
+  return nullptr;
+}
+PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int rnd, pb_stream) {
+  for (long r = 0; r < rows_p * nb; ++r) {
+    const long rp = r % rows_p;
+    for (int c = 0; c < F; ++c) {
+      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c], y = gy[r * F + c];
+      gh[r * 2 * F + c] = mr(y * gelu_f(g), rnd);
+      gh[r * 2 * F + F + c] = mr(y * a * gelu_d(g), rnd);
+    }
+  }
+  return nullptr;
+}
+PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int rnd, pb_stream) {
+  for (long r = 0; r < rows; ++r) {
+    float* p = S + r * ld;
+    float mx = -INFINITY;
+    for (int c = 0; c < cols; ++c) mx = std::max(mx, p[c]);
+    double s = 0;
+    for (int c = 0; c < cols; ++c) s += std::exp(p[c] - mx);
+    for (int c = 0; c < cols; ++c) p[c] = mr((float)(std::exp(p[c] - mx) / s), rnd);
+    for (long c = cols; c < ld; ++c) p[c] = 0.f;
+  }
+  return nullptr;
+}
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int rnd, pb_stream) {
+  for (long r = 0; r < rows_p * nb; ++r) {
+    const float* p = P + (r % rows_p) * ld;
+    float* d = dS + r * ld;
+    double dot = 0;
+    for (int c = 0; c < cols; ++c) dot += (double)p[c] * d[c];
+    for (int c = 0; c < cols; ++c) d[c] = mr(p[c] * (d[c] - (float)dot), rnd);
+  }
+  return nullptr;
+}
+PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int i = 0; i < N; ++i) {
+        double s = 0;
+        for (int c = 0; c < d; ++c) s += (double)go[(b * N + i) * ldg + h * d + c] * o[(long)i * ldo + h * d + c];
+        delta[(b * H + h) * N + i] = (float)s;
+      }
+  return nullptr;
+}
+PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
+                int col_mode, int rnd, pb_stream) {
+  for (long b = 0; b < nb; ++b)
+    for (int h = 0; h < H; ++h)
+      for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+          const long bh = b * H + h;
+          const float dl = col_mode ? delta[bh * cols + c] : delta[bh * rows + r];
+          float* p = dP + (bh * rows + r) * ld + c;
+          *p = mr(scale * P[((long)h * rows + r) * ld + c] * (*p - dl), rnd);
+        }
+  return nullptr;
+}
+PBK pbk_timestep_embedding(float t, int dim, int flip, float shift, float* out, pb_stream) {
+  const int half = dim / 2;
+  for (int j = 0; j < half; ++j) {
+    const float e = std::exp(-std::log(10000.f) * (float)j / ((float)half - shift));
+    const float a = t * e;
+    if (flip) { out[j] = std::cos(a); out[half + j] = std::sin(a); } else { out[j] = std::sin(a); out[half + j] = std::cos(a); }
+  }
+  return nullptr;
+}
+PBK pbk_gemv(const float* Wm, const float* x, const float* bias, int N, int K, int silu_in, int silu_out, float* y, pb_stream) {
+  for (int n = 0; n < N; ++n) {
+    double s = 0;
+    for (int k = 0; k < K; ++k) s += (double)Wm[(long)n * K + k] * (silu_in ? silu_f(x[k]) : x[k]);
+    float v = (float)s + (bias ? bias[n] : 0.f);
+    y[n] = silu_out ? silu_f(v) : v;
+  }
+  return nullptr;
+}
+PBK pbk_pack_conv3x3(const float* w, int Co, int Ci, float* fwd, float* bwd, int rnd, pb_stream) {
+  for (long co = 0; co < Co; ++co)
+    for (long ci = 0; ci < Ci; ++ci)
+      for (int tap = 0; tap < 9; ++tap) {
+        const float v = mr(w[(co * Ci + ci) * 9 + tap], rnd);
+        if (fwd) fwd[(co * 9 + tap) * Ci + ci] = v;
+        if (bwd) bwd[(ci * 9 + (8 - tap)) * Co + co] = v;
+      }
+  return nullptr;
+}
+
+PBK pbk_gram2(const float* Wm, const float* Vp, int k, long n, double* G, double* M, pb_stream) {
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) {
+      double a = 0, b = 0;
+      for (long c = 0; c < n; ++c) { a += (double)Wm[i * n + c] * Wm[j * n + c]; if (Vp) b += (double)Wm[i * n + c] * Vp[j * n + c]; }
+      G[i * k + j] = a; if (M) M[i * k + j] = b;
+    }
+  return nullptr;
+}
+PBK pbk_jacobi(const double* G, const double* M, int k, float* Rm, float* sv, pb_stream) {
+  std::vector<double> A(G, G + k * k), X(k * k, 0.0);
+  for (int i = 0; i < k; ++i) X[i * k + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0, diag = 0;
+    for (int i = 0; i < k; ++i) for (int j = 0; j < k; ++j) (i == j ? diag : off) += A[i * k + j] * A[i * k + j];
+    if (off <= 1e-30 * diag) break;
+    for (int p = 0; p < k - 1; ++p)
+      for (int q = p + 1; q < k; ++q) {
+        const double apq = A[p * k + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double tau = (A[q * k + q] - A[p * k + p]) / (2.0 * apq);
+        const double t = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c;
+        for (int i = 0; i < k; ++i) {
+          const double aip = A[i * k + p], aiq = A[i * k + q];
+          A[i * k + p] = c * aip - s * aiq; A[i * k + q] = s * aip + c * aiq;
+          const double xip = X[i * k + p], xiq = X[i * k + q];
+          X[i * k + p] = c * xip - s * xiq; X[i * k + q] = s * xip + c * xiq;
+        }
+        for (int i = 0; i < k; ++i) {
+          const double api = A[p * k + i], aqi = A[q * k + i];
+          A[p * k + i] = c * api - s * aqi; A[q * k + i] = s * api + c * aqi;
+        }
+      }
+  }
+  std::vector<int> order(k);
+  for (int i = 0; i < k; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return A[a * k + a] > A[b * k + b]; });
+  for (int i = 0; i < k; ++i) {
+    const int e = order[i];
+    const double l = std::max(A[e * k + e], 1e-300), inv = 1.0 / std::sqrt(l);
+    double dot = 0;
+    if (M) for (int j = 0; j < k; ++j) dot += X[j * k + e] * M[j * k + i];
+    const double sg = (M && dot < 0) ? -1.0 : 1.0;
+    for (int j = 0; j < k; ++j) Rm[i * k + j] = (float)(sg * inv * X[j * k + e]);
+    sv[i] = (float)std::sqrt(std::sqrt(l));
+  }
+  return nullptr;
+}
+PBK pbk_rotate(const float* Wm, const float* Rm, const float* Vp, int k, long n, float atol, float rtol, float* V, float* metrics,
+               pb_stream) {
+  double d2 = 0, viol = 0;
+  for (long c = 0; c < n; ++c)
+    for (int i = 0; i < k; ++i) {
+      float v = 0.f;
+      for (int j = 0; j < k; ++j) v += Rm[i * k + j] * Wm[j * n + c];
+      V[i * n + c] = v;
+      if (Vp) { const float d = v - Vp[i * n + c]; d2 += (double)d * d; if (std::fabs(d) > atol + rtol * std::fabs(v)) viol += 1; }
+    }
+  if (metrics) { metrics[0] = (float)d2; metrics[1] = (float)viol; }
+  return nullptr;
+}

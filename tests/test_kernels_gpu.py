@@ -1,0 +1,274 @@
+"""GPU unit tests of the leaf kernels (pbk_*), each against plain PyTorch fp32/fp64 of the same op.
+The tcgen05 GEMM multiplies TF32-truncated operands with fp32 accumulation; the reference for it is
+an fp64 product of the same truncated operands, so the tolerance only covers accumulation order."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusion_pullback_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False          # the torch references must be true fp32
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _ok(err):
+    assert err is None, err.decode()
+    torch.cuda.synchronize()
+
+
+def tf32_trunc(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def gemm(A, B, D, *, M, N_, K, lda, ldb, ldd, sAb=0, sAh=0, sBb=0, sBh=0, sDb=0, sDh=0, nb=1, nh=1,
+         bias=None, R=None, ldr=0, sRb=0, sRh=0, alpha=1.0, beta=0.0, conv=0, H=0, W=0, seg2=None, rnd=0):
+    g = N.PbGemm()
+    g.M, g.N, g.nseg = M, N_, 1 if seg2 is None else 2
+    s = g.seg[0]
+    s.A, s.lda, s.sAb, s.sAh, s.B, s.ldb, s.sBb, s.sBh, s.K = A.data_ptr(), lda, sAb, sAh, B.data_ptr(), ldb, sBb, sBh, K
+    if seg2 is not None:
+        A2, B2, K2, lda2, ldb2 = seg2
+        s = g.seg[1]
+        s.A, s.lda, s.sAb, s.sAh, s.B, s.ldb, s.sBb, s.sBh, s.K = A2.data_ptr(), lda2, 0, 0, B2.data_ptr(), ldb2, 0, 0, K2
+    g.D, g.ldd, g.sDb, g.sDh = D.data_ptr(), ldd, sDb, sDh
+    g.R = R.data_ptr() if R is not None else None
+    g.ldr, g.sRb, g.sRh = ldr, sRb, sRh
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.alpha, g.beta, g.nb, g.nh, g.conv, g.H, g.W, g.round_tf32 = alpha, beta, nb, nh, conv, H, W, rnd
+    _ok(N.leaf("pbk_gemm")(C.byref(g), _st()))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 32), (256, 64, 64), (300, 200, 96), (64, 40, 40), (1000, 1280, 1280),
+                                    (320, 2560, 1280), (77, 320, 768), (4096, 320, 320), (5, 64, 1000)])
+def test_gemm_plain(M, Nn, K):
+    torch.manual_seed(M + Nn + K)
+    Kp = (K + 3) // 4 * 4
+    A = torch.randn(M, Kp, device="cuda")
+    B = torch.randn(Nn, Kp, device="cuda")
+    Np = (Nn + 3) // 4 * 4
+    bias = torch.randn(Np, device="cuda")
+    R = torch.randn(M, Np, device="cuda")
+    D = torch.full((M, Np), float("nan"), device="cuda")
+    gemm(A, B, D, M=M, N_=Nn, K=K, lda=Kp, ldb=Kp, ldd=Np, bias=bias, R=R, ldr=Np, alpha=0.5, beta=2.0)
+    ref = 0.5 * (tf32_trunc(A)[:, :K].double() @ tf32_trunc(B)[:, :K].double().T) + bias[:Nn].double() + 2.0 * R[:, :Nn].double()
+    assert rel(D[:, :Nn], ref) < 1e-5
+    if Np > Nn:
+        assert torch.isnan(D[:, Nn:]).all()           # columns beyond N untouched
+
+
+def test_gemm_two_segments_and_inplace_residual():
+    torch.manual_seed(0)
+    M, Nn, K1, K2 = 512, 320, 640, 320
+    A1, A2 = torch.randn(M, K1, device="cuda"), torch.randn(M, K2, device="cuda")
+    B = torch.randn(Nn, K1 + K2, device="cuda")
+    D = torch.randn(M, Nn, device="cuda")
+    D0 = D.clone()
+    gemm(A1, B, D, M=M, N_=Nn, K=K1, lda=K1, ldb=K1 + K2, ldd=Nn, R=D, ldr=Nn, beta=1.0,
+         seg2=(A2, B[:, K1:], K2, K2, K1 + K2))
+    ref = tf32_trunc(torch.cat([A1, A2], 1)).double() @ tf32_trunc(B).double().T + D0.double()
+    assert rel(D, ref) < 1e-5
+
+
+@pytest.mark.parametrize("nb,nh,Ntok,d,Nk", [(3, 8, 256, 40, 256), (2, 8, 64, 160, 64), (5, 2, 100, 32, 77), (2, 5, 1024, 64, 1024)])
+def test_gemm_attention_shapes(nb, nh, Ntok, d, Nk):
+    """S[b,h] = scale * Q_b[:, h*d:(h+1)*d] K[:, h*d:(h+1)*d]^T with K broadcast over b (cross/self primal K)."""
+    torch.manual_seed(1)
+    Cc = nh * d
+    Q = torch.randn(nb, Ntok, Cc, device="cuda")
+    Km = torch.randn(Nk, Cc, device="cuda")
+    ld = (Nk + 3) // 4 * 4
+    S = torch.zeros(nb, nh, Ntok, ld, device="cuda")
+    gemm(Q, Km, S, M=Ntok, N_=Nk, K=d, lda=Cc, sAb=Ntok * Cc, sAh=d, ldb=Cc, sBb=0, sBh=d, ldd=ld,
+         sDb=nh * Ntok * ld, sDh=Ntok * ld, nb=nb, nh=nh, alpha=d ** -0.5)
+    q = tf32_trunc(Q).double().view(nb, Ntok, nh, d).permute(0, 2, 1, 3)
+    k = tf32_trunc(Km).double().view(Nk, nh, d).permute(1, 0, 2)
+    ref = torch.einsum("bhid,hjd->bhij", q, k) * d ** -0.5
+    assert rel(S[..., :Nk], ref) < 1e-5
+    # O[b][:, h*d:(h+1)*d] = P[b,h] Vt[h]^T  with Vt [h][d][Nk]
+    Vt = torch.randn(nh, d, ld, device="cuda")
+    O = torch.zeros(nb, Ntok, Cc, device="cuda")
+    gemm(S, Vt, O, M=Ntok, N_=d, K=Nk, lda=ld, sAb=nh * Ntok * ld, sAh=Ntok * ld, ldb=ld, sBh=d * ld, ldd=Cc,
+         sDb=Ntok * Cc, sDh=d, nb=nb, nh=nh)
+    ref = torch.einsum("bhij,hdj->bihd", tf32_trunc(S)[..., :Nk].double(), tf32_trunc(Vt)[..., :Nk].double()).reshape(nb, Ntok, Cc)
+    assert rel(O, ref) < 1e-5
+
+
+@pytest.mark.parametrize("nb,H,W,Ci,Co", [(1, 64, 64, 320, 320), (5, 8, 8, 1280, 1280), (3, 16, 16, 64, 96), (2, 32, 32, 640, 320),
+                                          (5, 4, 4, 64, 64), (1, 2, 2, 32, 32), (2, 12, 12, 64, 64), (1, 96, 96, 32, 64)])
+def test_gemm_conv3x3(nb, H, W, Ci, Co):
+    torch.manual_seed(2)
+    x = torch.randn(nb, H, W, Ci, device="cuda")                      # NHWC
+    w = torch.randn(Co, Ci, 3, 3, device="cuda") / math.sqrt(9 * Ci)
+    bias = torch.randn(Co, device="cuda")
+    fwd = torch.empty(Co, 9, Ci, device="cuda")
+    bwd = torch.empty(Ci, 9, Co, device="cuda")
+    _ok(N.leaf("pbk_pack_conv3x3")(_p(w), Co, Ci, _p(fwd), _p(bwd), 0, _st()))
+    assert torch.equal(fwd, w.permute(0, 2, 3, 1).reshape(Co, 9, Ci))
+    assert torch.equal(bwd, w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, 9, Co))
+    y = torch.zeros(nb, H, W, Co, device="cuda")
+    gemm(x, fwd, y, M=nb * H * W, N_=Co, K=Ci, lda=Ci, ldb=9 * Ci, ldd=Co, nb=nb, conv=1, H=H, W=W, bias=bias)
+    ref = F.conv2d(tf32_trunc(x).double().permute(0, 3, 1, 2), tf32_trunc(w).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(y, ref) < 5e-5                          # fp32 accumulation over K = 9 * Ci up to 11520
+    # transpose conv (bwd-data) through the flipped pack
+    gy = torch.randn(nb, H, W, Co, device="cuda")
+    gx = torch.zeros(nb, H, W, Ci, device="cuda")
+    gemm(gy, bwd, gx, M=nb * H * W, N_=Ci, K=Co, lda=Co, ldb=9 * Co, ldd=Ci, nb=nb, conv=1, H=H, W=W)
+    ref = F.conv_transpose2d(tf32_trunc(gy).double().permute(0, 3, 1, 2), tf32_trunc(w).double(), padding=1).permute(0, 2, 3, 1)
+    assert rel(gx, ref) < 5e-5
+
+
+def test_groupnorm_fwd_and_lin():
+    torch.manual_seed(3)
+    nb, HW, Cc, G = 3, 256, 320, 32
+    x = torch.randn(1, HW, Cc, device="cuda") * 2 + 0.5
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    mean, rstd = torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
+    tmp = torch.empty(nb * (Cc + G) * 2 + 16, device="cuda")
+    _ok(N.leaf("pbk_gn_stats")(_p(x), 1, HW, Cc, G, C.c_float(1e-5), _p(mean), _p(rstd), _p(tmp), _st()))
+    y = torch.empty_like(x)
+    for silu in (0, 1):
+        _ok(N.leaf("pbk_gn_apply")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), 1, HW, Cc, G, silu, 0, _p(y), _st()))
+
+        def f(z):
+            o = F.group_norm(z.permute(0, 2, 1), G, gamma, beta, 1e-5).permute(0, 2, 1)
+            return F.silu(o) if silu else o
+        assert rel(y, f(x)) < 1e-5
+        t = torch.randn(nb, HW, Cc, device="cuda")
+        out = torch.empty_like(t)
+        _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t), nb, 0, _p(out),
+                                 C.c_float(0), 0, _p(tmp), _st()))
+        ref = torch.cat([torch.func.jvp(f, (x,), (t[i:i + 1],))[1] for i in range(nb)])
+        assert rel(out, ref) < 2e-5
+        _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t), nb, 1, _p(out),
+                                 C.c_float(0), 0, _p(tmp), _st()))
+        ref = torch.cat([torch.func.vjp(f, x)[1](t[i:i + 1])[0] for i in range(nb)])
+        assert rel(out, ref) < 2e-5
+
+
+def test_layernorm_geglu_softmax():
+    torch.manual_seed(4)
+    nb, rows, Cc = 3, 200, 320
+    x = torch.randn(rows, Cc, device="cuda") + 0.3
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    y, mean, rstd = torch.empty_like(x), torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    _ok(N.leaf("pbk_ln_fwd")(_p(x), C.c_long(rows), Cc, _p(gamma), _p(beta), C.c_float(1e-5), _p(y), _p(mean), _p(rstd), 0, _st()))
+    f = lambda z: F.layer_norm(z, (Cc,), gamma, beta, 1e-5)
+    assert rel(y, f(x)) < 1e-5
+    t = torch.randn(nb, rows, Cc, device="cuda")
+    out = torch.empty_like(t)
+    for mode in (0, 1):
+        _ok(N.leaf("pbk_ln_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), C.c_long(rows), Cc, _p(t), nb, mode, _p(out), C.c_float(0), 0, _st()))
+        if mode == 0:
+            ref = torch.stack([torch.func.jvp(f, (x,), (t[i],))[1] for i in range(nb)])
+        else:
+            ref = torch.stack([torch.func.vjp(f, x)[1](t[i])[0] for i in range(nb)])
+        assert rel(out, ref) < 2e-5
+    # GEGLU
+    Fd = 4 * Cc
+    h = torch.randn(rows, 2 * Fd, device="cuda")
+    g = lambda z: z[..., :Fd] * F.gelu(z[..., Fd:])
+    yy = torch.empty(rows, Fd, device="cuda")
+    _ok(N.leaf("pbk_geglu_fwd")(_p(h), C.c_long(rows), Fd, _p(yy), 0, _st()))
+    assert rel(yy, g(h)) < 1e-5
+    dh = torch.randn(nb, rows, 2 * Fd, device="cuda")
+    dy = torch.empty(nb, rows, Fd, device="cuda")
+    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), 0, _st()))
+    assert rel(dy, torch.stack([torch.func.jvp(g, (h,), (dh[i],))[1] for i in range(nb)])) < 2e-5
+    gy = torch.randn(nb, rows, Fd, device="cuda")
+    gh = torch.empty(nb, rows, 2 * Fd, device="cuda")
+    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), 0, _st()))
+    assert rel(gh, torch.stack([torch.func.vjp(g, h)[1](gy[i])[0] for i in range(nb)])) < 2e-5
+    # softmax + its linearisation, short (warp) and long (block) rows
+    for cols in (77, 256, 4096):
+        ld = (cols + 3) // 4 * 4
+        S = torch.randn(rows, ld, device="cuda") * 3
+        P = S.clone()
+        _ok(N.leaf("pbk_softmax_fwd")(_p(P), C.c_long(rows), cols, C.c_long(ld), 0, _st()))
+        sm = lambda z: torch.softmax(z, -1)
+        assert rel(P[:, :cols], sm(S[:, :cols])) < 1e-5
+        dS = torch.randn(nb, rows, ld, device="cuda")
+        ref = torch.stack([torch.func.jvp(sm, (S[:, :cols],), (dS[i, :, :cols],))[1] for i in range(nb)])
+        _ok(N.leaf("pbk_softmax_lin")(_p(P), C.c_long(rows), _p(dS), nb, cols, C.c_long(ld), 0, _st()))
+        assert rel(dS[..., :cols], ref) < 2e-5
+
+
+def test_data_movement():
+    torch.manual_seed(5)
+    nb, H, W, Cc = 2, 8, 8, 64
+    x = torch.randn(nb, H, W, Cc, device="cuda")
+    y = torch.empty(nb, 2 * H, 2 * W, Cc, device="cuda")
+    _ok(N.leaf("pbk_upsample2x")(_p(x), nb, H, W, Cc, _p(y), 0, _st()))
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+    gx = torch.empty_like(x)
+    _ok(N.leaf("pbk_upsample2x_vjp")(_p(y), nb, H, W, Cc, _p(gx), C.c_float(0), 0, _st()))
+    assert rel(gx, 4 * x) < 1e-6
+    for pad in (1, 0):                                 # SD pad 1 / DDPM (0,1,0,1) pad
+        Ho = Wo = H // 2
+        col = torch.empty(nb, Ho, Wo, 9, Cc, device="cuda")
+        _ok(N.leaf("pbk_im2col_s2")(_p(x), nb, H, W, Cc, pad, Ho, Wo, _p(col), 0, _st()))
+        xp = x.permute(0, 3, 1, 2)
+        xp = F.pad(xp, (1, 1, 1, 1)) if pad else F.pad(xp, (0, 1, 0, 1))
+        ref = F.unfold(xp, 3, stride=2).view(nb, Cc, 9, Ho, Wo).permute(0, 3, 4, 2, 1)
+        assert torch.equal(col, ref.contiguous())
+        g = torch.randn_like(col)
+        gx = torch.empty_like(x)
+        _ok(N.leaf("pbk_col2im_s2")(_p(g), nb, H, W, Cc, pad, Ho, Wo, _p(gx), C.c_float(0), 0, _st()))
+        fold = F.fold(g.permute(0, 4, 3, 1, 2).reshape(nb, Cc * 9, Ho * Wo), (H + 2 * pad if pad else H + 1,) * 2, 3, stride=2)
+        fold = fold[:, :, 1:-1, 1:-1] if pad else fold[:, :, :-1, :-1]
+        assert rel(gx, fold.permute(0, 2, 3, 1)) < 1e-6
+    # transpose (V^T per head) and strided copy
+    src = torch.randn(3, 100, 48, device="cuda")
+    dst = torch.zeros(3, 48, 104, device="cuda")
+    _ok(N.leaf("pbk_transpose")(_p(dst), C.c_long(104), C.c_long(48 * 104), C.c_long(0), _p(src), C.c_long(48), C.c_long(100 * 48),
+                                C.c_long(0), 3, 1, 100, 48, C.c_float(0), 0, _st()))
+    assert torch.equal(dst[:, :, :100], src.transpose(1, 2))
+    # thin direct convs (conv_in and its transpose)
+    xi = torch.randn(nb, H, W, 4, device="cuda")
+    w = torch.randn(32, 4, 3, 3, device="cuda")
+    b = torch.randn(32, device="cuda")
+    fwd, bwd = torch.empty(32, 9, 4, device="cuda"), torch.empty(4, 9, 32, device="cuda")
+    _ok(N.leaf("pbk_pack_conv3x3")(_p(w), 32, 4, _p(fwd), _p(bwd), 0, _st()))
+    yo = torch.empty(nb, H, W, 32, device="cuda")
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, 4, _p(fwd), _p(b), 32, _p(yo), C.c_float(0), _st()))
+    assert rel(yo, F.conv2d(xi.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)) < 1e-5
+    go = torch.randn(nb, H, W, 32, device="cuda")
+    gi = torch.empty(nb, H, W, 4, device="cuda")
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, 32, _p(bwd), None, 4, _p(gi), C.c_float(0), _st()))
+    assert rel(gi, F.conv_transpose2d(go.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)) < 1e-5
+
+
+def test_orthonormalize_matches_svd():
+    torch.manual_seed(6)
+    for k, n in ((5, 16384), (16, 16384), (2, 196608), (50, 4096)):
+        Wm = torch.randn(k, n, device="cuda") * torch.linspace(3, 0.5, k, device="cuda")[:, None]
+        Vp = torch.linalg.svd(Wm + 0.01 * torch.randn_like(Wm), full_matrices=False)[2].contiguous()
+        G, M = torch.empty(k, k, dtype=torch.float64, device="cuda"), torch.empty(k, k, dtype=torch.float64, device="cuda")
+        Rm, sv, V, met = (torch.empty(k, k, device="cuda"), torch.empty(k, device="cuda"), torch.empty(k, n, device="cuda"),
+                          torch.empty(2, device="cuda"))
+        _ok(N.leaf("pbk_gram2")(_p(Wm), _p(Vp), k, C.c_long(n), _p(G), _p(M), _st()))
+        _ok(N.leaf("pbk_jacobi")(_p(G), _p(M), k, _p(Rm), _p(sv), _st()))
+        _ok(N.leaf("pbk_rotate")(_p(Wm), _p(Rm), _p(Vp), k, C.c_long(n), C.c_float(1e-4), C.c_float(1e-5), _p(V), _p(met), _st()))
+        _, s, Vh = torch.linalg.svd(Wm.double(), full_matrices=False)
+        assert torch.allclose(sv.double(), s.sqrt(), rtol=1e-5)
+        cos = (V.double() * Vh).sum(1).abs()
+        assert float(cos.min()) > 1 - 1e-6
+        assert torch.allclose(V @ V.T, torch.eye(k, device="cuda"), atol=1e-5)
+        assert float((V * Vp).sum(1).min()) > 0          # sign continuity with Vprev
+        assert abs(float(met[0]) - float((V - Vp).pow(2).sum())) < 1e-3 * float((V - Vp).pow(2).sum()) + 1e-6
