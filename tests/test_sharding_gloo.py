@@ -1,0 +1,67 @@
+"""World-size-2 gloo test (CPU) of the N > 1 host logic: problems dealt round-robin, one all-gather of (s, vT)."""
+import ctypes as C
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffusion_pullback_b200.sharding import gather_results, shard_problems
+
+
+def _solve(problem, L):
+    from diffusion_pullback_b200.engine import PullbackEngine, unet_config
+    from oracle import unet_torch as UT
+    m = UT.build_unet("uncond_tiny")
+    x, t, _ = UT.synthetic_inputs("uncond_tiny", seed=1234 + problem)
+    eng = PullbackEngine(unet_config(m), 32, 32, "mid", 0, 2, 0, "cpu", _lib=L)
+    eng.bind(m.state_dict())
+    eng.set_point(x, float(t), None)
+    g = torch.Generator().manual_seed(problem)
+    q, _ = torch.linalg.qr(torch.randn(eng.n_in, 2, generator=g))
+    u, s, vT, _ = eng.pullback(q.T.contiguous(), 2, 2, 0.0)
+    return s, vT
+
+
+def _worker(rank, world, port, n_problems, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.hostsim.build import build
+    L = C.CDLL(build())
+    mine = shard_problems(n_problems, rank, world)
+    local = [(p,) + _solve(p, L) for p in mine]
+    allr = gather_results(local, n_problems, 2, 3 * 32 * 32, "cpu")
+    if rank == 0:
+        q.put({k: (v[0], v[1]) for k, v in allr.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_problems_covers_everything_once():
+    for n in (0, 1, 3, 8, 10):
+        for w in (1, 2, 4, 8):
+            got = sorted(i for r in range(w) for i in shard_problems(n, r, w))
+            assert got == list(range(n))
+            sizes = [len(shard_problems(n, r, w)) for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_two_ranks_gather_all_problems():
+    from tests.hostsim.build import build
+    build()
+    n_problems, world = 3, 2                                  # ragged: rank 0 solves 2, rank 1 solves 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_problems, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [0, 1, 2]
+    L = C.CDLL(build())
+    for p in range(n_problems):
+        s, vT = _solve(p, L)
+        assert torch.allclose(res[p][0], s, rtol=1e-5) and torch.allclose(res[p][1].abs(), vT.abs(), atol=1e-5)
