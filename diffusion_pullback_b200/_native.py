@@ -53,6 +53,15 @@ class PbGemm(C.Structure):
                 ("round_tf32", C.c_int), ("precise", C.c_int)]
 
 
+class PbAttnLin(C.Structure):
+    _fields_ = [("Mr", C.c_int), ("Nc", C.c_int), ("d", C.c_int), ("nb", C.c_int), ("nh", C.c_int), ("nseg", C.c_int),
+                ("seg", PbGemmSeg * 2), ("alpha1", C.c_float), ("alpha2", C.c_float), ("beta", C.c_float),
+                ("Pm", C.c_void_p), ("ldp", C.c_long), ("sPh", C.c_long), ("delta", C.c_void_p), ("delta_mode", C.c_int),
+                ("want_rsum", C.c_int), ("O", C.c_void_p), ("ldo", C.c_long), ("C1", C.c_void_p), ("ldc", C.c_long),
+                ("sCh", C.c_long), ("D", C.c_void_p), ("ldd", C.c_long), ("sDb", C.c_long), ("R", C.c_void_p),
+                ("ldr", C.c_long), ("sRb", C.c_long), ("round_tf32", C.c_int)]
+
+
 _lib = None
 _raw = None
 

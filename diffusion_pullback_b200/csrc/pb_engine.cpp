@@ -89,6 +89,7 @@ struct pb_handle {
   int rnd_p = 1, rnd_t = 1, rnd_w = 1;      // primal activations / tangents / packed weights
   int prec_p = 0, prec_t = 0, prec_a = 0;   // primal GEMMs / tangent weight GEMMs / tangent attention GEMMs
   int rnd = 1;                              // rounding flag of the pass being interpreted
+  int fused_min_tokens = 512;               // self-attention layers with >= this many tokens use the fused kernel
   std::string err;
   long launches = 0;
   // CUDA graph of one iteration (jvp + vjp + orthonormalise)
@@ -446,11 +447,39 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   return PB_OK;
 }
 
+bool use_fused(const pb_handle* h, const Op& o) {
+  return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
+}
+
 int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
   float* P = h->CP(o.P_off); float* Vt = h->CP(o.Vt_off);
   float* dS = h->WP(h->w_s1);
   const long sS = (long)hd * N * ldk;
+  if (use_fused(h, o)) {
+    // dO = P dV (plain GEMM)  then  dO += [P o dS] V - rowsum(P o dS) o O  with dS = (dQ K^T + Q dK^T)/sqrt(d) never stored
+    const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
+    float* dVt = h->WP(h->w_s3);
+    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dqkv + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f, h->rnd, st));
+    PbGemm g = plain_gemm(P, ldk, N, dVt, ldk, d, Nk, h->T(o.y), C);
+    g.seg[0].sAh = (long)N * ldk; g.seg[0].sBb = (long)C * ldk; g.seg[0].sBh = (long)d * ldk;
+    g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    PbAttnLin a{};
+    a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 2;
+    a.seg[0].A = dqkv; a.seg[0].lda = 3 * C; a.seg[0].sAb = (long)N * 3 * C; a.seg[0].sAh = d;
+    a.seg[0].B = qkv + C; a.seg[0].ldb = 3 * C; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.seg[1].A = qkv; a.seg[1].lda = 3 * C; a.seg[1].sAb = 0; a.seg[1].sAh = d;
+    a.seg[1].B = dqkv + C; a.seg[1].ldb = 3 * C; a.seg[1].sBb = (long)N * 3 * C; a.seg[1].sBh = d;
+    a.alpha1 = o.scale; a.alpha2 = 1.f; a.beta = 1.f;
+    a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
+    a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
+    a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
+    a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C; a.R = h->T(o.y); a.ldr = C; a.sRb = (long)N * C;
+    a.round_tf32 = h->rnd;
+    CK(pbk_attn_lin(&a, st));
+    return PB_OK;
+  }
   if (o.cross) {
     const float* kv = h->CP(o.bias_eff_off);
     PbGemm g = plain_gemm(h->T(o.x), C, N, kv, 2 * C, Nk, d, dS, ldk);
@@ -491,6 +520,43 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const long sS = (long)hd * N * ldk;
   const float* V; long ldkv;
   if (o.cross) { V = h->CP(o.bias_eff_off) + C; ldkv = 2 * C; } else { V = h->P(o.x) + 2 * C; ldkv = 3 * C; }
+  if (use_fused(h, o)) {
+    float* gx = h->T(o.x); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
+    float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
+    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));           // delta = rowsum(Obar o O)
+    PbAttnLin a{};
+    // Qbar = scale * [P o (Obar V^T - delta_row)] K
+    a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
+    a.seg[0].A = gO; a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
+    a.seg[0].B = V; a.seg[0].ldb = ldkv; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.alpha1 = 1.f; a.alpha2 = o.scale;
+    a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
+    a.delta = delta; a.delta_mode = 1;
+    a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
+    a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
+    a.round_tf32 = h->rnd;
+    CK(pbk_attn_lin(&a, st));
+    // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q     (rows = keys, columns = queries)
+    PbAttnLin b{};
+    b.Mr = Nk; b.Nc = N; b.d = d; b.nb = nb; b.nh = hd; b.nseg = 1;
+    b.seg[0].A = V; b.seg[0].lda = ldkv; b.seg[0].sAb = 0; b.seg[0].sAh = d;
+    b.seg[0].B = gO; b.seg[0].ldb = C; b.seg[0].sBb = (long)N * C; b.seg[0].sBh = d;
+    b.alpha1 = 1.f; b.alpha2 = o.scale;
+    b.Pm = Pt; b.ldp = ldq; b.sPh = (long)Nk * ldq;
+    b.delta = delta; b.delta_mode = 2;
+    b.C1 = Qt; b.ldc = ldq; b.sCh = (long)d * ldq;
+    b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
+    b.round_tf32 = h->rnd;
+    CK(pbk_attn_lin(&b, st));
+    // Vbar = P^T Obar
+    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
+    PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, 3 * C);
+    g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
+    g.sDb = (long)N * 3 * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
+    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    h->vals[o.x].ginit = true;
+    return PB_OK;
+  }
   {                                                                                // dP = gO V^T
     PbGemm g = plain_gemm(gO, C, N, V, ldkv, Nk, d, gS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
@@ -824,7 +890,8 @@ PB_API int pb_set_option(pb_handle* h, const char* name, int value) {
   if (!h || !name) return PB_EINVAL;
   struct { const char* n; int* p; bool rebind; } opts[] = {
       {"round_primal", &h->rnd_p, false}, {"round_tangent", &h->rnd_t, false}, {"round_weights", &h->rnd_w, true},
-      {"precise_primal", &h->prec_p, false}, {"precise_tangent", &h->prec_t, false}, {"precise_attn", &h->prec_a, false}};
+      {"precise_primal", &h->prec_p, false}, {"precise_tangent", &h->prec_t, false}, {"precise_attn", &h->prec_a, false},
+      {"fused_min_tokens", &h->fused_min_tokens, false}};
   for (auto& o : opts)
     if (!strcmp(name, o.n)) {
       *o.p = value; drop_graph(h); h->point = false;

@@ -93,6 +93,27 @@ PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, 
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
                 int col_mode, int round_tf32, pb_stream st);
 
+// ---- fused attention linearisation (no N x N tangent in HBM); implemented in pb_attn_sm100.cu ----
+// Per (b, h), rows r in [0, Mr), score columns c in [0, Nc), head dim d (head h occupies columns [h*d, (h+1)*d) of A/B/D/R/O):
+//   S[r][c]  = alpha1 * sum_seg  A_seg[b][r][h*d + :] . B_seg[b][c][h*d + :]         (batch / head strides as in PbGemmSeg)
+//   T[r][c]  = Pm[h][r][c] * (S[r][c] - delta),  delta = 0 | delta[b][h][r] (mode 1) | delta[b][h][c] (mode 2)
+//   D[b][r][h*d + n] = alpha2 * sum_c T[r][c] * C1[h][n][c]  -  (want_rsum ? rowsum_c(T[r][:]) * O[r][h*d + n] : 0)
+//                      + beta * R[b][r][h*d + n]
+struct PbAttnLin {
+  int Mr, Nc, d, nb, nh, nseg;
+  PbGemmSeg seg[2];                 // seg[i].K is ignored (K = d)
+  float alpha1, alpha2, beta;
+  const float* Pm; long ldp, sPh;   // [nh][Mr][ldp]
+  const float* delta; int delta_mode;
+  int want_rsum; const float* O; long ldo;
+  const float* C1; long ldc, sCh;   // [nh][d][ldc]
+  float* D; long ldd, sDb;
+  const float* R; long ldr, sRb;
+  int round_tf32;
+};
+PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
+PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);
+
 // ---- time embedding (primal only) ----
 PBK pbk_timestep_embedding(float t, int dim, int flip_sin_to_cos, float freq_shift, float* out, pb_stream st);
 // y = act_out(W[N][K] . act_in(x) + bias); act flags: 1 = SiLU

@@ -353,6 +353,44 @@ PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int 
         }
   return nullptr;
 }
+PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
+  if (d % 4 || d < 8 || d > 64) return "attn_lin: head dim must be a multiple of 4 in [8, 64]";
+  return nullptr;
+}
+PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
+  const PbAttnLin& a = *ap;
+  for (long b = 0; b < a.nb; ++b)
+    for (long h = 0; h < a.nh; ++h) {
+#pragma omp parallel for schedule(static)
+      for (int r = 0; r < a.Mr; ++r) {
+        std::vector<float> T(a.Nc);
+        double rs = 0;
+        for (int c = 0; c < a.Nc; ++c) {
+          float s = 0.f;
+          for (int sg = 0; sg < a.nseg; ++sg) {
+            const float* A = a.seg[sg].A + b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
+            const float* B = a.seg[sg].B + b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
+            for (int k = 0; k < a.d; ++k) s += trunc_tf32(A[k]) * trunc_tf32(B[k]);
+          }
+          float dl = 0.f;
+          if (a.delta && a.delta_mode == 1) dl = a.delta[(b * a.nh + h) * a.Mr + r];
+          if (a.delta && a.delta_mode == 2) dl = a.delta[(b * a.nh + h) * a.Nc + c];
+          T[c] = rna(a.Pm[h * a.sPh + (long)r * a.ldp + c] * (a.alpha1 * s - dl));
+          rs += T[c];
+        }
+        for (int n = 0; n < a.d; ++n) {
+          double acc = 0;
+          const float* C1 = a.C1 + h * a.sCh + (long)n * a.ldc;
+          for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * trunc_tf32(C1[c]);
+          float v = a.alpha2 * (float)acc;
+          if (a.want_rsum && a.O) v -= (float)rs * a.O[(long)r * a.ldo + h * a.d + n];
+          if (a.R) v += a.beta * a.R[b * a.sRb + (long)r * a.ldr + h * a.d + n];
+          a.D[b * a.sDb + (long)r * a.ldd + h * a.d + n] = mr(v, a.round_tf32);
+        }
+      }
+    }
+  return nullptr;
+}
 PBK pbk_timestep_embedding(float t, int dim, int flip, float shift, float* out, pb_stream) {
   const int half = dim / 2;
   for (int j = 0; j < half; ++j) {

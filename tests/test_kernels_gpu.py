@@ -272,3 +272,51 @@ def test_orthonormalize_matches_svd():
         assert torch.allclose(V @ V.T, torch.eye(k, device="cuda"), atol=1e-5)
         assert float((V * Vp).sum(1).min()) > 0          # sign continuity with Vprev
         assert abs(float(met[0]) - float((V - Vp).pow(2).sum())) < 1e-3 * float((V - Vp).pow(2).sum()) + 1e-6
+
+
+@pytest.mark.parametrize("Mr,Nc,d,nb,nh,nseg,mode", [(256, 256, 40, 2, 2, 2, 0), (200, 333, 16, 1, 3, 1, 1), (384, 128, 64, 2, 2, 1, 2),
+                                                       (1024, 1024, 40, 3, 8, 2, 0), (128, 640, 32, 2, 1, 2, 1), (4096, 4096, 40, 1, 2, 2, 0)])
+def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode):
+    """D = alpha2 * [Pm o (alpha1 * sum_seg A B^T - delta)] C1^T - rowsum(.) o O + beta * R   (PbAttnLin)."""
+    torch.manual_seed(7)
+    Cc = nh * d
+    ldp = (Nc + 3) // 4 * 4
+    A0 = torch.randn(nb, Mr, Cc, device="cuda"); B0 = torch.randn(Nc, Cc, device="cuda")          # tangent x primal
+    A1 = torch.randn(Mr, Cc, device="cuda"); B1 = torch.randn(nb, Nc, Cc, device="cuda")          # primal x tangent
+    Pm = torch.softmax(torch.randn(nh, Mr, ldp, device="cuda") * 2, -1).contiguous()
+    C1 = torch.randn(nh, d, ldp, device="cuda")
+    O = torch.randn(Mr, Cc, device="cuda"); R = torch.randn(nb, Mr, Cc, device="cuda")
+    delta = torch.randn(nb, nh, Mr if mode == 1 else Nc, device="cuda") if mode else None
+    D = R.clone()
+    a = N.PbAttnLin()
+    a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, nb, nh, nseg
+    s0 = a.seg[0]
+    s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = A0.data_ptr(), Cc, Mr * Cc, d, B0.data_ptr(), Cc, 0, d
+    s1 = a.seg[1]
+    s1.A, s1.lda, s1.sAb, s1.sAh, s1.B, s1.ldb, s1.sBb, s1.sBh = A1.data_ptr(), Cc, 0, d, B1.data_ptr(), Cc, Nc * Cc, d
+    a.alpha1, a.alpha2, a.beta = d ** -0.5, 0.7, 1.0
+    a.Pm, a.ldp, a.sPh = Pm.data_ptr(), ldp, Mr * ldp
+    a.delta, a.delta_mode = (delta.data_ptr() if mode else None), mode
+    a.want_rsum, a.O, a.ldo = int(mode == 0), O.data_ptr(), Cc
+    a.C1, a.ldc, a.sCh = C1.data_ptr(), ldp, d * ldp
+    a.D, a.ldd, a.sDb, a.R, a.ldr, a.sRb, a.round_tf32 = D.data_ptr(), Cc, Mr * Cc, D.data_ptr(), Cc, Mr * Cc, 0
+    _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+    t = lambda z: tf32_trunc(z).double()
+    S = torch.einsum("bihd,jhd->bhij", t(A0).view(nb, Mr, nh, d), t(B0).view(Nc, nh, d))
+    if nseg == 2:
+        S = S + torch.einsum("ihd,bjhd->bhij", t(A1).view(Mr, nh, d), t(B1).view(nb, Nc, nh, d))
+    S = S * d ** -0.5
+    if mode == 1:
+        S = S - delta.double()[..., :, None]
+    if mode == 2:
+        S = S - delta.double()[..., None, :]
+    T = Pm.double()[None, :, :, :Nc] * S
+    # the kernel RNA-rounds T to TF32 before the second contraction
+    Tr = T.float()
+    Tr = ((Tr.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).double()
+    acc = torch.einsum("bhij,hnj->bihn", Tr, t(C1)[..., :Nc]).reshape(nb, Mr, Cc)
+    ref = 0.7 * acc + R.double()
+    if mode == 0:
+        rs = Tr.sum(-1)                                               # [nb, nh, Mr]
+        ref = ref - (rs.permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
+    assert rel(D, ref) < 2e-4, rel(D, ref)                            # a few T elements round the other way (fp32 vs fp64 S)
