@@ -1,10 +1,11 @@
 // Fused attention-linearisation kernel for sm_100a (tcgen05 + TMEM + TMA): the tangent / cotangent of
 // softmax attention without ever materialising the N x N score tangent in HBM.
 //
-// Per (tangent b, head h) and 128-row tile, looping over 128-column tiles j of the score matrix:
+// Per (tangent b, head h) and 128-row tile, looping over 64-column steps j of the score matrix (2-deep pipeline):
 //     S   = alpha1 * sum_seg A_seg[rows] . B_seg[cols_j]^T                (tcgen05.mma kind::tf32, K = head dim, -> TMEM)
-//     T   = Pm[rows, cols_j] o (S - delta)                                 (CUDA cores: tcgen05.ld, P from L2/HBM, RNA round)
-//     Acc += T . C1[cols_j]                                                (tcgen05.mma, A = T staged in swizzled smem, -> TMEM)
+//     T   = Pm[rows, cols_j] o (S - delta)                                 (CUDA cores: tcgen05.ld; the P tile arrives by TMA in
+//                                                                          the swizzled A-operand layout and is overwritten in place)
+//     Acc += T . C1[cols_j]                                                (tcgen05.mma, A = T in swizzled smem, -> TMEM)
 //     r   += rowsum(T)
 // and finally  D[rows] = alpha2 * Acc - r o O[rows] + beta * R[rows].
 // With (A, B, Pm, delta, C1) chosen by the engine this is
@@ -31,20 +32,21 @@ const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, lon
 namespace pbattn {
 using namespace pbtc;
 
-constexpr int TILE = 128;              // rows and columns of one score tile
+constexpr int TM = 128;                // score-tile rows per CTA
+constexpr int TN = 64;                 // score-tile columns per pipeline step
 constexpr int BK = 32;                 // fp32 per 128-byte swizzle row
-constexpr int KT_BYTES = TILE * BK * 4;   // one [128 x 32] k-block tile: 16 KB
+constexpr int NST = 2;                 // pipeline depth of every streamed operand
+constexpr int A_KT = TM * BK * 4;      // [128 x 32] k-block tile: 16 KB
+constexpr int B_KT = TN * BK * 4;      // [ 64 x 32] k-block tile:  8 KB
 constexpr int NTHREADS = 320;
-constexpr int NCOMPUTE = 256;
 
 struct alignas(64) Params {
-  CUtensorMap mapA[2], mapB[2], mapC;
+  CUtensorMap mapA[2], mapB[2], mapC, mapP;
   int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2];
-  uint32_t a_bytes, b_bytes, c_bytes;  // bytes per stage fill
+  uint32_t a_bytes, b_bytes, c_bytes, p_bytes;   // bytes per barrier phase
   int nseg, kbd, dpad, d;              // k-blocks over the head dim, accumulator width (multiple of 16)
   int Mr, Nc, nb, nh;
   float alpha1, alpha2, beta;
-  const float* Pm; long ldp, sPh;
   const float* delta; int delta_mode;
   int want_rsum; const float* O; long ldo;
   float* D; long ldd, sDb;
@@ -52,45 +54,52 @@ struct alignas(64) Params {
   int round_tf32;
 };
 
-// smem: [A: nseg*kbd tiles][B: nseg*kbd tiles][C1: 4 k-blocks of dpad rows][T: 4 tiles][rsum 2 x 128 floats][barriers]
-__host__ __device__ inline int smem_a_bytes(int nseg, int kbd) { return nseg * kbd * KT_BYTES; }
-__host__ __device__ inline int smem_c_bytes(int dpad) { return 4 * dpad * BK * 4; }
+__host__ __device__ inline int smem_a_bytes(int nseg, int kbd) { return nseg * kbd * A_KT; }
+__host__ __device__ inline int smem_b_bytes(int nseg, int kbd) { return nseg * kbd * B_KT; }
+__host__ __device__ inline int smem_c_bytes(int dpad) { return (TN / BK) * dpad * BK * 4; }
+constexpr int PT_BYTES = (TN / BK) * A_KT;       // P in / T out, in place: 32 KB per stage
 
+// smem: [A resident][B x NST][C1 x NST][P/T x NST][rsum 2 x 128 floats][barriers]
 __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int ab = smem_a_bytes(p.nseg, p.kbd);
+  const int bbytes = smem_b_bytes(p.nseg, p.kbd), cbytes = smem_c_bytes(p.dpad);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + ab;
-  uint8_t* sC = sB + ab;
-  uint8_t* sT = sC + smem_c_bytes(p.dpad);
-  float* s_rsum = reinterpret_cast<float*>(sT + 4 * KT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rsum + 2 * TILE);
+  uint8_t* sB = sA + smem_a_bytes(p.nseg, p.kbd);
+  uint8_t* sC = sB + NST * bbytes;
+  uint8_t* sPT = sC + NST * cbytes;
+  float* s_rsum = reinterpret_cast<float*>(sPT + NST * PT_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rsum + 2 * TM);
   uint64_t* a_full = bars + 0;
-  uint64_t* b_full = bars + 1;
-  uint64_t* b_empty = bars + 2;
-  uint64_t* c_full = bars + 3;
-  uint64_t* c_empty = bars + 4;
-  uint64_t* s_full = bars + 5;     // [2]
-  uint64_t* s_free = bars + 7;     // [2]
-  uint64_t* t_full = bars + 9;
-  uint64_t* t_empty = bars + 10;
-  uint64_t* acc_full = bars + 11;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* acc_full = bars + 1;
+  uint64_t* b_full = bars + 2;       // each of the following: [NST]
+  uint64_t* b_empty = bars + 4;
+  uint64_t* c_full = bars + 6;
+  uint64_t* c_empty = bars + 8;
+  uint64_t* p_full = bars + 10;
+  uint64_t* pt_empty = bars + 12;
+  uint64_t* s_full = bars + 14;
+  uint64_t* s_free = bars + 16;
+  uint64_t* t_full = bars + 18;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * TILE;
-  const int bat_h = blockIdx.y % p.nh, bat_b = blockIdx.y / p.nh;
-  const int nj = (p.Nc + TILE - 1) / TILE;
+  const int r0 = blockIdx.x * TM;
+  // tangents fastest: the nb CTAs that share one head's P rows run back to back, so P comes from L2 for all but the first
+  const int bat_b = blockIdx.y % p.nb, bat_h = blockIdx.y / p.nb;
+  const int nj = (p.Nc + TN - 1) / TN;
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 1); mbar_init(b_full, 1); mbar_init(b_empty, 1); mbar_init(c_full, 1); mbar_init(c_empty, 1);
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&s_free[0], 8); mbar_init(&s_free[1], 8);
-    mbar_init(t_full, 8); mbar_init(t_empty, 1); mbar_init(acc_full, 1);
+    mbar_init(a_full, 1); mbar_init(acc_full, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1);
+      mbar_init(&p_full[i], 1); mbar_init(&pt_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
+      mbar_init(&t_full[i], 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(512)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(256)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -98,8 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
-  const uint32_t tm_acc = tmem_base + 256;
+  const uint32_t tm_acc = tmem_base + NST * TN;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -107,56 +115,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       mbar_arrive_expect_tx(a_full, p.a_bytes);
       for (int s = 0; s < p.nseg; ++s)
         for (int kb = 0; kb < p.kbd; ++kb)
-          tma_load_4d(sA + (s * p.kbd + kb) * KT_BYTES, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+          tma_load_4d(sA + (s * p.kbd + kb) * A_KT, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
       for (int j = 0; j < nj; ++j) {
-        const int c0 = j * TILE;
-        mbar_wait(b_empty, (j & 1) ^ 1);
-        mbar_arrive_expect_tx(b_full, p.b_bytes);
+        const int c0 = j * TN, st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&b_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
         for (int s = 0; s < p.nseg; ++s)
           for (int kb = 0; kb < p.kbd; ++kb)
-            tma_load_4d(sB + (s * p.kbd + kb) * KT_BYTES, &p.mapB[s], b_full, kb * BK, c0, bat_h * p.b_hmul[s], bat_b * p.b_bmul[s]);
-        mbar_wait(c_empty, (j & 1) ^ 1);
-        mbar_arrive_expect_tx(c_full, p.c_bytes);
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_4d(sC + kb * p.dpad * BK * 4, &p.mapC, c_full, c0 + kb * BK, 0, bat_h, 0);
+            tma_load_4d(sB + st * bbytes + (s * p.kbd + kb) * B_KT, &p.mapB[s], &b_full[st], kb * BK, c0, bat_h * p.b_hmul[s],
+                        bat_b * p.b_bmul[s]);
+        mbar_wait(&pt_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&p_full[st], p.p_bytes);
+        for (int kb = 0; kb < TN / BK; ++kb)
+          tma_load_4d(sPT + st * PT_BYTES + kb * A_KT, &p.mapP, &p_full[st], c0 + kb * BK, r0, bat_h, 0);
+        mbar_wait(&c_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&c_full[st], p.c_bytes);
+        for (int kb = 0; kb < TN / BK; ++kb)
+          tma_load_4d(sC + st * cbytes + kb * p.dpad * BK * 4, &p.mapC, &c_full[st], c0 + kb * BK, 0, bat_h, 0);
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TILE >> 3) << 17) | (uint32_t(TILE >> 4) << 24);
-      const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TILE >> 4) << 24);
+      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+      const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
       auto do_acc = [&](int jj) {
-        mbar_wait(c_full, jj & 1);
-        mbar_wait(t_full, jj & 1);
+        const int st = jj & 1;
+        const uint32_t ph = (jj >> 1) & 1;
+        mbar_wait(&c_full[st], ph);
+        mbar_wait(&t_full[st], ph);
         tcgen05_fence_after();
-        for (int kb = 0; kb < 4; ++kb) {
-          const uint64_t adesc = make_smem_desc(smem_u32(sT + kb * KT_BYTES));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sC + kb * p.dpad * BK * 4));
+        for (int kb = 0; kb < TN / BK; ++kb) {
+          const uint64_t adesc = make_smem_desc(smem_u32(sPT + st * PT_BYTES + kb * A_KT));
+          const uint64_t bdesc = make_smem_desc(smem_u32(sC + st * cbytes + kb * p.dpad * BK * 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k) mma_tf32(tm_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, (jj | kb | k) ? 1u : 0u);
         }
-        tcgen05_commit(c_empty);
-        tcgen05_commit(t_empty);
+        tcgen05_commit(&c_empty[st]);
+        tcgen05_commit(&pt_empty[st]);
       };
       mbar_wait(a_full, 0);
       for (int j = 0; j < nj; ++j) {
-        mbar_wait(b_full, j & 1);
-        mbar_wait(&s_free[j & 1], ((j >> 1) & 1) ^ 1);
+        const int st = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&b_full[st], ph);
+        mbar_wait(&s_free[st], ph ^ 1);
         tcgen05_fence_after();
         bool first = true;
         for (int s = 0; s < p.nseg; ++s)
           for (int kb = 0; kb < p.kbd; ++kb) {
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + (s * p.kbd + kb) * KT_BYTES));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + (s * p.kbd + kb) * KT_BYTES));
+            const uint64_t adesc = make_smem_desc(smem_u32(sA + (s * p.kbd + kb) * A_KT));
+            const uint64_t bdesc = make_smem_desc(smem_u32(sB + st * bbytes + (s * p.kbd + kb) * B_KT));
             const int nk = min(4, (p.d - kb * BK + 7) / 8);     // columns past d are TMA zero fill: skip those MMAs
             for (int k = 0; k < nk; ++k) {
-              mma_tf32(tm_s[j & 1], adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, first ? 0u : 1u);
+              mma_tf32(tmem_base + st * TN, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, first ? 0u : 1u);
               first = false;
             }
           }
-        tcgen05_commit(b_empty);
-        tcgen05_commit(&s_full[j & 1]);
+        tcgen05_commit(&b_empty[st]);
+        tcgen05_commit(&s_full[st]);
         if (j > 0) do_acc(j - 1);
       }
       do_acc(nj - 1);
@@ -166,69 +184,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     // =========================== compute warps ===========================
     const int cw = warp - 2;                  // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
-    const int hh = cw >> 2;                   // column half
+    const int hh = cw >> 2;                   // which 32-column k-block of the 64-column step this warp owns
     const int row = q * 32 + lane;            // tile row
     const int r = r0 + row;
     const bool row_ok = r < p.Mr;
-    const float* prow = p.Pm + bat_h * p.sPh + (long)(row_ok ? r : 0) * p.ldp;
     const float* dbase = p.delta ? p.delta + ((long)bat_b * p.nh + bat_h) * (p.delta_mode == 1 ? p.Mr : p.Nc) : nullptr;
     const float drow = (dbase && p.delta_mode == 1 && row_ok) ? dbase[r] : 0.f;
+    const uint32_t tm_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(hh * 32);
     float rsum = 0.f;
     for (int j = 0; j < nj; ++j) {
-      const int cbase = j * TILE + hh * 64;
-      // P for this thread's 64 columns: issued before waiting on the tensor core
-      float4 pv[16];
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const int cbase = j * TN + hh * 32;
+      float dcol[32];
+      if (p.delta_mode == 2) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int c = cbase + 4 * i;
-        if (row_ok && c + 3 < p.Nc) pv[i] = *reinterpret_cast<const float4*>(prow + c);
-        else {
-          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row_ok) {
-            if (c < p.Nc) pv[i].x = prow[c];
-            if (c + 1 < p.Nc) pv[i].y = prow[c + 1];
-            if (c + 2 < p.Nc) pv[i].z = prow[c + 2];
-          }
-        }
+        for (int i = 0; i < 32; ++i) dcol[i] = (cbase + i < p.Nc) ? dbase[cbase + i] : 0.f;
       }
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      uint8_t* tb = sPT + st * PT_BYTES + hh * A_KT + row * 128;
+      mbar_wait(&p_full[st], ph);
+      float4 pv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(tb + ((i ^ (row & 7)) << 4));
+      mbar_wait(&s_full[st], ph);
       tcgen05_fence_after();
-      uint32_t sv[2][32];
-      tmem_ld32(tm_s[j & 1] + (uint32_t(q * 32) << 16) + uint32_t(hh * 64), sv[0]);
-      tmem_ld32(tm_s[j & 1] + (uint32_t(q * 32) << 16) + uint32_t(hh * 64 + 32), sv[1]);
+      uint32_t sv[32];
+      tmem_ld32(tm_row + st * TN, sv);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[j & 1]);
-      mbar_wait(t_empty, (j & 1) ^ 1);
+      if (lane == 0) mbar_arrive(&s_free[st]);
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint8_t* tb = sT + (hh * 2 + ch) * KT_BYTES + row * 128;
+      for (int i = 0; i < 8; ++i) {
+        const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
+        float o[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 pq = pv[ch * 8 + i];
-          const float pp[4] = {pq.x, pq.y, pq.z, pq.w};
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = cbase + ch * 32 + i * 4 + e;
-            float dl = drow;
-            if (p.delta_mode == 2) dl = (c < p.Nc) ? dbase[c] : 0.f;
-            const float t = pp[e] * (p.alpha1 * __uint_as_float(sv[ch][i * 4 + e]) - dl);
-            o[e] = rna_tf32(t);
-            rsum += o[e];
-          }
-          *reinterpret_cast<float4*>(tb + ((i ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e) {
+          const float dl = p.delta_mode == 2 ? dcol[i * 4 + e] : drow;
+          const float t = pp[e] * (p.alpha1 * __uint_as_float(sv[i * 4 + e]) - dl);
+          o[e] = rna_tf32(t);
+          rsum += o[e];
         }
+        *reinterpret_cast<float4*>(tb + ((i ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_full);
+      if (lane == 0) mbar_arrive(&t_full[st]);
     }
     // ---- epilogue: D = alpha2 * Acc - rsum o O + beta * R ----
-    s_rsum[hh * TILE + row] = rsum;
+    s_rsum[hh * TM + row] = rsum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (hh == 0) {
-      const float rs = p.want_rsum ? s_rsum[row] + s_rsum[TILE + row] : 0.f;
+      const float rs = p.want_rsum ? s_rsum[row] + s_rsum[TM + row] : 0.f;
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();
       float* dptr = p.D + (long)bat_b * p.sDb + (long)(row_ok ? r : 0) * p.ldd + bat_h * p.d;
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 
@@ -283,7 +289,6 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.nseg = a.nseg; p.d = a.d; p.kbd = (a.d + BK - 1) / BK; p.dpad = (a.d + 15) / 16 * 16;
   p.Mr = a.Mr; p.Nc = a.Nc; p.nb = a.nb; p.nh = a.nh;
   p.alpha1 = a.alpha1; p.alpha2 = a.alpha2; p.beta = a.R ? a.beta : 0.f;
-  p.Pm = a.Pm; p.ldp = a.ldp; p.sPh = a.sPh;
   p.delta = a.delta; p.delta_mode = a.delta ? a.delta_mode : 0;
   p.want_rsum = a.want_rsum; p.O = a.O; p.ldo = a.ldo;
   p.D = a.D; p.ldd = a.ldd; p.sDb = a.sDb; p.R = a.R; p.ldr = a.ldr; p.sRb = a.sRb; p.round_tf32 = a.round_tf32;
@@ -295,9 +300,9 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   for (int s = 0; s < a.nseg; ++s) {
     const PbGemmSeg& sg = a.seg[s];
     uint32_t ab, bb;
-    if (const char* e = pbgemm::encode_plain(&p.mapA[s], sg.A, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, TILE, &p.a_hmul[s],
+    if (const char* e = pbgemm::encode_plain(&p.mapA[s], sg.A, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, TM, &p.a_hmul[s],
                                               &p.a_bmul[s], &ab)) return e;
-    if (const char* e = pbgemm::encode_plain(&p.mapB[s], sg.B, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, TILE, &p.b_hmul[s],
+    if (const char* e = pbgemm::encode_plain(&p.mapB[s], sg.B, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, TN, &p.b_hmul[s],
                                               &p.b_bmul[s], &bb)) return e;
     abytes += ab * p.kbd; bbytes += bb * p.kbd;
   }
@@ -308,17 +313,24 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     uint64_t stb[3] = {uint64_t(a.ldc) * 4, uint64_t(a.sCh) * 4, uint64_t(a.sCh) * 4 * a.nh};
     uint32_t box[4] = {uint32_t(BK), uint32_t(a.d), 1, 1};
     if (const char* e = pbgemm::encode4(&p.mapC, a.C1, dims, stb, box)) return e;
-    p.c_bytes = 4u * uint32_t(a.d) * BK * 4;
+    p.c_bytes = uint32_t(TN / BK) * uint32_t(a.d) * BK * 4;
   }
-  const int smem = 2 * smem_a_bytes(p.nseg, p.kbd) + smem_c_bytes(p.dpad) + 4 * KT_BYTES + 2 * TILE * 4 + 128 + 1024;
-  static int configured = 0;
-  if (configured < smem) {
+  {
+    // Pm: [nh][Mr][ldp]; box = [32 columns] x [128 rows]
+    int hm, bm; uint32_t pb;
+    if (const char* e = pbgemm::encode_plain(&p.mapP, a.Pm, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, TM, &hm, &bm, &pb)) return e;
+    p.p_bytes = pb * (TN / BK);
+  }
+  const int smem = smem_a_bytes(p.nseg, p.kbd) + NST * (smem_b_bytes(p.nseg, p.kbd) + smem_c_bytes(p.dpad) + PT_BYTES) + 2 * TM * 4 +
+                   256 + 1024;
+  static bool configured = false;
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = 227 * 1024;
+    configured = true;
   }
   if (smem > 227 * 1024) return "attn_lin: shared memory budget exceeded";
-  dim3 grid((a.Mr + TILE - 1) / TILE, a.nb * a.nh);
+  dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
   attn_lin_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(st)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -160,7 +160,7 @@ struct Planner {
     o.x = x; o.y = y; o.eps = eps; o.silu = silu; o.groups = G;
     o.gamma = vec(p + ".weight", h->vals[x].C); o.beta = vec(p + ".bias", h->vals[x].C);
     o.mean_off = cache_alloc(G); o.rstd_off = cache_alloc(G);
-    h->n_gn = std::max(h->n_gn, (size_t)(h->vals[x].C + G) * 2);
+    h->n_gn = std::max(h->n_gn, std::max(pbk_gn_tmp_floats((int)vx.rows, vx.C, G, h->kmax), pbk_gn_tmp_floats((int)vx.rows, vx.C, G, 1)));
     return y;
   }
   int ln(int x, const std::string& p) {
@@ -928,7 +928,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->n_out = h->vals[h->out_val].rows * h->vals[h->out_val].C;
   const size_t K = k_max;
   h->w_s1 = p.work_alloc(h->n_s1 * K); h->w_s2 = p.work_alloc(h->n_s2 * K); h->w_s3 = p.work_alloc(h->n_s3 * K);
-  h->w_delta = p.work_alloc(h->n_delta * K); h->w_gn = p.work_alloc(h->n_gn * K + 64);
+  h->w_delta = p.work_alloc(h->n_delta * K); h->w_gn = p.work_alloc(h->n_gn + 64);
   h->w_V = p.work_alloc(K * h->n_in); h->w_Vprev = p.work_alloc(K * h->n_in); h->w_W = p.work_alloc(K * h->n_in);
   h->w_U = p.work_alloc(K * h->n_out);
   h->w_G = p.work_alloc(2 * K * K); h->w_M = p.work_alloc(2 * K * K); h->w_R = p.work_alloc(K * K);

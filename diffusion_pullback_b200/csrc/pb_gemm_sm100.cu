@@ -34,6 +34,7 @@ struct alignas(64) Params {
   int nseg, taps, conv_ctot;
   int M, N, nb, nh;
   int conv, H, W, bw, bh, bb, tiles_w, tiles_h;
+  int raster_b, mt, nt;
   float* D; const float* R; const float* bias;
   long ldd, sDb, sDh, ldr, sRb, sRh;
   float alpha, beta;
@@ -51,8 +52,8 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // + barriers + 1024B alignment slack
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_constant__ Params p) {
+template <int BN, int STAGES, int OCC>
+__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = Smem<BN, STAGES>;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates ----
-  const int n0 = blockIdx.x * BN;
+  int n0 = blockIdx.x * BN;
   int m0 = 0, bat_b = 0, bat_h = 0;          // plain mode
   int cx0 = 0, cy0 = 0, cb0 = 0;             // conv mode tile origin
   if (p.conv) {
@@ -73,6 +74,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h; t /= p.tiles_h;
     cx0 = tw * p.bw; cy0 = th * p.bh; cb0 = t * p.bb;
+  } else if (p.raster_b) {
+    // 1-D launch, tangent index fastest: the nb CTAs that read the same broadcast A tile (attention probabilities)
+    // are adjacent in launch order, so A comes from HBM once and from L2 nb - 1 times
+    int t = blockIdx.x;
+    bat_b = t % p.nb; t /= p.nb;
+    n0 = (t % p.nt) * BN; t /= p.nt;
+    m0 = (t % p.mt) * BM;
+    bat_h = t / p.mt;
   } else {
     m0 = blockIdx.y * BM;
     bat_h = blockIdx.z % p.nh;
@@ -85,10 +94,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_base_smem)),
-                 "r"(BN)
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -291,17 +301,18 @@ const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, lon
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OCC>
 static const char* launch_t(const Params& p, dim3 grid, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
+  static_assert(S::TOTAL * OCC <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  gemm_tf32_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(p);
+  gemm_tf32_kernel<BN, STAGES, OCC><<<grid, NTHREADS, S::TOTAL, st>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
@@ -309,6 +320,12 @@ static const char* launch_t(const Params& p, dim3 grid, cudaStream_t st) {
 }  // namespace pbgemm
 
 extern "C" __attribute__((visibility("default"))) void pb_gemm_set_tmap_tf32(int on) { pbgemm::g_tmap_dtype_tf32 = on; }
+
+// tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic) / CTAs per SM (1 or 2)
+static int g_force_bn = 0, g_occ = 2, g_use160 = 0;
+extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int occ, int use160) {
+  g_force_bn = force_bn; g_occ = occ; g_use160 = use160;
+}
 
 // Returns nullptr on success, else a static error string.  Stream-ordered, no host sync.
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
@@ -325,7 +342,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       (g.R && (reinterpret_cast<uintptr_t>(g.R) & 15)) || (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)))
     return "gemm: D/R/bias must be 16-byte aligned with ld % 4 == 0";
 
-  // tile width: 64 for narrow outputs or when 128-wide tiles cannot fill the machine
+  // tile width: 160 when it divides N (every SD channel count is a multiple of 160: no padded columns), 64 for narrow
+  // outputs or when wider tiles cannot fill the machine, else 128
   int BN = 128;
   long mt = g.conv ? 0 : (long)((g.M + BM - 1) / BM) * g.nb * g.nh;
   if (g.conv) {
@@ -339,7 +357,9 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   } else {
     p.taps = 1;
   }
-  if (g.N <= 64 || mt * ((g.N + 127) / 128) < 148) BN = 64;
+  if (g_use160 && g.N % 160 == 0 && mt * (g.N / 160) >= 148) BN = 160;
+  else if (g.N <= 64 || mt * ((g.N + 127) / 128) < 148) BN = 64;
+  if (g_force_bn) BN = g_force_bn;
 
   int ktot = 0;
   for (int s = 0; s < g.nseg; ++s) {
@@ -375,7 +395,20 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   ktot *= p.taps;
   dim3 grid((g.N + BN - 1) / BN, g.conv ? (unsigned)mt : (unsigned)((g.M + BM - 1) / BM),
             g.conv ? 1 : (unsigned)(g.nb * g.nh));
+  if (!g.conv && g.nb > 1 && g.seg[0].sAb == 0 && (g.nseg == 1 || g.seg[1].sAb == 0)) {
+    p.raster_b = 1; p.nt = (int)grid.x; p.mt = (int)grid.y;
+    grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+  }
   const bool shallow = ktot <= 6;
-  if (BN == 128) return shallow ? launch_t<128, 2>(p, grid, st) : launch_t<128, 6>(p, grid, st);
-  return shallow ? launch_t<64, 2>(p, grid, st) : launch_t<64, 8>(p, grid, st);
+  const bool occ2 = g_occ >= 2;
+  if (BN == 160) {
+    if (shallow) return launch_t<160, 2, 2>(p, grid, st);
+    return occ2 ? launch_t<160, 3, 2>(p, grid, st) : launch_t<160, 6, 1>(p, grid, st);
+  }
+  if (BN == 128) {
+    if (shallow) return launch_t<128, 2, 2>(p, grid, st);
+    return occ2 ? launch_t<128, 3, 2>(p, grid, st) : launch_t<128, 6, 1>(p, grid, st);
+  }
+  if (shallow) return launch_t<64, 2, 2>(p, grid, st);
+  return occ2 ? launch_t<64, 4, 2>(p, grid, st) : launch_t<64, 8, 1>(p, grid, st);
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <vector>
 
@@ -335,49 +336,83 @@ __global__ void gn_sums_k(const float* __restrict__ xp, const float* __restrict_
     }
   }
   __syncthreads();
+  // per-chunk partials, combined in a fixed order by the finalize kernels (no atomics: runs are bit-reproducible)
+  float* part = sums + ((long)blockIdx.x * gridDim.y + b) * C * 2;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < R; ++r) s += sh[(long)r * C * 2 + i];
-    atomicAdd(sums + (long)b * C * 2 + i, s);
+    part[i] = s;
   }
 }
 
-__global__ void gn_finalize_fwd_k(const float* __restrict__ x, const float* __restrict__ sums, int HW, int C, int G,
-                                  float eps, float* __restrict__ mean, float* __restrict__ rstd) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
+// deterministic block reduction of two doubles (blockDim.x = 128)
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[2 * w] = a; sh[2 * w + 1] = b; }
+  __syncthreads();
+  a = sh[0] + sh[2] + sh[4] + sh[6];
+  b = sh[1] + sh[3] + sh[5] + sh[7];
+}
+
+// one block (128 threads) per (image, group): sums the per-chunk partials in a fixed order
+__global__ void gn_finalize_fwd_k(const float* __restrict__ x, const float* __restrict__ part, int chunks, int nb, int HW,
+                                  int C, int G, float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+  __shared__ double sh[8];
+  __shared__ double s_mg;
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
   const double n = HW;
-  double msum = 0.0;
-  for (int i = 0; i < cpg; ++i) {
+  // pass 1: group mean from per-channel pivoted sums
+  double msum = 0.0, dummy = 0.0;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
     const int c = g * cpg + i;
-    msum += (double)x[(long)b * HW * C + c] + (double)sums[((long)b * C + c) * 2] / n;
+    double s1 = 0.0;
+    for (int k = 0; k < chunks; ++k) s1 += part[(((long)k * nb + b) * C + c) * 2];
+    msum += (double)x[(long)b * HW * C + c] + s1 / n;
   }
-  const double mg = msum / cpg;
-  double m2 = 0.0;
-  for (int i = 0; i < cpg; ++i) {
+  block_sum2(msum, dummy, sh);
+  if (threadIdx.x == 0) s_mg = msum / cpg;
+  __syncthreads();
+  const double mg = s_mg;
+  double m2 = 0.0; dummy = 0.0;
+  for (int i = threadIdx.x; i < cpg; i += blockDim.x) {
     const int c = g * cpg + i;
-    const double s1 = sums[((long)b * C + c) * 2], s2 = sums[((long)b * C + c) * 2 + 1];
+    double s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+      s1 += part[(((long)k * nb + b) * C + c) * 2];
+      s2 += part[(((long)k * nb + b) * C + c) * 2 + 1];
+    }
     const double mc = (double)x[(long)b * HW * C + c] + s1 / n;
     m2 += (s2 - s1 * s1 / n) + n * (mc - mg) * (mc - mg);
   }
-  const double var = m2 / (n * cpg);
-  mean[b * G + g] = (float)mg;
-  rstd[b * G + g] = (float)(1.0 / sqrt(var + (double)eps));
+  __syncthreads();
+  block_sum2(m2, dummy, sh);
+  if (threadIdx.x == 0) {
+    const double var = m2 / (n * cpg);
+    mean[b * G + g] = (float)mg;
+    rstd[b * G + g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 // tmp[b][g] = (mean_g(u), mean_g(xhat*u))
-__global__ void gn_finalize_lin_k(const float* __restrict__ sums, int HW, int C, int G, float* __restrict__ tmp) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
+__global__ void gn_finalize_lin_k(const float* __restrict__ part, int chunks, int nb, int HW, int C, int G,
+                                  float* __restrict__ tmp) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
   double s1 = 0, s2 = 0;
-  for (int i = 0; i < cpg; ++i) {
-    s1 += sums[((long)b * C + g * cpg + i) * 2];
-    s2 += sums[((long)b * C + g * cpg + i) * 2 + 1];
+  for (int i = threadIdx.x; i < cpg * chunks; i += blockDim.x) {
+    const int k = i / cpg, c = g * cpg + i % cpg;
+    s1 += part[(((long)k * nb + b) * C + c) * 2];
+    s2 += part[(((long)k * nb + b) * C + c) * 2 + 1];
   }
-  const double n = (double)HW * cpg;
-  tmp[((long)b * G + g) * 2] = (float)(s1 / n);
-  tmp[((long)b * G + g) * 2 + 1] = (float)(s2 / n);
+  block_sum2(s1, s2, sh);
+  if (threadIdx.x == 0) {
+    const double n = (double)HW * cpg;
+    tmp[((long)b * G + g) * 2] = (float)(s1 / n);
+    tmp[((long)b * G + g) * 2 + 1] = (float)(s2 / n);
+  }
 }
 
 __global__ void gn_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
@@ -805,7 +840,13 @@ PBK pbk_graph_destroy(void* graph_exec) {
   return cuda_err(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)));
 }
 
-PBK pbk_gemm(const PbGemm* g, pb_stream st) { return pb_gemm_launch(*g, S(st)); }
+PBK pbk_gemm(const PbGemm* g, pb_stream st) {
+  static const bool trace = getenv("PB_TRACE_GEMM") != nullptr;     // shape log for scripts/bench_gemm.py
+  if (trace)
+    printf("GEMM M=%d N=%d K0=%d K1=%d nseg=%d nb=%d nh=%d conv=%d H=%d W=%d res=%d\n", g->M, g->N, g->seg[0].K,
+           g->nseg > 1 ? g->seg[1].K : 0, g->nseg, g->nb, g->nh, g->conv, g->H, g->W, g->R != nullptr);
+  return pb_gemm_launch(*g, S(st));
+}
 
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
                        float* y, float beta, pb_stream st) {
@@ -872,38 +913,45 @@ PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {
 }
 
 // ---- GroupNorm ----
+// floats of scratch pbk_gn_stats / pbk_gn_lin need: per-chunk partials + finalized group means
+static int gn_chunks(int HW, int C, int nb) {
+  const GnGeom g = gn_geom(C);
+  int chunks = std::max(1, std::min((HW + g.R - 1) / g.R, (kSMs * 4 + nb - 1) / nb));
+  const int ppb = (HW + chunks - 1) / chunks;
+  return (HW + ppb - 1) / ppb;
+}
+extern "C" __attribute__((visibility("default"))) size_t pbk_gn_tmp_floats(int HW, int C, int G, int nb) {
+  return (size_t)gn_chunks(HW, C, nb) * nb * C * 2 + (size_t)nb * G * 2 + 16;
+}
 static const char* gn_launch_sums(int mode, const float* xp, const float* mean, const float* rstd, const float* gamma,
                                   const float* beta, int HW, int C, int G, int silu, const float* t, int nb,
-                                  float* sums, cudaStream_t st) {
+                                  float* part, int* chunks_out, cudaStream_t st) {
   if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
   const GnGeom g = gn_geom(C);
   if (g.QPT > GN_MAX_QPT) return "groupnorm: channel count not supported (too many quads per thread)";
   const int block = g.TP * g.R;
   const size_t shmem = (size_t)g.R * C * 2 * sizeof(float);
-  // enough blocks to cover the machine, but at least R pixels each
-  int chunks = std::max(1, std::min((HW + g.R - 1) / g.R, (kSMs * 4 + nb - 1) / nb));
+  const int chunks = gn_chunks(HW, C, nb);
   const int ppb = (HW + chunks - 1) / chunks;
-  chunks = (HW + ppb - 1) / ppb;
+  *chunks_out = chunks;
   dim3 grid(chunks, nb);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)nb * C * 2 * sizeof(float), st);
-  if (e != cudaSuccess) return cuda_err(e);
   if (shmem > 48 * 1024) {
     if (mode == 0) cudaFuncSetAttribute(gn_sums_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
     if (mode == 1) cudaFuncSetAttribute(gn_sums_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
     if (mode == 2) cudaFuncSetAttribute(gn_sums_k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem);
   }
-  if (mode == 0) gn_sums_k<0><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
-  else if (mode == 1) gn_sums_k<1><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
-  else gn_sums_k<2><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, sums);
+  if (mode == 0) gn_sums_k<0><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, part);
+  else if (mode == 1) gn_sums_k<1><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, part);
+  else gn_sums_k<2><<<grid, block, shmem, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.TP, g.QPT, g.R, ppb, part);
   return last_err();
 }
 
 PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float* tmp,
                  pb_stream st) {
-  if (G > 1024) return "groupnorm: too many groups";
-  if (const char* e = gn_launch_sums(0, x, nullptr, nullptr, nullptr, nullptr, HW, C, G, 0, nullptr, nb, tmp, S(st)))
+  int chunks = 0;
+  if (const char* e = gn_launch_sums(0, x, nullptr, nullptr, nullptr, nullptr, HW, C, G, 0, nullptr, nb, tmp, &chunks, S(st)))
     return e;
-  gn_finalize_fwd_k<<<nb, ((G + 31) / 32) * 32, 0, S(st)>>>(x, tmp, HW, C, G, eps, mean, rstd);
+  gn_finalize_fwd_k<<<nb * G, 128, 0, S(st)>>>(x, tmp, chunks, nb, HW, C, G, eps, mean, rstd);
   return last_err();
 }
 PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int nb,
@@ -916,11 +964,12 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
                float* tmp, pb_stream st) {
-  float* sums = tmp;                                  // [nb][C][2]
-  tmp = tmp + (size_t)nb * C * 2;                     // [nb][G][2]
-  if (const char* e = gn_launch_sums(mode ? 2 : 1, xp, mean, rstd, gamma, beta, HW, C, G, silu, t, nb, sums, S(st)))
+  int chunks = 0;
+  float* part = tmp;
+  if (const char* e = gn_launch_sums(mode ? 2 : 1, xp, mean, rstd, gamma, beta, HW, C, G, silu, t, nb, part, &chunks, S(st)))
     return e;
-  gn_finalize_lin_k<<<nb, ((G + 31) / 32) * 32, 0, S(st)>>>(sums, HW, C, G, tmp);
+  tmp = tmp + (size_t)chunks * nb * C * 2;            // [nb][G][2]
+  gn_finalize_lin_k<<<nb * G, 128, 0, S(st)>>>(part, chunks, nb, HW, C, G, tmp);
   const long total4 = (long)nb * HW * (C / 4);
   if (mode == 0)
     gn_apply_lin_k<0><<<grid_for(total4, 256, 16), 256, 0, S(st)>>>(xp, mean, rstd, gamma, beta, tmp, total4, HW, C, G,

@@ -55,7 +55,8 @@ PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, 
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
 
 // ---- GroupNorm (+ optional SiLU) ----
-// tmp: nb*C*2 floats of scratch
+// tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch (per-chunk partial sums, combined in a fixed order)
+extern "C" __attribute__((visibility("default"))) size_t pbk_gn_tmp_floats(int HW, int C, int G, int nb);
 PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float* tmp,
                  pb_stream st);
 PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const float* gamma, const float* beta, int nb,
@@ -63,7 +64,7 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 // Linearisation of y = act(gamma * xhat + beta) around the cached primal xp (one image, [HW][C]).
 //   mode 0 (JVP): out = act'(.) * gamma * rstd * (t - mean_g(t) - xhat * mean_g(xhat * t))
 //   mode 1 (VJP): g = t * act'(.) * gamma ; out = rstd * (g - mean_g(g) - xhat * mean_g(xhat * g))
-// out = result + acc * out.  tmp: nb*(C+G)*2 floats of scratch.
+// out = result + acc * out.  tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch.
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
                float* tmp, pb_stream st);

@@ -198,6 +198,7 @@ PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream) {
   return nullptr;
 }
 
+extern "C" __attribute__((visibility("default"))) size_t pbk_gn_tmp_floats(int, int, int, int) { return 16; }
 PBK pbk_gn_stats(const float* x, int nb, int HW, int C, int G, float eps, float* mean, float* rstd, float*, pb_stream) {
   const int cpg = C / G;
   for (int b = 0; b < nb; ++b)
