@@ -50,7 +50,8 @@ class PbGemm(C.Structure):
                 ("R", C.c_void_p), ("ldr", C.c_long), ("sRb", C.c_long), ("sRh", C.c_long),
                 ("bias", C.c_void_p), ("alpha", C.c_float), ("beta", C.c_float),
                 ("nb", C.c_int), ("nh", C.c_int), ("conv", C.c_int), ("H", C.c_int), ("W", C.c_int),
-                ("round_tf32", C.c_int), ("precise", C.c_int)]
+                ("round_tf32", C.c_int), ("precise", C.c_int),
+                ("ws", C.c_void_p), ("ws_floats", C.c_long)]
 
 
 class PbAttnLin(C.Structure):

@@ -27,6 +27,8 @@
 namespace {
 
 constexpr size_t kAlign = 256;
+constexpr size_t kSplitFloats = size_t(8) << 20;   // split-K partial tiles (32 MB)
+
 inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
 inline int round4(int v) { return (v + 3) / 4 * 4; }
 
@@ -81,6 +83,7 @@ struct pb_handle {
   size_t w_s1 = 0, w_s2 = 0, w_s3 = 0, w_delta = 0, w_gn = 0;
   size_t w_V = 0, w_Vprev = 0, w_W = 0, w_U = 0, w_G = 0, w_M = 0, w_R = 0, w_sv = 0, w_met = 0, w_x = 0;
   size_t n_s1 = 0, n_s2 = 0, n_s3 = 0, n_delta = 0, n_gn = 0;   // floats per tangent
+  size_t w_splitk = 0, n_splitk = 0;
   char* packed = nullptr; char* cache = nullptr; char* work = nullptr;
   int in_val = -1, out_val = -1;
   long n_in = 0, n_out = 0;
@@ -369,6 +372,12 @@ struct Planner {
     if (e__) return fail(h, PB_ECUDA, std::string(#call ": ") + e__); \
   } while (0)
 
+// every GEMM gets the handle's split-K scratch (partial tiles of the K-split tail wave)
+const char* gemm_call(const pb_handle* h, PbGemm& g, pb_stream st) {
+  g.ws = h->WP(h->w_splitk); g.ws_floats = (long)h->n_splitk;
+  return pbk_gemm(&g, st);
+}
+
 PbGemm plain_gemm(const float* A, long lda, long M, const float* B, long ldb, int N, int K, float* D, long ldd) {
   PbGemm g = pb_gemm_init();
   g.M = (int)M; g.N = N;
@@ -388,7 +397,7 @@ int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
   if (o.res >= 0) { g.R = primal ? h->P(o.res) : h->T(o.res); g.ldr = vy.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = primal ? h->prec_p : h->prec_t;
-  CK(pbk_gemm(&g, st));
+  CK(gemm_call(h, g, st));
   return PB_OK;
 }
 // gx (+)= gy (*) W^T ; gres (+)= gy
@@ -399,7 +408,7 @@ int run_gemm_bwd(pb_handle* h, const Op& o, int nb, pb_stream st) {
   if (vx.ginit) { g.R = h->T(o.x); g.ldr = vx.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = h->prec_t;
-  CK(pbk_gemm(&g, st));
+  CK(gemm_call(h, g, st));
   vx.ginit = true;
   if (o.res >= 0) {
     Val& vr = h->vals[o.res];
@@ -420,7 +429,7 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
     PbGemm g = plain_gemm(ctx, h->cfg.cross_attention_dim, Nk, h->Wf(o.kv), h->cfg.cross_attention_dim, 2 * C,
                           h->cfg.cross_attention_dim, kv, 2 * C);
     g.round_tf32 = h->rnd;
-    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_p; CK(gemm_call(h, g, st));
     Q = h->P(o.x); ldq_ = C; K = kv; V = kv + C; ldkv = 2 * C;
   } else {
     Q = h->P(o.x); K = Q + C; V = Q + 2 * C; ldq_ = ldkv = 3 * C;
@@ -429,7 +438,7 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   {
     PbGemm g = plain_gemm(Q, ldq_, N, K, ldkv, Nk, d, P, ldk);
     g.seg[0].sAh = d; g.seg[0].sBh = d; g.sDh = (long)N * ldk; g.nh = hd; g.alpha = o.scale;
-    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_p; CK(gemm_call(h, g, st));
   }
   CK(pbk_softmax_fwd(P, (long)hd * N, Nk, ldk, h->rnd, st));
   float* Vt = h->CP(o.Vt_off); float* Kt = h->CP(o.Kt_off);
@@ -442,7 +451,7 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   {
     PbGemm g = plain_gemm(P, ldk, N, Vt, ldk, d, Nk, h->P(o.y), C);
     g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk; g.sDh = d; g.nh = hd; g.round_tf32 = h->rnd;
-    g.precise = h->prec_p; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_p; CK(gemm_call(h, g, st));
   }
   return PB_OK;
 }
@@ -464,7 +473,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(P, ldk, N, dVt, ldk, d, Nk, h->T(o.y), C);
     g.seg[0].sAh = (long)N * ldk; g.seg[0].sBb = (long)C * ldk; g.seg[0].sBh = (long)d * ldk;
     g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
     PbAttnLin a{};
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 2;
     a.seg[0].A = dqkv; a.seg[0].lda = 3 * C; a.seg[0].sAb = (long)N * 3 * C; a.seg[0].sAh = d;
@@ -485,7 +494,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(h->T(o.x), C, N, kv, 2 * C, Nk, d, dS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   } else {
     const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
     PbGemm g = plain_gemm(dqkv, 3 * C, N, qkv + C, 3 * C, Nk, d, dS, ldk);       // dQ K^T
@@ -494,7 +503,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     g.seg[1].A = qkv; g.seg[1].lda = 3 * C; g.seg[1].sAb = 0; g.seg[1].sAh = d;
     g.seg[1].B = dqkv + C; g.seg[1].ldb = 3 * C; g.seg[1].sBb = (long)N * 3 * C; g.seg[1].sBh = d; g.seg[1].K = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   CK(pbk_softmax_lin(P, (long)hd * N, dS, nb, Nk, ldk, h->rnd, st));
   PbGemm g = plain_gemm(dS, ldk, N, Vt, ldk, d, Nk, h->T(o.y), C);                // dP V
@@ -508,7 +517,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     g.seg[1].A = P; g.seg[1].lda = ldk; g.seg[1].sAb = 0; g.seg[1].sAh = (long)N * ldk;
     g.seg[1].B = dVt; g.seg[1].ldb = ldk; g.seg[1].sBb = (long)C * ldk; g.seg[1].sBh = (long)d * ldk; g.seg[1].K = Nk;
   }
-  g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+  g.precise = h->prec_a; CK(gemm_call(h, g, st));
   return PB_OK;
 }
 
@@ -553,7 +562,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, 3 * C);
     g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
     g.sDb = (long)N * 3 * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
     h->vals[o.x].ginit = true;
     return PB_OK;
   }
@@ -561,7 +570,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(gO, C, N, V, ldkv, Nk, d, gS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   CK(pbk_softmax_lin(P, (long)hd * N, gS, nb, Nk, ldk, h->rnd, st));              // gS = P o (dP - rowsum(P o dP))
   const long ldx = o.cross ? C : 3 * C;
@@ -570,7 +579,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(gS, ldk, N, Kt, ldk, d, Nk, gx, ldx);
     g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   h->vals[o.x].ginit = true;
   if (o.cross) return PB_OK;
@@ -583,21 +592,21 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(V, ldkv, Nk, gO, C, N, d, gSt, ldq);
     g.seg[0].sAh = d; g.seg[0].sBb = (long)N * C; g.seg[0].sBh = d;
     g.sDb = sSt; g.sDh = (long)Nk * ldq; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   CK(pbk_attn_ds(Pt, gSt, delta, 1.f, nb, hd, Nk, N, ldq, 1, h->rnd, st));        // gS^T = P^T o (dP^T - delta_i)
   {                                                                                // gK = scale gS^T Q
     PbGemm g = plain_gemm(gSt, ldq, Nk, Qt, ldq, d, N, gx + C, ldx);
     g.seg[0].sAb = sSt; g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBh = (long)d * ldq;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
   {                                                                                // gV = P^T gO
     PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, ldx);
     g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
-    g.precise = h->prec_a; CK(pbk_gemm(&g, st));
+    g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   return PB_OK;
 }
@@ -934,6 +943,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->w_G = p.work_alloc(2 * K * K); h->w_M = p.work_alloc(2 * K * K); h->w_R = p.work_alloc(K * K);
   h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4);
   h->w_x = p.work_alloc((size_t)h->n_in);
+  h->n_splitk = kSplitFloats; h->w_splitk = p.work_alloc(kSplitFloats);
   h->sizes.packed_weight_bytes = h->packed_top; h->sizes.primal_cache_bytes = h->cache_top; h->sizes.workspace_bytes = h->work_top;
   h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out;
   if (sizes) *sizes = h->sizes;

@@ -33,6 +33,8 @@ struct PbGemm {
   int round_tf32;                        // round the stored result to TF32 (RNA) for a GEMM-only consumer
   int precise;                           // 0: one TF32 pass; 1: error-compensated 3xTF32 (A and B split hi/lo);
                                          // 2: B (weights) split hi/lo, A as given
+  // optional split-K scratch owned by the caller (nullptr: never split): room for the partial tiles
+  float* ws; long ws_floats;
 };
 
 static inline PbGemm pb_gemm_init() {

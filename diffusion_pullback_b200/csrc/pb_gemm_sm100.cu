@@ -1,13 +1,20 @@
 // tcgen05 / TMA TF32 GEMM for sm_100a: the contraction engine behind every conv / linear /
 // attention product of the pullback hot path (primal, JVP and VJP passes).
 //
-// One CTA computes one 128 x BN output tile:
+// Persistent kernel, one CTA per SM, each CTA walks a static list of work items (128 x BN output tile, K split):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 4D, 128B-swizzled K-major tiles, OOB zero fill
 //                 supplies conv padding, K/M/N tails and attention-head tails)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, fp32 accum in TMEM)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> alpha/bias/residual -> 128-byte row segments to HBM)
-// smem ring of STAGES x (A 16 KB + B BN*128 B) with full/empty mbarriers; MMA completion is
-// signalled with tcgen05.commit.  See pb_gemm.h for the operation this implements.
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, fp32 accumulators in TMEM,
+//                 two accumulator stages so the epilogue of item i overlaps the main loop of item i + 1)
+//   warps 2..5  : epilogue: tcgen05.ld 32x32b -> alpha / bias / residual / RNA rounding -> 128B-swizzled smem staging
+//                 -> TMA tensor store (the residual tile arrives by TMA into the same staging buffer, 3 chunks ahead)
+// smem: STAGES x (A 16 KB + B BN*128 B) operand ring with full/empty mbarriers (MMA completion by tcgen05.commit)
+// + 4 x 16 KB staging buffers.
+// Scheduling: output tiles are dealt round-robin to the CTAs.  The tiles of the last, partial wave (all tiles when there
+// are fewer tiles than SMs: small-M weight-streaming layers) are cut along K into `splits` items each so that the wave
+// fills the machine; such items store their raw partial tile to scratch through the same TMA epilogue and
+// splitk_reduce_k sums the partials in split order (deterministic) and applies alpha / bias / residual / rounding.
+// See pb_gemm.h for the operation this implements.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -24,17 +31,27 @@ namespace pbgemm {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // 32 fp32 = 128 bytes = one swizzle row
 constexpr int NTHREADS = 192;
+constexpr int EPI_W = 32;              // epilogue chunk: 32 columns = one 128-byte staging row
+constexpr int NBUF = 4;                // staging buffers
+constexpr int EPI_BYTES = BM * EPI_W * 4;
+constexpr int ACC_STRIDE = 256;        // TMEM columns between the two accumulator stages
 
 struct alignas(64) Params {
   CUtensorMap mapA[2];
   CUtensorMap mapB[2];
+  CUtensorMap mapD, mapR;
   int kblocks[2];                      // ceil(K_seg / 32)
   uint32_t tx_bytes[2];                // bytes one stage's A+B boxes deliver (boxes are clamped to the tensor)
-  int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2];
+  int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2], d_bmul, d_hmul;
   int nseg, taps, conv_ctot;
   int M, N, nb, nh;
   int conv, H, W, bw, bh, bb, tiles_w, tiles_h;
-  int raster_b, mt, nt;
+  CUtensorMap mapW;                    // split-K scratch as a [tile][split][128][BN] tensor
+  int raster_b, mt, nt, items;
+  int full_tiles;                      // tiles [0, full_tiles) are whole items; every later tile is `splits` partial items
+  int splits, kb_per_split;            // partial item s covers flat k-blocks [s*kb_per_split, (s+1)*kb_per_split)
+  float* ws;
+  int epi_tma; uint32_t r_bytes;       // epilogue through smem staging + TMA (else guarded direct stores)
   float* D; const float* R; const float* bias;
   long ldd, sDb, sDh, ldr, sRb, sRh;
   float alpha, beta;
@@ -48,57 +65,99 @@ struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;         // + barriers + 1024B alignment slack
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STAGING_OFF + NBUF * EPI_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;         // + barriers + 1024B alignment slack
 };
 
-template <int BN, int STAGES, int OCC>
-__global__ void __launch_bounds__(NTHREADS, OCC) gemm_tf32_kernel(const __grid_constant__ Params p) {
+struct Tile {
+  int n0, m0, bat_b, bat_h;            // plain mode
+  int cx0, cy0, cb0;                   // conv mode tile origin
+  int split, tile_id, partial;
+};
+
+template <int BN>
+__device__ __forceinline__ Tile decode_tile(const Params& p, int tile) {
+  Tile t;
+  t.m0 = t.bat_b = t.bat_h = t.cx0 = t.cy0 = t.cb0 = t.split = t.partial = 0;
+  t.tile_id = tile;
+  int v = tile;
+  if (p.raster_b) {
+    // tangent index fastest: the nb tiles that read the same broadcast A tile (attention probabilities) run at the same
+    // time on neighbouring SMs, so A comes from HBM once and from L2 nb - 1 times
+    t.bat_b = v % p.nb; v /= p.nb;
+    t.n0 = (v % p.nt) * BN; v /= p.nt;
+    t.m0 = (v % p.mt) * BM;
+    t.bat_h = v / p.mt;
+    return t;
+  }
+  t.n0 = (v % p.nt) * BN; v /= p.nt;
+  int m = v % p.mt; v /= p.mt;
+  if (p.conv) {
+    const int tw = m % p.tiles_w; m /= p.tiles_w;
+    const int th = m % p.tiles_h; m /= p.tiles_h;
+    t.cx0 = tw * p.bw; t.cy0 = th * p.bh; t.cb0 = m * p.bb;
+  } else {
+    t.m0 = m * BM;
+    t.bat_h = v % p.nh;
+    t.bat_b = v / p.nh;
+  }
+  return t;
+}
+
+template <int BN>
+__device__ __forceinline__ Tile decode_item(const Params& p, int item) {
+  if (item < p.full_tiles) return decode_tile<BN>(p, item);
+  const int j = item - p.full_tiles;
+  Tile t = decode_tile<BN>(p, p.full_tiles + j / p.splits);
+  t.split = j % p.splits;
+  t.partial = 1;
+  return t;
+}
+
+// row r of a tile -> element offsets of D / R (false: the row lies outside the tensor)
+__device__ __forceinline__ bool tile_row(const Params& p, const Tile& t, int r, long* d_off, long* r_off) {
+  if (p.conv) {
+    const int w = r % p.bw;
+    const int hh = (r / p.bw) % p.bh;
+    const int bb = r / (p.bw * p.bh);
+    const int x = t.cx0 + w, y = t.cy0 + hh, b = t.cb0 + bb;
+    const long pix = (static_cast<long>(b) * p.H + y) * p.W + x;
+    *d_off = pix * p.ldd;
+    *r_off = pix * p.ldr;
+    return (x < p.W) && (y < p.H) && (b < p.nb);
+  }
+  *d_off = t.bat_b * p.sDb + t.bat_h * p.sDh + static_cast<long>(t.m0 + r) * p.ldd;
+  *r_off = t.bat_b * p.sRb + t.bat_h * p.sRh + static_cast<long>(t.m0 + r) * p.ldr;
+  return (t.m0 + r) < p.M;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = Smem<BN, STAGES>;
+  uint8_t* staging = smem + S::STAGING_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint64_t* r_bar = tmem_empty_bar + 2;              // [NBUF]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(r_bar + NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---- tile coordinates ----
-  int n0 = blockIdx.x * BN;
-  int m0 = 0, bat_b = 0, bat_h = 0;          // plain mode
-  int cx0 = 0, cy0 = 0, cb0 = 0;             // conv mode tile origin
-  if (p.conv) {
-    int t = blockIdx.y;
-    const int tw = t % p.tiles_w; t /= p.tiles_w;
-    const int th = t % p.tiles_h; t /= p.tiles_h;
-    cx0 = tw * p.bw; cy0 = th * p.bh; cb0 = t * p.bb;
-  } else if (p.raster_b) {
-    // 1-D launch, tangent index fastest: the nb CTAs that read the same broadcast A tile (attention probabilities)
-    // are adjacent in launch order, so A comes from HBM once and from L2 nb - 1 times
-    int t = blockIdx.x;
-    bat_b = t % p.nb; t /= p.nb;
-    n0 = (t % p.nt) * BN; t /= p.nt;
-    m0 = (t % p.mt) * BM;
-    bat_h = t / p.mt;
-  } else {
-    m0 = blockIdx.y * BM;
-    bat_h = blockIdx.z % p.nh;
-    bat_b = blockIdx.z / p.nh;
-  }
-  const int total_kb = p.taps * (p.kblocks[0] + (p.nseg > 1 ? p.kblocks[1] : 0));
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < NBUF; ++i) mbar_init(&r_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_base_smem)),
-                 "r"(TMEM_COLS)
+                 "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -107,30 +166,35 @@ __global__ void __launch_bounds__(NTHREADS, OCC) gemm_tf32_kernel(const __grid_c
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
+  const int kb_tap = p.kblocks[0] + (p.nseg > 1 ? p.kblocks[1] : 0);
+  const int total_kb = p.taps * kb_tap;
+
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int dy = p.conv ? tap / 3 - 1 : 0;
-        const int dx = p.conv ? tap % 3 - 1 : 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          for (int kb = 0; kb < p.kblocks[s]; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * S::STAGE_BYTES;
-            uint8_t* sb = sa + S::A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
-            if (p.conv) {
-              tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, cx0 + dx, cy0 + dy, cb0);
-              tma_load_4d(sb, &p.mapB[s], &full_bar[stage], tap * p.conv_ctot + kb * BK, n0, 0, 0);
-            } else {
-              tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, m0, bat_h * p.a_hmul[s],
-                          bat_b * p.a_bmul[s]);
-              tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * BK, n0, bat_h * p.b_hmul[s],
-                          bat_b * p.b_bmul[s]);
-            }
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const Tile t = decode_item<BN>(p, item);
+        const int kb_begin = t.partial ? t.split * p.kb_per_split : 0;
+        const int kb_end = t.partial ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+        for (int it = kb_begin; it < kb_end; ++it) {
+          const int tap = it / kb_tap;
+          int kb = it - tap * kb_tap;
+          const int s = kb < p.kblocks[0] ? 0 : 1;
+          if (s) kb -= p.kblocks[0];
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
+          if (p.conv) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, t.cx0 + dx, t.cy0 + dy, t.cb0);
+            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], tap * p.conv_ctot + kb * BK, t.n0, 0, 0);
+          } else {
+            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, t.m0, t.bat_h * p.a_hmul[s], t.bat_b * p.a_bmul[s]);
+            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * BK, t.n0, t.bat_h * p.b_hmul[s], t.bat_b * p.b_bmul[s]);
           }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -140,102 +204,193 @@ __global__ void __launch_bounds__(NTHREADS, OCC) gemm_tf32_kernel(const __grid_c
       constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
                                  (uint32_t(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int li = 0;
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+        const bool partial = item >= p.full_tiles;
+        const int kb_begin = partial ? ((item - p.full_tiles) % p.splits) * p.kb_per_split : 0;
+        const int kb_end = partial ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+        const int as = li & 1;
+        mbar_wait(&tmem_empty_bar[as], ((li >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-        const uint64_t adesc = make_smem_desc(sa);
-        const uint64_t bdesc = make_smem_desc(sa + S::A_BYTES);
+        const uint32_t d_tmem = tmem_base + uint32_t(as * ACC_STRIDE);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + S::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
-          mma_tf32(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
+            mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        tcgen05_commit(&tmem_full_bar[as]);
       }
-      tcgen05_commit(tmem_full_bar);
     }
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // tile row
-    bool row_ok;
-    long d_off, r_off;
-    if (p.conv) {
-      const int w = r % p.bw;
-      const int hh = (r / p.bw) % p.bh;
-      const int bb = r / (p.bw * p.bh);
-      const int x = cx0 + w, y = cy0 + hh, b = cb0 + bb;
-      row_ok = (x < p.W) && (y < p.H) && (b < p.nb);
-      const long pix = (static_cast<long>(b) * p.H + y) * p.W + x;
-      d_off = pix * p.ldd;
-      r_off = pix * p.ldr;
-    } else {
-      row_ok = (m0 + r) < p.M;
-      d_off = bat_b * p.sDb + bat_h * p.sDh + static_cast<long>(m0 + r) * p.ldd;
-      r_off = bat_b * p.sRb + bat_h * p.sRh + static_cast<long>(m0 + r) * p.ldr;
-    }
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const float alpha = p.alpha, beta = p.beta;
+    const bool t0 = (threadIdx.x == 64);      // the thread that drives the staging TMA traffic
+    const uint32_t swz = uint32_t(r & 7);
+    uint32_t gch = 0;                         // chunks pushed through the staging ring so far (this CTA)
+    uint32_t r_par = 0;                       // bit b: parity of the next residual load into staging buffer b
+    int li = 0;
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
+      const Tile t = decode_item<BN>(p, item);
+      const int as = li & 1;
+      const int nchunks = min(BN / EPI_W, (p.N - t.n0 + EPI_W - 1) / EPI_W);
+      // TMA stores clip the inner dimension in 16-byte units: a ragged last chunk (N % 4 != 0) takes the guarded direct path
+      const int ntma = t.partial ? nchunks
+                                 : !p.epi_tma ? 0 : ((p.N & 3) && t.n0 + nchunks * EPI_W > p.N) ? nchunks - 1 : nchunks;
+      const uint32_t acc = tmem_base + uint32_t(as * ACC_STRIDE) + (uint32_t(q * 32) << 16);
+      const float alpha = t.partial ? 1.f : p.alpha, beta = p.beta;
+      const bool has_r = p.R != nullptr && !t.partial;
+      const float* bias = t.partial ? nullptr : p.bias;
+      const int rnd = t.partial ? 0 : p.round_tf32;
+      const CUtensorMap* dmap = t.partial ? &p.mapW : &p.mapD;
+      int c1 = p.conv ? t.cx0 : t.m0, c2 = p.conv ? t.cy0 : t.bat_h * p.d_hmul, c3 = p.conv ? t.cb0 : t.bat_b * p.d_bmul;
+      const int rc1 = c1, rc2 = c2, rc3 = c3;
+      int dcol0 = t.n0;
+      if (t.partial) { c1 = ((t.tile_id - p.full_tiles) * p.splits + t.split) * BM; c2 = c3 = 0; dcol0 = 0; }
+      auto prefetch_r = [&](int c, uint32_t g) {   // residual chunk c of this tile -> staging buffer g % NBUF
+        const uint32_t b = g % NBUF;
+        mbar_arrive_expect_tx(&r_bar[b], p.r_bytes);
+        tma_load_4d(staging + b * EPI_BYTES, &p.mapR, &r_bar[b], t.n0 + c * EPI_W, rc1, rc2, rc3);
+      };
+      long d_off, r_off;
+      const bool row_ok = tile_row(p, t, r, &d_off, &r_off);
+
+      if (t0 && has_r)
+        for (int c = 0; c < min(3, ntma); ++c) prefetch_r(c, gch + c);
+      mbar_wait(&tmem_full_bar[as], (li >> 1) & 1);
+      tcgen05_fence_after();
+
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nc = n0 + c * 32;
-      if (nc >= p.N) break;                   // warp-uniform
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
-      if (!row_ok) continue;
-      float* dptr = p.D + d_off + nc;
-      const float* rptr = p.R ? p.R + r_off + nc : nullptr;
-      const bool full = (nc + 32 <= p.N);
+      for (int c = 0; c < nchunks; ++c) {
+        const int nc = t.n0 + c * EPI_W;
+        uint32_t v[32];
+        tmem_ld32(acc + uint32_t(c * EPI_W), v);
+        if (c == nchunks - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+        const bool full = (nc + EPI_W <= p.N);
+        if (c < ntma) {
+          const uint32_t b = gch % NBUF;
+          uint8_t* sbuf = staging + b * EPI_BYTES + r * 128;
+          if (has_r) { mbar_wait(&r_bar[b], (r_par >> b) & 1u); r_par ^= 1u << b; }
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float o[4];
+          for (int j = 0; j < 32; j += 4) {
+            float4* sp = reinterpret_cast<float4*>(sbuf + ((uint32_t(j >> 2) ^ swz) << 4));
+            float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
-        if (full) {
-          if (p.bias) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + nc + j);
-            o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
-          }
-          if (rptr) {
-            const float4 rv = *reinterpret_cast<const float4*>(rptr + j);
-            o[0] += beta * rv.x; o[1] += beta * rv.y; o[2] += beta * rv.z; o[3] += beta * rv.w;
-          }
-          if (p.round_tf32) {
+            for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
+            if (bias) {
+              if (full) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias + nc + j);
+                o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+              } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              uint32_t t;
-              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(o[e]));
-              o[e] = __uint_as_float(t);
-            }
-          }
-          *reinterpret_cast<float4*>(dptr + j) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (nc + j + e < p.N) {
-              float t = o[e];
-              if (p.bias) t += p.bias[nc + j + e];
-              if (rptr) t += beta * rptr[j + e];
-              if (p.round_tf32) {
-                uint32_t u;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(t));
-                t = __uint_as_float(u);
+                for (int e = 0; e < 4; ++e) if (nc + j + e < p.N) o[e] += bias[nc + j + e];
               }
-              dptr[j + e] = t;
+            }
+            if (has_r) {
+              const float4 rv = *sp;
+              o[0] += beta * rv.x; o[1] += beta * rv.y; o[2] += beta * rv.z; o[3] += beta * rv.w;
+            }
+            if (rnd) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
+            }
+            *sp = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (t0) {
+            tma_store_4d(dmap, staging + b * EPI_BYTES, dcol0 + c * EPI_W, c1, c2, c3);
+            bulk_commit();
+            bulk_wait_read<1>();              // every store but the newest has left its staging buffer
+            if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
+          }
+          ++gch;
+        } else if (row_ok) {
+          float* dptr = p.D + d_off + nc;
+          const float* rptr = has_r ? p.R + r_off + nc : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nc + j < p.N) {
+              float o = alpha * __uint_as_float(v[j]);
+              if (bias) o += bias[nc + j];
+              if (rptr) o += beta * rptr[j];
+              if (rnd) o = rna_tf32(o);
+              dptr[j] = o;
             }
           }
         }
       }
     }
+    if (t0) bulk_wait<0>();
     tcgen05_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Sums the `splits` partial tiles of every split tile in split order and applies the epilogue.  One thread per
+// (tile row, 4 columns); partials are [tile][split][128][BN] fp32, L2-resident right after the GEMM.
+template <int BN>
+__global__ void __launch_bounds__(256) splitk_reduce_k(const __grid_constant__ Params p, int ntail) {
+  constexpr int QN = BN / 4;
+  const long total = static_cast<long>(ntail) * BM * QN;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % QN);
+    const int r = static_cast<int>((i / QN) % BM);
+    const int tt = static_cast<int>(i / (QN * BM));
+    const Tile t = decode_tile<BN>(p, p.full_tiles + tt);
+    const int nc = t.n0 + cq * 4;
+    long d_off, r_off;
+    if (nc >= p.N || !tile_row(p, t, r, &d_off, &r_off)) continue;
+    const float4* src = reinterpret_cast<const float4*>(p.ws + (static_cast<size_t>(tt) * p.splits * BM + r) * BN) + cq;
+    float4 a = __ldcg(src);
+    for (int s = 1; s < p.splits; ++s) {
+      const float4 b = __ldcg(src + static_cast<size_t>(s) * BM * QN);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float o[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
+    float* dptr = p.D + d_off + nc;
+    const float* rptr = p.R ? p.R + r_off + nc : nullptr;
+    if (nc + 4 <= p.N) {
+      if (p.bias) {
+        const float4 bv = *reinterpret_cast<const float4*>(p.bias + nc);
+        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+      }
+      if (rptr) {
+        const float4 rv = *reinterpret_cast<const float4*>(rptr);
+        o[0] += p.beta * rv.x; o[1] += p.beta * rv.y; o[2] += p.beta * rv.z; o[3] += p.beta * rv.w;
+      }
+      if (p.round_tf32) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
+      }
+      *reinterpret_cast<float4*>(dptr) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (int e = 0; e < 4 && nc + e < p.N; ++e) {
+        float v = o[e];
+        if (p.bias) v += p.bias[nc + e];
+        if (rptr) v += p.beta * rptr[e];
+        if (p.round_tf32) v = rna_tf32(v);
+        dptr[e] = v;
+      }
+    }
   }
 }
 
@@ -301,19 +456,38 @@ const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, lon
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-template <int BN, int STAGES, int OCC>
-static const char* launch_t(const Params& p, dim3 grid, cudaStream_t st) {
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
-  static_assert(S::TOTAL * OCC <= 227 * 1024, "shared memory budget");
+  static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
+  static_assert(2 * BN <= 512 && BN <= ACC_STRIDE, "two accumulator stages must fit TMEM");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  gemm_tf32_kernel<BN, STAGES, OCC><<<grid, NTHREADS, S::TOTAL, st>>>(p);
+  gemm_tf32_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(p);
   cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cudaGetErrorString(e);
+  if (p.splits > 1) {
+    const int ntail = (p.items - p.full_tiles) / p.splits;
+    const long threads = static_cast<long>(ntail) * BM * (BN / 4);
+    const int blocks = (int)std::min<long>((threads + 255) / 256, 8L * sm_count());
+    splitk_reduce_k<BN><<<blocks, 256, 0, st>>>(p, ntail);
+    e = cudaGetLastError();
+  }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
@@ -321,11 +495,13 @@ static const char* launch_t(const Params& p, dim3 grid, cudaStream_t st) {
 
 extern "C" __attribute__((visibility("default"))) void pb_gemm_set_tmap_tf32(int on) { pbgemm::g_tmap_dtype_tf32 = on; }
 
-// tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic) / CTAs per SM (1 or 2)
-static int g_force_bn = 0, g_occ = 2, g_use160 = 0;
-extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int occ, int use160) {
-  g_force_bn = force_bn; g_occ = occ; g_use160 = use160;
+// tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic), split-K policy (0 off, 1 heuristic,
+// >1 forced split count), allow BN = 160
+static int g_force_bn = 0, g_split = 1, g_use160 = 1, g_split_min_kb = 48;
+extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int split, int use160) {
+  g_force_bn = force_bn; g_split = split; g_use160 = use160;
 }
+extern "C" __attribute__((visibility("default"))) void pb_gemm_tune_split_min_kb(int kb) { g_split_min_kb = kb; }
 
 // Returns nullptr on success, else a static error string.  Stream-ordered, no host sync.
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
@@ -342,10 +518,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       (g.R && (reinterpret_cast<uintptr_t>(g.R) & 15)) || (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)))
     return "gemm: D/R/bias must be 16-byte aligned with ld % 4 == 0";
 
-  // tile width: 160 when it divides N (every SD channel count is a multiple of 160: no padded columns), 64 for narrow
-  // outputs or when wider tiles cannot fill the machine, else 128
-  int BN = 128;
-  long mt = g.conv ? 0 : (long)((g.M + BM - 1) / BM) * g.nb * g.nh;
+  long mt;
   if (g.conv) {
     p.bw = std::min(pow2_floor(g.W), 128);
     p.bh = std::min(pow2_floor(g.H), 128 / p.bw);
@@ -355,11 +528,20 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
     mt = (long)p.tiles_w * p.tiles_h * ((g.nb + p.bb - 1) / p.bb);
     p.taps = 9;
   } else {
+    mt = (g.M + BM - 1) / BM;
     p.taps = 1;
   }
-  if (g_use160 && g.N % 160 == 0 && mt * (g.N / 160) >= 148) BN = 160;
-  else if (g.N <= 64 || mt * ((g.N + 127) / 128) < 148) BN = 64;
+  const long nz = g.conv ? 1 : (long)g.nb * g.nh;
+  const int nsm = sm_count();
+  // tile width: 160 when it divides N (every SD channel count is a multiple of 160: no padded columns), 64 for narrow
+  // outputs, else 128
+  int BN = 128;
+  if (g_use160 && g.N % 160 == 0) BN = 160;
+  else if (g.N <= 64) BN = 64;
+  else if (g.N <= 128 || g.N % 128 == 0) BN = 128;
+  else if (g.N % 128 <= 64 && mt * nz * ((g.N + 63) / 64) <= 2L * nsm) BN = 64;
   if (g_force_bn) BN = g_force_bn;
+  const long nt = (g.N + BN - 1) / BN;
 
   int ktot = 0;
   for (int s = 0; s < g.nseg; ++s) {
@@ -393,22 +575,68 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
     }
   }
   ktot *= p.taps;
-  dim3 grid((g.N + BN - 1) / BN, g.conv ? (unsigned)mt : (unsigned)((g.M + BM - 1) / BM),
-            g.conv ? 1 : (unsigned)(g.nb * g.nh));
-  if (!g.conv && g.nb > 1 && g.seg[0].sAb == 0 && (g.nseg == 1 || g.seg[1].sAb == 0)) {
-    p.raster_b = 1; p.nt = (int)grid.x; p.mt = (int)grid.y;
-    grid = dim3(grid.x * grid.y * grid.z, 1, 1);
+
+  // epilogue tensor maps (D store / R load through the staging buffers); narrow outputs use guarded direct stores
+  p.epi_tma = g.N >= EPI_W ? 1 : 0;
+  if (p.epi_tma) {
+    const char* err;
+    if (g.conv) {
+      uint32_t box[4] = {uint32_t(EPI_W), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
+      uint64_t dims[4] = {uint64_t(g.N), uint64_t(g.W), uint64_t(g.H), uint64_t(g.nb)};
+      uint64_t sd[3] = {uint64_t(g.ldd) * 4, uint64_t(g.ldd) * 4 * g.W, uint64_t(g.ldd) * 4 * g.W * g.H};
+      err = encode4(&p.mapD, g.D, dims, sd, box);
+      if (err) return err;
+      if (g.R) {
+        uint64_t sr[3] = {uint64_t(g.ldr) * 4, uint64_t(g.ldr) * 4 * g.W, uint64_t(g.ldr) * 4 * g.W * g.H};
+        err = encode4(&p.mapR, g.R, dims, sr, box);
+        if (err) return err;
+      }
+      p.r_bytes = uint32_t(p.bw * p.bh * p.bb) * EPI_W * 4;
+    } else {
+      int hm, bm;
+      err = encode_plain(&p.mapD, g.D, g.M, g.N, g.ldd, g.sDh, g.nh, g.sDb, g.nb, BM, &p.d_hmul, &p.d_bmul, &p.r_bytes);
+      if (err) return err;
+      if ((g.nh > 1 && !p.d_hmul) || (g.nb > 1 && !p.d_bmul)) return "gemm: D needs a stride for every batch dimension";
+      if (g.R) {
+        err = encode_plain(&p.mapR, g.R, g.M, g.N, g.ldr, g.sRh, g.nh, g.sRb, g.nb, BM, &hm, &bm, &p.r_bytes);
+        if (err) return err;
+        if (hm != p.d_hmul || bm != p.d_bmul) return "gemm: R must be batched like D";
+      }
+    }
   }
-  const bool shallow = ktot <= 6;
-  const bool occ2 = g_occ >= 2;
-  if (BN == 160) {
-    if (shallow) return launch_t<160, 2, 2>(p, grid, st);
-    return occ2 ? launch_t<160, 3, 2>(p, grid, st) : launch_t<160, 6, 1>(p, grid, st);
+
+  if (!g.conv && g.nb > 1 && g.seg[0].sAb == 0 && (g.nseg == 1 || g.seg[1].sAb == 0)) p.raster_b = 1;
+  p.mt = (int)mt; p.nt = (int)nt;
+  p.splits = 1; p.kb_per_split = ktot;
+  const long tiles = mt * nt * nz;
+  // tiles of the last, partial wave are cut along K so that the wave fills the machine (see the header comment); only
+  // when the K loop is deep enough for the saving to outweigh the reduction pass
+  long full = tiles, tail = 0;
+  if (g_split && g.ws && ktot >= g_split_min_kb) {
+    tail = tiles % nsm;
+    int s = tail ? (int)std::min<long>(nsm / tail, 32) : 1;
+    if (g_split > 1) s = g_split;
+    s = std::min(s, ktot / 8);
+    if (tail) s = (int)std::min<long>(s, g.ws_floats / (tail * BM * BN));
+    if (tail && s > 1) {
+      p.kb_per_split = (ktot + s - 1) / s;
+      p.splits = (ktot + p.kb_per_split - 1) / p.kb_per_split;
+      full = tiles - tail;
+      p.ws = g.ws;
+      uint64_t dims[4] = {uint64_t(BN), uint64_t(tail) * p.splits * BM, 1, 1};
+      uint64_t sw[3] = {uint64_t(BN) * 4, uint64_t(BN) * 4, uint64_t(BN) * 4};
+      uint32_t box[4] = {uint32_t(EPI_W), uint32_t(BM), 1, 1};
+      const char* err = encode4(&p.mapW, g.ws, dims, sw, box);
+      if (err) return err;
+    } else {
+      tail = 0;
+    }
   }
-  if (BN == 128) {
-    if (shallow) return launch_t<128, 2, 2>(p, grid, st);
-    return occ2 ? launch_t<128, 3, 2>(p, grid, st) : launch_t<128, 6, 1>(p, grid, st);
-  }
-  if (shallow) return launch_t<64, 2, 2>(p, grid, st);
-  return occ2 ? launch_t<64, 4, 2>(p, grid, st) : launch_t<64, 8, 1>(p, grid, st);
+  p.full_tiles = (int)full;
+  p.items = (int)(full + tail * p.splits);
+  const int grid = (int)std::min<long>(p.items, nsm);
+  if (BN == 160) return launch_t<160, 4>(p, grid, st);
+  if (BN == 128) return launch_t<128, 5>(p, grid, st);
+  if (BN == 64) return launch_t<64, 6>(p, grid, st);
+  return "gemm: unsupported tile width";
 }

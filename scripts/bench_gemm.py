@@ -19,7 +19,9 @@ for line in open(sys.argv[1]):
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 f = N.leaf("pbk_gemm")
 tune = N.raw().pb_gemm_tune
-cfgs = [("occ1 bn128", (0, 1, 0)), ("occ2 bn128", (0, 2, 0)), ("occ1 bn160", (0, 1, 1)), ("occ2 bn160", (0, 2, 1))]
+cfgs = [("default", (0, 1, 1)), ("nosplit", (0, 0, 1)), ("no160", (0, 1, 0)), ("bn128", (128, 1, 0))]
+ws = torch.empty(8 << 20, device="cuda")
+
 if len(sys.argv) > 2:
     cfgs = [c for c in cfgs if c[0] in sys.argv[2:]]
 rows = []
@@ -48,6 +50,7 @@ for key, cnt in shapes.items():
         if res:
             g.R, g.ldr, g.sRb, g.beta = D[r].data_ptr(), D.shape[-1], M * D.shape[-1], 1.0
         g.alpha, g.nb, g.nh, g.conv, g.H, g.W, g.round_tf32 = 1.0, (nb if conv else nbat), 1, conv, H, W, 1
+        g.ws, g.ws_floats = ws.data_ptr(), ws.numel()
         gs.append(g)
     uss = []
     for name, cfg in cfgs:

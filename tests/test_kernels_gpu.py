@@ -33,7 +33,7 @@ def tf32_trunc(t):
 
 
 def gemm(A, B, D, *, M, N_, K, lda, ldb, ldd, sAb=0, sAh=0, sBb=0, sBh=0, sDb=0, sDh=0, nb=1, nh=1,
-         bias=None, R=None, ldr=0, sRb=0, sRh=0, alpha=1.0, beta=0.0, conv=0, H=0, W=0, seg2=None, rnd=0):
+         bias=None, R=None, ldr=0, sRb=0, sRh=0, alpha=1.0, beta=0.0, conv=0, H=0, W=0, seg2=None, rnd=0, splitk=True):
     g = N.PbGemm()
     g.M, g.N, g.nseg = M, N_, 1 if seg2 is None else 2
     s = g.seg[0]
@@ -47,7 +47,19 @@ def gemm(A, B, D, *, M, N_, K, lda, ldb, ldd, sAb=0, sAh=0, sBb=0, sBh=0, sDb=0,
     g.ldr, g.sRb, g.sRh = ldr, sRb, sRh
     g.bias = bias.data_ptr() if bias is not None else None
     g.alpha, g.beta, g.nb, g.nh, g.conv, g.H, g.W, g.round_tf32 = alpha, beta, nb, nh, conv, H, W, rnd
+    if splitk:                               # split-K scratch as the engine provides it
+        ws = _scratch()
+        g.ws, g.ws_floats = ws.data_ptr(), ws.numel()
     _ok(N.leaf("pbk_gemm")(C.byref(g), _st()))
+
+
+_SCRATCH = []
+
+
+def _scratch():
+    if not _SCRATCH:
+        _SCRATCH.append(torch.empty(8 << 20, device="cuda"))
+    return _SCRATCH[0]
 
 
 def rel(a, b):
@@ -55,7 +67,9 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("M,Nn,K", [(128, 128, 32), (256, 64, 64), (300, 200, 96), (64, 40, 40), (1000, 1280, 1280),
-                                    (320, 2560, 1280), (77, 320, 768), (4096, 320, 320), (5, 64, 1000)])
+                                    (320, 2560, 1280), (77, 320, 768), (4096, 320, 320), (5, 64, 1000), (320, 1280, 11520),
+                                    (20480, 320, 320), (130, 7, 64), (257, 13, 100), (64, 16, 16), (1280, 1920, 640),
+                                    (700, 77, 160), (3000, 4096, 40)])
 def test_gemm_plain(M, Nn, K):
     torch.manual_seed(M + Nn + K)
     Kp = (K + 3) // 4 * 4
@@ -70,6 +84,33 @@ def test_gemm_plain(M, Nn, K):
     assert rel(D[:, :Nn], ref) < 1e-5
     if Np > Nn:
         assert torch.isnan(D[:, Nn:]).all()           # columns beyond N untouched
+
+
+@pytest.mark.parametrize("M,Nn,K,conv", [(320, 1280, 1280, 1), (320, 1280, 11520, 0), (64, 1280, 1280, 1), (1280, 640, 640, 1),
+                                         (100, 200, 2000, 0)])
+def test_gemm_split_k_is_deterministic_and_matches_unsplit(M, Nn, K, conv):
+    """Small-M weight-streaming shapes take the split-K path: same result (to accumulation order) as the unsplit
+    kernel, bit-identical from run to run, residual + bias + rounding applied once by the reducing CTA."""
+    torch.manual_seed(7)
+    if conv:
+        nb = M // 64
+        A = torch.randn(nb, 8, 8, K, device="cuda")
+        B = torch.randn(Nn, 9 * K, device="cuda") / math.sqrt(9 * K)
+        kw = dict(M=M, N_=Nn, K=K, lda=K, ldb=9 * K, ldd=Nn, nb=nb, conv=1, H=8, W=8)
+    else:
+        A = torch.randn(M, K, device="cuda")
+        B = torch.randn(Nn, K, device="cuda") / math.sqrt(K)
+        kw = dict(M=M, N_=Nn, K=K, lda=K, ldb=K, ldd=Nn)
+    bias = torch.randn(Nn, device="cuda")
+    R = torch.randn(M, Nn, device="cuda")
+    outs = []
+    for splitk in (True, True, False):
+        D = torch.full((M, Nn), float("nan"), device="cuda")
+        gemm(A, B, D, bias=bias, R=R, ldr=Nn, alpha=0.5, beta=2.0, rnd=1, splitk=splitk, **kw)
+        outs.append(D)
+    assert torch.equal(outs[0], outs[1])
+    assert rel(outs[0], outs[2]) < 2e-4               # both TF32-rounded on store: one-ulp flips allowed
+    assert not torch.isnan(outs[0]).any()
 
 
 def test_gemm_two_segments_and_inplace_residual():
