@@ -300,9 +300,9 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   for (int s = 0; s < a.nseg; ++s) {
     const PbGemmSeg& sg = a.seg[s];
     uint32_t ab, bb;
-    if (const char* e = pbgemm::encode_plain(&p.mapA[s], sg.A, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, TM, &p.a_hmul[s],
+    if (const char* e = pbgemm::encode_plain(&p.mapA[s], static_cast<const float*>(sg.A), a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, TM, &p.a_hmul[s],
                                               &p.a_bmul[s], &ab)) return e;
-    if (const char* e = pbgemm::encode_plain(&p.mapB[s], sg.B, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, TN, &p.b_hmul[s],
+    if (const char* e = pbgemm::encode_plain(&p.mapB[s], static_cast<const float*>(sg.B), a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, TN, &p.b_hmul[s],
                                               &p.b_bmul[s], &bb)) return e;
     abytes += ab * p.kbd; bbytes += bb * p.kbd;
   }

@@ -2,8 +2,8 @@
 //
 //   D[b,h][m,n] = alpha * sum_seg sum_k A_seg[b,h][m,k] * B_seg[b,h][n,k]  + bias[n] + beta * R[b,h][m,n]
 //
-// All matrices are fp32, K-major (row-major [rows][K]); the contraction runs on the tcgen05 tensor
-// cores as TF32 with fp32 accumulation in TMEM.
+// All matrices are K-major (row-major [rows][K]), fp32 or fp16; the contraction runs on the tcgen05 tensor
+// cores as TF32 or F16 with fp32 accumulation in TMEM.
 //
 //  * plain mode: A is [M][K] with leading dimension lda and two batch strides (b = tangent index,
 //    h = attention head); a stride of 0 broadcasts the operand over that batch dimension.
@@ -13,9 +13,12 @@
 #pragma once
 #include <cstdint>
 
+enum { PB_GEMM_F32 = 0, PB_GEMM_F16 = 1 };
+
+// leading dimensions and batch strides are in ELEMENTS of the operand type
 struct PbGemmSeg {
-  const float* A; long lda, sAb, sAh;
-  const float* B; long ldb, sBb, sBh;
+  const void* A; long lda, sAb, sAh;
+  const void* B; long ldb, sBb, sBh;
   int K;
 };
 
@@ -23,8 +26,8 @@ struct PbGemm {
   int M, N;
   int nseg;
   PbGemmSeg seg[2];
-  float* D; long ldd, sDb, sDh;
-  const float* R; long ldr, sRb, sRh;   // optional residual (may alias D element-for-element)
+  void* D; long ldd, sDb, sDh;
+  const void* R; long ldr, sRb, sRh;    // optional residual of D's type (may alias D element-for-element)
   const float* bias;                     // optional [N]
   float alpha, beta;
   int nb, nh;                            // batch extents (plain mode); conv mode: nb images, nh = 1
@@ -35,6 +38,9 @@ struct PbGemm {
                                          // 2: B (weights) split hi/lo, A as given
   // optional split-K scratch owned by the caller (nullptr: never split): room for the partial tiles
   float* ws; long ws_floats;
+  // element types: operands A/B fp32 (TF32 tensor cores) or fp16 (kind::f16); D/R fp32 or fp16 (fp16 needs fp16
+  // operands); bias, alpha, beta and the accumulation are always fp32
+  int ab_dtype, d_dtype;
 };
 
 static inline PbGemm pb_gemm_init() {

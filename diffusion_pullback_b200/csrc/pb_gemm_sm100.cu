@@ -14,14 +14,19 @@
 // are fewer tiles than SMs: small-M weight-streaming layers) are cut along K into `splits` items each so that the wave
 // fills the machine; such items store their raw partial tile to scratch through the same TMA epilogue and
 // splitk_reduce_k sums the partials in split order (deterministic) and applies alpha / bias / residual / rounding.
+// Operand / output types (template parameters): fp32 operands run as kind::tf32 (32-element k-blocks), fp16 operands as
+// kind::f16 (64-element k-blocks, half the L2->smem bytes per flop); accumulation is fp32 in TMEM either way and the
+// output / residual is fp32 or fp16 (32-column chunks: 128-byte or 64-byte staging rows).
 // See pb_gemm.h for the operation this implements.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <algorithm>
+#include <type_traits>
 
 #include "pb_gemm.h"
 #include "pb_tc.cuh"
@@ -29,7 +34,8 @@
 namespace pbgemm {
 
 constexpr int BM = 128;
-constexpr int BK = 32;                 // 32 fp32 = 128 bytes = one swizzle row
+constexpr int BK = 32;                 // k-block of the fp32 / TF32 path: 32 fp32 = 128 bytes = one swizzle row
+constexpr int BK16 = 64;               // k-block of the fp16 path: 64 halves = 128 bytes
 constexpr int NTHREADS = 192;
 constexpr int EPI_W = 32;              // epilogue chunk: 32 columns = one 128-byte staging row
 constexpr int NBUF = 4;                // staging buffers
@@ -52,7 +58,7 @@ struct alignas(64) Params {
   int splits, kb_per_split;            // partial item s covers flat k-blocks [s*kb_per_split, (s+1)*kb_per_split)
   float* ws;
   int epi_tma; uint32_t r_bytes;       // epilogue through smem staging + TMA (else guarded direct stores)
-  float* D; const float* R; const float* bias;
+  void* D; const void* R; const float* bias;
   long ldd, sDb, sDh, ldr, sRb, sRh;
   float alpha, beta;
   int round_tf32;
@@ -132,8 +138,74 @@ __device__ __forceinline__ bool tile_row(const Params& p, const Tile& t, int r, 
   return (t.m0 + r) < p.M;
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_constant__ Params p) {
+// 32 accumulator columns of tile row r -> staging row (swizzled 16-byte chunks), fused with alpha / bias / residual
+// (the residual chunk is already in the staging buffer) / rounding
+template <bool OUT16>
+__device__ __forceinline__ void stage_chunk(uint8_t* buf, int r, const uint32_t (&v)[32], float alpha, float beta,
+                                            const float* bias, int nc, int N, bool full, bool has_r, int rnd) {
+  if constexpr (!OUT16) {
+    uint8_t* row = buf + r * 128;
+    const uint32_t swz = uint32_t(r & 7);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      float4* sp = reinterpret_cast<float4*>(row + ((uint32_t(j >> 2) ^ swz) << 4));
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
+      if (bias) {
+        if (full) {
+          const float4 bv = *reinterpret_cast<const float4*>(bias + nc + j);
+          o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (nc + j + e < N) o[e] += bias[nc + j + e];
+        }
+      }
+      if (has_r) {
+        const float4 rv = *sp;
+        o[0] += beta * rv.x; o[1] += beta * rv.y; o[2] += beta * rv.z; o[3] += beta * rv.w;
+      }
+      if (rnd) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
+      }
+      *sp = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    uint8_t* row = buf + r * 64;
+    const uint32_t swz = uint32_t((r >> 1) & 3);
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4* sp = reinterpret_cast<uint4*>(row + ((uint32_t(j >> 3) ^ swz) << 4));
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
+      if (bias) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (full || nc + j + e < N) o[e] += bias[nc + j + e];
+      }
+      if (has_r) {
+        const uint4 rv = *sp;
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(rh[e]);
+          o[2 * e] += beta * f.x; o[2 * e + 1] += beta * f.y;
+        }
+      }
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+      *sp = ov;
+    }
+  }
+}
+
+template <int BN, int STAGES, bool AB16, bool D16>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
+  using OutT = typename std::conditional<D16, __half, float>::type;
+  constexpr int KB_ELEMS = AB16 ? BK16 : BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   using S = Smem<BN, STAGES>;
@@ -188,11 +260,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
           mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
           if (p.conv) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, t.cx0 + dx, t.cy0 + dy, t.cb0);
-            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], tap * p.conv_ctot + kb * BK, t.n0, 0, 0);
+            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.cx0 + dx, t.cy0 + dy, t.cb0);
+            // filter as a (channel, tap, out-channel) tensor: a k-block running past the channel count is zero-filled
+            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, tap, t.n0, 0);
           } else {
-            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * BK, t.m0, t.bat_h * p.a_hmul[s], t.bat_b * p.a_bmul[s]);
-            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * BK, t.n0, t.bat_h * p.b_hmul[s], t.bat_b * p.b_bmul[s]);
+            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.m0, t.bat_h * p.a_hmul[s], t.bat_b * p.a_bmul[s]);
+            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, t.n0, t.bat_h * p.b_hmul[s], t.bat_b * p.b_bmul[s]);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -201,7 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) |
+      // instruction descriptor: fp32 accumulate; A/B format tf32 (2) or f16 (0); N >> 3, M >> 4
+      constexpr uint32_t idesc = (1u << 4) | (AB16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(BN >> 3) << 17) |
                                  (uint32_t(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int li = 0;
@@ -220,9 +294,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + S::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
-            mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // advance 8 tf32 / 16 halves = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
+            if constexpr (AB16)
+              mma_f16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+            else
+              mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
           }
           tcgen05_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -235,17 +312,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // tile row
     const bool t0 = (threadIdx.x == 64);      // the thread that drives the staging TMA traffic
-    const uint32_t swz = uint32_t(r & 7);
     uint32_t gch = 0;                         // chunks pushed through the staging ring so far (this CTA)
     uint32_t r_par = 0;                       // bit b: parity of the next residual load into staging buffer b
+    constexpr int TAILQ = D16 ? 7 : 3;        // TMA stores clip the inner dimension in 16-byte units
     int li = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
       const Tile t = decode_item<BN>(p, item);
       const int as = li & 1;
       const int nchunks = min(BN / EPI_W, (p.N - t.n0 + EPI_W - 1) / EPI_W);
-      // TMA stores clip the inner dimension in 16-byte units: a ragged last chunk (N % 4 != 0) takes the guarded direct path
+      // a ragged last chunk (N not a multiple of 16 bytes) takes the guarded direct path
       const int ntma = t.partial ? nchunks
-                                 : !p.epi_tma ? 0 : ((p.N & 3) && t.n0 + nchunks * EPI_W > p.N) ? nchunks - 1 : nchunks;
+                                 : !p.epi_tma ? 0 : ((p.N & TAILQ) && t.n0 + nchunks * EPI_W > p.N) ? nchunks - 1 : nchunks;
       const uint32_t acc = tmem_base + uint32_t(as * ACC_STRIDE) + (uint32_t(q * 32) << 16);
       const float alpha = t.partial ? 1.f : p.alpha, beta = p.beta;
       const bool has_r = p.R != nullptr && !t.partial;
@@ -282,53 +359,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
         const bool full = (nc + EPI_W <= p.N);
         if (c < ntma) {
           const uint32_t b = gch % NBUF;
-          uint8_t* sbuf = staging + b * EPI_BYTES + r * 128;
+          uint8_t* sbuf = staging + b * EPI_BYTES;
           if (has_r) { mbar_wait(&r_bar[b], (r_par >> b) & 1u); r_par ^= 1u << b; }
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4* sp = reinterpret_cast<float4*>(sbuf + ((uint32_t(j >> 2) ^ swz) << 4));
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[j + e]);
-            if (bias) {
-              if (full) {
-                const float4 bv = *reinterpret_cast<const float4*>(bias + nc + j);
-                o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) if (nc + j + e < p.N) o[e] += bias[nc + j + e];
-              }
-            }
-            if (has_r) {
-              const float4 rv = *sp;
-              o[0] += beta * rv.x; o[1] += beta * rv.y; o[2] += beta * rv.z; o[3] += beta * rv.w;
-            }
-            if (rnd) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
-            }
-            *sp = make_float4(o[0], o[1], o[2], o[3]);
-          }
+          if (t.partial) stage_chunk<false>(sbuf, r, v, alpha, beta, bias, nc, p.N, full, has_r, rnd);
+          else stage_chunk<D16>(sbuf, r, v, alpha, beta, bias, nc, p.N, full, has_r, rnd);
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (t0) {
-            tma_store_4d(dmap, staging + b * EPI_BYTES, dcol0 + c * EPI_W, c1, c2, c3);
+            tma_store_4d(dmap, sbuf, dcol0 + c * EPI_W, c1, c2, c3);
             bulk_commit();
             bulk_wait_read<1>();              // every store but the newest has left its staging buffer
             if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
           }
           ++gch;
         } else if (row_ok) {
-          float* dptr = p.D + d_off + nc;
-          const float* rptr = has_r ? p.R + r_off + nc : nullptr;
+          OutT* dptr = static_cast<OutT*>(p.D) + d_off + nc;
+          const OutT* rptr = has_r ? static_cast<const OutT*>(p.R) + r_off + nc : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (nc + j < p.N) {
               float o = alpha * __uint_as_float(v[j]);
               if (bias) o += bias[nc + j];
-              if (rptr) o += beta * rptr[j];
-              if (rnd) o = rna_tf32(o);
-              dptr[j] = o;
+              if (rptr) o += beta * static_cast<float>(rptr[j]);
+              if (rnd && !D16) o = rna_tf32(o);
+              dptr[j] = static_cast<OutT>(o);
             }
           }
         }
@@ -346,8 +400,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tf32_kernel(const __grid_con
 
 // Sums the `splits` partial tiles of every split tile in split order and applies the epilogue.  One thread per
 // (tile row, 4 columns); partials are [tile][split][128][BN] fp32, L2-resident right after the GEMM.
-template <int BN>
+template <int BN, bool D16>
 __global__ void __launch_bounds__(256) splitk_reduce_k(const __grid_constant__ Params p, int ntail) {
+  using OutT = typename std::conditional<D16, __half, float>::type;
   constexpr int QN = BN / 4;
   const long total = static_cast<long>(ntail) * BM * QN;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -366,30 +421,25 @@ __global__ void __launch_bounds__(256) splitk_reduce_k(const __grid_constant__ P
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
     float o[4] = {a.x * p.alpha, a.y * p.alpha, a.z * p.alpha, a.w * p.alpha};
-    float* dptr = p.D + d_off + nc;
-    const float* rptr = p.R ? p.R + r_off + nc : nullptr;
-    if (nc + 4 <= p.N) {
-      if (p.bias) {
-        const float4 bv = *reinterpret_cast<const float4*>(p.bias + nc);
-        o[0] += bv.x; o[1] += bv.y; o[2] += bv.z; o[3] += bv.w;
+    OutT* dptr = static_cast<OutT*>(p.D) + d_off + nc;
+    const OutT* rptr = p.R ? static_cast<const OutT*>(p.R) + r_off + nc : nullptr;
+    const int nv = min(4, p.N - nc);
+    for (int e = 0; e < nv; ++e) {
+      if (p.bias) o[e] += p.bias[nc + e];
+      if (rptr) o[e] += p.beta * static_cast<float>(rptr[e]);
+      if (p.round_tf32 && !D16) o[e] = rna_tf32(o[e]);
+    }
+    if (nv == 4) {
+      if constexpr (D16) {
+        uint2 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+        oh[0] = __floats2half2_rn(o[0], o[1]); oh[1] = __floats2half2_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(dptr) = ov;
+      } else {
+        *reinterpret_cast<float4*>(dptr) = make_float4(o[0], o[1], o[2], o[3]);
       }
-      if (rptr) {
-        const float4 rv = *reinterpret_cast<const float4*>(rptr);
-        o[0] += p.beta * rv.x; o[1] += p.beta * rv.y; o[2] += p.beta * rv.z; o[3] += p.beta * rv.w;
-      }
-      if (p.round_tf32) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
-      }
-      *reinterpret_cast<float4*>(dptr) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
-      for (int e = 0; e < 4 && nc + e < p.N; ++e) {
-        float v = o[e];
-        if (p.bias) v += p.bias[nc + e];
-        if (rptr) v += p.beta * rptr[e];
-        if (p.round_tf32) v = rna_tf32(v);
-        dptr[e] = v;
-      }
+      for (int e = 0; e < nv; ++e) dptr[e] = static_cast<OutT>(o[e]);
     }
   }
 }
@@ -414,10 +464,9 @@ static EncodeFn get_encode() {
   return fn;
 }
 
-static int g_tmap_dtype_tf32 = 0;   // 0: FLOAT32 (MMA truncates), 1: TFLOAT32 tensor-map type
-
-const char* encode4(CUtensorMap* m, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                           const uint32_t box[4]) {
+// 4-D tiled tensor map over fp32 (f16 = 0) or fp16 (f16 = 1) elements; strides in bytes; swizzle 128 or 64 bytes
+const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4], int swizzle_bytes) {
   EncodeFn fn = get_encode();
   if (!fn) return "cuTensorMapEncodeTiled entry point not available";
   cuuint64_t gd[4]; cuuint64_t gs[3]; cuuint32_t bx[4]; cuuint32_t es[4] = {1, 1, 1, 1};
@@ -426,10 +475,10 @@ const char* encode4(CUtensorMap* m, const float* base, const uint64_t dims[4], c
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return "tensor base not 16-byte aligned";
   for (int i = 0; i < 3; ++i)
     if (gs[i] % 16 != 0 || gs[i] == 0) return "tensor stride not a positive multiple of 16 bytes";
-  CUresult r = fn(m, g_tmap_dtype_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                  const_cast<float*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd,
+                  gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[256];
     snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u",
@@ -440,18 +489,28 @@ const char* encode4(CUtensorMap* m, const float* base, const uint64_t dims[4], c
   }
   return nullptr;
 }
+const char* encode4(CUtensorMap* m, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                    const uint32_t box[4]) {
+  return encode4x(m, base, 0, dims, strides_bytes, box, 128);
+}
 
-// plain operand [rows][K] with (h, b) batch strides; stride 0 => broadcast (extent 1)
-const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, long ld, long sh, int nh, long sb,
-                                int nb, int box_rows, int* hmul, int* bmul, uint32_t* bytes) {
+// plain operand [rows][K] with (h, b) batch strides (in elements); stride 0 => broadcast (extent 1).
+// box = box_cols x min(box_rows, rows); *bytes = bytes one box delivers
+const char* encode_plainx(CUtensorMap* m, const void* base, int f16, int rows, int K, long ld, long sh, int nh, long sb,
+                          int nb, int box_cols, int box_rows, int swizzle_bytes, int* hmul, int* bmul, uint32_t* bytes) {
+  const uint64_t es = f16 ? 2 : 4;
   box_rows = std::min(box_rows, rows);
-  *bytes = uint32_t(box_rows) * BK * 4;
+  *bytes = uint32_t(box_rows) * box_cols * es;
   *hmul = (sh != 0 && nh > 1) ? 1 : 0;
   *bmul = (sb != 0 && nb > 1) ? 1 : 0;
   uint64_t dims[4] = {uint64_t(K), uint64_t(rows), uint64_t(*hmul ? nh : 1), uint64_t(*bmul ? nb : 1)};
-  uint64_t st[3] = {uint64_t(ld) * 4, uint64_t(*hmul ? sh : ld) * 4, uint64_t(*bmul ? sb : ld) * 4};
-  uint32_t box[4] = {uint32_t(BK), uint32_t(box_rows), 1, 1};
-  return encode4(m, base, dims, st, box);
+  uint64_t st[3] = {uint64_t(ld) * es, uint64_t(*hmul ? sh : ld) * es, uint64_t(*bmul ? sb : ld) * es};
+  uint32_t box[4] = {uint32_t(box_cols), uint32_t(box_rows), 1, 1};
+  return encode4x(m, base, f16, dims, st, box, swizzle_bytes);
+}
+const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, long ld, long sh, int nh, long sb,
+                         int nb, int box_rows, int* hmul, int* bmul, uint32_t* bytes) {
+  return encode_plainx(m, base, 0, rows, K, ld, sh, nh, sb, nb, BK, box_rows, 128, hmul, bmul, bytes);
 }
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
@@ -466,36 +525,42 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AB16, bool D16>
 static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(2 * BN <= 512 && BN <= ACC_STRIDE, "two accumulator stages must fit TMEM");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AB16, D16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          S::TOTAL);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     configured = true;
   }
-  gemm_tf32_kernel<BN, STAGES><<<grid, NTHREADS, S::TOTAL, st>>>(p);
+  gemm_tc_kernel<BN, STAGES, AB16, D16><<<grid, NTHREADS, S::TOTAL, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);
   if (p.splits > 1) {
     const int ntail = (p.items - p.full_tiles) / p.splits;
     const long threads = static_cast<long>(ntail) * BM * (BN / 4);
     const int blocks = (int)std::min<long>((threads + 255) / 256, 8L * sm_count());
-    splitk_reduce_k<BN><<<blocks, 256, 0, st>>>(p, ntail);
+    splitk_reduce_k<BN, D16><<<blocks, 256, 0, st>>>(p, ntail);
     e = cudaGetLastError();
   }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
+template <bool AB16, bool D16>
+static const char* launch_bn(int BN, const Params& p, int grid, cudaStream_t st) {
+  if (BN == 160) return launch_t<160, 4, AB16, D16>(p, grid, st);
+  if (BN == 128) return launch_t<128, 5, AB16, D16>(p, grid, st);
+  if (BN == 64) return launch_t<64, 6, AB16, D16>(p, grid, st);
+  return "gemm: unsupported tile width";
+}
+
 }  // namespace pbgemm
 
-extern "C" __attribute__((visibility("default"))) void pb_gemm_set_tmap_tf32(int on) { pbgemm::g_tmap_dtype_tf32 = on; }
-
-// tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic), split-K policy (0 off, 1 heuristic,
+// tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic), split policy (0 off, 1 heuristic,
 // >1 forced split count), allow BN = 160
 static int g_force_bn = 0, g_split = 1, g_use160 = 1, g_split_min_kb = 48;
 extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int split, int use160) {
@@ -507,6 +572,11 @@ extern "C" __attribute__((visibility("default"))) void pb_gemm_tune_split_min_kb
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   using namespace pbgemm;
   if (g.M <= 0 || g.N <= 0) return "gemm: empty problem";
+  const int ab16 = g.ab_dtype == PB_GEMM_F16, d16 = g.d_dtype == PB_GEMM_F16;
+  if (!ab16 && d16) return "gemm: fp16 output needs fp16 operands";
+  const int KB = ab16 ? BK16 : BK;            // k-block in elements (128 bytes)
+  const long aes = ab16 ? 2 : 4, des = d16 ? 2 : 4;
+  const int dq = d16 ? 8 : 4;                 // elements per 16 bytes of D / R
   Params p;
   memset(&p, 0, sizeof p);
   p.nseg = g.nseg; p.M = g.M; p.N = g.N; p.nb = g.nb; p.nh = g.nh;
@@ -514,9 +584,9 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   p.D = g.D; p.R = g.R; p.bias = g.bias;
   p.ldd = g.ldd; p.sDb = g.sDb; p.sDh = g.sDh; p.ldr = g.ldr; p.sRb = g.sRb; p.sRh = g.sRh;
   p.alpha = g.alpha; p.beta = g.R ? g.beta : 0.f; p.round_tf32 = g.round_tf32;
-  if ((g.ldd % 4) || (g.R && (g.ldr % 4)) || (reinterpret_cast<uintptr_t>(g.D) & 15) ||
+  if ((g.ldd % dq) || (g.R && (g.ldr % dq)) || (reinterpret_cast<uintptr_t>(g.D) & 15) ||
       (g.R && (reinterpret_cast<uintptr_t>(g.R) & 15)) || (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)))
-    return "gemm: D/R/bias must be 16-byte aligned with ld % 4 == 0";
+    return "gemm: D/R/bias must be 16-byte aligned with a leading dimension that is a multiple of 16 bytes";
 
   long mt;
   if (g.conv) {
@@ -547,58 +617,65 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   for (int s = 0; s < g.nseg; ++s) {
     const PbGemmSeg& sg = g.seg[s];
     if (sg.K <= 0) return "gemm: empty K segment";
-    p.kblocks[s] = (sg.K + BK - 1) / BK;
+    p.kblocks[s] = (sg.K + KB - 1) / KB;
     ktot += p.kblocks[s];
     const char* err;
     if (g.conv) {
       if (g.nseg != 1) return "gemm: conv mode takes one segment";
-      if (sg.K % BK) return "gemm: conv channels must be a multiple of 32";
+      if (sg.K % 8) return "gemm: conv channels must be a multiple of 8";
       p.conv_ctot = sg.K;
       uint64_t dims[4] = {uint64_t(sg.K), uint64_t(g.W), uint64_t(g.H), uint64_t(g.nb)};
-      uint64_t stb[3] = {uint64_t(sg.lda) * 4, uint64_t(sg.lda) * 4 * g.W, uint64_t(sg.lda) * 4 * g.W * g.H};
-      uint32_t box[4] = {uint32_t(BK), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
-      err = encode4(&p.mapA[s], sg.A, dims, stb, box);
+      uint64_t stb[3] = {uint64_t(sg.lda) * aes, uint64_t(sg.lda) * aes * g.W, uint64_t(sg.lda) * aes * g.W * g.H};
+      uint32_t box[4] = {uint32_t(KB), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
+      err = encode4x(&p.mapA[s], sg.A, ab16, dims, stb, box, 128);
       if (err) return err;
-      int hm, bm; uint32_t bbytes;
-      err = encode_plain(&p.mapB[s], sg.B, g.N, 9 * sg.K, sg.ldb, 0, 1, 0, 1, BN, &hm, &bm, &bbytes);
+      // packed filter [N][9][C] as a (C, tap, N) tensor
+      uint64_t bd[4] = {uint64_t(sg.K), 9, uint64_t(g.N), 1};
+      uint64_t bs[3] = {uint64_t(sg.K) * aes, uint64_t(sg.ldb) * aes, uint64_t(sg.ldb) * aes};
+      const uint32_t brow = (uint32_t)std::min(BN, g.N);
+      uint32_t bbox[4] = {uint32_t(KB), 1, brow, 1};
+      err = encode4x(&p.mapB[s], sg.B, ab16, bd, bs, bbox, 128);
       if (err) return err;
-      p.tx_bytes[s] = uint32_t(p.bw * p.bh * p.bb) * BK * 4 + bbytes;
+      p.tx_bytes[s] = uint32_t(p.bw * p.bh * p.bb + brow) * 128;
     } else {
       uint32_t abytes, bbytes;
-      err = encode_plain(&p.mapA[s], sg.A, g.M, sg.K, sg.lda, sg.sAh, g.nh, sg.sAb, g.nb, BM, &p.a_hmul[s],
-                         &p.a_bmul[s], &abytes);
+      err = encode_plainx(&p.mapA[s], sg.A, ab16, g.M, sg.K, sg.lda, sg.sAh, g.nh, sg.sAb, g.nb, KB, BM, 128, &p.a_hmul[s],
+                          &p.a_bmul[s], &abytes);
       if (err) return err;
-      err = encode_plain(&p.mapB[s], sg.B, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sg.sBb, g.nb, BN, &p.b_hmul[s],
-                         &p.b_bmul[s], &bbytes);
+      err = encode_plainx(&p.mapB[s], sg.B, ab16, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sg.sBb, g.nb, KB, BN, 128, &p.b_hmul[s],
+                          &p.b_bmul[s], &bbytes);
       if (err) return err;
       p.tx_bytes[s] = abytes + bbytes;
     }
   }
   ktot *= p.taps;
 
-  // epilogue tensor maps (D store / R load through the staging buffers); narrow outputs use guarded direct stores
+  // epilogue tensor maps (D store / R load through the staging buffers: 32-column chunks, 128-byte fp32 or 64-byte fp16
+  // rows); narrow outputs use guarded direct stores
   p.epi_tma = g.N >= EPI_W ? 1 : 0;
   if (p.epi_tma) {
     const char* err;
+    const int swz = d16 ? 64 : 128;
     if (g.conv) {
       uint32_t box[4] = {uint32_t(EPI_W), uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
       uint64_t dims[4] = {uint64_t(g.N), uint64_t(g.W), uint64_t(g.H), uint64_t(g.nb)};
-      uint64_t sd[3] = {uint64_t(g.ldd) * 4, uint64_t(g.ldd) * 4 * g.W, uint64_t(g.ldd) * 4 * g.W * g.H};
-      err = encode4(&p.mapD, g.D, dims, sd, box);
+      uint64_t sd[3] = {uint64_t(g.ldd) * des, uint64_t(g.ldd) * des * g.W, uint64_t(g.ldd) * des * g.W * g.H};
+      err = encode4x(&p.mapD, g.D, d16, dims, sd, box, swz);
       if (err) return err;
       if (g.R) {
-        uint64_t sr[3] = {uint64_t(g.ldr) * 4, uint64_t(g.ldr) * 4 * g.W, uint64_t(g.ldr) * 4 * g.W * g.H};
-        err = encode4(&p.mapR, g.R, dims, sr, box);
+        uint64_t sr[3] = {uint64_t(g.ldr) * des, uint64_t(g.ldr) * des * g.W, uint64_t(g.ldr) * des * g.W * g.H};
+        err = encode4x(&p.mapR, g.R, d16, dims, sr, box, swz);
         if (err) return err;
       }
-      p.r_bytes = uint32_t(p.bw * p.bh * p.bb) * EPI_W * 4;
+      p.r_bytes = uint32_t(p.bw * p.bh * p.bb) * EPI_W * des;
     } else {
       int hm, bm;
-      err = encode_plain(&p.mapD, g.D, g.M, g.N, g.ldd, g.sDh, g.nh, g.sDb, g.nb, BM, &p.d_hmul, &p.d_bmul, &p.r_bytes);
+      err = encode_plainx(&p.mapD, g.D, d16, g.M, g.N, g.ldd, g.sDh, g.nh, g.sDb, g.nb, EPI_W, BM, swz, &p.d_hmul, &p.d_bmul,
+                          &p.r_bytes);
       if (err) return err;
       if ((g.nh > 1 && !p.d_hmul) || (g.nb > 1 && !p.d_bmul)) return "gemm: D needs a stride for every batch dimension";
       if (g.R) {
-        err = encode_plain(&p.mapR, g.R, g.M, g.N, g.ldr, g.sRh, g.nh, g.sRb, g.nb, BM, &hm, &bm, &p.r_bytes);
+        err = encode_plainx(&p.mapR, g.R, d16, g.M, g.N, g.ldr, g.sRh, g.nh, g.sRb, g.nb, EPI_W, BM, swz, &hm, &bm, &p.r_bytes);
         if (err) return err;
         if (hm != p.d_hmul || bm != p.d_bmul) return "gemm: R must be batched like D";
       }
@@ -626,7 +703,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       uint64_t dims[4] = {uint64_t(BN), uint64_t(tail) * p.splits * BM, 1, 1};
       uint64_t sw[3] = {uint64_t(BN) * 4, uint64_t(BN) * 4, uint64_t(BN) * 4};
       uint32_t box[4] = {uint32_t(EPI_W), uint32_t(BM), 1, 1};
-      const char* err = encode4(&p.mapW, g.ws, dims, sw, box);
+      const char* err = encode4x(&p.mapW, g.ws, 0, dims, sw, box, 128);
       if (err) return err;
     } else {
       tail = 0;
@@ -635,8 +712,6 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   p.full_tiles = (int)full;
   p.items = (int)(full + tail * p.splits);
   const int grid = (int)std::min<long>(p.items, nsm);
-  if (BN == 160) return launch_t<160, 4>(p, grid, st);
-  if (BN == 128) return launch_t<128, 5>(p, grid, st);
-  if (BN == 64) return launch_t<64, 6>(p, grid, st);
-  return "gemm: unsupported tile width";
+  if (ab16) return d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
+  return launch_bn<false, false>(BN, p, grid, st);
 }

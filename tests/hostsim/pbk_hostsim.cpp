@@ -30,6 +30,10 @@ inline float trunc_tf32(float x) { if (kExact) return x; uint32_t u; memcpy(&u, 
 inline float mr(float x, int r) { return r ? rna(x) : x; }
 inline float opA(float x, int precise) { return precise == 1 ? x : trunc_tf32(x); }
 inline float opB(float x, int precise) { return precise >= 1 ? x : trunc_tf32(x); }
+// element accessors for buffers that are fp32 (dt = 0) or fp16 (dt = 1; round-to-nearest-even like cvt.rn.f16.f32)
+using h16 = _Float16;
+inline float ldx(const void* p, int dt, long i) { return dt ? (float)static_cast<const h16*>(p)[i] : static_cast<const float*>(p)[i]; }
+inline void stx(void* p, int dt, long i, float v) { if (dt) static_cast<h16*>(p)[i] = (h16)v; else static_cast<float*>(p)[i] = v; }
 inline float sigm(float x) { return 1.f / (1.f + std::exp(-x)); }
 inline float silu_f(float x) { return x * sigm(x); }
 inline float silu_d(float x) { float s = sigm(x); return s * (1.f + x * (1.f - s)); }
@@ -51,10 +55,12 @@ PBK pbk_graph_destroy(void*) { return nullptr; }
 PBK pbk_gemm(const PbGemm* gp, pb_stream) {
   const PbGemm& g = *gp;
   if (g.M <= 0 || g.N <= 0) return "gemm: empty problem";
+  const int ab = g.ab_dtype, dd = g.d_dtype;
+  if (!ab && dd) return "gemm: fp16 output needs fp16 operands";
   if (g.conv) {
     const PbGemmSeg& s = g.seg[0];
     const int C = s.K, H = g.H, W = g.W;
-    if (C % 32) return "gemm: conv channels must be a multiple of 32";
+    if (C % 8) return "gemm: conv channels must be a multiple of 8";
 #pragma omp parallel for collapse(2) schedule(static)
     for (long pix = 0; pix < (long)g.nb * H * W; ++pix)
       for (int n = 0; n < g.N; ++n) {
@@ -63,16 +69,18 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
         for (int tap = 0; tap < 9; ++tap) {
           const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
           if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-          const float* a = s.A + ((b * H + iy) * W + ix) * s.lda;
-          const float* w = s.B + (long)n * s.ldb + (long)tap * C;
+          const long a0 = ((b * H + iy) * W + ix) * s.lda;
+          const long w0 = (long)n * s.ldb + (long)tap * C;
           float part = 0.f;
-          for (int c = 0; c < C; ++c) part += opA(a[c], g.precise) * opB(w[c], g.precise);
+          for (int c = 0; c < C; ++c)
+            part += ab ? ldx(s.A, 1, a0 + c) * ldx(s.B, 1, w0 + c)
+                       : opA(ldx(s.A, 0, a0 + c), g.precise) * opB(ldx(s.B, 0, w0 + c), g.precise);
           acc += part;
         }
         float v = g.alpha * (float)acc;
         if (g.bias) v += g.bias[n];
-        if (g.R) v += g.beta * g.R[pix * g.ldr + n];
-        g.D[pix * g.ldd + n] = mr(v, g.round_tf32);
+        if (g.R) v += g.beta * ldx(g.R, dd, pix * g.ldr + n);
+        stx(g.D, dd, pix * g.ldd + n, dd ? v : mr(v, g.round_tf32));
       }
     return nullptr;
   }
@@ -84,16 +92,18 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
           double acc = 0.0;
           for (int si = 0; si < g.nseg; ++si) {
             const PbGemmSeg& s = g.seg[si];
-            const float* a = s.A + b * s.sAb + h * s.sAh + (long)m * s.lda;
-            const float* w = s.B + b * s.sBb + h * s.sBh + (long)n * s.ldb;
+            const long a0 = b * s.sAb + h * s.sAh + (long)m * s.lda;
+            const long w0 = b * s.sBb + h * s.sBh + (long)n * s.ldb;
             float part = 0.f;
-            for (int k = 0; k < s.K; ++k) part += opA(a[k], g.precise) * opB(w[k], g.precise);
+            for (int k = 0; k < s.K; ++k)
+              part += ab ? ldx(s.A, 1, a0 + k) * ldx(s.B, 1, w0 + k)
+                         : opA(ldx(s.A, 0, a0 + k), g.precise) * opB(ldx(s.B, 0, w0 + k), g.precise);
             acc += part;
           }
           float v = g.alpha * (float)acc;
           if (g.bias) v += g.bias[n];
-          if (g.R) v += g.beta * g.R[b * g.sRb + h * g.sRh + (long)m * g.ldr + n];
-          g.D[b * g.sDb + h * g.sDh + (long)m * g.ldd + n] = mr(v, g.round_tf32);
+          if (g.R) v += g.beta * ldx(g.R, dd, b * g.sRb + h * g.sRh + (long)m * g.ldr + n);
+          stx(g.D, dd, b * g.sDb + h * g.sDh + (long)m * g.ldd + n, dd ? v : mr(v, g.round_tf32));
         }
     }
   return nullptr;
@@ -369,8 +379,8 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
         for (int c = 0; c < a.Nc; ++c) {
           float s = 0.f;
           for (int sg = 0; sg < a.nseg; ++sg) {
-            const float* A = a.seg[sg].A + b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
-            const float* B = a.seg[sg].B + b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
+            const float* A = static_cast<const float*>(a.seg[sg].A) + b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
+            const float* B = static_cast<const float*>(a.seg[sg].B) + b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
             for (int k = 0; k < a.d; ++k) s += trunc_tf32(A[k]) * trunc_tf32(B[k]);
           }
           float dl = 0.f;

@@ -33,7 +33,8 @@ def tf32_trunc(t):
 
 
 def gemm(A, B, D, *, M, N_, K, lda, ldb, ldd, sAb=0, sAh=0, sBb=0, sBh=0, sDb=0, sDh=0, nb=1, nh=1,
-         bias=None, R=None, ldr=0, sRb=0, sRh=0, alpha=1.0, beta=0.0, conv=0, H=0, W=0, seg2=None, rnd=0, splitk=True):
+         bias=None, R=None, ldr=0, sRb=0, sRh=0, alpha=1.0, beta=0.0, conv=0, H=0, W=0, seg2=None, rnd=0, splitk=True,
+         ab_dtype=0, d_dtype=0):
     g = N.PbGemm()
     g.M, g.N, g.nseg = M, N_, 1 if seg2 is None else 2
     s = g.seg[0]
@@ -47,6 +48,7 @@ def gemm(A, B, D, *, M, N_, K, lda, ldb, ldd, sAb=0, sAh=0, sBb=0, sBh=0, sDb=0,
     g.ldr, g.sRb, g.sRh = ldr, sRb, sRh
     g.bias = bias.data_ptr() if bias is not None else None
     g.alpha, g.beta, g.nb, g.nh, g.conv, g.H, g.W, g.round_tf32 = alpha, beta, nb, nh, conv, H, W, rnd
+    g.ab_dtype, g.d_dtype = ab_dtype, d_dtype
     if splitk:                               # split-K scratch as the engine provides it
         ws = _scratch()
         g.ws, g.ws_floats = ws.data_ptr(), ws.numel()
@@ -60,6 +62,11 @@ def _scratch():
     if not _SCRATCH:
         _SCRATCH.append(torch.empty(8 << 20, device="cuda"))
     return _SCRATCH[0]
+
+
+def gemm16(A, B, D, *, M, N_, K, lda, ldb, ldd, out16=True, **kw):
+    """fp16-operand GEMM (kind::f16); D / R are fp16 (out16) or fp32."""
+    return gemm(A, B, D, M=M, N_=N_, K=K, lda=lda, ldb=ldb, ldd=ldd, ab_dtype=1, d_dtype=1 if out16 else 0, **kw)
 
 
 def rel(a, b):
@@ -84,6 +91,67 @@ def test_gemm_plain(M, Nn, K):
     assert rel(D[:, :Nn], ref) < 1e-5
     if Np > Nn:
         assert torch.isnan(D[:, Nn:]).all()           # columns beyond N untouched
+
+
+@pytest.mark.parametrize("out16", [True, False])
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (300, 200, 96), (64, 40, 40), (1000, 1280, 1280), (320, 1280, 11520),
+                                    (20480, 320, 320), (130, 7, 64), (257, 13, 104), (64, 16, 16), (700, 77, 160),
+                                    (3000, 4096, 40), (4096, 960, 320)])
+def test_gemm_f16_plain(M, Nn, K, out16):
+    torch.manual_seed(M + Nn + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.randn(M, Kp, device="cuda").half()
+    B = torch.randn(Nn, Kp, device="cuda").half()
+    q = 8 if out16 else 4
+    Np = (Nn + q - 1) // q * q
+    odt = torch.float16 if out16 else torch.float32
+    bias = torch.randn(Np, device="cuda")
+    R = torch.randn(M, Np, device="cuda").to(odt)
+    D = torch.full((M, Np), float("nan"), device="cuda", dtype=odt)
+    gemm16(A, B, D, M=M, N_=Nn, K=K, lda=Kp, ldb=Kp, ldd=Np, out16=out16, bias=bias, R=R, ldr=Np, alpha=0.25, beta=2.0)
+    ref = 0.25 * (A[:, :K].double() @ B[:, :K].double().T) + bias[:Nn].double() + 2.0 * R[:, :Nn].double()
+    assert rel(D[:, :Nn], ref) < (6e-4 if out16 else 1e-5)
+    if out16:                                           # correctly rounded: at most one fp16 ulp from the exact result
+        assert ((D[:, :Nn].double() - ref).abs() <= ref.abs() * 2 ** -10 + 1e-3).all()
+    if Np > Nn:
+        assert torch.isnan(D[:, Nn:]).all()
+
+
+@pytest.mark.parametrize("nb,H,W,Ci,Co", [(1, 64, 64, 320, 320), (5, 8, 8, 1280, 1280), (3, 16, 16, 64, 96), (2, 32, 32, 640, 320),
+                                          (5, 4, 4, 32, 64), (1, 2, 2, 32, 32), (2, 12, 12, 96, 64)])
+def test_gemm_f16_conv3x3(nb, H, W, Ci, Co):
+    """fp16 implicit-GEMM conv: filter read as a (channel, tap, out) tensor, so channel counts need not fill a k-block."""
+    torch.manual_seed(2)
+    x = torch.randn(nb, H, W, Ci, device="cuda").half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda") / math.sqrt(9 * Ci)).half()
+    fwd = w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci).contiguous()
+    R = torch.randn(nb, H, W, Co, device="cuda").half()
+    y = torch.zeros(nb, H, W, Co, device="cuda", dtype=torch.float16)
+    gemm16(x, fwd, y, M=nb * H * W, N_=Co, K=Ci, lda=Ci, ldb=9 * Ci, ldd=Co, nb=nb, conv=1, H=H, W=W, R=R, ldr=Co, beta=1.0)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, padding=1).permute(0, 2, 3, 1) + R.double()
+    assert rel(y, ref) < 6e-4
+
+
+def test_gemm_f16_attention_batched():
+    """Head-strided fp16 operands, fp32 scores out, then probabilities x V^T with a broadcast A (raster_b path)."""
+    torch.manual_seed(1)
+    nb, nh, Ntok, d = 3, 8, 256, 40
+    Cc = nh * d
+    Q = torch.randn(nb, Ntok, Cc, device="cuda").half()
+    Km = torch.randn(Ntok, Cc, device="cuda").half()
+    S = torch.zeros(nb, nh, Ntok, Ntok, device="cuda")
+    gemm16(Q, Km, S, M=Ntok, N_=Ntok, K=d, lda=Cc, sAb=Ntok * Cc, sAh=d, ldb=Cc, sBb=0, sBh=d, ldd=Ntok,
+           sDb=nh * Ntok * Ntok, sDh=Ntok * Ntok, nb=nb, nh=nh, alpha=d ** -0.5, out16=False)
+    q = Q.double().view(nb, Ntok, nh, d).permute(0, 2, 1, 3)
+    k = Km.double().view(Ntok, nh, d).permute(1, 0, 2)
+    assert rel(S, torch.einsum("bhid,hjd->bhij", q, k) * d ** -0.5) < 1e-5
+    P = torch.softmax(S[0], -1).half()                                   # [nh][N][N], shared by all tangents
+    dVt = torch.randn(nb, nh, d, Ntok, device="cuda").half()
+    O = torch.zeros(nb, Ntok, Cc, device="cuda", dtype=torch.float16)
+    gemm16(P, dVt, O, M=Ntok, N_=d, K=Ntok, lda=Ntok, sAb=0, sAh=Ntok * Ntok, ldb=Ntok, sBb=nh * d * Ntok, sBh=d * Ntok,
+           ldd=Cc, sDb=Ntok * Cc, sDh=d, nb=nb, nh=nh)
+    ref = torch.einsum("hij,bhdj->bihd", P.double(), dVt.double()).reshape(nb, Ntok, Cc)
+    assert rel(O, ref) < 6e-4
 
 
 @pytest.mark.parametrize("M,Nn,K,conv", [(320, 1280, 1280, 1), (320, 1280, 11520, 0), (64, 1280, 1280, 1), (1280, 640, 640, 1),
