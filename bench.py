@@ -11,8 +11,11 @@ k VJP columns + re-orthonormalisation; value = (ranks x steps x iterations) / se
 
   value     : inputs (x_t, ctx, V0) resident in HBM before the timed region, device-timed with CUDA events, max over ranks
   e2e       : the same steps through the C-ABI host entry pb_pullback_host (pinned HOST buffers in and out)
-  roofline  : algorithmic flops of one iteration (2 k F_tan) / measured iteration time, against the measured
-              dense bf16 peak of MEASURED_PEAKS.json (the MMA kind used is TF32, nominally half that peak)
+  roofline  : the dominant kernel (gemm_tc_kernel, the tcgen05 implicit-GEMM behind every conv / linear / attention product):
+              algorithmic flops (2 M N K per product) / device time of its launches, measured live with an event pair
+              around every launch of two eagerly launched iterations (pb_profile_*), against the measured dense bf16 peak of
+              MEASURED_PEAKS.json (the MMA kind used is TF32, nominally half that peak); `traffic` = DRAM bytes per launch from
+              the ncu pass committed under profiles/; `step_*` = the whole step (2 k F_tan per iteration)
   cpu_baseline (N = 1, rank 0): the oracle port of the reference algorithm on torch-CPU, one iteration
   --impl reference: the reference's CPU path (oracle port) alone, on the same config / metric
 
@@ -246,11 +249,39 @@ def run_ours(args, wl):
     h2d = 4 * (eng.n_in + (ctx.numel() if ctx is not None else 0) + k * eng.n_in)
     d2h = 4 * (k * eng.n_out + k + k * eng.n_in)
 
+    # ---- per-kernel timing: two eagerly launched iterations with an event pair around every contraction launch ----
+    prof, prof_iters = None, 2
+    if rank == 0:
+        eng.set_point(xd[0], tval, ctxd)
+        torch.cuda.synchronize()
+        eng.profile_begin()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        eng.pullback(v0d[0], prof_iters, prof_iters, 0.0)
+        pe1.record()
+        torch.cuda.synchronize()
+        prof = eng.profile_read()
+        prof["_eager_ms_per_iter"] = pe0.elapsed_time(pe1) / prof_iters
+
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
         flops_iter = 2.0 * k * f_tan * 1e9
         step_flops = flops_iter * iters + f_primal * 1e9
         achieved = step_flops * K / secs / 1e12 if f_tan else None
+        kernels = {}
+        for name in ("gemm_tc_kernel", "attn_lin_kernel"):
+            kms, kfl, kn = prof[name]
+            if kn:
+                kernels[name] = {"launches_per_iter": kn / prof_iters, "ms_per_iter": kms / prof_iters,
+                                 "avg_launch_us": 1e3 * kms / kn, "achieved_tflops": kfl / kms / 1e9,
+                                 "share_of_eager_iter": kms / prof_iters / prof["_eager_ms_per_iter"]}
+        dom = max(kernels, key=lambda n: kernels[n]["ms_per_iter"]) if kernels else None
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+        if dom and os.path.exists(tp):
+            tj = json.load(open(tp)).get(wl, {}).get(dom)
+            if tj:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
                 "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,

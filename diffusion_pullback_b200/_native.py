@@ -114,6 +114,10 @@ def _declare(L):
     L.pb_weight_info.restype = C.c_int
     L.pb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb_set_option.restype = C.c_int
+    L.pb_profile_begin.argtypes = [vp]
+    L.pb_profile_begin.restype = C.c_int
+    L.pb_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
+    L.pb_profile_read.restype = C.c_int
     for name in ("pb_create", "pb_plan", "pb_bind_weights", "pb_set_point", "pb_jvp", "pb_vjp",
                  "pb_orthonormalize", "pb_pullback", "pb_pullback_host"):
         getattr(L, name).restype = C.c_int

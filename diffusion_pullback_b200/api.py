@@ -63,7 +63,8 @@ def get_h_uncond(self, x=None, t=None, op=None, block_idx=None, verbose=False):
     return eng.set_point(x, _timestep(t), None, want_h=True)
 
 
-def _pullback(self, sample, timestep, ctx, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info):
+def _pullback(self, sample, timestep, ctx, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info,
+              tangent_group=None):
     time_s = time.time()
     k = int(pca_rank)
     ctx_len = ctx.shape[1] if ctx is not None else 0
@@ -75,7 +76,16 @@ def _pullback(self, sample, timestep, ctx, op, block_idx, pca_rank, min_iter, ma
         vT, _ = torch.linalg.qr(vT)
         v0 = vT.T.contiguous()
     eng.set_point(sample, _timestep(timestep), ctx)
-    u, s, vT, info = eng.pullback(v0, min_iter, max_iter, convergence_threshold)
+    if tangent_group is not None:
+        # one problem, k columns split over the ranks of the group (sharding.pullback_tangent_sharded); V0 of the
+        # group's first rank is used by everyone
+        import torch.distributed as dist
+        from .sharding import pullback_tangent_sharded
+        v0 = v0.to(sample.device, torch.float32).contiguous()
+        dist.broadcast(v0, src=dist.get_global_rank(tangent_group, 0), group=tangent_group)
+        u, s, vT, info = pullback_tangent_sharded(eng, v0, min_iter, max_iter, convergence_threshold, tangent_group)
+    else:
+        u, s, vT, info = eng.pullback(v0, min_iter, max_iter, convergence_threshold)
     print(f"power method : {info.iters_done - 1}-th step convergence : ", info.last_dist)
     if info.converged:
         print("reach convergence threshold : ", info.last_dist)
@@ -89,18 +99,22 @@ def _pullback(self, sample, timestep, ctx, op, block_idx, pca_rank, min_iter, ma
 @torch.no_grad()
 def local_encoder_pullback_zt(self, sample, timestep, encoder_hidden_states=None, op=None, block_idx=None,
                               pca_rank=50, chunk_size=25, min_iter=10, max_iter=100, convergence_threshold=1e-3,
-                              v0=None, return_info=False):
+                              v0=None, return_info=False, tangent_group=None):
     """`utils.py:722-816`.  `chunk_size` bounds memory in the reference and does not change results; the
-    k tangents always ride the batch axis of one pass here.  Returns (u [n_out,k], s [k], vT [k,n_in])."""
+    k tangents always ride the batch axis of one pass here.  Returns (u [n_out,k], s [k], vT [k,n_in]).
+    Extensions (defaults keep the reference behaviour): `v0` start subspace [k, n_in]; `return_info`;
+    `tangent_group`: a torch.distributed group whose ranks all make this call on the same problem and split its
+    k columns (one all-gather of W per iteration)."""
     return _pullback(self, sample, timestep, encoder_hidden_states, op, block_idx, pca_rank, min_iter, max_iter,
-                     convergence_threshold, v0, return_info)
+                     convergence_threshold, v0, return_info, tangent_group)
 
 
 @torch.no_grad()
 def local_encoder_pullback_xt(self, x, t, op=None, block_idx=None, pca_rank=50, chunk_size=25, min_iter=10, max_iter=100,
-                              convergence_threshold=1e-3, v0=None, return_info=False):
+                              convergence_threshold=1e-3, v0=None, return_info=False, tangent_group=None):
     """`utils.py:165-249` (unconditional `UNet2DModel`)."""
-    return _pullback(self, x, t, None, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info)
+    return _pullback(self, x, t, None, op, block_idx, pca_rank, min_iter, max_iter, convergence_threshold, v0, return_info,
+                     tangent_group)
 
 
 def patch_unet(unet):

@@ -98,6 +98,10 @@ struct pb_handle {
   // CUDA graph of one iteration (jvp + vjp + orthonormalise)
   void* graph = nullptr; int graph_k = 0; float graph_tol = 0.f; int use_graph = 1; bool warm = false;
   const float* graph_u = nullptr; const float* graph_s = nullptr; long graph_nodes = 0;
+  // timing probes (pb_profile_begin / pb_profile_read): one event pair per contraction-kernel launch
+  struct Probe { void* e0; void* e1; double flops; int kind; };
+  bool profiling = false;
+  std::vector<Probe> probes;
 
   float* P(int v) const { return reinterpret_cast<float*>(cache + vals[v].p_off); }
   float* T(int v) const { return reinterpret_cast<float*>(work + vals[v].t_off); }
@@ -372,10 +376,30 @@ struct Planner {
     if (e__) return fail(h, PB_ECUDA, std::string(#call ": ") + e__); \
   } while (0)
 
+// timing probe around one leaf launch (eager launches only: event records are not captured into the iteration graph)
+template <class F>
+const char* probed(pb_handle* h, int kind, double flops, pb_stream st, F&& launch) {
+  if (!h->profiling) return launch();
+  pb_handle::Probe pr{nullptr, nullptr, flops, kind};
+  if (const char* e = pbk_event_record(&pr.e0, st)) return e;
+  const char* err = launch();
+  if (const char* e = pbk_event_record(&pr.e1, st)) return e;
+  h->probes.push_back(pr);
+  return err;
+}
+
 // every GEMM gets the handle's split-K scratch (partial tiles of the K-split tail wave)
-const char* gemm_call(const pb_handle* h, PbGemm& g, pb_stream st) {
+const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
   g.ws = h->WP(h->w_splitk); g.ws_floats = (long)h->n_splitk;
-  return pbk_gemm(&g, st);
+  double k = 0;
+  for (int s = 0; s < g.nseg; ++s) k += g.seg[s].K;
+  const double flops = 2.0 * g.M * g.N * k * (g.conv ? 9.0 : (double)g.nb * g.nh);
+  return probed(h, PB_PROBE_GEMM, flops, st, [&] { return pbk_gemm(&g, st); });
+}
+// fused attention linearisation: S (nseg products over the head dim) + T . C1 per (tangent, head)
+const char* attn_lin_call(pb_handle* h, const PbAttnLin& a, pb_stream st) {
+  const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1) * a.nb * a.nh;
+  return probed(h, PB_PROBE_ATTN, flops, st, [&] { return pbk_attn_lin(&a, st); });
 }
 
 PbGemm plain_gemm(const float* A, long lda, long M, const float* B, long ldb, int N, int K, float* D, long ldd) {
@@ -486,7 +510,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C; a.R = h->T(o.y); a.ldr = C; a.sRb = (long)N * C;
     a.round_tf32 = h->rnd;
-    CK(pbk_attn_lin(&a, st));
+    CK(attn_lin_call(h, a, st));
     return PB_OK;
   }
   if (o.cross) {
@@ -544,7 +568,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
     a.round_tf32 = h->rnd;
-    CK(pbk_attn_lin(&a, st));
+    CK(attn_lin_call(h, a, st));
     // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q     (rows = keys, columns = queries)
     PbAttnLin b{};
     b.Mr = Nk; b.Nc = N; b.d = d; b.nb = nb; b.nh = hd; b.nseg = 1;
@@ -556,7 +580,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     b.C1 = Qt; b.ldc = ldq; b.sCh = (long)d * ldq;
     b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
     b.round_tf32 = h->rnd;
-    CK(pbk_attn_lin(&b, st));
+    CK(attn_lin_call(h, b, st));
     // Vbar = P^T Obar
     CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
     PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, 3 * C);
@@ -866,10 +890,31 @@ PB_API int pb_create(const pb_unet_cfg* cfg, pb_handle** out) {
 PB_API void pb_destroy(pb_handle* h) {
   if (!h) return;
   drop_graph(h);
+  for (auto& p : h->probes) { pbk_event_destroy(p.e0); pbk_event_destroy(p.e1); }
   delete h;
 }
 
 PB_API int64_t pb_kernel_launches(const pb_handle* h) { return h ? h->launches : 0; }
+
+PB_API int pb_profile_begin(pb_handle* h) {
+  if (!h) return PB_EINVAL;
+  for (auto& p : h->probes) { pbk_event_destroy(p.e0); pbk_event_destroy(p.e1); }
+  h->probes.clear();
+  h->profiling = true;
+  return PB_OK;
+}
+PB_API int pb_profile_read(pb_handle* h, int32_t kind, double* ms, double* flops, int64_t* launches) {
+  if (!h || !ms || !flops || !launches) return PB_EINVAL;
+  h->profiling = false;
+  *ms = 0; *flops = 0; *launches = 0;
+  for (const auto& p : h->probes) {
+    if (p.kind != kind) continue;
+    const float t = pbk_event_elapsed_ms(p.e0, p.e1);
+    if (t < 0.f) return fail(h, PB_ECUDA, "event timing failed");
+    *ms += t; *flops += p.flops; ++*launches;
+  }
+  return PB_OK;
+}
 
 // Enumerates the state_dict entries the planned path consumes (name + PyTorch shape), in plan order.
 PB_API int pb_weight_count(const pb_handle* h) {
@@ -1051,7 +1096,7 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
   float host_met[2] = {0.f, 0.f};
   for (int i = 0; i < max_iter; ++i) {
     bool replayed = false;
-    if (h->use_graph) {
+    if (h->use_graph && !h->profiling) {
       if (h->graph && (h->graph_k != k || h->graph_tol != tol || h->graph_u != u || h->graph_s != s)) drop_graph(h);
       if (!h->graph && h->warm) {     // the first iteration ever runs eagerly (one-time kernel attribute setup)
         const char* e = pbk_graph_begin(stream);

@@ -840,6 +840,22 @@ PBK pbk_graph_destroy(void* graph_exec) {
   return cuda_err(cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec)));
 }
 
+PBK pbk_event_record(void** ev, pb_stream st) {
+  if (!*ev) {
+    cudaEvent_t e;
+    if (const char* err = cuda_err(cudaEventCreate(&e))) return err;
+    *ev = e;
+  }
+  return cuda_err(cudaEventRecord(static_cast<cudaEvent_t>(*ev), S(st)));
+}
+extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void* e0, void* e1) {
+  float ms = 0.f;
+  if (cudaEventSynchronize(static_cast<cudaEvent_t>(e1)) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(e0), static_cast<cudaEvent_t>(e1)) != cudaSuccess) return -1.f;
+  return ms;
+}
+PBK pbk_event_destroy(void* ev) { return ev ? cuda_err(cudaEventDestroy(static_cast<cudaEvent_t>(ev))) : nullptr; }
+
 PBK pbk_gemm(const PbGemm* g, pb_stream st) {
   static const bool trace = getenv("PB_TRACE_GEMM") != nullptr;     // shape log for scripts/bench_gemm.py
   if (trace)

@@ -30,6 +30,11 @@ PBK pbk_graph_end(pb_stream st, void** graph_exec, long* kernel_nodes);
 PBK pbk_graph_launch(void* graph_exec, pb_stream st);
 PBK pbk_graph_destroy(void* graph_exec);
 
+// ---- timing probes (pb_profile_*: per-kernel roofline of bench.py) ----
+PBK pbk_event_record(void** ev, pb_stream st);                                    // creates *ev on first use
+extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void* e0, void* e1);   // waits for e1
+PBK pbk_event_destroy(void* ev);
+
 // ---- contraction ----
 PBK pbk_gemm(const PbGemm* g, pb_stream st);
 // direct 3x3/s1/p1 conv for tiny channel counts (conv_in and its transpose); w is [Cout][9][Cin]

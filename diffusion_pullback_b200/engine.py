@@ -117,6 +117,19 @@ class PullbackEngine:
     def set_option(self, name: str, value: int):
         self._ck(self.L.pb_set_option(self.h, name.encode(), int(value)))
 
+    def profile_begin(self):
+        """Start bracketing every contraction-kernel launch with an event pair (eager launches, no graph replay)."""
+        self._ck(self.L.pb_profile_begin(self.h))
+
+    def profile_read(self):
+        """Stop probing; {kernel class: (device ms, algorithmic flops, launches)} since profile_begin()."""
+        out = {}
+        for name, kind in (("gemm_tc_kernel", 0), ("attn_lin_kernel", 1)):
+            ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+            self._ck(self.L.pb_profile_read(self.h, kind, C.byref(ms), C.byref(fl), C.byref(n)))
+            out[name] = (ms.value, fl.value, n.value)
+        return out
+
     @property
     def launches(self) -> int:
         return int(self.L.pb_kernel_launches(self.h))

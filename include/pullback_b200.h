@@ -126,6 +126,15 @@ int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t
 int64_t pb_kernel_launches(const pb_handle* h);
 int pb_set_option(pb_handle* h, const char* name, int value);
 
+/* Timing probes for the roofline report (bench.py): after pb_profile_begin() every contraction-kernel launch made
+ * through this handle is bracketed by an event pair on its stream (launches go out eagerly, no graph replay);
+ * pb_profile_read() stops probing, waits, and returns the summed device time, the algorithmic flops (2 M N K per
+ * product) and the launch count of one kernel class. */
+#define PB_PROBE_GEMM 0                      /* gemm_tc_kernel: conv / linear / attention products */
+#define PB_PROBE_ATTN 1                      /* attn_lin_kernel: fused attention linearisation */
+int pb_profile_begin(pb_handle* h);
+int pb_profile_read(pb_handle* h, int32_t kind, double* ms, double* flops, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ PBK pbk_graph_begin(pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_end(pb_stream, void**, long*) { return "hostsim: no graphs"; }
 PBK pbk_graph_launch(void*, pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_destroy(void*) { return nullptr; }
+// timing probes: the double has no clock; a non-null token keeps the engine's bookkeeping exercised
+PBK pbk_event_record(void** ev, pb_stream) { static int token; *ev = &token; return nullptr; }
+extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void*, void*) { return 0.f; }
+PBK pbk_event_destroy(void*) { return nullptr; }
 
 PBK pbk_gemm(const PbGemm* gp, pb_stream) {
   const PbGemm& g = *gp;

@@ -6,7 +6,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from diffusion_pullback_b200.sharding import gather_results, shard_problems
+from diffusion_pullback_b200.sharding import (gather_results, plan_2d, pullback_tangent_sharded, shard_columns,
+                                              shard_problems)
 
 
 def _solve(problem, L):
@@ -65,3 +66,61 @@ def test_two_ranks_gather_all_problems():
     for p in range(n_problems):
         s, vT = _solve(p, L)
         assert torch.allclose(res[p][0], s, rtol=1e-5) and torch.allclose(res[p][1].abs(), vT.abs(), atol=1e-5)
+
+
+# ---- tangent sharding inside one problem (secondary partitioning) ----
+def test_plan_2d_and_column_shards():
+    assert plan_2d(10, 8) == (4, 2)          # BASELINE configs[3]: 10 timesteps on 8 GPUs -> 2 groups of 4
+    assert plan_2d(10, 4) == (2, 2) and plan_2d(10, 2) == (1, 2) and plan_2d(1, 8) == (8, 1) and plan_2d(16, 8) == (1, 8)
+    for k in (1, 2, 5, 16):
+        for size in (1, 2, 3, 4, 8):
+            spans = [shard_columns(k, r, size) for r in range(size)]
+            assert spans[0][0] == 0 and spans[-1][1] == k
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _tangent_setup(L, k):
+    from diffusion_pullback_b200.engine import PullbackEngine, unet_config
+    from oracle import unet_torch as UT
+    m = UT.build_unet("uncond_tiny")
+    x, t, _ = UT.synthetic_inputs("uncond_tiny", seed=77)
+    eng = PullbackEngine(unet_config(m), 32, 32, "mid", 0, k, 0, "cpu", _lib=L)
+    eng.bind(m.state_dict())
+    eng.set_point(x, float(t), None)
+    g = torch.Generator().manual_seed(5)
+    q, _ = torch.linalg.qr(torch.randn(eng.n_in, k, generator=g))
+    return eng, q.T.contiguous()
+
+
+def _tangent_worker(rank, world, port, k, iters, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tests.hostsim.build import build
+    eng, v0 = _tangent_setup(C.CDLL(build()), k)
+    u, s, vT, info = pullback_tangent_sharded(eng, v0, iters, iters, 0.0, group=None)
+    q.put((rank, u, s, vT, info.iters_done))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_split_the_columns_of_one_problem():
+    from tests.hostsim.build import build
+    L = C.CDLL(build())
+    k, iters, world = 3, 3, 2                                 # ragged: rank 0 owns 2 columns, rank 1 owns 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 500
+    procs = [ctx.Process(target=_tangent_worker, args=(r, world, port, k, iters, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=240) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    eng, v0 = _tangent_setup(L, k)
+    u, s, vT, info = eng.pullback(v0, iters, iters, 0.0)      # the unsharded loop (pb_pullback)
+    for _, u_r, s_r, vT_r, done in got:
+        assert done == iters
+        assert torch.allclose(s_r, s, rtol=1e-5)
+        assert torch.allclose(vT_r, vT, atol=1e-5) and torch.allclose(u_r, u, rtol=1e-4, atol=1e-5)
