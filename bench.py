@@ -291,10 +291,17 @@ def run_ours(args, wl):
                 "clocks": clocks,
                 "e2e": {"value": world * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
-                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
-                             "note": "algorithmic flops of one step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; "
-                                     "dominant kernel gemm_tf32_kernel (tcgen05 kind::tf32, nominal peak = half of bf16); peak = " + peak_src}}
+                "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
+                             "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": (kernels[dom]["achieved_tflops"] / peak_tf) if dom else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
+                             "step_achieved": achieved, "step_frac": (achieved / peak_tf) if achieved else None,
+                             "kernels": kernels,
+                             "note": "achieved = algorithmic flops (2 M N K per product) of the dominant kernel's launches / their summed "
+                                     "device time, event pair around every launch of 2 eager iterations; the kernel runs tcgen05 kind::tf32 "
+                                     "(fp32-parity path; hardware peak = half of the bf16 peak used as denominator); step_* = algorithmic "
+                                     "flops of one whole step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; traffic = "
+                                     "DRAM bytes per launch (ncu, profiles/); peak = " + peak_src}}
         if world == 1 and not args.no_cpu_baseline:
             k_s = k
             sec_iter = cpu_reference_iteration(model_name, op, bi, k_s)

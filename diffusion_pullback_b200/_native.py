@@ -60,7 +60,9 @@ class PbAttnLin(C.Structure):
                 ("Pm", C.c_void_p), ("ldp", C.c_long), ("sPh", C.c_long), ("delta", C.c_void_p), ("delta_mode", C.c_int),
                 ("want_rsum", C.c_int), ("O", C.c_void_p), ("ldo", C.c_long), ("C1", C.c_void_p), ("ldc", C.c_long),
                 ("sCh", C.c_long), ("D", C.c_void_p), ("ldd", C.c_long), ("sDb", C.c_long), ("R", C.c_void_p),
-                ("ldr", C.c_long), ("sRb", C.c_long), ("round_tf32", C.c_int)]
+                ("ldr", C.c_long), ("sRb", C.c_long), ("round_tf32", C.c_int),
+                ("C2", C.c_void_p), ("ldc2", C.c_long), ("sC2h", C.c_long), ("sC2b", C.c_long),
+                ("D2", C.c_void_p), ("ldd2", C.c_long), ("sD2b", C.c_long)]
 
 
 _lib = None

@@ -1,20 +1,29 @@
 // Fused attention-linearisation kernel for sm_100a (tcgen05 + TMEM + TMA): the tangent / cotangent of
-// softmax attention without ever materialising the N x N score tangent in HBM.
+// softmax attention without ever materialising the N x N score tangent in HBM, streaming the probability
+// matrix exactly once per (tangent, head) for every product that contracts with it.
 //
-// Per (tangent b, head h) and 128-row tile, looping over 64-column steps j of the score matrix (2-deep pipeline):
-//     S   = alpha1 * sum_seg A_seg[rows] . B_seg[cols_j]^T                (tcgen05.mma kind::tf32, K = head dim, -> TMEM)
-//     T   = Pm[rows, cols_j] o (S - delta)                                 (CUDA cores: tcgen05.ld; the P tile arrives by TMA in
-//                                                                          the swizzled A-operand layout and is overwritten in place)
+// Per (tangent b, head h) and 128-row tile, looping over 32-column steps j of the score matrix:
+//     S   = alpha1 * sum_seg A_seg[rows] . B_seg[cols_j]^T                (tcgen05.mma kind::tf32, K = head dim, -> TMEM ring of 4)
+//     Acc2 += Pm[rows, cols_j] . C2[cols_j]                                (optional: the P tile as it arrived by TMA)
+//     T   = Pm[rows, cols_j] o (S - delta)                                 (CUDA cores: tcgen05.ld; the P tile sits in the swizzled
+//                                                                          A-operand layout and is overwritten in place)
 //     Acc += T . C1[cols_j]                                                (tcgen05.mma, A = T in swizzled smem, -> TMEM)
 //     r   += rowsum(T)
-// and finally  D[rows] = alpha2 * Acc - r o O[rows] + beta * R[rows].
-// With (A, B, Pm, delta, C1) chosen by the engine this is
-//   JVP   : dO  = [P o dS] V - rowsum(P o dS) o O  (+ P dV from a plain GEMM via R),   dS = (dQ K^T + Q dK^T)/sqrt(d)
+// and finally  D[rows] = alpha2 * Acc - r o O[rows] + beta * R[rows]  (and D2[rows] = Acc2; without D2, Acc2 is Acc).
+// With (A, B, Pm, delta, C1, C2) chosen by the engine this is
+//   JVP   : dO  = [P o dS] V - rowsum(P o dS) o O + P dV,                  dS = (dQ K^T + Q dK^T)/sqrt(d)
 //   VJP-A : Qbar = [P   o (Obar V^T  - delta_row)] K / sqrt(d)
-//   VJP-B : Kbar = [P^T o (V Obar^T  - delta_col)] Q / sqrt(d)             (delta = rowsum(Obar o O))
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator, warps 2..9 compute (each TMEM lane
-// quarter is shared by two warps that split the 128 columns).  S is double-buffered in TMEM so the tensor core computes
-// S(j+1) while the CUDA cores turn S(j) into T(j).  See pb_kernels.h (PbAttnLin) for the exact semantics.
+//   VJP-B : Kbar = [P^T o (V Obar^T  - delta_col)] Q / sqrt(d),  Vbar = P^T Obar        (delta = rowsum(Obar o O))
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator, warps 2..9 compute in two groups of
+// four that take alternate column steps (each warp owns one TMEM lane quarter = 32 tile rows, all 32 columns of its step).
+// Pipeline: four independent smem rings -- S operands B (3 stages), C2 (3), C1 (4-5: a C1 tile lives until the accumulate
+// MMA LAG = 2 steps later has retired) and the in-place P/T tiles (every remaining 16 KB) -- all fed by one producer
+// thread that issues each ring's load as early as that ring allows (per-ring skew), so that every operand of step j is
+// requested about three steps before the tensor core needs it; S itself sits in a TMEM ring of 4; the accumulate MMA
+// trails the S MMA by two steps so that the tensor core never waits for the CUDA cores.
+// Head-dim tail: a head dim of 32 m + 8 (or + 16) keeps its last k-block in a 32-byte (64-byte) swizzled tile instead of
+// a zero-padded 128-byte one (SD-1.5's d = 40: A 40 KB instead of 64 KB, which is what buys the deep P ring).
+// See pb_kernels.h (PbAttnLin) for the exact semantics.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <algorithm>
@@ -24,64 +33,107 @@
 #include "pb_tc.cuh"
 
 namespace pbgemm {
-const char* encode4(CUtensorMap* m, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3], const uint32_t box[4]);
-const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, long ld, long sh, int nh, long sb, int nb, int box_rows,
-                         int* hmul, int* bmul, uint32_t* bytes);
+const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4], int swizzle_bytes);
+const char* encode_plainx(CUtensorMap* m, const void* base, int f16, int rows, int K, long ld, long sh, int nh, long sb,
+                          int nb, int box_cols, int box_rows, int swizzle_bytes, int* hmul, int* bmul, uint32_t* bytes);
 }
 
 namespace pbattn {
 using namespace pbtc;
 
 constexpr int TM = 128;                // score-tile rows per CTA
-constexpr int TN = 64;                 // score-tile columns per pipeline step
+constexpr int TN = 32;                 // score-tile columns per pipeline step = one 128-byte k-block of the T . C1 product
 constexpr int BK = 32;                 // fp32 per 128-byte swizzle row
-constexpr int NST = 2;                 // pipeline depth of every streamed operand
-constexpr int A_KT = TM * BK * 4;      // [128 x 32] k-block tile: 16 KB
-constexpr int B_KT = TN * BK * 4;      // [ 64 x 32] k-block tile:  8 KB
+constexpr int NS = 4;                  // S ring in TMEM
+constexpr int LAG = 2;                 // the accumulate MMA of step j is issued with the S MMA of step j + LAG
+constexpr int NB = 3;                  // B ring and C2 ring
+constexpr int MAX_NC1 = 6, MAX_NPT = 8;
+constexpr int PT_BYTES = TM * BK * 4;  // P in / T out, in place: 16 KB per stage
 constexpr int NTHREADS = 320;
+constexpr int TMEM_COLS = 256;         // S ring [0, 128), Acc [128, 192), Acc2 [192, 256)
 
 struct alignas(64) Params {
-  CUtensorMap mapA[2], mapB[2], mapC, mapP;
+  CUtensorMap mapA[2], mapB[2];        // full 32-float k-blocks of the S operands
+  CUtensorMap mapAt[2], mapBt[2];      // the compact tail k-block (8 or 16 floats), if any
+  CUtensorMap mapC, mapC2, mapP;
   int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2];
   uint32_t a_bytes, b_bytes, c_bytes, p_bytes;   // bytes per barrier phase
-  int nseg, kbd, dpad, d;              // k-blocks over the head dim, accumulator width (multiple of 16)
+  int nseg, d, dpad;                   // accumulator width dpad = d rounded up to 16
+  int kfull, tail;                     // S contraction: kfull 128-byte k-blocks + a tail of `tail` floats (0, 8, 16)
+  int a_seg_bytes, b_seg_bytes;        // smem bytes of one segment's A tile set / B tile set
+  int b_stage_bytes, c_tile_bytes;     // one ring stage of B (all segments) / one C tile
+  int nc1_st, npt_st;                  // ring depths of C1 and P/T
+  int has_c2, sep_acc2;
   int Mr, Nc, nb, nh;
   float alpha1, alpha2, beta;
   const float* delta; int delta_mode;
   int want_rsum; const float* O; long ldo;
   float* D; long ldd, sDb;
   const float* R; long ldr, sRb;
+  float* D2; long ldd2, sD2b;
   int round_tf32;
 };
 
-__host__ __device__ inline int smem_a_bytes(int nseg, int kbd) { return nseg * kbd * A_KT; }
-__host__ __device__ inline int smem_b_bytes(int nseg, int kbd) { return nseg * kbd * B_KT; }
-__host__ __device__ inline int smem_c_bytes(int dpad) { return (TN / BK) * dpad * BK * 4; }
-constexpr int PT_BYTES = (TN / BK) * A_KT;       // P in / T out, in place: 32 KB per stage
+// K-major swizzled smem matrix descriptor; swizzle span 128 / 64 / 32 bytes, 8-row groups 8 * span apart
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t saddr, int span) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((8 * span) >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(span == 128 ? 2 : span == 64 ? 4 : 6) << 61;
+  return d;
+}
 
-// smem: [A resident][B x NST][C1 x NST][P/T x NST][rsum 2 x 128 floats][barriers]
+// position in a ring of n stages: stage index + phase bit, advanced without division (the role loops are single-warp
+// instruction streams: every integer division by a runtime ring depth costs ~100 cycles of dependent latency)
+struct Ring {
+  int idx; uint32_t ph;
+  __device__ __forceinline__ void next(int n) { if (++idx == n) { idx = 0; ph ^= 1u; } }
+  __device__ __forceinline__ void next2(int n) { idx += 2; if (idx >= n) { idx -= n; ph ^= 1u; } }   // n >= 2
+};
+
+// smem: [A resident][B ring][C1 ring][C2 ring][P/T ring][rsum 2 x 128 floats][barriers]
+// Template parameters fix the contraction shape so that the single-warp issue loops unroll into straight-line code
+// (NSEG segments, KFULL full k-blocks, NTAIL tail k-steps of 8 floats, C2M: 0 no second product, 1 folded into Acc,
+// 2 separate accumulator); NSEG < 0 is the generic kernel that reads the shape from Params.
+template <int NSEG, int KFULL, int NTAIL, int C2M>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_constant__ Params p) {
+  constexpr bool GEN = NSEG < 0;
+  const int nseg = GEN ? p.nseg : NSEG;
+  const int kfull = GEN ? p.kfull : KFULL;
+  const int tail = GEN ? p.tail : NTAIL * 8;
+  const bool has_c2 = GEN ? (p.has_c2 != 0) : (C2M != 0);
+  const bool sep_acc2 = GEN ? (p.sep_acc2 != 0) : (C2M == 2);
+  const int a_seg_bytes = GEN ? p.a_seg_bytes : KFULL * TM * 128 + TM * NTAIL * 32;
+  const int b_seg_bytes = GEN ? p.b_seg_bytes : KFULL * TN * 128 + TN * NTAIL * 32;
+  const int b_stage_bytes = GEN ? p.b_stage_bytes : (NSEG > 0 ? NSEG : 1) * (KFULL * TN * 128 + TN * NTAIL * 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int bbytes = smem_b_bytes(p.nseg, p.kbd), cbytes = smem_c_bytes(p.dpad);
+  const int NC1 = p.nc1_st, NPT = p.npt_st;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + smem_a_bytes(p.nseg, p.kbd);
-  uint8_t* sC = sB + NST * bbytes;
-  uint8_t* sPT = sC + NST * cbytes;
-  float* s_rsum = reinterpret_cast<float*>(sPT + NST * PT_BYTES);
+  uint8_t* sB = sA + nseg * a_seg_bytes;
+  uint8_t* sC = sB + NB * b_stage_bytes;
+  uint8_t* sC2 = sC + NC1 * p.c_tile_bytes;
+  uint8_t* sPT = sC2 + (has_c2 ? NB * p.c_tile_bytes : 0);
+  float* s_rsum = reinterpret_cast<float*>(sPT + NPT * PT_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_rsum + 2 * TM);
   uint64_t* a_full = bars + 0;
   uint64_t* acc_full = bars + 1;
-  uint64_t* b_full = bars + 2;       // each of the following: [NST]
-  uint64_t* b_empty = bars + 4;
-  uint64_t* c_full = bars + 6;
-  uint64_t* c_empty = bars + 8;
-  uint64_t* p_full = bars + 10;
-  uint64_t* pt_empty = bars + 12;
-  uint64_t* s_full = bars + 14;
-  uint64_t* s_free = bars + 16;
-  uint64_t* t_full = bars + 18;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* b_full = bars + 2;                 // [NB]
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* c2_full = b_empty + NB;            // [NB]
+  uint64_t* c2_empty = c2_full + NB;
+  uint64_t* c_full = c2_empty + NB;            // [MAX_NC1]
+  uint64_t* c_empty = c_full + MAX_NC1;
+  uint64_t* s_full = c_empty + MAX_NC1;        // [NS]
+  uint64_t* s_free = s_full + NS;
+  uint64_t* p_full = s_free + NS;              // [MAX_NPT]
+  uint64_t* pt_empty = p_full + MAX_NPT;
+  uint64_t* t_full = pt_empty + MAX_NPT;
+  uint64_t* p_used = t_full + MAX_NPT;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(p_used + MAX_NPT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * TM;
@@ -91,15 +143,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(acc_full, 1);
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1);
-      mbar_init(&p_full[i], 1); mbar_init(&pt_empty[i], 1); mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8);
-      mbar_init(&t_full[i], 8);
-    }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&c2_full[i], 1); mbar_init(&c2_empty[i], 1); }
+    for (int i = 0; i < MAX_NC1; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); }
+    for (int i = 0; i < MAX_NPT; ++i) { mbar_init(&p_full[i], 1); mbar_init(&pt_empty[i], 1); mbar_init(&t_full[i], 4); mbar_init(&p_used[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -107,112 +158,189 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  const uint32_t tm_acc = tmem_base + NST * TN;
+  const uint32_t tm_acc = tmem_base + NS * TN;
+  const uint32_t tm_acc2 = sep_acc2 ? tm_acc + 64 : tm_acc;
+  const int tail_span = tail * 4;                              // bytes per row of the tail tile (32 or 64)
+  const int a_tail_off = kfull * TM * 128, b_tail_off = kfull * TN * 128;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
       mbar_arrive_expect_tx(a_full, p.a_bytes);
-      for (int s = 0; s < p.nseg; ++s)
-        for (int kb = 0; kb < p.kbd; ++kb)
-          tma_load_4d(sA + (s * p.kbd + kb) * A_KT, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
-      for (int j = 0; j < nj; ++j) {
-        const int c0 = j * TN, st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&b_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
-        for (int s = 0; s < p.nseg; ++s)
-          for (int kb = 0; kb < p.kbd; ++kb)
-            tma_load_4d(sB + st * bbytes + (s * p.kbd + kb) * B_KT, &p.mapB[s], &b_full[st], kb * BK, c0, bat_h * p.b_hmul[s],
-                        bat_b * p.b_bmul[s]);
-        mbar_wait(&pt_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&p_full[st], p.p_bytes);
-        for (int kb = 0; kb < TN / BK; ++kb)
-          tma_load_4d(sPT + st * PT_BYTES + kb * A_KT, &p.mapP, &p_full[st], c0 + kb * BK, r0, bat_h, 0);
-        mbar_wait(&c_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&c_full[st], p.c_bytes);
-        for (int kb = 0; kb < TN / BK; ++kb)
-          tma_load_4d(sC + st * cbytes + kb * p.dpad * BK * 4, &p.mapC, &c_full[st], c0 + kb * BK, 0, bat_h, 0);
+      for (int s = 0; s < nseg; ++s) {
+        uint8_t* dst = sA + s * a_seg_bytes;
+        for (int kb = 0; kb < kfull; ++kb)
+          tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+        if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+      }
+      // ring X may run (depth_X - life_X) steps ahead of the MMA issuer (life: steps until the consuming MMA has retired);
+      // each ring's load of item m is issued at producer iteration m + off_X so that all waits of one iteration fall on
+      // the same MMA step
+      const int ahead_b = NB, ahead_c1 = NC1 - LAG, ahead_pt = NPT - LAG;
+      const int ahead_max = max(ahead_b, max(ahead_c1, ahead_pt));
+      const int off_b = ahead_max - ahead_b, off_c1 = ahead_max - ahead_c1, off_pt = ahead_max - ahead_pt;
+      Ring rp{0, 0}, rb{0, 0}, rc{0, 0};
+      const int ah[2] = {bat_h * p.a_hmul[0], bat_h * p.a_hmul[1]};
+      const int bh[2] = {bat_h * p.b_hmul[0], bat_h * p.b_hmul[1]}, bb[2] = {bat_b * p.b_bmul[0], bat_b * p.b_bmul[1]};
+      (void)ah;
+      for (int i = 0; i < nj + ahead_max; ++i) {
+        int m = i - off_pt;
+        if (m >= 0 && m < nj) {
+          mbar_wait(&pt_empty[rp.idx], rp.ph ^ 1);
+          mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
+          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], m * TN, r0, bat_h, 0);
+          rp.next(NPT);
+        }
+        m = i - off_b;
+        if (m >= 0 && m < nj) {
+          const int c0 = m * TN, st = rb.idx;
+          mbar_wait(&b_empty[st], rb.ph ^ 1);
+          mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
+#pragma unroll
+          for (int s = 0; s < nseg; ++s) {
+            uint8_t* dst = sB + st * b_stage_bytes + s * b_seg_bytes;
+            for (int kb = 0; kb < kfull; ++kb) tma_load_4d(dst + kb * TN * 128, &p.mapB[s], &b_full[st], kb * BK, c0, bh[s], bb[s]);
+            if (tail) tma_load_4d(dst + b_tail_off, &p.mapBt[s], &b_full[st], kfull * BK, c0, bh[s], bb[s]);
+          }
+          if (has_c2) {
+            mbar_wait(&c2_empty[st], rb.ph ^ 1);
+            mbar_arrive_expect_tx(&c2_full[st], p.c_bytes);
+            tma_load_4d(sC2 + st * p.c_tile_bytes, &p.mapC2, &c2_full[st], c0, 0, bat_h, bat_b);
+          }
+          rb.next(NB);
+        }
+        m = i - off_c1;
+        if (m >= 0 && m < nj) {
+          mbar_wait(&c_empty[rc.idx], rc.ph ^ 1);
+          mbar_arrive_expect_tx(&c_full[rc.idx], p.c_bytes);
+          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], m * TN, 0, bat_h, 0);
+          rc.next(NC1);
+        }
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // the whole warp walks the loop; one elected lane issues (see elect_one)
+    {
       const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
       const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
-      auto do_acc = [&](int jj) {
-        const int st = jj & 1;
-        const uint32_t ph = (jj >> 1) & 1;
-        mbar_wait(&c_full[st], ph);
-        mbar_wait(&t_full[st], ph);
+      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+      const uint32_t uA = sm_u, uB = uA + nseg * a_seg_bytes, uC = uB + NB * b_stage_bytes, uC2 = uC + NC1 * p.c_tile_bytes;
+      const uint32_t uPT = uC2 + (has_c2 ? NB * p.c_tile_bytes : 0);
+      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + 64 : u_acc;
+      uint32_t acc_on = 0, acc2_on = 0;                          // 0 until the accumulator has been written once
+      // descriptors: desc(addr + off) = desc(addr) + (off >> 4) (all of smem fits the 14-bit address field)
+      const uint64_t dA = make_smem_desc(uA), dB = make_smem_desc(uB), dC = make_smem_desc(uC), dC2 = make_smem_desc(uC2);
+      const uint64_t dPT = make_smem_desc(uPT);
+      const uint64_t dAt = make_desc_sw(uA + a_tail_off, tail_span), dBt = make_desc_sw(uB + b_tail_off, tail_span);
+      const uint32_t a_seg16 = a_seg_bytes >> 4, b_seg16 = b_seg_bytes >> 4, b_stage16 = b_stage_bytes >> 4, c_tile16 = p.c_tile_bytes >> 4;
+      const int nk_last = min(4, (p.d - (kfull - 1) * BK + 7) / 8);   // columns past d are TMA zero fill: skip those MMAs
+      const int ntail = tail >> 3;
+      Ring rb{0, 0}, rs{0, 0}, rp{0, 0}, ra_pt{0, 0}, ra_c{0, 0};       // S operands / S in TMEM / P for the C2 product / accumulate: T, C1
+      auto do_acc = [&]() {                                      // Acc += T(jj) . C1(jj), jj = the accumulate rings' position
+        mbar_wait(&c_full[ra_c.idx], ra_c.ph);
+        mbar_wait(&t_full[ra_pt.idx], ra_pt.ph);
         tcgen05_fence_after();
-        for (int kb = 0; kb < TN / BK; ++kb) {
-          const uint64_t adesc = make_smem_desc(smem_u32(sPT + st * PT_BYTES + kb * A_KT));
-          const uint64_t bdesc = make_smem_desc(smem_u32(sC + st * cbytes + kb * p.dpad * BK * 4));
+        const uint64_t adesc = dPT + uint64_t(ra_pt.idx * (PT_BYTES >> 4));
+        const uint64_t bdesc = dC + uint64_t(ra_c.idx * c_tile16);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_tf32(tm_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, (jj | kb | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) mma_tf32(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
+          tcgen05_commit(&c_empty[ra_c.idx]);
+          tcgen05_commit(&pt_empty[ra_pt.idx]);
         }
-        tcgen05_commit(&c_empty[st]);
-        tcgen05_commit(&pt_empty[st]);
+        __syncwarp();
+        acc_on = 1;
+        ra_c.next(NC1); ra_pt.next(NPT);
       };
       mbar_wait(a_full, 0);
       for (int j = 0; j < nj; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&b_full[st], ph);
-        mbar_wait(&s_free[st], ph ^ 1);
+        mbar_wait(&b_full[rb.idx], rb.ph);
+        mbar_wait(&s_free[rs.idx], rs.ph ^ 1);
         tcgen05_fence_after();
-        bool first = true;
-        for (int s = 0; s < p.nseg; ++s)
-          for (int kb = 0; kb < p.kbd; ++kb) {
-            const uint64_t adesc = make_smem_desc(smem_u32(sA + (s * p.kbd + kb) * A_KT));
-            const uint64_t bdesc = make_smem_desc(smem_u32(sB + st * bbytes + (s * p.kbd + kb) * B_KT));
-            const int nk = min(4, (p.d - kb * BK + 7) / 8);     // columns past d are TMA zero fill: skip those MMAs
-            for (int k = 0; k < nk; ++k) {
-              mma_tf32(tmem_base + st * TN, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, first ? 0u : 1u);
-              first = false;
+        if (elect_one()) {
+          uint32_t on = 0;
+          const uint32_t d_s = tm_u + rs.idx * TN;
+#pragma unroll
+          for (int s = 0; s < nseg; ++s) {
+            const uint64_t a0 = dA + uint64_t(s * a_seg16), b0 = dB + uint64_t(rb.idx * b_stage16 + s * b_seg16);
+#pragma unroll
+            for (int kb = 0; kb < kfull; ++kb) {
+              const uint64_t adesc = a0 + uint64_t(kb * (TM * 128 >> 4)), bdesc = b0 + uint64_t(kb * (TN * 128 >> 4));
+              const int nk = (GEN && kb == kfull - 1) ? nk_last : 4;   // specialised shapes have whole k-blocks only
+#pragma unroll
+              for (int k = 0; k < nk; ++k) { mma_tf32(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, on); on = 1; }
+            }
+            if (ntail) {
+              const uint64_t adesc = dAt + uint64_t(s * a_seg16), bdesc = dBt + uint64_t(rb.idx * b_stage16 + s * b_seg16);
+#pragma unroll
+              for (int k = 0; k < ntail; ++k) { mma_tf32(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, on); on = 1; }
             }
           }
-        tcgen05_commit(&b_empty[st]);
-        tcgen05_commit(&s_full[st]);
-        if (j > 0) do_acc(j - 1);
+          tcgen05_commit(&b_empty[rb.idx]);
+          tcgen05_commit(&s_full[rs.idx]);
+        }
+        __syncwarp();
+        if (has_c2) {                                          // Acc2 += P(j) . C2(j), before the CUDA cores overwrite P(j)
+          mbar_wait(&c2_full[rb.idx], rb.ph);
+          mbar_wait(&p_full[rp.idx], rp.ph);
+          tcgen05_fence_after();
+          const uint64_t adesc = dPT + uint64_t(rp.idx * (PT_BYTES >> 4));
+          const uint64_t bdesc = dC2 + uint64_t(rb.idx * c_tile16);
+          const uint32_t on = sep_acc2 ? acc2_on : acc_on;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_tf32(u_acc2, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, on | uint32_t(k));
+            tcgen05_commit(&c2_empty[rb.idx]);
+            tcgen05_commit(&p_used[rp.idx]);
+          }
+          __syncwarp();
+          if (sep_acc2) acc2_on = 1; else acc_on = 1;
+          rp.next(NPT);
+        }
+        rb.next(NB); rs.next(NS);
+        if (j >= LAG) do_acc();
       }
-      do_acc(nj - 1);
-      tcgen05_commit(acc_full);
+      for (int jj = max(0, nj - LAG); jj < nj; ++jj) do_acc();
+      if (elect_one()) tcgen05_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // =========================== compute warps ===========================
-    const int cw = warp - 2;                  // 0..7
+    const int grp = (warp - 2) >> 2;          // 0 / 1: takes the even / odd column steps
     const int q = warp & 3;                   // TMEM lane quarter this warp may access (warp id % 4)
-    const int hh = cw >> 2;                   // which 32-column k-block of the 64-column step this warp owns
     const int row = q * 32 + lane;            // tile row
     const int r = r0 + row;
     const bool row_ok = r < p.Mr;
     const float* dbase = p.delta ? p.delta + ((long)bat_b * p.nh + bat_h) * (p.delta_mode == 1 ? p.Mr : p.Nc) : nullptr;
     const float drow = (dbase && p.delta_mode == 1 && row_ok) ? dbase[r] : 0.f;
-    const uint32_t tm_row = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(hh * 32);
+    const uint32_t tm_row = tmem_base + (uint32_t(q * 32) << 16);
     float rsum = 0.f;
-    for (int j = 0; j < nj; ++j) {
-      const int st = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
-      const int cbase = j * TN + hh * 32;
+    Ring rp{grp, 0}, rs{grp, 0};              // this group's position in the P/T ring and the S ring (advance by 2)
+    const uint32_t swz = uint32_t(row & 7);
+    for (int j = grp; j < nj; j += 2) {
+      const int st = rp.idx, ss = rs.idx;
+      const uint32_t ph = rp.ph;
+      const int cbase = j * TN;
       float dcol[32];
       if (p.delta_mode == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) dcol[i] = (cbase + i < p.Nc) ? dbase[cbase + i] : 0.f;
+        for (int i = 0; i < 32; ++i) dcol[i] = (cbase + i < p.Nc) ? __ldg(dbase + cbase + i) : 0.f;
       }
-      uint8_t* tb = sPT + st * PT_BYTES + hh * A_KT + row * 128;
+      uint8_t* tb = sPT + st * PT_BYTES + row * 128;
       mbar_wait(&p_full[st], ph);
       float4 pv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(tb + ((i ^ (row & 7)) << 4));
-      mbar_wait(&s_full[st], ph);
+      for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(tb + ((uint32_t(i) ^ swz) << 4));
+      mbar_wait(&s_full[ss], rs.ph);
       tcgen05_fence_after();
       uint32_t sv[32];
-      tmem_ld32(tm_row + st * TN, sv);
+      tmem_ld32(tm_row + ss * TN, sv);
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[st]);
+      if (lane == 0) mbar_arrive(&s_free[ss]);
+      float4 tv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
@@ -224,25 +352,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           o[e] = rna_tf32(t);
           rsum += o[e];
         }
-        *reinterpret_cast<float4*>(tb + ((i ^ (row & 7)) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+        tv[i] = make_float4(o[0], o[1], o[2], o[3]);
       }
+      if (has_c2) mbar_wait(&p_used[st], ph);                  // the P . C2 MMA has consumed the tile
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + ((uint32_t(i) ^ swz) << 4)) = tv[i];
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[st]);
+      rp.next2(NPT); rs.next2(NS);
     }
-    // ---- epilogue: D = alpha2 * Acc - rsum o O + beta * R ----
-    s_rsum[hh * TM + row] = rsum;
+    // ---- epilogue: group 0: D = alpha2 * Acc - rsum o O + beta * R ; group 1: D2 = Acc2 ----
+    s_rsum[grp * TM + row] = rsum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (hh == 0) {
-      const float rs = p.want_rsum ? s_rsum[row] + s_rsum[TM + row] : 0.f;
+    if (grp == 0 || sep_acc2) {
+      const float rs = (grp == 0 && p.want_rsum) ? s_rsum[row] + s_rsum[TM + row] : 0.f;
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();
-      float* dptr = p.D + (long)bat_b * p.sDb + (long)(row_ok ? r : 0) * p.ldd + bat_h * p.d;
-      const float* rptr = p.R ? p.R + (long)bat_b * p.sRb + (long)(row_ok ? r : 0) * p.ldr + bat_h * p.d : nullptr;
-      const float* optr = (p.want_rsum && p.O) ? p.O + (long)(row_ok ? r : 0) * p.ldo + bat_h * p.d : nullptr;
+      const long rr = row_ok ? r : 0;
+      float* dptr; const float* rptr = nullptr; const float* optr = nullptr;
+      float alpha;
+      uint32_t tm;
+      if (grp == 0) {
+        dptr = p.D + (long)bat_b * p.sDb + rr * p.ldd + bat_h * p.d;
+        if (p.R) rptr = p.R + (long)bat_b * p.sRb + rr * p.ldr + bat_h * p.d;
+        if (p.want_rsum && p.O) optr = p.O + rr * p.ldo + bat_h * p.d;
+        alpha = p.alpha2; tm = tm_acc;
+      } else {
+        dptr = p.D2 + (long)bat_b * p.sD2b + rr * p.ldd2 + bat_h * p.d;
+        alpha = 1.f; tm = tm_acc2;
+      }
       for (int c16 = 0; c16 < p.dpad; c16 += 16) {
         uint32_t v[16];
-        tmem_ld16(tm_acc + (uint32_t(q * 32) << 16) + uint32_t(c16), v);
+        tmem_ld16(tm + (uint32_t(q * 32) << 16) + uint32_t(c16), v);
         if (!row_ok) continue;
 #pragma unroll
         for (int g = 0; g < 16; g += 4) {
@@ -250,7 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           if (n >= p.d) break;                         // d is a multiple of 4
           float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = p.alpha2 * __uint_as_float(v[g + e]);
+          for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[g + e]);
           if (optr) { const float4 ov = *reinterpret_cast<const float4*>(optr + n); o[0] -= rs * ov.x; o[1] -= rs * ov.y; o[2] -= rs * ov.z; o[3] -= rs * ov.w; }
           if (rptr) { const float4 rv = *reinterpret_cast<const float4*>(rptr + n); o[0] += p.beta * rv.x; o[1] += p.beta * rv.y; o[2] += p.beta * rv.z; o[3] += p.beta * rv.w; }
           if (p.round_tf32) {
@@ -266,7 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -284,27 +426,47 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (const char* e = pbk_attn_lin_supported(a.d, a.Mr, a.Nc)) return e;
   if (a.nseg < 1 || a.nseg > 2) return "attn_lin: 1 or 2 segments";
   if ((long)a.nb * a.nh > 65535) return "attn_lin: batch too large";
+  if (a.D2 && !a.C2) return "attn_lin: D2 needs C2";
   Params p;
   memset(&p, 0, sizeof p);
-  p.nseg = a.nseg; p.d = a.d; p.kbd = (a.d + BK - 1) / BK; p.dpad = (a.d + 15) / 16 * 16;
+  p.nseg = a.nseg; p.d = a.d; p.dpad = (a.d + 15) / 16 * 16;
+  // S contraction over the head dim: full 32-float k-blocks + a compact tail of 8 / 16 floats (a longer tail is a full block)
+  const int rem = a.d % BK;
+  p.tail = rem == 0 ? 0 : rem <= 8 ? 8 : rem <= 16 ? 16 : 0;
+  p.kfull = a.d / BK + ((rem > 16) ? 1 : 0);
   p.Mr = a.Mr; p.Nc = a.Nc; p.nb = a.nb; p.nh = a.nh;
   p.alpha1 = a.alpha1; p.alpha2 = a.alpha2; p.beta = a.R ? a.beta : 0.f;
   p.delta = a.delta; p.delta_mode = a.delta ? a.delta_mode : 0;
   p.want_rsum = a.want_rsum; p.O = a.O; p.ldo = a.ldo;
   p.D = a.D; p.ldd = a.ldd; p.sDb = a.sDb; p.R = a.R; p.ldr = a.ldr; p.sRb = a.sRb; p.round_tf32 = a.round_tf32;
-  if ((a.ldd % 4) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % 4) ||
+  p.has_c2 = a.C2 ? 1 : 0; p.sep_acc2 = a.D2 ? 1 : 0; p.D2 = a.D2; p.ldd2 = a.ldd2; p.sD2b = a.sD2b;
+  if ((a.ldd % 4) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % 4) || (a.D2 && a.ldd2 % 4) ||
       ((reinterpret_cast<uintptr_t>(a.D) | reinterpret_cast<uintptr_t>(a.R) | reinterpret_cast<uintptr_t>(a.O) |
-        reinterpret_cast<uintptr_t>(a.Pm)) & 15))
-    return "attn_lin: D/R/O/P must be 16-byte aligned with ld % 4 == 0";
+        reinterpret_cast<uintptr_t>(a.Pm) | reinterpret_cast<uintptr_t>(a.D2)) & 15))
+    return "attn_lin: D/D2/R/O/P must be 16-byte aligned with ld % 4 == 0";
+  const int tail_span = p.tail * 4;
+  p.a_seg_bytes = p.kfull * TM * 128 + TM * tail_span;
+  p.b_seg_bytes = p.kfull * TN * 128 + TN * tail_span;
+  p.b_stage_bytes = p.nseg * p.b_seg_bytes;
+  p.c_tile_bytes = p.dpad * 128;
   uint32_t abytes = 0, bbytes = 0;
   for (int s = 0; s < a.nseg; ++s) {
     const PbGemmSeg& sg = a.seg[s];
-    uint32_t ab, bb;
-    if (const char* e = pbgemm::encode_plain(&p.mapA[s], static_cast<const float*>(sg.A), a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, TM, &p.a_hmul[s],
-                                              &p.a_bmul[s], &ab)) return e;
-    if (const char* e = pbgemm::encode_plain(&p.mapB[s], static_cast<const float*>(sg.B), a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, TN, &p.b_hmul[s],
-                                              &p.b_bmul[s], &bb)) return e;
-    abytes += ab * p.kbd; bbytes += bb * p.kbd;
+    uint32_t ab = 0, bb = 0;
+    if (p.kfull) {
+      if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, BK, TM, 128,
+                                                &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
+      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, BK, TN, 128,
+                                                &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
+      abytes += ab * p.kfull; bbytes += bb * p.kfull;
+    }
+    if (p.tail) {
+      if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, p.tail, TM,
+                                                tail_span, &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
+      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.tail, TN,
+                                                tail_span, &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
+      abytes += ab; bbytes += bb;
+    }
   }
   p.a_bytes = abytes; p.b_bytes = bbytes;
   {
@@ -312,26 +474,53 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), 1};
     uint64_t stb[3] = {uint64_t(a.ldc) * 4, uint64_t(a.sCh) * 4, uint64_t(a.sCh) * 4 * a.nh};
     uint32_t box[4] = {uint32_t(BK), uint32_t(a.d), 1, 1};
-    if (const char* e = pbgemm::encode4(&p.mapC, a.C1, dims, stb, box)) return e;
-    p.c_bytes = uint32_t(TN / BK) * uint32_t(a.d) * BK * 4;
+    if (const char* e = pbgemm::encode4x(&p.mapC, a.C1, 0, dims, stb, box, 128)) return e;
+    p.c_bytes = uint32_t(a.d) * BK * 4;
+  }
+  if (a.C2) {
+    // C2: [nb][nh][d][ldc2]
+    if ((a.ldc2 % 4) || (reinterpret_cast<uintptr_t>(a.C2) & 15)) return "attn_lin: C2 must be 16-byte aligned with ld % 4 == 0";
+    uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), uint64_t(a.nb)};
+    uint64_t stb[3] = {uint64_t(a.ldc2) * 4, uint64_t(a.nh > 1 ? a.sC2h : a.ldc2) * 4, uint64_t(a.nb > 1 ? a.sC2b : a.ldc2) * 4};
+    uint32_t box[4] = {uint32_t(BK), uint32_t(a.d), 1, 1};
+    if (const char* e = pbgemm::encode4x(&p.mapC2, a.C2, 0, dims, stb, box, 128)) return e;
   }
   {
     // Pm: [nh][Mr][ldp]; box = [32 columns] x [128 rows]
     int hm, bm; uint32_t pb;
-    if (const char* e = pbgemm::encode_plain(&p.mapP, a.Pm, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, TM, &hm, &bm, &pb)) return e;
-    p.p_bytes = pb * (TN / BK);
+    if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, 0, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, BK, TM, 128, &hm, &bm, &pb)) return e;
+    p.p_bytes = pb;
   }
-  const int smem = smem_a_bytes(p.nseg, p.kbd) + NST * (smem_b_bytes(p.nseg, p.kbd) + smem_c_bytes(p.dpad) + PT_BYTES) + 2 * TM * 4 +
-                   256 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
-  }
+  // ring depths from the shared-memory budget: B and C2 rings of NB stages, C1 ring of 5 (4 when tight), every
+  // remaining 16 KB goes to the in-place P/T ring
+  const int budget = 227 * 1024 - 1024 - (2 * TM * 4 + 1024);
+  const int fixed = p.nseg * p.a_seg_bytes + NB * p.b_stage_bytes + (p.has_c2 ? NB * p.c_tile_bytes : 0);
+  int nc1 = 5;
+  int npt = std::min((budget - fixed - nc1 * p.c_tile_bytes) / PT_BYTES, MAX_NPT);
+  if (npt < 5) { nc1 = 4; npt = std::min((budget - fixed - nc1 * p.c_tile_bytes) / PT_BYTES, MAX_NPT); }
+  if (npt < LAG + 1) return "attn_lin: shared memory budget exceeded";
+  p.nc1_st = nc1; p.npt_st = npt;
+  const int smem = fixed + nc1 * p.c_tile_bytes + npt * PT_BYTES + 2 * TM * 4 + 1024 + 1024;
   if (smem > 227 * 1024) return "attn_lin: shared memory budget exceeded";
   dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
-  attn_lin_kernel<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(st)>>>(p);
+  const int c2m = a.C2 ? (a.D2 ? 2 : 1) : 0;
+  const bool whole = (a.d % BK) <= 16;                         // every full k-block is complete (no OOB-padded block)
+  void (*kern)(Params) = attn_lin_kernel<-1, -1, -1, -1>;
+#define PB_ATTN_CASE(NSEG_, KF_, NT_, C2M_) \
+  if (whole && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ * 8 && c2m == C2M_) kern = attn_lin_kernel<NSEG_, KF_, NT_, C2M_>;
+  PB_ATTN_CASE(2, 1, 1, 1) PB_ATTN_CASE(1, 1, 1, 0) PB_ATTN_CASE(1, 1, 1, 2)      // head dim 40 (SD-1.x 64x64 layers): JVP, VJP-A, VJP-B
+  PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // head dim 64 (SD-2.x)
+#undef PB_ATTN_CASE
+  static void (*configured[8])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
+  int ci = 0;
+  while (ci < 8 && configured[ci] && configured[ci] != kern) ++ci;
+  if (ci == 8) return "attn_lin: internal (instantiation table full)";
+  if (!configured[ci]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    configured[ci] = kern;
+  }
+  kern<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(st)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -398,7 +398,7 @@ const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
 }
 // fused attention linearisation: S (nseg products over the head dim) + T . C1 per (tangent, head)
 const char* attn_lin_call(pb_handle* h, const PbAttnLin& a, pb_stream st) {
-  const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1) * a.nb * a.nh;
+  const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1 + (a.C2 ? 1 : 0)) * a.nb * a.nh;
   return probed(h, PB_PROBE_ATTN, flops, st, [&] { return pbk_attn_lin(&a, st); });
 }
 
@@ -490,25 +490,22 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   float* dS = h->WP(h->w_s1);
   const long sS = (long)hd * N * ldk;
   if (use_fused(h, o)) {
-    // dO = P dV (plain GEMM)  then  dO += [P o dS] V - rowsum(P o dS) o O  with dS = (dQ K^T + Q dK^T)/sqrt(d) never stored
+    // dO = [P o dS] V - rowsum(P o dS) o O + P dV   with dS = (dQ K^T + Q dK^T)/sqrt(d) never stored and P streamed once
     const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
     float* dVt = h->WP(h->w_s3);
     CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dqkv + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f, h->rnd, st));
-    PbGemm g = plain_gemm(P, ldk, N, dVt, ldk, d, Nk, h->T(o.y), C);
-    g.seg[0].sAh = (long)N * ldk; g.seg[0].sBb = (long)C * ldk; g.seg[0].sBh = (long)d * ldk;
-    g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
     PbAttnLin a{};
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 2;
     a.seg[0].A = dqkv; a.seg[0].lda = 3 * C; a.seg[0].sAb = (long)N * 3 * C; a.seg[0].sAh = d;
     a.seg[0].B = qkv + C; a.seg[0].ldb = 3 * C; a.seg[0].sBb = 0; a.seg[0].sBh = d;
     a.seg[1].A = qkv; a.seg[1].lda = 3 * C; a.seg[1].sAb = 0; a.seg[1].sAh = d;
     a.seg[1].B = dqkv + C; a.seg[1].ldb = 3 * C; a.seg[1].sBb = (long)N * 3 * C; a.seg[1].sBh = d;
-    a.alpha1 = o.scale; a.alpha2 = 1.f; a.beta = 1.f;
+    a.alpha1 = o.scale; a.alpha2 = 1.f; a.beta = 0.f;
     a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
     a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
-    a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C; a.R = h->T(o.y); a.ldr = C; a.sRb = (long)N * C;
+    a.C2 = dVt; a.ldc2 = ldk; a.sC2h = (long)d * ldk; a.sC2b = (long)C * ldk;
+    a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
     return PB_OK;
@@ -569,7 +566,8 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
-    // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q     (rows = keys, columns = queries)
+    // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q  and  Vbar = P^T Obar  (rows = keys, columns = queries; P^T streamed once)
+    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
     PbAttnLin b{};
     b.Mr = Nk; b.Nc = N; b.d = d; b.nb = nb; b.nh = hd; b.nseg = 1;
     b.seg[0].A = V; b.seg[0].lda = ldkv; b.seg[0].sAb = 0; b.seg[0].sAh = d;
@@ -579,14 +577,10 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     b.delta = delta; b.delta_mode = 2;
     b.C1 = Qt; b.ldc = ldq; b.sCh = (long)d * ldq;
     b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
+    b.C2 = gOt; b.ldc2 = ldq; b.sC2h = (long)d * ldq; b.sC2b = (long)C * ldq;
+    b.D2 = gx + 2 * C; b.ldd2 = 3 * C; b.sD2b = (long)N * 3 * C;
     b.round_tf32 = h->rnd;
     CK(attn_lin_call(h, b, st));
-    // Vbar = P^T Obar
-    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
-    PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, 3 * C);
-    g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
-    g.sDb = (long)N * 3 * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
     h->vals[o.x].ginit = true;
     return PB_OK;
   }

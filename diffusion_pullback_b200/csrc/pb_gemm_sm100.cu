@@ -273,10 +273,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // the whole warp walks the loop; one elected lane issues (see elect_one)
+    {
       // instruction descriptor: fp32 accumulate; A/B format tf32 (2) or f16 (0); N >> 3, M >> 4
       constexpr uint32_t idesc = (1u << 4) | (AB16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(BN >> 3) << 17) |
                                  (uint32_t(BM >> 4) << 24);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0; uint32_t phase = 0;
       int li = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
@@ -286,25 +289,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const int as = li & 1;
         mbar_wait(&tmem_empty_bar[as], ((li >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(as * ACC_STRIDE);
+        const uint32_t d_tmem = tmem_u + uint32_t(as * ACC_STRIDE);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sa = smem_u + stage * S::STAGE_BYTES;
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + S::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // advance 8 tf32 / 16 halves = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
-            if constexpr (AB16)
-              mma_f16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
-            else
-              mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              // advance 8 tf32 / 16 halves = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
+              if constexpr (AB16)
+                mma_f16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+              else
+                mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+            }
+            tcgen05_commit(&empty_bar[stage]);
           }
-          tcgen05_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full_bar[as]);
+        if (elect_one()) tcgen05_commit(&tmem_full_bar[as]);
+        __syncwarp();
       }
     }
   } else {
@@ -464,7 +471,7 @@ static EncodeFn get_encode() {
   return fn;
 }
 
-// 4-D tiled tensor map over fp32 (f16 = 0) or fp16 (f16 = 1) elements; strides in bytes; swizzle 128 or 64 bytes
+// 4-D tiled tensor map over fp32 (f16 = 0) or fp16 (f16 = 1) elements; strides in bytes; swizzle 128, 64 or 32 bytes
 const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t dims[4], const uint64_t strides_bytes[3],
                      const uint32_t box[4], int swizzle_bytes) {
   EncodeFn fn = get_encode();
@@ -477,7 +484,7 @@ const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t d
     if (gs[i] % 16 != 0 || gs[i] == 0) return "tensor stride not a positive multiple of 16 bytes";
   CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd,
                   gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[256];

@@ -103,8 +103,11 @@ PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int 
 // Per (b, h), rows r in [0, Mr), score columns c in [0, Nc), head dim d (head h occupies columns [h*d, (h+1)*d) of A/B/D/R/O):
 //   S[r][c]  = alpha1 * sum_seg  A_seg[b][r][h*d + :] . B_seg[b][c][h*d + :]         (batch / head strides as in PbGemmSeg)
 //   T[r][c]  = Pm[h][r][c] * (S[r][c] - delta),  delta = 0 | delta[b][h][r] (mode 1) | delta[b][h][c] (mode 2)
-//   D[b][r][h*d + n] = alpha2 * sum_c T[r][c] * C1[h][n][c]  -  (want_rsum ? rowsum_c(T[r][:]) * O[r][h*d + n] : 0)
-//                      + beta * R[b][r][h*d + n]
+//   E[r][n]  = sum_c Pm[h][r][c] * C2[b][h][n][c]                                     (optional second product on the same P tile)
+//   D[b][r][h*d + n] = alpha2 * (sum_c T[r][c] * C1[h][n][c]  +  (D2 ? 0 : E[r][n]))
+//                      - (want_rsum ? rowsum_c(T[r][:]) * O[r][h*d + n] : 0)  + beta * R[b][r][h*d + n]
+//   D2[b][r][h*d + n] = E[r][n]                                                       (when D2 is given)
+// so that the probability matrix is streamed exactly once per (tangent, head) for everything that contracts with it.
 struct PbAttnLin {
   int Mr, Nc, d, nb, nh, nseg;
   PbGemmSeg seg[2];                 // seg[i].K is ignored (K = d)
@@ -116,6 +119,8 @@ struct PbAttnLin {
   float* D; long ldd, sDb;
   const float* R; long ldr, sRb;
   int round_tf32;
+  const float* C2; long ldc2, sC2h, sC2b;   // optional [nb][nh][d][ldc2]
+  float* D2; long ldd2, sD2b;               // optional separate output of the C2 product
 };
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);

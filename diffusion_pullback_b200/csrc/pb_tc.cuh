@@ -14,6 +14,18 @@ namespace pbtc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// One elected lane of a fully converged warp.  The MMA / TMA warps run their loops with all 32 lanes (uniform control
+// flow keeps stage indices, descriptors and TMEM addresses in uniform registers) and issue through the elected lane;
+// a loop entered by a single lane instead makes the compiler wrap every tcgen05.mma in an ELECT / R2UR waterfall.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -397,6 +397,14 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
           double acc = 0;
           const float* C1 = a.C1 + h * a.sCh + (long)n * a.ldc;
           for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * trunc_tf32(C1[c]);
+          double e2 = 0;
+          if (a.C2) {
+            const float* C2 = a.C2 + b * a.sC2b + h * a.sC2h + (long)n * a.ldc2;
+            const float* Pr = a.Pm + h * a.sPh + (long)r * a.ldp;
+            for (int c = 0; c < a.Nc; ++c) e2 += (double)trunc_tf32(Pr[c]) * trunc_tf32(C2[c]);
+            if (a.D2) a.D2[b * a.sD2b + (long)r * a.ldd2 + h * a.d + n] = mr((float)e2, a.round_tf32);
+            else acc += e2;
+          }
           float v = a.alpha2 * (float)acc;
           if (a.want_rsum && a.O) v -= (float)rs * a.O[(long)r * a.ldo + h * a.d + n];
           if (a.R) v += a.beta * a.R[b * a.sRb + (long)r * a.ldr + h * a.d + n];

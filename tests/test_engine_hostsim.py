@@ -62,6 +62,23 @@ def test_operator_level_parity(hostsim, name, op, bi):
     assert rel(eng.vjp(G[:2]), Wref[:2]) < 2e-5
 
 
+def test_fused_attention_path_matches_unfused(hostsim):
+    """The engine's fused self-attention linearisation (P . dV and P^T . Obar folded into pbk_attn_lin) against the
+    materialised-score path, on the same cached point."""
+    k = 2
+    outs = []
+    for fused_min in (1, 1 << 30):
+        eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, k, dict(EXACT, fused_min_tokens=fused_min))
+        eng.set_point(x, float(t), ctx)
+        torch.manual_seed(0)
+        V = PO.initial_subspace(x.numel(), k)
+        U = eng.jvp(V)
+        W = eng.vjp(torch.randn(torch.Size(U.shape), generator=torch.Generator().manual_seed(3)))
+        outs.append((U, W))
+    # the fused double always contracts in TF32 (truncated operands, RNA-rounded T): TF32-level agreement
+    assert rel(outs[0][0], outs[1][0]) < 1e-3 and rel(outs[0][1], outs[1][1]) < 1e-3
+
+
 def _golden(small=True):
     out = []
     for f in sorted(os.listdir(GOLDEN)):

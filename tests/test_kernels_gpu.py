@@ -385,10 +385,13 @@ def test_orthonormalize_matches_svd():
         assert abs(float(met[0]) - float((V - Vp).pow(2).sum())) < 1e-3 * float((V - Vp).pow(2).sum()) + 1e-6
 
 
+@pytest.mark.parametrize("c2", [0, 1, 2])          # no second product / folded into D / separate output D2
 @pytest.mark.parametrize("Mr,Nc,d,nb,nh,nseg,mode", [(256, 256, 40, 2, 2, 2, 0), (200, 333, 16, 1, 3, 1, 1), (384, 128, 64, 2, 2, 1, 2),
-                                                       (1024, 1024, 40, 3, 8, 2, 0), (128, 640, 32, 2, 1, 2, 1), (4096, 4096, 40, 1, 2, 2, 0)])
-def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode):
-    """D = alpha2 * [Pm o (alpha1 * sum_seg A B^T - delta)] C1^T - rowsum(.) o O + beta * R   (PbAttnLin)."""
+                                                       (1024, 1024, 40, 3, 8, 2, 0), (128, 640, 32, 2, 1, 2, 1), (4096, 4096, 40, 1, 2, 2, 0),
+                                                       (300, 97, 48, 2, 2, 2, 2), (160, 2048, 8, 1, 2, 1, 0), (512, 512, 56, 2, 1, 2, 1),
+                                                       (256, 544, 36, 2, 2, 2, 0), (2304, 2304, 64, 2, 5, 2, 0)])
+def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode, c2):
+    """D = alpha2 * ([Pm o (alpha1 * sum_seg A B^T - delta)] C1^T [+ Pm C2^T]) - rowsum(.) o O + beta * R ; D2 = Pm C2^T   (PbAttnLin)."""
     torch.manual_seed(7)
     Cc = nh * d
     ldp = (Nc + 3) // 4 * 4
@@ -411,6 +414,12 @@ def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode):
     a.want_rsum, a.O, a.ldo = int(mode == 0), O.data_ptr(), Cc
     a.C1, a.ldc, a.sCh = C1.data_ptr(), ldp, d * ldp
     a.D, a.ldd, a.sDb, a.R, a.ldr, a.sRb, a.round_tf32 = D.data_ptr(), Cc, Mr * Cc, D.data_ptr(), Cc, Mr * Cc, 0
+    C2 = torch.randn(nb, nh, d, ldp, device="cuda")
+    D2 = torch.full((nb, Mr, Cc), float("nan"), device="cuda")
+    if c2:
+        a.C2, a.ldc2, a.sC2h, a.sC2b = C2.data_ptr(), ldp, d * ldp, nh * d * ldp
+    if c2 == 2:
+        a.D2, a.ldd2, a.sD2b = D2.data_ptr(), Cc, Mr * Cc
     _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
     t = lambda z: tf32_trunc(z).double()
     S = torch.einsum("bihd,jhd->bhij", t(A0).view(nb, Mr, nh, d), t(B0).view(Nc, nh, d))
@@ -426,6 +435,12 @@ def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode):
     Tr = T.float()
     Tr = ((Tr.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).double()
     acc = torch.einsum("bhij,hnj->bihn", Tr, t(C1)[..., :Nc]).reshape(nb, Mr, Cc)
+    if c2:
+        e2 = torch.einsum("hij,bhnj->bihn", t(Pm)[..., :Nc], t(C2)[..., :Nc]).reshape(nb, Mr, Cc)
+        if c2 == 1:
+            acc = acc + e2
+        else:
+            assert rel(D2, e2) < 1e-5, rel(D2, e2)
     ref = 0.7 * acc + R.double()
     if mode == 0:
         rs = Tr.sum(-1)                                               # [nb, nh, Mr]
