@@ -180,11 +180,13 @@ def run_ours(args, wl):
     _, t, ctx = SY.synthetic_inputs(model_name)
     tval = float(t)
     # one independent problem per (rank, step): synthetic x_t and the reference's randn + QR start (utils.py:750-752)
+    tangent = args.shard == "tangent" and world > 1          # every rank works on the SAME problem and owns k / world of its columns
+    prank = 0 if tangent else rank
     xs, v0s = [], []
     for i in range(K + Wm):
-        g = torch.Generator().manual_seed(1234 + 1000 * i + rank)
+        g = torch.Generator().manual_seed(1234 + 1000 * i + prank)
         xs.append(torch.randn(1, cfg["in_channels"], size, size, generator=g))
-        g2 = torch.Generator().manual_seed(i * world + rank)
+        g2 = torch.Generator().manual_seed(i * world + prank)
         q, _ = torch.linalg.qr(torch.randn(eng.n_in, k, generator=g2))
         v0s.append(q.T.contiguous())
     xd = [x.to(dev) for x in xs]
@@ -194,7 +196,11 @@ def run_ours(args, wl):
 
     def step(i):
         eng.set_point(xd[i], tval, ctxd)
-        u, s, vT, info = eng.pullback(v0d[i], iters, iters, 0.0)
+        if tangent:
+            from diffusion_pullback_b200.sharding import pullback_tangent_sharded
+            u, s, vT, info = pullback_tangent_sharded(eng, v0d[i], iters, iters, 0.0)
+        else:
+            u, s, vT, info = eng.pullback(v0d[i], iters, iters, 0.0)
         return s, vT
 
     def barrier():
@@ -214,7 +220,7 @@ def run_ours(args, wl):
     for i in range(Wm, Wm + K):
         results.append(step(i))
     payload = torch.cat([torch.cat([s, vT.reshape(-1)]) for s, vT in results])
-    if world > 1:
+    if world > 1 and not tangent:
         gathered = [torch.empty_like(payload) for _ in range(world)]
         dist.all_gather(gathered, payload)                   # the single collective: singular values + vectors of every problem
     e1.record()
@@ -227,19 +233,34 @@ def run_ours(args, wl):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax)
     secs = ms / 1e3
-    value = world * K * iters / secs
+    nprob = K if tangent else world * K                       # problems solved by the whole job
+    value = nprob * iters / secs
 
     # ---- e2e: the C-ABI host entry with pinned host buffers, H2D / D2H inside the timed region ----
     xh = [x.contiguous().pin_memory() for x in xs]
     v0h = [v.pin_memory() for v in v0s]
     ctxh = ctx.contiguous().pin_memory() if ctx is not None else None
     out = (torch.empty(k, eng.n_out).pin_memory(), torch.empty(k).pin_memory(), torch.empty(k, eng.n_in).pin_memory())
+    def e2e_step(i):
+        if not tangent:
+            eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
+            return
+        # tangent-sharded: host buffers in, the public sharded call, host buffers out
+        from diffusion_pullback_b200.sharding import pullback_tangent_sharded
+        x = xh[i].to(dev, non_blocking=True)
+        v0 = v0h[i].to(dev, non_blocking=True)
+        c = ctxh.to(dev, non_blocking=True) if ctxh is not None else None
+        eng.set_point(x, tval, c)
+        u, s, vT, _ = pullback_tangent_sharded(eng, v0, iters, iters, 0.0)
+        out[0].copy_(u); out[1].copy_(s); out[2].copy_(vT)
+        torch.cuda.synchronize()
+
     for i in range(min(Wm, 1)):
-        eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(Wm, Wm + K):
-        eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
+        e2e_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -283,13 +304,14 @@ def run_ours(args, wl):
             if tj:
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
                 "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,
                            "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K,
-                           "parallelism": f"problem-sharded x{world}", "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
+                           "parallelism": (f"tangent-sharded x{world} (k columns of one problem split over the ranks, one all-gather of W per iteration)"
+                                           if tangent else f"problem-sharded x{world}"), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
                            "column_iters_per_s": value * k},
                 "clocks": clocks,
-                "e2e": {"value": world * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": (world if not tangent else 1) * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
                              "peak": peak_tf, "unit": "TFLOP/s",
@@ -321,6 +343,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="problem", choices=["problem", "tangent"],
+                    help="N > 1: independent problems per rank (default, weak scaling) or the k columns of each problem split over the ranks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
