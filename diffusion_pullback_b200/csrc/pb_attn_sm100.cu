@@ -14,8 +14,9 @@
 //   JVP   : dO  = [P o dS] V - rowsum(P o dS) o O + P dV,                  dS = (dQ K^T + Q dK^T)/sqrt(d)
 //   VJP-A : Qbar = [P   o (Obar V^T  - delta_row)] K / sqrt(d)
 //   VJP-B : Kbar = [P^T o (V Obar^T  - delta_col)] Q / sqrt(d),  Vbar = P^T Obar        (delta = rowsum(Obar o O))
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (one thread) + TMEM allocator, warps 2..9 compute in two groups of
-// four that take alternate column steps (each warp owns one TMEM lane quarter = 32 tile rows, all 32 columns of its step).
+// Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + issuer of the score MMAs, warp 10 issuer of the accumulating
+// MMAs, warps 2..9 compute in two groups of four that take alternate column steps (each warp owns one TMEM lane quarter =
+// 32 tile rows, all 32 columns of its step).
 // Pipeline: four independent smem rings -- S operands B (3 stages), C2 (3), C1 (4-5: a C1 tile lives until the accumulate
 // MMA LAG = 2 steps later has retired) and the in-place P/T tiles (every remaining 16 KB) -- all fed by one producer
 // thread that issues each ring's load as early as that ring allows (per-ring skew), so that every operand of step j is
@@ -50,7 +51,7 @@ constexpr int LAG = 2;                 // the accumulate MMA of step j is issued
 constexpr int NB = 3;                  // B ring and C2 ring
 constexpr int MAX_NC1 = 6, MAX_NPT = 8;
 constexpr int PT_BYTES = TM * BK * 4;  // P in / T out, in place: 16 KB per stage
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;          // warp 0 TMA, 1 S issue, 2..9 compute, 10 accumulate issue
 constexpr int TMEM_COLS = 256;         // S ring [0, 128), Acc [128, 192), Acc2 [192, 256)
 
 struct alignas(64) Params {
@@ -218,42 +219,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    // the whole warp walks the loop; one elected lane issues (see elect_one)
-    {
-      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
-      const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
-      const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-      const uint32_t sm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
-      const uint32_t uA = sm_u, uB = uA + nseg * a_seg_bytes, uC = uB + NB * b_stage_bytes, uC2 = uC + NC1 * p.c_tile_bytes;
-      const uint32_t uPT = uC2 + (has_c2 ? NB * p.c_tile_bytes : 0);
-      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + 64 : u_acc;
-      uint32_t acc_on = 0, acc2_on = 0;                          // 0 until the accumulator has been written once
-      // descriptors: desc(addr + off) = desc(addr) + (off >> 4) (all of smem fits the 14-bit address field)
-      const uint64_t dA = make_smem_desc(uA), dB = make_smem_desc(uB), dC = make_smem_desc(uC), dC2 = make_smem_desc(uC2);
-      const uint64_t dPT = make_smem_desc(uPT);
+  } else if (warp == 1 || warp == 10) {
+    // =========================== MMA issuers ===========================
+    // warp 1 issues the score products S(j), warp 10 the products that accumulate over the steps (P . C2, T . C1): two
+    // single-warp instruction streams instead of one.  The whole warp walks its loop; one elected lane issues (elect_one).
+    const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t sm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    const uint32_t uA = sm_u, uB = uA + nseg * a_seg_bytes, uC = uB + NB * b_stage_bytes, uC2 = uC + NC1 * p.c_tile_bytes;
+    const uint32_t uPT = uC2 + (has_c2 ? NB * p.c_tile_bytes : 0);
+    // descriptors: desc(addr + off) = desc(addr) + (off >> 4) (all of smem fits the 14-bit address field)
+    const uint32_t c_tile16 = p.c_tile_bytes >> 4;
+    if (warp == 1) {
+      const uint64_t dA = make_smem_desc(uA), dB = make_smem_desc(uB);
       const uint64_t dAt = make_desc_sw(uA + a_tail_off, tail_span), dBt = make_desc_sw(uB + b_tail_off, tail_span);
-      const uint32_t a_seg16 = a_seg_bytes >> 4, b_seg16 = b_seg_bytes >> 4, b_stage16 = b_stage_bytes >> 4, c_tile16 = p.c_tile_bytes >> 4;
+      const uint32_t a_seg16 = a_seg_bytes >> 4, b_seg16 = b_seg_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
       const int nk_last = min(4, (p.d - (kfull - 1) * BK + 7) / 8);   // columns past d are TMA zero fill: skip those MMAs
       const int ntail = tail >> 3;
-      Ring rb{0, 0}, rs{0, 0}, rp{0, 0}, ra_pt{0, 0}, ra_c{0, 0};       // S operands / S in TMEM / P for the C2 product / accumulate: T, C1
-      auto do_acc = [&]() {                                      // Acc += T(jj) . C1(jj), jj = the accumulate rings' position
-        mbar_wait(&c_full[ra_c.idx], ra_c.ph);
-        mbar_wait(&t_full[ra_pt.idx], ra_pt.ph);
-        tcgen05_fence_after();
-        const uint64_t adesc = dPT + uint64_t(ra_pt.idx * (PT_BYTES >> 4));
-        const uint64_t bdesc = dC + uint64_t(ra_c.idx * c_tile16);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_tf32(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
-          tcgen05_commit(&c_empty[ra_c.idx]);
-          tcgen05_commit(&pt_empty[ra_pt.idx]);
-        }
-        __syncwarp();
-        acc_on = 1;
-        ra_c.next(NC1); ra_pt.next(NPT);
-      };
+      Ring rb{0, 0}, rs{0, 0};                                   // S operands / S in TMEM
       mbar_wait(a_full, 0);
       for (int j = 0; j < nj; ++j) {
         mbar_wait(&b_full[rb.idx], rb.ph);
@@ -282,24 +266,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           tcgen05_commit(&s_full[rs.idx]);
         }
         __syncwarp();
-        if (has_c2) {                                          // Acc2 += P(j) . C2(j), before the CUDA cores overwrite P(j)
-          mbar_wait(&c2_full[rb.idx], rb.ph);
+        rb.next(NB); rs.next(NS);
+      }
+    } else {
+      const uint64_t dC = make_smem_desc(uC), dC2 = make_smem_desc(uC2), dPT = make_smem_desc(uPT);
+      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + 64 : u_acc;
+      uint32_t acc_on = 0, acc2_on = 0;                          // 0 until the accumulator has been written once
+      Ring rc2{0, 0}, rp{0, 0}, ra_pt{0, 0}, ra_c{0, 0};         // C2 / P for the C2 product / accumulate: T, C1
+      auto do_acc = [&]() {                                      // Acc += T(jj) . C1(jj), jj = the accumulate rings' position
+        mbar_wait(&c_full[ra_c.idx], ra_c.ph);
+        mbar_wait(&t_full[ra_pt.idx], ra_pt.ph);
+        tcgen05_fence_after();
+        const uint64_t adesc = dPT + uint64_t(ra_pt.idx * (PT_BYTES >> 4));
+        const uint64_t bdesc = dC + uint64_t(ra_c.idx * c_tile16);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mma_tf32(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
+          tcgen05_commit(&c_empty[ra_c.idx]);
+          tcgen05_commit(&pt_empty[ra_pt.idx]);
+        }
+        __syncwarp();
+        acc_on = 1;
+        ra_c.next(NC1); ra_pt.next(NPT);
+      };
+      for (int j = 0; j < nj; ++j) {
+        if (has_c2) {                                            // Acc2 += P(j) . C2(j), before the CUDA cores overwrite P(j)
+          mbar_wait(&c2_full[rc2.idx], rc2.ph);
           mbar_wait(&p_full[rp.idx], rp.ph);
           tcgen05_fence_after();
           const uint64_t adesc = dPT + uint64_t(rp.idx * (PT_BYTES >> 4));
-          const uint64_t bdesc = dC2 + uint64_t(rb.idx * c_tile16);
+          const uint64_t bdesc = dC2 + uint64_t(rc2.idx * c_tile16);
           const uint32_t on = sep_acc2 ? acc2_on : acc_on;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma_tf32(u_acc2, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, on | uint32_t(k));
-            tcgen05_commit(&c2_empty[rb.idx]);
+            tcgen05_commit(&c2_empty[rc2.idx]);
             tcgen05_commit(&p_used[rp.idx]);
           }
           __syncwarp();
           if (sep_acc2) acc2_on = 1; else acc_on = 1;
-          rp.next(NPT);
+          rp.next(NPT); rc2.next(NB);
         }
-        rb.next(NB); rs.next(NS);
         if (j >= LAG) do_acc();
       }
       for (int jj = max(0, nj - LAG); jj < nj; ++jj) do_acc();

@@ -781,6 +781,89 @@ __global__ void pack_conv3x3_k(const float* __restrict__ w, int Co, int Ci, floa
   }
 }
 
+
+// conv_in and its transpose, register / shared-memory blocked (the two "thin" kernels above are the generic fallback).
+// thin-in: each thread owns TWO output channels (its 2 x 9 x CIN filter taps stay in registers) and walks a strip of
+// pixels; the CIN inputs of a tap are one broadcast load per warp.  w: [Cout][9][CIN].
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __restrict__ x, int nb, int H, int W,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             int Cout, float* __restrict__ y, float beta) {
+  const int cp = blockIdx.y * blockDim.x + threadIdx.x;       // output-channel pair
+  if (2 * cp >= Cout) return;
+  float wr[2][9 * CIN];
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int i = 0; i < 9 * CIN; ++i) wr[e][i] = w[(long)(2 * cp + e) * 9 * CIN + i];
+  const float b0 = bias ? bias[2 * cp] : 0.f, b1 = bias ? bias[2 * cp + 1] : 0.f;
+  const long total = (long)nb * H * W;
+  for (long pix = blockIdx.x; pix < total; pix += gridDim.x) {
+    const int px = int(pix % W), py = int((pix / W) % H);
+    const float* xc = x + pix * CIN;
+    float a0 = b0, a1 = b1;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
+      const float* xp = xc + ((long)dy * W + dx) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float xv = __ldg(xp + ci);
+        a0 = fmaf(xv, wr[0][tap * CIN + ci], a0);
+        a1 = fmaf(xv, wr[1][tap * CIN + ci], a1);
+      }
+    }
+    float2* yp = reinterpret_cast<float2*>(y + pix * Cout + 2 * cp);
+    if (beta != 0.f) { const float2 o = *yp; a0 += beta * o.x; a1 += beta * o.y; }
+    *yp = make_float2(a0, a1);
+  }
+}
+// thin-out: the whole filter ([COUT <= 4][9][Cin], 46 KB for SD) sits in shared memory; one warp per output pixel,
+// lanes split the input channels in float4 quads, four warp reductions per pixel.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __restrict__ x, int nb, int H, int W, int Cin,
+                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                               float* __restrict__ y, float beta) {
+  extern __shared__ float4 wsm[];                              // [COUT][9][Cin / 4]
+  const int C4 = Cin / 4;
+  for (int i = threadIdx.x; i < COUT * 9 * C4; i += blockDim.x) wsm[i] = reinterpret_cast<const float4*>(w)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const long total = (long)nb * H * W;
+  for (long pix = warp; pix < total; pix += nwarps) {
+    const int px = int(pix % W), py = int((pix / W) % H);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+      if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
+      const float4* xp = reinterpret_cast<const float4*>(x + (pix + (long)dy * W + dx) * Cin);
+      for (int c4 = lane; c4 < C4; c4 += 32) {
+        const float4 xv = xp[c4];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+          const float4 wv = wsm[(co * 9 + tap) * C4 + c4];
+          acc[co] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[co]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      float v = warp_sum(acc[co]);
+      if (lane == 0) {
+        if (bias) v += bias[co];
+        float* p = y + pix * COUT + co;
+        *p = beta != 0.f ? v + beta * *p : v;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ==================================================================================================
@@ -866,11 +949,31 @@ PBK pbk_gemm(const PbGemm* g, pb_stream st) {
 
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
                        float* y, float beta, pb_stream st) {
-  if (Cout <= 8 && Cin >= 32) {
-    const long pix = (long)nb * H * W;
+  const long pix = (long)nb * H * W;
+  if ((Cin == 3 || Cin == 4) && Cout % 2 == 0 && Cout >= 64) {                  // conv_in
+    const int gy = (Cout / 2 + 255) / 256;
+    const int bx = std::min(256, ((Cout / 2 + 31) / 32) * 32);
+    dim3 grid((unsigned)std::min<long>(pix, (long)kSMs * 8 / ((Cout / 2 + bx - 1) / bx)), (Cout / 2 + bx - 1) / bx);
+    (void)gy;
+    if (Cin == 4) conv3x3_thin_in_reg_k<4><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta);
+    else conv3x3_thin_in_reg_k<3><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta);
+  } else if ((Cout == 3 || Cout == 4) && Cin % 4 == 0 && (size_t)Cout * 9 * Cin * 4 <= 96 * 1024 &&
+             (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // its transpose
+    const int shmem = Cout * 9 * Cin * 4;
+    const unsigned blocks = (unsigned)std::min<long>((pix + 7) / 8, (long)kSMs * 2);
+    if (Cout == 4) {
+      static bool cfg4 = false;
+      if (!cfg4) { cudaFuncSetAttribute(conv3x3_thin_out_smem_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg4 = true; }
+      conv3x3_thin_out_smem_k<4><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
+    } else {
+      static bool cfg3 = false;
+      if (!cfg3) { cudaFuncSetAttribute(conv3x3_thin_out_smem_k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg3 = true; }
+      conv3x3_thin_out_smem_k<3><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
+    }
+  } else if (Cout <= 8 && Cin >= 32) {
     conv3x3_direct_thin_out<8><<<grid_for(pix * 32, 256), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
   } else {
-    const long total = (long)nb * H * W * Cout;
+    const long total = pix * Cout;
     conv3x3_direct_thin_in<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
   }
   return last_err();

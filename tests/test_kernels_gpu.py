@@ -365,6 +365,28 @@ def test_data_movement():
     assert rel(gi, F.conv_transpose2d(go.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)) < 1e-5
 
 
+@pytest.mark.parametrize("nb,H,W,Cin,Cout", [(5, 64, 64, 4, 320), (2, 19, 23, 3, 128), (3, 16, 16, 4, 64), (1, 8, 8, 4, 1280)])
+def test_thin_convs_blocked(nb, H, W, Cin, Cout):
+    """conv_in (Cin 3 / 4 -> Cout, register-blocked) and its transpose (filter in shared memory), incl. beta accumulation."""
+    torch.manual_seed(11)
+    xi = torch.randn(nb, H, W, Cin, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / 6
+    b = torch.randn(Cout, device="cuda")
+    fwd, bwd = torch.empty(Cout, 9, Cin, device="cuda"), torch.empty(Cin, 9, Cout, device="cuda")
+    _ok(N.leaf("pbk_pack_conv3x3")(_p(w), Cout, Cin, _p(fwd), _p(bwd), 0, _st()))
+    y0 = torch.randn(nb, H, W, Cout, device="cuda")
+    yo = y0.clone()
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, Cin, _p(fwd), _p(b), Cout, _p(yo), C.c_float(0.5), _st()))
+    ref = F.conv2d(xi.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1) + 0.5 * y0
+    assert rel(yo, ref) < 1e-5
+    go = torch.randn(nb, H, W, Cout, device="cuda")
+    g0 = torch.randn(nb, H, W, Cin, device="cuda")
+    gi = g0.clone()
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, Cout, _p(bwd), None, Cin, _p(gi), C.c_float(1.0), _st()))
+    ref = F.conv_transpose2d(go.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1) + g0
+    assert rel(gi, ref) < 1e-5
+
+
 def test_orthonormalize_matches_svd():
     torch.manual_seed(6)
     for k, n in ((5, 16384), (16, 16384), (2, 196608), (50, 4096)):
