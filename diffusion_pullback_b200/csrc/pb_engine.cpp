@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -40,6 +41,9 @@ struct Val {                 // one activation tensor, [rows][C] per image (NHWC
   size_t p_off;              // primal copy in the primal cache (bytes)
   size_t t_off;              // k_max tangents / cotangents in the workspace (bytes)
   bool ginit;                // vjp bookkeeping: cotangent buffer already holds a contribution
+  // fp16-operand policy (analyse_f16): the JVP tangent / the VJP cotangent of this tensor is produced by an elementwise
+  // kernel for exactly one consumer, a GEMM that reads it as its A operand, and is stored as halves in the same buffer
+  bool t16 = false, g16 = false;
 };
 
 enum WKind { WK_VEC, WK_RAW, WK_LIN, WK_CONV3, WK_CONV3_S2 };
@@ -48,6 +52,7 @@ struct WSpec {
   std::vector<std::string> names;   // sources, concatenated along the output dimension
   int out, in;                      // total rows, columns (conv: Co, Ci)
   size_t fwd_off, bwd_off;          // bytes in the packed region
+  size_t fwd16_off = 0, bwd16_off = 0;   // fp16 copies of the two GEMM layouts (0: none)
 };
 
 enum OpKind { OP_IN, OP_CONV_DIRECT, OP_GN, OP_LN, OP_GEMM, OP_CONCAT, OP_IM2COL, OP_UPSAMPLE, OP_GEGLU, OP_ATTN, OP_OUT };
@@ -59,6 +64,8 @@ struct Op {
   size_t bias_eff_off = 0, mean_off = 0, rstd_off = 0;
   float eps = 0.f; int silu = 0, groups = 0;
   int conv = 0;                     // OP_GEMM: 1 = 3x3 / s1 / p1 implicit GEMM
+  int a16_jvp = 0;                  // OP_GEMM: the JVP reads its A operand (tangent of x) as fp16
+  int a16_vjp = 0;                  // OP_GEMM: the VJP reads its A operand (cotangent of y) as fp16: 1 stored so, 2 converted first
   int pad_lo = 0, Ho = 0, Wo = 0;   // OP_IM2COL
   // OP_ATTN
   int heads = 0, d = 0, cross = 0, Nq = 0, Nk = 0, ldk = 0, ldq = 0, kv = -1;
@@ -93,6 +100,8 @@ struct pb_handle {
   int prec_p = 0, prec_t = 0, prec_a = 0;   // primal GEMMs / tangent weight GEMMs / tangent attention GEMMs
   int rnd = 1;                              // rounding flag of the pass being interpreted
   int fused_min_tokens = 512;               // self-attention layers with >= this many tokens use the fused kernel
+  int f16 = -1;                             // fp16-operand GEMMs on the tangent passes: -1 = if the backend has them
+  size_t w_cvt = 0, n_cvt = 0;              // fp16 staging of a multi-consumer cotangent (halves per tangent)
   std::string err;
   long launches = 0;
   // CUDA graph of one iteration (jvp + vjp + orthonormalise)
@@ -109,6 +118,9 @@ struct pb_handle {
   float* WP(size_t off) const { return reinterpret_cast<float*>(work + off); }
   float* Wf(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].fwd_off); }
   float* Wb(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].bwd_off); }
+  void* Wf16(int w) const { return packed + wspecs[w].fwd16_off; }
+  void* Wb16(int w) const { return packed + wspecs[w].bwd16_off; }
+  bool use_f16() const { return f16 > 0; }
 };
 
 namespace {
@@ -149,6 +161,10 @@ struct Planner {
     s.fwd_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 4);
     if (kind == WK_LIN || kind == WK_CONV3 || kind == WK_CONV3_S2) {
       s.bwd_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 4);
+      if (h->use_f16() && n % 4 == 0 && in % 8 == 0 && out % 8 == 0) {
+        s.fwd16_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 2);
+        s.bwd16_off = h->packed_top; h->packed_top = align_up(h->packed_top + n * 2);
+      }
     }
     h->wspecs.push_back(s);
     h->windex[key] = (int)h->wspecs.size() - 1;
@@ -366,6 +382,45 @@ struct Planner {
   }
 };
 
+// fp16-operand policy.  kind::f16 carries the same 10-bit mantissa as kind::tf32 at half the operand bytes (the big
+// convolutions are bound by L2 -> SM bytes, profiles/r1b_gemm_per_shape.txt).  A GEMM's A operand may be fp16 when the
+// tensor is written by ONE elementwise kernel (which then stores halves, round_tf32 = 2) and read by nothing else:
+//   JVP: x of the GEMM is produced by GN / LN / GEGLU / im2col / upsample and has no other consumer
+//   VJP: y of the GEMM (no residual) has exactly one consumer, a GN / LN / GEGLU op, whose VJP kernel writes the cotangent
+// 3x3 convolutions whose cotangent has several contributors convert it once (pbk_to_f16) instead.
+void analyse_f16(pb_handle* h) {
+  if (!h->use_f16()) return;
+  const int nv = (int)h->vals.size();
+  std::vector<int> consumers(nv, 0), producer(nv, -1);
+  for (int i = 0; i < (int)h->ops.size(); ++i) {
+    const Op& o = h->ops[i];
+    if (o.y >= 0 && o.kind != OP_OUT) producer[o.y] = i;
+    for (int v : {o.x, o.x2, o.res}) if (v >= 0) ++consumers[v];
+  }
+  // PB_F16_MASK (debug): bit 0 JVP convs, 1 JVP linears, 2 VJP stored-as-fp16, 3 VJP converted convs
+  const char* env = getenv("PB_F16_MASK");
+  const int mask = env ? atoi(env) : 15;
+  auto elementwise = [&](OpKind k, bool vjp) {
+    return k == OP_GN || k == OP_LN || k == OP_GEGLU || (!vjp && (k == OP_IM2COL || k == OP_UPSAMPLE));
+  };
+  size_t cvt = 0;
+  for (int i = 0; i < (int)h->ops.size(); ++i) {
+    Op& o = h->ops[i];
+    if (o.kind != OP_GEMM || h->wspecs[o.w].fwd16_off == 0) continue;
+    const Val& vx = h->vals[o.x]; const Val& vy = h->vals[o.y];
+    if (vx.C % 8 || vy.C % 8) continue;                        // fp16 rows must keep 16-byte strides
+    if ((mask & (o.conv ? 1 : 2)) && consumers[o.x] == 1 && producer[o.x] >= 0 && elementwise(h->ops[producer[o.x]].kind, false)) {
+      o.a16_jvp = 1; h->vals[o.x].t16 = true;
+    }
+    if ((mask & 4) && o.res < 0 && consumers[o.y] == 1) {
+      for (const Op& c : h->ops)
+        if (c.x == o.y && elementwise(c.kind, true)) { o.a16_vjp = 1; h->vals[o.y].g16 = true; }
+    }
+    if ((mask & 8) && !o.a16_vjp && o.conv) { o.a16_vjp = 2; cvt = std::max(cvt, (size_t)vy.rows * vy.C); }
+  }
+  h->n_cvt = cvt;
+}
+
 // ---------------------------------------------------------------------------------------------
 // interpreters
 // ---------------------------------------------------------------------------------------------
@@ -421,6 +476,7 @@ int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
   if (o.res >= 0) { g.R = primal ? h->P(o.res) : h->T(o.res); g.ldr = vy.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = primal ? h->prec_p : h->prec_t;
+  if (!primal && o.a16_jvp) { g.seg[0].B = h->Wf16(o.w); g.ab_dtype = PB_GEMM_F16; }    // A holds halves (Val::t16)
   CK(gemm_call(h, g, st));
   return PB_OK;
 }
@@ -432,6 +488,13 @@ int run_gemm_bwd(pb_handle* h, const Op& o, int nb, pb_stream st) {
   if (vx.ginit) { g.R = h->T(o.x); g.ldr = vx.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = h->prec_t;
+  if (o.a16_vjp) {
+    if (o.a16_vjp == 2) {                                      // several contributors summed in fp32: convert once
+      CK(pbk_to_f16(h->WP(h->w_cvt), h->T(o.y), (size_t)vy.rows * vy.C * nb, st));
+      g.seg[0].A = h->WP(h->w_cvt);
+    }
+    g.seg[0].B = h->Wb16(o.w); g.ab_dtype = PB_GEMM_F16;
+  }
   CK(gemm_call(h, g, st));
   vx.ginit = true;
   if (o.res >= 0) {
@@ -723,13 +786,13 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
       case OP_GN: {
         const Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->rnd, h->WP(h->w_gn), st));
+                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->vals[o.y].t16 ? 2 : h->rnd, h->WP(h->w_gn), st));
         break;
       }
       case OP_LN: {
         const Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.x), nb, 0, h->T(o.y), 0.f,
-                      h->rnd, st));
+                      h->vals[o.y].t16 ? 2 : h->rnd, st));
         break;
       }
       case OP_GEMM:
@@ -742,13 +805,13 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
         break;
       }
       case OP_IM2COL:
-        CK(pbk_im2col_s2(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->T(o.y), h->rnd, st));
+        CK(pbk_im2col_s2(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
         break;
       case OP_UPSAMPLE:
-        CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->rnd, st));
+        CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
         break;
       case OP_GEGLU:
-        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->rnd, st));
+        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
         break;
       case OP_ATTN:
         if (int e = run_attn_jvp(h, o, nb, st)) return e;
@@ -781,7 +844,7 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
         break;
       case OP_GEGLU:
         if (h->vals[o.x].ginit) return fail(h, PB_ESTATE, "internal: GEGLU input has several consumers");
-        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->rnd, st));
+        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->vals[o.x].g16 ? 2 : h->rnd, st));
         h->vals[o.x].ginit = true;
         break;
       case OP_UPSAMPLE: {
@@ -809,14 +872,14 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
       case OP_LN: {
         Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.y), nb, 1, h->T(o.x),
-                      v.ginit ? 1.f : 0.f, h->rnd, st));
+                      v.ginit ? 1.f : 0.f, v.g16 ? 2 : h->rnd, st));
         v.ginit = true;
         break;
       }
       case OP_GN: {
         Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, h->WP(h->w_gn), st));
+                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, v.g16 ? 2 : h->rnd, h->WP(h->w_gn), st));
         v.ginit = true;
         break;
       }
@@ -940,6 +1003,11 @@ PB_API int pb_set_option(pb_handle* h, const char* name, int value) {
       {"round_primal", &h->rnd_p, false}, {"round_tangent", &h->rnd_t, false}, {"round_weights", &h->rnd_w, true},
       {"precise_primal", &h->prec_p, false}, {"precise_tangent", &h->prec_t, false}, {"precise_attn", &h->prec_a, false},
       {"fused_min_tokens", &h->fused_min_tokens, false}};
+  if (!strcmp(name, "f16_operands")) {          // changes the plan (fp16 weight copies, operand dtypes): plan again
+    if (value && !pbk_has_f16_operands()) return fail(h, PB_EINVAL, "this backend has no fp16-operand GEMMs");
+    h->f16 = value ? 1 : 0; h->planned = h->bound = h->point = false; drop_graph(h);
+    return PB_OK;
+  }
   for (auto& o : opts)
     if (!strcmp(name, o.n)) {
       *o.p = value; drop_graph(h); h->point = false;
@@ -965,8 +1033,9 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->H = height; h->W = width; h->op = op; h->block_idx = block_idx; h->kmax = k_max; h->ctx_len = ctx_len;
   h->vals.clear(); h->ops.clear(); h->wspecs.clear(); h->windex.clear();
   h->cache_top = h->work_top = h->packed_top = 0;
-  h->n_s1 = h->n_s2 = h->n_s3 = h->n_delta = h->n_gn = 0;
+  h->n_s1 = h->n_s2 = h->n_s3 = h->n_delta = h->n_gn = 0; h->n_cvt = 0;
   h->sizes = pb_sizes{};
+  if (h->f16 < 0) h->f16 = pbk_has_f16_operands() ? 1 : 0;
   Planner p{h, ""};
   const int c0 = h->cfg.block_out_channels[0];
   h->c_sin = p.cache_alloc(c0); h->c_e1 = p.cache_alloc(4 * c0); h->c_temb = p.cache_alloc(4 * c0);
@@ -974,6 +1043,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   if (!p.build()) return fail(h, PB_EINVAL, p.error);
   h->n_in = (long)h->cfg.in_channels * height * width;
   h->n_out = h->vals[h->out_val].rows * h->vals[h->out_val].C;
+  analyse_f16(h);
   const size_t K = k_max;
   h->w_s1 = p.work_alloc(h->n_s1 * K); h->w_s2 = p.work_alloc(h->n_s2 * K); h->w_s3 = p.work_alloc(h->n_s3 * K);
   h->w_delta = p.work_alloc(h->n_delta * K); h->w_gn = p.work_alloc(h->n_gn + 64);
@@ -983,6 +1053,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4);
   h->w_x = p.work_alloc((size_t)h->n_in);
   h->n_splitk = kSplitFloats; h->w_splitk = p.work_alloc(kSplitFloats);
+  h->w_cvt = p.work_alloc((h->n_cvt * K + 1) / 2);          // halves
   h->sizes.packed_weight_bytes = h->packed_top; h->sizes.primal_cache_bytes = h->cache_top; h->sizes.workspace_bytes = h->work_top;
   h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out;
   if (sizes) *sizes = h->sizes;
@@ -1034,6 +1105,11 @@ PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n,
       row += rows;
     }
     if (row != s.out) return fail(h, PB_EINVAL, "unexpected shape for " + s.names[0]);
+    if (s.fwd16_off) {
+      const size_t n = (size_t)s.out * s.in * ((s.kind == WK_CONV3 || s.kind == WK_CONV3_S2) ? 9 : 1);
+      CK(pbk_to_f16(h->packed + s.fwd16_off, reinterpret_cast<const float*>(h->packed + s.fwd_off), n, stream));
+      CK(pbk_to_f16(h->packed + s.bwd16_off, reinterpret_cast<const float*>(h->packed + s.bwd_off), n, stream));
+    }
   }
   h->bound = true;
   return PB_OK;

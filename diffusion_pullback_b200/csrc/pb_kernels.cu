@@ -4,6 +4,7 @@
 // time embedding and the weight packers.  All HBM-bound: 128-bit accesses along the channel axis,
 // grids sized to cover 148 SMs, reductions by warp shuffles.  See pb_kernels.h for semantics.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,18 @@ __device__ __forceinline__ float maybe_round(float x, int r) { return r ? rna_tf
 __device__ __forceinline__ float4 maybe_round4(float4 v, int r) {
   if (r) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
   return v;
+}
+// Store four consecutive elements at element offset `off` (a multiple of 4) of a tensor produced for a GEMM-only consumer:
+// rnd 0 fp32 as is, 1 fp32 RNA-rounded to TF32, 2 fp16 (the buffer then holds halves; element offsets are unchanged).
+__device__ __forceinline__ void store_out4(float* out, long off, float4 v, int rnd) {
+  if (rnd == 2) {
+    uint2 h;
+    *reinterpret_cast<__half2*>(&h.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&h.y) = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + off) = h;
+  } else {
+    *reinterpret_cast<float4*>(out + off) = maybe_round4(v, rnd);
+  }
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -112,7 +125,7 @@ __global__ void upsample2x_k(const float4* __restrict__ x, int nb, int H, int W,
     const int ox = int(t % (2 * W)); t /= 2 * W;
     const int oy = int(t % (2 * H)); t /= 2 * H;
     const int b = int(t);
-    y[i] = maybe_round4(x[(((long)b * H + oy / 2) * W + ox / 2) * C4 + c], rnd);
+    store_out4(reinterpret_cast<float*>(y), 4 * i, x[(((long)b * H + oy / 2) * W + ox / 2) * C4 + c], rnd);
   }
 }
 __global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, int W, int C4, float4* __restrict__ gx,
@@ -136,6 +149,10 @@ __global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, i
     gx[i] = maybe_round4(a, rnd);
   }
 }
+__global__ void to_f16_k(__half* __restrict__ dst, const float* __restrict__ src, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+    store_out4(reinterpret_cast<float*>(dst), 4 * (long)i, reinterpret_cast<const float4*>(src)[i], 2);
+}
 __global__ void round_tf32_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
@@ -157,7 +174,7 @@ __global__ void im2col_s2_k(const float4* __restrict__ x, int nb, int H, int W, 
     const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
     float4 v = make_float4(0, 0, 0, 0);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long)b * H + iy) * W + ix) * C4 + c];
-    col[i] = maybe_round4(v, rnd);
+    store_out4(reinterpret_cast<float*>(col), 4 * i, v, rnd);
   }
 }
 __global__ void col2im_s2_k(const float4* __restrict__ col, int nb, int H, int W, int C4, int pad, int Ho, int Wo,
@@ -466,9 +483,8 @@ __global__ void gn_apply_lin_k(const float* __restrict__ xp, const float* __rest
       else v = rs * (ts[e] * f - m1 - xh * m2);
       o[e] = v;
     }
-    float4* op = reinterpret_cast<float4*>(out) + i;
-    if (acc != 0.f) { const float4 p = *op; o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
-    *op = maybe_round4(make_float4(o[0], o[1], o[2], o[3]), rnd);
+    if (acc != 0.f) { const float4 p = reinterpret_cast<const float4*>(out)[i]; o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
+    store_out4(out, 4 * i, make_float4(o[0], o[1], o[2], o[3]), rnd);
   }
 }
 
@@ -535,9 +551,8 @@ __global__ void ln_lin_k(const float* __restrict__ xp, const float* __restrict__
         const float xh = (xs[e] - m) * rs;
         o[e] = MODE == 0 ? gs[e] * rs * (ts[e] - m1 - xh * m2) : rs * (ts[e] * gs[e] - m1 - xh * m2);
       }
-      float4* op = reinterpret_cast<float4*>(out + r * C + c);
-      if (acc != 0.f) { const float4 p = *op; o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
-      *op = maybe_round4(make_float4(o[0], o[1], o[2], o[3]), rnd);
+      if (acc != 0.f) { const float4 p = *reinterpret_cast<const float4*>(out + r * C + c); o[0] += acc * p.x; o[1] += acc * p.y; o[2] += acc * p.z; o[3] += acc * p.w; }
+      store_out4(out, r * C + c, make_float4(o[0], o[1], o[2], o[3]), rnd);
     }
   }
 }
@@ -569,7 +584,7 @@ __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const flo
     const float4 dg = *reinterpret_cast<const float4*>(dh + r * 2 * F + F + c);
     float4 o = make_float4(da.x * gelu_f(g.x) + a.x * gelu_d(g.x) * dg.x, da.y * gelu_f(g.y) + a.y * gelu_d(g.y) * dg.y,
                            da.z * gelu_f(g.z) + a.z * gelu_d(g.z) * dg.z, da.w * gelu_f(g.w) + a.w * gelu_d(g.w) * dg.w);
-    *reinterpret_cast<float4*>(dy + r * F + c) = maybe_round4(o, rnd);
+    store_out4(dy, r * F + c, o, rnd);
   }
 }
 __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ gy, long rows, int F,
@@ -585,8 +600,8 @@ __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const flo
     float4 ga = make_float4(y.x * gelu_f(g.x), y.y * gelu_f(g.y), y.z * gelu_f(g.z), y.w * gelu_f(g.w));
     float4 gg = make_float4(y.x * a.x * gelu_d(g.x), y.y * a.y * gelu_d(g.y), y.z * a.z * gelu_d(g.z),
                             y.w * a.w * gelu_d(g.w));
-    *reinterpret_cast<float4*>(gh + r * 2 * F + c) = maybe_round4(ga, rnd);
-    *reinterpret_cast<float4*>(gh + r * 2 * F + F + c) = maybe_round4(gg, rnd);
+    store_out4(gh, r * 2 * F + c, ga, rnd);
+    store_out4(gh, r * 2 * F + F + c, gg, rnd);
   }
 }
 
@@ -1026,6 +1041,12 @@ PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, 
                                                                reinterpret_cast<float4*>(gx), beta, round_tf32);
   return last_err();
 }
+extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return 1; }
+PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) {
+  if (n % 4 || (reinterpret_cast<uintptr_t>(dst) & 7) || (reinterpret_cast<uintptr_t>(src) & 15)) return "to_f16: n % 4 and alignment";
+  to_f16_k<<<grid_for((long)(n / 4), 256, 16), 256, 0, S(st)>>>(static_cast<__half*>(dst), src, n / 4);
+  return last_err();
+}
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {
   round_tf32_k<<<grid_for((long)n, 256, 16), 256, 0, S(st)>>>(dst, src, n);
   return last_err();
@@ -1083,6 +1104,7 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
                float* tmp, pb_stream st) {
+  if (round_tf32 == 2 && acc != 0.f) return "groupnorm: fp16 output cannot accumulate";
   int chunks = 0;
   float* part = tmp;
   if (const char* e = gn_launch_sums(mode ? 2 : 1, xp, mean, rstd, gamma, beta, HW, C, G, silu, t, nb, part, &chunks, S(st)))
@@ -1109,6 +1131,7 @@ PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
                const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st) {
   CHECK_ALIGN4(C, "layernorm: C");
+  if (round_tf32 == 2 && acc != 0.f) return "layernorm: fp16 output cannot accumulate";
   const long rows = rows_p * nb;
   if (mode == 0) ln_lin_k<0><<<grid_for(rows * 32, 256, 8), 256, 0, S(st)>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, round_tf32);
   else ln_lin_k<1><<<grid_for(rows * 32, 256, 8), 256, 0, S(st)>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, round_tf32);

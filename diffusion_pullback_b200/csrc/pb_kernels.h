@@ -6,6 +6,9 @@
 //
 // Conventions: fp32, activations are [batch][pixels-or-tokens][channels] (NHWC), `st` is a
 // cudaStream_t, every call is stream-ordered and returns nullptr or a static error string.
+// `round_tf32` of a producer: 0 store fp32 as is; 1 RNA-round to TF32 (the consumer is a TF32 GEMM); 2 store fp16 --
+// the output buffer then holds halves at the same element offsets and its only consumer is an fp16-operand GEMM
+// (pbk_gn_lin, pbk_ln_lin, pbk_geglu_jvp/vjp, pbk_im2col_s2, pbk_upsample2x; not together with accumulation).
 // "xp" arguments are PRIMAL tensors cached once per (x_t, t, prompt); "t"/"g" arguments carry the
 // nb tangent (JVP) or cotangent (VJP) directions packed on the batch axis.
 #pragma once
@@ -58,6 +61,9 @@ PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int ro
 PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int round_tf32,
                        pb_stream st);
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
+// fp16-operand GEMMs (kind::f16, same 10-bit mantissa as TF32, half the operand bytes): 1 if the backend has them
+extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands();
+PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st);               // n % 4 == 0
 
 // ---- GroupNorm (+ optional SiLU) ----
 // tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch (per-chunk partial sums, combined in a fixed order)

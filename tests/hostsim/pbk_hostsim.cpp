@@ -51,6 +51,9 @@ PBK pbk_graph_begin(pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_end(pb_stream, void**, long*) { return "hostsim: no graphs"; }
 PBK pbk_graph_launch(void*, pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_destroy(void*) { return nullptr; }
+// the double models the fp32 / TF32 policy only: the engine asks and keeps every operand in fp32
+extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return 0; }
+PBK pbk_to_f16(void*, const float*, size_t, pb_stream) { return "hostsim: fp16 operands are not modelled"; }
 // timing probes: the double has no clock; a non-null token keeps the engine's bookkeeping exercised
 PBK pbk_event_record(void** ev, pb_stream) { static int token; *ev = &token; return nullptr; }
 extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void*, void*) { return 0.f; }
