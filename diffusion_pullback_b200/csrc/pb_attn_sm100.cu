@@ -48,11 +48,12 @@ constexpr int TN = 32;                 // score-tile columns per pipeline step =
 constexpr int BK = 32;                 // fp32 per 128-byte swizzle row
 constexpr int NS = 4;                  // S ring in TMEM
 constexpr int LAG = 2;                 // the accumulate MMA of step j is issued with the S MMA of step j + LAG
-constexpr int NB = 3;                  // B ring and C2 ring
+constexpr int MAX_NB = 3;              // B ring and C2 ring: 3 stages, 2 when shared memory is tight (head dim > 64)
 constexpr int MAX_NC1 = 6, MAX_NPT = 8;
 constexpr int PT_BYTES = TM * BK * 4;  // P in / T out, in place: 16 KB per stage
 constexpr int NTHREADS = 352;          // warp 0 TMA, 1 S issue, 2..9 compute, 10 accumulate issue
-constexpr int TMEM_COLS = 256;         // S ring [0, 128), Acc [128, 192), Acc2 [192, 256)
+constexpr int TMEM_COLS = 512;         // S ring [0, 128), Acc [128, 224), Acc2 [224, 320)
+constexpr int ACC2_OFF = 96;           // head dim <= 96
 
 struct alignas(64) Params {
   CUtensorMap mapA[2], mapB[2];        // full 32-float k-blocks of the S operands
@@ -64,7 +65,7 @@ struct alignas(64) Params {
   int kfull, tail;                     // S contraction: kfull 128-byte k-blocks + a tail of `tail` floats (0, 8, 16)
   int a_seg_bytes, b_seg_bytes;        // smem bytes of one segment's A tile set / B tile set
   int b_stage_bytes, c_tile_bytes;     // one ring stage of B (all segments) / one C tile
-  int nc1_st, npt_st;                  // ring depths of C1 and P/T
+  int nb_st, nc1_st, npt_st;           // ring depths of B / C2, C1 and P/T
   int has_c2, sep_acc2;
   int Mr, Nc, nb, nh;
   float alpha1, alpha2, beta;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   const int b_stage_bytes = GEN ? p.b_stage_bytes : (NSEG > 0 ? NSEG : 1) * (KFULL * TN * 128 + TN * NTAIL * 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int NC1 = p.nc1_st, NPT = p.npt_st;
+  const int NB = p.nb_st, NC1 = p.nc1_st, NPT = p.npt_st;
   uint8_t* sA = smem;
   uint8_t* sB = sA + nseg * a_seg_bytes;
   uint8_t* sC = sB + NB * b_stage_bytes;
@@ -122,11 +123,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_rsum + 2 * TM);
   uint64_t* a_full = bars + 0;
   uint64_t* acc_full = bars + 1;
-  uint64_t* b_full = bars + 2;                 // [NB]
-  uint64_t* b_empty = b_full + NB;
-  uint64_t* c2_full = b_empty + NB;            // [NB]
-  uint64_t* c2_empty = c2_full + NB;
-  uint64_t* c_full = c2_empty + NB;            // [MAX_NC1]
+  uint64_t* b_full = bars + 2;                 // [MAX_NB]
+  uint64_t* b_empty = b_full + MAX_NB;
+  uint64_t* c2_full = b_empty + MAX_NB;        // [MAX_NB]
+  uint64_t* c2_empty = c2_full + MAX_NB;
+  uint64_t* c_full = c2_empty + MAX_NB;        // [MAX_NC1]
   uint64_t* c_empty = c_full + MAX_NC1;
   uint64_t* s_full = c_empty + MAX_NC1;        // [NS]
   uint64_t* s_free = s_full + NS;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(acc_full, 1);
-    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&c2_full[i], 1); mbar_init(&c2_empty[i], 1); }
+    for (int i = 0; i < MAX_NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); mbar_init(&c2_full[i], 1); mbar_init(&c2_empty[i], 1); }
     for (int i = 0; i < MAX_NC1; ++i) { mbar_init(&c_full[i], 1); mbar_init(&c_empty[i], 1); }
     for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); }
     for (int i = 0; i < MAX_NPT; ++i) { mbar_init(&p_full[i], 1); mbar_init(&pt_empty[i], 1); mbar_init(&t_full[i], 4); mbar_init(&p_used[i], 1); }
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   const uint32_t tm_acc = tmem_base + NS * TN;
-  const uint32_t tm_acc2 = sep_acc2 ? tm_acc + 64 : tm_acc;
+  const uint32_t tm_acc2 = sep_acc2 ? tm_acc + ACC2_OFF : tm_acc;
   const int tail_span = tail * 4;                              // bytes per row of the tail tile (32 or 64)
   const int a_tail_off = kfull * TM * 128, b_tail_off = kfull * TN * 128;
 
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       }
     } else {
       const uint64_t dC = make_smem_desc(uC), dC2 = make_smem_desc(uC2), dPT = make_smem_desc(uPT);
-      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + 64 : u_acc;
+      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + ACC2_OFF : u_acc;
       uint32_t acc_on = 0, acc2_on = 0;                          // 0 until the accumulator has been written once
       Ring rc2{0, 0}, rp{0, 0}, ra_pt{0, 0}, ra_c{0, 0};         // C2 / P for the C2 product / accumulate: T, C1
       auto do_acc = [&]() {                                      // Acc += T(jj) . C1(jj), jj = the accumulate rings' position
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
 }  // namespace pbattn
 
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
-  if (d % 4 || d < 8 || d > 64) return "attn_lin: head dim must be a multiple of 4 in [8, 64]";
+  if (d % 4 || d < 8 || d > 96) return "attn_lin: head dim must be a multiple of 4 in [8, 96]";
   if (Mr < 1 || Nc < 1) return "attn_lin: empty problem";
   return nullptr;
 }
@@ -498,16 +499,22 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, 0, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, BK, TM, 128, &hm, &bm, &pb)) return e;
     p.p_bytes = pb;
   }
-  // ring depths from the shared-memory budget: B and C2 rings of NB stages, C1 ring of 5 (4 when tight), every
-  // remaining 16 KB goes to the in-place P/T ring
+  // ring depths from the shared-memory budget: B and C2 rings of 3 stages, C1 ring of 5 (4 when tight), every remaining
+  // 16 KB goes to the in-place P/T ring; big head dims (80: SD-1.x 32x32 layers) fall back to 2 / 3 stages
   const int budget = 227 * 1024 - 1024 - (2 * TM * 4 + 1024);
-  const int fixed = p.nseg * p.a_seg_bytes + NB * p.b_stage_bytes + (p.has_c2 ? NB * p.c_tile_bytes : 0);
-  int nc1 = 5;
-  int npt = std::min((budget - fixed - nc1 * p.c_tile_bytes) / PT_BYTES, MAX_NPT);
-  if (npt < 5) { nc1 = 4; npt = std::min((budget - fixed - nc1 * p.c_tile_bytes) / PT_BYTES, MAX_NPT); }
+  int nbst = MAX_NB, nc1 = 5, npt = 0;
+  auto fit = [&]() {
+    const int fixed = p.nseg * p.a_seg_bytes + nbst * p.b_stage_bytes + (p.has_c2 ? nbst * p.c_tile_bytes : 0);
+    npt = std::min((budget - fixed - nc1 * p.c_tile_bytes) / PT_BYTES, MAX_NPT);
+    return fixed + nc1 * p.c_tile_bytes;
+  };
+  int used = fit();
+  if (npt < 5) { nc1 = 4; used = fit(); }
+  if (npt < LAG + 1) { nbst = 2; nc1 = LAG + 1; used = fit(); }
   if (npt < LAG + 1) return "attn_lin: shared memory budget exceeded";
+  p.nb_st = nbst;
   p.nc1_st = nc1; p.npt_st = npt;
-  const int smem = fixed + nc1 * p.c_tile_bytes + npt * PT_BYTES + 2 * TM * 4 + 1024 + 1024;
+  const int smem = used + npt * PT_BYTES + 2 * TM * 4 + 1024 + 1024;
   if (smem > 227 * 1024) return "attn_lin: shared memory budget exceeded";
   dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
   const int c2m = a.C2 ? (a.D2 ? 2 : 1) : 0;
@@ -517,11 +524,12 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (whole && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ * 8 && c2m == C2M_) kern = attn_lin_kernel<NSEG_, KF_, NT_, C2M_>;
   PB_ATTN_CASE(2, 1, 1, 1) PB_ATTN_CASE(1, 1, 1, 0) PB_ATTN_CASE(1, 1, 1, 2)      // head dim 40 (SD-1.x 64x64 layers): JVP, VJP-A, VJP-B
   PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // head dim 64 (SD-2.x)
+  PB_ATTN_CASE(2, 2, 2, 1) PB_ATTN_CASE(1, 2, 2, 0) PB_ATTN_CASE(1, 2, 2, 2)      // head dim 80 (SD-1.x 32x32 layers)
 #undef PB_ATTN_CASE
-  static void (*configured[8])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
+  static void (*configured[12])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
   int ci = 0;
-  while (ci < 8 && configured[ci] && configured[ci] != kern) ++ci;
-  if (ci == 8) return "attn_lin: internal (instantiation table full)";
+  while (ci < 12 && configured[ci] && configured[ci] != kern) ++ci;
+  if (ci == 12) return "attn_lin: internal (instantiation table full)";
   if (!configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);

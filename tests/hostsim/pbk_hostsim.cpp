@@ -372,7 +372,7 @@ PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int 
   return nullptr;
 }
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
-  if (d % 4 || d < 8 || d > 64) return "attn_lin: head dim must be a multiple of 4 in [8, 64]";
+  if (d % 4 || d < 8 || d > 96) return "attn_lin: head dim must be a multiple of 4 in [8, 96]";
   return nullptr;
 }
 PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {

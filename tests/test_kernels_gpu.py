@@ -411,7 +411,8 @@ def test_orthonormalize_matches_svd():
 @pytest.mark.parametrize("Mr,Nc,d,nb,nh,nseg,mode", [(256, 256, 40, 2, 2, 2, 0), (200, 333, 16, 1, 3, 1, 1), (384, 128, 64, 2, 2, 1, 2),
                                                        (1024, 1024, 40, 3, 8, 2, 0), (128, 640, 32, 2, 1, 2, 1), (4096, 4096, 40, 1, 2, 2, 0),
                                                        (300, 97, 48, 2, 2, 2, 2), (160, 2048, 8, 1, 2, 1, 0), (512, 512, 56, 2, 1, 2, 1),
-                                                       (256, 544, 36, 2, 2, 2, 0), (2304, 2304, 64, 2, 5, 2, 0)])
+                                                       (256, 544, 36, 2, 2, 2, 0), (2304, 2304, 64, 2, 5, 2, 0),
+                                                       (1024, 1024, 80, 2, 8, 2, 0), (512, 512, 96, 1, 2, 1, 2), (256, 384, 72, 2, 2, 2, 1)])
 def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode, c2):
     """D = alpha2 * ([Pm o (alpha1 * sum_seg A B^T - delta)] C1^T [+ Pm C2^T]) - rowsum(.) o O + beta * R ; D2 = Pm C2^T   (PbAttnLin)."""
     torch.manual_seed(7)
