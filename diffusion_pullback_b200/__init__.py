@@ -1,5 +1,6 @@
 """pullback_b200 -- B200-native (sm_100a) implementation of Diffusion-Pullback's
 `local_encoder_pullback_zt/xt` hot path.  See DESIGN.md."""
-from .api import (get_h, get_h_uncond, local_encoder_pullback_xt, local_encoder_pullback_zt,  # noqa: F401
+from .api import (eps, get_h, get_h_uncond, local_encoder_pullback_xt, local_encoder_pullback_zt,  # noqa: F401
                   patch_unet, refresh_weights)
+from .ddim import DDIMSchedule, ddim_forward_steps, ddim_inversion  # noqa: F401
 from .engine import PullbackEngine, unet_config  # noqa: F401

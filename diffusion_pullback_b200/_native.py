@@ -116,6 +116,8 @@ def _declare(L):
     L.pb_weight_info.restype = C.c_int
     L.pb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb_set_option.restype = C.c_int
+    L.pb_ddim_step.argtypes = [vp, vp, f32, f32, vp, vp, i64, vp]
+    L.pb_ddim_step.restype = C.c_int
     L.pb_profile_begin.argtypes = [vp]
     L.pb_profile_begin.restype = C.c_int
     L.pb_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]

@@ -55,6 +55,16 @@ def get_h(self, sample=None, timestep=None, encoder_hidden_states=None, op=None,
     return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
 
 
+def eps(self, sample, timestep, encoder_hidden_states=None):
+    """The whole U-Net, x_t -> noise prediction: what the reference calls as `self.unet(latents, t,
+    encoder_hidden_states=prompt_emb).sample` in its DDIM loops (`edit.py:164-168`, `:458-462`); one latent per call."""
+    if sample.shape[0] != 1:
+        return torch.cat([eps(self, sample[i:i + 1], timestep, encoder_hidden_states[i:i + 1]) for i in range(sample.shape[0])], 0)
+    ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+    eng = _engine_for(self, sample, "full", 0, 1, ctx_len)
+    return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
+
+
 def get_h_uncond(self, x=None, t=None, op=None, block_idx=None, verbose=False):
     """`utils.py:114-163`; only ('mid', 0) is valid, anything else raises ValueError like the reference."""
     if x.shape[0] != 1:
@@ -122,6 +132,7 @@ def patch_unet(unet):
     if hasattr(unet, "up_blocks") and unet_config(unet)["kind"] == 0:
         unet.get_h = types.MethodType(get_h, unet)
         unet.local_encoder_pullback_zt = types.MethodType(local_encoder_pullback_zt, unet)
+        unet.eps = types.MethodType(eps, unet)
     else:
         unet.get_h = types.MethodType(get_h_uncond, unet)
         unet.local_encoder_pullback_xt = types.MethodType(local_encoder_pullback_xt, unet)

@@ -357,9 +357,10 @@ struct Planner {
              : attn_block(x, c.heads[L - 1], H, W, "mid_block.attentions.0");
     if (x < 0) return false;
     x = resnet(x, Cm, H, W, "mid_block.resnets.1"); if (x < 0) return false;
-    if (h->op == PB_OP_UP) {
+    if (h->op == PB_OP_UP || h->op == PB_OP_FULL) {
       if (!cond) { error = "(op, block_idx) is not valid: get_h_uncond supports ('mid', 0) only"; return false; }
-      for (int i = 0; i <= h->block_idx; ++i) {
+      const int last_up = h->op == PB_OP_FULL ? L - 1 : h->block_idx;
+      for (int i = 0; i <= last_up; ++i) {
         const std::string bp = "up_blocks." + std::to_string(i);
         const int out_ch = c.block_out_channels[L - 1 - i];
         for (int j = 0; j <= c.layers_per_block; ++j) {
@@ -374,6 +375,16 @@ struct Planner {
         }
         if (i != L - 1) { x = upsample(x, H, W, bp + ".upsamplers.0"); if (x < 0) return false; H *= 2; W *= 2; }
       }
+    }
+    if (h->op == PB_OP_FULL) {
+      // eps head: GroupNorm -> SiLU -> Conv3x3(C0 -> in_channels), the thin direct conv (few output channels)
+      int a = gn(x, "conv_norm_out", c.norm_eps, 1); if (a < 0) return false;
+      int y = val((long)H * W, c.in_channels);
+      Op& o = push(OP_CONV_DIRECT);
+      o.x = a; o.y = y; o.H = H; o.W = W;
+      o.w = weight(WK_CONV3, {"conv_out.weight"}, c.in_channels, h->vals[a].C);
+      o.bias = vec("conv_out.bias", c.in_channels);
+      x = y;
     }
     { Op& o = push(OP_OUT); o.x = x; o.H = H; o.W = W; }
     h->out_val = x;
@@ -953,6 +964,12 @@ PB_API void pb_destroy(pb_handle* h) {
 
 PB_API int64_t pb_kernel_launches(const pb_handle* h) { return h ? h->launches : 0; }
 
+PB_API int pb_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, int64_t n,
+                        void* stream) {
+  if (!x || !eps || !x_next || n < 0) return PB_EINVAL;
+  return pbk_ddim_step(x, eps, a_t, a_next, x_next, pred_x0, (long)n, stream) ? PB_EINVAL : PB_OK;
+}
+
 PB_API int pb_profile_begin(pb_handle* h) {
   if (!h) return PB_EINVAL;
   for (auto& p : h->probes) { pbk_event_destroy(p.e0); pbk_event_destroy(p.e1); }
@@ -1028,6 +1045,8 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   if (op == PB_OP_MID) { if (block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid"); }
   else if (op == PB_OP_UP) {
     if (h->cfg.kind != PB_UNET_COND || block_idx < 0 || block_idx >= h->cfg.n_levels) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
+  } else if (op == PB_OP_FULL) {
+    if (h->cfg.kind != PB_UNET_COND || block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   } else return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   if (h->cfg.kind == PB_UNET_COND && ctx_len < 1) return fail(h, PB_EINVAL, "ctx_len must be >= 1 for a conditional U-Net");
   h->H = height; h->W = width; h->op = op; h->block_idx = block_idx; h->kmax = k_max; h->ctx_len = ctx_len;
@@ -1095,7 +1114,7 @@ PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n,
           break;
         case WK_CONV3:
           // conv_in (thin direct kernel, fp32 FMA) keeps full precision
-          CK(pbk_pack_conv3x3(d.data, s.out, s.in, fwd, bwd, (s.in % 32 == 0) ? h->rnd_w : 0, stream));
+          CK(pbk_pack_conv3x3(d.data, s.out, s.in, fwd, bwd, (s.in % 32 == 0 && s.out % 32 == 0) ? h->rnd_w : 0, stream));
           break;
         case WK_CONV3_S2:
           CK(pbk_pack_conv3x3(d.data, s.out, s.in, fwd, nullptr, h->rnd_w, stream));

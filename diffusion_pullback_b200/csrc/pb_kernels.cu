@@ -153,6 +153,15 @@ __global__ void to_f16_k(__half* __restrict__ dst, const float* __restrict__ src
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
     store_out4(reinterpret_cast<float*>(dst), 4 * (long)i, reinterpret_cast<const float4*>(src)[i], 2);
 }
+__global__ void ddim_step_k(const float* __restrict__ x, const float* __restrict__ eps, float c_x0, float c_eps0, float c_x,
+                            float c_eps, float* __restrict__ x_next, float* __restrict__ pred_x0, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float xv = x[i], ev = eps[i];
+    const float p0 = c_x0 * xv - c_eps0 * ev;             // (x - sqrt(1 - a_t) eps) / sqrt(a_t)
+    if (pred_x0) pred_x0[i] = p0;
+    x_next[i] = c_x * p0 + c_eps * ev;
+  }
+}
 __global__ void round_tf32_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
@@ -1045,6 +1054,14 @@ extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { r
 PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) {
   if (n % 4 || (reinterpret_cast<uintptr_t>(dst) & 7) || (reinterpret_cast<uintptr_t>(src) & 15)) return "to_f16: n % 4 and alignment";
   to_f16_k<<<grid_for((long)(n / 4), 256, 16), 256, 0, S(st)>>>(static_cast<__half*>(dst), src, n / 4);
+  return last_err();
+}
+PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n,
+                  pb_stream st) {
+  if (!(a_t > 0.f) || !(a_next >= 0.f) || a_t > 1.f || a_next > 1.f) return "ddim_step: alphas_cumprod must lie in (0, 1]";
+  const float is = 1.f / sqrtf(a_t);
+  ddim_step_k<<<grid_for(n, 256, 8), 256, 0, S(st)>>>(x, eps, is, sqrtf(1.f - a_t) * is, sqrtf(a_next), sqrtf(1.f - a_next),
+                                                     x_next, pred_x0, n);
   return last_err();
 }
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {

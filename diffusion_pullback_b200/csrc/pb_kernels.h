@@ -137,6 +137,10 @@ PBK pbk_timestep_embedding(float t, int dim, int flip_sin_to_cos, float freq_shi
 PBK pbk_gemv(const float* Wm, const float* x, const float* bias, int N, int K, int silu_in, int silu_out, float* y,
              pb_stream st);
 
+// ---- DDIM update (eta = 0): x_next = sqrt(a_next) * (x - sqrt(1 - a_t) * eps) / sqrt(a_t) + sqrt(1 - a_next) * eps ----
+PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n,
+                  pb_stream st);
+
 // ---- weight packing (one-time) ----
 // w [Co][Ci][3][3] (PyTorch) -> fwd [Co][9][Ci], bwd [Ci][9][Co] with taps flipped (transpose conv)
 PBK pbk_pack_conv3x3(const float* w, int Co, int Ci, float* fwd, float* bwd, int round_tf32, pb_stream st);

@@ -1,0 +1,121 @@
+"""The reference's custom DDIM scheduler and its sampling / inversion loops on the B200 engine (first
+"next" row): same names and call shapes as `/root/reference/src/utils/utils.py:273-315` (`set_timesteps`, `step`,
+bound onto the scheduler with `types.MethodType` at `utils.py:340-342`) and `/root/reference/src/modules/edit.py`
+`run_DDIMinversion` (`:112-183`) / `DDIMforwardsteps` (`:385-482`), minus the VAE and the CPU latent buffering.
+
+    unet   = pb200.patch_unet(model.unet)           # also binds unet.eps(sample, timestep, encoder_hidden_states)
+    sched  = pb200.DDIMSchedule(alphas_cumprod)     # stands where `self.scheduler` stands
+    z_T    = pb200.ddim_inversion(unet, sched, z_0, inv_prompt_emb, inv_steps)
+    z_t, t, t_idx = pb200.ddim_forward_steps(unet, sched, z_T, for_prompt_emb, for_steps, 0, t_edit_idx)
+
+The U-Net runs as the engine's primal pass over the FULL plan (pb_plan op = PB_OP_FULL: every block + conv_norm_out +
+SiLU + conv_out, hand-written sm_100a kernels) and the update is `pb_ddim_step`; no torch op touches the latents.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+
+class SchedulerOutput:
+    """`utils.py:1166-1169`: `.prev_sample` (x_next) and `.x0` (the predicted x_0)."""
+
+    def __init__(self, xt_next, P_xt):
+        self.prev_sample, self.x0 = xt_next, P_xt
+
+
+class DDIMSchedule:
+    """`alphas_cumprod` [T] (the diffusers scheduler's table) + the reference's float-timestep logic."""
+
+    def __init__(self, alphas_cumprod, t_max: float = 999.0, _lib=None):
+        self.alphas_cumprod = torch.as_tensor(alphas_cumprod, dtype=torch.float32).cpu()
+        self.t_max = float(t_max)
+        self.timesteps = self.timesteps_next = None
+        self._L = _lib
+
+    def set_timesteps(self, num_inferences, device=None, is_inversion=False):
+        """`utils.py:273-286` verbatim semantics (float timesteps; inversion adds 1e-6 and walks upwards)."""
+        device = "cpu" if device is None else device
+        seq = torch.linspace(0, 1, num_inferences, device=device) * self.t_max
+        if is_inversion:
+            seq = seq + 1e-6
+            seq_prev = torch.cat([torch.tensor([-1], device=device), seq[:-1]], dim=0)
+            self.timesteps, self.timesteps_next = seq_prev[1:], seq[1:]
+        else:
+            seq_prev = torch.cat([torch.tensor([-1], device=device), seq[:-1]], dim=0)
+            self.timesteps, self.timesteps_next = reversed(seq[1:]), reversed(seq_prev[1:])
+
+    def scale_model_input(self, sample, t):
+        return sample
+
+    def _alpha(self, t):
+        # `extract` (utils.py:1302-1317): torch.gather(a, 0, t.long()) -- the float timestep is truncated
+        return float(self.alphas_cumprod[int(torch.as_tensor(t).long())])
+
+    def step(self, et, t, xt, eta=0.0, **kwargs):
+        """`utils.py:288-315`, eta = 0 (the only value the reference passes): one fused elementwise kernel."""
+        if eta != 0:
+            raise NotImplementedError("the reference always calls step(..., eta=0)")
+        t_idx = self.timesteps.tolist().index(float(t))
+        t_next = self.timesteps_next[t_idx]
+        L = self._L if self._L is not None else N.lib()
+        if xt.device.type != "cuda" and self._L is None:
+            raise RuntimeError("diffusion_pullback_b200 runs on a CUDA (sm_100a) device only (no CPU fallback exists)")
+        xt = xt.contiguous().float()
+        et = et.contiguous().float()
+        x_next, p_xt = torch.empty_like(xt), torch.empty_like(xt)
+        st = C.c_void_p(torch.cuda.current_stream(xt.device).cuda_stream) if xt.device.type == "cuda" else C.c_void_p(0)
+        rc = L.pb_ddim_step(C.c_void_p(xt.data_ptr()), C.c_void_p(et.data_ptr()), self._alpha(t), self._alpha(t_next),
+                            C.c_void_p(x_next.data_ptr()), C.c_void_p(p_xt.data_ptr()), xt.numel(), st)
+        if rc != 0:
+            raise ValueError("pb_ddim_step: invalid arguments")
+        return SchedulerOutput(x_next, p_xt)
+
+
+def _eps(unet, latents, t, ctx, guidance_scale, neg_ctx):
+    """Noise prediction with optional classifier-free guidance (`edit.py:150-175`, `:447-468`); the engine evaluates one
+    latent at a time, so the guided pair is two primal passes."""
+    outs = []
+    for i in range(latents.shape[0]):
+        x = latents[i:i + 1]
+        c = ctx[i:i + 1] if ctx.shape[0] == latents.shape[0] else ctx[:1]
+        if guidance_scale > 1.0 and neg_ctx is not None:
+            n = neg_ctx[i:i + 1] if neg_ctx.shape[0] == latents.shape[0] else neg_ctx[:1]
+            e_un, e_c = unet.eps(x, t, n), unet.eps(x, t, c)
+            outs.append(e_un + guidance_scale * (e_c - e_un))
+        else:
+            outs.append(unet.eps(x, t, c))
+    return torch.cat(outs, 0)
+
+
+@torch.no_grad()
+def ddim_inversion(unet, scheduler, z0, prompt_emb, num_inference_steps, guidance_scale=1.0, null_prompt_emb=None):
+    """`run_DDIMinversion` (`edit.py:112-183`) from the latent on: z_0 -> z_T; the last timestep is skipped (`:151-152`)."""
+    scheduler.set_timesteps(num_inference_steps, device="cpu", is_inversion=True)
+    latents = z0
+    for i, t in enumerate(scheduler.timesteps):
+        if i == len(scheduler.timesteps) - 1:
+            break
+        noise_pred = _eps(unet, latents, t, prompt_emb, guidance_scale, null_prompt_emb)
+        latents = scheduler.step(noise_pred, t, latents, eta=0).prev_sample
+    return latents
+
+
+@torch.no_grad()
+def ddim_forward_steps(unet, scheduler, zt, prompt_emb, num_inference_steps, t_start_idx=0, t_end_idx=-1, guidance_scale=1.0,
+                       neg_prompt_emb=None):
+    """`DDIMforwardsteps` (`edit.py:385-482`) up to the VAE decode: returns `(latents, t, t_idx)` when `t_end_idx` is
+    reached (`:432-434`), else the final latents."""
+    scheduler.set_timesteps(num_inference_steps, device="cpu")
+    latents = zt
+    for t_idx, t in enumerate(scheduler.timesteps):
+        if t_idx < t_start_idx:
+            continue
+        if t_idx == t_end_idx and t_idx != t_start_idx:
+            return latents, t, t_idx
+        noise_pred = _eps(unet, latents, t, prompt_emb, guidance_scale, neg_prompt_emb)
+        latents = scheduler.step(noise_pred, t, latents, eta=0).prev_sample
+    return latents

@@ -12,7 +12,7 @@ import torch
 
 from . import _native as N
 
-PB_OP = {"mid": 0, "up": 1}
+PB_OP = {"mid": 0, "up": 1, "full": 2}          # "full": the whole conditional U-Net, x_t -> eps (block_idx 0)
 _ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: KeyError}
 
 

@@ -55,7 +55,7 @@ class SyntheticUNet:
         if self._sd is None:
             from .engine import PullbackEngine, unet_config
             cfg = unet_config(self)
-            op, bi = ("up", len(cfg["block_out_channels"]) - 1) if cfg["kind"] == 0 else ("mid", 0)
+            op, bi = ("full", 0) if cfg["kind"] == 0 else ("mid", 0)
             if self.upto is not None:
                 op, bi = self.upto
             s = self.config["sample_size"]
@@ -100,7 +100,7 @@ def synthetic_state_dict(specs, seed: int = 0, device="cpu"):
     sd = {}
     for name, shape in specs:
         g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
-        if ".norm" in name or name.startswith("norm") or "group_norm" in name:
+        if ".norm" in name or name.startswith("norm") or "group_norm" in name or "norm_out" in name:
             p = 1.0 + 0.1 * torch.randn(shape, generator=g) if name.endswith("weight") else 0.1 * torch.randn(shape, generator=g)
         else:
             wshape = shape if name.endswith("weight") else shapes[name[:-4] + "weight"]

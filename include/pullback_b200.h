@@ -33,7 +33,8 @@ enum pb_unet_kind {
   PB_UNET_COND = 0,   /* diffusers UNet2DConditionModel (Stable Diffusion): get_h, utils.py:438-527   */
   PB_UNET_UNCOND = 1  /* diffusers UNet2DModel (DDPM CelebA-HQ ...): get_h_uncond, utils.py:114-163   */
 };
-enum pb_op { PB_OP_MID = 0, PB_OP_UP = 1 }; /* `op='down'` raises in the reference  */
+enum pb_op { PB_OP_MID = 0, PB_OP_UP = 1,   /* `op='down'` raises in the reference  */
+             PB_OP_FULL = 2 };               /* the whole conditional U-Net: x_t -> eps (conv_norm_out, SiLU, conv_out); block_idx 0 */
 
 #define PB_MAX_LEVELS 8
 
@@ -125,6 +126,13 @@ int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t
  * options: "use_graph" (default 1), "round_tf32" (default 1; re-bind weights after changing it). */
 int64_t pb_kernel_launches(const pb_handle* h);
 int pb_set_option(pb_handle* h, const char* name, int value);
+
+/* One deterministic DDIM update (the reference's custom scheduler `step`, src/utils/utils.py:288-315, eta = 0):
+ *   pred_x0 = (x - sqrt(1 - a_t) * eps) / sqrt(a_t);   x_next = sqrt(a_next) * pred_x0 + sqrt(1 - a_next) * eps
+ * over n contiguous floats; x_next may alias x, pred_x0 may be NULL.  a_t / a_next are alphas_cumprod gathered by the
+ * caller at t.long() / t_next.long() like `extract` (utils.py:1302-1317). */
+int pb_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, int64_t n,
+                 void* stream);
 
 /* Timing probes for the roofline report (bench.py): after pb_profile_begin() every contraction-kernel launch made
  * through this handle is bracketed by an event pair on its stream (launches go out eagerly, no graph replay);

@@ -594,6 +594,16 @@ class UNet2DConditionModel(nn.Module):
                 else:
                     raise ValueError(t)
                 self.up_blocks.append(blk)
+            # diffusers 0.11.0 UNet2DConditionModel tail: GroupNorm -> SiLU -> Conv3x3(C0 -> out_channels = in_channels)
+            self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, boc[0], eps=cfg.norm_eps)
+            self.conv_out = nn.Conv2d(boc[0], cfg.in_channels, 3, padding=1)
+
+    def forward(self, sample, timestep, encoder_hidden_states=None):
+        """The full noise prediction eps(x_t, t, prompt) (diffusers 0.11.0 `UNet2DConditionModel.forward`, what the
+        reference calls as `self.unet(latents, t, encoder_hidden_states=...).sample`, `edit.py:164-168`, `:458-462`)."""
+        from oracle.pullback_oracle import get_h
+        x = get_h(self, sample, timestep, encoder_hidden_states, "up", len(self.up_blocks) - 1)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
 
     @property
     def dtype(self):
@@ -651,7 +661,7 @@ def seeded_init_(model: nn.Module, seed: int = 0) -> nn.Module:
     perturbed away from (1, 0) so parity tests exercise them."""
     for name, p in model.named_parameters():
         g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
-        is_norm = ".norm" in name or name.startswith("norm") or "group_norm" in name
+        is_norm = ".norm" in name or name.startswith("norm") or "group_norm" in name or "norm_out" in name
         if is_norm:
             if name.endswith("weight"):
                 p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))

@@ -417,6 +417,15 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
     }
   return nullptr;
 }
+PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n, pb_stream) {
+  if (!(a_t > 0.f) || !(a_next >= 0.f) || a_t > 1.f || a_next > 1.f) return "ddim_step: alphas_cumprod must lie in (0, 1]";
+  for (long i = 0; i < n; ++i) {
+    const float p0 = (x[i] - std::sqrt(1.f - a_t) * eps[i]) / std::sqrt(a_t);
+    if (pred_x0) pred_x0[i] = p0;
+    x_next[i] = std::sqrt(a_next) * p0 + std::sqrt(1.f - a_next) * eps[i];
+  }
+  return nullptr;
+}
 PBK pbk_timestep_embedding(float t, int dim, int flip, float shift, float* out, pb_stream) {
   const int half = dim / 2;
   for (int j = 0; j < half; ++j) {

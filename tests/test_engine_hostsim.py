@@ -23,7 +23,7 @@ def hostsim():
 
 
 def make_engine(L, name, op, bi, k, opts=None):
-    m = UT.build_unet(name, build_up=(op == "up"))
+    m = UT.build_unet(name, build_up=(op in ("up", "full")))
     x, t, ctx = UT.synthetic_inputs(name)
     eng = PullbackEngine(unet_config(m), x.shape[2], x.shape[3], op, bi, k, ctx.shape[1] if ctx is not None else 0, "cpu", _lib=L)
     for kk, v in (opts or {}).items():
@@ -81,7 +81,7 @@ def test_fused_attention_path_matches_unfused(hostsim):
 
 def _golden(small=True):
     out = []
-    for f in sorted(os.listdir(GOLDEN)):
+    for f in sorted(f for f in os.listdir(GOLDEN) if not f.startswith("ddim_")):
         g = torch.load(os.path.join(GOLDEN, f))
         if (g["n_params"] < 5e6) == small:       # tiny configs only: the scalar double is slow
             out.append(f)
@@ -166,3 +166,33 @@ def test_unet_config_reads_diffusers_style_config():
     assert c["kind"] == 0 and c["heads"] == [5, 10, 20, 20] and c["down_has_attn"] == [1, 1, 1, 0] and c["up_has_attn"] == [0, 1, 1, 1]
     cu = unet_config(UT.build_unet("celebahq"))
     assert cu["kind"] == 1 and cu["heads"] == [1] * 6 and cu["down_has_attn"] == [0, 0, 0, 0, 1, 0] and cu["downsample_padding"] == 0
+
+
+# ---- the whole U-Net (x_t -> eps) and the reference's DDIM loops on the engine ----
+def test_full_unet_eps_matches_oracle(hostsim):
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "full", 0, 1, EXACT)
+    e = eng.set_point(x, float(t), ctx, want_h=True)
+    ref = m(x, t, encoder_hidden_states=ctx)
+    assert e.shape == ref.shape == x.shape and rel(e, ref) < 1e-5
+
+
+def test_ddim_loops_follow_the_reference_schedule(hostsim):
+    """Inversion then sampling (with classifier-free guidance) through pb_ddim_step + the FULL plan, against the oracle
+    restatement of edit.py:112-183 / :385-482 on the same U-Net."""
+    import types
+    import diffusion_pullback_b200 as PB
+    from oracle import ddim_oracle as DO
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "full", 0, 1, EXACT)
+    fake = types.SimpleNamespace(eps=lambda s, tt, c: eng.set_point(s, float(tt), c, want_h=True))
+    neg = torch.randn(ctx.shape, generator=torch.Generator().manual_seed(9))
+    ac = DO.sd_alphas_cumprod()
+    sched = PB.DDIMSchedule(ac, _lib=hostsim)
+    hostsim.pb_ddim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    zT = PB.ddim_inversion(fake, sched, x, ctx, 6)
+    zT_ref = DO.ddim_inversion(m, DO.Scheduler(ac), x, ctx, 6)
+    assert rel(zT, zT_ref) < 1e-4
+    out = PB.ddim_forward_steps(fake, sched, zT, ctx, 5, 0, 3, guidance_scale=2.5, neg_prompt_emb=neg)
+    ref = DO.ddim_forward_steps(m, DO.Scheduler(ac), zT_ref, ctx, 5, 0, 3, guidance_scale=2.5, neg_ctx=neg)
+    assert out[2] == ref[2] == 3 and float(out[1]) == float(ref[1]) and rel(out[0], ref[0]) < 1e-4
+    full = PB.ddim_forward_steps(fake, sched, zT, ctx, 5)
+    assert rel(full, DO.ddim_forward_steps(m, DO.Scheduler(ac), zT_ref, ctx, 5)) < 1e-4

@@ -118,7 +118,7 @@ def test_oracle_matches_dense_jacobian(name, op, bi):
 def _golden_files():
     if not os.path.isdir(GOLDEN):
         return []
-    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt"))
+    return sorted(f for f in os.listdir(GOLDEN) if f.endswith(".pt") and not f.startswith("ddim_"))
 
 
 @pytest.mark.parametrize("fname", _golden_files())
@@ -135,3 +135,52 @@ def test_oracle_reproduces_golden(fname):
     rep = PO.parity_report(s, vT, g["s"], g["vT"])
     assert rep["s_rel_max"] < 1e-4, rep
     assert rep["subspace"] > 0.9995 and rep["cos_min_gapped"] > 0.995, rep
+
+
+# ---- DDIM scheduler: the restatement against the reference's own functions, run verbatim ----
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+@pytest.mark.parametrize("inversion", [False, True])
+def test_ddim_restatement_matches_verbatim_reference(inversion):
+    import types
+    from oracle import ddim_oracle as DO
+    U = RS.load()
+    ac = DO.sd_alphas_cumprod()
+    ref = types.SimpleNamespace(t_max=999.0, alphas_cumprod=ac)
+    ref.set_timesteps = types.MethodType(U.set_timesteps, ref)        # utils.py:273-286, bound like utils.py:340-342
+    ref.step = types.MethodType(U.step, ref)                           # utils.py:288-315
+    ours = DO.Scheduler(ac)
+    ref.set_timesteps(12, is_inversion=inversion)
+    ours.set_timesteps(12, is_inversion=inversion)
+    assert torch.equal(torch.as_tensor(list(ref.timesteps)), torch.as_tensor(list(ours.timesteps)))
+    assert torch.equal(torch.as_tensor(list(ref.timesteps_next)), torch.as_tensor(list(ours.timesteps_next)))
+    g = torch.Generator().manual_seed(3)
+    xt, et = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for t in list(ref.timesteps)[:-1] if inversion else list(ref.timesteps):
+        out = ref.step(et, t, xt, eta=0)
+        x2, p2 = ours.step(et, t, xt)
+        assert torch.equal(out.prev_sample, x2) and torch.equal(out.x0, p2)              # SchedulerOutput: utils.py:1166-1169
+        assert torch.equal(U.extract(ac, t, xt.shape), DO.extract(ac, t, xt.shape))
+
+
+def test_full_forward_is_the_up_path_plus_the_eps_head():
+    m = UT.build_unet("sd_tiny")
+    x, t, ctx = UT.synthetic_inputs("sd_tiny")
+    e = m(x, t, encoder_hidden_states=ctx)
+    assert e.shape == x.shape
+    hl = PO.get_h(m, x, t, ctx, "up", 3)
+    assert torch.equal(e, m.conv_out(torch.nn.functional.silu(m.conv_norm_out(hl))))
+
+
+@pytest.mark.parametrize("name", ["sd_tiny", "sd_small"])
+def test_ddim_oracle_reproduces_golden(name):
+    """oracle/ddim_oracle.py against the trajectories minted from the reference's verbatim scheduler functions."""
+    from oracle import ddim_oracle as DO
+    g = torch.load(os.path.join(GOLDEN, f"ddim_{name}.pt"))
+    m = UT.build_unet(name)
+    z0, t, ctx = UT.synthetic_inputs(name)
+    assert torch.allclose(m(z0, t, encoder_hidden_states=ctx), g["eps0"], rtol=1e-5, atol=1e-6)
+    s = DO.Scheduler(DO.sd_alphas_cumprod())
+    zT = DO.ddim_inversion(m, s, z0, ctx, g["inv_steps"])
+    assert torch.allclose(zT, g["zT"], rtol=1e-5, atol=1e-6)
+    z, te, ie = DO.ddim_forward_steps(m, s, zT, ctx, g["for_steps"], 0, g["t_end_idx"], g["guidance_scale"], g["neg"])
+    assert ie == g["idx_edit"] and float(te) == g["t_edit"] and torch.allclose(z, g["z_edit"], rtol=1e-5, atol=1e-6)

@@ -77,7 +77,7 @@ def test_operator_level_vs_oracle(name, op, bi):
 
 def _golden_files(full):
     out = []
-    for f in sorted(os.listdir(GOLDEN)):
+    for f in sorted(f for f in os.listdir(GOLDEN) if not f.startswith("ddim_")):
         if f.endswith(".pt"):
             g = torch.load(os.path.join(GOLDEN, f))
             if (g["n_params"] > 60e6) == full:
@@ -196,3 +196,31 @@ def test_full_size_properties_sd21_768():
     u, s, vT, info = eng.pullback(V, 3, 3, 0.0)
     assert torch.allclose(vT @ vT.T, torch.eye(2, device=DEV), atol=1e-4)
     assert torch.allclose(u.norm(dim=1), s, rtol=0.1) and bool(s[0] >= s[1])
+
+
+# ---- the whole U-Net (x_t -> eps) and the reference's DDIM loops ----
+@pytest.mark.parametrize("name", ["sd_tiny", "sd_small"])
+def test_full_unet_eps_and_ddim_vs_golden(name):
+    """eps(x_t, t, prompt) through the FULL plan and the inversion / guided-sampling loops through pb_ddim_step, against
+    trajectories minted from the reference's verbatim scheduler functions (scripts/make_golden_ddim.py).  TF32 contractions:
+    5e-3 on one forward, 2e-2 on a trajectory of 8 + 2 x 4 chained forwards."""
+    g = torch.load(os.path.join(GOLDEN, f"ddim_{name}.pt"))
+    unet = PB.patch_unet(SY.SyntheticUNet(name, device=DEV))
+    z0, t, ctx = SY.synthetic_inputs(name, device=DEV)
+    e = unet.eps(z0, t, ctx)
+    assert e.shape == z0.shape and rel(e, g["eps0"]) < 5e-3
+    sched = PB.DDIMSchedule(ddim_alphas())
+    zT = PB.ddim_inversion(unet, sched, z0, ctx, g["inv_steps"])
+    assert rel(zT, g["zT"]) < 2e-2
+    z, te, ie = PB.ddim_forward_steps(unet, sched, g["zT"].to(DEV), ctx, g["for_steps"], 0, g["t_end_idx"],
+                                      guidance_scale=g["guidance_scale"], neg_prompt_emb=g["neg"].to(DEV))
+    assert ie == g["idx_edit"] and float(te) == g["t_edit"] and rel(z, g["z_edit"]) < 2e-2
+    # the pullback at the edit point of that trajectory runs on the same object (the reference's pipeline order)
+    u, s, vT = unet.local_encoder_pullback_zt(z, te, ctx, op="mid", block_idx=0, pca_rank=2, min_iter=2, max_iter=2,
+                                              convergence_threshold=0.0)
+    assert torch.isfinite(s).all() and float(s[0]) >= float(s[1]) > 0
+
+
+def ddim_alphas():
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2     # SD `scaled_linear`
+    return torch.cumprod(1.0 - betas, dim=0)
