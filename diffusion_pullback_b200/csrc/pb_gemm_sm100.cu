@@ -698,7 +698,19 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   long full = tiles, tail = 0;
   if (g_split && g.ws && ktot >= g_split_min_kb) {
     tail = tiles % nsm;
-    int s = tail ? (int)std::min<long>(nsm / tail, 32) : 1;
+    // split count of the tail wave: minimise (rounds the tail items need) x (k-blocks per item); a tail of 80 tiles is
+    // better cut in 5 (3 rounds of 1/5) than run whole on 80 of the 148 SMs
+    int s = 1;
+    if (tail) {
+      long best = (long)ktot + 1;
+      const int smax = (int)std::min<long>(std::min(32, ktot / 8), g.ws_floats / (tail * BM * BN));
+      for (int c = 1; c <= smax; ++c) {
+        const long kb = (ktot + c - 1) / c;
+        // in k-block times: rounds x (k-blocks + pipeline fill and partial-tile store) + the reduce pass over c partials
+        const long cost = c == 1 ? kb : ((tail * c + nsm - 1) / nsm) * (kb + 6) + tail * c / 16;
+        if (cost < best) { best = cost; s = c; }
+      }
+    }
     if (g_split > 1) s = g_split;
     s = std::min(s, ktot / 8);
     if (tail) s = (int)std::min<long>(s, g.ws_floats / (tail * BM * BN));
