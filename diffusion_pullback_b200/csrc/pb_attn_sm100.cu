@@ -19,9 +19,9 @@
 // 32 tile rows, all 32 columns of its step).
 // Pipeline: four independent smem rings -- S operands B (3 stages), C2 (3), C1 (4-5: a C1 tile lives until the accumulate
 // MMA LAG = 2 steps later has retired) and the in-place P/T tiles (every remaining 16 KB) -- all fed by one producer
-// thread that issues each ring's load as early as that ring allows (per-ring skew), so that every operand of step j is
-// requested about three steps before the tensor core needs it; S itself sits in a TMEM ring of 4; the accumulate MMA
-// trails the S MMA by two steps so that the tensor core never waits for the CUDA cores.
+// thread that polls the rings' "empty" barriers and refills whichever stage its consumer has released, so that every
+// operand of step j is requested as many steps ahead as its ring is deep; S itself sits in a TMEM ring of 4; the
+// accumulate MMA trails the S MMA by two steps so that the tensor core never waits for the CUDA cores.
 // Head-dim tail: a head dim of 32 m + 8 (or + 16) keeps its last k-block in a 32-byte (64-byte) swizzled tile instead of
 // a zero-padded 128-byte one (SD-1.5's d = 40: A 40 KB instead of 64 KB, which is what buys the deep P ring).
 // See pb_kernels.h (PbAttnLin) for the exact semantics.
@@ -175,28 +175,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
         if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
       }
-      // ring X may run (depth_X - life_X) steps ahead of the MMA issuer (life: steps until the consuming MMA has retired);
-      // each ring's load of item m is issued at producer iteration m + off_X so that all waits of one iteration fall on
-      // the same MMA step
-      const int ahead_b = NB, ahead_c1 = NC1 - LAG, ahead_pt = NPT - LAG;
-      const int ahead_max = max(ahead_b, max(ahead_c1, ahead_pt));
-      const int off_b = ahead_max - ahead_b, off_c1 = ahead_max - ahead_c1, off_pt = ahead_max - ahead_pt;
+      // Every ring is refilled as soon as ITS consumer releases a stage: the S-operand rings are released by the score
+      // MMAs, the P/T and C1 rings two steps later by the accumulate MMAs, so one thread polls the three "empty" barriers
+      // instead of blocking on them in a fixed order (a blocked P wait would hold back the B tiles the score warp needs).
       Ring rp{0, 0}, rb{0, 0}, rc{0, 0};
-      const int ah[2] = {bat_h * p.a_hmul[0], bat_h * p.a_hmul[1]};
+      int mp = 0, mb = 0, mc = 0;
       const int bh[2] = {bat_h * p.b_hmul[0], bat_h * p.b_hmul[1]}, bb[2] = {bat_b * p.b_bmul[0], bat_b * p.b_bmul[1]};
-      (void)ah;
-      for (int i = 0; i < nj + ahead_max; ++i) {
-        int m = i - off_pt;
-        if (m >= 0 && m < nj) {
-          mbar_wait(&pt_empty[rp.idx], rp.ph ^ 1);
-          mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
-          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], m * TN, r0, bat_h, 0);
-          rp.next(NPT);
-        }
-        m = i - off_b;
-        if (m >= 0 && m < nj) {
-          const int c0 = m * TN, st = rb.idx;
-          mbar_wait(&b_empty[st], rb.ph ^ 1);
+      long long t0 = clock64();
+      unsigned spins = 0;
+      while (mp < nj || mb < nj || mc < nj) {
+        bool any = false;
+        if (mb < nj && mbar_try_wait(&b_empty[rb.idx], rb.ph ^ 1) && (!has_c2 || mbar_try_wait(&c2_empty[rb.idx], rb.ph ^ 1))) {
+          const int c0 = mb * TN, st = rb.idx;
           mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
 #pragma unroll
           for (int s = 0; s < nseg; ++s) {
@@ -205,18 +195,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
             if (tail) tma_load_4d(dst + b_tail_off, &p.mapBt[s], &b_full[st], kfull * BK, c0, bh[s], bb[s]);
           }
           if (has_c2) {
-            mbar_wait(&c2_empty[st], rb.ph ^ 1);
             mbar_arrive_expect_tx(&c2_full[st], p.c_bytes);
             tma_load_4d(sC2 + st * p.c_tile_bytes, &p.mapC2, &c2_full[st], c0, 0, bat_h, bat_b);
           }
-          rb.next(NB);
+          rb.next(NB); ++mb; any = true;
         }
-        m = i - off_c1;
-        if (m >= 0 && m < nj) {
-          mbar_wait(&c_empty[rc.idx], rc.ph ^ 1);
+        if (mp < nj && mbar_try_wait(&pt_empty[rp.idx], rp.ph ^ 1)) {
+          mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
+          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TN, r0, bat_h, 0);
+          rp.next(NPT); ++mp; any = true;
+        }
+        if (mc < nj && mbar_try_wait(&c_empty[rc.idx], rc.ph ^ 1)) {
           mbar_arrive_expect_tx(&c_full[rc.idx], p.c_bytes);
-          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], m * TN, 0, bat_h, 0);
-          rc.next(NC1);
+          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TN, 0, bat_h, 0);
+          rc.next(NC1); ++mc; any = true;
+        }
+        if (any) { spins = 0; }
+        else if ((++spins & 0xfff) == 0 && clock64() - t0 > 8000000000LL) {     // a protocol bug must trap, never hang the GPU
+          printf("pb_attn: producer timeout block (%d,%d)\n", blockIdx.x, blockIdx.y);
+          __trap();
         }
       }
     }
