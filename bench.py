@@ -304,7 +304,7 @@ def run_ours(args, wl):
             if tj:
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "f16/tf32 operands, f32 accumulate", "data": "synthetic",
                 "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,
                            "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K,
                            "parallelism": (f"tangent-sharded x{world} (k columns of one problem split over the ranks, one all-gather of W per iteration)"
@@ -320,8 +320,9 @@ def run_ours(args, wl):
                              "step_achieved": achieved, "step_frac": (achieved / peak_tf) if achieved else None,
                              "kernels": kernels,
                              "note": "achieved = algorithmic flops (2 M N K per product) of the dominant kernel's launches / their summed "
-                                     "device time, event pair around every launch of 2 eager iterations; the kernel runs tcgen05 kind::tf32 "
-                                     "(fp32-parity path; hardware peak = half of the bf16 peak used as denominator); step_* = algorithmic "
+                                     "device time, event pair around every launch of 2 eager iterations; the kernel runs tcgen05 kind::f16 where the operand "
+                                     "can be stored as halves (every 3x3 conv, GN/LN/GEGLU-fed linears) and kind::tf32 elsewhere (hardware peak = "
+                                     "half of the bf16 peak used as denominator), fp32 accumulation; step_* = algorithmic "
                                      "flops of one whole step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; traffic = "
                                      "DRAM bytes per launch (ncu, profiles/); peak = " + peak_src}}
         if world == 1 and not args.no_cpu_baseline:
