@@ -2,5 +2,7 @@
 `local_encoder_pullback_zt/xt` hot path.  See DESIGN.md."""
 from .api import (eps, get_h, get_h_uncond, local_encoder_pullback_xt, local_encoder_pullback_zt,  # noqa: F401
                   patch_unet, refresh_weights)
-from .ddim import DDIMSchedule, ddim_forward_steps, ddim_inversion  # noqa: F401
+from .cache import (load_or_compute_local_basis, local_basis_dir, local_basis_name, local_basis_paths,  # noqa: F401
+                    normalize_basis)
+from .ddim import DDIMSchedule, ddim_forward_steps, ddim_inversion, x_space_guidance, x_space_guidance_edit  # noqa: F401
 from .engine import PullbackEngine, unet_config  # noqa: F401

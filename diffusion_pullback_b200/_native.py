@@ -118,6 +118,8 @@ def _declare(L):
     L.pb_set_option.restype = C.c_int
     L.pb_ddim_step.argtypes = [vp, vp, f32, f32, vp, vp, i64, vp]
     L.pb_ddim_step.restype = C.c_int
+    L.pb_lincomb3.argtypes = [vp, f32, vp, f32, vp, f32, vp, i64, vp]
+    L.pb_lincomb3.restype = C.c_int
     L.pb_profile_begin.argtypes = [vp]
     L.pb_profile_begin.restype = C.c_int
     L.pb_profile_read.argtypes = [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]

@@ -970,6 +970,11 @@ PB_API int pb_ddim_step(const float* x, const float* eps, float a_t, float a_nex
   return pbk_ddim_step(x, eps, a_t, a_next, x_next, pred_x0, (long)n, stream) ? PB_EINVAL : PB_OK;
 }
 
+PB_API int pb_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, void* stream) {
+  if (!out || !x || n < 0) return PB_EINVAL;
+  return pbk_lincomb3(out, a, x, b, y, c, z, (long)n, stream) ? PB_ECUDA : PB_OK;
+}
+
 PB_API int pb_profile_begin(pb_handle* h) {
   if (!h) return PB_EINVAL;
   for (auto& p : h->probes) { pbk_event_destroy(p.e0); pbk_event_destroy(p.e1); }

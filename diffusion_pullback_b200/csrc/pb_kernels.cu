@@ -162,6 +162,14 @@ __global__ void ddim_step_k(const float* __restrict__ x, const float* __restrict
     x_next[i] = c_x * p0 + c_eps * ev;
   }
 }
+__global__ void lincomb3_k(float* __restrict__ out, float a, const float* x, float b, const float* y, float c, const float* z, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = a * x[i];
+    if (y) v = fmaf(b, y[i], v);
+    if (z) v = fmaf(c, z[i], v);
+    out[i] = v;
+  }
+}
 __global__ void round_tf32_k(float* __restrict__ dst, const float* __restrict__ src, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = rna_tf32(src[i]);
@@ -1062,6 +1070,10 @@ PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, flo
   const float is = 1.f / sqrtf(a_t);
   ddim_step_k<<<grid_for(n, 256, 8), 256, 0, S(st)>>>(x, eps, is, sqrtf(1.f - a_t) * is, sqrtf(a_next), sqrtf(1.f - a_next),
                                                      x_next, pred_x0, n);
+  return last_err();
+}
+PBK pbk_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long n, pb_stream st) {
+  lincomb3_k<<<grid_for(n, 256, 8), 256, 0, S(st)>>>(out, a, x, b, y, c, z, n);
   return last_err();
 }
 PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st) {

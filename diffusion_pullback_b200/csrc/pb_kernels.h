@@ -141,6 +141,9 @@ PBK pbk_gemv(const float* Wm, const float* x, const float* bias, int N, int K, i
 PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n,
                   pb_stream st);
 
+// out = a x + b y + c z (y, z optional)
+PBK pbk_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long n, pb_stream st);
+
 // ---- weight packing (one-time) ----
 // w [Co][Ci][3][3] (PyTorch) -> fwd [Co][9][Ci], bwd [Ci][9][Co] with taps flipped (transpose conv)
 PBK pbk_pack_conv3x3(const float* w, int Co, int Ci, float* fwd, float* bwd, int round_tf32, pb_stream st);

@@ -119,3 +119,41 @@ def ddim_forward_steps(unet, scheduler, zt, prompt_emb, num_inference_steps, t_s
         noise_pred = _eps(unet, latents, t, prompt_emb, guidance_scale, neg_prompt_emb)
         latents = scheduler.step(noise_pred, t, latents, eta=0).prev_sample
     return latents
+
+
+def _lincomb3(a, x, b, y, c, z, _lib=None):
+    """a x + b y + c z through `pb_lincomb3` (one fused elementwise kernel on the tensors' device)."""
+    L = _lib if _lib is not None else N.lib()
+    if x.device.type != "cuda" and _lib is None:
+        raise RuntimeError("diffusion_pullback_b200 runs on a CUDA (sm_100a) device only (no CPU fallback exists)")
+    x = x.contiguous().float()
+    y = y.contiguous().float() if y is not None else None
+    z = z.contiguous().float() if z is not None else None
+    out = torch.empty_like(x)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream) if x.device.type == "cuda" else C.c_void_p(0)
+    if L.pb_lincomb3(p(out), float(a), p(x), float(b), p(y), float(c), p(z), x.numel(), st) != 0:
+        raise ValueError("pb_lincomb3: invalid arguments")
+    return out
+
+
+@torch.no_grad()
+def x_space_guidance(unet, scheduler, zt, t_idx, vk, single_edit_step, edit_prompt_emb, x_space_guidance_scale, _lib=None):
+    """`EditStableDiffusion.x_space_guidance` (`edit.py:484-502`): perturb z_t along the pullback direction v_k, predict the
+    noise at both points with the edit prompt, and move z_t by the scaled difference (DDS regularisation)."""
+    t = scheduler.timesteps[t_idx]
+    zt_edit = _lincomb3(1.0, zt, single_edit_step, vk.reshape(zt.shape), 0.0, None, _lib)          # zt + step * vk
+    et_null = unet.eps(zt, t, edit_prompt_emb)
+    et_edit = unet.eps(zt_edit, t, edit_prompt_emb)
+    return _lincomb3(1.0, zt, x_space_guidance_scale, et_edit, -x_space_guidance_scale, et_null, _lib)
+
+
+@torch.no_grad()
+def x_space_guidance_edit(unet, scheduler, zt, t_idx, vk, num_step, single_edit_step, edit_prompt_emb, x_space_guidance_scale,
+                          _lib=None):
+    """The edit loop of `edit.py:290-301`: `num_step` guidance steps from z_t; returns the list [z_t, z_t^1, ...]."""
+    zt_list = [zt.clone()]
+    for _ in range(num_step):
+        zt_list.append(x_space_guidance(unet, scheduler, zt_list[-1], t_idx, vk, single_edit_step, edit_prompt_emb,
+                                        x_space_guidance_scale, _lib))
+    return zt_list

@@ -134,6 +134,11 @@ int pb_set_option(pb_handle* h, const char* name, int value);
 int pb_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, int64_t n,
                  void* stream);
 
+/* out = a * x + b * y + c * z over n contiguous floats (y / z may be NULL with b / c = 0; out may alias any input): the two
+ * elementwise updates of the reference's x-space guidance (src/modules/edit.py:484-502):
+ *   zt_edit = zt + single_edit_step * vk            and            zt_edit = zt + scale * (et_edit - et_null). */
+int pb_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, int64_t n, void* stream);
+
 /* Timing probes for the roofline report (bench.py): after pb_profile_begin() every contraction-kernel launch made
  * through this handle is bracketed by an event pair on its stream (launches go out eagerly, no graph replay);
  * pb_profile_read() stops probing, waits, and returns the summed device time, the algorithmic flops (2 M N K per

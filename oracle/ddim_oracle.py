@@ -93,3 +93,14 @@ def ddim_forward_steps(unet, sched: Scheduler, zt, ctx, num_steps, t_start_idx=0
             return latents, t, t_idx
         latents = sched.step(_eps(unet, latents, t, ctx, guidance_scale, neg_ctx), t, latents)[0]
     return latents
+
+
+@torch.no_grad()
+def x_space_guidance(unet, sched: Scheduler, zt, t_idx, vk, single_edit_step, edit_prompt_emb, scale):
+    """`edit.py:484-502`: one batch-2 U-Net call on [zt, zt + step * vk] with the edit prompt, then
+    zt + scale * (eps_edit - eps_null)."""
+    t = sched.timesteps[t_idx]
+    zt_edit = zt + single_edit_step * vk
+    et = unet(torch.cat([zt, zt_edit], dim=0), t, encoder_hidden_states=edit_prompt_emb.repeat(2, 1, 1))
+    et_null, et_edit = et.chunk(2)
+    return zt + scale * (et_edit - et_null)

@@ -426,6 +426,10 @@ PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, flo
   }
   return nullptr;
 }
+PBK pbk_lincomb3(float* out, float a, const float* x, float b, const float* y, float c, const float* z, long n, pb_stream) {
+  for (long i = 0; i < n; ++i) out[i] = a * x[i] + (y ? b * y[i] : 0.f) + (z ? c * z[i] : 0.f);
+  return nullptr;
+}
 PBK pbk_timestep_embedding(float t, int dim, int flip, float shift, float* out, pb_stream) {
   const int half = dim / 2;
   for (int j = 0; j < half; ++j) {

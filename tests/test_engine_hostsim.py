@@ -196,3 +196,45 @@ def test_ddim_loops_follow_the_reference_schedule(hostsim):
     assert out[2] == ref[2] == 3 and float(out[1]) == float(ref[1]) and rel(out[0], ref[0]) < 1e-4
     full = PB.ddim_forward_steps(fake, sched, zT, ctx, 5)
     assert rel(full, DO.ddim_forward_steps(m, DO.Scheduler(ac), zT_ref, ctx, 5)) < 1e-4
+
+
+def test_x_space_guidance_and_cache_format(hostsim, tmp_path):
+    """the x-space guidance edit loop on the engine against the oracle restatement of
+    edit.py:484-502, and the u-/s-/vT- cache files with the reference's names, re-use rule and normalisation."""
+    import types
+    import diffusion_pullback_b200 as PB
+    from oracle import ddim_oracle as DO
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "full", 0, 1, EXACT)
+    fake = types.SimpleNamespace(eps=lambda s, tt, c: eng.set_point(s, float(tt), c, want_h=True))
+    hostsim.pb_lincomb3.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    ac = DO.sd_alphas_cumprod()
+    sched, osched = PB.DDIMSchedule(ac, _lib=hostsim), DO.Scheduler(ac)
+    sched.set_timesteps(10); osched.set_timesteps(10)
+    vk = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    vk = vk / vk.norm()
+    zs = PB.x_space_guidance_edit(fake, sched, x, 3, vk, 3, 1.5, ctx, 0.7, _lib=hostsim)
+    z = x
+    for i in range(3):
+        z = DO.x_space_guidance(m, osched, z, 3, vk, 1.5, ctx, 0.7)
+        assert rel(zs[i + 1], z) < 1e-4
+    assert len(zs) == 4 and torch.equal(zs[0], x)
+    # cache format (edit.py:218-268)
+    name = PB.local_basis_name("Examples", 0, 0.7, "a photo", "mid", 0, 0)
+    assert name == 'local_basis-Examples_0-0.7T-"a photo"-mid-block_0-seed_0'
+    d = PB.local_basis_dir("Examples", 100, 5, root=str(tmp_path))
+    assert d.endswith("inputs/local_encoder_pullback_stable_diffusion-dataset_Examples-num_steps_100-pca_rank_5")
+    calls = []
+
+    def pullback(sample, timestep, encoder_hidden_states, op, block_idx, pca_rank, **kw):
+        calls.append(kw)
+        g = torch.Generator().manual_seed(1)
+        return torch.randn(12, pca_rank, generator=g), torch.rand(pca_rank, generator=g), torch.randn(pca_rank, 20, generator=g)
+
+    u1, s1, v1 = PB.load_or_compute_local_basis(types.SimpleNamespace(local_encoder_pullback_zt=pullback), x, t, ctx, d, name, "mid", 0, 5)
+    assert calls == [dict(chunk_size=5, min_iter=10, max_iter=50, convergence_threshold=1e-4)]         # edit.py:236-239
+    up, sp, vp = PB.local_basis_paths(d, name)
+    assert os.path.basename(up) == "u-" + name + ".pt" and all(os.path.exists(p) for p in (up, sp, vp))
+    assert torch.allclose(u1.norm(dim=0), torch.ones(5)) and torch.allclose(v1.norm(dim=1), torch.ones(5))
+    u2, s2, v2 = PB.load_or_compute_local_basis(types.SimpleNamespace(local_encoder_pullback_zt=pullback), x, t, ctx, d, name, "mid", 0, 5)
+    assert len(calls) == 1 and s2 is None and torch.equal(u1, u2) and torch.equal(v1, v2)           # cache hit: no recompute
+    assert torch.equal(torch.load(sp), s1)

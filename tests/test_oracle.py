@@ -184,3 +184,22 @@ def test_ddim_oracle_reproduces_golden(name):
     assert torch.allclose(zT, g["zT"], rtol=1e-5, atol=1e-6)
     z, te, ie = DO.ddim_forward_steps(m, s, zT, ctx, g["for_steps"], 0, g["t_end_idx"], g["guidance_scale"], g["neg"])
     assert ie == g["idx_edit"] and float(te) == g["t_edit"] and torch.allclose(z, g["z_edit"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+def test_x_space_guidance_restatement_matches_verbatim_reference():
+    """oracle x_space_guidance against `EditStableDiffusion.x_space_guidance` (edit.py:484-502) run verbatim on a stand-in self."""
+    from oracle import ddim_oracle as DO
+    RS.load()
+    import modules.edit as E                                   # the reference module, imported in place
+    m = UT.build_unet("sd_tiny")
+    zt, _, ctx = UT.synthetic_inputs("sd_tiny")
+    s = DO.Scheduler(DO.sd_alphas_cumprod())
+    s.set_timesteps(10)
+    vk = torch.randn(zt.shape, generator=torch.Generator().manual_seed(2))
+    vk = vk / vk.norm()
+    me = types.SimpleNamespace(scheduler=s, edit_prompt_emb=ctx, x_space_guidance_scale=0.7,
+                               unet=lambda x, t, encoder_hidden_states: types.SimpleNamespace(sample=m(x, t, encoder_hidden_states=encoder_hidden_states)))
+    ref = E.EditStableDiffusion.x_space_guidance(me, zt, 3, vk, 1.5)
+    ours = DO.x_space_guidance(m, s, zt, 3, vk, 1.5, ctx, 0.7)
+    assert torch.equal(ref, ours)

@@ -219,6 +219,17 @@ def test_full_unet_eps_and_ddim_vs_golden(name):
     u, s, vT = unet.local_encoder_pullback_zt(z, te, ctx, op="mid", block_idx=0, pca_rank=2, min_iter=2, max_iter=2,
                                               convergence_threshold=0.0)
     assert torch.isfinite(s).all() and float(s[0]) >= float(s[1]) > 0
+    # ... followed by the x-space guidance edit along the first direction (edit.py:290-301, :484-502), against the oracle
+    from oracle import ddim_oracle as DO
+    m = UT.build_unet(name)
+    osched = DO.Scheduler(ddim_alphas())
+    osched.set_timesteps(g["for_steps"])
+    vk = vT[0].reshape(z.shape)
+    zs = PB.x_space_guidance_edit(unet, sched, z, ie, vk, 2, 1.0, ctx, 0.5)
+    zo = z.cpu()
+    for i in range(2):
+        zo = DO.x_space_guidance(m, osched, zo, ie, vk.cpu(), 1.0, ctx.cpu(), 0.5)
+        assert rel(zs[i + 1], zo) < 1e-2
 
 
 def ddim_alphas():
