@@ -34,6 +34,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's version banner / debug log goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 # name: (model config, op, block_idx, k, iterations, F_tan GF, primal GF)
 WORKLOADS = {

@@ -107,6 +107,11 @@ struct pb_handle {
   // CUDA graph of one iteration (jvp + vjp + orthonormalise)
   void* graph = nullptr; int graph_k = 0; float graph_tol = 0.f; int use_graph = 1; bool warm = false;
   const float* graph_u = nullptr; const float* graph_s = nullptr; long graph_nodes = 0;
+  // CUDA graphs of a stand-alone pb_jvp / pb_vjp at k columns (the tangent-sharded loop calls them once per iteration):
+  // they run between the handle's own staging buffers, so one capture serves every caller pointer
+  struct DirGraph { void* exec = nullptr; long nodes = 0; };
+  std::map<int, DirGraph> jvp_graphs, vjp_graphs;
+  bool warm_jvp = false, warm_vjp = false;
   // timing probes (pb_profile_begin / pb_profile_read): one event pair per contraction-kernel launch
   struct Probe { void* e0; void* e1; double flops; int kind; };
   bool profiling = false;
@@ -930,6 +935,42 @@ int check_ready(pb_handle* h, int k, bool need_point) {
 
 void drop_graph(pb_handle* h) {
   if (h->graph) { pbk_graph_destroy(h->graph); h->graph = nullptr; }
+  for (auto* m : {&h->jvp_graphs, &h->vjp_graphs}) {
+    for (auto& kv : *m) if (kv.second.exec) pbk_graph_destroy(kv.second.exec);
+    m->clear();
+  }
+}
+
+// Stand-alone J V / U^T J through a cached CUDA graph: user buffers are copied to / from the handle's staging buffers
+// (k x n_in and k x n_out floats: a few MB) so that the captured pointers never change.
+template <class Run>
+int run_direction(pb_handle* h, std::map<int, pb_handle::DirGraph>& graphs, bool& warm, int k, const float* in, size_t in_bytes,
+                  float* stage_in, float* stage_out, float* out, size_t out_bytes, pb_stream stream, Run&& run) {
+  if (!h->use_graph || h->profiling) return run(in, out);
+  CK(pbk_copy(stage_in, in, in_bytes, stream));
+  pb_handle::DirGraph& g = graphs[k];
+  if (!g.exec && warm) {
+    if (pbk_graph_begin(stream) == nullptr) {
+      const long before = h->launches;
+      const int rc = run(stage_in, stage_out);
+      const char* e2 = pbk_graph_end(stream, &g.exec, &g.nodes);
+      h->launches = before;
+      if (rc) { drop_graph(h); return rc; }
+      if (e2) { drop_graph(h); return fail(h, PB_ECUDA, std::string("graph capture: ") + e2); }
+    } else {
+      h->use_graph = 0;                    // backend without graph support: launch directly
+      return run(in, out);
+    }
+  }
+  if (g.exec) {
+    if (const char* e = pbk_graph_launch(g.exec, stream)) return fail(h, PB_ECUDA, std::string("graph launch: ") + e);
+    h->launches += g.nodes;
+  } else {
+    if (int e = run(stage_in, stage_out)) return e;          // the first call ever runs eagerly (one-time kernel attribute setup)
+    warm = true;
+  }
+  CK(pbk_copy(out, stage_out, out_bytes, stream));
+  return PB_OK;
 }
 
 }  // namespace
@@ -1154,13 +1195,15 @@ PB_API int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx,
 PB_API int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream) {
   if (int e = check_ready(h, k, true)) return e;
   if (!V || !U) return fail(h, PB_EINVAL, "null pointer");
-  return run_jvp(h, V, k, U, stream);
+  return run_direction(h, h->jvp_graphs, h->warm_jvp, k, V, (size_t)k * h->n_in * 4, h->WP(h->w_V), h->WP(h->w_U), U,
+                       (size_t)k * h->n_out * 4, stream, [&](const float* a, float* b) { return run_jvp(h, a, k, b, stream); });
 }
 
 PB_API int pb_vjp(pb_handle* h, const float* U, int32_t k, float* W, void* stream) {
   if (int e = check_ready(h, k, true)) return e;
   if (!U || !W) return fail(h, PB_EINVAL, "null pointer");
-  return run_vjp(h, U, k, W, stream);
+  return run_direction(h, h->vjp_graphs, h->warm_vjp, k, U, (size_t)k * h->n_out * 4, h->WP(h->w_U), h->WP(h->w_W), W,
+                       (size_t)k * h->n_in * 4, stream, [&](const float* a, float* b) { return run_vjp(h, a, k, b, stream); });
 }
 
 PB_API int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t k, float atol, float* V, float* s, float* metrics,
