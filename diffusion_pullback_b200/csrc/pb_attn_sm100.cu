@@ -27,6 +27,7 @@
 // See pb_kernels.h (PbAttnLin) for the exact semantics.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstring>
 
@@ -75,6 +76,7 @@ struct alignas(64) Params {
   const float* R; long ldr, sRb;
   float* D2; long ldd2, sD2b;
   int round_tf32;
+  float inv_pscale;                    // 1 / p_scale of the (possibly pre-scaled) probability matrix
 };
 
 // K-major swizzled smem matrix descriptor; swizzle span 128 / 64 / 32 bytes, 8-row groups 8 * span apart
@@ -100,17 +102,21 @@ struct Ring {
 // Template parameters fix the contraction shape so that the single-warp issue loops unroll into straight-line code
 // (NSEG segments, KFULL full k-blocks, NTAIL tail k-steps of 8 floats, C2M: 0 no second product, 1 folded into Acc,
 // 2 separate accumulator); NSEG < 0 is the generic kernel that reads the shape from Params.
-template <int NSEG, int KFULL, int NTAIL, int C2M>
+// P16: the probability matrix (pre-scaled by p_scale = Nc so that it sits in fp16's normal range), C1 and C2 are fp16 and
+// the step is 64 columns wide: P / T tiles are still 128 rows x 128 bytes in the same swizzle, the two accumulating
+// products run as kind::f16, and the P tile -- the largest stream of the kernel -- is half the bytes per column.
+template <int NSEG, int KFULL, int NTAIL, int C2M, bool P16>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_constant__ Params p) {
   constexpr bool GEN = NSEG < 0;
+  constexpr int TNc = P16 ? 64 : 32;            // score columns per step
   const int nseg = GEN ? p.nseg : NSEG;
   const int kfull = GEN ? p.kfull : KFULL;
   const int tail = GEN ? p.tail : NTAIL * 8;
   const bool has_c2 = GEN ? (p.has_c2 != 0) : (C2M != 0);
   const bool sep_acc2 = GEN ? (p.sep_acc2 != 0) : (C2M == 2);
   const int a_seg_bytes = GEN ? p.a_seg_bytes : KFULL * TM * 128 + TM * NTAIL * 32;
-  const int b_seg_bytes = GEN ? p.b_seg_bytes : KFULL * TN * 128 + TN * NTAIL * 32;
-  const int b_stage_bytes = GEN ? p.b_stage_bytes : (NSEG > 0 ? NSEG : 1) * (KFULL * TN * 128 + TN * NTAIL * 32);
+  const int b_seg_bytes = GEN ? p.b_seg_bytes : KFULL * TNc * 128 + TNc * NTAIL * 32;
+  const int b_stage_bytes = GEN ? p.b_stage_bytes : (NSEG > 0 ? NSEG : 1) * (KFULL * TNc * 128 + TNc * NTAIL * 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int NB = p.nb_st, NC1 = p.nc1_st, NPT = p.npt_st;
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   const int r0 = blockIdx.x * TM;
   // tangents fastest: the nb CTAs that share one head's P rows run back to back, so P comes from L2 for all but the first
   const int bat_b = blockIdx.y % p.nb, bat_h = blockIdx.y / p.nb;
-  const int nj = (p.Nc + TN - 1) / TN;
+  const int nj = (p.Nc + TNc - 1) / TNc;
 
   if (threadIdx.x == 0) {
     mbar_init(a_full, 1); mbar_init(acc_full, 1);
@@ -160,10 +166,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  const uint32_t tm_acc = tmem_base + NS * TN;
+  const uint32_t tm_acc = tmem_base + NS * TNc;
   const uint32_t tm_acc2 = sep_acc2 ? tm_acc + ACC2_OFF : tm_acc;
   const int tail_span = tail * 4;                              // bytes per row of the tail tile (32 or 64)
-  const int a_tail_off = kfull * TM * 128, b_tail_off = kfull * TN * 128;
+  const int a_tail_off = kfull * TM * 128, b_tail_off = kfull * TNc * 128;
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -186,12 +192,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       while (mp < nj || mb < nj || mc < nj) {
         bool any = false;
         if (mb < nj && mbar_try_wait(&b_empty[rb.idx], rb.ph ^ 1) && (!has_c2 || mbar_try_wait(&c2_empty[rb.idx], rb.ph ^ 1))) {
-          const int c0 = mb * TN, st = rb.idx;
+          const int c0 = mb * TNc, st = rb.idx;
           mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
 #pragma unroll
           for (int s = 0; s < nseg; ++s) {
             uint8_t* dst = sB + st * b_stage_bytes + s * b_seg_bytes;
-            for (int kb = 0; kb < kfull; ++kb) tma_load_4d(dst + kb * TN * 128, &p.mapB[s], &b_full[st], kb * BK, c0, bh[s], bb[s]);
+            for (int kb = 0; kb < kfull; ++kb) tma_load_4d(dst + kb * TNc * 128, &p.mapB[s], &b_full[st], kb * BK, c0, bh[s], bb[s]);
             if (tail) tma_load_4d(dst + b_tail_off, &p.mapBt[s], &b_full[st], kfull * BK, c0, bh[s], bb[s]);
           }
           if (has_c2) {
@@ -202,12 +208,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         }
         if (mp < nj && mbar_try_wait(&pt_empty[rp.idx], rp.ph ^ 1)) {
           mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
-          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TN, r0, bat_h, 0);
+          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TNc, r0, bat_h, 0);
           rp.next(NPT); ++mp; any = true;
         }
         if (mc < nj && mbar_try_wait(&c_empty[rc.idx], rc.ph ^ 1)) {
           mbar_arrive_expect_tx(&c_full[rc.idx], p.c_bytes);
-          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TN, 0, bat_h, 0);
+          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TNc, 0, bat_h, 0);
           rc.next(NC1); ++mc; any = true;
         }
         if (any) { spins = 0; }
@@ -221,8 +227,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     // =========================== MMA issuers ===========================
     // warp 1 issues the score products S(j), warp 10 the products that accumulate over the steps (P . C2, T . C1): two
     // single-warp instruction streams instead of one.  The whole warp walks its loop; one elected lane issues (elect_one).
-    const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
-    const uint32_t idesc_a = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TNc >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_a = (1u << 4) | (P16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     const uint32_t uA = sm_u, uB = uA + nseg * a_seg_bytes, uC = uB + NB * b_stage_bytes, uC2 = uC + NC1 * p.c_tile_bytes;
@@ -243,13 +249,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         tcgen05_fence_after();
         if (elect_one()) {
           uint32_t on = 0;
-          const uint32_t d_s = tm_u + rs.idx * TN;
+          const uint32_t d_s = tm_u + rs.idx * TNc;
 #pragma unroll
           for (int s = 0; s < nseg; ++s) {
             const uint64_t a0 = dA + uint64_t(s * a_seg16), b0 = dB + uint64_t(rb.idx * b_stage16 + s * b_seg16);
 #pragma unroll
             for (int kb = 0; kb < kfull; ++kb) {
-              const uint64_t adesc = a0 + uint64_t(kb * (TM * 128 >> 4)), bdesc = b0 + uint64_t(kb * (TN * 128 >> 4));
+              const uint64_t adesc = a0 + uint64_t(kb * (TM * 128 >> 4)), bdesc = b0 + uint64_t(kb * (TNc * 128 >> 4));
               const int nk = (GEN && kb == kfull - 1) ? nk_last : 4;   // specialised shapes have whole k-blocks only
 #pragma unroll
               for (int k = 0; k < nk; ++k) { mma_tf32(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, on); on = 1; }
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       }
     } else {
       const uint64_t dC = make_smem_desc(uC), dC2 = make_smem_desc(uC2), dPT = make_smem_desc(uPT);
-      const uint32_t u_acc = tm_u + NS * TN, u_acc2 = sep_acc2 ? u_acc + ACC2_OFF : u_acc;
+      const uint32_t u_acc = tm_u + NS * TNc, u_acc2 = sep_acc2 ? u_acc + ACC2_OFF : u_acc;
       uint32_t acc_on = 0, acc2_on = 0;                          // 0 until the accumulator has been written once
       Ring rc2{0, 0}, rp{0, 0}, ra_pt{0, 0}, ra_c{0, 0};         // C2 / P for the C2 product / accumulate: T, C1
       auto do_acc = [&]() {                                      // Acc += T(jj) . C1(jj), jj = the accumulate rings' position
@@ -279,7 +285,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         const uint64_t bdesc = dC + uint64_t(ra_c.idx * c_tile16);
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_tf32(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
+          for (int k = 0; k < 4; ++k) {
+            if constexpr (P16) mma_f16(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
+            else mma_tf32(u_acc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, acc_on | uint32_t(k));
+          }
           tcgen05_commit(&c_empty[ra_c.idx]);
           tcgen05_commit(&pt_empty[ra_pt.idx]);
         }
@@ -297,7 +306,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           const uint32_t on = sep_acc2 ? acc2_on : acc_on;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_tf32(u_acc2, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, on | uint32_t(k));
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (P16) mma_f16(u_acc2, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, on | uint32_t(k));
+              else mma_tf32(u_acc2, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_a, on | uint32_t(k));
+            }
             tcgen05_commit(&c2_empty[rc2.idx]);
             tcgen05_commit(&p_used[rp.idx]);
           }
@@ -327,41 +339,87 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     for (int j = grp; j < nj; j += 2) {
       const int st = rp.idx, ss = rs.idx;
       const uint32_t ph = rp.ph;
-      const int cbase = j * TN;
-      float dcol[32];
-      if (p.delta_mode == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) dcol[i] = (cbase + i < p.Nc) ? __ldg(dbase + cbase + i) : 0.f;
-      }
+      const int cbase = j * TNc;
       uint8_t* tb = sPT + st * PT_BYTES + row * 128;
-      mbar_wait(&p_full[st], ph);
-      float4 pv[8];
+      if constexpr (!P16) {
+        float dcol[32];
+        if (p.delta_mode == 2) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(tb + ((uint32_t(i) ^ swz) << 4));
-      mbar_wait(&s_full[ss], rs.ph);
-      tcgen05_fence_after();
-      uint32_t sv[32];
-      tmem_ld32(tm_row + ss * TN, sv);
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[ss]);
-      float4 tv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float dl = p.delta_mode == 2 ? dcol[i * 4 + e] : drow;
-          const float t = pp[e] * (p.alpha1 * __uint_as_float(sv[i * 4 + e]) - dl);
-          o[e] = rna_tf32(t);
-          rsum += o[e];
+          for (int i = 0; i < 32; ++i) dcol[i] = (cbase + i < p.Nc) ? __ldg(dbase + cbase + i) : 0.f;
         }
-        tv[i] = make_float4(o[0], o[1], o[2], o[3]);
-      }
-      if (has_c2) mbar_wait(&p_used[st], ph);                  // the P . C2 MMA has consumed the tile
+        mbar_wait(&p_full[st], ph);
+        float4 pv[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + ((uint32_t(i) ^ swz) << 4)) = tv[i];
+        for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const float4*>(tb + ((uint32_t(i) ^ swz) << 4));
+        mbar_wait(&s_full[ss], rs.ph);
+        tcgen05_fence_after();
+        uint32_t sv[32];
+        tmem_ld32(tm_row + ss * TNc, sv);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[ss]);
+        float4 tv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pp[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float dl = p.delta_mode == 2 ? dcol[i * 4 + e] : drow;
+            const float t = pp[e] * (p.alpha1 * __uint_as_float(sv[i * 4 + e]) - dl);
+            o[e] = rna_tf32(t);
+            rsum += o[e];
+          }
+          tv[i] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        if (has_c2) mbar_wait(&p_used[st], ph);                  // the P . C2 MMA has consumed the tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + ((uint32_t(i) ^ swz) << 4)) = tv[i];
+      } else {
+        // 64 columns per step: the row is 8 chunks of 8 halves (scaled probabilities), T goes back as halves
+        mbar_wait(&p_full[st], ph);
+        uint4 pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pv[i] = *reinterpret_cast<const uint4*>(tb + ((uint32_t(i) ^ swz) << 4));
+        mbar_wait(&s_full[ss], rs.ph);
+        tcgen05_fence_after();
+        uint4 tv[8];
+#pragma unroll
+        for (int hv = 0; hv < 2; ++hv) {
+          uint32_t sv[32];
+          tmem_ld32(tm_row + ss * TNc + hv * 32, sv);
+          if (hv == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[ss]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ci = hv * 4 + i;
+            const __half2* ph2 = reinterpret_cast<const __half2*>(&pv[ci]);
+            __half2 oh[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const float2 pf = __half22float2(ph2[e2]);
+              const int col = ci * 8 + e2 * 2;
+              float d0 = drow, d1 = drow;
+              if (p.delta_mode == 2) {
+                d0 = (cbase + col < p.Nc) ? __ldg(dbase + cbase + col) : 0.f;
+                d1 = (cbase + col + 1 < p.Nc) ? __ldg(dbase + cbase + col + 1) : 0.f;
+              }
+              const float t0 = pf.x * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2]) - d0);
+              const float t1 = pf.y * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2 + 1]) - d1);
+              oh[e2] = __floats2half2_rn(t0, t1);
+              const float2 back = __half22float2(oh[e2]);        // the row sum of what the tensor core will see
+              rsum += back.x + back.y;
+            }
+            tv[ci] = *reinterpret_cast<const uint4*>(oh);
+          }
+        }
+        if (has_c2) mbar_wait(&p_used[st], ph);                  // the P . C2 MMA has consumed the tile
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(tb + ((uint32_t(i) ^ swz) << 4)) = tv[i];
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_full[st]);
@@ -371,7 +429,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     s_rsum[grp * TM + row] = rsum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (grp == 0 || sep_acc2) {
-      const float rs = (grp == 0 && p.want_rsum) ? s_rsum[row] + s_rsum[TM + row] : 0.f;
+      const float rs = (grp == 0 && p.want_rsum) ? (s_rsum[row] + s_rsum[TM + row]) * p.inv_pscale : 0.f;
       mbar_wait(acc_full, 0);
       tcgen05_fence_after();
       const long rr = row_ok ? r : 0;
@@ -382,10 +440,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         dptr = p.D + (long)bat_b * p.sDb + rr * p.ldd + bat_h * p.d;
         if (p.R) rptr = p.R + (long)bat_b * p.sRb + rr * p.ldr + bat_h * p.d;
         if (p.want_rsum && p.O) optr = p.O + rr * p.ldo + bat_h * p.d;
-        alpha = p.alpha2; tm = tm_acc;
+        alpha = p.alpha2 * p.inv_pscale; tm = tm_acc;
       } else {
         dptr = p.D2 + (long)bat_b * p.sD2b + rr * p.ldd2 + bat_h * p.d;
-        alpha = 1.f; tm = tm_acc2;
+        alpha = p.inv_pscale; tm = tm_acc2;
       }
       for (int c16 = 0; c16 < p.dpad; c16 += 16) {
         uint32_t v[16];
@@ -432,6 +490,11 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (a.nseg < 1 || a.nseg > 2) return "attn_lin: 1 or 2 segments";
   if ((long)a.nb * a.nh > 65535) return "attn_lin: batch too large";
   if (a.D2 && !a.C2) return "attn_lin: D2 needs C2";
+  const int p16 = a.p16 ? 1 : 0;                // Pm (pre-scaled by p_scale), C1, C2 hold halves; 64-column steps
+  const int TNh = p16 ? 64 : TN;                // score columns per step
+  const long ces = p16 ? 2 : 4;                 // element size of Pm / C1 / C2
+  const int cq = p16 ? 8 : 4;                   // elements per 16 bytes
+  if (p16 && !(a.p_scale > 0.f)) return "attn_lin: p_scale must be positive";
   Params p;
   memset(&p, 0, sizeof p);
   p.nseg = a.nseg; p.d = a.d; p.dpad = (a.d + 15) / 16 * 16;
@@ -445,13 +508,14 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.want_rsum = a.want_rsum; p.O = a.O; p.ldo = a.ldo;
   p.D = a.D; p.ldd = a.ldd; p.sDb = a.sDb; p.R = a.R; p.ldr = a.ldr; p.sRb = a.sRb; p.round_tf32 = a.round_tf32;
   p.has_c2 = a.C2 ? 1 : 0; p.sep_acc2 = a.D2 ? 1 : 0; p.D2 = a.D2; p.ldd2 = a.ldd2; p.sD2b = a.sD2b;
-  if ((a.ldd % 4) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % 4) || (a.D2 && a.ldd2 % 4) ||
+  p.inv_pscale = p16 ? 1.f / a.p_scale : 1.f;
+  if ((a.ldd % 4) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % cq) || (a.ldc % cq) || (a.D2 && a.ldd2 % 4) ||
       ((reinterpret_cast<uintptr_t>(a.D) | reinterpret_cast<uintptr_t>(a.R) | reinterpret_cast<uintptr_t>(a.O) |
         reinterpret_cast<uintptr_t>(a.Pm) | reinterpret_cast<uintptr_t>(a.D2)) & 15))
-    return "attn_lin: D/D2/R/O/P must be 16-byte aligned with ld % 4 == 0";
+    return "attn_lin: D/D2/R/O/P must be 16-byte aligned with rows that are multiples of 16 bytes";
   const int tail_span = p.tail * 4;
   p.a_seg_bytes = p.kfull * TM * 128 + TM * tail_span;
-  p.b_seg_bytes = p.kfull * TN * 128 + TN * tail_span;
+  p.b_seg_bytes = p.kfull * TNh * 128 + TNh * tail_span;
   p.b_stage_bytes = p.nseg * p.b_seg_bytes;
   p.c_tile_bytes = p.dpad * 128;
   uint32_t abytes = 0, bbytes = 0;
@@ -461,39 +525,39 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     if (p.kfull) {
       if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, BK, TM, 128,
                                                 &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, BK, TN, 128,
+      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, BK, TNh, 128,
                                                 &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab * p.kfull; bbytes += bb * p.kfull;
     }
     if (p.tail) {
       if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, p.tail, TM,
                                                 tail_span, &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.tail, TN,
+      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.tail, TNh,
                                                 tail_span, &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab; bbytes += bb;
     }
   }
   p.a_bytes = abytes; p.b_bytes = bbytes;
   {
-    // C1: [nh][d][ldc], K-major over the score columns; box = [32 columns] x [d rows]
+    // C1: [nh][d][ldc], K-major over the score columns; box = [one step of columns = 128 bytes] x [d rows]
     uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), 1};
-    uint64_t stb[3] = {uint64_t(a.ldc) * 4, uint64_t(a.sCh) * 4, uint64_t(a.sCh) * 4 * a.nh};
-    uint32_t box[4] = {uint32_t(BK), uint32_t(a.d), 1, 1};
-    if (const char* e = pbgemm::encode4x(&p.mapC, a.C1, 0, dims, stb, box, 128)) return e;
-    p.c_bytes = uint32_t(a.d) * BK * 4;
+    uint64_t stb[3] = {uint64_t(a.ldc) * ces, uint64_t(a.sCh) * ces, uint64_t(a.sCh) * ces * a.nh};
+    uint32_t box[4] = {uint32_t(TNh), uint32_t(a.d), 1, 1};
+    if (const char* e = pbgemm::encode4x(&p.mapC, a.C1, p16, dims, stb, box, 128)) return e;
+    p.c_bytes = uint32_t(a.d) * 128;
   }
   if (a.C2) {
     // C2: [nb][nh][d][ldc2]
-    if ((a.ldc2 % 4) || (reinterpret_cast<uintptr_t>(a.C2) & 15)) return "attn_lin: C2 must be 16-byte aligned with ld % 4 == 0";
+    if ((a.ldc2 % cq) || (reinterpret_cast<uintptr_t>(a.C2) & 15)) return "attn_lin: C2 must be 16-byte aligned with rows that are multiples of 16 bytes";
     uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), uint64_t(a.nb)};
-    uint64_t stb[3] = {uint64_t(a.ldc2) * 4, uint64_t(a.nh > 1 ? a.sC2h : a.ldc2) * 4, uint64_t(a.nb > 1 ? a.sC2b : a.ldc2) * 4};
-    uint32_t box[4] = {uint32_t(BK), uint32_t(a.d), 1, 1};
-    if (const char* e = pbgemm::encode4x(&p.mapC2, a.C2, 0, dims, stb, box, 128)) return e;
+    uint64_t stb[3] = {uint64_t(a.ldc2) * ces, uint64_t(a.nh > 1 ? a.sC2h : a.ldc2) * ces, uint64_t(a.nb > 1 ? a.sC2b : a.ldc2) * ces};
+    uint32_t box[4] = {uint32_t(TNh), uint32_t(a.d), 1, 1};
+    if (const char* e = pbgemm::encode4x(&p.mapC2, a.C2, p16, dims, stb, box, 128)) return e;
   }
   {
-    // Pm: [nh][Mr][ldp]; box = [32 columns] x [128 rows]
+    // Pm: [nh][Mr][ldp]; box = [one step of columns = 128 bytes] x [128 rows]
     int hm, bm; uint32_t pb;
-    if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, 0, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, BK, TM, 128, &hm, &bm, &pb)) return e;
+    if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, p16, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, TNh, TM, 128, &hm, &bm, &pb)) return e;
     p.p_bytes = pb;
   }
   // ring depths from the shared-memory budget: B and C2 rings of 3 stages, C1 ring of 5 (4 when tight), every remaining
@@ -516,17 +580,18 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
   const int c2m = a.C2 ? (a.D2 ? 2 : 1) : 0;
   const bool whole = (a.d % BK) <= 16;                         // every full k-block is complete (no OOB-padded block)
-  void (*kern)(Params) = attn_lin_kernel<-1, -1, -1, -1>;
-#define PB_ATTN_CASE(NSEG_, KF_, NT_, C2M_) \
-  if (whole && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ * 8 && c2m == C2M_) kern = attn_lin_kernel<NSEG_, KF_, NT_, C2M_>;
+  void (*kern)(Params) = p16 ? attn_lin_kernel<-1, -1, -1, -1, true> : attn_lin_kernel<-1, -1, -1, -1, false>;
+#define PB_ATTN_CASE(NSEG_, KF_, NT_, C2M_)                                                      \
+  if (whole && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ * 8 && c2m == C2M_)            \
+    kern = p16 ? attn_lin_kernel<NSEG_, KF_, NT_, C2M_, true> : attn_lin_kernel<NSEG_, KF_, NT_, C2M_, false>;
   PB_ATTN_CASE(2, 1, 1, 1) PB_ATTN_CASE(1, 1, 1, 0) PB_ATTN_CASE(1, 1, 1, 2)      // head dim 40 (SD-1.x 64x64 layers): JVP, VJP-A, VJP-B
   PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // head dim 64 (SD-2.x)
   PB_ATTN_CASE(2, 2, 2, 1) PB_ATTN_CASE(1, 2, 2, 0) PB_ATTN_CASE(1, 2, 2, 2)      // head dim 80 (SD-1.x 32x32 layers)
 #undef PB_ATTN_CASE
-  static void (*configured[12])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
+  static void (*configured[24])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
   int ci = 0;
-  while (ci < 12 && configured[ci] && configured[ci] != kern) ++ci;
-  if (ci == 12) return "attn_lin: internal (instantiation table full)";
+  while (ci < 24 && configured[ci] && configured[ci] != kern) ++ci;
+  if (ci == 24) return "attn_lin: internal (instantiation table full)";
   if (!configured[ci]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return cudaGetErrorString(e);

@@ -71,6 +71,9 @@ struct Op {
   int heads = 0, d = 0, cross = 0, Nq = 0, Nk = 0, ldk = 0, ldq = 0, kv = -1;
   float scale = 0.f;
   size_t P_off = 0, Pt_off = 0, Qt_off = 0, Kt_off = 0, Vt_off = 0;
+  // fp16 copies for the fused linearisation kernel (p16 = 1): N-scaled P and P^T, and the transposed primal operands
+  int p16 = 0;
+  size_t P16_off = 0, Pt16_off = 0, Qt16_off = 0, Kt16_off = 0, Vt16_off = 0;
 };
 
 }  // namespace
@@ -250,6 +253,15 @@ struct Planner {
       o.Pt_off = cache_alloc((size_t)heads * Nk * o.ldq);
       o.Qt_off = cache_alloc((size_t)C * o.ldq);
     }
+    static const int f16_mask = getenv("PB_F16_MASK") ? atoi(getenv("PB_F16_MASK")) : 31;   // bit 4: fp16 attention operands
+    if (!cross && h->use_f16() && (f16_mask & 16) && o.d <= 64 && N % 8 == 0 && Nk % 8 == 0 && pbk_attn_lin_supported(o.d, (int)N, Nk) == nullptr) {
+      o.p16 = 1;                                  // ldk == Nk and ldq == N here: the fp16 copies share the fp32 geometry
+      o.P16_off = cache_alloc((size_t)heads * N * o.ldk / 2);
+      o.Pt16_off = cache_alloc((size_t)heads * Nk * o.ldq / 2);
+      o.Vt16_off = cache_alloc((size_t)C * o.ldk / 2);
+      o.Kt16_off = cache_alloc((size_t)C * o.ldk / 2);
+      o.Qt16_off = cache_alloc((size_t)C * o.ldq / 2);
+    }
     h->n_s1 = std::max(h->n_s1, (size_t)heads * N * o.ldk);
     if (!cross) h->n_s2 = std::max(h->n_s2, (size_t)heads * Nk * o.ldq);
     h->n_s3 = std::max(h->n_s3, (size_t)C * std::max(o.ldk, o.ldq));
@@ -413,9 +425,9 @@ void analyse_f16(pb_handle* h) {
     if (o.y >= 0 && o.kind != OP_OUT) producer[o.y] = i;
     for (int v : {o.x, o.x2, o.res}) if (v >= 0) ++consumers[v];
   }
-  // PB_F16_MASK (debug): bit 0 JVP convs, 1 JVP linears, 2 VJP stored-as-fp16, 3 VJP converted convs
+  // PB_F16_MASK (debug): bit 0 JVP convs, 1 JVP linears, 2 VJP stored-as-fp16, 3 VJP converted convs, 4 attention (Planner::attn)
   const char* env = getenv("PB_F16_MASK");
-  const int mask = env ? atoi(env) : 15;
+  const int mask = env ? atoi(env) : 31;
   auto elementwise = [&](OpKind k, bool vjp) {
     return k == OP_GN || k == OP_LN || k == OP_GEGLU || (!vjp && (k == OP_IM2COL || k == OP_UPSAMPLE));
   };
@@ -550,6 +562,14 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   if (!o.cross) {
     CK(pbk_transpose(h->CP(o.Qt_off), o.ldq, 0, (long)d * o.ldq, Q, ldq_, 0, d, 1, hd, N, d, 0.f, h->rnd, st));
     CK(pbk_transpose(h->CP(o.Pt_off), o.ldq, 0, (long)Nk * o.ldq, P, ldk, 0, (long)N * ldk, 1, hd, N, Nk, 0.f, h->rnd, st));
+    if (o.p16) {
+      // probabilities scaled by the row length sit around 1: fp16's normal range (softmax rows of 4096 are ~2e-4 unscaled)
+      CK(pbk_to_f16_scaled(h->CP(o.P16_off), P, (size_t)hd * N * ldk, (float)Nk, st));
+      CK(pbk_to_f16_scaled(h->CP(o.Pt16_off), h->CP(o.Pt_off), (size_t)hd * Nk * o.ldq, (float)N, st));
+      CK(pbk_to_f16(h->CP(o.Vt16_off), Vt, (size_t)C * ldk, st));
+      CK(pbk_to_f16(h->CP(o.Kt16_off), Kt, (size_t)C * ldk, st));
+      CK(pbk_to_f16(h->CP(o.Qt16_off), h->CP(o.Qt_off), (size_t)C * o.ldq, st));
+    }
   }
   {
     PbGemm g = plain_gemm(P, ldk, N, Vt, ldk, d, Nk, h->P(o.y), C);
@@ -572,7 +592,8 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     // dO = [P o dS] V - rowsum(P o dS) o O + P dV   with dS = (dQ K^T + Q dK^T)/sqrt(d) never stored and P streamed once
     const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
     float* dVt = h->WP(h->w_s3);
-    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dqkv + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f, h->rnd, st));
+    const bool p16 = o.p16 && h->use_f16();
+    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dqkv + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f, p16 ? 2 : h->rnd, st));
     PbAttnLin a{};
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 2;
     a.seg[0].A = dqkv; a.seg[0].lda = 3 * C; a.seg[0].sAb = (long)N * 3 * C; a.seg[0].sAh = d;
@@ -584,6 +605,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.C2 = dVt; a.ldc2 = ldk; a.sC2h = (long)d * ldk; a.sC2b = (long)C * ldk;
+    if (p16) { a.p16 = 1; a.p_scale = (float)Nk; a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
@@ -642,11 +664,13 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
     a.delta = delta; a.delta_mode = 1;
     a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
+    const bool p16 = o.p16 && h->use_f16();
+    if (p16) { a.p16 = 1; a.p_scale = (float)Nk; a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Kt16_off); }
     a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
     // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q  and  Vbar = P^T Obar  (rows = keys, columns = queries; P^T streamed once)
-    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
+    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, p16 ? 2 : h->rnd, st));
     PbAttnLin b{};
     b.Mr = Nk; b.Nc = N; b.d = d; b.nb = nb; b.nh = hd; b.nseg = 1;
     b.seg[0].A = V; b.seg[0].lda = ldkv; b.seg[0].sAb = 0; b.seg[0].sAh = d;
@@ -658,6 +682,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
     b.C2 = gOt; b.ldc2 = ldq; b.sC2h = (long)d * ldq; b.sC2b = (long)C * ldq;
     b.D2 = gx + 2 * C; b.ldd2 = 3 * C; b.sD2b = (long)N * 3 * C;
+    if (p16) { b.p16 = 1; b.p_scale = (float)N; b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
     b.round_tf32 = h->rnd;
     CK(attn_lin_call(h, b, st));
     h->vals[o.x].ginit = true;

@@ -109,9 +109,13 @@ __global__ void transpose_k(float* __restrict__ dst, long ldd, long sbd, long sh
     const int c = c0 + i, r = r0 + threadIdx.x;
     if (c < C && r < R) {
       float v = tile[threadIdx.x][i];
-      float* p = d + (long)c * ldd + r;
-      if (beta != 0.f) v += beta * *p;
-      *p = maybe_round(v, rnd);
+      if (rnd == 2) {                                            // halves: dst, ldd and the batch strides count elements
+        reinterpret_cast<__half*>(dst)[(long)b * sbd + (long)h * shd + (long)c * ldd + r] = __float2half_rn(v);
+      } else {
+        float* p = d + (long)c * ldd + r;
+        if (beta != 0.f) v += beta * *p;
+        *p = maybe_round(v, rnd);
+      }
     }
   }
 }
@@ -149,9 +153,12 @@ __global__ void upsample2x_vjp_k(const float4* __restrict__ gy, int nb, int H, i
     gx[i] = maybe_round4(a, rnd);
   }
 }
-__global__ void to_f16_k(__half* __restrict__ dst, const float* __restrict__ src, size_t n4) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
-    store_out4(reinterpret_cast<float*>(dst), 4 * (long)i, reinterpret_cast<const float4*>(src)[i], 2);
+__global__ void to_f16_k(__half* __restrict__ dst, const float* __restrict__ src, size_t n4, float scale) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(src)[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    store_out4(reinterpret_cast<float*>(dst), 4 * (long)i, v, 2);
+  }
 }
 __global__ void ddim_step_k(const float* __restrict__ x, const float* __restrict__ eps, float c_x0, float c_eps0, float c_x,
                             float c_eps, float* __restrict__ x_next, float* __restrict__ pred_x0, long n) {
@@ -1039,6 +1046,7 @@ PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int 
 PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, long lds, long sbs, long shs, int nb,
                   int nh, int R, int C, float beta, int round_tf32, pb_stream st) {
   if ((long)nb * nh > 65535 || (R + 31) / 32 > 65535) return "transpose: batch / row extent too large";
+  if (round_tf32 == 2 && beta != 0.f) return "transpose: fp16 output cannot accumulate";
   dim3 grid((C + 31) / 32, (R + 31) / 32, nb * nh), block(32, 8);
   transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, sbd, shd, src, lds, sbs, shs, nh, R, C, beta, round_tf32);
   return last_err();
@@ -1059,11 +1067,12 @@ PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, 
   return last_err();
 }
 extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return 1; }
-PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) {
+PBK pbk_to_f16_scaled(void* dst, const float* src, size_t n, float scale, pb_stream st) {
   if (n % 4 || (reinterpret_cast<uintptr_t>(dst) & 7) || (reinterpret_cast<uintptr_t>(src) & 15)) return "to_f16: n % 4 and alignment";
-  to_f16_k<<<grid_for((long)(n / 4), 256, 16), 256, 0, S(st)>>>(static_cast<__half*>(dst), src, n / 4);
+  to_f16_k<<<grid_for((long)(n / 4), 256, 16), 256, 0, S(st)>>>(static_cast<__half*>(dst), src, n / 4, scale);
   return last_err();
 }
+PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) { return pbk_to_f16_scaled(dst, src, n, 1.f, st); }
 PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n,
                   pb_stream st) {
   if (!(a_t > 0.f) || !(a_next >= 0.f) || a_t > 1.f || a_next > 1.f) return "ddim_step: alphas_cumprod must lie in (0, 1]";

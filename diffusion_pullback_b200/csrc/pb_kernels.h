@@ -8,7 +8,7 @@
 // cudaStream_t, every call is stream-ordered and returns nullptr or a static error string.
 // `round_tf32` of a producer: 0 store fp32 as is; 1 RNA-round to TF32 (the consumer is a TF32 GEMM); 2 store fp16 --
 // the output buffer then holds halves at the same element offsets and its only consumer is an fp16-operand GEMM
-// (pbk_gn_lin, pbk_ln_lin, pbk_geglu_jvp/vjp, pbk_im2col_s2, pbk_upsample2x; not together with accumulation).
+// (pbk_gn_lin, pbk_ln_lin, pbk_geglu_jvp/vjp, pbk_im2col_s2, pbk_upsample2x, pbk_transpose; not together with accumulation).
 // "xp" arguments are PRIMAL tensors cached once per (x_t, t, prompt); "t"/"g" arguments carry the
 // nb tangent (JVP) or cotangent (VJP) directions packed on the batch axis.
 #pragma once
@@ -64,6 +64,7 @@ PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
 // fp16-operand GEMMs (kind::f16, same 10-bit mantissa as TF32, half the operand bytes): 1 if the backend has them
 extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands();
 PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st);               // n % 4 == 0
+PBK pbk_to_f16_scaled(void* dst, const float* src, size_t n, float scale, pb_stream st);
 
 // ---- GroupNorm (+ optional SiLU) ----
 // tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch (per-chunk partial sums, combined in a fixed order)
@@ -127,6 +128,9 @@ struct PbAttnLin {
   int round_tf32;
   const float* C2; long ldc2, sC2h, sC2b;   // optional [nb][nh][d][ldc2]
   float* D2; long ldd2, sD2b;               // optional separate output of the C2 product
+  // p16: Pm, C1 and C2 hold HALVES (leading dimensions / strides in elements, rows multiples of 8) and Pm is pre-scaled by
+  // p_scale (= Nc keeps softmax probabilities in fp16's normal range); the kernel divides the products by p_scale again
+  int p16; float p_scale;
 };
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);

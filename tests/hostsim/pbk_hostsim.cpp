@@ -54,6 +54,7 @@ PBK pbk_graph_destroy(void*) { return nullptr; }
 // the double models the fp32 / TF32 policy only: the engine asks and keeps every operand in fp32
 extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return 0; }
 PBK pbk_to_f16(void*, const float*, size_t, pb_stream) { return "hostsim: fp16 operands are not modelled"; }
+PBK pbk_to_f16_scaled(void*, const float*, size_t, float, pb_stream) { return "hostsim: fp16 operands are not modelled"; }
 // timing probes: the double has no clock; a non-null token keeps the engine's bookkeeping exercised
 PBK pbk_event_record(void** ev, pb_stream) { static int token; *ev = &token; return nullptr; }
 extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void*, void*) { return 0.f; }
@@ -377,6 +378,7 @@ PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
 }
 PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
   const PbAttnLin& a = *ap;
+  if (a.p16) return "hostsim: fp16 attention operands are not modelled";
   for (long b = 0; b < a.nb; ++b)
     for (long h = 0; h < a.nh; ++h) {
 #pragma omp parallel for schedule(static)

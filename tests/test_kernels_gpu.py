@@ -387,6 +387,69 @@ def test_thin_convs_blocked(nb, H, W, Cin, Cout):
     assert rel(gi, ref) < 1e-5
 
 
+@pytest.mark.parametrize("c2", [0, 1, 2])
+@pytest.mark.parametrize("Mr,Nc,d,nb,nh,nseg,mode", [(256, 256, 40, 2, 2, 2, 0), (384, 128, 64, 2, 2, 1, 2), (1024, 1024, 40, 3, 8, 2, 0),
+                                                       (128, 640, 32, 2, 1, 2, 1), (4096, 4096, 40, 1, 2, 2, 0), (300, 104, 48, 2, 2, 2, 2),
+                                                       (512, 512, 56, 2, 1, 2, 1), (2304, 2304, 64, 1, 5, 2, 0), (200, 328, 16, 1, 3, 1, 1)])
+def test_attn_lin_fused_fp16_operands(Mr, Nc, d, nb, nh, nseg, mode, c2):
+    """PbAttnLin with p16 = 1: Pm (pre-scaled by p_scale = Nc), C1 and C2 in fp16, 64-column steps, kind::f16 accumulating products."""
+    torch.manual_seed(7)
+    Cc = nh * d
+    ldp = (Nc + 7) // 8 * 8
+    A0 = torch.randn(nb, Mr, Cc, device="cuda"); B0 = torch.randn(Nc, Cc, device="cuda")
+    A1 = torch.randn(Mr, Cc, device="cuda"); B1 = torch.randn(nb, Nc, Cc, device="cuda")
+    Pm = torch.softmax(torch.randn(nh, Mr, ldp, device="cuda") * 2, -1).contiguous()
+    Pm[..., Nc:] = 0
+    P16 = (Pm * Nc).half().contiguous()
+    C1 = torch.randn(nh, d, ldp, device="cuda").half()
+    C2 = torch.randn(nb, nh, d, ldp, device="cuda").half()
+    O = torch.randn(Mr, Cc, device="cuda"); R = torch.randn(nb, Mr, Cc, device="cuda")
+    delta = torch.randn(nb, nh, Mr if mode == 1 else Nc, device="cuda") if mode else None
+    D = R.clone()
+    D2 = torch.full((nb, Mr, Cc), float("nan"), device="cuda")
+    a = N.PbAttnLin()
+    a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, nb, nh, nseg
+    s0 = a.seg[0]
+    s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = A0.data_ptr(), Cc, Mr * Cc, d, B0.data_ptr(), Cc, 0, d
+    s1 = a.seg[1]
+    s1.A, s1.lda, s1.sAb, s1.sAh, s1.B, s1.ldb, s1.sBb, s1.sBh = A1.data_ptr(), Cc, 0, d, B1.data_ptr(), Cc, Nc * Cc, d
+    a.alpha1, a.alpha2, a.beta = d ** -0.5, 0.7, 1.0
+    a.Pm, a.ldp, a.sPh = P16.data_ptr(), ldp, Mr * ldp
+    a.delta, a.delta_mode = (delta.data_ptr() if mode else None), mode
+    a.want_rsum, a.O, a.ldo = int(mode == 0), O.data_ptr(), Cc
+    a.C1, a.ldc, a.sCh = C1.data_ptr(), ldp, d * ldp
+    a.D, a.ldd, a.sDb, a.R, a.ldr, a.sRb, a.round_tf32 = D.data_ptr(), Cc, Mr * Cc, D.data_ptr(), Cc, Mr * Cc, 0
+    a.p16, a.p_scale = 1, float(Nc)
+    if c2:
+        a.C2, a.ldc2, a.sC2h, a.sC2b = C2.data_ptr(), ldp, d * ldp, nh * d * ldp
+    if c2 == 2:
+        a.D2, a.ldd2, a.sD2b = D2.data_ptr(), Cc, Mr * Cc
+    _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+    t = lambda z: tf32_trunc(z).double()
+    S = torch.einsum("bihd,jhd->bhij", t(A0).view(nb, Mr, nh, d), t(B0).view(Nc, nh, d))
+    if nseg == 2:
+        S = S + torch.einsum("ihd,bjhd->bhij", t(A1).view(Mr, nh, d), t(B1).view(nb, Nc, nh, d))
+    S = S * d ** -0.5
+    if mode == 1:
+        S = S - delta.double()[..., :, None]
+    if mode == 2:
+        S = S - delta.double()[..., None, :]
+    Ps = P16.double()[None, :, :, :Nc]                                 # the scaled probabilities the kernel reads
+    Tr = (Ps * S).float().half().double()                              # T is rounded to fp16 before the second contraction
+    acc = torch.einsum("bhij,hnj->bihn", Tr, C1.double()[..., :Nc]).reshape(nb, Mr, Cc) / Nc
+    if c2:
+        e2 = torch.einsum("hij,bhnj->bihn", P16.double()[..., :Nc], C2.double()[..., :Nc]).reshape(nb, Mr, Cc) / Nc
+        if c2 == 1:
+            acc = acc + e2
+        else:
+            assert rel(D2, e2) < 1e-5, rel(D2, e2)
+    ref = 0.7 * acc + R.double()
+    if mode == 0:
+        rs = Tr.sum(-1) / Nc
+        ref = ref - (rs.permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
+    assert rel(D, ref) < 3e-4, rel(D, ref)                             # a few T elements round the other way (fp32 vs fp64 S)
+
+
 def test_orthonormalize_matches_svd():
     torch.manual_seed(6)
     for k, n in ((5, 16384), (16, 16384), (2, 196608), (50, 4096)):
