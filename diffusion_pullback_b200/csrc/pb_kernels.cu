@@ -456,6 +456,98 @@ __global__ void gn_finalize_lin_k(const float* __restrict__ part, int chunks, in
   }
 }
 
+// One-launch GroupNorm linearisation: a block owns one (image, group) pair, sums over it (pass 1, HBM), and applies
+// (pass 2, the same bytes again from L2).  Replaces partial sums + finalize + apply (three launches and a round trip
+// of per-chunk partials) whenever there are enough (image, group) pairs to fill the machine.  Threads are laid out
+// [pixel lane][channel vector] so that no index needs a division inside the loops; V = 4 / 2 / 1 channels per access.
+template <int MODE, int V>
+__global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                                                      const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
+  __shared__ double sh[2][16];
+  __shared__ float s_m[2];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / G, cv = cpg / V;
+  const int rows = blockDim.x / cv;                      // pixel lanes
+  const int tid = threadIdx.x;
+  const bool active = tid < rows * cv;
+  const int j = active ? (tid % cv) * V : 0, p0 = tid / cv;
+  const float mu = mean[g], rs = rstd[g];
+  const float* xg = xp + g * cpg + j;
+  const float* tg = t + (long)b * HW * C + g * cpg + j;
+  float* og = out + (long)b * HW * C + g * cpg + j;
+  float ga[V], be[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) { ga[k] = gamma[g * cpg + j + k]; be[k] = beta_[g * cpg + j + k]; }
+  auto load = [&](const float* base, long p, float (&v)[V]) {
+    if constexpr (V == 4) { const float4 q = *reinterpret_cast<const float4*>(base + p * C); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else if constexpr (V == 2) { const float2 q = *reinterpret_cast<const float2*>(base + p * C); v[0] = q.x; v[1] = q.y; }
+    else v[0] = base[p * C];
+  };
+  float s1 = 0.f, s2 = 0.f;
+  if (active)
+    for (int p = p0; p < HW; p += rows) {
+      float xv[V], tv[V];
+      load(xg, p, xv); load(tg, p, tv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float xh = (xv[k] - mu) * rs;
+        float u = tv[k];
+        if (MODE == 1) u *= silu ? ga[k] * silu_d(fmaf(ga[k], xh, be[k])) : ga[k];
+        s1 += u; s2 = fmaf(xh, u, s2);
+      }
+    }
+  double d1 = s1, d2 = s2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = d1; sh[1][tid >> 5] = d2; }
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0, c = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
+    const double n = (double)HW * cpg;
+    s_m[0] = (float)(a / n); s_m[1] = (float)(c / n);
+  }
+  __syncthreads();
+  const float m1 = s_m[0], m2 = s_m[1];
+  if (!active) return;
+  for (int p = p0; p < HW; p += rows) {
+    float xv[V], tv[V], o[V];
+    load(xg, p, xv); load(tg, p, tv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float xh = (xv[k] - mu) * rs;
+      const float f = silu ? ga[k] * silu_d(fmaf(ga[k], xh, be[k])) : ga[k];
+      o[k] = MODE == 0 ? f * rs * (tv[k] - m1 - xh * m2) : rs * (tv[k] * f - m1 - xh * m2);
+    }
+    float* op = og + (long)p * C;
+    if (acc != 0.f) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] += acc * op[k];
+    }
+    if (rnd == 2) {
+      __half* hp = reinterpret_cast<__half*>(out) + ((long)b * HW * C + g * cpg + j) + (long)p * C;
+      if constexpr (V == 4) {
+        uint2 hv;
+        *reinterpret_cast<__half2*>(&hv.x) = __floats2half2_rn(o[0], o[1]);
+        *reinterpret_cast<__half2*>(&hv.y) = __floats2half2_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(hp) = hv;
+      } else if constexpr (V == 2) {
+        *reinterpret_cast<__half2*>(hp) = __floats2half2_rn(o[0], o[1]);
+      } else {
+        hp[0] = __float2half_rn(o[0]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) o[k] = maybe_round(o[k], rnd);
+      if constexpr (V == 4) *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+      else if constexpr (V == 2) *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
+      else op[0] = o[0];
+    }
+  }
+}
+
 __global__ void gn_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
                                const float* __restrict__ rstd, const float* __restrict__ gamma,
                                const float* __restrict__ beta_, long total4, int HW, int C, int G, int silu, int rnd,
@@ -1143,6 +1235,23 @@ PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const floa
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
                float* tmp, pb_stream st) {
   if (round_tf32 == 2 && acc != 0.f) return "groupnorm: fp16 output cannot accumulate";
+  if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
+  {
+    // enough (image, group) pairs to fill the SMs, or a tensor small enough that launch count is all that matters:
+    // one launch per GroupNorm (gn_lin_group_k); otherwise partial sums over pixel chunks + finalize + apply
+    const int cpg = C / G;
+    const long pairs = (long)G * nb;
+    const int V = cpg % 4 == 0 ? 4 : cpg % 2 == 0 ? 2 : 1;
+    if ((pairs >= 120 || (long)nb * HW * C <= (1L << 20)) && cpg / V <= 256) {
+      dim3 grid(G, nb);
+      const int block = 512;
+#define PB_GN_GROUP(M_, V_) gn_lin_group_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32)
+      if (mode == 0) { if (V == 4) PB_GN_GROUP(0, 4); else if (V == 2) PB_GN_GROUP(0, 2); else PB_GN_GROUP(0, 1); }
+      else { if (V == 4) PB_GN_GROUP(1, 4); else if (V == 2) PB_GN_GROUP(1, 2); else PB_GN_GROUP(1, 1); }
+#undef PB_GN_GROUP
+      return last_err();
+    }
+  }
   int chunks = 0;
   float* part = tmp;
   if (const char* e = gn_launch_sums(mode ? 2 : 1, xp, mean, rstd, gamma, beta, HW, C, G, silu, t, nb, part, &chunks, S(st)))
