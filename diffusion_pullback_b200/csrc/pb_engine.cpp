@@ -582,6 +582,12 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
 bool use_fused(const pb_handle* h, const Op& o) {
   return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
 }
+// cross-attention (77 text keys: three 32-column steps per tile) through the same kernel: one launch instead of
+// GEMM + softmax-linearisation + GEMM and no score tangent in HBM
+bool use_fused_cross(const pb_handle* h, const Op& o) {
+  static const bool off = getenv("PB_NO_FUSED_CROSS") != nullptr;      // A/B switch
+  return !off && o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
+}
 
 int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
@@ -606,6 +612,22 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.C2 = dVt; a.ldc2 = ldk; a.sC2h = (long)d * ldk; a.sC2b = (long)C * ldk;
     if (p16) { a.p16 = 1; a.p_scale = (float)Nk; a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
+    a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
+    a.round_tf32 = h->rnd;
+    CK(attn_lin_call(h, a, st));
+    return PB_OK;
+  }
+  if (o.cross && use_fused_cross(h, o)) {
+    // dO = [P o dS] V - rowsum(P o dS) o O with dS = dQ K^T / sqrt(d); the text keys / values are constants
+    const float* kv = h->CP(o.bias_eff_off);
+    PbAttnLin a{};
+    a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
+    a.seg[0].A = h->T(o.x); a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
+    a.seg[0].B = kv; a.seg[0].ldb = 2 * C; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.alpha1 = o.scale; a.alpha2 = 1.f;
+    a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
+    a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
+    a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
@@ -685,6 +707,24 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     if (p16) { b.p16 = 1; b.p_scale = (float)N; b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
     b.round_tf32 = h->rnd;
     CK(attn_lin_call(h, b, st));
+    h->vals[o.x].ginit = true;
+    return PB_OK;
+  }
+  if (o.cross && use_fused_cross(h, o)) {
+    // Qbar = scale * [P o (Obar V^T - delta_row)] K,  delta = rowsum(Obar o O); no Kbar / Vbar (text constants)
+    float* delta = h->WP(h->w_delta);
+    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));
+    PbAttnLin a{};
+    a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
+    a.seg[0].A = gO; a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
+    a.seg[0].B = V; a.seg[0].ldb = ldkv; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.alpha1 = 1.f; a.alpha2 = o.scale;
+    a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
+    a.delta = delta; a.delta_mode = 1;
+    a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
+    a.D = h->T(o.x); a.ldd = C; a.sDb = (long)N * C;
+    a.round_tf32 = h->rnd;
+    CK(attn_lin_call(h, a, st));
     h->vals[o.x].ginit = true;
     return PB_OK;
   }
