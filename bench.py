@@ -34,8 +34,24 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's version banner / debug log goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write banners there (NCCL prints its version line on the first
+# collective whatever NCCL_DEBUG_FILE says), so the process-level stdout is pointed at stderr and the JSON line goes out
+# through a saved copy of the original descriptor.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
+
 
 # name: (model config, op, block_idx, k, iterations, F_tan GF, primal GF)
 WORKLOADS = {
@@ -156,7 +172,7 @@ def run_reference(args, wl):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, wl):
@@ -333,7 +349,7 @@ def run_ours(args, wl):
             line["cpu_baseline"] = {"value": 1.0 / sec_iter, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"1 of {iters} subspace iterations at rank {k_s} on the full {model_name} {op}-{bi} problem "
                                               f"(oracle port of utils.py:722-816, torch-cpu fp32, {sec_iter:.1f} s)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -349,6 +365,7 @@ def main():
     ap.add_argument("--shard", default="problem", choices=["problem", "tangent"],
                     help="N > 1: independent problems per rank (default, weak scaling) or the k columns of each problem split over the ranks")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
         run_reference(args, args.workload)
