@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <algorithm>
@@ -569,7 +570,7 @@ static const char* launch_bn(int BN, const Params& p, int grid, cudaStream_t st)
 
 // tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic), split policy (0 off, 1 heuristic,
 // >1 forced split count), allow BN = 160
-static int g_force_bn = 0, g_split = 1, g_use160 = 1, g_split_min_kb = 48;
+static int g_force_bn = 0, g_split = 1, g_use160 = 1, g_split_min_kb = 24;
 extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int split, int use160) {
   g_force_bn = force_bn; g_split = split; g_use160 = use160;
 }
@@ -696,7 +697,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   // tiles of the last, partial wave are cut along K so that the wave fills the machine (see the header comment); only
   // when the K loop is deep enough for the saving to outweigh the reduction pass
   long full = tiles, tail = 0;
-  if (g_split && g.ws && ktot >= g_split_min_kb) {
+  static const int env_min_kb = getenv("PB_SPLIT_MIN_KB") ? atoi(getenv("PB_SPLIT_MIN_KB")) : 0;     // A/B switch
+  if (g_split && g.ws && ktot >= (env_min_kb ? env_min_kb : g_split_min_kb)) {
     tail = tiles % nsm;
     // split count of the tail wave: minimise (rounds the tail items need) x (k-blocks per item); a tail of 80 tiles is
     // better cut in 5 (3 rounds of 1/5) than run whole on 80 of the 148 SMs

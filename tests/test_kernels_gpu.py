@@ -272,6 +272,38 @@ def test_groupnorm_fwd_and_lin():
         assert rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("nb,HW,Cc,G", [(5, 4096, 320, 32), (5, 64, 1280, 32), (2, 1024, 160, 32), (3, 256, 96, 32), (1, 4096, 128, 32),
+                                       (2, 65536, 128, 32)])
+def test_groupnorm_lin_both_paths(nb, HW, Cc, G):
+    """pbk_gn_lin through the one-launch group kernel (4 / 2 / 1 channels per access: cpg 40, 10, 5, 3) and through the chunked
+    three-launch path (few (image, group) pairs on a large tensor), fp32 / accumulate / fp16 outputs, against torch autograd."""
+    torch.manual_seed(5)
+    x = torch.randn(1, HW, Cc, device="cuda") * 1.5 + 0.3
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    mean, rstd = torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
+    nfl = N.raw().pbk_gn_tmp_floats
+    nfl.restype = C.c_size_t
+    tmp = torch.empty(max(nfl(HW, Cc, G, nb), nfl(HW, Cc, G, 1)), device="cuda")
+    _ok(N.leaf("pbk_gn_stats")(_p(x), 1, HW, Cc, G, C.c_float(1e-5), _p(mean), _p(rstd), _p(tmp), _st()))
+    f = lambda z: F.silu(F.group_norm(z.permute(0, 2, 1), G, gamma, beta, 1e-5).permute(0, 2, 1))
+    t = torch.randn(nb, HW, Cc, device="cuda")
+    for mode in (0, 1):
+        if mode == 0:
+            ref = torch.cat([torch.func.jvp(f, (x,), (t[i:i + 1],))[1] for i in range(nb)])
+        else:
+            ref = torch.cat([torch.func.vjp(f, x)[1](t[i:i + 1])[0] for i in range(nb)])
+        prev = torch.randn_like(t)
+        out = prev.clone()
+        _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, 1, _p(t), nb, mode, _p(out),
+                                 C.c_float(1.0), 0, _p(tmp), _st()))
+        assert rel(out, ref + prev) < 3e-5
+        if Cc % 8 == 0:
+            o16 = torch.zeros(nb, HW, Cc, device="cuda", dtype=torch.float16)
+            _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, 1, _p(t), nb, mode, _p(o16),
+                                     C.c_float(0), 2, _p(tmp), _st()))
+            assert rel(o16.float(), ref) < 1e-3
+
+
 def test_layernorm_geglu_softmax():
     torch.manual_seed(4)
     nb, rows, Cc = 3, 200, 320
