@@ -121,7 +121,9 @@ struct pb_handle {
   std::vector<Probe> probes;
 
   float* P(int v) const { return reinterpret_cast<float*>(cache + vals[v].p_off); }
-  float* T(int v) const { return reinterpret_cast<float*>(work + vals[v].t_off); }
+  // VJP only: cotangent buffer of val v may be another val's buffer handed over without a copy (residual fan-in, run_gemm_bwd)
+  std::vector<int> alias;
+  float* T(int v) const { return reinterpret_cast<float*>(work + vals[alias.empty() ? v : alias[v]].t_off); }
   float* CP(size_t off) const { return reinterpret_cast<float*>(cache + off); }
   float* WP(size_t off) const { return reinterpret_cast<float*>(work + off); }
   float* Wf(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].fwd_off); }
@@ -527,7 +529,13 @@ int run_gemm_bwd(pb_handle* h, const Op& o, int nb, pb_stream st) {
   vx.ginit = true;
   if (o.res >= 0) {
     Val& vr = h->vals[o.res];
-    CK(pbk_copy2d(h->T(o.res), vr.C, h->T(o.y), vy.C, vy.rows * nb, vy.C, vr.ginit ? 1.f : 0.f, h->rnd, st));
+    if (!vr.ginit && !o.a16_vjp) {
+      // first contribution to the residual input: y's cotangent buffer is dead after this op, so it BECOMES the residual's
+      // cotangent buffer (later contributions accumulate into it in place) instead of being copied
+      h->alias[o.res] = h->alias[o.y];
+    } else {
+      CK(pbk_copy2d(h->T(o.res), vr.C, h->T(o.y), vy.C, vy.rows * nb, vy.C, vr.ginit ? 1.f : 0.f, h->rnd, st));
+    }
     vr.ginit = true;
   }
   return PB_OK;
@@ -910,6 +918,9 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
 int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
   h->rnd = h->rnd_t;
   for (Val& v : h->vals) v.ginit = false;
+  h->alias.resize(h->vals.size());
+  for (size_t i = 0; i < h->alias.size(); ++i) h->alias[i] = (int)i;
+  struct Unalias { pb_handle* h; ~Unalias() { h->alias.clear(); } } unalias{h};       // the JVP / primal see every val's own buffer
   for (size_t i = h->ops.size(); i-- > 0;) {
     const Op& o = h->ops[i];
     if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
