@@ -98,7 +98,7 @@ struct Ring {
   __device__ __forceinline__ void next2(int n) { idx += 2; if (idx >= n) { idx -= n; ph ^= 1u; } }   // n >= 2
 };
 
-// smem: [A resident][B ring][C1 ring][C2 ring][P/T ring][rsum 2 x 128 floats][barriers]
+// smem: [A resident][B ring][C1 ring][C2 ring][P/T ring][rsum 2 x 128 floats][column deltas 8 x 64 floats][barriers]
 // Template parameters fix the contraction shape so that the single-warp issue loops unroll into straight-line code
 // (NSEG segments, KFULL full k-blocks, NTAIL tail k-steps of 8 floats, C2M: 0 no second product, 1 folded into Acc,
 // 2 separate accumulator); NSEG < 0 is the generic kernel that reads the shape from Params.
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   uint8_t* sC2 = sC + NC1 * p.c_tile_bytes;
   uint8_t* sPT = sC2 + (has_c2 ? NB * p.c_tile_bytes : 0);
   float* s_rsum = reinterpret_cast<float*>(sPT + NPT * PT_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rsum + 2 * TM);
+  float* s_dcol = s_rsum + 2 * TM;                       // [8 compute warps][64]: the step's column deltas (delta_mode 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dcol + 8 * 64);
   uint64_t* a_full = bars + 0;
   uint64_t* acc_full = bars + 1;
   uint64_t* b_full = bars + 2;                 // [MAX_NB]
@@ -377,6 +378,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(tb + ((uint32_t(i) ^ swz) << 4)) = tv[i];
       } else {
         // 64 columns per step: the row is 8 chunks of 8 halves (scaled probabilities), T goes back as halves
+        float* sd = s_dcol + (warp - 2) * 64;
+        if (p.delta_mode == 2) {                                 // one coalesced load per warp, read back as broadcasts
+          const int c0 = cbase + lane, c1 = c0 + 32;
+          sd[lane] = c0 < p.Nc ? __ldg(dbase + c0) : 0.f;
+          sd[32 + lane] = c1 < p.Nc ? __ldg(dbase + c1) : 0.f;
+          __syncwarp();
+        }
         mbar_wait(&p_full[st], ph);
         uint4 pv[8];
 #pragma unroll
@@ -398,15 +406,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
             const int ci = hv * 4 + i;
             const __half2* ph2 = reinterpret_cast<const __half2*>(&pv[ci]);
             __half2 oh[4];
+            float dl[8];
+            if (p.delta_mode == 2) {
+              const float4 da = *reinterpret_cast<const float4*>(sd + ci * 8), db = *reinterpret_cast<const float4*>(sd + ci * 8 + 4);
+              dl[0] = da.x; dl[1] = da.y; dl[2] = da.z; dl[3] = da.w; dl[4] = db.x; dl[5] = db.y; dl[6] = db.z; dl[7] = db.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) dl[e] = drow;
+            }
 #pragma unroll
             for (int e2 = 0; e2 < 4; ++e2) {
               const float2 pf = __half22float2(ph2[e2]);
-              const int col = ci * 8 + e2 * 2;
-              float d0 = drow, d1 = drow;
-              if (p.delta_mode == 2) {
-                d0 = (cbase + col < p.Nc) ? __ldg(dbase + cbase + col) : 0.f;
-                d1 = (cbase + col + 1 < p.Nc) ? __ldg(dbase + cbase + col + 1) : 0.f;
-              }
+              const float d0 = dl[e2 * 2], d1 = dl[e2 * 2 + 1];
               const float t0 = pf.x * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2]) - d0);
               const float t1 = pf.y * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2 + 1]) - d1);
               oh[e2] = __floats2half2_rn(t0, t1);
@@ -562,7 +573,7 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   }
   // ring depths from the shared-memory budget: B and C2 rings of 3 stages, C1 ring of 5 (4 when tight), every remaining
   // 16 KB goes to the in-place P/T ring; big head dims (80: SD-1.x 32x32 layers) fall back to 2 / 3 stages
-  const int budget = 227 * 1024 - 1024 - (2 * TM * 4 + 1024);
+  const int budget = 227 * 1024 - 1024 - (2 * TM * 4 + 8 * 64 * 4 + 1024);
   int nbst = MAX_NB, nc1 = 5, npt = 0;
   auto fit = [&]() {
     const int fixed = p.nseg * p.a_seg_bytes + nbst * p.b_stage_bytes + (p.has_c2 ? nbst * p.c_tile_bytes : 0);
@@ -575,7 +586,7 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (npt < LAG + 1) return "attn_lin: shared memory budget exceeded";
   p.nb_st = nbst;
   p.nc1_st = nc1; p.npt_st = npt;
-  const int smem = used + npt * PT_BYTES + 2 * TM * 4 + 1024 + 1024;
+  const int smem = used + npt * PT_BYTES + 2 * TM * 4 + 8 * 64 * 4 + 1024 + 1024;
   if (smem > 227 * 1024) return "attn_lin: shared memory budget exceeded";
   dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
   const int c2m = a.C2 ? (a.D2 ? 2 : 1) : 0;
