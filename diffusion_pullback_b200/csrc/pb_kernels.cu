@@ -5,6 +5,7 @@
 // grids sized to cover 148 SMs, reductions by warp shuffles.  See pb_kernels.h for semantics.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -460,14 +461,19 @@ __global__ void gn_finalize_lin_k(const float* __restrict__ part, int chunks, in
 // (pass 2, the same bytes again from L2).  Replaces partial sums + finalize + apply (three launches and a round trip
 // of per-chunk partials) whenever there are enough (image, group) pairs to fill the machine.  Threads are laid out
 // [pixel lane][channel vector] so that no index needs a division inside the loops; V = 4 / 2 / 1 channels per access.
-template <int MODE, int V>
-__global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ xp, const float* __restrict__ mean,
-                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta_, int HW, int C, int G, int silu,
-                                                      const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
+// SPLIT > 1: the pixels of one (image, group) pair are shared by a cluster of SPLIT blocks (grid.z) that exchange their
+// partial sums through distributed shared memory in rank order (deterministic), for the layers with many pixels per group.
+template <int MODE, int V, int SPLIT>
+__device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, const float* __restrict__ mean,
+                                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                                                  const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
   __shared__ double sh[2][16];
+  __shared__ double s_part[2];
   __shared__ float s_m[2];
   const int g = blockIdx.x, b = blockIdx.y;
+  const int pix_lo = SPLIT > 1 ? int(blockIdx.z) * (HW / SPLIT) : 0;
+  const int pix_hi = SPLIT > 1 ? pix_lo + HW / SPLIT : HW;
   const int cpg = C / G, cv = cpg / V;
   const int rows = blockDim.x / cv;                      // pixel lanes
   const int tid = threadIdx.x;
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ 
   };
   float s1 = 0.f, s2 = 0.f;
   if (active)
-    for (int p = p0; p < HW; p += rows) {
+    for (int p = pix_lo + p0; p < pix_hi; p += rows) {
       float xv[V], tv[V];
       load(xg, p, xv); load(tg, p, tv);
 #pragma unroll
@@ -506,13 +512,33 @@ __global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ 
   if (tid == 0) {
     double a = 0, c = 0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
-    const double n = (double)HW * cpg;
-    s_m[0] = (float)(a / n); s_m[1] = (float)(c / n);
+    s_part[0] = a; s_part[1] = c;
   }
-  __syncthreads();
+  if constexpr (SPLIT > 1) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                        // every block's partial is in its shared memory
+    if (tid == 0) {
+      double a = 0, c = 0;
+      for (int r = 0; r < SPLIT; ++r) {
+        const double* rp = cluster.map_shared_rank(s_part, r);
+        a += rp[0]; c += rp[1];
+      }
+      const double n = (double)HW * cpg;
+      s_m[0] = (float)(a / n); s_m[1] = (float)(c / n);
+    }
+    cluster.sync();                                        // nobody leaves (or reuses s_part) while a peer may still read it
+  } else {
+    __syncthreads();
+    if (tid == 0) {
+      const double n = (double)HW * cpg;
+      s_m[0] = (float)(s_part[0] / n); s_m[1] = (float)(s_part[1] / n);
+    }
+    __syncthreads();
+  }
   const float m1 = s_m[0], m2 = s_m[1];
   if (!active) return;
-  for (int p = p0; p < HW; p += rows) {
+  for (int p = pix_lo + p0; p < pix_hi; p += rows) {
     float xv[V], tv[V], o[V];
     load(xg, p, xv); load(tg, p, tv);
 #pragma unroll
@@ -546,6 +572,22 @@ __global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ 
       else op[0] = o[0];
     }
   }
+}
+
+template <int MODE, int V>
+__global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                                                      const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
+  gn_lin_group_body<MODE, V, 1>(xp, mean, rstd, gamma, beta_, HW, C, G, silu, t, out, acc, rnd);
+}
+constexpr int GN_SPLIT = 4;
+template <int MODE, int V>
+__global__ void __cluster_dims__(1, 1, GN_SPLIT) __launch_bounds__(512)
+gn_lin_group_cluster_k(const float* __restrict__ xp, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ gamma, const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                       const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
+  gn_lin_group_body<MODE, V, GN_SPLIT>(xp, mean, rstd, gamma, beta_, HW, C, G, silu, t, out, acc, rnd);
 }
 
 __global__ void gn_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
@@ -821,23 +863,24 @@ __global__ void softmax_lin_k(const float* __restrict__ P, long rows_p, float* _
   }
 }
 
+// thread per (tangent, row, head): heads are contiguous along a row, so a warp reads whole rows with 128-bit loads
 __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float* __restrict__ o, long ldo, int nb,
                              int N, int H, int d, float* __restrict__ delta) {
-  const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
-  const long total = (long)nb * H * N;
-  for (long w = warp; w < total; w += nw) {
+  const long total = (long)nb * N * H;
+  const int d4 = d / 4;
+  for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
     long t = w;
-    const int i = int(t % N); t /= N;
     const int h = int(t % H); t /= H;
+    const int i = int(t % N); t /= N;
     const int b = int(t);
-    const float* g = go + ((long)b * N + i) * ldg + h * d;
-    const float* oo = o + (long)i * ldo + h * d;
+    const float4* g = reinterpret_cast<const float4*>(go + ((long)b * N + i) * ldg + h * d);
+    const float4* oo = reinterpret_cast<const float4*>(o + (long)i * ldo + h * d);
     float s = 0.f;
-    for (int c = lane; c < d; c += 32) s = fmaf(g[c], oo[c], s);
-    s = warp_sum(s);
-    if (lane == 0) delta[w] = s;
+    for (int c = 0; c < d4; ++c) {
+      const float4 a = g[c], q = oo[c];
+      s = fmaf(a.x, q.x, fmaf(a.y, q.y, fmaf(a.z, q.z, fmaf(a.w, q.w, s))));
+    }
+    delta[((long)b * H + h) * N + i] = s;
   }
 }
 __global__ void attn_ds_k(const float* __restrict__ P, float* __restrict__ dP, const float* __restrict__ delta,
@@ -1243,9 +1286,14 @@ PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const floa
     const long pairs = (long)G * nb;
     const int V = cpg % 4 == 0 ? 4 : cpg % 2 == 0 ? 2 : 1;
     if ((pairs >= 120 || (long)nb * HW * C <= (1L << 20)) && cpg / V <= 256) {
-      dim3 grid(G, nb);
+      const bool split = HW >= 1024 && HW % GN_SPLIT == 0;          // many pixels per group: a cluster of blocks per pair
+      dim3 grid(G, nb, split ? GN_SPLIT : 1);
       const int block = 512;
-#define PB_GN_GROUP(M_, V_) gn_lin_group_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32)
+#define PB_GN_GROUP(M_, V_)                                                                                                   \
+  do {                                                                                                                        \
+    if (split) gn_lin_group_cluster_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32); \
+    else gn_lin_group_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32);             \
+  } while (0)
       if (mode == 0) { if (V == 4) PB_GN_GROUP(0, 4); else if (V == 2) PB_GN_GROUP(0, 2); else PB_GN_GROUP(0, 1); }
       else { if (V == 4) PB_GN_GROUP(1, 4); else if (V == 2) PB_GN_GROUP(1, 2); else PB_GN_GROUP(1, 1); }
 #undef PB_GN_GROUP
@@ -1323,7 +1371,9 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
                    pb_stream st) {
   const long total = (long)nb * H * N;
-  attn_delta_k<<<grid_for(total * 32, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta);
+  if (d % 4 || ldg % 4 || ldo % 4 || ((reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(o)) & 15))
+    return "attn_delta: head dim and leading dimensions must be multiples of 4 with 16-byte aligned bases";
+  attn_delta_k<<<grid_for(total, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta);
   return last_err();
 }
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,

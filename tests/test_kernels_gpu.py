@@ -304,6 +304,18 @@ def test_groupnorm_lin_both_paths(nb, HW, Cc, G):
             assert rel(o16.float(), ref) < 1e-3
 
 
+def test_attn_delta():
+    """delta[b][h][i] = sum_c go[b][i][h d + c] o[i][h d + c] (the row term of the softmax cotangent)."""
+    torch.manual_seed(8)
+    for nb, Ntok, H, d in ((5, 4096, 8, 40), (2, 100, 3, 12), (1, 64, 1, 512)):
+        Cc = H * d
+        go, o = torch.randn(nb, Ntok, Cc, device="cuda"), torch.randn(Ntok, Cc, device="cuda")
+        delta = torch.empty(nb, H, Ntok, device="cuda")
+        _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Cc), _p(o), C.c_long(Cc), nb, Ntok, H, d, _p(delta), _st()))
+        ref = (go.double() * o.double()[None]).view(nb, Ntok, H, d).sum(-1).permute(0, 2, 1)
+        assert rel(delta, ref) < 1e-5
+
+
 def test_layernorm_geglu_softmax():
     torch.manual_seed(4)
     nb, rows, Cc = 3, 200, 320
