@@ -1,18 +1,20 @@
-// tcgen05 / TMA TF32 GEMM for sm_100a: the contraction engine behind every conv / linear /
-// attention product of the pullback hot path (primal, JVP and VJP passes).
+// tcgen05 / TMA GEMM (TF32 or fp16 operands, fp32 accumulation) for sm_100a: the contraction engine behind every
+// conv / linear / attention product of the pullback hot path (primal, JVP and VJP passes).
 //
 // Persistent kernel, one CTA per SM, each CTA walks a static list of work items (128 x BN output tile, K split):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 4D, 128B-swizzled K-major tiles, OOB zero fill
 //                 supplies conv padding, K/M/N tails and attention-head tails)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, fp32 accumulators in TMEM,
-//                 two accumulator stages so the epilogue of item i overlaps the main loop of item i + 1)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (the whole warp walks the loop, one elected lane issues; kind::tf32
+//                 or kind::f16, fp32 accumulators in TMEM, two accumulator stages so the epilogue of item i overlaps the
+//                 main loop of item i + 1)
 //   warps 2..5  : epilogue: tcgen05.ld 32x32b -> alpha / bias / residual / RNA rounding -> 128B-swizzled smem staging
 //                 -> TMA tensor store (the residual tile arrives by TMA into the same staging buffer, 3 chunks ahead)
 // smem: STAGES x (A 16 KB + B BN*128 B) operand ring with full/empty mbarriers (MMA completion by tcgen05.commit)
 // + 4 x 16 KB staging buffers.
 // Scheduling: output tiles are dealt round-robin to the CTAs.  The tiles of the last, partial wave (all tiles when there
 // are fewer tiles than SMs: small-M weight-streaming layers) are cut along K into `splits` items each so that the wave
-// fills the machine; such items store their raw partial tile to scratch through the same TMA epilogue and
+// fills the machine (split count from a small cost model: rounds x k-blocks + reduce); such items store their raw partial
+// tile to scratch through the same TMA epilogue and
 // splitk_reduce_k sums the partials in split order (deterministic) and applies alpha / bias / residual / rounding.
 // Operand / output types (template parameters): fp32 operands run as kind::tf32 (32-element k-blocks), fp16 operands as
 // kind::f16 (64-element k-blocks, half the L2->smem bytes per flop); accumulation is fp32 in TMEM either way and the
