@@ -418,8 +418,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
             for (int e2 = 0; e2 < 4; ++e2) {
               const float2 pf = __half22float2(ph2[e2]);
               const float d0 = dl[e2 * 2], d1 = dl[e2 * 2 + 1];
-              const float t0 = pf.x * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2]) - d0);
-              const float t1 = pf.y * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2 + 1]) - d1);
+              float t0 = pf.x * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2]) - d0);
+              float t1 = pf.y * (p.alpha1 * __uint_as_float(sv[i * 8 + e2 * 2 + 1]) - d1);
+              t0 = fminf(fmaxf(t0, -65504.f), 65504.f);         // saturate instead of producing inf
+              t1 = fminf(fmaxf(t1, -65504.f), 65504.f);
               oh[e2] = __floats2half2_rn(t0, t1);
               const float2 back = __half22float2(oh[e2]);        // the row sum of what the tensor core will see
               rsum += back.x + back.y;

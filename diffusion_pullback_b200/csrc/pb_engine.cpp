@@ -135,6 +135,8 @@ struct pb_handle {
 
 namespace {
 
+float attn_pscale(int n);
+
 int fail(pb_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
@@ -571,9 +573,9 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
     CK(pbk_transpose(h->CP(o.Qt_off), o.ldq, 0, (long)d * o.ldq, Q, ldq_, 0, d, 1, hd, N, d, 0.f, h->rnd, st));
     CK(pbk_transpose(h->CP(o.Pt_off), o.ldq, 0, (long)Nk * o.ldq, P, ldk, 0, (long)N * ldk, 1, hd, N, Nk, 0.f, h->rnd, st));
     if (o.p16) {
-      // probabilities scaled by the row length sit around 1: fp16's normal range (softmax rows of 4096 are ~2e-4 unscaled)
-      CK(pbk_to_f16_scaled(h->CP(o.P16_off), P, (size_t)hd * N * ldk, (float)Nk, st));
-      CK(pbk_to_f16_scaled(h->CP(o.Pt16_off), h->CP(o.Pt_off), (size_t)hd * Nk * o.ldq, (float)N, st));
+      // scaled fp16 copies of P and P^T (attn_pscale) and plain fp16 copies of the transposed primal operands
+      CK(pbk_to_f16_scaled(h->CP(o.P16_off), P, (size_t)hd * N * ldk, attn_pscale(Nk), st));
+      CK(pbk_to_f16_scaled(h->CP(o.Pt16_off), h->CP(o.Pt_off), (size_t)hd * Nk * o.ldq, attn_pscale(N), st));
       CK(pbk_to_f16(h->CP(o.Vt16_off), Vt, (size_t)C * ldk, st));
       CK(pbk_to_f16(h->CP(o.Kt16_off), Kt, (size_t)C * ldk, st));
       CK(pbk_to_f16(h->CP(o.Qt16_off), h->CP(o.Qt_off), (size_t)C * o.ldq, st));
@@ -586,6 +588,12 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   }
   return PB_OK;
 }
+
+// Scale of the fp16 probability copies: sqrt(row length), rounded to a power of two.  Unscaled, a near-uniform row of 4096
+// entries (2.4e-4 each) puts T = P o (S - delta) into fp16's subnormal range; scaled by the full row length, a peaked row
+// (P -> 1) would overflow for |S - delta| > 16.  sqrt(N) keeps uniform rows normal down to |S| ~ 4e-3 and peaked rows finite up
+// to |S| ~ 1e3; the kernel divides the products by the same factor and saturates T at the fp16 maximum.
+float attn_pscale(int n) { return std::exp2(std::floor(0.5f * std::log2((float)std::max(n, 1)) + 0.5f)); }
 
 bool use_fused(const pb_handle* h, const Op& o) {
   return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
@@ -619,7 +627,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.C2 = dVt; a.ldc2 = ldk; a.sC2h = (long)d * ldk; a.sC2b = (long)C * ldk;
-    if (p16) { a.p16 = 1; a.p_scale = (float)Nk; a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
+    if (p16) { a.p16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
@@ -695,7 +703,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.delta = delta; a.delta_mode = 1;
     a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
     const bool p16 = o.p16 && h->use_f16();
-    if (p16) { a.p16 = 1; a.p_scale = (float)Nk; a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Kt16_off); }
+    if (p16) { a.p16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Kt16_off); }
     a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
@@ -712,7 +720,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
     b.C2 = gOt; b.ldc2 = ldq; b.sC2h = (long)d * ldq; b.sC2b = (long)C * ldq;
     b.D2 = gx + 2 * C; b.ldd2 = 3 * C; b.sD2b = (long)N * 3 * C;
-    if (p16) { b.p16 = 1; b.p_scale = (float)N; b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
+    if (p16) { b.p16 = 1; b.p_scale = attn_pscale(N); b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
     b.round_tf32 = h->rnd;
     CK(attn_lin_call(h, b, st));
     h->vals[o.x].ginit = true;
