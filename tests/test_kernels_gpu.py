@@ -494,6 +494,38 @@ def test_attn_lin_fused_fp16_operands(Mr, Nc, d, nb, nh, nseg, mode, c2):
     assert rel(D, ref) < 3e-4, rel(D, ref)                             # a few T elements round the other way (fp32 vs fp64 S)
 
 
+def test_attn_lin_fp16_range_peaked_and_uniform_rows():
+    """fp16 probability path at the two ends of the range: near one-hot rows with large scores (trained attention) and uniform rows
+    with tiny scores, p_scale = sqrt(Nc) as the engine chooses it: finite and accurate."""
+    torch.manual_seed(9)
+    Mr = Nc = 1024; d = 40; nb = 2; nh = 2; Cc = nh * d
+    for sharp, amp in ((40.0, 30.0), (0.0, 1e-2)):
+        A0 = torch.randn(nb, Mr, Cc, device="cuda") * amp; B0 = torch.randn(Nc, Cc, device="cuda")
+        Pm = torch.softmax(torch.randn(nh, Mr, Nc, device="cuda") * sharp, -1).contiguous()
+        ps = 2.0 ** round(math.log2(math.sqrt(Nc)))
+        P16 = (Pm * ps).half().contiguous()
+        C1 = torch.randn(nh, d, Nc, device="cuda").half()
+        O = torch.randn(Mr, Cc, device="cuda")
+        D = torch.zeros(nb, Mr, Cc, device="cuda")
+        a = N.PbAttnLin()
+        a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, nb, nh, 1
+        s0 = a.seg[0]
+        s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = A0.data_ptr(), Cc, Mr * Cc, d, B0.data_ptr(), Cc, 0, d
+        a.alpha1, a.alpha2, a.beta = d ** -0.5, 1.0, 0.0
+        a.Pm, a.ldp, a.sPh = P16.data_ptr(), Nc, Mr * Nc
+        a.want_rsum, a.O, a.ldo = 1, O.data_ptr(), Cc
+        a.C1, a.ldc, a.sCh = C1.data_ptr(), Nc, d * Nc
+        a.D, a.ldd, a.sDb, a.round_tf32 = D.data_ptr(), Cc, Mr * Cc, 0
+        a.p16, a.p_scale = 1, ps
+        _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+        assert torch.isfinite(D).all()
+        S = torch.einsum("bihd,jhd->bhij", tf32_trunc(A0).double().view(nb, Mr, nh, d), tf32_trunc(B0).double().view(Nc, nh, d)) * d ** -0.5
+        T = Pm.double()[None] * S
+        ref = torch.einsum("bhij,hnj->bihn", T, C1.double()).reshape(nb, Mr, Cc)
+        ref = ref - (T.sum(-1).permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
+        assert rel(D, ref) < 2e-3, (sharp, amp, rel(D, ref))
+
+
 def test_orthonormalize_matches_svd():
     torch.manual_seed(6)
     for k, n in ((5, 16384), (16, 16384), (2, 196608), (50, 4096)):
