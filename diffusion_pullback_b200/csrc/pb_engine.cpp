@@ -66,6 +66,7 @@ struct Op {
   int conv = 0;                     // OP_GEMM: 1 = 3x3 / s1 / p1 implicit GEMM
   int a16_jvp = 0;                  // OP_GEMM: the JVP reads its A operand (tangent of x) as fp16
   int a16_vjp = 0;                  // OP_GEMM: the VJP reads its A operand (cotangent of y) as fp16: 1 stored so, 2 converted first
+  int d16_jvp = 0;                  // OP_GEMM: the JVP writes its output as fp16 (sole consumer: GEGLU, which reads halves)
   int pad_lo = 0, Ho = 0, Wo = 0;   // OP_IM2COL
   // OP_ATTN
   int heads = 0, d = 0, cross = 0, Nq = 0, Nk = 0, ldk = 0, ldq = 0, kv = -1;
@@ -136,6 +137,7 @@ struct pb_handle {
 namespace {
 
 float attn_pscale(int n);
+bool geglu_in16(const pb_handle* h, const Op& o);
 
 int fail(pb_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -444,6 +446,9 @@ void analyse_f16(pb_handle* h) {
     if ((mask & (o.conv ? 1 : 2)) && consumers[o.x] == 1 && producer[o.x] >= 0 && elementwise(h->ops[producer[o.x]].kind, false)) {
       o.a16_jvp = 1; h->vals[o.x].t16 = true;
     }
+    if (o.a16_jvp && (mask & 2) && !o.conv && o.res < 0 && consumers[o.y] == 1)
+      for (const Op& c : h->ops)
+        if (c.kind == OP_GEGLU && c.x == o.y) o.d16_jvp = 1;    // ff1 -> GEGLU: the widest tensor of a transformer block
     if ((mask & 4) && o.res < 0 && consumers[o.y] == 1) {
       for (const Op& c : h->ops)
         if (c.x == o.y && elementwise(c.kind, true)) { o.a16_vjp = 1; h->vals[o.y].g16 = true; }
@@ -509,6 +514,7 @@ int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
   g.round_tf32 = h->rnd;
   g.precise = primal ? h->prec_p : h->prec_t;
   if (!primal && o.a16_jvp) { g.seg[0].B = h->Wf16(o.w); g.ab_dtype = PB_GEMM_F16; }    // A holds halves (Val::t16)
+  if (!primal && o.d16_jvp) g.d_dtype = PB_GEMM_F16;
   CK(gemm_call(h, g, st));
   return PB_OK;
 }
@@ -594,6 +600,13 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
 // (P -> 1) would overflow for |S - delta| > 16.  sqrt(N) keeps uniform rows normal down to |S| ~ 4e-3 and peaked rows finite up
 // to |S| ~ 1e3; the kernel divides the products by the same factor and saturates T at the fp16 maximum.
 float attn_pscale(int n) { return std::exp2(std::floor(0.5f * std::log2((float)std::max(n, 1)) + 0.5f)); }
+
+// the GEGLU input tangent was written as halves by its producer GEMM (Op::d16_jvp)
+bool geglu_in16(const pb_handle* h, const Op& o) {
+  for (const Op& g : h->ops)
+    if (g.kind == OP_GEMM && g.y == o.x) return g.d16_jvp != 0;
+  return false;
+}
 
 bool use_fused(const pb_handle* h, const Op& o) {
   return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
@@ -908,7 +921,8 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
         CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
         break;
       case OP_GEGLU:
-        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
+        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y),
+                         (h->vals[o.y].t16 ? 2 : h->rnd) | (geglu_in16(h, o) ? 4 : 0), st));
         break;
       case OP_ATTN:
         if (int e = run_attn_jvp(h, o, nb, st)) return e;

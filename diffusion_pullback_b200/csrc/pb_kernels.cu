@@ -493,7 +493,8 @@ __device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, 
   };
   float s1 = 0.f, s2 = 0.f;
   if (active)
-    for (int p = pix_lo + p0; p < pix_hi; p += rows) {
+#pragma unroll 4
+    for (int p = pix_lo + p0; p < pix_hi; p += rows) {        // unrolled: four pixels' loads in flight per thread
       float xv[V], tv[V];
       load(xg, p, xv); load(tg, p, tv);
 #pragma unroll
@@ -538,6 +539,7 @@ __device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, 
   }
   const float m1 = s_m[0], m2 = s_m[1];
   if (!active) return;
+#pragma unroll 4
   for (int p = pix_lo + p0; p < pix_hi; p += rows) {
     float xv[V], tv[V], o[V];
     load(xg, p, xv); load(tg, p, tv);
@@ -729,6 +731,8 @@ __global__ void geglu_fwd_k(const float* __restrict__ h, long rows, int F, float
     *reinterpret_cast<float4*>(y + r * F + c) = maybe_round4(o, rnd);
   }
 }
+// IN16: the tangent dh holds halves (written by an fp16-output GEMM); rnd 2: dy is stored as halves
+template <bool IN16>
 __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ dh, long rows, int F,
                             float* __restrict__ dy, int rnd) {
   const int F4 = F / 4;
@@ -738,8 +742,17 @@ __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const flo
     const long rp = r % rows_p;
     const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
     const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
-    const float4 da = *reinterpret_cast<const float4*>(dh + r * 2 * F + c);
-    const float4 dg = *reinterpret_cast<const float4*>(dh + r * 2 * F + F + c);
+    float4 da, dg;
+    if constexpr (IN16) {
+      const __half* dhh = reinterpret_cast<const __half*>(dh);
+      const uint2 ua = *reinterpret_cast<const uint2*>(dhh + r * 2 * F + c), ug = *reinterpret_cast<const uint2*>(dhh + r * 2 * F + F + c);
+      const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&ua.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&ua.y));
+      const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&ug.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&ug.y));
+      da = make_float4(a0.x, a0.y, a1.x, a1.y); dg = make_float4(g0.x, g0.y, g1.x, g1.y);
+    } else {
+      da = *reinterpret_cast<const float4*>(dh + r * 2 * F + c);
+      dg = *reinterpret_cast<const float4*>(dh + r * 2 * F + F + c);
+    }
     float4 o = make_float4(da.x * gelu_f(g.x) + a.x * gelu_d(g.x) * dg.x, da.y * gelu_f(g.y) + a.y * gelu_d(g.y) * dg.y,
                            da.z * gelu_f(g.z) + a.z * gelu_d(g.z) * dg.z, da.w * gelu_f(g.w) + a.w * gelu_d(g.w) * dg.w);
     store_out4(dy, r * F + c, o, rnd);
@@ -1343,7 +1356,9 @@ PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, 
                   pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
-  geglu_jvp_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32);
+  // round_tf32 bit 2 (value 4): the tangent input dh holds halves
+  if (round_tf32 & 4) geglu_jvp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & 3);
+  else geglu_jvp_k<false><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32);
   return last_err();
 }
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,

@@ -89,6 +89,7 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 
 // ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
 PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st);
+// round_tf32 + 4: the tangent input dh holds halves (it was written by an fp16-output GEMM)
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
                   pb_stream st);
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
