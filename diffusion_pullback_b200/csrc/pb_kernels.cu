@@ -486,17 +486,21 @@ __device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, 
   float ga[V], be[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) { ga[k] = gamma[g * cpg + j + k]; be[k] = beta_[g * cpg + j + k]; }
-  auto load = [&](const float* base, long p, float (&v)[V]) {
-    if constexpr (V == 4) { const float4 q = *reinterpret_cast<const float4*>(base + p * C); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-    else if constexpr (V == 2) { const float2 q = *reinterpret_cast<const float2*>(base + p * C); v[0] = q.x; v[1] = q.y; }
-    else v[0] = base[p * C];
+  auto load = [&](const float* q_, float (&v)[V]) {
+    if constexpr (V == 4) { const float4 q = *reinterpret_cast<const float4*>(q_); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else if constexpr (V == 2) { const float2 q = *reinterpret_cast<const float2*>(q_); v[0] = q.x; v[1] = q.y; }
+    else v[0] = q_[0];
   };
+  const long step = (long)rows * C;                      // pointer increment per loop iteration (no index math inside)
+  const long first = (long)(pix_lo + p0) * C;
   float s1 = 0.f, s2 = 0.f;
-  if (active)
+  if (active) {
+    const float* xq = xg + first;
+    const float* tq = tg + first;
 #pragma unroll 4
-    for (int p = pix_lo + p0; p < pix_hi; p += rows) {        // unrolled: four pixels' loads in flight per thread
+    for (int p = pix_lo + p0; p < pix_hi; p += rows, xq += step, tq += step) {   // unrolled: four pixels' loads in flight
       float xv[V], tv[V];
-      load(xg, p, xv); load(tg, p, tv);
+      load(xq, xv); load(tq, tv);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         const float xh = (xv[k] - mu) * rs;
@@ -505,6 +509,7 @@ __device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, 
         s1 += u; s2 = fmaf(xh, u, s2);
       }
     }
+  }
   double d1 = s1, d2 = s2;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
@@ -539,23 +544,25 @@ __device__ __forceinline__ void gn_lin_group_body(const float* __restrict__ xp, 
   }
   const float m1 = s_m[0], m2 = s_m[1];
   if (!active) return;
+  const float* xq = xg + first;
+  const float* tq = tg + first;
+  float* op = og + first;
+  __half* hp = reinterpret_cast<__half*>(out) + ((long)b * HW * C + g * cpg + j) + first;
 #pragma unroll 4
-  for (int p = pix_lo + p0; p < pix_hi; p += rows) {
+  for (int p = pix_lo + p0; p < pix_hi; p += rows, xq += step, tq += step, op += step, hp += step) {
     float xv[V], tv[V], o[V];
-    load(xg, p, xv); load(tg, p, tv);
+    load(xq, xv); load(tq, tv);
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const float xh = (xv[k] - mu) * rs;
       const float f = silu ? ga[k] * silu_d(fmaf(ga[k], xh, be[k])) : ga[k];
       o[k] = MODE == 0 ? f * rs * (tv[k] - m1 - xh * m2) : rs * (tv[k] * f - m1 - xh * m2);
     }
-    float* op = og + (long)p * C;
     if (acc != 0.f) {
 #pragma unroll
       for (int k = 0; k < V; ++k) o[k] += acc * op[k];
     }
     if (rnd == 2) {
-      __half* hp = reinterpret_cast<__half*>(out) + ((long)b * HW * C + g * cpg + j) + (long)p * C;
       if constexpr (V == 4) {
         uint2 hv;
         *reinterpret_cast<__half2*>(&hv.x) = __floats2half2_rn(o[0], o[1]);
@@ -583,13 +590,12 @@ __global__ void __launch_bounds__(512) gn_lin_group_k(const float* __restrict__ 
                                                       const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
   gn_lin_group_body<MODE, V, 1>(xp, mean, rstd, gamma, beta_, HW, C, G, silu, t, out, acc, rnd);
 }
-constexpr int GN_SPLIT = 4;
-template <int MODE, int V>
-__global__ void __cluster_dims__(1, 1, GN_SPLIT) __launch_bounds__(512)
+template <int MODE, int V, int SPLIT>
+__global__ void __cluster_dims__(1, 1, SPLIT) __launch_bounds__(512)
 gn_lin_group_cluster_k(const float* __restrict__ xp, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta_, int HW, int C, int G, int silu,
                        const float* __restrict__ t, float* __restrict__ out, float acc, int rnd) {
-  gn_lin_group_body<MODE, V, GN_SPLIT>(xp, mean, rstd, gamma, beta_, HW, C, G, silu, t, out, acc, rnd);
+  gn_lin_group_body<MODE, V, SPLIT>(xp, mean, rstd, gamma, beta_, HW, C, G, silu, t, out, acc, rnd);
 }
 
 __global__ void gn_apply_fwd_k(const float* __restrict__ x, const float* __restrict__ mean,
@@ -1299,16 +1305,24 @@ PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const floa
     const long pairs = (long)G * nb;
     const int V = cpg % 4 == 0 ? 4 : cpg % 2 == 0 ? 2 : 1;
     if ((pairs >= 120 || (long)nb * HW * C <= (1L << 20)) && cpg / V <= 256) {
-      const bool split = HW >= 1024 && HW % GN_SPLIT == 0;          // many pixels per group: a cluster of blocks per pair
-      dim3 grid(G, nb, split ? GN_SPLIT : 1);
+      // many pixels per group: a cluster of 2 / 4 / 8 blocks per pair (PB_GN_SPLIT overrides the choice: tuning)
+      static const int env_split = getenv("PB_GN_SPLIT") ? atoi(getenv("PB_GN_SPLIT")) : 0;
+      int nsplit = env_split ? (HW >= 1024 ? env_split : 1) : (HW >= 4096 ? 4 : 1);   // measured: 4096 pixels 48 -> 41 us, 1024 pixels 19 -> 25 us
+      if (nsplit != 2 && nsplit != 4 && nsplit != 8) nsplit = 1;
+      if (HW % nsplit) nsplit = 1;
+      dim3 grid(G, nb, nsplit);
       const int block = 512;
-#define PB_GN_GROUP(M_, V_)                                                                                                   \
-  do {                                                                                                                        \
-    if (split) gn_lin_group_cluster_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32); \
-    else gn_lin_group_k<M_, V_><<<grid, block, 0, S(st)>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32);             \
+#define PB_GN_ARGS xp, mean, rstd, gamma, beta, HW, C, G, silu, t, out, acc, round_tf32
+#define PB_GN_GROUP(M_, V_)                                                                                   \
+  do {                                                                                                        \
+    if (nsplit == 2) gn_lin_group_cluster_k<M_, V_, 2><<<grid, block, 0, S(st)>>>(PB_GN_ARGS);               \
+    else if (nsplit == 4) gn_lin_group_cluster_k<M_, V_, 4><<<grid, block, 0, S(st)>>>(PB_GN_ARGS);          \
+    else if (nsplit == 8) gn_lin_group_cluster_k<M_, V_, 8><<<grid, block, 0, S(st)>>>(PB_GN_ARGS);          \
+    else gn_lin_group_k<M_, V_><<<grid, block, 0, S(st)>>>(PB_GN_ARGS);                                      \
   } while (0)
       if (mode == 0) { if (V == 4) PB_GN_GROUP(0, 4); else if (V == 2) PB_GN_GROUP(0, 2); else PB_GN_GROUP(0, 1); }
       else { if (V == 4) PB_GN_GROUP(1, 4); else if (V == 2) PB_GN_GROUP(1, 2); else PB_GN_GROUP(1, 1); }
+#undef PB_GN_ARGS
 #undef PB_GN_GROUP
       return last_err();
     }
