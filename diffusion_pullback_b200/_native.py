@@ -38,6 +38,12 @@ class PbIterInfo(C.Structure):
     _fields_ = [("iters_done", C.c_int32), ("converged", C.c_int32), ("last_dist", C.c_float)]
 
 
+class PbPlanInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_ops", "n_gemm", "n_conv3x3", "n_gemm_f16_jvp", "n_gemm_f16_vjp_stored",
+                                         "n_gemm_f16_vjp_converted", "n_gemm_d16_jvp", "n_attn", "n_attn_fused_self",
+                                         "n_attn_fused_cross", "n_attn_p16")]
+
+
 class PbGemmSeg(C.Structure):
     _fields_ = [("A", C.c_void_p), ("lda", C.c_long), ("sAb", C.c_long), ("sAh", C.c_long),
                 ("B", C.c_void_p), ("ldb", C.c_long), ("sBb", C.c_long), ("sBh", C.c_long),
@@ -116,6 +122,8 @@ def _declare(L):
     L.pb_weight_info.restype = C.c_int
     L.pb_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     L.pb_set_option.restype = C.c_int
+    L.pb_plan_summary.argtypes = [vp, C.POINTER(PbPlanInfo)]
+    L.pb_plan_summary.restype = C.c_int
     L.pb_ddim_step.argtypes = [vp, vp, f32, f32, vp, vp, i64, vp]
     L.pb_ddim_step.restype = C.c_int
     L.pb_lincomb3.argtypes = [vp, f32, vp, f32, vp, f32, vp, i64, vp]

@@ -1103,6 +1103,29 @@ PB_API void pb_destroy(pb_handle* h) {
 
 PB_API int64_t pb_kernel_launches(const pb_handle* h) { return h ? h->launches : 0; }
 
+PB_API int pb_plan_summary(const pb_handle* h, pb_plan_info* info) {
+  if (!h || !info) return PB_EINVAL;
+  if (!h->planned) return PB_ESTATE;
+  *info = pb_plan_info{};
+  info->n_ops = (int32_t)h->ops.size();
+  for (const Op& o : h->ops) {
+    if (o.kind == OP_GEMM) {
+      ++info->n_gemm;
+      info->n_conv3x3 += o.conv ? 1 : 0;
+      info->n_gemm_f16_jvp += o.a16_jvp ? 1 : 0;
+      info->n_gemm_f16_vjp_stored += o.a16_vjp == 1 ? 1 : 0;
+      info->n_gemm_f16_vjp_converted += o.a16_vjp == 2 ? 1 : 0;
+      info->n_gemm_d16_jvp += o.d16_jvp ? 1 : 0;
+    } else if (o.kind == OP_ATTN) {
+      ++info->n_attn;
+      info->n_attn_fused_self += use_fused(h, o) ? 1 : 0;
+      info->n_attn_fused_cross += use_fused_cross(h, o) ? 1 : 0;
+      info->n_attn_p16 += (use_fused(h, o) && o.p16) ? 1 : 0;
+    }
+  }
+  return PB_OK;
+}
+
 PB_API int pb_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, int64_t n,
                         void* stream) {
   if (!x || !eps || !x_next || n < 0) return PB_EINVAL;

@@ -127,6 +127,18 @@ int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t
 int64_t pb_kernel_launches(const pb_handle* h);
 int pb_set_option(pb_handle* h, const char* name, int value);
 
+/* Diagnostics of the current plan (host-only, valid after pb_plan): how many ops of each kind the truncated U-Net became and
+ * which of them the fp16-operand policy / the fused attention kernel cover. */
+typedef struct pb_plan_info {
+  int32_t n_ops, n_gemm, n_conv3x3;
+  int32_t n_gemm_f16_jvp;             /* GEMMs whose JVP reads fp16 operands (A stored as halves by its producer) */
+  int32_t n_gemm_f16_vjp_stored;      /* VJP: cotangent stored as halves by its single elementwise contributor */
+  int32_t n_gemm_f16_vjp_converted;   /* VJP: 3x3 convs whose fp32 cotangent is converted once */
+  int32_t n_gemm_d16_jvp;             /* JVP GEMMs writing fp16 output (sole consumer reads halves) */
+  int32_t n_attn, n_attn_fused_self, n_attn_fused_cross, n_attn_p16;
+} pb_plan_info;
+int pb_plan_summary(const pb_handle* h, pb_plan_info* info);
+
 /* One deterministic DDIM update (the reference's custom scheduler `step`, src/utils/utils.py:288-315, eta = 0):
  *   pred_x0 = (x - sqrt(1 - a_t) * eps) / sqrt(a_t);   x_next = sqrt(a_next) * pred_x0 + sqrt(1 - a_next) * eps
  * over n contiguous floats; x_next may alias x, pred_x0 may be NULL.  a_t / a_next are alphas_cumprod gathered by the

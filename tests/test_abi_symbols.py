@@ -49,3 +49,38 @@ def test_product_api_has_no_cpu_path():
     x, t, _ = UT.synthetic_inputs("uncond_tiny")
     with pytest.raises(RuntimeError):
         m.local_encoder_pullback_xt(x, t, op="mid", block_idx=0, pca_rank=2, min_iter=1, max_iter=1)
+
+
+def test_plan_of_the_headline_workload_host_only():
+    """pb_create / pb_plan / pb_plan_summary are host logic: on the product library, without a GPU, the SD-v1.5 mid-block plan
+    must put every 3x3 convolution on fp16 operands in both passes and every >= 512-token attention layer on the fused kernel."""
+    from diffusion_pullback_b200 import _native as N
+    from diffusion_pullback_b200 import synthetic as SY
+    from diffusion_pullback_b200.engine import unet_config
+    L = N.lib()
+    cfg = unet_config(SY.SyntheticUNet("sd15"))
+    c = N.PbUnetCfg()
+    c.kind, c.in_channels, c.n_levels = cfg["kind"], cfg["in_channels"], len(cfg["block_out_channels"])
+    for i, v in enumerate(cfg["block_out_channels"]):
+        c.block_out_channels[i], c.down_has_attn[i], c.up_has_attn[i], c.heads[i] = v, cfg["down_has_attn"][i], cfg["up_has_attn"][i], cfg["heads"][i]
+    c.layers_per_block, c.cross_attention_dim = cfg["layers_per_block"], cfg["cross_attention_dim"]
+    c.norm_num_groups, c.norm_eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    c.flip_sin_to_cos, c.freq_shift, c.downsample_padding = cfg["flip_sin_to_cos"], cfg["freq_shift"], cfg["downsample_padding"]
+    h = C.c_void_p()
+    assert L.pb_create(C.byref(c), C.byref(h)) == 0
+    try:
+        sizes = N.PbSizes()
+        assert L.pb_plan(h, 64, 64, 0, 0, 5, 77, C.byref(sizes)) == 0
+        assert (sizes.n_in, sizes.n_out) == (4 * 64 * 64, 1280 * 8 * 8)
+        info = N.PbPlanInfo()
+        assert L.pb_plan_summary(h, C.byref(info)) == 0
+        # 10 resnets (2 per level on 4 levels + 2 in the mid block) x 2 convs = 20 stride-1 3x3 convs (the 3 downsamplers are im2col GEMMs)
+        assert info.n_conv3x3 == 20
+        assert info.n_gemm_f16_jvp >= info.n_conv3x3 + 3                      # every 3x3 conv, the downsamplers, GN/LN/GEGLU-fed linears
+        assert info.n_gemm_f16_vjp_stored + info.n_gemm_f16_vjp_converted >= info.n_conv3x3
+        assert info.n_attn == 14                                              # 7 transformer blocks x (self + cross)
+        assert info.n_attn_fused_self == 4 and info.n_attn_fused_cross == 4   # the 64x64 and 32x32 levels (>= 512 tokens)
+        assert info.n_attn_p16 == 2                                           # head dim 40 (64x64); head dim 80 keeps fp32 probabilities
+        assert info.n_gemm_d16_jvp == 7                                       # ff1 -> GEGLU in every transformer block
+    finally:
+        L.pb_destroy(h)
