@@ -65,6 +65,15 @@ def eps(self, sample, timestep, encoder_hidden_states=None):
     return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
 
 
+def eps_uncond(self, x, t):
+    """The whole unconditional U-Net (`UNet2DModel`), x_t -> noise prediction: `self.unet(x, t).sample` of the reference's
+    uncond DDIM loops (`edit.py:1601-1714`); one image per call."""
+    if x.shape[0] != 1:
+        return torch.cat([eps_uncond(self, x[i:i + 1], t) for i in range(x.shape[0])], 0)
+    eng = _engine_for(self, x, "full", 0, 1, 0)
+    return eng.set_point(x, _timestep(t), None, want_h=True)
+
+
 def get_h_uncond(self, x=None, t=None, op=None, block_idx=None, verbose=False):
     """`utils.py:114-163`; only ('mid', 0) is valid, anything else raises ValueError like the reference."""
     if x.shape[0] != 1:
@@ -136,4 +145,5 @@ def patch_unet(unet):
     else:
         unet.get_h = types.MethodType(get_h_uncond, unet)
         unet.local_encoder_pullback_xt = types.MethodType(local_encoder_pullback_xt, unet)
+        unet.eps = types.MethodType(eps_uncond, unet)
     return unet

@@ -381,7 +381,8 @@ struct Planner {
     if (x < 0) return false;
     x = resnet(x, Cm, H, W, "mid_block.resnets.1"); if (x < 0) return false;
     if (h->op == PB_OP_UP || h->op == PB_OP_FULL) {
-      if (!cond) { error = "(op, block_idx) is not valid: get_h_uncond supports ('mid', 0) only"; return false; }
+      // get_h_uncond stops at the mid block (utils.py:158-163); the unconditional up path exists for the full forward only
+      if (!cond && h->op == PB_OP_UP) { error = "(op, block_idx) is not valid: get_h_uncond supports ('mid', 0) only"; return false; }
       const int last_up = h->op == PB_OP_FULL ? L - 1 : h->block_idx;
       for (int i = 0; i <= last_up; ++i) {
         const std::string bp = "up_blocks." + std::to_string(i);
@@ -392,7 +393,8 @@ struct Planner {
           int cat = concat(x, s.v);
           x = resnet(cat, out_ch, H, W, bp + ".resnets." + std::to_string(j)); if (x < 0) return false;
           if (c.up_has_attn[i]) {
-            x = transformer(x, c.heads[L - 1 - i], H, W, bp + ".attentions." + std::to_string(j));
+            const std::string ap = bp + ".attentions." + std::to_string(j);
+            x = cond ? transformer(x, c.heads[L - 1 - i], H, W, ap) : attn_block(x, c.heads[L - 1 - i], H, W, ap);
             if (x < 0) return false;
           }
         }
@@ -1213,7 +1215,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   else if (op == PB_OP_UP) {
     if (h->cfg.kind != PB_UNET_COND || block_idx < 0 || block_idx >= h->cfg.n_levels) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   } else if (op == PB_OP_FULL) {
-    if (h->cfg.kind != PB_UNET_COND || block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
+    if (block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   } else return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   if (h->cfg.kind == PB_UNET_COND && ctx_len < 1) return fail(h, PB_EINVAL, "ctx_len must be >= 1 for a conditional U-Net");
   h->H = height; h->W = width; h->op = op; h->block_idx = block_idx; h->kmax = k_max; h->ctx_len = ctx_len;

@@ -78,6 +78,8 @@ class DDIMSchedule:
 def _eps(unet, latents, t, ctx, guidance_scale, neg_ctx):
     """Noise prediction with optional classifier-free guidance (`edit.py:150-175`, `:447-468`); the engine evaluates one
     latent at a time, so the guided pair is two primal passes."""
+    if ctx is None:                                   # unconditional UNet2DModel: `self.unet(x, t).sample` (edit.py:1601-1714)
+        return torch.cat([unet.eps(latents[i:i + 1], t) for i in range(latents.shape[0])], 0)
     outs = []
     for i in range(latents.shape[0]):
         x = latents[i:i + 1]

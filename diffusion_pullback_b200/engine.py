@@ -35,7 +35,9 @@ def unet_config(unet) -> dict:
         up = list(get("up_block_types"))
     else:
         heads = [1 if ahd is None else c // int(ahd) for c in boc]
-        up = []
+        # UNet2DModel: `up_block_types` when the config has it, else the mirror of the down path (an AttnUpBlock2D where the
+        # down path has an AttnDownBlock2D); only the full forward (op='full') reads it
+        up = list(get("up_block_types", None) or ["AttnUpBlock2D" if "Attn" in t else "UpBlock2D" for t in reversed(down)])
     return dict(kind=0 if cond else 1, in_channels=int(get("in_channels")), block_out_channels=boc,
                 down_has_attn=[int("Attn" in t) for t in down], up_has_attn=[int("Attn" in t) for t in up] + [0] * (L - len(up)),
                 heads=heads, layers_per_block=int(get("layers_per_block")),

@@ -55,7 +55,7 @@ class SyntheticUNet:
         if self._sd is None:
             from .engine import PullbackEngine, unet_config
             cfg = unet_config(self)
-            op, bi = ("full", 0) if cfg["kind"] == 0 else ("mid", 0)
+            op, bi = ("full", 0)
             if self.upto is not None:
                 op, bi = self.upto
             s = self.config["sample_size"]

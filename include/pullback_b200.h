@@ -34,7 +34,7 @@ enum pb_unet_kind {
   PB_UNET_UNCOND = 1  /* diffusers UNet2DModel (DDPM CelebA-HQ ...): get_h_uncond, utils.py:114-163   */
 };
 enum pb_op { PB_OP_MID = 0, PB_OP_UP = 1,   /* `op='down'` raises in the reference  */
-             PB_OP_FULL = 2 };               /* the whole conditional U-Net: x_t -> eps (conv_norm_out, SiLU, conv_out); block_idx 0 */
+             PB_OP_FULL = 2 };               /* the whole U-Net: x_t -> eps (up path, conv_norm_out, SiLU, conv_out); block_idx 0 */
 
 #define PB_MAX_LEVELS 8
 

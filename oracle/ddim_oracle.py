@@ -61,6 +61,8 @@ class Scheduler:
 
 def _eps(unet, latents, t, ctx, guidance_scale, neg_ctx):
     """noise prediction with optional classifier-free guidance (`edit.py:150-175`, `:447-468`)."""
+    if ctx is None:
+        return unet(latents, t)
     if guidance_scale > 1.0 and neg_ctx is not None:
         e_un = unet(latents, t, encoder_hidden_states=neg_ctx)
         e_c = unet(latents, t, encoder_hidden_states=ctx)

@@ -77,7 +77,7 @@ def get_h_uncond(unet, x, t, op=None, block_idx=None):
 
 def make_h_fn(unet, t, ctx, op, block_idx):
     """x[B,C,H,W] -> h[B,Co,Ho,Wo] closure, SD or uncond by model type."""
-    if hasattr(unet, "up_blocks"):
+    if type(unet).__name__ == "UNet2DConditionModel":      # UNet2DModel has up_blocks too (full forward)
         def f(x):
             c = None if ctx is None else ctx.expand(x.shape[0], -1, -1)
             return get_h(unet, x, t, c, op, block_idx)

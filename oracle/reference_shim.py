@@ -57,7 +57,7 @@ def bind(unet):
     """Monkey-patches the reference methods onto `unet` exactly like `utils.py:103-104`,
     `:326`, `:333` do."""
     U = load()
-    if hasattr(unet, "up_blocks"):
+    if type(unet).__name__ == "UNet2DConditionModel":      # UNet2DModel has up_blocks too (full forward)
         unet.get_h = types.MethodType(U.get_h, unet)
         unet.local_encoder_pullback_zt = types.MethodType(U.local_encoder_pullback_zt, unet)
     else:

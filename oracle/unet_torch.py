@@ -450,6 +450,37 @@ class UpBlock2D(nn.Module):
         return hidden_states
 
 
+class AttnUpBlock2D(nn.Module):
+    """diffusers 0.11.0 `AttnUpBlock2D` (UNet2DModel): [concat skip -> ResnetBlock2D -> AttentionBlock] x num_layers, then
+    Upsample2D.  In-repo analogue: the `up` levels with `attn` of `src/models/ddpm/diffusion.py:96-118`."""
+    has_cross_attention = False
+
+    def __init__(self, in_channels, prev_output_channel, out_channels, temb_channels, num_layers, eps, groups,
+                 attn_num_head_channels, add_upsample):
+        super().__init__()
+        rs = []
+        for i in range(num_layers):
+            skip = in_channels if i == num_layers - 1 else out_channels
+            rin = prev_output_channel if i == 0 else out_channels
+            rs.append(ResnetBlock2D(rin + skip, out_channels, temb_channels, groups=groups, eps=eps))
+        self.resnets = nn.ModuleList(rs)
+        self.attentions = nn.ModuleList([
+            AttentionBlock(out_channels, attn_num_head_channels, groups=groups, eps=eps) for _ in range(num_layers)])
+        self.upsamplers = None
+        if add_upsample:
+            self.upsamplers = nn.ModuleList([Upsample2D(out_channels, out_channels)])
+
+    def forward(self, hidden_states, res_hidden_states_tuple, temb=None, upsample_size=None):
+        for r, a in zip(self.resnets, self.attentions):
+            res = res_hidden_states_tuple[-1]
+            res_hidden_states_tuple = res_hidden_states_tuple[:-1]
+            hidden_states = a(r(torch.cat([hidden_states, res], dim=1), temb))
+        if self.upsamplers is not None:
+            for u in self.upsamplers:
+                hidden_states = u(hidden_states, upsample_size)
+        return hidden_states
+
+
 class CrossAttnUpBlock2D(nn.Module):
     has_cross_attention = True
 
@@ -615,7 +646,7 @@ class UNet2DConditionModel(nn.Module):
 
 
 class UNet2DModel(nn.Module):
-    def __init__(self, cfg: UncondConfig):
+    def __init__(self, cfg: UncondConfig, build_up: bool = True):
         super().__init__()
         self.cfg = cfg
         boc = cfg.block_out_channels
@@ -640,6 +671,46 @@ class UNet2DModel(nn.Module):
             self.down_blocks.append(blk)
         self.mid_block = UNetMidBlock2D(boc[-1], ted, cfg.norm_eps, cfg.norm_num_groups,
                                         cfg.attention_head_dim)
+        if build_up:
+            # up path + eps head of diffusers 0.11.0 `UNet2DModel` (mirror of the down path: an Attn block where the down path has one)
+            self.up_blocks = nn.ModuleList()
+            rboc = list(reversed(boc))
+            up_types = ["AttnUpBlock2D" if t == "AttnDownBlock2D" else "UpBlock2D" for t in reversed(cfg.down_block_types)]
+            out_ch = rboc[0]
+            for i, t in enumerate(up_types):
+                final = i == len(boc) - 1
+                prev, out_ch = out_ch, rboc[i]
+                in_ch = rboc[min(i + 1, len(boc) - 1)]
+                if t == "UpBlock2D":
+                    blk = UpBlock2D(in_ch, prev, out_ch, ted, cfg.layers_per_block + 1, cfg.norm_eps, cfg.norm_num_groups, not final)
+                else:
+                    blk = AttnUpBlock2D(in_ch, prev, out_ch, ted, cfg.layers_per_block + 1, cfg.norm_eps, cfg.norm_num_groups,
+                                        cfg.attention_head_dim, not final)
+                self.up_blocks.append(blk)
+            self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, boc[0], eps=cfg.norm_eps)
+            self.conv_out = nn.Conv2d(boc[0], cfg.in_channels, 3, padding=1)
+
+    def forward(self, sample, timestep):
+        """The full noise prediction of the unconditional model (diffusers 0.11.0 `UNet2DModel.forward`; the reference calls it
+        as `self.unet(x, t).sample` in its uncond DDIM loops, `edit.py:1601-1714`)."""
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], dtype=torch.long, device=sample.device)
+        elif t.dim() == 0:
+            t = t[None].to(sample.device)
+        t = t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
+        emb = self.time_embedding(self.time_proj(t).to(dtype=self.dtype))
+        x = self.conv_in(sample)
+        skips = (x,)
+        for blk in self.down_blocks:
+            x, res = blk(hidden_states=x, temb=emb)
+            skips += res
+        x = self.mid_block(x, emb)
+        for blk in self.up_blocks:
+            n = len(blk.resnets)
+            res, skips = skips[-n:], skips[:-n]
+            x = blk(x, res, emb)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
 
     @property
     def dtype(self):
@@ -683,7 +754,7 @@ def build_unet(name: str, seed: int = 0, build_up: bool = True) -> nn.Module:
     if isinstance(cfg, CondConfig):
         m = UNet2DConditionModel(cfg, build_up=build_up)
     else:
-        m = UNet2DModel(cfg)
+        m = UNet2DModel(cfg, build_up=build_up)
     seeded_init_(m, seed)
     return m.eval().requires_grad_(False)
 

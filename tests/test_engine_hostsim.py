@@ -238,3 +238,23 @@ def test_x_space_guidance_and_cache_format(hostsim, tmp_path):
     u2, s2, v2 = PB.load_or_compute_local_basis(types.SimpleNamespace(local_encoder_pullback_zt=pullback), x, t, ctx, d, name, "mid", 0, 5)
     assert len(calls) == 1 and s2 is None and torch.equal(u1, u2) and torch.equal(v1, v2)           # cache hit: no recompute
     assert torch.equal(torch.load(sp), s1)
+
+
+def test_full_uncond_unet_eps_matches_oracle(hostsim):
+    """UNet2DModel (the CelebA-HQ family): the FULL plan with AttnUpBlock2D / UpBlock2D levels against the oracle forward."""
+    eng, m, x, t, ctx = make_engine(hostsim, "uncond_tiny", "full", 0, 1, EXACT)
+    e = eng.set_point(x, float(t), None, want_h=True)
+    ref = m(x, t)
+    assert e.shape == ref.shape == x.shape and rel(e, ref) < 1e-5
+
+
+def test_uncond_ddim_loop_on_the_engine(hostsim):
+    import types
+    import diffusion_pullback_b200 as PB
+    from oracle import ddim_oracle as DO
+    eng, m, x, t, _ = make_engine(hostsim, "uncond_tiny", "full", 0, 1, EXACT)
+    fake = types.SimpleNamespace(eps=lambda s, tt: eng.set_point(s, float(tt), None, want_h=True))
+    hostsim.pb_ddim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    ac = torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0)
+    z = PB.ddim_forward_steps(fake, PB.DDIMSchedule(ac, _lib=hostsim), x, None, 4)
+    assert rel(z, DO.ddim_forward_steps(m, DO.Scheduler(ac), x, None, 4)) < 1e-4

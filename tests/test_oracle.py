@@ -91,6 +91,16 @@ def test_restated_unet2dmodel_matches_inrepo_ddpm():
             cp(f"down_blocks.{i}.downsamplers.0.conv", f"down.{i}.downsample.conv")
     res("mid_block.resnets.0", "mid.block_1"); att("mid_block.attentions.0", "mid.attn_1")
     res("mid_block.resnets.1", "mid.block_2")
+    # up path + eps head (diffusion.py:96-126): diffusers up_blocks[i] is the DDPM level 3 - i
+    for i in range(4):
+        lvl = 3 - i
+        for j in range(3):
+            res(f"up_blocks.{i}.resnets.{j}", f"up.{lvl}.block.{j}")
+            if lvl == 2:
+                att(f"up_blocks.{i}.attentions.{j}", f"up.{lvl}.attn.{j}")
+        if lvl != 0:
+            cp(f"up_blocks.{i}.upsamplers.0.conv", f"up.{lvl}.upsample.conv")
+    cp("conv_norm_out", "norm_out"); cp("conv_out", "conv_out")
     missing = m.load_state_dict(sd, strict=True)
     x, t, _ = UT.synthetic_inputs("uncond_tiny")
     with torch.no_grad():
@@ -98,6 +108,12 @@ def test_restated_unet2dmodel_matches_inrepo_ddpm():
         h = PO.get_h_uncond(m, x, t, "mid", 0)
     assert h.shape == h_ref.shape
     assert torch.allclose(h, h_ref, rtol=1e-4, atol=1e-5), float((h - h_ref).abs().max())
+    # the full noise prediction: the reference's own forward (diffusion.py:145-203) against the restated UNet2DModel.forward
+    with torch.no_grad():
+        e_ref = ddpm(x, t)
+        e = m(x, t)
+    assert e.shape == e_ref.shape == x.shape
+    assert torch.allclose(e, e_ref, rtol=1e-4, atol=1e-5), float((e - e_ref).abs().max())
 
 
 @pytest.mark.parametrize("name,op,bi", [("sd_tiny", "mid", 0)])

@@ -232,6 +232,22 @@ def test_full_unet_eps_and_ddim_vs_golden(name):
         assert rel(zs[i + 1], zo) < 1e-2
 
 
+def test_full_uncond_unet_eps_and_ddim_vs_oracle():
+    """UNet2DModel family (CelebA-HQ layout): x_t -> eps through the FULL plan (AttnUpBlock2D / UpBlock2D levels) and a short
+    deterministic DDIM sampling loop, against the oracle (pinned to the reference's in-repo DDPM forward, tests/test_oracle.py)."""
+    from oracle import ddim_oracle as DO
+    name = "uncond_tiny"
+    m = UT.build_unet(name)
+    unet = PB.patch_unet(SY.SyntheticUNet(name, device=DEV))
+    x, t, _ = SY.synthetic_inputs(name, device=DEV)
+    e = unet.eps(x, t)
+    assert e.shape == x.shape and rel(e, m(x.cpu(), t)) < 5e-3
+    ac = torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0)                  # DDPM linear betas
+    z = PB.ddim_forward_steps(unet, PB.DDIMSchedule(ac), x, None, 5)
+    zo = DO.ddim_forward_steps(m, DO.Scheduler(ac), x.cpu(), None, 5)
+    assert rel(z, zo) < 2e-2
+
+
 def ddim_alphas():
     betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2     # SD `scaled_linear`
     return torch.cumprod(1.0 - betas, dim=0)
