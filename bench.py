@@ -138,13 +138,26 @@ def run_reference(args, wl):
     torch.set_num_threads(cores)
     m = UT.build_unet(model_name, build_up=(op == "up"))
     x, t, ctx = UT.synthetic_inputs(model_name)
-    f = PO.make_h_fn(m, t, ctx, op, bi)
+    on_gpu = args.ref_device == "cuda"
+    if on_gpu:
+        # the same reference algorithm through torch eager autograd on this box's GPU (fp32, TF32 off like
+        # torch 2.1's matmul default) -- "the reference on B200"; not the driver's reference arm (that one is --ref-device cpu)
+        tf32 = os.environ.get("PB_REF_TF32", "0") == "1"     # 1: let cuBLAS / cuDNN use TF32 (the operand precision of our own path)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        m = m.to("cuda:0")
+        x, t = x.to("cuda:0"), t.to("cuda:0")
+        ctx = None if ctx is None else ctx.to("cuda:0")
 
     def iteration(k_s, seed):
         torch.manual_seed(seed)
         v0 = PO.initial_subspace(x.numel(), k_s)
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         PO.local_encoder_pullback(m, x, t, ctx, op, bi, k_s, 1, 1, 0.0, v0=v0)
+        if on_gpu:
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
 
     t_col = iteration(1, 0)                                  # probe (also warms the thread pool)
@@ -168,10 +181,17 @@ def run_reference(args, wl):
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl, "model": model_name, "op": op, "block_idx": bi, "pca_rank": k, "power_iters": iters,
-                       "device": "host CPU (torch-cpu autograd, oracle port of the reference algorithm)"},
+                       "device": ("cuda:0 (torch eager autograd fp32, TF32 off, oracle port of the reference algorithm)" if on_gpu else
+                                  "host CPU (torch-cpu autograd, oracle port of the reference algorithm)")},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if on_gpu:
+        line["impl"] = "reference_gpu"
+        line["reference_gpu"] = dict(line.pop("cpu_baseline"), device=torch.cuda.get_device_name(0), tf32=tf32,
+                                     peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)
+        line["config"]["device"] = line["config"]["device"].replace("TF32 off", "TF32 on" if tf32 else "TF32 off")
+        del line["reference_gpu"]["cores"], line["reference_gpu"]["kind"]
     emit(line)
 
 
@@ -362,6 +382,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu (the reference arm) or cuda (torch eager autograd on this box's GPU, SURVEY s.8d-ii)")
     ap.add_argument("--shard", default="problem", choices=["problem", "tangent"],
                     help="N > 1: independent problems per rank (default, weak scaling) or the k columns of each problem split over the ranks")
     args = ap.parse_args()

@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
     jobs, objs = [], []
     for src in _sources():
