@@ -117,7 +117,8 @@ struct pb_handle {
   std::map<int, DirGraph> jvp_graphs, vjp_graphs;
   bool warm_jvp = false, warm_vjp = false;
   // timing probes (pb_profile_begin / pb_profile_read): one event pair per contraction-kernel launch
-  struct Probe { void* e0; void* e1; double flops; int kind; };
+  struct Probe { void* e0; void* e1; double flops; int kind; std::string label; };
+  std::string probe_label;                   // shape of the launch being probed (PB_PROFILE_DUMP)
   bool profiling = false;
   std::vector<Probe> probes;
 
@@ -474,7 +475,7 @@ void analyse_f16(pb_handle* h) {
 template <class F>
 const char* probed(pb_handle* h, int kind, double flops, pb_stream st, F&& launch) {
   if (!h->profiling) return launch();
-  pb_handle::Probe pr{nullptr, nullptr, flops, kind};
+  pb_handle::Probe pr{nullptr, nullptr, flops, kind, h->probe_label};
   if (const char* e = pbk_event_record(&pr.e0, st)) return e;
   const char* err = launch();
   if (const char* e = pbk_event_record(&pr.e1, st)) return e;
@@ -488,11 +489,22 @@ const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
   double k = 0;
   for (int s = 0; s < g.nseg; ++s) k += g.seg[s].K;
   const double flops = 2.0 * g.M * g.N * k * (g.conv ? 9.0 : (double)g.nb * g.nh);
+  if (h->profiling) {
+    char b[160];
+    snprintf(b, sizeof b, "gemm M=%d N=%d K=%d nseg=%d nb=%d nh=%d conv=%d HW=%dx%d res=%d ab16=%d d16=%d", g.M, g.N, (int)k, g.nseg, g.nb, g.nh,
+             g.conv, g.H, g.W, g.R ? 1 : 0, g.ab_dtype == PB_GEMM_F16, g.d_dtype == PB_GEMM_F16);
+    h->probe_label = b;
+  }
   return probed(h, PB_PROBE_GEMM, flops, st, [&] { return pbk_gemm(&g, st); });
 }
 // fused attention linearisation: S (nseg products over the head dim) + T . C1 per (tangent, head)
 const char* attn_lin_call(pb_handle* h, const PbAttnLin& a, pb_stream st) {
   const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1 + (a.C2 ? 1 : 0)) * a.nb * a.nh;
+  if (h->profiling) {
+    char b[160];
+    snprintf(b, sizeof b, "attn Mr=%d Nc=%d d=%d nseg=%d c2=%d nb=%d nh=%d", a.Mr, a.Nc, a.d, a.nseg, a.C2 ? 1 : 0, a.nb, a.nh);
+    h->probe_label = b;
+  }
   return probed(h, PB_PROBE_ATTN, flops, st, [&] { return pbk_attn_lin(&a, st); });
 }
 
@@ -1155,6 +1167,14 @@ PB_API int pb_profile_read(pb_handle* h, int32_t kind, double* ms, double* flops
     const float t = pbk_event_elapsed_ms(p.e0, p.e1);
     if (t < 0.f) return fail(h, PB_ECUDA, "event timing failed");
     *ms += t; *flops += p.flops; ++*launches;
+  }
+  // PB_PROFILE_DUMP=<path>: one line per probed launch (us, algorithmic GF, shape) for per-shape tables (profiles/)
+  if (const char* path = getenv("PB_PROFILE_DUMP")) {
+    if (FILE* f = fopen(path, kind == PB_PROBE_GEMM ? "w" : "a")) {
+      for (const auto& p : h->probes)
+        if (p.kind == kind) fprintf(f, "%.2f us %.3f GF %s\n", 1e3 * pbk_event_elapsed_ms(p.e0, p.e1), p.flops * 1e-9, p.label.c_str());
+      fclose(f);
+    }
   }
   return PB_OK;
 }
