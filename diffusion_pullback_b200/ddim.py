@@ -142,11 +142,14 @@ def _lincomb3(a, x, b, y, c, z, _lib=None):
 @torch.no_grad()
 def x_space_guidance(unet, scheduler, zt, t_idx, vk, single_edit_step, edit_prompt_emb, x_space_guidance_scale, _lib=None):
     """`EditStableDiffusion.x_space_guidance` (`edit.py:484-502`): perturb z_t along the pullback direction v_k, predict the
-    noise at both points with the edit prompt, and move z_t by the scaled difference (DDS regularisation)."""
+    noise at both points with the edit prompt, and move z_t by the scaled difference (DDS regularisation).
+    `edit_prompt_emb=None`: the unconditional variant, `EditUncondDiffusion.x_space_guidance` (`edit.py:1716-1734`)."""
     t = scheduler.timesteps[t_idx]
     zt_edit = _lincomb3(1.0, zt, single_edit_step, vk.reshape(zt.shape), 0.0, None, _lib)          # zt + step * vk
-    et_null = unet.eps(zt, t, edit_prompt_emb)
-    et_edit = unet.eps(zt_edit, t, edit_prompt_emb)
+    if edit_prompt_emb is None:
+        et_null, et_edit = unet.eps(zt, t), unet.eps(zt_edit, t)
+    else:
+        et_null, et_edit = unet.eps(zt, t, edit_prompt_emb), unet.eps(zt_edit, t, edit_prompt_emb)
     return _lincomb3(1.0, zt, x_space_guidance_scale, et_edit, -x_space_guidance_scale, et_null, _lib)
 
 

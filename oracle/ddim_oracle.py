@@ -103,6 +103,9 @@ def x_space_guidance(unet, sched: Scheduler, zt, t_idx, vk, single_edit_step, ed
     zt + scale * (eps_edit - eps_null)."""
     t = sched.timesteps[t_idx]
     zt_edit = zt + single_edit_step * vk
-    et = unet(torch.cat([zt, zt_edit], dim=0), t, encoder_hidden_states=edit_prompt_emb.repeat(2, 1, 1))
+    if edit_prompt_emb is None:                       # `EditUncondDiffusion.x_space_guidance`, edit.py:1716-1734
+        et = unet(torch.cat([zt, zt_edit], dim=0), t)
+    else:
+        et = unet(torch.cat([zt, zt_edit], dim=0), t, encoder_hidden_states=edit_prompt_emb.repeat(2, 1, 1))
     et_null, et_edit = et.chunk(2)
     return zt + scale * (et_edit - et_null)

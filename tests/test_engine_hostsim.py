@@ -258,3 +258,23 @@ def test_uncond_ddim_loop_on_the_engine(hostsim):
     ac = torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0)
     z = PB.ddim_forward_steps(fake, PB.DDIMSchedule(ac, _lib=hostsim), x, None, 4)
     assert rel(z, DO.ddim_forward_steps(m, DO.Scheduler(ac), x, None, 4)) < 1e-4
+
+
+def test_uncond_x_space_guidance_on_the_engine(hostsim):
+    """`EditUncondDiffusion.x_space_guidance` (edit.py:1716-1734): the prompt-less edit loop through the FULL plan."""
+    import types
+    import diffusion_pullback_b200 as PB
+    from oracle import ddim_oracle as DO
+    eng, m, x, t, _ = make_engine(hostsim, "uncond_tiny", "full", 0, 1, EXACT)
+    fake = types.SimpleNamespace(eps=lambda s, tt: eng.set_point(s, float(tt), None, want_h=True))
+    hostsim.pb_lincomb3.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    ac = torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0)
+    sched, osched = PB.DDIMSchedule(ac, _lib=hostsim), DO.Scheduler(ac)
+    sched.set_timesteps(10); osched.set_timesteps(10)
+    vk = torch.randn(x.shape, generator=torch.Generator().manual_seed(2))
+    vk = vk / vk.norm()
+    zs = PB.x_space_guidance_edit(fake, sched, x, 3, vk, 2, 1.5, None, 0.7, _lib=hostsim)
+    z = x
+    for i in range(2):
+        z = DO.x_space_guidance(m, osched, z, 3, vk, 1.5, None, 0.7)
+        assert rel(zs[i + 1], z) < 1e-4

@@ -219,3 +219,21 @@ def test_x_space_guidance_restatement_matches_verbatim_reference():
     ref = E.EditStableDiffusion.x_space_guidance(me, zt, 3, vk, 1.5)
     ours = DO.x_space_guidance(m, s, zt, 3, vk, 1.5, ctx, 0.7)
     assert torch.equal(ref, ours)
+
+
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+def test_uncond_x_space_guidance_restatement_matches_verbatim_reference():
+    """oracle x_space_guidance (no prompt) against `EditUncondDiffusion.x_space_guidance` (edit.py:1716-1734) run verbatim."""
+    from oracle import ddim_oracle as DO
+    RS.load()
+    import modules.edit as E
+    m = UT.build_unet("uncond_tiny")
+    xt, _, _ = UT.synthetic_inputs("uncond_tiny")
+    s = DO.Scheduler(torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0))
+    s.set_timesteps(10)
+    vk = torch.randn(xt.shape, generator=torch.Generator().manual_seed(2))
+    vk = vk / vk.norm()
+    me = types.SimpleNamespace(scheduler=s, x_space_guidance_scale=0.7, unet=lambda x, t: m(x, t))
+    ref = E.EditUncondDiffusion.x_space_guidance(me, xt, 3, vk, 1.5)
+    ours = DO.x_space_guidance(m, s, xt, 3, vk, 1.5, None, 0.7)
+    assert torch.equal(ref, ours)

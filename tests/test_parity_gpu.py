@@ -246,6 +246,16 @@ def test_full_uncond_unet_eps_and_ddim_vs_oracle():
     z = PB.ddim_forward_steps(unet, PB.DDIMSchedule(ac), x, None, 5)
     zo = DO.ddim_forward_steps(m, DO.Scheduler(ac), x.cpu(), None, 5)
     assert rel(z, zo) < 2e-2
+    # prompt-less x-space guidance, `EditUncondDiffusion.x_space_guidance` (edit.py:1716-1734)
+    sched, osched = PB.DDIMSchedule(ac), DO.Scheduler(ac)
+    sched.set_timesteps(10); osched.set_timesteps(10)
+    vk = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).to(DEV)
+    vk = vk / vk.norm()
+    zs = PB.x_space_guidance_edit(unet, sched, x, 3, vk, 2, 1.0, None, 0.5)
+    zo = x.cpu()
+    for i in range(2):
+        zo = DO.x_space_guidance(m, osched, zo, 3, vk.cpu(), 1.0, None, 0.5)
+        assert rel(zs[i + 1], zo) < 1e-2
 
 
 def ddim_alphas():
