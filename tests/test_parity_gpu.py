@@ -261,3 +261,22 @@ def test_full_uncond_unet_eps_and_ddim_vs_oracle():
 def ddim_alphas():
     betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2     # SD `scaled_linear`
     return torch.cumprod(1.0 - betas, dim=0)
+
+
+@pytest.mark.parametrize("k", [1, 16])
+def test_rank_extremes_vs_oracle(k):
+    """Rank 1 (a single tangent: no batching, a 1 x 1 Gram matrix) and rank 16 (BASELINE.json configs[3]) on sd_small against
+    the CPU oracle on the same V0; tolerances of the file header."""
+    name, iters = "sd_small", 3
+    m = UT.build_unet(name, build_up=False)
+    x, t, ctx = UT.synthetic_inputs(name)
+    torch.manual_seed(0)
+    v0 = PO.initial_subspace(x.numel(), k)
+    u_ref, s_ref, v_ref = PO.local_encoder_pullback(m, x, t, ctx, "mid", 0, k, iters, iters, 0.0, v0=v0)
+    unet = PB.patch_unet(SY.SyntheticUNet(name, upto=("mid", 0), device=DEV))
+    u, s, vT, info = _call(unet, x, t, ctx, "mid", 0, k, iters, v0)
+    assert u.shape == u_ref.shape and s.shape == (k,) and vT.shape == (k, x.numel()) and info["iters_done"] == iters
+    rep = PO.parity_report(s, vT, s_ref, v_ref, u.cpu(), u_ref)
+    print(k, {kk: rep[kk] for kk in ("s_rel_max", "subspace", "cos_min_gapped", "u_subspace")})
+    assert rep["s_rel_max"] < 1e-3 and rep["subspace"] > 0.999 and rep["cos_min_gapped"] > 0.99 and rep["u_subspace"] > 0.999, rep
+    assert torch.allclose((vT @ vT.T).cpu(), torch.eye(k), atol=1e-4)
