@@ -335,6 +335,12 @@ def run_ours(args, wl):
                                  "avg_launch_us": 1e3 * kms / kn, "achieved_tflops": kfl / kms / 1e9,
                                  "share_of_eager_iter": kms / prof_iters / prof["_eager_ms_per_iter"]}
         dom = max(kernels, key=lambda n: kernels[n]["ms_per_iter"]) if kernels else None
+        # the GEMM launches by operand type, each against its own tensor-pipe peak (kind::tf32 = half the 16-bit rate)
+        for name, pk in (("gemm_tc_kernel[kind::f16]", peak_tf), ("gemm_tc_kernel[kind::tf32]", peak_tf / 2)):
+            kms, kfl, kn = prof.get(name, (0, 0, 0))
+            if kn:
+                kernels[name] = {"launches_per_iter": kn / prof_iters, "ms_per_iter": kms / prof_iters, "avg_launch_us": 1e3 * kms / kn,
+                                 "achieved_tflops": kfl / kms / 1e9, "peak_tflops": pk, "frac": kfl / kms / 1e9 / pk}
         traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if dom and os.path.exists(tp):

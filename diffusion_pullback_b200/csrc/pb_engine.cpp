@@ -117,7 +117,8 @@ struct pb_handle {
   std::map<int, DirGraph> jvp_graphs, vjp_graphs;
   bool warm_jvp = false, warm_vjp = false;
   // timing probes (pb_profile_begin / pb_profile_read): one event pair per contraction-kernel launch
-  struct Probe { void* e0; void* e1; double flops; int kind; std::string label; };
+  struct Probe { void* e0; void* e1; double flops; int kind; std::string label; int f16 = 0; };
+  int probe_f16 = 0;                          // operand type of the GEMM being probed (PB_PROBE_GEMM_TF32 / _F16)
   std::string probe_label;                   // shape of the launch being probed (PB_PROFILE_DUMP)
   bool profiling = false;
   std::vector<Probe> probes;
@@ -475,7 +476,7 @@ void analyse_f16(pb_handle* h) {
 template <class F>
 const char* probed(pb_handle* h, int kind, double flops, pb_stream st, F&& launch) {
   if (!h->profiling) return launch();
-  pb_handle::Probe pr{nullptr, nullptr, flops, kind, h->probe_label};
+  pb_handle::Probe pr{nullptr, nullptr, flops, kind, h->probe_label, h->probe_f16};
   if (const char* e = pbk_event_record(&pr.e0, st)) return e;
   const char* err = launch();
   if (const char* e = pbk_event_record(&pr.e1, st)) return e;
@@ -489,6 +490,7 @@ const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
   double k = 0;
   for (int s = 0; s < g.nseg; ++s) k += g.seg[s].K;
   const double flops = 2.0 * g.M * g.N * k * (g.conv ? 9.0 : (double)g.nb * g.nh);
+  h->probe_f16 = g.ab_dtype == PB_GEMM_F16;
   if (h->profiling) {
     char b[160];
     snprintf(b, sizeof b, "gemm M=%d N=%d K=%d nseg=%d nb=%d nh=%d conv=%d HW=%dx%d res=%d ab16=%d d16=%d", g.M, g.N, (int)k, g.nseg, g.nb, g.nh,
@@ -1162,14 +1164,18 @@ PB_API int pb_profile_read(pb_handle* h, int32_t kind, double* ms, double* flops
   if (!h || !ms || !flops || !launches) return PB_EINVAL;
   h->profiling = false;
   *ms = 0; *flops = 0; *launches = 0;
+  // PB_PROBE_GEMM_TF32 / PB_PROBE_GEMM_F16: the GEMM launches of one operand type (each has its own tensor-pipe peak)
+  const int base = (kind == PB_PROBE_GEMM_TF32 || kind == PB_PROBE_GEMM_F16) ? PB_PROBE_GEMM : kind;
   for (const auto& p : h->probes) {
-    if (p.kind != kind) continue;
+    if (p.kind != base) continue;
+    if (kind == PB_PROBE_GEMM_TF32 && p.f16) continue;
+    if (kind == PB_PROBE_GEMM_F16 && !p.f16) continue;
     const float t = pbk_event_elapsed_ms(p.e0, p.e1);
     if (t < 0.f) return fail(h, PB_ECUDA, "event timing failed");
     *ms += t; *flops += p.flops; ++*launches;
   }
   // PB_PROFILE_DUMP=<path>: one line per probed launch (us, algorithmic GF, shape) for per-shape tables (profiles/)
-  if (const char* path = getenv("PB_PROFILE_DUMP")) {
+  if (const char* path = (kind == base ? getenv("PB_PROFILE_DUMP") : nullptr)) {
     if (FILE* f = fopen(path, kind == PB_PROBE_GEMM ? "w" : "a")) {
       for (const auto& p : h->probes)
         if (p.kind == kind) fprintf(f, "%.2f us %.3f GF %s\n", 1e3 * pbk_event_elapsed_ms(p.e0, p.e1), p.flops * 1e-9, p.label.c_str());

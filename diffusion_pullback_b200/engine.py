@@ -126,7 +126,7 @@ class PullbackEngine:
     def profile_read(self):
         """Stop probing; {kernel class: (device ms, algorithmic flops, launches)} since profile_begin()."""
         out = {}
-        for name, kind in (("gemm_tc_kernel", 0), ("attn_lin_kernel", 1)):
+        for name, kind in (("gemm_tc_kernel", 0), ("attn_lin_kernel", 1), ("gemm_tc_kernel[kind::tf32]", 2), ("gemm_tc_kernel[kind::f16]", 3)):
             ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
             self._ck(self.L.pb_profile_read(self.h, kind, C.byref(ms), C.byref(fl), C.byref(n)))
             out[name] = (ms.value, fl.value, n.value)

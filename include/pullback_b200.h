@@ -157,6 +157,8 @@ int pb_lincomb3(float* out, float a, const float* x, float b, const float* y, fl
  * product) and the launch count of one kernel class. */
 #define PB_PROBE_GEMM 0                      /* gemm_tc_kernel: conv / linear / attention products */
 #define PB_PROBE_ATTN 1                      /* attn_lin_kernel: fused attention linearisation */
+#define PB_PROBE_GEMM_TF32 2                 /* the gemm_tc_kernel launches with fp32 operands (tcgen05 kind::tf32) */
+#define PB_PROBE_GEMM_F16 3                  /* the gemm_tc_kernel launches with fp16 operands (tcgen05 kind::f16) */
 int pb_profile_begin(pb_handle* h);
 int pb_profile_read(pb_handle* h, int32_t kind, double* ms, double* flops, int64_t* launches);
 
