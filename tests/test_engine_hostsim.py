@@ -278,3 +278,27 @@ def test_uncond_x_space_guidance_on_the_engine(hostsim):
     for i in range(2):
         z = DO.x_space_guidance(m, osched, z, 3, vk, 1.5, None, 0.7)
         assert rel(zs[i + 1], z) < 1e-4
+
+
+def test_probe_bookkeeping_and_dump(hostsim, tmp_path, monkeypatch):
+    """pb_profile_begin / pb_profile_read: every contraction launch of the probed iterations is counted once, the GEMM launches
+    split by operand type add up (PB_PROBE_GEMM_TF32 + PB_PROBE_GEMM_F16 = PB_PROBE_GEMM, launches and flops), and
+    PB_PROFILE_DUMP writes one labelled line per probed launch."""
+    dump = tmp_path / "probe.txt"
+    monkeypatch.setenv("PB_PROFILE_DUMP", str(dump))
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, 3)
+    eng.set_point(x, float(t), ctx)
+    torch.manual_seed(0)
+    V0 = PO.initial_subspace(x.numel(), 3)
+    eng.profile_begin()
+    eng.pullback(V0, 2, 2, 0.0)
+    prof = eng.profile_read()
+    _, fl, n = prof["gemm_tc_kernel"]
+    _, fl32, n32 = prof["gemm_tc_kernel[kind::tf32]"]
+    _, fl16, n16 = prof["gemm_tc_kernel[kind::f16]"]
+    _, fla, na = prof["attn_lin_kernel"]
+    assert n > 0 and n32 + n16 == n and abs(fl32 + fl16 - fl) <= 1e-9 * fl
+    assert n16 == 0                                                    # the host simulator models fp32 operands only
+    lines = dump.read_text().strip().splitlines()
+    assert len(lines) == n + na and sum(l.split(" GF ")[1].startswith("gemm M=") for l in lines) == n
+    assert sum("ab16=1" in l for l in lines) == n16

@@ -280,3 +280,23 @@ def test_rank_extremes_vs_oracle(k):
     print(k, {kk: rep[kk] for kk in ("s_rel_max", "subspace", "cos_min_gapped", "u_subspace")})
     assert rep["s_rel_max"] < 1e-3 and rep["subspace"] > 0.999 and rep["cos_min_gapped"] > 0.99 and rep["u_subspace"] > 0.999, rep
     assert torch.allclose((vT @ vT.T).cpu(), torch.eye(k), atol=1e-4)
+
+
+def test_probe_split_by_operand_type():
+    """The roofline probes (bench.py): GEMM launches split by operand type add up, and the device path does run kind::f16."""
+    unet = SY.SyntheticUNet("sd_small", upto=("mid", 0), device=DEV)
+    x, t, ctx = SY.synthetic_inputs("sd_small")
+    eng = PB.PullbackEngine(PB.unet_config(unet), 32, 32, "mid", 0, 4, ctx.shape[1], DEV)
+    eng.bind(unet.state_dict())
+    torch.manual_seed(0)
+    V0 = PO.initial_subspace(x.numel(), 4)
+    eng.set_point(x, float(t), ctx)
+    eng.pullback(V0, 2, 2, 0.0)                                   # warm (one-time kernel attribute setup)
+    eng.profile_begin()
+    eng.pullback(V0, 2, 2, 0.0)
+    prof = eng.profile_read()
+    ms, fl, n = prof["gemm_tc_kernel"]
+    ms32, fl32, n32 = prof["gemm_tc_kernel[kind::tf32]"]
+    ms16, fl16, n16 = prof["gemm_tc_kernel[kind::f16]"]
+    assert n > 0 and n16 > 0 and n32 > 0 and n32 + n16 == n and abs(fl32 + fl16 - fl) <= 1e-9 * fl
+    assert ms > 0 and abs(ms32 + ms16 - ms) <= 1e-3 * ms
