@@ -223,6 +223,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // descriptor fetches overlap the prologue: operands by the producer lane, output / residual / scratch by the store thread
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&p.mapA[0]); prefetch_tmap(&p.mapB[0]);
+    if (p.nseg > 1) { prefetch_tmap(&p.mapA[1]); prefetch_tmap(&p.mapB[1]); }
+  } else if (threadIdx.x == 64) {
+    if (p.epi_tma) prefetch_tmap(&p.mapD);
+    if (p.R != nullptr && p.epi_tma) prefetch_tmap(&p.mapR);
+    if (p.splits > 1) prefetch_tmap(&p.mapW);
+  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
@@ -398,7 +407,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         }
       }
     }
-    if (t0) bulk_wait<0>();
+    // the staging buffers must have been read before the CTA exits; the global writes themselves complete with the kernel
+    // (every consumer of D or of the split-K scratch is a later kernel in the stream)
+    if (t0) bulk_wait_read<0>();
     tcgen05_fence_before();
   }
   __syncthreads();
