@@ -109,6 +109,10 @@ def _declare(L):
     L.pb_bind_weights.argtypes = [vp, C.POINTER(PbTensorDesc), i32, vp, vp]
     L.pb_set_point.argtypes = [vp, vp, f32, vp, vp, vp, vp, vp]
     L.pb_jvp.argtypes = [vp, vp, i32, vp, vp]
+    L.pb_set_slots.argtypes = [vp, i32, C.c_size_t]
+    L.pb_set_slots.restype = C.c_int
+    L.pb_select_slot.argtypes = [vp, i32]
+    L.pb_select_slot.restype = C.c_int
     L.pb_vjp.argtypes = [vp, vp, i32, vp, vp]
     L.pb_orthonormalize.argtypes = [vp, vp, vp, i32, f32, vp, vp, vp, vp]
     L.pb_pullback.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp, C.POINTER(PbIterInfo), vp]

@@ -44,6 +44,7 @@ struct Val {                 // one activation tensor, [rows][C] per image (NHWC
   // fp16-operand policy (analyse_f16): the JVP tangent / the VJP cotangent of this tensor is produced by an elementwise
   // kernel for exactly one consumer, a GEMM that reads it as its A operand, and is stored as halves in the same buffer
   bool t16 = false, g16 = false;
+  bool d16 = false;          // the JVP tangent is written as halves by its producer GEMM (Op::d16_jvp)
 };
 
 enum WKind { WK_VEC, WK_RAW, WK_LIN, WK_CONV3, WK_CONV3_S2 };
@@ -123,11 +124,25 @@ struct pb_handle {
   bool profiling = false;
   std::vector<Probe> probes;
 
-  float* P(int v) const { return reinterpret_cast<float*>(cache + vals[v].p_off); }
+  // Problem slots (pb_set_slots): `slots` independent problems (x_t, t, ctx) share the weights and run their k_slot tangent
+  // columns as ONE batch of slots * k_slot images.  Each slot has its own primal cache (cache + slot * cache_stride); a tangent
+  // buffer holds the slots back to back ([slot][column][rows][C]), so the weight GEMMs and the data-movement kernels take the
+  // whole batch in one launch while the ops that read primal quantities run once per slot on their k_slot images.
+  int slots = 1, slot = 0, k_slot = 0;
+  size_t cache_stride = 0;
+  bool pass_vjp = false;                      // element size of a tangent buffer: Val::t16 (JVP) / Val::g16 (VJP)
+  std::vector<char> slot_point;               // pb_set_point done for slot i
+
+  float* P(int v) const { return reinterpret_cast<float*>(cache + slot * cache_stride + vals[v].p_off); }
   // VJP only: cotangent buffer of val v may be another val's buffer handed over without a copy (residual fan-in, run_gemm_bwd)
   std::vector<int> alias;
-  float* T(int v) const { return reinterpret_cast<float*>(work + vals[alias.empty() ? v : alias[v]].t_off); }
-  float* CP(size_t off) const { return reinterpret_cast<float*>(cache + off); }
+  float* T(int v) const {
+    const Val& a = vals[alias.empty() ? v : alias[v]];
+    size_t off = a.t_off;
+    if (slot) off += (size_t)slot * k_slot * a.rows * a.C * ((pass_vjp ? vals[v].g16 : (vals[v].t16 || vals[v].d16)) ? 2 : 4);
+    return reinterpret_cast<float*>(work + off);
+  }
+  float* CP(size_t off) const { return reinterpret_cast<float*>(cache + slot * cache_stride + off); }
   float* WP(size_t off) const { return reinterpret_cast<float*>(work + off); }
   float* Wf(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].fwd_off); }
   float* Wb(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].bwd_off); }
@@ -452,7 +467,7 @@ void analyse_f16(pb_handle* h) {
     }
     if (o.a16_jvp && (mask & 2) && !o.conv && o.res < 0 && consumers[o.y] == 1)
       for (const Op& c : h->ops)
-        if (c.kind == OP_GEGLU && c.x == o.y) o.d16_jvp = 1;    // ff1 -> GEGLU: the widest tensor of a transformer block
+        if (c.kind == OP_GEGLU && c.x == o.y) { o.d16_jvp = 1; h->vals[o.y].d16 = true; }    // ff1 -> GEGLU: the widest tensor of a transformer block
     if ((mask & 4) && o.res < 0 && consumers[o.y] == 1) {
       for (const Op& c : h->ops)
         if (c.x == o.y && elementwise(c.kind, true)) { o.a16_vjp = 1; h->vals[o.y].g16 = true; }
@@ -897,9 +912,12 @@ int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h
   return PB_OK;
 }
 
-int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
-  h->rnd = h->rnd_t;
-  for (const Op& o : h->ops) {
+// ops that read primal quantities (normalisation statistics, activation arguments, attention probabilities): with several
+// problem slots they run once per slot; everything else (weight GEMMs, data movement) takes all slots in one launch
+bool per_slot_op(int kind) { return kind == OP_GN || kind == OP_LN || kind == OP_GEGLU || kind == OP_ATTN; }
+
+int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_stream st) {
+  {
     switch (o.kind) {
       case OP_IN: {
         const Val& v = h->vals[o.y];
@@ -953,15 +971,25 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
   return PB_OK;
 }
 
-int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
-  h->rnd = h->rnd_t;
-  for (Val& v : h->vals) v.ginit = false;
-  h->alias.resize(h->vals.size());
-  for (size_t i = 0; i < h->alias.size(); ++i) h->alias[i] = (int)i;
-  struct Unalias { pb_handle* h; ~Unalias() { h->alias.clear(); } } unalias{h};       // the JVP / primal see every val's own buffer
-  for (size_t i = h->ops.size(); i-- > 0;) {
-    const Op& o = h->ops[i];
-    if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
+struct SlotGuard { pb_handle* h; ~SlotGuard() { h->slot = 0; } };
+
+int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
+  h->rnd = h->rnd_t; h->pass_vjp = false; h->k_slot = nb / h->slots;
+  SlotGuard guard{h};
+  for (const Op& o : h->ops) {
+    if (h->slots > 1 && per_slot_op(o.kind)) {
+      for (int p = 0; p < h->slots; ++p) {
+        h->slot = p;
+        if (int e = jvp_op(h, o, V, h->k_slot, U, st)) return e;
+      }
+      h->slot = 0;
+    } else if (int e = jvp_op(h, o, V, nb, U, st)) return e;
+  }
+  return PB_OK;
+}
+
+int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_stream st) {
+  {
     switch (o.kind) {
       case OP_OUT: {
         Val& v = h->vals[o.x];
@@ -1029,6 +1057,29 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
   return PB_OK;
 }
 
+int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
+  h->rnd = h->rnd_t; h->pass_vjp = true; h->k_slot = nb / h->slots;
+  SlotGuard guard{h};
+  for (Val& v : h->vals) v.ginit = false;
+  h->alias.resize(h->vals.size());
+  for (size_t i = 0; i < h->alias.size(); ++i) h->alias[i] = (int)i;
+  struct Unalias { pb_handle* h; ~Unalias() { h->alias.clear(); } } unalias{h};       // the JVP / primal see every val's own buffer
+  for (size_t i = h->ops.size(); i-- > 0;) {
+    const Op& o = h->ops[i];
+    if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
+    if (h->slots > 1 && per_slot_op(o.kind)) {
+      const bool had = h->vals[o.x].ginit;               // every slot sees the bookkeeping state the op started from
+      for (int p = 0; p < h->slots; ++p) {
+        h->slot = p;
+        h->vals[o.x].ginit = had;
+        if (int e = vjp_op(h, o, U, h->k_slot, Wout, st)) return e;
+      }
+      h->slot = 0;
+    } else if (int e = vjp_op(h, o, U, nb, Wout, st)) return e;
+  }
+  return PB_OK;
+}
+
 int run_ortho(pb_handle* h, const float* Wm, const float* Vprev, int k, float atol, float* V, float* s, float* metrics, pb_stream st) {
   double* G = reinterpret_cast<double*>(h->work + h->w_G);
   double* M = reinterpret_cast<double*>(h->work + h->w_M);
@@ -1042,8 +1093,10 @@ int check_ready(pb_handle* h, int k, bool need_point) {
   if (!h) return PB_EINVAL;
   if (!h->planned) return fail(h, PB_ESTATE, "pb_plan has not been called");
   if (!h->bound) return fail(h, PB_ESTATE, "pb_bind_weights has not been called");
-  if (need_point && !h->point) return fail(h, PB_ESTATE, "pb_set_point has not been called");
+  if (need_point && !h->point) return fail(h, PB_ESTATE, h->slots > 1 ? "pb_set_point has not been called for every problem slot"
+                                                                       : "pb_set_point has not been called");
   if (k < 1 || k > h->kmax) return fail(h, PB_EINVAL, "pca_rank must be in [1, k_max]");
+  if (need_point && h->slots > 1 && k % h->slots) return fail(h, PB_EINVAL, "the column count must be a multiple of the problem slots");
   return PB_OK;
 }
 
@@ -1264,7 +1317,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->w_V = p.work_alloc(K * h->n_in); h->w_Vprev = p.work_alloc(K * h->n_in); h->w_W = p.work_alloc(K * h->n_in);
   h->w_U = p.work_alloc(K * h->n_out);
   h->w_G = p.work_alloc(2 * K * K); h->w_M = p.work_alloc(2 * K * K); h->w_R = p.work_alloc(K * K);
-  h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4);
+  h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4 + 2 * K);      // (dist^2, not-close count) per problem slot
   h->w_x = p.work_alloc((size_t)h->n_in);
   h->n_splitk = kSplitFloats; h->w_splitk = p.work_alloc(kSplitFloats);
   h->w_cvt = p.work_alloc((h->n_cvt * K + 1) / 2);          // halves
@@ -1329,15 +1382,45 @@ PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n,
   return PB_OK;
 }
 
+// Problem slots: `slots` independent problems share this handle's weights and run their tangent columns as one batch (see
+// pb_handle::slots).  k_max of pb_plan must be a multiple of `slots` (k_max / slots columns per problem); the primal cache
+// handed to pb_set_point is `slots` caches of cache_stride_bytes (>= pb_sizes::primal_cache_bytes, 256-byte multiple) each.
+PB_API int pb_set_slots(pb_handle* h, int32_t slots, size_t cache_stride_bytes) {
+  if (!h) return PB_EINVAL;
+  if (!h->planned) return fail(h, PB_ESTATE, "pb_plan has not been called");
+  if (slots < 1 || h->kmax % slots) return fail(h, PB_EINVAL, "slots must divide k_max");
+  if (slots > 1 && (cache_stride_bytes < h->sizes.primal_cache_bytes || cache_stride_bytes % 256))
+    return fail(h, PB_EINVAL, "cache_stride_bytes must be a 256-byte multiple >= primal_cache_bytes");
+  drop_graph(h);
+  h->slots = slots; h->slot = 0; h->cache_stride = slots > 1 ? cache_stride_bytes : 0;
+  h->slot_point.assign(slots, 0); h->point = false;
+  return PB_OK;
+}
+// The slot the next pb_set_point fills (0 .. slots - 1).
+PB_API int pb_select_slot(pb_handle* h, int32_t slot) {
+  if (!h) return PB_EINVAL;
+  if (slot < 0 || slot >= h->slots) return fail(h, PB_EINVAL, "slot out of range");
+  h->slot = slot;
+  return PB_OK;
+}
+
 PB_API int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx, void* primal_cache, void* workspace, float* h_out,
                         void* stream) {
   if (int e = check_ready(h, 1, false)) return e;
   if (!x || !primal_cache || !workspace) return fail(h, PB_EINVAL, "null pointer");
+  const int slot = h->slot;                       // chosen by pb_select_slot; back to 0 afterwards
+  SlotGuard guard{h};
   h->point = false;
-  if (h->cache != primal_cache || h->work != workspace) drop_graph(h);
+  if (h->cache != primal_cache || h->work != workspace) {
+    drop_graph(h);
+    h->slot_point.assign(h->slots, 0);
+  }
   h->cache = static_cast<char*>(primal_cache); h->work = static_cast<char*>(workspace);
+  if ((int)h->slot_point.size() != h->slots) h->slot_point.assign(h->slots, 0);
+  h->slot_point[slot] = 0;
   if (int e = run_primal(h, x, t, ctx, h_out, stream)) return e;
-  h->point = true;
+  h->slot_point[slot] = 1;
+  h->point = std::all_of(h->slot_point.begin(), h->slot_point.end(), [](char c) { return c != 0; });
   return PB_OK;
 }
 
@@ -1364,22 +1447,29 @@ PB_API int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, i
 
 PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u, float* s,
                        float* vT, pb_iter_info* info, void* stream) {
-  if (int e = check_ready(h, k, true)) return e;
+  // with problem slots, k is the rank PER PROBLEM: V0 / vT are [slots][k][n_in], u is [slots][k][n_out], s is [slots][k]; every
+  // problem runs the same number of iterations (the early exit needs all of them converged at the same check)
+  const int P = h->slots, kt = k * P;
+  if (int e = check_ready(h, kt, true)) return e;
   if (!V0 || !u || !s || !vT) return fail(h, PB_EINVAL, "null pointer");
   if (max_iter < 1) return fail(h, PB_EINVAL, "max_iter must be >= 1");
+  if (P > 64) return fail(h, PB_EINVAL, "at most 64 problem slots");
   float* Va = h->WP(h->w_V); float* Vb = h->WP(h->w_Vprev);
   float* Wm = h->WP(h->w_W); float* met = h->WP(h->w_met);
-  const size_t vbytes = (size_t)k * h->n_in * 4;
+  const size_t vbytes = (size_t)kt * h->n_in * 4;
   CK(pbk_copy(Vb, V0, vbytes, stream));
   // One iteration (utils.py:758-799): Vprev = Vb -> U = J Vprev -> W = U^T J -> (s, Va) = svd(W); then Vb <- Va.
   auto iteration = [&]() -> int {
-    if (int e = run_jvp(h, Vb, k, u, stream)) return e;
-    if (int e = run_vjp(h, u, k, Wm, stream)) return e;
-    if (int e = run_ortho(h, Wm, Vb, k, tol, Va, s, met, stream)) return e;
+    if (int e = run_jvp(h, Vb, kt, u, stream)) return e;
+    if (int e = run_vjp(h, u, kt, Wm, stream)) return e;
+    for (int p = 0; p < P; ++p) {
+      const size_t o = (size_t)p * k * h->n_in;
+      if (int e = run_ortho(h, Wm + o, Vb + o, k, tol, Va + o, s + (size_t)p * k, met + 2 * p, stream)) return e;
+    }
     return PB_OK;
   };
   int done = 0, converged = 0;
-  float host_met[2] = {0.f, 0.f};
+  float host_met[128] = {0.f, 0.f};
   for (int i = 0; i < max_iter; ++i) {
     bool replayed = false;
     if (h->use_graph && !h->profiling) {
@@ -1412,8 +1502,10 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
     const bool last = (i + 1 == max_iter);
     // the reference tests allclose(v_prev, v, atol) and i > min_iter after every iteration (utils.py:806-808)
     if (i > min_iter || last) {
-      CK(pbk_download(host_met, met, sizeof host_met, stream));
-      if (i > min_iter && host_met[1] == 0.f) { converged = 1; }
+      CK(pbk_download(host_met, met, sizeof(float) * 2 * P, stream));
+      bool all_close = true;
+      for (int p = 0; p < P; ++p) all_close = all_close && host_met[2 * p + 1] == 0.f;
+      if (i > min_iter && all_close) { converged = 1; }
     }
     if (converged || last) break;
     CK(pbk_copy(Vb, Va, vbytes, stream));
@@ -1429,6 +1521,7 @@ PB_API int pb_pullback_host(pb_handle* h, const float* x_host, float t, const fl
                             int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
                             pb_iter_info* info, void* stream) {
   if (int e = check_ready(h, k, false)) return e;
+  if (h->slots > 1) return fail(h, PB_ESTATE, "pb_pullback_host runs one problem per call (pb_set_slots(h, 1, 0))");
   if (!h->cache || !h->work) return fail(h, PB_ESTATE, "pb_set_point must have been called once to attach the cache / workspace");
   if (!x_host || !V0_host || !u_host || !s_host || !vT_host) return fail(h, PB_EINVAL, "null pointer");
   float* dx = h->WP(h->w_x);

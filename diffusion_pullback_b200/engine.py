@@ -166,7 +166,18 @@ class PullbackEngine:
             self.stream.synchronize()          # `keep` may be freed after this
         self.bound = True
 
-    def set_point(self, x, t, ctx=None, want_h=False):
+    def set_slots(self, slots: int):
+        """Throughput mode (pb_set_slots): `slots` independent problems share the weights and run their k_max / slots tangent
+        columns each as one batch.  Re-allocates the primal cache (one per slot)."""
+        slots = int(slots)
+        stride = (int(self.sizes.primal_cache_bytes) + 255) // 256 * 256
+        self._ck(self.L.pb_set_slots(self.h, slots, stride if slots > 1 else 0))
+        self.slots = slots
+        self.cache = torch.zeros(max(stride * slots, 16), dtype=torch.uint8, device=self.device)
+
+    def set_point(self, x, t, ctx=None, want_h=False, slot=0):
+        if slot:
+            self._ck(self.L.pb_select_slot(self.h, int(slot)))
         x = self._f32(x, (-1,))
         assert x.numel() == self.n_in, "x_t shape does not match the planned geometry"
         if ctx is not None:
@@ -208,12 +219,14 @@ class PullbackEngine:
         return s, V, met
 
     def pullback(self, V0, min_iter, max_iter, tol):
-        """utils.py:756-808 on the device: returns (u [k, n_out], s [k], vT [k, n_in], info)."""
+        """utils.py:756-808 on the device: returns (u [k, n_out], s [k], vT [k, n_in], info).  With problem slots V0 is
+        [slots * k, n_in] (slot-major) and so are the results."""
         V0 = self._f32(V0, (-1, self.n_in))
-        k = V0.shape[0]
-        u = torch.empty(k, self.n_out, device=self.device)
-        s = torch.empty(k, device=self.device)
-        vT = torch.empty(k, self.n_in, device=self.device)
+        kt = V0.shape[0]
+        k = kt // getattr(self, "slots", 1)
+        u = torch.empty(kt, self.n_out, device=self.device)
+        s = torch.empty(kt, device=self.device)
+        vT = torch.empty(kt, self.n_in, device=self.device)
         info = N.PbIterInfo()
         self._enter()
         self._ck(self.L.pb_pullback(self.h, self._p(V0), k, int(min_iter), int(max_iter), float(tol), self._p(u), self._p(s),

@@ -95,6 +95,15 @@ int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n, void* 
 int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx, void* primal_cache, void* workspace,
                  float* h_out, void* stream);
 
+/* Problem slots (throughput mode; the reference solves its problems one process after another, scripts of SURVEY.md s.3.1):
+ * `slots` independent problems (x_t, t, ctx) share the handle's weights and run their tangent columns as ONE batch, so the
+ * weight GEMMs see M = HW * k * slots.  k_max of pb_plan must be a multiple of `slots`; the region handed to pb_set_point as
+ * `primal_cache` is then `slots` caches of cache_stride_bytes each.  pb_select_slot picks the slot the next pb_set_point
+ * fills; pb_pullback takes the rank PER PROBLEM with V0 / vT [slots][k][n_in], u [slots][k][n_out], s [slots][k], and every
+ * problem runs the same number of iterations (early exit only when all have converged).  slots = 1 (default): unchanged. */
+int pb_set_slots(pb_handle* h, int32_t slots, size_t cache_stride_bytes);
+int pb_select_slot(pb_handle* h, int32_t slot);
+
 /* U[k][n_out] = J V,  V: [k][n_in]   (both NCHW-flattened rows; replaces the jacfwd call, utils.py:766-775) */
 int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream);
 /* W[k][n_in] = U^T J, U: [k][n_out]  (replaces autograd.functional.jacobian, utils.py:790-797) */

@@ -302,3 +302,42 @@ def test_probe_bookkeeping_and_dump(hostsim, tmp_path, monkeypatch):
     lines = dump.read_text().strip().splitlines()
     assert len(lines) == n + na and sum(l.split(" GF ")[1].startswith("gemm M=") for l in lines) == n
     assert sum("ab16=1" in l for l in lines) == n16
+
+
+@pytest.mark.parametrize("name,op,bi", [("sd_tiny", "mid", 0), ("sd_tiny", "up", 1), ("uncond_tiny", "mid", 0)])
+def test_problem_slots_match_one_problem_at_a_time(hostsim, name, op, bi):
+    """pb_set_slots: three independent problems (different x_t, t, prompt) batched through one handle give, per problem, what
+    the same handle gives one problem at a time (JVP, VJP and the whole iteration)."""
+    P, k, iters = 3, 2, 3
+    eng, m, x, t, ctx = make_engine(hostsim, name, op, bi, P * k, EXACT)
+    g = torch.Generator().manual_seed(5)
+    xs = [x] + [torch.randn(x.shape, generator=g) for _ in range(P - 1)]
+    ts = [float(t), 301.0, 850.5]
+    cs = [ctx] + [torch.randn(ctx.shape, generator=g) for _ in range(P - 1)] if ctx is not None else [None] * P
+    torch.manual_seed(0)
+    V0 = torch.cat([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0)
+    G = None
+    single = []
+    for p in range(P):                                               # one problem at a time (slots = 1)
+        eng.set_point(xs[p], ts[p], cs[p])
+        Up = eng.jvp(V0[p * k:(p + 1) * k])
+        if G is None:
+            G = torch.randn(P * k, Up.shape[1], generator=g)
+        Wp = eng.vjp(G[p * k:(p + 1) * k])
+        single.append((Up, Wp) + tuple(eng.pullback(V0[p * k:(p + 1) * k], iters, iters, 0.0)[:3]))
+    eng.set_slots(P)
+    for p in range(P):
+        eng.set_point(xs[p], ts[p], cs[p], slot=p)
+    U, W = eng.jvp(V0), eng.vjp(G)
+    u, s, vT, info = eng.pullback(V0, iters, iters, 0.0)
+    assert info.iters_done == iters
+    for p in range(P):
+        sl = slice(p * k, (p + 1) * k)
+        Up, Wp, up, sp, vp = single[p]
+        assert rel(U[sl], Up) < 1e-6 and rel(W[sl], Wp) < 1e-6
+        assert rel(s[sl], sp) < 1e-5 and rel(u[sl], up) < 1e-4 and rel(vT[sl], vp) < 1e-4
+    with pytest.raises(ValueError):
+        eng.jvp(V0[:P * k - 1])                                      # the column count must be a multiple of the slots
+    eng.set_slots(1)                                                 # back to one problem per call
+    eng.set_point(xs[1], ts[1], cs[1])
+    assert rel(eng.jvp(V0[k:2 * k]), single[1][0]) < 1e-6
