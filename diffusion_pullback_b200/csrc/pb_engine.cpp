@@ -206,7 +206,7 @@ struct Planner {
   Op& push(OpKind k) { h->ops.emplace_back(); h->ops.back().kind = k; return h->ops.back(); }
 
   int gn(int x, const std::string& p, float eps, int silu) {
-    const Val& vx = h->vals[x];
+    const Val vx = h->vals[x];                       // by value: val() below may reallocate h->vals
     const int G = h->cfg.norm_num_groups;
     if (vx.C % G || vx.C % 4) { error = "GroupNorm channels must divide into groups and be a multiple of 4"; return -1; }
     int y = val(vx.rows, vx.C);
