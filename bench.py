@@ -211,8 +211,16 @@ def run_ours(args, wl):
     unet = SY.SyntheticUNet(model_name, upto=(op, bi), device=dev)
     cfg = PB.unet_config(unet)
     size, ctx_len = unet.config["sample_size"], unet.config["ctx_len"]
+    S = max(1, args.slots)                                   # problems per step (batched through pb_set_slots when > 1)
+    if S > 1 and (args.shard == "tangent" or S * k > 64):
+        raise SystemExit("bench.py: --slots needs problem sharding and slots * pca_rank <= 64")
     eng = PB.PullbackEngine(cfg, size, size, op, bi, k, ctx_len, dev)
     eng.bind(unet.state_dict())
+    engS = None
+    if S > 1:
+        engS = PB.PullbackEngine(cfg, size, size, op, bi, S * k, ctx_len, dev)
+        engS.bind(unet.state_dict())
+        engS.set_slots(S)
     unet._sd = None                                          # packed copy lives in the engine now
     torch.cuda.empty_cache()
     _, t, ctx = SY.synthetic_inputs(model_name)
@@ -221,7 +229,7 @@ def run_ours(args, wl):
     tangent = args.shard == "tangent" and world > 1          # every rank works on the SAME problem and owns k / world of its columns
     prank = 0 if tangent else rank
     xs, v0s = [], []
-    for i in range(K + Wm):
+    for i in range((K + Wm) * S):
         g = torch.Generator().manual_seed(1234 + 1000 * i + prank)
         xs.append(torch.randn(1, cfg["in_channels"], size, size, generator=g))
         g2 = torch.Generator().manual_seed(i * world + prank)
@@ -233,6 +241,11 @@ def run_ours(args, wl):
     results = []
 
     def step(i):
+        if S > 1:                                            # S problems, one tangent batch of S * k columns
+            for p in range(S):
+                engS.set_point(xd[i * S + p], tval, ctxd, slot=p)
+            u, s, vT, info = engS.pullback(torch.cat(v0d[i * S:(i + 1) * S], 0), iters, iters, 0.0)
+            return s, vT
         eng.set_point(xd[i], tval, ctxd)
         if tangent:
             from diffusion_pullback_b200.sharding import pullback_tangent_sharded
@@ -251,7 +264,7 @@ def run_ours(args, wl):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = eng.launches
+    l0 = engS.launches if S > 1 else eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -265,13 +278,13 @@ def run_ours(args, wl):
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    launches = eng.launches - l0
+    launches = (engS.launches if S > 1 else eng.launches) - l0
     if world > 1:
         tmax = torch.tensor([ms], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax)
     secs = ms / 1e3
-    nprob = K if tangent else world * K                       # problems solved by the whole job
+    nprob = K if tangent else world * K * S                   # problems solved by the whole job
     value = nprob * iters / secs
 
     # ---- e2e: the C-ABI host entry with pinned host buffers, H2D / D2H inside the timed region ----
@@ -326,7 +339,7 @@ def run_ours(args, wl):
         peak_tf, peak_hbm, peak_src = peaks()
         flops_iter = 2.0 * k * f_tan * 1e9
         step_flops = flops_iter * iters + f_primal * 1e9
-        achieved = step_flops * K / secs / 1e12 if f_tan else None
+        achieved = step_flops * K * S / secs / 1e12 if f_tan else None
         kernels = {}
         for name in ("gemm_tc_kernel", "attn_lin_kernel"):
             kms, kfl, kn = prof[name]
@@ -350,9 +363,10 @@ def run_ours(args, wl):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "f16/tf32 operands, f32 accumulate", "data": "synthetic",
                 "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,
-                           "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K,
+                           "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K * S, "slots": S,
                            "parallelism": (f"tangent-sharded x{world} (k columns of one problem split over the ranks, one all-gather of W per iteration)"
-                                           if tangent else f"problem-sharded x{world}"), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
+                                           if tangent else f"problem-sharded x{world}") +
+                                          (f"; {S} problems per step batched through pb_set_slots (value), e2e and kernel probes one problem per call" if S > 1 else ""), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
                            "column_iters_per_s": value * k},
                 "clocks": clocks,
                 "e2e": {"value": (world if not tangent else 1) * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -388,6 +402,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=1,
+                    help="problem slots (pb_set_slots): each step solves this many independent problems as ONE tangent batch "
+                         "(throughput mode; default 1 = one problem per step, the reference's granularity)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the reference arm) or cuda (torch eager autograd on this box's GPU, SURVEY s.8d-ii)")
     ap.add_argument("--shard", default="problem", choices=["problem", "tangent"],

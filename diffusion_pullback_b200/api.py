@@ -136,14 +136,59 @@ def local_encoder_pullback_xt(self, x, t, op=None, block_idx=None, pca_rank=50, 
                      tangent_group)
 
 
+@torch.no_grad()
+def local_encoder_pullback_many(self, samples, timesteps, encoder_hidden_states=None, op=None, block_idx=None, pca_rank=50,
+                                min_iter=10, max_iter=100, convergence_threshold=1e-3, v0=None):
+    """Extension (throughput mode, no counterpart in the reference, which solves its problems one process after another --
+    `src/scripts/*.sh`, `main.py:71-76`): P independent problems of the same geometry in one call.  `samples` [P, C, H, W],
+    `timesteps` P values, `encoder_hidden_states` [P, L, D] (or None for the unconditional family), `v0` optional
+    [P, k, n_in].  The problems share the packed weights and run their k tangent columns each as one batch of P * k images
+    (pb_set_slots): weight GEMMs and data movement in one launch over all problems, primal-dependent ops once per problem.
+    Every problem runs the same number of iterations (the early exit needs all of them converged at the same check).
+    Returns a list of P tuples (u [n_out, k], s [k], vT [k, n_in])."""
+    P, k = samples.shape[0], int(pca_rank)
+    ctx = encoder_hidden_states
+    ctx_len = ctx.shape[1] if ctx is not None else 0
+    if samples.device.type != "cuda":
+        raise RuntimeError("diffusion_pullback_b200 runs on a CUDA (sm_100a) device only (no CPU fallback exists)")
+    if P * k > 64:
+        raise ValueError("P * pca_rank must be <= 64 (k_max of one handle)")
+    engines = self.__dict__.setdefault("_pb200_slot_engines", {})
+    key = (samples.device.index, samples.shape[2], samples.shape[3], op, block_idx, ctx_len, P, k)
+    eng = engines.get(key)
+    if eng is None:
+        eng = PullbackEngine(unet_config(self), samples.shape[2], samples.shape[3], op, block_idx, P * k, ctx_len, samples.device)
+        eng.bind(self.state_dict())
+        eng.set_slots(P)
+        engines[key] = eng
+    return _pullback_many_on(eng, samples, timesteps, ctx, k, min_iter, max_iter, convergence_threshold, v0)
+
+
+def _pullback_many_on(eng, samples, timesteps, ctx, k, min_iter, max_iter, convergence_threshold, v0=None):
+    """The body of `local_encoder_pullback_many` on an engine whose slots are set (one per sample)."""
+    P, n_in = samples.shape[0], samples[0].numel()
+    if v0 is None:
+        v0 = []
+        for _ in range(P):                       # per problem the reference's own start (utils.py:750-752)
+            q, _ = torch.linalg.qr(torch.randn(n_in, k, device=samples.device, dtype=torch.float))
+            v0.append(q.T)
+        v0 = torch.stack(v0, 0)
+    for p in range(P):
+        eng.set_point(samples[p:p + 1], _timestep(timesteps[p]), None if ctx is None else ctx[p:p + 1], slot=p)
+    u, s, vT, info = eng.pullback(v0.reshape(P * k, n_in), min_iter, max_iter, convergence_threshold)
+    return [(u[p * k:(p + 1) * k].T, s[p * k:(p + 1) * k], vT[p * k:(p + 1) * k]) for p in range(P)]
+
+
 def patch_unet(unet):
     """The monkey-patch of `utils.py:103-104` (uncond) / `:326`, `:333` (Stable Diffusion)."""
     if hasattr(unet, "up_blocks") and unet_config(unet)["kind"] == 0:
         unet.get_h = types.MethodType(get_h, unet)
         unet.local_encoder_pullback_zt = types.MethodType(local_encoder_pullback_zt, unet)
+        unet.local_encoder_pullback_many = types.MethodType(local_encoder_pullback_many, unet)
         unet.eps = types.MethodType(eps, unet)
     else:
         unet.get_h = types.MethodType(get_h_uncond, unet)
         unet.local_encoder_pullback_xt = types.MethodType(local_encoder_pullback_xt, unet)
+        unet.local_encoder_pullback_many = types.MethodType(local_encoder_pullback_many, unet)
         unet.eps = types.MethodType(eps_uncond, unet)
     return unet

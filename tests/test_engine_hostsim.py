@@ -341,3 +341,28 @@ def test_problem_slots_match_one_problem_at_a_time(hostsim, name, op, bi):
     eng.set_slots(1)                                                 # back to one problem per call
     eng.set_point(xs[1], ts[1], cs[1])
     assert rel(eng.jvp(V0[k:2 * k]), single[1][0]) < 1e-6
+
+
+def test_pullback_many_body_matches_single_calls(hostsim):
+    """`local_encoder_pullback_many` (api.py): its body on a slotted engine against per-problem calls; also the RNG draw of
+    the default start (one randn + QR per problem, like utils.py:750-752)."""
+    from diffusion_pullback_b200.api import _pullback_many_on
+    P, k, iters = 2, 2, 2
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, P * k, EXACT)
+    g = torch.Generator().manual_seed(9)
+    xs = torch.cat([x, torch.randn(x.shape, generator=g)], 0)
+    cs = torch.cat([ctx, torch.randn(ctx.shape, generator=g)], 0)
+    ts = [float(t), 420.0]
+    torch.manual_seed(3)
+    v0 = torch.stack([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0)
+    single = []
+    for p in range(P):
+        eng.set_point(xs[p:p + 1], ts[p], cs[p:p + 1])
+        single.append(eng.pullback(v0[p], iters, iters, 0.0))
+    eng.set_slots(P)
+    torch.manual_seed(3)
+    out = _pullback_many_on(eng, xs, ts, cs, k, iters, iters, 0.0)          # default start: same draws as v0 above
+    for p in range(P):
+        u, s, vT = out[p]
+        up, sp, vp, _ = single[p]
+        assert u.shape == (up.shape[1], k) and rel(s, sp) < 1e-5 and rel(vT, vp) < 1e-4 and rel(u.T, up) < 1e-4
