@@ -214,7 +214,9 @@ struct Planner {
     o.x = x; o.y = y; o.eps = eps; o.silu = silu; o.groups = G;
     o.gamma = vec(p + ".weight", h->vals[x].C); o.beta = vec(p + ".bias", h->vals[x].C);
     o.mean_off = cache_alloc(G); o.rstd_off = cache_alloc(G);
-    h->n_gn = std::max(h->n_gn, std::max(pbk_gn_tmp_floats((int)vx.rows, vx.C, G, h->kmax), pbk_gn_tmp_floats((int)vx.rows, vx.C, G, 1)));
+    // the scratch of the chunked path is not monotone in the image count (chunk count x images), and the op may run on any
+    // number of images up to k_max (primal pass: 1; problem slots: k_max / slots)
+    for (int nb = 1; nb <= h->kmax; ++nb) h->n_gn = std::max(h->n_gn, pbk_gn_tmp_floats((int)vx.rows, vx.C, G, nb));
     return y;
   }
   int ln(int x, const std::string& p) {
