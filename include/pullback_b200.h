@@ -115,7 +115,8 @@ int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t 
                       float* metrics, void* stream);
 
 /* The whole loop of utils.py:756-808: V0 [k][n_in] -> u [k][n_out] (the reference returns its transpose view),
- * s [k], vT [k][n_in].  Device pointers; info is host memory. */
+ * s [k], vT [k][n_in].  Device pointers; info is host memory.  With problem slots (pb_set_slots) k is the rank per problem
+ * and every buffer is slot-major: V0 / vT [slots][k][n_in], u [slots][k][n_out], s [slots][k]. */
 int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u,
                 float* s, float* vT, pb_iter_info* info, void* stream);
 
