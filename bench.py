@@ -292,7 +292,16 @@ def run_ours(args, wl):
     v0h = [v.pin_memory() for v in v0s]
     ctxh = ctx.contiguous().pin_memory() if ctx is not None else None
     out = (torch.empty(k, eng.n_out).pin_memory(), torch.empty(k).pin_memory(), torch.empty(k, eng.n_in).pin_memory())
+    if S > 1:                                                # host buffers of S problems per step (pb_pullback_host_slots)
+        xhS = [torch.cat([xs[i * S + p].reshape(1, -1) for p in range(S)], 0).contiguous().pin_memory() for i in range(K + Wm)]
+        v0hS = [torch.cat(v0s[i * S:(i + 1) * S], 0).contiguous().pin_memory() for i in range(K + Wm)]
+        ctxhS = ctx.repeat(S, 1, 1).contiguous().pin_memory() if ctx is not None else None
+        outS = (torch.empty(S * k, eng.n_out).pin_memory(), torch.empty(S * k).pin_memory(), torch.empty(S * k, eng.n_in).pin_memory())
+
     def e2e_step(i):
+        if S > 1:
+            engS.pullback_host(xhS[i], [tval] * S, ctxhS, v0hS[i], iters, iters, 0.0, out=outS)
+            return
         if not tangent:
             eng.pullback_host(xh[i], tval, ctxh, v0h[i], iters, iters, 0.0, out=out)
             return
@@ -318,8 +327,8 @@ def run_ours(args, wl):
         tmax = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_s = float(tmax)
-    h2d = 4 * (eng.n_in + (ctx.numel() if ctx is not None else 0) + k * eng.n_in)
-    d2h = 4 * (k * eng.n_out + k + k * eng.n_in)
+    h2d = 4 * S * (eng.n_in + (ctx.numel() if ctx is not None else 0) + k * eng.n_in)
+    d2h = 4 * S * (k * eng.n_out + k + k * eng.n_in)
 
     # ---- per-kernel timing: two eagerly launched iterations with an event pair around every contraction launch ----
     prof, prof_iters = None, 2
@@ -366,10 +375,10 @@ def run_ours(args, wl):
                            "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K * S, "slots": S,
                            "parallelism": (f"tangent-sharded x{world} (k columns of one problem split over the ranks, one all-gather of W per iteration)"
                                            if tangent else f"problem-sharded x{world}") +
-                                          (f"; {S} problems per step batched through pb_set_slots (value), e2e and kernel probes one problem per call" if S > 1 else ""), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
+                                          (f"; {S} problems per step batched through pb_set_slots (value and e2e; the kernel probes time one problem per call)" if S > 1 else ""), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
                            "column_iters_per_s": value * k},
                 "clocks": clocks,
-                "e2e": {"value": (world if not tangent else 1) * K * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": (world if not tangent else 1) * K * S * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
                              "peak": peak_tf, "unit": "TFLOP/s",

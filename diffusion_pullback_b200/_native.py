@@ -118,6 +118,8 @@ def _declare(L):
     L.pb_pullback.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp, C.POINTER(PbIterInfo), vp]
     L.pb_pullback_host.argtypes = [vp, vp, f32, vp, vp, i32, i32, i32, f32, vp, vp, vp,
                                    C.POINTER(PbIterInfo), vp]
+    L.pb_pullback_host_slots.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp, vp, C.POINTER(PbIterInfo), vp]
+    L.pb_pullback_host_slots.restype = C.c_int
     L.pb_kernel_launches.argtypes = [vp]
     L.pb_kernel_launches.restype = C.c_int64
     L.pb_weight_count.argtypes = [vp]

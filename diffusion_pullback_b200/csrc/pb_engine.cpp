@@ -1519,34 +1519,62 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
 
 // The same call with HOST buffers (what a host-language binding of the reference's method would hand over):
 // copies x_t / ctx / V0 in, runs the primal pass and the iteration, copies (u, s, vT) out.  Blocking.
-PB_API int pb_pullback_host(pb_handle* h, const float* x_host, float t, const float* ctx_host, const float* V0_host, int32_t k,
-                            int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
-                            pb_iter_info* info, void* stream) {
-  if (int e = check_ready(h, k, false)) return e;
-  if (h->slots > 1) return fail(h, PB_ESTATE, "pb_pullback_host runs one problem per call (pb_set_slots(h, 1, 0))");
+// With problem slots: x [slots][n_in], t [slots], ctx [slots][ctx_len][dim], V0 / vT [slots][k][n_in], u [slots][k][n_out], s [slots][k].
+static int pullback_host_impl(pb_handle* h, const float* x_host, const float* t_host, const float* ctx_host, const float* V0_host, int32_t k,
+                              int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
+                              pb_iter_info* info, void* stream) {
+  const int P = h->slots;
+  const size_t kt = (size_t)k * P;
+  if (int e = check_ready(h, (int)kt, false)) return e;
   if (!h->cache || !h->work) return fail(h, PB_ESTATE, "pb_set_point must have been called once to attach the cache / workspace");
-  if (!x_host || !V0_host || !u_host || !s_host || !vT_host) return fail(h, PB_EINVAL, "null pointer");
-  float* dx = h->WP(h->w_x);
-  float* dctx = nullptr;
-  CK(pbk_upload(dx, x_host, (size_t)h->n_in * 4, stream));
-  if (h->cfg.kind == PB_UNET_COND) {
-    if (!ctx_host) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
-    // staged in the S3 scratch (free until the first attention op runs; run_primal copies it into the cache first)
-    dctx = h->WP(h->w_s3);
-    if ((size_t)h->ctx_len * h->cfg.cross_attention_dim > h->n_s3 * (size_t)h->kmax)
-      return fail(h, PB_ESTATE, "internal: scratch too small for the text context");
-    CK(pbk_upload(dctx, ctx_host, (size_t)h->ctx_len * h->cfg.cross_attention_dim * 4, stream));
-  }
+  if (!x_host || !t_host || !V0_host || !u_host || !s_host || !vT_host) return fail(h, PB_EINVAL, "null pointer");
+  if (h->cfg.kind == PB_UNET_COND && !ctx_host) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
+  const size_t ctx_floats = (size_t)h->ctx_len * h->cfg.cross_attention_dim;
+  if (h->cfg.kind == PB_UNET_COND && ctx_floats > h->n_s3 * (size_t)h->kmax)
+    return fail(h, PB_ESTATE, "internal: scratch too small for the text context");
   h->point = false;
-  if (int e = run_primal(h, dx, t, dctx, nullptr, stream)) return e;
+  h->slot_point.assign(P, 0);
+  {
+    SlotGuard guard{h};
+    for (int p = 0; p < P; ++p) {
+      // staged in the x / S3 scratch (S3 is free until the first attention op runs; run_primal copies the context into the cache
+      // first); the next slot's upload is stream-ordered behind this slot's primal pass
+      float* dx = h->WP(h->w_x);
+      float* dctx = nullptr;
+      CK(pbk_upload(dx, x_host + (size_t)p * h->n_in, (size_t)h->n_in * 4, stream));
+      if (h->cfg.kind == PB_UNET_COND) {
+        dctx = h->WP(h->w_s3);
+        CK(pbk_upload(dctx, ctx_host + (size_t)p * ctx_floats, ctx_floats * 4, stream));
+      }
+      h->slot = p;
+      if (int e = run_primal(h, dx, t_host[p], dctx, nullptr, stream)) return e;
+      h->slot_point[p] = 1;
+    }
+  }
   h->point = true;
   float* dV0 = h->WP(h->w_W);          // W is overwritten only after V0 has been copied to Vprev
-  CK(pbk_upload(dV0, V0_host, (size_t)k * h->n_in * 4, stream));
+  CK(pbk_upload(dV0, V0_host, kt * h->n_in * 4, stream));
   float* du = h->WP(h->w_U); float* ds = h->WP(h->w_sv);
   float* dvT_slot = h->WP(h->w_Vprev); // Vprev is dead once the last iteration has produced V
   if (int e = pb_pullback(h, dV0, k, min_iter, max_iter, tol, du, ds, dvT_slot, info, stream)) return e;
-  CK(pbk_download(u_host, du, (size_t)k * h->n_out * 4, stream));
-  CK(pbk_download(s_host, ds, (size_t)k * 4, stream));
-  CK(pbk_download(vT_host, dvT_slot, (size_t)k * h->n_in * 4, stream));
+  CK(pbk_download(u_host, du, kt * h->n_out * 4, stream));
+  CK(pbk_download(s_host, ds, kt * 4, stream));
+  CK(pbk_download(vT_host, dvT_slot, kt * h->n_in * 4, stream));
   return PB_OK;
+}
+
+PB_API int pb_pullback_host(pb_handle* h, const float* x_host, float t, const float* ctx_host, const float* V0_host, int32_t k,
+                            int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
+                            pb_iter_info* info, void* stream) {
+  if (!h) return PB_EINVAL;
+  if (h->slots > 1) return fail(h, PB_ESTATE, "pb_pullback_host runs one problem per call: use pb_pullback_host_slots");
+  return pullback_host_impl(h, x_host, &t, ctx_host, V0_host, k, min_iter, max_iter, tol, u_host, s_host, vT_host, info, stream);
+}
+
+// Host-buffer entry for a handle with problem slots: one call solves `slots` problems (see pullback_host_impl for the layouts).
+PB_API int pb_pullback_host_slots(pb_handle* h, const float* x_host, const float* t_host, const float* ctx_host, const float* V0_host,
+                                  int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host,
+                                  float* vT_host, pb_iter_info* info, void* stream) {
+  if (!h) return PB_EINVAL;
+  return pullback_host_impl(h, x_host, t_host, ctx_host, V0_host, k, min_iter, max_iter, tol, u_host, s_host, vT_host, info, stream);
 }

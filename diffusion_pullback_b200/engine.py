@@ -243,6 +243,14 @@ class PullbackEngine:
             out = (torch.empty(k, self.n_out, pin_memory=pin), torch.empty(k, pin_memory=pin), torch.empty(k, self.n_in, pin_memory=pin))
         u, s, vT = out
         info = N.PbIterInfo()
+        P = getattr(self, "slots", 1)
+        if P > 1:
+            # problem slots: x [P, n_in], t P values, ctx [P, L, D], V0 [P * k, n_in] (slot-major), contiguous fp32 CPU tensors
+            th = torch.as_tensor(t, dtype=torch.float32).reshape(P).contiguous()
+            self._ck(self.L.pb_pullback_host_slots(self.h, self._p(x), self._p(th), self._p(ctx), self._p(V0), k // P, int(min_iter),
+                                                   int(max_iter), float(tol), self._p(u), self._p(s), self._p(vT), C.byref(info),
+                                                   self._st()))
+            return u, s, vT, info
         self._ck(self.L.pb_pullback_host(self.h, self._p(x), float(t), self._p(ctx), self._p(V0), k, int(min_iter), int(max_iter),
                                          float(tol), self._p(u), self._p(s), self._p(vT), C.byref(info), self._st()))
         return u, s, vT, info

@@ -128,6 +128,12 @@ int pb_pullback_host(pb_handle* h, const float* x_host, float t, const float* ct
                      int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host,
                      float* vT_host, pb_iter_info* info, void* stream);
 
+/* The host-buffer call for a handle with problem slots: x_host [slots][n_in], t_host [slots], ctx_host [slots][ctx_len][dim],
+ * V0_host / vT_host [slots][k][n_in], u_host [slots][k][n_out], s_host [slots][k]; k is the rank per problem. */
+int pb_pullback_host_slots(pb_handle* h, const float* x_host, const float* t_host, const float* ctx_host,
+                           const float* V0_host, int32_t k, int32_t min_iter, int32_t max_iter, float tol, float* u_host,
+                           float* s_host, float* vT_host, pb_iter_info* info, void* stream);
+
 /* After pb_plan(): the state_dict entries (diffusers key + PyTorch shape, ndim <= 4) the planned path consumes. */
 int pb_weight_count(const pb_handle* h);
 int pb_weight_info(const pb_handle* h, int32_t index, const char** name, int32_t* ndim, int64_t* shape);

@@ -366,3 +366,28 @@ def test_pullback_many_body_matches_single_calls(hostsim):
         u, s, vT = out[p]
         up, sp, vp, _ = single[p]
         assert u.shape == (up.shape[1], k) and rel(s, sp) < 1e-5 and rel(vT, vp) < 1e-4 and rel(u.T, up) < 1e-4
+
+
+def test_host_entry_with_problem_slots(hostsim):
+    """pb_pullback_host_slots: host buffers in / out for P problems in one call, against the device entry slot by slot."""
+    P, k, iters = 2, 2, 2
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, P * k, EXACT)
+    g = torch.Generator().manual_seed(11)
+    xs = torch.cat([x, torch.randn(x.shape, generator=g)], 0).contiguous()
+    cs = torch.cat([ctx, torch.randn(ctx.shape, generator=g)], 0).contiguous()
+    ts = [float(t), 512.25]
+    torch.manual_seed(1)
+    V0 = torch.cat([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0).contiguous()
+    eng.set_slots(P)
+    for p in range(P):
+        eng.set_point(xs[p:p + 1], ts[p], cs[p:p + 1], slot=p)
+    u, s, vT, _ = eng.pullback(V0, iters, iters, 0.0)
+    # fresh points through the host entry (it runs the primal passes itself)
+    uh, sh, vh, info = eng.pullback_host(xs.reshape(P, -1), ts, cs, V0, iters, iters, 0.0)
+    assert info.iters_done == iters
+    assert rel(sh, s) < 1e-6 and rel(uh, u) < 1e-5 and rel(vh, vT) < 1e-5
+    eng.set_slots(1)                                                 # and the one-problem entry still works afterwards
+    eng.set_point(xs[1:2], ts[1], cs[1:2])
+    u1, s1, v1, _ = eng.pullback(V0[k:2 * k], iters, iters, 0.0)
+    uh1, sh1, vh1, _ = eng.pullback_host(xs[1].reshape(-1).contiguous(), ts[1], cs[1].contiguous(), V0[k:2 * k].contiguous(), iters, iters, 0.0)
+    assert rel(sh1, s1) < 1e-6 and rel(vh1, v1) < 1e-5 and rel(s1, s[k:2 * k]) < 1e-5
