@@ -66,11 +66,24 @@ METRIC, UNIT = "pullback JVP-iters/sec", "iters/s"
 
 
 def peaks():
+    """Roofline denominators: 16-bit tensor peak as burst (a kernel timed in isolation) and sustained (a kernel inside a long
+    step) from MEASURED_PEAKS.json (driver-written), HBM GB/s, and the TF32 peak measured with the same recipe by
+    scripts/measure_peaks.py (profiles/measured_tf32_peak.json); without that file TF32 counts as half the 16-bit rate."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", d["bf16_tflops"]), d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        out = {"burst": d["bf16_tflops"], "sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "hbm": d["hbm_gbs"],
+               "source": "measured (MEASURED_PEAKS.json: bf16 burst for per-launch fractions, sustained for the whole step)"}
+    else:
+        out = {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    t = os.path.join(ROOT, "profiles", "measured_tf32_peak.json")
+    if os.path.exists(t):
+        d = json.load(open(t))
+        out.update(tf32_burst=d["tf32_tflops"], tf32_sustained=d["tf32_tflops_sustained"],
+                   tf32_source="measured (profiles/measured_tf32_peak.json, scripts/measure_peaks.py)")
+    else:
+        out.update(tf32_burst=out["burst"] / 2, tf32_sustained=out["sustained"] / 2, tf32_source="nominal (half the 16-bit rate)")
+    return out
 
 
 class ClockSampler:
@@ -125,6 +138,36 @@ def cpu_reference_iteration(model_name, op, bi, k_s, iters=1, threads=None):
     t0 = time.perf_counter()
     PO.local_encoder_pullback(m, x, t, ctx, op, bi, k_s, iters, iters, 0.0, v0=v0)
     return (time.perf_counter() - t0) / iters
+
+
+def gpu_reference_iteration(model_name, op, bi, k, tf32):
+    """ORACLE LEG: SURVEY.md s.8d(ii), "the reference on B200" -- the oracle port of the reference algorithm through torch eager
+    autograd on cuda:0 (dual-number forward over the k tangents + k backward passes, cuDNN / cuBLAS), fp32 with TF32 off (the
+    reference's torch-2.1 default) or on (the operand precision of this repo's own path).  Returns seconds per subspace
+    iteration at rank k (one warm-up iteration at rank 1, one timed at rank k)."""
+    from oracle import pullback_oracle as PO
+    from oracle import unet_torch as UT
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = bool(tf32)
+    try:
+        m = UT.build_unet(model_name, build_up=(op == "up")).to("cuda:0")
+        x, t, ctx = UT.synthetic_inputs(model_name)
+        x, t = x.to("cuda:0"), t.to("cuda:0")
+        ctx = None if ctx is None else ctx.to("cuda:0")
+        dt = None
+        for k_s in (1, k):
+            torch.manual_seed(0)
+            v0 = PO.initial_subspace(x.numel(), k_s, device="cuda:0")
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            PO.local_encoder_pullback(m, x, t, ctx, op, bi, k_s, 1, 1, 0.0, v0=v0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        return dt
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        del m
+        torch.cuda.empty_cache()
 
 
 def run_reference(args, wl):
@@ -345,7 +388,8 @@ def run_ours(args, wl):
         prof["_eager_ms_per_iter"] = pe0.elapsed_time(pe1) / prof_iters
 
     if rank == 0:
-        peak_tf, peak_hbm, peak_src = peaks()
+        pk_all = peaks()
+        peak_tf, peak_burst, peak_hbm, peak_src = pk_all["sustained"], pk_all["burst"], pk_all["hbm"], pk_all["source"]
         flops_iter = 2.0 * k * f_tan * 1e9
         step_flops = flops_iter * iters + f_primal * 1e9
         achieved = step_flops * K * S / secs / 1e12 if f_tan else None
@@ -358,7 +402,7 @@ def run_ours(args, wl):
                                  "share_of_eager_iter": kms / prof_iters / prof["_eager_ms_per_iter"]}
         dom = max(kernels, key=lambda n: kernels[n]["ms_per_iter"]) if kernels else None
         # the GEMM launches by operand type, each against its own tensor-pipe peak (kind::tf32 = half the 16-bit rate)
-        for name, pk in (("gemm_tc_kernel[kind::f16]", peak_tf), ("gemm_tc_kernel[kind::tf32]", peak_tf / 2)):
+        for name, pk in (("gemm_tc_kernel[kind::f16]", peak_burst), ("gemm_tc_kernel[kind::tf32]", pk_all["tf32_burst"])):
             kms, kfl, kn = prof.get(name, (0, 0, 0))
             if kn:
                 kernels[name] = {"launches_per_iter": kn / prof_iters, "ms_per_iter": kms / prof_iters, "avg_launch_us": 1e3 * kms / kn,
@@ -381,8 +425,9 @@ def run_ours(args, wl):
                 "e2e": {"value": (world if not tangent else 1) * K * S * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
                 "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
-                             "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": (kernels[dom]["achieved_tflops"] / peak_tf) if dom else None,
+                             "peak": peak_burst, "unit": "TFLOP/s",
+                             "frac": (kernels[dom]["achieved_tflops"] / peak_burst) if dom else None,
+                             "peak_sustained": peak_tf, "peak_tf32": pk_all["tf32_burst"], "peak_tf32_source": pk_all["tf32_source"],
                              "traffic": traffic, "traffic_source": traffic_src,
                              "step_achieved": achieved, "step_frac": (achieved / peak_tf) if achieved else None,
                              "kernels": kernels,
@@ -392,6 +437,19 @@ def run_ours(args, wl):
                                      "half of the bf16 peak used as denominator), fp32 accumulation; step_* = algorithmic "
                                      "flops of one whole step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; traffic = "
                                      "DRAM bytes per launch (ncu, profiles/); peak = " + peak_src}}
+        if world == 1 and not args.no_ref_gpu:
+            # the reference algorithm on THIS GPU (torch eager autograd), one iteration at the workload's rank: the anchor of the
+            # north star's ">= 20x the reference's single-GPU wall clock" (A100-equivalent taken as r = 1)
+            rg = {}
+            for tag, tf32 in (("fp32", False), ("tf32", True)):
+                sec = gpu_reference_iteration(model_name, op, bi, k, tf32)
+                rg[tag] = {"value": 1.0 / sec, "unit": UNIT, "s_per_iter": sec, "speedup_value": value / (1.0 / sec),
+                           "speedup_e2e": line["e2e"]["value"] / (1.0 / sec)}
+            rg["sample"] = (f"1 of {iters} subspace iterations at rank {k} on the full {model_name} {op}-{bi} problem, oracle port of "
+                            "utils.py:722-816 through torch eager autograd on cuda:0 (cuDNN / cuBLAS), after one rank-1 warm-up iteration; "
+                            "fp32 = TF32 off (the reference's precision), tf32 = allow_tf32 on")
+            rg["device"] = torch.cuda.get_device_name(0)
+            line["reference_gpu"] = rg
         if world == 1 and not args.no_cpu_baseline:
             k_s = k
             sec_iter = cpu_reference_iteration(model_name, op, bi, k_s)
@@ -411,6 +469,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU leg (torch eager autograd, 1 iteration)")
     ap.add_argument("--slots", type=int, default=1,
                     help="problem slots (pb_set_slots): each step solves this many independent problems as ONE tangent batch "
                          "(throughput mode; default 1 = one problem per step, the reference's granularity)")

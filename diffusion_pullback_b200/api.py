@@ -42,14 +42,22 @@ def refresh_weights(unet):
         eng.bind(unet.state_dict())
 
 
-def _timestep(t):
-    return float(t.reshape(-1)[0]) if torch.is_tensor(t) else float(t)
+def _timestep(t, i=0):
+    """Sample i's timestep: a scalar / 0-dim / 1-element value is shared by the batch (the reference expands it,
+    utils.py:461-468); a tensor with one entry per sample is indexed."""
+    if torch.is_tensor(t):
+        t = t.reshape(-1)
+        return float(t[i] if t.numel() > 1 else t[0])
+    return float(t)
 
 
 def get_h(self, sample=None, timestep=None, encoder_hidden_states=None, op=None, block_idx=None, verbose=False):
-    """`utils.py:438-527`: the truncated U-Net forward; batch 1 (the pullback's use of it)."""
+    """`utils.py:438-527`: the truncated U-Net forward.  A batch (the reference expands the timestep over it,
+    utils.py:461-468) is evaluated one latent at a time on the same planned engine."""
     if sample.shape[0] != 1:
-        raise ValueError("diffusion_pullback_b200.get_h evaluates one latent at a time")
+        ehs = encoder_hidden_states
+        return torch.cat([get_h(self, sample[i:i + 1], _timestep(timestep, i), None if ehs is None else ehs[i:i + 1], op, block_idx)
+                          for i in range(sample.shape[0])], 0)
     ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
     eng = _engine_for(self, sample, op, block_idx, 1, ctx_len)
     return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
@@ -59,7 +67,9 @@ def eps(self, sample, timestep, encoder_hidden_states=None):
     """The whole U-Net, x_t -> noise prediction: what the reference calls as `self.unet(latents, t,
     encoder_hidden_states=prompt_emb).sample` in its DDIM loops (`edit.py:164-168`, `:458-462`); one latent per call."""
     if sample.shape[0] != 1:
-        return torch.cat([eps(self, sample[i:i + 1], timestep, encoder_hidden_states[i:i + 1]) for i in range(sample.shape[0])], 0)
+        ehs = encoder_hidden_states
+        return torch.cat([eps(self, sample[i:i + 1], _timestep(timestep, i), None if ehs is None else ehs[i:i + 1])
+                          for i in range(sample.shape[0])], 0)
     ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
     eng = _engine_for(self, sample, "full", 0, 1, ctx_len)
     return eng.set_point(sample, _timestep(timestep), encoder_hidden_states, want_h=True)
@@ -69,7 +79,7 @@ def eps_uncond(self, x, t):
     """The whole unconditional U-Net (`UNet2DModel`), x_t -> noise prediction: `self.unet(x, t).sample` of the reference's
     uncond DDIM loops (`edit.py:1601-1714`); one image per call."""
     if x.shape[0] != 1:
-        return torch.cat([eps_uncond(self, x[i:i + 1], t) for i in range(x.shape[0])], 0)
+        return torch.cat([eps_uncond(self, x[i:i + 1], _timestep(t, i)) for i in range(x.shape[0])], 0)
     eng = _engine_for(self, x, "full", 0, 1, 0)
     return eng.set_point(x, _timestep(t), None, want_h=True)
 
@@ -77,7 +87,7 @@ def eps_uncond(self, x, t):
 def get_h_uncond(self, x=None, t=None, op=None, block_idx=None, verbose=False):
     """`utils.py:114-163`; only ('mid', 0) is valid, anything else raises ValueError like the reference."""
     if x.shape[0] != 1:
-        raise ValueError("diffusion_pullback_b200.get_h evaluates one latent at a time")
+        return torch.cat([get_h_uncond(self, x[i:i + 1], _timestep(t, i), op, block_idx) for i in range(x.shape[0])], 0)
     eng = _engine_for(self, x, op, block_idx, 1, 0)
     return eng.set_point(x, _timestep(t), None, want_h=True)
 

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "pb_host_util.h"
 #include "pb_kernels.h"
 #include "pb_tc.cuh"
 
@@ -601,15 +602,7 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // head dim 64 (SD-2.x)
   PB_ATTN_CASE(2, 2, 2, 1) PB_ATTN_CASE(1, 2, 2, 0) PB_ATTN_CASE(1, 2, 2, 2)      // head dim 80 (SD-1.x 32x32 layers)
 #undef PB_ATTN_CASE
-  static void (*configured[24])(Params) = {};                   // one-time opt-in to 227 KB of dynamic smem per instantiation
-  int ci = 0;
-  while (ci < 24 && configured[ci] && configured[ci] != kern) ++ci;
-  if (ci == 24) return "attn_lin: internal (instantiation table full)";
-  if (!configured[ci]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured[ci] = kern;
-  }
+  if (const char* err = pbhost::optin_smem(kern, 227 * 1024)) return err;   // once per (device, instantiation)
   kern<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(st)>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -1351,6 +1351,17 @@ PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n,
         return fail(h, PB_EINVAL, "unexpected shape for " + name);
       const int rows = (int)(numel / per_row);
       if (row + rows > s.out) return fail(h, PB_EINVAL, "unexpected shape for " + name);
+      {
+        // the PyTorch shape pb_weight_info reports: [rows] | [rows][in] | [rows][in][3][3] (a transposed or re-shaped tensor
+        // with the right element count must not be accepted silently)
+        const int want_nd = s.kind == WK_VEC ? 1 : (s.kind == WK_CONV3 || s.kind == WK_CONV3_S2) ? 4 : 2;
+        // (a 1x1 convolution [rows][in][1][1] is the same matrix as a Linear weight: SD-1.x proj_in / proj_out / conv_shortcut)
+        const bool conv1x1 = want_nd == 2 && d.ndim == 4 && d.shape[2] == 1 && d.shape[3] == 1;
+        bool ok = (d.ndim == want_nd || conv1x1) && d.shape[0] == rows && rows == s.out / (int)s.names.size();
+        if (ok && want_nd >= 2) ok = d.shape[1] == s.in;
+        if (ok && want_nd == 4) ok = d.shape[2] == 3 && d.shape[3] == 3;
+        if (!ok) return fail(h, PB_EINVAL, "unexpected shape for " + name);
+      }
       float* fwd = reinterpret_cast<float*>(h->packed + s.fwd_off);
       float* bwd = reinterpret_cast<float*>(h->packed + s.bwd_off);
       switch (s.kind) {
@@ -1451,6 +1462,7 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
                        float* vT, pb_iter_info* info, void* stream) {
   // with problem slots, k is the rank PER PROBLEM: V0 / vT are [slots][k][n_in], u is [slots][k][n_out], s is [slots][k]; every
   // problem runs the same number of iterations (the early exit needs all of them converged at the same check)
+  if (!h) return PB_EINVAL;
   const int P = h->slots, kt = k * P;
   if (int e = check_ready(h, kt, true)) return e;
   if (!V0 || !u || !s || !vT) return fail(h, PB_EINVAL, "null pointer");
@@ -1523,6 +1535,7 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
 static int pullback_host_impl(pb_handle* h, const float* x_host, const float* t_host, const float* ctx_host, const float* V0_host, int32_t k,
                               int32_t min_iter, int32_t max_iter, float tol, float* u_host, float* s_host, float* vT_host,
                               pb_iter_info* info, void* stream) {
+  if (!h) return PB_EINVAL;
   const int P = h->slots;
   const size_t kt = (size_t)k * P;
   if (int e = check_ready(h, (int)kt, false)) return e;

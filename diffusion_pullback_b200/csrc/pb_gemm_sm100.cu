@@ -32,6 +32,7 @@
 #include <type_traits>
 
 #include "pb_gemm.h"
+#include "pb_host_util.h"
 #include "pb_tc.cuh"
 
 namespace pbgemm {
@@ -536,28 +537,14 @@ const char* encode_plain(CUtensorMap* m, const float* base, int rows, int K, lon
 
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
+static int sm_count() { return pbhost::sm_count(); }
 
 template <int BN, int STAGES, bool AB16, bool D16>
 static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
   using S = Smem<BN, STAGES>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(2 * BN <= 512 && BN <= ACC_STRIDE, "two accumulator stages must fit TMEM");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AB16, D16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::TOTAL);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    configured = true;
-  }
+  if (const char* err = pbhost::optin_smem(gemm_tc_kernel<BN, STAGES, AB16, D16>, S::TOTAL)) return err;
   gemm_tc_kernel<BN, STAGES, AB16, D16><<<grid, NTHREADS, S::TOTAL, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cudaGetErrorString(e);

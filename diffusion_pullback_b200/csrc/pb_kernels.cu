@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "pb_host_util.h"
 #include "pb_kernels.h"
 
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st);
@@ -1155,12 +1156,10 @@ PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const floa
     const int shmem = Cout * 9 * Cin * 4;
     const unsigned blocks = (unsigned)std::min<long>((pix + 7) / 8, (long)kSMs * 2);
     if (Cout == 4) {
-      static bool cfg4 = false;
-      if (!cfg4) { cudaFuncSetAttribute(conv3x3_thin_out_smem_k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg4 = true; }
+      if (const char* err = pbhost::optin_smem(conv3x3_thin_out_smem_k<4>, 96 * 1024)) return err;
       conv3x3_thin_out_smem_k<4><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
     } else {
-      static bool cfg3 = false;
-      if (!cfg3) { cudaFuncSetAttribute(conv3x3_thin_out_smem_k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg3 = true; }
+      if (const char* err = pbhost::optin_smem(conv3x3_thin_out_smem_k<3>, 96 * 1024)) return err;
       conv3x3_thin_out_smem_k<3><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
     }
   } else if (Cout <= 8 && Cin >= 32) {

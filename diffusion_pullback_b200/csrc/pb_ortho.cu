@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <algorithm>
 
+#include "pb_host_util.h"
 #include "pb_kernels.h"
 
 namespace {
@@ -125,8 +126,18 @@ __global__ void jacobi_k(const double* __restrict__ G, const double* __restrict_
     }
   }
   __syncwarp();
+  const double lmax = fmax(lam[order[0]], 0.0);
   for (int i = lane; i < k; i += 32) {
     const int e = order[i];
+    // Numerically null direction of W: W W^T squares the conditioning, so an eigenvalue below ~1e-13 of the largest carries
+    // no information (fp64 Gram of fp32 data).  torch.linalg.svd would return an arbitrary orthonormal completion there; this
+    // returns a ZERO row with s = 0 instead of round-off divided by ~0 (a non-orthonormal basis would silently corrupt the
+    // next J V).  A zero column stays zero through the iteration (J 0 = 0), so the caller sees s_i = 0, v_i = 0.
+    if (!(lam[e] > 1e-13 * lmax)) {
+      for (int j = 0; j < k; ++j) Rm[i * k + j] = 0.f;
+      sv[i] = 0.f;
+      continue;
+    }
     const double l = fmax(lam[e], 1e-300);
     const double inv = 1.0 / sqrt(l);
     double dot = 0.0;                            // <V_i, Vprev_i> = inv * sum_j X[j][e] M[j][i]
@@ -175,24 +186,14 @@ PBK pbk_gram2(const float* Wm, const float* Vprev, int k, long n, double* G, dou
   if (M) cudaMemsetAsync(M, 0, sizeof(double) * k * k, s);
   int kChunk = std::min(kChunkMax, (96 * 1024 / (2 * k * 4)) / 32 * 32);
   const size_t shmem = (size_t)2 * k * kChunk * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gram2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    attr = true;
-  }
+  if (const char* err = pbhost::optin_smem(gram2_k, 100 * 1024)) return err;
   const unsigned grid = (unsigned)std::max<long>(1, std::min<long>((n + kChunk - 1) / kChunk, 148 * 2));
   gram2_k<<<grid, 256, shmem, s>>>(Wm, Vprev, k, n, kChunk, G, M);
   return last_err();
 }
 PBK pbk_jacobi(const double* G, const double* M, int k, float* Rm, float* sv, pb_stream st) {
   if (k < 1 || k > kMaxK) return "ortho: pca_rank must be in [1, 64]";
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(jacobi_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxK * kMaxK * 8);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    attr = true;
-  }
+  if (const char* err = pbhost::optin_smem(jacobi_k, 2 * kMaxK * kMaxK * 8)) return err;
   jacobi_k<<<1, 32, (size_t)2 * k * k * sizeof(double), static_cast<cudaStream_t>(st)>>>(G, M, k, Rm, sv);
   return last_err();
 }

@@ -95,18 +95,28 @@ class PullbackEngine:
     def _ck(self, rc):
         if rc != 0:
             msg = self.L.pb_last_error(self.h).decode()
+            g, self._guard = getattr(self, "_guard", None), None
+            if g is not None:
+                g.__exit__(None, None, None)
             raise _ERRORS.get(rc, RuntimeError)(msg)
 
     def _st(self):
         return C.c_void_p(self.stream.cuda_stream) if self.stream is not None else C.c_void_p(0)
 
     def _enter(self):
+        # the C side launches on the CURRENT device (kernel attributes, tensor maps, streams): make it this engine's
+        # device for the duration of the call, whatever the caller's current device is
         if self.stream is not None:
+            self._guard = torch.cuda.device(self.device)
+            self._guard.__enter__()
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
 
     def _exit(self):
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            g, self._guard = self._guard, None
+            if g is not None:
+                g.__exit__(None, None, None)
 
     def _f32(self, t, shape=None):
         t = t.detach().to(self.device, torch.float32).contiguous()
@@ -244,13 +254,16 @@ class PullbackEngine:
         u, s, vT = out
         info = N.PbIterInfo()
         P = getattr(self, "slots", 1)
+        self._enter()
         if P > 1:
             # problem slots: x [P, n_in], t P values, ctx [P, L, D], V0 [P * k, n_in] (slot-major), contiguous fp32 CPU tensors
             th = torch.as_tensor(t, dtype=torch.float32).reshape(P).contiguous()
             self._ck(self.L.pb_pullback_host_slots(self.h, self._p(x), self._p(th), self._p(ctx), self._p(V0), k // P, int(min_iter),
                                                    int(max_iter), float(tol), self._p(u), self._p(s), self._p(vT), C.byref(info),
                                                    self._st()))
+            self._exit()
             return u, s, vT, info
         self._ck(self.L.pb_pullback_host(self.h, self._p(x), float(t), self._p(ctx), self._p(V0), k, int(min_iter), int(max_iter),
                                          float(tol), self._p(u), self._p(s), self._p(vT), C.byref(info), self._st()))
+        self._exit()
         return u, s, vT, info

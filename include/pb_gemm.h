@@ -48,3 +48,14 @@ static inline PbGemm pb_gemm_init() {
   g.nseg = 1; g.alpha = 1.f; g.beta = 0.f; g.nb = 1; g.nh = 1;
   return g;
 }
+
+// tuning hooks of the sm_100a GEMM (scripts/bench_gemm.py): force a tile width (0 = heuristic), the split-K policy
+// (0 off, 1 heuristic, > 1 forced split count), allow BN = 160; minimum k-blocks for a split
+#ifdef __cplusplus
+extern "C" {
+#endif
+void pb_gemm_tune(int force_bn, int split, int use160);
+void pb_gemm_tune_split_min_kb(int kb);
+#ifdef __cplusplus
+}
+#endif

@@ -1,5 +1,7 @@
 // Leaf-kernel interface between the engine (pb_engine.cpp, device-agnostic host C++) and the
-// kernel library.  The product library implements every pbk_* as hand-written sm_100a CUDA
+// kernel library.  NOT part of the reference-facing ABI (that is pullback_b200.h): these symbols are exported from
+// libpullback_b200.so so that every kernel can be unit-tested against torch through ctypes (tests/test_kernels_gpu.py) and
+// timed alone (scripts/bench_gemm.py, scripts/bench_gn.py); tests/test_abi_symbols.py checks that each one is exported.  The product library implements every pbk_* as hand-written sm_100a CUDA
 // (pb_kernels.cu, pb_gemm_sm100.cu, pb_ortho.cu).  tests/hostsim/ provides a plain-C++ double of
 // the same symbols so the engine's sequencing logic can be unit-tested without a GPU; that double
 // is test infrastructure only and is never linked into, or reachable from, the product library.

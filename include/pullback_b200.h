@@ -110,7 +110,9 @@ int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream);
 int pb_vjp(pb_handle* h, const float* U, int32_t k, float* W, void* stream);
 /* (s, V) from W as torch.linalg.svd would give (utils.py:799): V rows orthonormal, s = sqrt(svdvals(W)),
  * descending.  Vprev (may be NULL) fixes the row signs and feeds metrics[0]=||V-Vprev||^2, metrics[1]=#violations
- * of allclose(atol,rtol=1e-5).  All device pointers; metrics may be NULL. */
+ * of allclose(atol,rtol=1e-5).  All device pointers; metrics may be NULL.  A numerically null direction of W (Gram
+ * eigenvalue below 1e-13 of the largest: W has rank < k) comes back as s_i = 0 with a ZERO row V_i, where LAPACK would
+ * return an arbitrary orthonormal completion. */
 int pb_orthonormalize(pb_handle* h, const float* W, const float* Vprev, int32_t k, float atol, float* V, float* s,
                       float* metrics, void* stream);
 

@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "libpb_hostsim.so")
 
 def build(force=False):
     srcs = [os.path.join(CSRC, "pb_engine.cpp"), os.path.join(HERE, "pbk_hostsim.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("pb_kernels.h", "pb_gemm.h")] + [os.path.join(ROOT, "include", "pullback_b200.h")]
+    deps = srcs + [os.path.join(ROOT, "include", f) for f in ("pb_kernels.h", "pb_gemm.h", "pullback_b200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     cmd = ["g++", "-O3", "-march=native", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- never linked into, loaded by, or reachable from the product library.
 //
-// A plain-C++ double of the leaf-kernel interface (csrc/pb_kernels.h) so that the HOST logic of the
+// A plain-C++ double of the leaf-kernel interface (include/pb_kernels.h) so that the HOST logic of the
 // engine (csrc/pb_engine.cpp: planning, weight packing, op sequencing, cotangent accumulation order,
 // workspace offsets, the iteration loop) can be unit-tested in the CPU-only authoring container
 // (`pytest -m "not gpu"`), where no CUDA kernel can run.  tests/hostsim/build.py links it with the
@@ -499,8 +499,11 @@ PBK pbk_jacobi(const double* G, const double* M, int k, float* Rm, float* sv, pb
   std::vector<int> order(k);
   for (int i = 0; i < k; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return A[a * k + a] > A[b * k + b]; });
+  const double lmax = std::max(A[order[0] * k + order[0]], 0.0);
   for (int i = 0; i < k; ++i) {
     const int e = order[i];
+    // numerically null direction of W (the Gram matrix squares the conditioning): a zero row with s = 0, not noise / 0
+    if (!(A[e * k + e] > 1e-13 * lmax)) { for (int j = 0; j < k; ++j) Rm[i * k + j] = 0.f; sv[i] = 0.f; continue; }
     const double l = std::max(A[e * k + e], 1e-300), inv = 1.0 / std::sqrt(l);
     double dot = 0;
     if (M) for (int j = 0; j < k; ++j) dot += X[j * k + e] * M[j * k + i];

@@ -23,11 +23,28 @@ def test_header_declares_the_documented_entry_points():
         assert must in names, must
 
 
+def _declared_leaf():
+    """The leaf-kernel interface (include/pb_kernels.h, include/pb_gemm.h): exported for kernel unit tests / micro-benchmarks."""
+    names = []
+    for f in ("pb_kernels.h", "pb_gemm.h"):
+        src = open(os.path.join(ROOT, "include", f)).read()
+        src = re.sub(r"//[^\n]*", "", src)
+        names += re.findall(r"\b(pbk_[a-z_0-9]+|pb_gemm_tune[a-z_0-9]*)\s*\(", src)
+    return sorted(set(names))
+
+
 def test_library_exports_every_declared_symbol():
+    import subprocess
     from diffusion_pullback_b200.build import build
-    lib = C.CDLL(build())
-    missing = [n for n in _declared() if not hasattr(lib, n)]
+    path = build()
+    lib = C.CDLL(path)
+    missing = [n for n in _declared() + _declared_leaf() if not hasattr(lib, n)]
     assert not missing, missing
+    # ... and nothing else: every exported pb* symbol is declared in include/*.h
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = sorted({l.split()[-1] for l in out.splitlines() if re.search(r" [TDB] (pb_|pbk_)", l)})
+    undeclared = [n for n in exported if n not in set(_declared() + _declared_leaf())]
+    assert not undeclared, undeclared
     lib.pb_backend.restype = C.c_char_p
     assert lib.pb_backend() == b"cuda-sm100a"
 

@@ -391,3 +391,17 @@ def test_host_entry_with_problem_slots(hostsim):
     u1, s1, v1, _ = eng.pullback(V0[k:2 * k], iters, iters, 0.0)
     uh1, sh1, vh1, _ = eng.pullback_host(xs[1].reshape(-1).contiguous(), ts[1], cs[1].contiguous(), V0[k:2 * k].contiguous(), iters, iters, 0.0)
     assert rel(sh1, s1) < 1e-6 and rel(vh1, v1) < 1e-5 and rel(s1, s[k:2 * k]) < 1e-5
+
+
+def test_orthonormalize_rank_deficient_rows_are_zero_not_noise(hostsim):
+    """W of rank 2 with k = 3.  The Gram / Jacobi path cannot resolve the null direction (W W^T squares the
+    conditioning); it must return it as s = 0 with a zero row, the two resolved rows staying orthonormal and equal to the SVD's."""
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, 3)
+    eng.set_point(x, float(t), ctx)
+    g = torch.Generator().manual_seed(1)
+    B = torch.randn(2, eng.n_in, generator=g)
+    W = torch.stack([B[0], B[1], 0.5 * B[0] - 2.0 * B[1]])
+    s, V, _ = eng.orthonormalize(W)
+    sref = torch.linalg.svdvals(W.double()).sqrt().float()
+    assert torch.allclose(s[:2], sref[:2], rtol=1e-5) and float(s[2]) == 0.0
+    assert torch.allclose(V[:2] @ V[:2].T, torch.eye(2), atol=1e-5) and float(V[2].abs().max()) == 0.0
