@@ -68,7 +68,8 @@ class PbAttnLin(C.Structure):
                 ("sCh", C.c_long), ("D", C.c_void_p), ("ldd", C.c_long), ("sDb", C.c_long), ("R", C.c_void_p),
                 ("ldr", C.c_long), ("sRb", C.c_long), ("round_tf32", C.c_int),
                 ("C2", C.c_void_p), ("ldc2", C.c_long), ("sC2h", C.c_long), ("sC2b", C.c_long),
-                ("D2", C.c_void_p), ("ldd2", C.c_long), ("sD2b", C.c_long), ("p16", C.c_int), ("p_scale", C.c_float)]
+                ("D2", C.c_void_p), ("ldd2", C.c_long), ("sD2b", C.c_long), ("p16", C.c_int), ("p_scale", C.c_float),
+                ("s16", C.c_int)]
 
 
 _lib = None

@@ -64,7 +64,9 @@ struct alignas(64) Params {
   int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2];
   uint32_t a_bytes, b_bytes, c_bytes, p_bytes;   // bytes per barrier phase
   int nseg, d, dpad;                   // accumulator width dpad = d rounded up to 16
-  int kfull, tail;                     // S contraction: kfull 128-byte k-blocks + a tail of `tail` floats (0, 8, 16)
+  int kfull, tail;                     // S contraction: kfull 128-byte k-blocks + a tail of `tail` 32-byte k-steps (0, 1, 2)
+  int nk_last;                         // MMAs (32-byte k-steps) of the last full k-block (3 when the head dim ends inside it)
+  int bk;                              // S-operand elements per 128-byte k-block (32 fp32, 64 fp16)
   int a_seg_bytes, b_seg_bytes;        // smem bytes of one segment's A tile set / B tile set
   int b_stage_bytes, c_tile_bytes;     // one ring stage of B (all segments) / one C tile
   int nb_st, nc1_st, npt_st;           // ring depths of B / C2, C1 and P/T
@@ -106,13 +108,17 @@ struct Ring {
 // P16: the probability matrix (pre-scaled by p_scale = Nc so that it sits in fp16's normal range), C1 and C2 are fp16 and
 // the step is 64 columns wide: P / T tiles are still 128 rows x 128 bytes in the same swizzle, the two accumulating
 // products run as kind::f16, and the P tile -- the largest stream of the kernel -- is half the bytes per column.
-template <int NSEG, int KFULL, int NTAIL, int C2M, bool P16>
+// M16: 0 all fp32 (TF32 MMAs); 1 P16 above; 2 = 1 + the S operands (A, B segments) are fp16 too (kind::f16 score MMAs over
+// 64-element k-blocks) and D / D2 are written as halves: the all-fp16 tangent plan of the engine.
+// NKL: MMAs of the last full k-block (4, or 3 when the head dim ends inside it: fp16 head dim 40 = 80 of 128 bytes).
+template <int NSEG, int KFULL, int NTAIL, int C2M, int M16, int NKL>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_constant__ Params p) {
   constexpr bool GEN = NSEG < 0;
+  constexpr bool P16 = M16 >= 1, S16 = M16 == 2;
   constexpr int TNc = P16 ? 64 : 32;            // score columns per step
   const int nseg = GEN ? p.nseg : NSEG;
   const int kfull = GEN ? p.kfull : KFULL;
-  const int tail = GEN ? p.tail : NTAIL * 8;
+  const int tail = GEN ? p.tail : NTAIL;        // 32-byte k-steps of the compact tail tile
   const bool has_c2 = GEN ? (p.has_c2 != 0) : (C2M != 0);
   const bool sep_acc2 = GEN ? (p.sep_acc2 != 0) : (C2M == 2);
   const int a_seg_bytes = GEN ? p.a_seg_bytes : KFULL * TM * 128 + TM * NTAIL * 32;
@@ -170,7 +176,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_base_smem;
   const uint32_t tm_acc = tmem_base + NS * TNc;
   const uint32_t tm_acc2 = sep_acc2 ? tm_acc + ACC2_OFF : tm_acc;
-  const int tail_span = tail * 4;                              // bytes per row of the tail tile (32 or 64)
+  const int tail_span = tail * 32;                             // bytes per row of the tail tile (32 or 64)
+  const int BKe = S16 ? 64 : BK;                               // S-operand elements per 128-byte k-block
   const int a_tail_off = kfull * TM * 128, b_tail_off = kfull * TNc * 128;
 
   if (warp == 0) {
@@ -180,8 +187,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       for (int s = 0; s < nseg; ++s) {
         uint8_t* dst = sA + s * a_seg_bytes;
         for (int kb = 0; kb < kfull; ++kb)
-          tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
-        if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BK, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+          tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BKe, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+        if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BKe, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
       }
       // Every ring is refilled as soon as ITS consumer releases a stage: the S-operand rings are released by the score
       // MMAs, the P/T and C1 rings two steps later by the accumulate MMAs, so one thread polls the three "empty" barriers
@@ -199,8 +206,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
 #pragma unroll
           for (int s = 0; s < nseg; ++s) {
             uint8_t* dst = sB + st * b_stage_bytes + s * b_seg_bytes;
-            for (int kb = 0; kb < kfull; ++kb) tma_load_4d(dst + kb * TNc * 128, &p.mapB[s], &b_full[st], kb * BK, c0, bh[s], bb[s]);
-            if (tail) tma_load_4d(dst + b_tail_off, &p.mapBt[s], &b_full[st], kfull * BK, c0, bh[s], bb[s]);
+            for (int kb = 0; kb < kfull; ++kb) tma_load_4d(dst + kb * TNc * 128, &p.mapB[s], &b_full[st], kb * BKe, c0, bh[s], bb[s]);
+            if (tail) tma_load_4d(dst + b_tail_off, &p.mapBt[s], &b_full[st], kfull * BKe, c0, bh[s], bb[s]);
           }
           if (has_c2) {
             mbar_arrive_expect_tx(&c2_full[st], p.c_bytes);
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     // =========================== MMA issuers ===========================
     // warp 1 issues the score products S(j), warp 10 the products that accumulate over the steps (P . C2, T . C1): two
     // single-warp instruction streams instead of one.  The whole warp walks its loop; one elected lane issues (elect_one).
-    const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TNc >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_s = (1u << 4) | (S16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(TNc >> 3) << 17) | (uint32_t(TM >> 4) << 24);
     const uint32_t idesc_a = (1u << 4) | (P16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(p.dpad >> 3) << 17) | (uint32_t(TM >> 4) << 24);
     const uint32_t tm_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sm_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
@@ -241,8 +248,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       const uint64_t dA = make_smem_desc(uA), dB = make_smem_desc(uB);
       const uint64_t dAt = make_desc_sw(uA + a_tail_off, tail_span), dBt = make_desc_sw(uB + b_tail_off, tail_span);
       const uint32_t a_seg16 = a_seg_bytes >> 4, b_seg16 = b_seg_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
-      const int nk_last = min(4, (p.d - (kfull - 1) * BK + 7) / 8);   // columns past d are TMA zero fill: skip those MMAs
-      const int ntail = tail >> 3;
+      const int nk_last = GEN ? p.nk_last : NKL;                 // columns past d are TMA zero fill: skip those MMAs
+      const int ntail = tail;
+      auto mma_s = [&](uint32_t d_s, uint64_t ad, uint64_t bd, uint32_t on) {
+        if constexpr (S16) mma_f16(d_s, ad, bd, idesc_s, on); else mma_tf32(d_s, ad, bd, idesc_s, on);
+      };
       Ring rb{0, 0}, rs{0, 0};                                   // S operands / S in TMEM
       mbar_wait(a_full, 0);
       for (int j = 0; j < nj; ++j) {
@@ -258,14 +268,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
 #pragma unroll
             for (int kb = 0; kb < kfull; ++kb) {
               const uint64_t adesc = a0 + uint64_t(kb * (TM * 128 >> 4)), bdesc = b0 + uint64_t(kb * (TNc * 128 >> 4));
-              const int nk = (GEN && kb == kfull - 1) ? nk_last : 4;   // specialised shapes have whole k-blocks only
+              const int nk = (kb == kfull - 1) ? nk_last : 4;
 #pragma unroll
-              for (int k = 0; k < nk; ++k) { mma_tf32(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, on); on = 1; }
+              for (int k = 0; k < 4; ++k)
+                if (k < nk) { mma_s(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), on); on = 1; }
             }
             if (ntail) {
               const uint64_t adesc = dAt + uint64_t(s * a_seg16), bdesc = dBt + uint64_t(rb.idx * b_stage16 + s * b_seg16);
 #pragma unroll
-              for (int k = 0; k < ntail; ++k) { mma_tf32(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc_s, on); on = 1; }
+              for (int k = 0; k < 2; ++k)
+                if (k < ntail) { mma_s(d_s, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), on); on = 1; }
             }
           }
           tcgen05_commit(&b_empty[rb.idx]);
@@ -450,15 +462,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       float* dptr; const float* rptr = nullptr; const float* optr = nullptr;
       float alpha;
       uint32_t tm;
+      long doff;                                     // element offset of this row's head slice in D / D2
       if (grp == 0) {
-        dptr = p.D + (long)bat_b * p.sDb + rr * p.ldd + bat_h * p.d;
+        doff = (long)bat_b * p.sDb + rr * p.ldd + bat_h * p.d;
+        dptr = p.D + doff;
         if (p.R) rptr = p.R + (long)bat_b * p.sRb + rr * p.ldr + bat_h * p.d;
         if (p.want_rsum && p.O) optr = p.O + rr * p.ldo + bat_h * p.d;
         alpha = p.alpha2 * p.inv_pscale; tm = tm_acc;
       } else {
-        dptr = p.D2 + (long)bat_b * p.sD2b + rr * p.ldd2 + bat_h * p.d;
+        doff = (long)bat_b * p.sD2b + rr * p.ldd2 + bat_h * p.d;
+        dptr = p.D2 + doff;
         alpha = p.inv_pscale; tm = tm_acc2;
       }
+      __half* hptr = reinterpret_cast<__half*>(grp == 0 ? p.D : p.D2) + doff;      // S16: the outputs hold halves
       for (int c16 = 0; c16 < p.dpad; c16 += 16) {
         uint32_t v[16];
         tmem_ld16(tm + (uint32_t(q * 32) << 16) + uint32_t(c16), v);
@@ -472,11 +488,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           for (int e = 0; e < 4; ++e) o[e] = alpha * __uint_as_float(v[g + e]);
           if (optr) { const float4 ov = *reinterpret_cast<const float4*>(optr + n); o[0] -= rs * ov.x; o[1] -= rs * ov.y; o[2] -= rs * ov.z; o[3] -= rs * ov.w; }
           if (rptr) { const float4 rv = *reinterpret_cast<const float4*>(rptr + n); o[0] += p.beta * rv.x; o[1] += p.beta * rv.y; o[2] += p.beta * rv.z; o[3] += p.beta * rv.w; }
-          if (p.round_tf32) {
+          if (p.round_tf32 && !S16) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = rna_tf32(o[e]);
           }
-          *reinterpret_cast<float4*>(dptr + n) = make_float4(o[0], o[1], o[2], o[3]);
+          if constexpr (S16) {
+            uint2 hv;
+            *reinterpret_cast<__half2*>(&hv.x) = __floats2half2_rn(o[0], o[1]);
+            *reinterpret_cast<__half2*>(&hv.y) = __floats2half2_rn(o[2], o[3]);
+            *reinterpret_cast<uint2*>(hptr + n) = hv;
+          } else {
+            *reinterpret_cast<float4*>(dptr + n) = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
       tcgen05_fence_before();
@@ -504,6 +527,9 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (a.nseg < 1 || a.nseg > 2) return "attn_lin: 1 or 2 segments";
   if ((long)a.nb * a.nh > 65535) return "attn_lin: batch too large";
   if (a.D2 && !a.C2) return "attn_lin: D2 needs C2";
+  const int s16 = a.s16 ? 1 : 0;                // the S operands (segments) and the outputs D / D2 hold halves too
+  if (s16 && !a.p16) return "attn_lin: fp16 S operands need the fp16 probability path";
+  if (s16 && a.R) return "attn_lin: no residual with fp16 outputs";
   const int p16 = a.p16 ? 1 : 0;                // Pm (pre-scaled by p_scale), C1, C2 hold halves; 64-column steps
   const int TNh = p16 ? 64 : TN;                // score columns per step
   const long ces = p16 ? 2 : 4;                 // element size of Pm / C1 / C2
@@ -512,10 +538,15 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   Params p;
   memset(&p, 0, sizeof p);
   p.nseg = a.nseg; p.d = a.d; p.dpad = (a.d + 15) / 16 * 16;
-  // S contraction over the head dim: full 32-float k-blocks + a compact tail of 8 / 16 floats (a longer tail is a full block)
-  const int rem = a.d % BK;
-  p.tail = rem == 0 ? 0 : rem <= 8 ? 8 : rem <= 16 ? 16 : 0;
-  p.kfull = a.d / BK + ((rem > 16) ? 1 : 0);
+  // S contraction over the head dim in 32-byte k-steps (8 fp32 / 16 halves = one MMA): full 128-byte k-blocks of 4 steps + a
+  // compact tail of 1 or 2 steps (32- / 64-byte swizzle); a 3-step remainder is a full block whose 4th MMA is skipped
+  const int ses = s16 ? 2 : 4;                  // S-operand element size
+  const int ksteps = (a.d * ses + 31) / 32, rem = ksteps % 4;
+  p.bk = 128 / ses;
+  p.kfull = ksteps / 4 + (rem == 3 ? 1 : 0);
+  p.tail = rem == 3 ? 0 : rem;
+  p.nk_last = rem == 3 ? 3 : 4;
+  if (s16 && (a.d % 8)) return "attn_lin: fp16 S operands need a head dim that is a multiple of 8";
   p.Mr = a.Mr; p.Nc = a.Nc; p.nb = a.nb; p.nh = a.nh;
   p.alpha1 = a.alpha1; p.alpha2 = a.alpha2; p.beta = a.R ? a.beta : 0.f;
   p.delta = a.delta; p.delta_mode = a.delta ? a.delta_mode : 0;
@@ -523,11 +554,13 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.D = a.D; p.ldd = a.ldd; p.sDb = a.sDb; p.R = a.R; p.ldr = a.ldr; p.sRb = a.sRb; p.round_tf32 = a.round_tf32;
   p.has_c2 = a.C2 ? 1 : 0; p.sep_acc2 = a.D2 ? 1 : 0; p.D2 = a.D2; p.ldd2 = a.ldd2; p.sD2b = a.sD2b;
   p.inv_pscale = p16 ? 1.f / a.p_scale : 1.f;
-  if ((a.ldd % 4) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % cq) || (a.ldc % cq) || (a.D2 && a.ldd2 % 4) ||
+  const int dq = s16 ? 8 : 4;                   // elements per 16 bytes of D / D2
+  if ((a.ldd % dq) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % cq) || (a.ldc % cq) || (a.D2 && a.ldd2 % dq) ||
       ((reinterpret_cast<uintptr_t>(a.D) | reinterpret_cast<uintptr_t>(a.R) | reinterpret_cast<uintptr_t>(a.O) |
         reinterpret_cast<uintptr_t>(a.Pm) | reinterpret_cast<uintptr_t>(a.D2)) & 15))
     return "attn_lin: D/D2/R/O/P must be 16-byte aligned with rows that are multiples of 16 bytes";
-  const int tail_span = p.tail * 4;
+  const int tail_span = p.tail * 32;
+  const int tail_el = tail_span / ses;          // elements per row of the tail tile
   p.a_seg_bytes = p.kfull * TM * 128 + TM * tail_span;
   p.b_seg_bytes = p.kfull * TNh * 128 + TNh * tail_span;
   p.b_stage_bytes = p.nseg * p.b_seg_bytes;
@@ -537,16 +570,16 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     const PbGemmSeg& sg = a.seg[s];
     uint32_t ab = 0, bb = 0;
     if (p.kfull) {
-      if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, BK, TM, 128,
+      if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, p.bk, TM, 128,
                                                 &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, BK, TNh, 128,
+      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.bk, TNh, 128,
                                                 &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab * p.kfull; bbytes += bb * p.kfull;
     }
     if (p.tail) {
-      if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, 0, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, p.tail, TM,
+      if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, tail_el, TM,
                                                 tail_span, &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, 0, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.tail, TNh,
+      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, tail_el, TNh,
                                                 tail_span, &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab; bbytes += bb;
     }
@@ -593,15 +626,22 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (smem > 227 * 1024) return "attn_lin: shared memory budget exceeded";
   dim3 grid((a.Mr + TM - 1) / TM, a.nb * a.nh);
   const int c2m = a.C2 ? (a.D2 ? 2 : 1) : 0;
-  const bool whole = (a.d % BK) <= 16;                         // every full k-block is complete (no OOB-padded block)
-  void (*kern)(Params) = p16 ? attn_lin_kernel<-1, -1, -1, -1, true> : attn_lin_kernel<-1, -1, -1, -1, false>;
-#define PB_ATTN_CASE(NSEG_, KF_, NT_, C2M_)                                                      \
-  if (whole && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ * 8 && c2m == C2M_)            \
-    kern = p16 ? attn_lin_kernel<NSEG_, KF_, NT_, C2M_, true> : attn_lin_kernel<NSEG_, KF_, NT_, C2M_, false>;
-  PB_ATTN_CASE(2, 1, 1, 1) PB_ATTN_CASE(1, 1, 1, 0) PB_ATTN_CASE(1, 1, 1, 2)      // head dim 40 (SD-1.x 64x64 layers): JVP, VJP-A, VJP-B
-  PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // head dim 64 (SD-2.x)
-  PB_ATTN_CASE(2, 2, 2, 1) PB_ATTN_CASE(1, 2, 2, 0) PB_ATTN_CASE(1, 2, 2, 2)      // head dim 80 (SD-1.x 32x32 layers)
+  void (*kern)(Params) = s16 ? attn_lin_kernel<-1, -1, -1, -1, 2, 4> : p16 ? attn_lin_kernel<-1, -1, -1, -1, 1, 4> : attn_lin_kernel<-1, -1, -1, -1, 0, 4>;
+  // shape-specialised instantiations (straight-line issue loops): (segments, full k-blocks, tail k-steps, C2 mode, MMAs of the last block)
+#define PB_ATTN_CASE(NSEG_, KF_, NT_, C2M_)                                                                        \
+  if (!p16 && p.nk_last == 4 && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ && c2m == C2M_)                 \
+    kern = attn_lin_kernel<NSEG_, KF_, NT_, C2M_, 0, 4>;
+  PB_ATTN_CASE(2, 1, 1, 1) PB_ATTN_CASE(1, 1, 1, 0) PB_ATTN_CASE(1, 1, 1, 2)      // fp32 head dim 40 (SD-1.x 64x64 layers): JVP, VJP-A, VJP-B
+  PB_ATTN_CASE(2, 2, 0, 1) PB_ATTN_CASE(1, 2, 0, 0) PB_ATTN_CASE(1, 2, 0, 2)      // fp32 head dim 64 (SD-2.x)
+  PB_ATTN_CASE(2, 2, 2, 1) PB_ATTN_CASE(1, 2, 2, 0) PB_ATTN_CASE(1, 2, 2, 2)      // fp32 head dim 80 (SD-1.x 32x32 layers)
 #undef PB_ATTN_CASE
+#define PB_ATTN_CASE16(NSEG_, KF_, NT_, C2M_, NKL_)                                                                \
+  if (s16 && p.nk_last == NKL_ && p.nseg == NSEG_ && p.kfull == KF_ && p.tail == NT_ && c2m == C2M_)               \
+    kern = attn_lin_kernel<NSEG_, KF_, NT_, C2M_, 2, NKL_>;
+  PB_ATTN_CASE16(2, 1, 0, 1, 3) PB_ATTN_CASE16(1, 1, 0, 0, 3) PB_ATTN_CASE16(1, 1, 0, 2, 3)   // fp16 head dim 40: 80 of 128 bytes
+  PB_ATTN_CASE16(2, 1, 0, 1, 4) PB_ATTN_CASE16(1, 1, 0, 0, 4) PB_ATTN_CASE16(1, 1, 0, 2, 4)   // fp16 head dim 64
+  PB_ATTN_CASE16(2, 1, 1, 1, 4) PB_ATTN_CASE16(1, 1, 1, 0, 4) PB_ATTN_CASE16(1, 1, 1, 2, 4)   // fp16 head dim 80: 128 + 32 bytes
+#undef PB_ATTN_CASE16
   if (const char* err = pbhost::optin_smem(kern, 227 * 1024)) return err;   // once per (device, instantiation)
   kern<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(st)>>>(p);
   cudaError_t e = cudaGetLastError();

@@ -41,10 +41,10 @@ struct Val {                 // one activation tensor, [rows][C] per image (NHWC
   size_t p_off;              // primal copy in the primal cache (bytes)
   size_t t_off;              // k_max tangents / cotangents in the workspace (bytes)
   bool ginit;                // vjp bookkeeping: cotangent buffer already holds a contribution
-  // fp16-operand policy (analyse_f16): the JVP tangent / the VJP cotangent of this tensor is produced by an elementwise
-  // kernel for exactly one consumer, a GEMM that reads it as its A operand, and is stored as halves in the same buffer
-  bool t16 = false, g16 = false;
-  bool d16 = false;          // the JVP tangent is written as halves by its producer GEMM (Op::d16_jvp)
+  // all-fp16 tangent plan (pb_handle::t16): the tangent / cotangent of this tensor is stored as halves -- every tensor whose
+  // channel count keeps 16-byte rows (C % 8 == 0); the x_t-shaped input of conv_in (and the 4-channel eps of the full plan)
+  // stays fp32
+  bool h16 = false;
 };
 
 enum WKind { WK_VEC, WK_RAW, WK_LIN, WK_CONV3, WK_CONV3_S2 };
@@ -65,17 +65,15 @@ struct Op {
   size_t bias_eff_off = 0, mean_off = 0, rstd_off = 0;
   float eps = 0.f; int silu = 0, groups = 0;
   int conv = 0;                     // OP_GEMM: 1 = 3x3 / s1 / p1 implicit GEMM
-  int a16_jvp = 0;                  // OP_GEMM: the JVP reads its A operand (tangent of x) as fp16
-  int a16_vjp = 0;                  // OP_GEMM: the VJP reads its A operand (cotangent of y) as fp16: 1 stored so, 2 converted first
-  int d16_jvp = 0;                  // OP_GEMM: the JVP writes its output as fp16 (sole consumer: GEGLU, which reads halves)
   int pad_lo = 0, Ho = 0, Wo = 0;   // OP_IM2COL
   // OP_ATTN
   int heads = 0, d = 0, cross = 0, Nq = 0, Nk = 0, ldk = 0, ldq = 0, kv = -1;
   float scale = 0.f;
   size_t P_off = 0, Pt_off = 0, Qt_off = 0, Kt_off = 0, Vt_off = 0;
-  // fp16 copies for the fused linearisation kernel (p16 = 1): N-scaled P and P^T, and the transposed primal operands
+  // fp16 copies for the fused linearisation kernel (p16 = 1): scaled P and P^T, the transposed primal operands, and (all-fp16
+  // tangent plan) X16 = the primal score operands as halves: the [N][3C] q/k/v projection (self) or the [Nk][2C] text k/v (cross)
   int p16 = 0;
-  size_t P16_off = 0, Pt16_off = 0, Qt16_off = 0, Kt16_off = 0, Vt16_off = 0;
+  size_t P16_off = 0, Pt16_off = 0, Qt16_off = 0, Kt16_off = 0, Vt16_off = 0, X16_off = 0;
 };
 
 }  // namespace
@@ -105,8 +103,9 @@ struct pb_handle {
   int prec_p = 0, prec_t = 0, prec_a = 0;   // primal GEMMs / tangent weight GEMMs / tangent attention GEMMs
   int rnd = 1;                              // rounding flag of the pass being interpreted
   int fused_min_tokens = 512;               // self-attention layers with >= this many tokens use the fused kernel
-  int f16 = -1;                             // fp16-operand GEMMs on the tangent passes: -1 = if the backend has them
-  size_t w_cvt = 0, n_cvt = 0;              // fp16 staging of a multi-consumer cotangent (halves per tangent)
+  int f16 = -1;                             // fp16 tangents + fp16-operand GEMMs on the tangent passes: -1 = if the backend has them
+  bool t16 = false;                         // the plan stores every tangent / cotangent as halves (decided by pb_plan: f16 and an eligible geometry)
+  size_t w_cvt = 0, n_cvt = 0;              // fp32 staging of an fp16 tangent for the materialised attention path (floats per tangent)
   std::string err;
   long launches = 0;
   // CUDA graph of one iteration (jvp + vjp + orthonormalise)
@@ -139,9 +138,12 @@ struct pb_handle {
   float* T(int v) const {
     const Val& a = vals[alias.empty() ? v : alias[v]];
     size_t off = a.t_off;
-    if (slot) off += (size_t)slot * k_slot * a.rows * a.C * ((pass_vjp ? vals[v].g16 : (vals[v].t16 || vals[v].d16)) ? 2 : 4);
+    if (slot) off += (size_t)slot * k_slot * a.rows * a.C * (vals[v].h16 ? 2 : 4);
     return reinterpret_cast<float*>(work + off);
   }
+  bool is16(int v) const { return vals[v].h16; }
+  // io flags of a tangent-path kernel reading the tangent of val `vin` and writing the tangent of val `vout` (pb_kernels.h)
+  int io(int vin, int vout) const { return (vin >= 0 && is16(vin) ? PB_IN_F16 : 0) | (vout >= 0 && is16(vout) ? PB_OUT_F16 : rnd); }
   float* CP(size_t off) const { return reinterpret_cast<float*>(cache + slot * cache_stride + off); }
   float* WP(size_t off) const { return reinterpret_cast<float*>(work + off); }
   float* Wf(int w) const { return reinterpret_cast<float*>(packed + wspecs[w].fwd_off); }
@@ -154,7 +156,6 @@ struct pb_handle {
 namespace {
 
 float attn_pscale(int n);
-bool geglu_in16(const pb_handle* h, const Op& o);
 
 int fail(pb_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
@@ -268,7 +269,8 @@ struct Planner {
     int y = val(N, C);
     Op& o = push(OP_ATTN);
     o.x = q; o.y = y; o.heads = heads; o.d = C / heads; o.cross = cross; o.Nq = (int)N; o.Nk = Nk; o.kv = kv;
-    o.ldk = round4(Nk); o.ldq = round4((int)N);
+    // leading dimensions of the probability matrices / transposed operands: 16-byte rows for fp32 AND for their fp16 copies
+    o.ldk = h->use_f16() ? (Nk + 7) / 8 * 8 : round4(Nk); o.ldq = h->use_f16() ? ((int)N + 7) / 8 * 8 : round4((int)N);
     o.scale = 1.0f / std::sqrt((float)o.d);
     if (C % heads || o.d % 4) { error = "attention head dim must be a multiple of 4"; return -1; }
     o.P_off = cache_alloc((size_t)heads * N * o.ldk);
@@ -278,15 +280,20 @@ struct Planner {
       o.Pt_off = cache_alloc((size_t)heads * Nk * o.ldq);
       o.Qt_off = cache_alloc((size_t)C * o.ldq);
     }
-    static const int f16_mask = getenv("PB_F16_MASK") ? atoi(getenv("PB_F16_MASK")) : 31;   // bit 4: fp16 attention operands
-    if (!cross && h->use_f16() && (f16_mask & 16) && o.d <= 64 && N % 8 == 0 && Nk % 8 == 0 && pbk_attn_lin_supported(o.d, (int)N, Nk) == nullptr) {
-      o.p16 = 1;                                  // ldk == Nk and ldq == N here: the fp16 copies share the fp32 geometry
+    if (h->use_f16() && o.d % 8 == 0 && pbk_attn_lin_supported(o.d, (int)N, Nk) == nullptr) {
+      // fp16 copies for the fused kernel (same geometry as the fp32 tensors): scaled P (and P^T), V^T, K^T (and Q^T), and the
+      // primal score operands X16 ([N][3C] q/k/v projection, or the [Nk][2C] text k/v of a cross-attention layer)
+      o.p16 = 1;
       o.P16_off = cache_alloc((size_t)heads * N * o.ldk / 2);
-      o.Pt16_off = cache_alloc((size_t)heads * Nk * o.ldq / 2);
       o.Vt16_off = cache_alloc((size_t)C * o.ldk / 2);
       o.Kt16_off = cache_alloc((size_t)C * o.ldk / 2);
-      o.Qt16_off = cache_alloc((size_t)C * o.ldq / 2);
+      o.X16_off = cache_alloc(cross ? (size_t)Nk * 2 * C / 2 : (size_t)N * 3 * C / 2);
+      if (!cross) {
+        o.Pt16_off = cache_alloc((size_t)heads * Nk * o.ldq / 2);
+        o.Qt16_off = cache_alloc((size_t)C * o.ldq / 2);
+      }
     }
+    h->n_cvt = std::max(h->n_cvt, (size_t)N * (cross ? C : 3 * C));
     h->n_s1 = std::max(h->n_s1, (size_t)heads * N * o.ldk);
     if (!cross) h->n_s2 = std::max(h->n_s2, (size_t)heads * Nk * o.ldq);
     h->n_s3 = std::max(h->n_s3, (size_t)C * std::max(o.ldk, o.ldq));
@@ -437,46 +444,29 @@ struct Planner {
   }
 };
 
-// fp16-operand policy.  kind::f16 carries the same 10-bit mantissa as kind::tf32 at half the operand bytes (the big
-// convolutions are bound by L2 -> SM bytes, profiles/r1b_gemm_per_shape.txt).  A GEMM's A operand may be fp16 when the
-// tensor is written by ONE elementwise kernel (which then stores halves, round_tf32 = 2) and read by nothing else:
-//   JVP: x of the GEMM is produced by GN / LN / GEGLU / im2col / upsample and has no other consumer
-//   VJP: y of the GEMM (no residual) has exactly one consumer, a GN / LN / GEGLU op, whose VJP kernel writes the cotangent
-// 3x3 convolutions whose cotangent has several contributors convert it once (pbk_to_f16) instead.
-void analyse_f16(pb_handle* h) {
+// All-fp16 tangent plan.  fp16 carries the same 10-bit mantissa as TF32 at half the bytes, and every tangent / cotangent
+// tensor of an iteration is read and written through HBM / L2 by a bandwidth- or operand-delivery-bound kernel
+// (profiles/r1final_launches_sd15_mid_k5.txt), so the plan stores ALL of them as halves: every weight GEMM runs kind::f16 with
+// fp16 output (and fp16 residual), the elementwise linearisation kernels read and write halves (pb_lin16.cu), the fused
+// attention kernel takes fp16 score operands.  Only the x_t-shaped ends stay fp32 (conv_in's 3- / 4-channel side, V, W, U).
+// Eligible when every GEMM has fp16 weight copies and every tensor a GEMM / elementwise kernel touches keeps 16-byte rows.
+void decide_t16(pb_handle* h) {
+  h->t16 = false;
   if (!h->use_f16()) return;
-  const int nv = (int)h->vals.size();
-  std::vector<int> consumers(nv, 0), producer(nv, -1);
-  for (int i = 0; i < (int)h->ops.size(); ++i) {
-    const Op& o = h->ops[i];
-    if (o.y >= 0 && o.kind != OP_OUT) producer[o.y] = i;
-    for (int v : {o.x, o.x2, o.res}) if (v >= 0) ++consumers[v];
+  std::vector<char> thin(h->vals.size(), 0);                 // touched only by the direct conv / the NCHW <-> NHWC ends
+  for (const Op& o : h->ops) {
+    if (o.kind == OP_IN) thin[o.y] = 1;
+    if (o.kind == OP_CONV_DIRECT && h->vals[o.y].C % 8) thin[o.y] = 1;    // eps head of the full plan (4 channels)
   }
-  // PB_F16_MASK (debug): bit 0 JVP convs, 1 JVP linears, 2 VJP stored-as-fp16, 3 VJP converted convs, 4 attention (Planner::attn)
-  const char* env = getenv("PB_F16_MASK");
-  const int mask = env ? atoi(env) : 31;
-  auto elementwise = [&](OpKind k, bool vjp) {
-    return k == OP_GN || k == OP_LN || k == OP_GEGLU || (!vjp && (k == OP_IM2COL || k == OP_UPSAMPLE));
-  };
-  size_t cvt = 0;
-  for (int i = 0; i < (int)h->ops.size(); ++i) {
-    Op& o = h->ops[i];
-    if (o.kind != OP_GEMM || h->wspecs[o.w].fwd16_off == 0) continue;
-    const Val& vx = h->vals[o.x]; const Val& vy = h->vals[o.y];
-    if (vx.C % 8 || vy.C % 8) continue;                        // fp16 rows must keep 16-byte strides
-    if ((mask & (o.conv ? 1 : 2)) && consumers[o.x] == 1 && producer[o.x] >= 0 && elementwise(h->ops[producer[o.x]].kind, false)) {
-      o.a16_jvp = 1; h->vals[o.x].t16 = true;
-    }
-    if (o.a16_jvp && (mask & 2) && !o.conv && o.res < 0 && consumers[o.y] == 1)
-      for (const Op& c : h->ops)
-        if (c.kind == OP_GEGLU && c.x == o.y) { o.d16_jvp = 1; h->vals[o.y].d16 = true; }    // ff1 -> GEGLU: the widest tensor of a transformer block
-    if ((mask & 4) && o.res < 0 && consumers[o.y] == 1) {
-      for (const Op& c : h->ops)
-        if (c.x == o.y && elementwise(c.kind, true)) { o.a16_vjp = 1; h->vals[o.y].g16 = true; }
-    }
-    if ((mask & 8) && !o.a16_vjp && o.conv) { o.a16_vjp = 2; cvt = std::max(cvt, (size_t)vy.rows * vy.C); }
+  for (const Op& o : h->ops) {
+    if (o.kind == OP_GEMM && h->wspecs[o.w].fwd16_off == 0) return;
+    if (o.kind == OP_IN || o.kind == OP_OUT || o.kind == OP_CONV_DIRECT) continue;
+    for (int v : {o.x, o.x2, o.y, o.res})
+      if (v >= 0 && (thin[v] || h->vals[v].C % 8)) return;
+    if (o.kind == OP_ATTN && ((o.d % 8) || (o.ldk % 8) || (!o.cross && o.ldq % 8))) return;
   }
-  h->n_cvt = cvt;
+  h->t16 = true;
+  for (size_t v = 0; v < h->vals.size(); ++v) h->vals[v].h16 = !thin[v] && h->vals[v].C % 8 == 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,8 +536,9 @@ int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
   if (o.res >= 0) { g.R = primal ? h->P(o.res) : h->T(o.res); g.ldr = vy.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = primal ? h->prec_p : h->prec_t;
-  if (!primal && o.a16_jvp) { g.seg[0].B = h->Wf16(o.w); g.ab_dtype = PB_GEMM_F16; }    // A holds halves (Val::t16)
-  if (!primal && o.d16_jvp) g.d_dtype = PB_GEMM_F16;
+  if (!primal && h->t16) {                                   // halves in (tangent, weights), halves out (and residual)
+    g.seg[0].B = h->Wf16(o.w); g.ab_dtype = PB_GEMM_F16; g.d_dtype = PB_GEMM_F16; g.round_tf32 = 0;
+  }
   CK(gemm_call(h, g, st));
   return PB_OK;
 }
@@ -559,23 +550,17 @@ int run_gemm_bwd(pb_handle* h, const Op& o, int nb, pb_stream st) {
   if (vx.ginit) { g.R = h->T(o.x); g.ldr = vx.C; g.beta = 1.f; }
   g.round_tf32 = h->rnd;
   g.precise = h->prec_t;
-  if (o.a16_vjp) {
-    if (o.a16_vjp == 2) {                                      // several contributors summed in fp32: convert once
-      CK(pbk_to_f16(h->WP(h->w_cvt), h->T(o.y), (size_t)vy.rows * vy.C * nb, st));
-      g.seg[0].A = h->WP(h->w_cvt);
-    }
-    g.seg[0].B = h->Wb16(o.w); g.ab_dtype = PB_GEMM_F16;
-  }
+  if (h->t16) { g.seg[0].B = h->Wb16(o.w); g.ab_dtype = PB_GEMM_F16; g.d_dtype = PB_GEMM_F16; g.round_tf32 = 0; }
   CK(gemm_call(h, g, st));
   vx.ginit = true;
   if (o.res >= 0) {
     Val& vr = h->vals[o.res];
-    if (!vr.ginit && !o.a16_vjp) {
+    if (!vr.ginit) {
       // first contribution to the residual input: y's cotangent buffer is dead after this op, so it BECOMES the residual's
       // cotangent buffer (later contributions accumulate into it in place) instead of being copied
       h->alias[o.res] = h->alias[o.y];
     } else {
-      CK(pbk_copy2d(h->T(o.res), vr.C, h->T(o.y), vy.C, vy.rows * nb, vy.C, vr.ginit ? 1.f : 0.f, h->rnd, st));
+      CK(pbk_copy2d(h->T(o.res), vr.C, h->T(o.y), vy.C, vy.rows * nb, vy.C, vr.ginit ? 1.f : 0.f, h->io(o.y, o.res), st));
     }
     vr.ginit = true;
   }
@@ -611,12 +596,17 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
   if (!o.cross) {
     CK(pbk_transpose(h->CP(o.Qt_off), o.ldq, 0, (long)d * o.ldq, Q, ldq_, 0, d, 1, hd, N, d, 0.f, h->rnd, st));
     CK(pbk_transpose(h->CP(o.Pt_off), o.ldq, 0, (long)Nk * o.ldq, P, ldk, 0, (long)N * ldk, 1, hd, N, Nk, 0.f, h->rnd, st));
-    if (o.p16) {
-      // scaled fp16 copies of P and P^T (attn_pscale) and plain fp16 copies of the transposed primal operands
-      CK(pbk_to_f16_scaled(h->CP(o.P16_off), P, (size_t)hd * N * ldk, attn_pscale(Nk), st));
+  }
+  if (o.p16 && h->t16) {
+    // fp16 copies for the fused kernel: scaled P (and P^T, attn_pscale), the transposed primal operands, the score operands
+    CK(pbk_to_f16_scaled(h->CP(o.P16_off), P, (size_t)hd * N * ldk, attn_pscale(Nk), st));
+    CK(pbk_to_f16(h->CP(o.Vt16_off), Vt, (size_t)C * ldk, st));
+    CK(pbk_to_f16(h->CP(o.Kt16_off), Kt, (size_t)C * ldk, st));
+    if (o.cross) {
+      CK(pbk_to_f16(h->CP(o.X16_off), h->CP(o.bias_eff_off), (size_t)Nk * 2 * C, st));
+    } else {
+      CK(pbk_to_f16(h->CP(o.X16_off), h->P(o.x), (size_t)N * 3 * C, st));
       CK(pbk_to_f16_scaled(h->CP(o.Pt16_off), h->CP(o.Pt_off), (size_t)hd * Nk * o.ldq, attn_pscale(N), st));
-      CK(pbk_to_f16(h->CP(o.Vt16_off), Vt, (size_t)C * ldk, st));
-      CK(pbk_to_f16(h->CP(o.Kt16_off), Kt, (size_t)C * ldk, st));
       CK(pbk_to_f16(h->CP(o.Qt16_off), h->CP(o.Qt_off), (size_t)C * o.ldq, st));
     }
   }
@@ -634,46 +624,45 @@ int run_attn_primal(pb_handle* h, const Op& o, const float* ctx, pb_stream st) {
 // to |S| ~ 1e3; the kernel divides the products by the same factor and saturates T at the fp16 maximum.
 float attn_pscale(int n) { return std::exp2(std::floor(0.5f * std::log2((float)std::max(n, 1)) + 0.5f)); }
 
-// the GEGLU input tangent was written as halves by its producer GEMM (Op::d16_jvp)
-bool geglu_in16(const pb_handle* h, const Op& o) {
-  for (const Op& g : h->ops)
-    if (g.kind == OP_GEMM && g.y == o.x) return g.d16_jvp != 0;
-  return false;
-}
-
 bool use_fused(const pb_handle* h, const Op& o) {
-  return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
+  return !o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr && (!h->t16 || o.p16);
 }
 // cross-attention (77 text keys: three 32-column steps per tile) through the same kernel: one launch instead of
 // GEMM + softmax-linearisation + GEMM and no score tangent in HBM
 bool use_fused_cross(const pb_handle* h, const Op& o) {
   static const bool off = getenv("PB_NO_FUSED_CROSS") != nullptr;      // A/B switch
-  return !off && o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr;
+  return !off && o.cross && o.Nq >= h->fused_min_tokens && pbk_attn_lin_supported(o.d, o.Nq, o.Nk) == nullptr && (!h->t16 || o.p16);
 }
+
+// element offset into a tangent buffer that holds floats (es = 4) or halves (es = 2)
+inline float* el(const void* p, long n, int es) { return reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(p)) + n * es); }
 
 int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
   float* P = h->CP(o.P_off); float* Vt = h->CP(o.Vt_off);
   float* dS = h->WP(h->w_s1);
   const long sS = (long)hd * N * ldk;
+  const bool t16 = h->t16;
+  const int es = t16 ? 2 : 4;                    // element size of the tangent buffers
   if (use_fused(h, o)) {
     // dO = [P o dS] V - rowsum(P o dS) o O + P dV   with dS = (dQ K^T + Q dK^T)/sqrt(d) never stored and P streamed once
-    const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
+    const float* qkv = t16 ? h->CP(o.X16_off) : h->P(o.x);       // primal [N][3C] (fp16 copy in the all-fp16 plan)
+    const float* dqkv = h->T(o.x);
     float* dVt = h->WP(h->w_s3);
-    const bool p16 = o.p16 && h->use_f16();
-    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dqkv + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f, p16 ? 2 : h->rnd, st));
+    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, el(dqkv, 2 * C, es), 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f,
+                     t16 ? (PB_IN_F16 | PB_OUT_F16) : h->rnd, st));
     PbAttnLin a{};
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 2;
     a.seg[0].A = dqkv; a.seg[0].lda = 3 * C; a.seg[0].sAb = (long)N * 3 * C; a.seg[0].sAh = d;
-    a.seg[0].B = qkv + C; a.seg[0].ldb = 3 * C; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.seg[0].B = el(qkv, C, es); a.seg[0].ldb = 3 * C; a.seg[0].sBb = 0; a.seg[0].sBh = d;
     a.seg[1].A = qkv; a.seg[1].lda = 3 * C; a.seg[1].sAb = 0; a.seg[1].sAh = d;
-    a.seg[1].B = dqkv + C; a.seg[1].ldb = 3 * C; a.seg[1].sBb = (long)N * 3 * C; a.seg[1].sBh = d;
+    a.seg[1].B = el(dqkv, C, es); a.seg[1].ldb = 3 * C; a.seg[1].sBb = (long)N * 3 * C; a.seg[1].sBh = d;
     a.alpha1 = o.scale; a.alpha2 = 1.f; a.beta = 0.f;
     a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
     a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
     a.C2 = dVt; a.ldc2 = ldk; a.sC2h = (long)d * ldk; a.sC2b = (long)C * ldk;
-    if (p16) { a.p16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
+    if (t16) { a.p16 = a.s16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
@@ -681,7 +670,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   }
   if (o.cross && use_fused_cross(h, o)) {
     // dO = [P o dS] V - rowsum(P o dS) o O with dS = dQ K^T / sqrt(d); the text keys / values are constants
-    const float* kv = h->CP(o.bias_eff_off);
+    const float* kv = t16 ? h->CP(o.X16_off) : h->CP(o.bias_eff_off);
     PbAttnLin a{};
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
     a.seg[0].A = h->T(o.x); a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
@@ -690,19 +679,28 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
     a.want_rsum = 1; a.O = h->P(o.y); a.ldo = C;
     a.C1 = Vt; a.ldc = ldk; a.sCh = (long)d * ldk;
+    if (t16) { a.p16 = a.s16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Vt16_off); }
     a.D = h->T(o.y); a.ldd = C; a.sDb = (long)N * C;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
     return PB_OK;
   }
+  // materialised path (few tokens or a head dim the fused kernel does not take): fp32 / TF32 inside; in the all-fp16 plan the
+  // tangent is converted once on the way in and the last product writes halves
+  const long ldx = o.cross ? C : 3 * C;
+  const float* dx = h->T(o.x);
+  if (t16) {
+    CK(pbk_to_f32(h->WP(h->w_cvt), dx, (size_t)nb * N * ldx, st));
+    dx = h->WP(h->w_cvt);
+  }
   if (o.cross) {
     const float* kv = h->CP(o.bias_eff_off);
-    PbGemm g = plain_gemm(h->T(o.x), C, N, kv, 2 * C, Nk, d, dS, ldk);
+    PbGemm g = plain_gemm(dx, C, N, kv, 2 * C, Nk, d, dS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
     g.precise = h->prec_a; CK(gemm_call(h, g, st));
   } else {
-    const float* qkv = h->P(o.x); const float* dqkv = h->T(o.x);
+    const float* qkv = h->P(o.x); const float* dqkv = dx;
     PbGemm g = plain_gemm(dqkv, 3 * C, N, qkv + C, 3 * C, Nk, d, dS, ldk);       // dQ K^T
     g.seg[0].sAb = (long)N * 3 * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.nseg = 2;                                                                    // + Q dK^T
@@ -715,9 +713,10 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   PbGemm g = plain_gemm(dS, ldk, N, Vt, ldk, d, Nk, h->T(o.y), C);                // dP V
   g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
   g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
+  if (t16) { g.d_dtype = PB_GEMM_F16; g.round_tf32 = 0; }
   if (!o.cross) {                                                                  // + P dV
     float* dVt = h->WP(h->w_s3);
-    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, h->T(o.x) + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f,
+    CK(pbk_transpose(dVt, ldk, (long)C * ldk, (long)d * ldk, dx + 2 * C, 3 * C, (long)N * 3 * C, d, nb, hd, Nk, d, 0.f,
                      h->rnd, st));
     g.nseg = 2;
     g.seg[1].A = P; g.seg[1].lda = ldk; g.seg[1].sAb = 0; g.seg[1].sAh = (long)N * ldk;
@@ -733,63 +732,59 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const float* gO = h->T(o.y);
   float* gS = h->WP(h->w_s1);
   const long sS = (long)hd * N * ldk;
+  const bool t16 = h->t16;
+  const int es = t16 ? 2 : 4;
   const float* V; long ldkv;
   if (o.cross) { V = h->CP(o.bias_eff_off) + C; ldkv = 2 * C; } else { V = h->P(o.x) + 2 * C; ldkv = 3 * C; }
-  if (use_fused(h, o)) {
-    float* gx = h->T(o.x); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
-    float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
-    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));           // delta = rowsum(Obar o O)
+  const bool fused_self = use_fused(h, o), fused_cross = o.cross && use_fused_cross(h, o);
+  if (fused_self || fused_cross) {
+    // the value operand of the score product as the fused kernel reads it: halves in the all-fp16 plan (X16: [N][3C] / [Nk][2C])
+    const float* Vs = t16 ? el(h->CP(o.X16_off), o.cross ? C : 2 * C, 2) : V;
+    float* gx = h->T(o.x); float* delta = h->WP(h->w_delta);
+    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, t16 ? PB_IN_F16 : 0, st));   // delta = rowsum(Obar o O)
+    const long ldx = o.cross ? C : 3 * C;
     PbAttnLin a{};
-    // Qbar = scale * [P o (Obar V^T - delta_row)] K
+    // Qbar = scale * [P o (Obar V^T - delta_row)] K   (cross-attention: the only cotangent -- text keys / values are constants)
     a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
     a.seg[0].A = gO; a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
-    a.seg[0].B = V; a.seg[0].ldb = ldkv; a.seg[0].sBb = 0; a.seg[0].sBh = d;
+    a.seg[0].B = Vs; a.seg[0].ldb = ldkv; a.seg[0].sBb = 0; a.seg[0].sBh = d;
     a.alpha1 = 1.f; a.alpha2 = o.scale;
     a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
     a.delta = delta; a.delta_mode = 1;
     a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
-    const bool p16 = o.p16 && h->use_f16();
-    if (p16) { a.p16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Kt16_off); }
-    a.D = gx; a.ldd = 3 * C; a.sDb = (long)N * 3 * C;
+    if (t16) { a.p16 = a.s16 = 1; a.p_scale = attn_pscale(Nk); a.Pm = h->CP(o.P16_off); a.C1 = h->CP(o.Kt16_off); }
+    a.D = gx; a.ldd = ldx; a.sDb = (long)N * ldx;
     a.round_tf32 = h->rnd;
     CK(attn_lin_call(h, a, st));
+    h->vals[o.x].ginit = true;
+    if (o.cross) return PB_OK;
     // Kbar = scale * [P^T o (V Obar^T - delta_col)] Q  and  Vbar = P^T Obar  (rows = keys, columns = queries; P^T streamed once)
-    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, p16 ? 2 : h->rnd, st));
+    float* gOt = h->WP(h->w_s3);
+    float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
+    CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f,
+                     t16 ? (PB_IN_F16 | PB_OUT_F16) : h->rnd, st));
     PbAttnLin b{};
     b.Mr = Nk; b.Nc = N; b.d = d; b.nb = nb; b.nh = hd; b.nseg = 1;
-    b.seg[0].A = V; b.seg[0].lda = ldkv; b.seg[0].sAb = 0; b.seg[0].sAh = d;
+    b.seg[0].A = Vs; b.seg[0].lda = ldkv; b.seg[0].sAb = 0; b.seg[0].sAh = d;
     b.seg[0].B = gO; b.seg[0].ldb = C; b.seg[0].sBb = (long)N * C; b.seg[0].sBh = d;
     b.alpha1 = 1.f; b.alpha2 = o.scale;
     b.Pm = Pt; b.ldp = ldq; b.sPh = (long)Nk * ldq;
     b.delta = delta; b.delta_mode = 2;
     b.C1 = Qt; b.ldc = ldq; b.sCh = (long)d * ldq;
-    b.D = gx + C; b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
+    b.D = el(gx, C, es); b.ldd = 3 * C; b.sDb = (long)N * 3 * C;
     b.C2 = gOt; b.ldc2 = ldq; b.sC2h = (long)d * ldq; b.sC2b = (long)C * ldq;
-    b.D2 = gx + 2 * C; b.ldd2 = 3 * C; b.sD2b = (long)N * 3 * C;
-    if (p16) { b.p16 = 1; b.p_scale = attn_pscale(N); b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
+    b.D2 = el(gx, 2 * C, es); b.ldd2 = 3 * C; b.sD2b = (long)N * 3 * C;
+    if (t16) { b.p16 = b.s16 = 1; b.p_scale = attn_pscale(N); b.Pm = h->CP(o.Pt16_off); b.C1 = h->CP(o.Qt16_off); }
     b.round_tf32 = h->rnd;
     CK(attn_lin_call(h, b, st));
-    h->vals[o.x].ginit = true;
     return PB_OK;
   }
-  if (o.cross && use_fused_cross(h, o)) {
-    // Qbar = scale * [P o (Obar V^T - delta_row)] K,  delta = rowsum(Obar o O); no Kbar / Vbar (text constants)
-    float* delta = h->WP(h->w_delta);
-    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));
-    PbAttnLin a{};
-    a.Mr = N; a.Nc = Nk; a.d = d; a.nb = nb; a.nh = hd; a.nseg = 1;
-    a.seg[0].A = gO; a.seg[0].lda = C; a.seg[0].sAb = (long)N * C; a.seg[0].sAh = d;
-    a.seg[0].B = V; a.seg[0].ldb = ldkv; a.seg[0].sBb = 0; a.seg[0].sBh = d;
-    a.alpha1 = 1.f; a.alpha2 = o.scale;
-    a.Pm = P; a.ldp = ldk; a.sPh = (long)N * ldk;
-    a.delta = delta; a.delta_mode = 1;
-    a.C1 = Kt; a.ldc = ldk; a.sCh = (long)d * ldk;
-    a.D = h->T(o.x); a.ldd = C; a.sDb = (long)N * C;
-    a.round_tf32 = h->rnd;
-    CK(attn_lin_call(h, a, st));
-    h->vals[o.x].ginit = true;
-    return PB_OK;
+  // materialised path: fp32 / TF32 inside; all-fp16 plan: convert the cotangent once, the products into gx write halves
+  if (t16) {
+    CK(pbk_to_f32(h->WP(h->w_cvt), gO, (size_t)nb * N * C, st));
+    gO = h->WP(h->w_cvt);
   }
+  const int dd = t16 ? PB_GEMM_F16 : PB_GEMM_F32;
   {                                                                                // dP = gO V^T
     PbGemm g = plain_gemm(gO, C, N, V, ldkv, Nk, d, gS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
@@ -802,7 +797,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   {                                                                                // gQ = scale gS K
     PbGemm g = plain_gemm(gS, ldk, N, Kt, ldk, d, Nk, gx, ldx);
     g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
-    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
     g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   h->vals[o.x].ginit = true;
@@ -811,7 +806,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
   float* gSt = h->WP(h->w_s2); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
   const long sSt = (long)hd * Nk * ldq;
-  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, st));
+  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, 0, st));
   {                                                                                // dP^T = V gO^T
     PbGemm g = plain_gemm(V, ldkv, Nk, gO, C, N, d, gSt, ldq);
     g.seg[0].sAh = d; g.seg[0].sBb = (long)N * C; g.seg[0].sBh = d;
@@ -820,16 +815,16 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   }
   CK(pbk_attn_ds(Pt, gSt, delta, 1.f, nb, hd, Nk, N, ldq, 1, h->rnd, st));        // gS^T = P^T o (dP^T - delta_i)
   {                                                                                // gK = scale gS^T Q
-    PbGemm g = plain_gemm(gSt, ldq, Nk, Qt, ldq, d, N, gx + C, ldx);
+    PbGemm g = plain_gemm(gSt, ldq, Nk, Qt, ldq, d, N, el(gx, C, es), ldx);
     g.seg[0].sAb = sSt; g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBh = (long)d * ldq;
-    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = h->rnd;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
     g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
   {                                                                                // gV = P^T gO
-    PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, gx + 2 * C, ldx);
+    PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, el(gx, 2 * C, es), ldx);
     g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
-    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
+    g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
     g.precise = h->prec_a; CK(gemm_call(h, g, st));
   }
   return PB_OK;
@@ -861,7 +856,7 @@ int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h
         break;
       }
       case OP_CONV_DIRECT:
-        CK(pbk_conv3x3_direct(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), h->Wf(o.bias), h->vals[o.y].C, h->P(o.y), 0.f, st));
+        CK(pbk_conv3x3_direct(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), h->Wf(o.bias), h->vals[o.y].C, h->P(o.y), 0.f, 0, st));
         break;
       case OP_GN: {
         const Val& v = h->vals[o.x];
@@ -927,18 +922,19 @@ int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_strea
         break;
       }
       case OP_CONV_DIRECT:
-        CK(pbk_conv3x3_direct(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), nullptr, h->vals[o.y].C, h->T(o.y), 0.f, st));
+        CK(pbk_conv3x3_direct(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->Wf(o.w), nullptr, h->vals[o.y].C, h->T(o.y), 0.f,
+                              h->io(o.x, o.y) & ~1, st));
         break;
       case OP_GN: {
         const Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->vals[o.y].t16 ? 2 : h->rnd, h->WP(h->w_gn), st));
+                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->io(o.x, o.y), h->WP(h->w_gn), st));
         break;
       }
       case OP_LN: {
         const Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.x), nb, 0, h->T(o.y), 0.f,
-                      h->vals[o.y].t16 ? 2 : h->rnd, st));
+                      h->io(o.x, o.y), st));
         break;
       }
       case OP_GEMM:
@@ -946,26 +942,27 @@ int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_strea
         break;
       case OP_CONCAT: {
         const Val& a = h->vals[o.x]; const Val& b = h->vals[o.x2]; const Val& y = h->vals[o.y];
-        CK(pbk_copy2d(h->T(o.y), y.C, h->T(o.x), a.C, a.rows * nb, a.C, 0.f, 0, st));
-        CK(pbk_copy2d(h->T(o.y) + a.C, y.C, h->T(o.x2), b.C, b.rows * nb, b.C, 0.f, 0, st));
+        const int f = h->t16 ? (PB_IN_F16 | PB_OUT_F16) : 0, es = h->t16 ? 2 : 4;
+        CK(pbk_copy2d(h->T(o.y), y.C, h->T(o.x), a.C, a.rows * nb, a.C, 0.f, f, st));
+        CK(pbk_copy2d(el(h->T(o.y), a.C, es), y.C, h->T(o.x2), b.C, b.rows * nb, b.C, 0.f, f, st));
         break;
       }
       case OP_IM2COL:
-        CK(pbk_im2col_s2(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
+        CK(pbk_im2col_s2(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, o.pad_lo, o.Ho, o.Wo, h->T(o.y), h->io(o.x, o.y), st));
         break;
       case OP_UPSAMPLE:
-        CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->vals[o.y].t16 ? 2 : h->rnd, st));
+        CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->io(o.x, o.y), st));
         break;
       case OP_GEGLU:
-        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y),
-                         (h->vals[o.y].t16 ? 2 : h->rnd) | (geglu_in16(h, o) ? 4 : 0), st));
+        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->io(o.x, o.y), st));
         break;
       case OP_ATTN:
         if (int e = run_attn_jvp(h, o, nb, st)) return e;
         break;
       case OP_OUT: {
         const Val& v = h->vals[o.x];
-        CK(pbk_transpose(U, v.rows, v.rows * v.C, 0, h->T(o.x), v.C, v.rows * v.C, 0, nb, 1, (int)v.rows, v.C, 0.f, 0, st));
+        CK(pbk_transpose(U, v.rows, v.rows * v.C, 0, h->T(o.x), v.C, v.rows * v.C, 0, nb, 1, (int)v.rows, v.C, 0.f,
+                         h->is16(o.x) ? PB_IN_F16 : 0, st));
         break;
       }
     }
@@ -995,7 +992,7 @@ int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_st
     switch (o.kind) {
       case OP_OUT: {
         Val& v = h->vals[o.x];
-        CK(pbk_transpose(h->T(o.x), v.C, v.rows * v.C, 0, U, v.rows, v.rows * v.C, 0, nb, 1, v.C, (int)v.rows, 0.f, h->rnd, st));
+        CK(pbk_transpose(h->T(o.x), v.C, v.rows * v.C, 0, U, v.rows, v.rows * v.C, 0, nb, 1, v.C, (int)v.rows, 0.f, h->io(-1, o.x), st));
         v.ginit = true;
         break;
       }
@@ -1004,25 +1001,26 @@ int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_st
         break;
       case OP_GEGLU:
         if (h->vals[o.x].ginit) return fail(h, PB_ESTATE, "internal: GEGLU input has several consumers");
-        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->vals[o.x].g16 ? 2 : h->rnd, st));
+        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->io(o.y, o.x), st));
         h->vals[o.x].ginit = true;
         break;
       case OP_UPSAMPLE: {
         Val& v = h->vals[o.x];
-        CK(pbk_upsample2x_vjp(h->T(o.y), nb, o.H, o.W, v.C, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, st));
+        CK(pbk_upsample2x_vjp(h->T(o.y), nb, o.H, o.W, v.C, h->T(o.x), v.ginit ? 1.f : 0.f, h->io(o.y, o.x), st));
         v.ginit = true;
         break;
       }
       case OP_IM2COL: {
         Val& v = h->vals[o.x];
-        CK(pbk_col2im_s2(h->T(o.y), nb, o.H, o.W, v.C, o.pad_lo, o.Ho, o.Wo, h->T(o.x), v.ginit ? 1.f : 0.f, h->rnd, st));
+        CK(pbk_col2im_s2(h->T(o.y), nb, o.H, o.W, v.C, o.pad_lo, o.Ho, o.Wo, h->T(o.x), v.ginit ? 1.f : 0.f, h->io(o.y, o.x), st));
         v.ginit = true;
         break;
       }
       case OP_CONCAT: {
         Val& a = h->vals[o.x]; Val& b = h->vals[o.x2]; const Val& y = h->vals[o.y];
-        CK(pbk_copy2d(h->T(o.x), a.C, h->T(o.y), y.C, a.rows * nb, a.C, a.ginit ? 1.f : 0.f, h->rnd, st));
-        CK(pbk_copy2d(h->T(o.x2), b.C, h->T(o.y) + a.C, y.C, b.rows * nb, b.C, b.ginit ? 1.f : 0.f, h->rnd, st));
+        const int f = h->t16 ? (PB_IN_F16 | PB_OUT_F16) : h->rnd, es = h->t16 ? 2 : 4;
+        CK(pbk_copy2d(h->T(o.x), a.C, h->T(o.y), y.C, a.rows * nb, a.C, a.ginit ? 1.f : 0.f, f, st));
+        CK(pbk_copy2d(h->T(o.x2), b.C, el(h->T(o.y), a.C, es), y.C, b.rows * nb, b.C, b.ginit ? 1.f : 0.f, f, st));
         a.ginit = b.ginit = true;
         break;
       }
@@ -1032,20 +1030,20 @@ int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_st
       case OP_LN: {
         Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.y), nb, 1, h->T(o.x),
-                      v.ginit ? 1.f : 0.f, v.g16 ? 2 : h->rnd, st));
+                      v.ginit ? 1.f : 0.f, h->io(o.y, o.x), st));
         v.ginit = true;
         break;
       }
       case OP_GN: {
         Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, v.g16 ? 2 : h->rnd, h->WP(h->w_gn), st));
+                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, h->io(o.y, o.x), h->WP(h->w_gn), st));
         v.ginit = true;
         break;
       }
       case OP_CONV_DIRECT: {
         Val& v = h->vals[o.x];
-        CK(pbk_conv3x3_direct(h->T(o.y), nb, o.H, o.W, h->vals[o.y].C, h->Wb(o.w), nullptr, v.C, h->T(o.x), 0.f, st));
+        CK(pbk_conv3x3_direct(h->T(o.y), nb, o.H, o.W, h->vals[o.y].C, h->Wb(o.w), nullptr, v.C, h->T(o.x), 0.f, h->io(o.y, o.x) & ~1, st));
         v.ginit = true;
         break;
       }
@@ -1183,15 +1181,14 @@ PB_API int pb_plan_summary(const pb_handle* h, pb_plan_info* info) {
     if (o.kind == OP_GEMM) {
       ++info->n_gemm;
       info->n_conv3x3 += o.conv ? 1 : 0;
-      info->n_gemm_f16_jvp += o.a16_jvp ? 1 : 0;
-      info->n_gemm_f16_vjp_stored += o.a16_vjp == 1 ? 1 : 0;
-      info->n_gemm_f16_vjp_converted += o.a16_vjp == 2 ? 1 : 0;
-      info->n_gemm_d16_jvp += o.d16_jvp ? 1 : 0;
+      info->n_gemm_f16_jvp += h->t16 ? 1 : 0;                // all-fp16 tangent plan: every GEMM of both passes, halves in and out
+      info->n_gemm_f16_vjp_stored += h->t16 ? 1 : 0;
+      info->n_gemm_d16_jvp += h->t16 ? 1 : 0;
     } else if (o.kind == OP_ATTN) {
       ++info->n_attn;
       info->n_attn_fused_self += use_fused(h, o) ? 1 : 0;
       info->n_attn_fused_cross += use_fused_cross(h, o) ? 1 : 0;
-      info->n_attn_p16 += (use_fused(h, o) && o.p16) ? 1 : 0;
+      info->n_attn_p16 += ((use_fused(h, o) || use_fused_cross(h, o)) && o.p16 && h->t16) ? 1 : 0;
     }
   }
   return PB_OK;
@@ -1312,7 +1309,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   if (!p.build()) return fail(h, PB_EINVAL, p.error);
   h->n_in = (long)h->cfg.in_channels * height * width;
   h->n_out = h->vals[h->out_val].rows * h->vals[h->out_val].C;
-  analyse_f16(h);
+  decide_t16(h);
   const size_t K = k_max;
   h->w_s1 = p.work_alloc(h->n_s1 * K); h->w_s2 = p.work_alloc(h->n_s2 * K); h->w_s3 = p.work_alloc(h->n_s3 * K);
   h->w_delta = p.work_alloc(h->n_delta * K); h->w_gn = p.work_alloc(h->n_gn + 64);
@@ -1322,7 +1319,7 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4 + 2 * K);      // (dist^2, not-close count) per problem slot
   h->w_x = p.work_alloc((size_t)h->n_in);
   h->n_splitk = kSplitFloats; h->w_splitk = p.work_alloc(kSplitFloats);
-  h->w_cvt = p.work_alloc((h->n_cvt * K + 1) / 2);          // halves
+  h->w_cvt = p.work_alloc(h->t16 ? h->n_cvt * K : 0);
   h->sizes.packed_weight_bytes = h->packed_top; h->sizes.primal_cache_bytes = h->cache_top; h->sizes.workspace_bytes = h->work_top;
   h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out;
   if (sizes) *sizes = h->sizes;

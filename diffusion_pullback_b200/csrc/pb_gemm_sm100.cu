@@ -581,7 +581,6 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   using namespace pbgemm;
   if (g.M <= 0 || g.N <= 0) return "gemm: empty problem";
   const int ab16 = g.ab_dtype == PB_GEMM_F16, d16 = g.d_dtype == PB_GEMM_F16;
-  if (!ab16 && d16) return "gemm: fp16 output needs fp16 operands";
   const int KB = ab16 ? BK16 : BK;            // k-block in elements (128 bytes)
   const long aes = ab16 ? 2 : 4, des = d16 ? 2 : 4;
   const int dq = d16 ? 8 : 4;                 // elements per 16 bytes of D / R
@@ -734,5 +733,5 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   p.items = (int)(full + tail * p.splits);
   const int grid = (int)std::min<long>(p.items, nsm);
   if (ab16) return d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
-  return launch_bn<false, false>(BN, p, grid, st);
+  return d16 ? launch_bn<false, true>(BN, p, grid, st) : launch_bn<false, false>(BN, p, grid, st);
 }

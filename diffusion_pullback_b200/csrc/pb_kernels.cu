@@ -12,28 +12,23 @@
 #include <algorithm>
 #include <vector>
 
+#include "pb_dev.cuh"
 #include "pb_host_util.h"
 #include "pb_kernels.h"
+#include "pb_lin16.h"
 
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st);
 
 namespace {
 
-constexpr int kSMs = 148;
+using namespace pbdev;
 
-inline const char* cuda_err(cudaError_t e) { return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
-inline const char* last_err() { return cuda_err(cudaGetLastError()); }
 inline cudaStream_t S(pb_stream st) { return static_cast<cudaStream_t>(st); }
-inline unsigned grid_for(long work, int block, int per_sm = 8) {
-  long g = (work + block - 1) / block;
-  return (unsigned)std::max<long>(1, std::min<long>(g, (long)kSMs * per_sm));
-}
+inline bool in16(int io) { return (io & PB_IN_F16) != 0; }
+inline bool out16(int io) { return (io & PB_RND_MASK) == PB_OUT_F16; }
+__host__ __device__ inline const __half* HP(const float* p) { return reinterpret_cast<const __half*>(p); }
+__host__ __device__ inline __half* HP(float* p) { return reinterpret_cast<__half*>(p); }
 
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 __device__ __forceinline__ float maybe_round(float x, int r) { return r ? rna_tf32(x) : x; }
 __device__ __forceinline__ float4 maybe_round4(float4 v, int r) {
   if (r) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); v.z = rna_tf32(v.z); v.w = rna_tf32(v.w); }
@@ -51,22 +46,17 @@ __device__ __forceinline__ void store_out4(float* out, long off, float4 v, int r
     *reinterpret_cast<float4*>(out + off) = maybe_round4(v, rnd);
   }
 }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+// four consecutive elements of a tensor that holds floats or (h16) halves at the same element offsets
+__device__ __forceinline__ float4 load_in4(const float* p, long off, bool h16) {
+  if (h16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p) + off);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return *reinterpret_cast<const float4*>(p + off);
 }
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float silu_f(float x) { return x * sigmoidf_(x); }
-__device__ __forceinline__ float silu_d(float x) { float s = sigmoidf_(x); return s * (1.f + x * (1.f - s)); }
-__device__ __forceinline__ float gelu_f(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_d(float g) {
-  return 0.5f * (1.f + erff(g * 0.70710678118654752f)) + g * 0.3989422804014327f * __expf(-0.5f * g * g);
+__device__ __forceinline__ float load_in1(const float* p, long off, bool h16) {
+  return h16 ? __half2float(reinterpret_cast<const __half*>(p)[off]) : p[off];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -96,15 +86,15 @@ __global__ void copy2d_s(float* __restrict__ dst, long ldd, const float* __restr
 
 // src_(b,h) [R][lds] -> dst_(b,h) [C][ldd];  blockIdx.z = b * nh + h
 __global__ void transpose_k(float* __restrict__ dst, long ldd, long sbd, long shd, const float* __restrict__ src,
-                            long lds, long sbs, long shs, int nh, int R, int C, float beta, int rnd) {
+                            long lds, long sbs, long shs, int nh, int R, int C, float beta, int rnd, int src16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z / nh, h = blockIdx.z % nh;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  const float* s = src + (long)b * sbs + (long)h * shs;
+  const long soff = (long)b * sbs + (long)h * shs;      // src16: src, lds and the batch strides count halves
   float* d = dst + (long)b * sbd + (long)h * shd;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? s[(long)r * lds + c] : 0.f;
+    tile[i][threadIdx.x] = (r < R && c < C) ? load_in1(src, soff + (long)r * lds + c, src16 != 0) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -237,7 +227,7 @@ __global__ void col2im_s2_k(const float4* __restrict__ col, int nb, int H, int W
 // thread per output element; for tiny Cin (conv_in)
 __global__ void conv3x3_direct_thin_in(const float* __restrict__ x, int nb, int H, int W, int Cin,
                                        const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                                       float* __restrict__ y, float beta) {
+                                       float* __restrict__ y, float beta, bool x16, bool y16) {
   const long total = (long)nb * H * W * Cout;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long t = i;
@@ -249,18 +239,19 @@ __global__ void conv3x3_direct_thin_in(const float* __restrict__ x, int nb, int 
     for (int tap = 0; tap < 9; ++tap) {
       const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
       if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const float* xp = x + (((long)b * H + iy) * W + ix) * Cin;
+      const long xo = (((long)b * H + iy) * W + ix) * Cin;
       const float* wp = w + ((long)co * 9 + tap) * Cin;
-      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(xp[ci], wp[ci], acc);
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(load_in1(x, xo + ci, x16), wp[ci], acc);
     }
-    y[i] = beta != 0.f ? acc + beta * y[i] : acc;
+    if (beta != 0.f) acc += beta * load_in1(y, i, y16);
+    if (y16) HP(y)[i] = __float2half_rn(acc); else y[i] = acc;
   }
 }
 // warp per output pixel, lanes split Cin; for tiny Cout (transpose of conv_in)
 template <int MAXCO>
 __global__ void conv3x3_direct_thin_out(const float* __restrict__ x, int nb, int H, int W, int Cin,
                                         const float* __restrict__ w, const float* __restrict__ bias, int Cout,
-                                        float* __restrict__ y, float beta) {
+                                        float* __restrict__ y, float beta, bool x16, bool y16) {
   const int lane = threadIdx.x & 31;
   const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
@@ -276,9 +267,9 @@ __global__ void conv3x3_direct_thin_out(const float* __restrict__ x, int nb, int
     for (int tap = 0; tap < 9; ++tap) {
       const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
       if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const float* xp = x + (((long)b * H + iy) * W + ix) * Cin;
+      const long xo = (((long)b * H + iy) * W + ix) * Cin;
       for (int ci = lane; ci < Cin; ci += 32) {
-        const float xv = xp[ci];
+        const float xv = load_in1(x, xo + ci, x16);
 #pragma unroll
         for (int co = 0; co < MAXCO; ++co)
           if (co < Cout) acc[co] = fmaf(xv, w[((long)co * 9 + tap) * Cin + ci], acc[co]);
@@ -290,8 +281,9 @@ __global__ void conv3x3_direct_thin_out(const float* __restrict__ x, int nb, int
         float v = warp_sum(acc[co]);
         if (lane == 0) {
           if (bias) v += bias[co];
-          float* p = y + pix * Cout + co;
-          *p = beta != 0.f ? v + beta * *p : v;
+          const long yo = pix * Cout + co;
+          if (beta != 0.f) v += beta * load_in1(y, yo, y16);
+          if (y16) HP(y)[yo] = __float2half_rn(v); else y[yo] = v;
         }
       }
     }
@@ -765,6 +757,7 @@ __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const flo
     store_out4(dy, r * F + c, o, rnd);
   }
 }
+template <bool IN16>
 __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ gy, long rows, int F,
                             float* __restrict__ gh, int rnd) {
   const int F4 = F / 4;
@@ -774,7 +767,7 @@ __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const flo
     const long rp = r % rows_p;
     const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
     const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
-    const float4 y = *reinterpret_cast<const float4*>(gy + r * F + c);
+    const float4 y = load_in4(gy, r * F + c, IN16);
     float4 ga = make_float4(y.x * gelu_f(g.x), y.y * gelu_f(g.y), y.z * gelu_f(g.z), y.w * gelu_f(g.w));
     float4 gg = make_float4(y.x * a.x * gelu_d(g.x), y.y * a.y * gelu_d(g.y), y.z * a.z * gelu_d(g.z),
                             y.w * a.w * gelu_d(g.w));
@@ -885,7 +878,7 @@ __global__ void softmax_lin_k(const float* __restrict__ P, long rows_p, float* _
 
 // thread per (tangent, row, head): heads are contiguous along a row, so a warp reads whole rows with 128-bit loads
 __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float* __restrict__ o, long ldo, int nb,
-                             int N, int H, int d, float* __restrict__ delta) {
+                             int N, int H, int d, float* __restrict__ delta, bool go16) {
   const long total = (long)nb * N * H;
   const int d4 = d / 4;
   for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
@@ -893,11 +886,11 @@ __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float
     const int h = int(t % H); t /= H;
     const int i = int(t % N); t /= N;
     const int b = int(t);
-    const float4* g = reinterpret_cast<const float4*>(go + ((long)b * N + i) * ldg + h * d);
+    const long goff = ((long)b * N + i) * ldg + h * d;
     const float4* oo = reinterpret_cast<const float4*>(o + (long)i * ldo + h * d);
     float s = 0.f;
     for (int c = 0; c < d4; ++c) {
-      const float4 a = g[c], q = oo[c];
+      const float4 a = load_in4(go, goff + 4 * c, go16), q = oo[c];
       s = fmaf(a.x, q.x, fmaf(a.y, q.y, fmaf(a.z, q.z, fmaf(a.w, q.w, s))));
     }
     delta[((long)b * H + h) * N + i] = s;
@@ -982,7 +975,7 @@ __global__ void pack_conv3x3_k(const float* __restrict__ w, int Co, int Ci, floa
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __restrict__ x, int nb, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
-                                                             int Cout, float* __restrict__ y, float beta) {
+                                                             int Cout, float* __restrict__ y, float beta, bool x16, bool y16) {
   const int cp = blockIdx.y * blockDim.x + threadIdx.x;       // output-channel pair
   if (2 * cp >= Cout) return;
   float wr[2][9 * CIN];
@@ -994,23 +987,29 @@ __global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __rest
   const long total = (long)nb * H * W;
   for (long pix = blockIdx.x; pix < total; pix += gridDim.x) {
     const int px = int(pix % W), py = int((pix / W) % H);
-    const float* xc = x + pix * CIN;
     float a0 = b0, a1 = b1;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
       if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
-      const float* xp = xc + ((long)dy * W + dx) * CIN;
+      const long xo = (pix + (long)dy * W + dx) * CIN;
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        const float xv = __ldg(xp + ci);
+        const float xv = load_in1(x, xo + ci, x16);
         a0 = fmaf(xv, wr[0][tap * CIN + ci], a0);
         a1 = fmaf(xv, wr[1][tap * CIN + ci], a1);
       }
     }
-    float2* yp = reinterpret_cast<float2*>(y + pix * Cout + 2 * cp);
-    if (beta != 0.f) { const float2 o = *yp; a0 += beta * o.x; a1 += beta * o.y; }
-    *yp = make_float2(a0, a1);
+    const long yo = pix * Cout + 2 * cp;
+    if (y16) {
+      __half2* yp = reinterpret_cast<__half2*>(HP(y) + yo);
+      if (beta != 0.f) { const float2 o = __half22float2(*yp); a0 += beta * o.x; a1 += beta * o.y; }
+      *yp = __floats2half2_rn(a0, a1);
+    } else {
+      float2* yp = reinterpret_cast<float2*>(y + yo);
+      if (beta != 0.f) { const float2 o = *yp; a0 += beta * o.x; a1 += beta * o.y; }
+      *yp = make_float2(a0, a1);
+    }
   }
 }
 // thin-out: the whole filter ([COUT <= 4][9][Cin], 46 KB for SD) sits in shared memory; one warp per output pixel,
@@ -1018,7 +1017,7 @@ __global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __rest
 template <int COUT>
 __global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __restrict__ x, int nb, int H, int W, int Cin,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
-                                                               float* __restrict__ y, float beta) {
+                                                               float* __restrict__ y, float beta, bool x16, bool y16) {
   extern __shared__ float4 wsm[];                              // [COUT][9][Cin / 4]
   const int C4 = Cin / 4;
   for (int i = threadIdx.x; i < COUT * 9 * C4; i += blockDim.x) wsm[i] = reinterpret_cast<const float4*>(w)[i];
@@ -1036,9 +1035,9 @@ __global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __re
     for (int tap = 0; tap < 9; ++tap) {
       const int dy = tap / 3 - 1, dx = tap % 3 - 1;
       if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
-      const float4* xp = reinterpret_cast<const float4*>(x + (pix + (long)dy * W + dx) * Cin);
+      const long xo = (pix + (long)dy * W + dx) * Cin;
       for (int c4 = lane; c4 < C4; c4 += 32) {
-        const float4 xv = xp[c4];
+        const float4 xv = load_in4(x, xo + 4 * c4, x16);
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
           const float4 wv = wsm[(co * 9 + tap) * C4 + c4];
@@ -1051,8 +1050,9 @@ __global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __re
       float v = warp_sum(acc[co]);
       if (lane == 0) {
         if (bias) v += bias[co];
-        float* p = y + pix * COUT + co;
-        *p = beta != 0.f ? v + beta * *p : v;
+        const long yo = pix * COUT + co;
+        if (beta != 0.f) v += beta * load_in1(y, yo, y16);
+        if (y16) HP(y)[yo] = __float2half_rn(v); else y[yo] = v;
       }
     }
   }
@@ -1142,36 +1142,41 @@ PBK pbk_gemm(const PbGemm* g, pb_stream st) {
 }
 
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
-                       float* y, float beta, pb_stream st) {
+                       float* y, float beta, int io, pb_stream st) {
   const long pix = (long)nb * H * W;
+  const bool x16 = in16(io), y16 = out16(io);
   if ((Cin == 3 || Cin == 4) && Cout % 2 == 0 && Cout >= 64) {                  // conv_in
     const int gy = (Cout / 2 + 255) / 256;
     const int bx = std::min(256, ((Cout / 2 + 31) / 32) * 32);
     dim3 grid((unsigned)std::min<long>(pix, (long)kSMs * 8 / ((Cout / 2 + bx - 1) / bx)), (Cout / 2 + bx - 1) / bx);
     (void)gy;
-    if (Cin == 4) conv3x3_thin_in_reg_k<4><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta);
-    else conv3x3_thin_in_reg_k<3><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta);
+    if (Cin == 4) conv3x3_thin_in_reg_k<4><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta, x16, y16);
+    else conv3x3_thin_in_reg_k<3><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta, x16, y16);
   } else if ((Cout == 3 || Cout == 4) && Cin % 4 == 0 && (size_t)Cout * 9 * Cin * 4 <= 96 * 1024 &&
              (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // its transpose
     const int shmem = Cout * 9 * Cin * 4;
     const unsigned blocks = (unsigned)std::min<long>((pix + 7) / 8, (long)kSMs * 2);
     if (Cout == 4) {
       if (const char* err = pbhost::optin_smem(conv3x3_thin_out_smem_k<4>, 96 * 1024)) return err;
-      conv3x3_thin_out_smem_k<4><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
+      conv3x3_thin_out_smem_k<4><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta, x16, y16);
     } else {
       if (const char* err = pbhost::optin_smem(conv3x3_thin_out_smem_k<3>, 96 * 1024)) return err;
-      conv3x3_thin_out_smem_k<3><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta);
+      conv3x3_thin_out_smem_k<3><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta, x16, y16);
     }
   } else if (Cout <= 8 && Cin >= 32) {
-    conv3x3_direct_thin_out<8><<<grid_for(pix * 32, 256), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
+    conv3x3_direct_thin_out<8><<<grid_for(pix * 32, 256), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta, x16, y16);
   } else {
     const long total = pix * Cout;
-    conv3x3_direct_thin_in<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta);
+    conv3x3_direct_thin_in<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(x, nb, H, W, Cin, w, bias, Cout, y, beta, x16, y16);
   }
   return last_err();
 }
 PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* col, int round_tf32,
                   pb_stream st) {
+  if (in16(round_tf32) && out16(round_tf32)) {      // pure data movement: [..][C] halves are [..][C / 2] floats
+    if (C % 8) return "im2col: C must be a multiple of 8 for fp16 tangents";
+    C /= 2; round_tf32 = 0;
+  } else if (in16(round_tf32)) return "im2col: fp16 input needs fp16 output";
   CHECK_ALIGN4(C, "im2col: C");
   const long total = (long)nb * Ho * Wo * 9 * (C / 4);
   im2col_s2_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(x), nb, H, W, C / 4, pad_lo,
@@ -1180,6 +1185,10 @@ PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int H
 }
 PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* gx, float beta,
                   int round_tf32, pb_stream st) {
+  if (in16(round_tf32)) {
+    if (!out16(round_tf32)) return "col2im: fp16 input needs fp16 output";
+    return pb16::col2im_s2(HP(col), nb, H, W, C, pad_lo, Ho, Wo, HP(gx), beta, S(st));
+  }
   CHECK_ALIGN4(C, "col2im: C");
   const long total = (long)nb * H * W * (C / 4);
   col2im_s2_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(col), nb, H, W, C / 4, pad_lo,
@@ -1190,6 +1199,10 @@ PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad_lo, int
 PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, int round_tf32,
                pb_stream st) {
   if (rows <= 0 || cols <= 0) return nullptr;
+  if (in16(round_tf32)) {
+    if (!out16(round_tf32)) return "copy2d: fp16 input needs fp16 output";
+    return pb16::copy2d(HP(dst), ldd, HP(src), lds, rows, cols, beta, S(st));
+  }
   const bool v4 = (cols % 4 == 0) && (ldd % 4 == 0) && (lds % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
   if (v4) copy2d_v4<<<grid_for(rows * (cols / 4), 256, 16), 256, 0, S(st)>>>(dst, ldd, src, lds, rows, cols / 4, beta, round_tf32);
@@ -1199,12 +1212,17 @@ PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int 
 PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, long lds, long sbs, long shs, int nb,
                   int nh, int R, int C, float beta, int round_tf32, pb_stream st) {
   if ((long)nb * nh > 65535 || (R + 31) / 32 > 65535) return "transpose: batch / row extent too large";
-  if (round_tf32 == 2 && beta != 0.f) return "transpose: fp16 output cannot accumulate";
+  if (out16(round_tf32) && beta != 0.f) return "transpose: fp16 output cannot accumulate";
   dim3 grid((C + 31) / 32, (R + 31) / 32, nb * nh), block(32, 8);
-  transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, sbd, shd, src, lds, sbs, shs, nh, R, C, beta, round_tf32);
+  transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, sbd, shd, src, lds, sbs, shs, nh, R, C, beta, round_tf32 & PB_RND_MASK,
+                                         in16(round_tf32) ? 1 : 0);
   return last_err();
 }
 PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int round_tf32, pb_stream st) {
+  if (in16(round_tf32) && out16(round_tf32)) {      // pure data movement: [..][C] halves are [..][C / 2] floats
+    if (C % 8) return "upsample: C must be a multiple of 8 for fp16 tangents";
+    C /= 2; round_tf32 = 0;
+  } else if (in16(round_tf32)) return "upsample: fp16 input needs fp16 output";
   CHECK_ALIGN4(C, "upsample: C");
   const long total = (long)nb * 4 * H * W * (C / 4);
   upsample2x_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(x), nb, H, W, C / 4,
@@ -1213,6 +1231,10 @@ PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int ro
 }
 PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int round_tf32,
                        pb_stream st) {
+  if (in16(round_tf32)) {
+    if (!out16(round_tf32)) return "upsample_vjp: fp16 input needs fp16 output";
+    return pb16::upsample2x_vjp(HP(gy), nb, H, W, C, HP(gx), beta, S(st));
+  }
   CHECK_ALIGN4(C, "upsample_vjp: C");
   const long total = (long)nb * H * W * (C / 4);
   upsample2x_vjp_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<const float4*>(gy), nb, H, W, C / 4,
@@ -1226,6 +1248,7 @@ PBK pbk_to_f16_scaled(void* dst, const float* src, size_t n, float scale, pb_str
   return last_err();
 }
 PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) { return pbk_to_f16_scaled(dst, src, n, 1.f, st); }
+PBK pbk_to_f32(float* dst, const void* src, size_t n, pb_stream st) { return pb16::to_f32(dst, static_cast<const __half*>(src), n, S(st)); }
 PBK pbk_ddim_step(const float* x, const float* eps, float a_t, float a_next, float* x_next, float* pred_x0, long n,
                   pb_stream st) {
   if (!(a_t > 0.f) || !(a_next >= 0.f) || a_t > 1.f || a_next > 1.f) return "ddim_step: alphas_cumprod must lie in (0, 1]";
@@ -1252,7 +1275,7 @@ static int gn_chunks(int HW, int C, int nb) {
   return (HW + ppb - 1) / ppb;
 }
 extern "C" __attribute__((visibility("default"))) size_t pbk_gn_tmp_floats(int HW, int C, int G, int nb) {
-  return (size_t)gn_chunks(HW, C, nb) * nb * C * 2 + (size_t)nb * G * 2 + 16;
+  return std::max((size_t)gn_chunks(HW, C, nb) * nb * C * 2 + (size_t)nb * G * 2 + 16, pb16::gn_tmp_floats(HW, C, G, nb));
 }
 static const char* gn_launch_sums(int mode, const float* xp, const float* mean, const float* rstd, const float* gamma,
                                   const float* beta, int HW, int C, int G, int silu, const float* t, int nb,
@@ -1295,6 +1318,10 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
                float* tmp, pb_stream st) {
+  if (in16(round_tf32)) {
+    if (!out16(round_tf32)) return "groupnorm: fp16 input needs fp16 output";
+    return pb16::gn_lin(xp, mean, rstd, gamma, beta, HW, C, G, silu, HP(t), nb, mode, HP(out), acc, tmp, nb, 0, S(st));
+  }
   if (round_tf32 == 2 && acc != 0.f) return "groupnorm: fp16 output cannot accumulate";
   if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
   {
@@ -1351,6 +1378,10 @@ PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float
 }
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
                const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st) {
+  if (in16(round_tf32)) {
+    if (!out16(round_tf32)) return "layernorm: fp16 input needs fp16 output";
+    return pb16::ln_lin(xp, mean, rstd, gamma, rows_p, C, HP(t), nb, mode, HP(out), acc, nb, 0, S(st));
+  }
   CHECK_ALIGN4(C, "layernorm: C");
   if (round_tf32 == 2 && acc != 0.f) return "layernorm: fp16 output cannot accumulate";
   const long rows = rows_p * nb;
@@ -1370,7 +1401,7 @@ PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, 
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
   // round_tf32 bit 2 (value 4): the tangent input dh holds halves
-  if (round_tf32 & 4) geglu_jvp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & 3);
+  if (in16(round_tf32)) geglu_jvp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & 3);
   else geglu_jvp_k<false><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32);
   return last_err();
 }
@@ -1378,7 +1409,8 @@ PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, 
                   pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
-  geglu_vjp_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32);
+  if (in16(round_tf32)) geglu_vjp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32 & PB_RND_MASK);
+  else geglu_vjp_k<false><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32);
   return last_err();
 }
 
@@ -1397,11 +1429,11 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
   return last_err();
 }
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
-                   pb_stream st) {
+                   int io, pb_stream st) {
   const long total = (long)nb * H * N;
   if (d % 4 || ldg % 4 || ldo % 4 || ((reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(o)) & 15))
     return "attn_delta: head dim and leading dimensions must be multiples of 4 with 16-byte aligned bases";
-  attn_delta_k<<<grid_for(total, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta);
+  attn_delta_k<<<grid_for(total, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta, in16(io));
   return last_err();
 }
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,

@@ -1,0 +1,438 @@
+// Elementwise linearisation kernels over fp16 TANGENTS (the all-fp16 tangent plan of the engine): every tangent /
+// cotangent tensor is [image][pixel-or-token][channel] halves, the cached primal quantities stay fp32, all arithmetic is fp32.
+// These are HBM-bound kernels: full-row coalesced 8- / 16-byte accesses along the channel axis, several rows in flight per
+// thread, grids sized from the SM count, fixed-order reductions (runs are bit-reproducible).
+//
+//   GroupNorm linearisation : gn16_sums_k  (per-(image, pixel-chunk, group) partial sums, every channel of a pixel row read by
+//                             one block so the accesses are whole 2 C-byte rows, not 2 C/G-byte group slices)
+//                             gn16_apply_k (re-reduces the few partials of its image in its prologue, then applies; the second
+//                             read of the tangent comes from L2)
+//   LayerNorm linearisation : ln16_k       (one warp per token, the row is held in registers: one read, one write)
+//   data movement with arithmetic: copy2d16_k (accumulating channel-slice copy), col2im16_k, upsample_vjp16_k, to_f32_k
+// Primal operands of image b are read at (b / k_slot) * p_stride: problem slots keep one primal cache per problem and the
+// tangent batch holds k_slot columns of every problem back to back (pb_set_slots).
+#include "pb_lin16.h"
+
+#include "pb_dev.cuh"
+
+namespace pb16 {
+using namespace pbdev;
+
+namespace {
+
+// A block owns a pixel chunk x a channel slab of Cblk channels (the whole row unless C > 2048: then nz slabs of whole groups)
+struct GnGeom16 { int nz, Cblk, CV, lanes, threads, chunks, ppb; };
+GnGeom16 gn_geom16(int HW, int C, int G, int nb) {
+  GnGeom16 g;
+  const int cpg = C / G;
+  g.nz = 1;
+  while ((C / g.nz) / 4 > 512 && g.nz < G) g.nz *= 2;
+  if (G % g.nz || ((C / g.nz) % cpg) || (C / g.nz) / 4 > 512) { g.nz = 0; return g; }   // unsupported geometry
+  g.Cblk = C / g.nz;
+  g.CV = g.Cblk / 4;                                               // channel quads per pixel row of the slab
+  g.lanes = std::max(1, std::min(std::min(512 / g.CV, 6144 / g.Cblk), 16));   // pixel lanes; smem = lanes * Cblk * 8 bytes <= 48 KB
+  g.threads = (g.CV * g.lanes + 31) / 32 * 32;
+  const int target = std::max(1, (kSMs * 3 + nb * g.nz - 1) / (nb * g.nz));
+  const int maxchunks = (HW + g.lanes - 1) / g.lanes;
+  g.chunks = std::max(1, std::min(maxchunks, target));
+  g.ppb = (HW + g.chunks - 1) / g.chunks;
+  g.ppb = (g.ppb + g.lanes - 1) / g.lanes * g.lanes;
+  g.chunks = (HW + g.ppb - 1) / g.ppb;
+  return g;
+}
+
+// MODE 0 (JVP): u = t ; MODE 1 (VJP): u = t * act'(gamma xhat + beta) * gamma.   part[b][chunk][g] = (sum u, sum xhat u)
+template <int MODE>
+__global__ void __launch_bounds__(512) gn16_sums_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                                                   const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
+                                                   long p_stride, float* __restrict__ part) {
+  extern __shared__ float2 sh2[];                                  // [lanes][Cblk] (sum u, sum xhat u) per channel
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int CV = Cblk / 4, cbase = blockIdx.z * Cblk;
+  const bool active = tid < CV * lanes;
+  const int cv = tid % CV, lane = tid / CV;
+  const int c0 = cbase + cv * 4, cpg = C / G;
+  const long ps = (long)(b / k_slot) * p_stride;
+  if (active) {
+    float mu[4], rs[4], ga[4], be[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (c0 + e) / cpg;
+      mu[e] = mean[ps + g]; rs[e] = rstd[ps + g];
+      ga[e] = MODE == 1 ? gamma[c0 + e] : 1.f; be[e] = MODE == 1 ? beta_[c0 + e] : 0.f;
+    }
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int p0 = chunk * ppb, p1 = min(HW, p0 + ppb);
+    const float* xq = xp + ps + (long)(p0 + lane) * C + c0;
+    const __half* tq = t + ((long)b * HW + p0 + lane) * C + c0;
+    const long step = (long)lanes * C;
+#pragma unroll 4
+    for (int pix = p0 + lane; pix < p1; pix += lanes, xq += step, tq += step) {
+      const float4 xv = *reinterpret_cast<const float4*>(xq);
+      const uint2 tu = *reinterpret_cast<const uint2*>(tq);
+      const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu.x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu.y));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (xs[e] - mu[e]) * rs[e];
+        float u = ts[e];
+        if (MODE == 1) u *= silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
+        s1[e] += u; s2[e] = fmaf(xh, u, s2[e]);
+      }
+    }
+    float2* sp = sh2 + (long)lane * Cblk + cv * 4;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sp[e] = make_float2(s1[e], s2[e]);
+  }
+  __syncthreads();
+  // one warp per group of the slab: lanes * cpg per-channel partials, summed in a fixed order
+  const int w = tid >> 5, l = tid & 31, nw = blockDim.x >> 5;
+  const int n = lanes * cpg, gb = Cblk / cpg, g0 = cbase / cpg;
+  for (int g = w; g < gb; g += nw) {
+    float a = 0.f, c = 0.f;
+    for (int i = l; i < n; i += 32) {
+      const float2 v = sh2[(long)(i / cpg) * Cblk + g * cpg + i % cpg];
+      a += v.x; c += v.y;
+    }
+    a = warp_sum(a); c = warp_sum(c);
+    if (l == 0) {
+      float* q = part + (((long)b * gridDim.x + chunk) * G + g0 + g) * 2;
+      q[0] = a; q[1] = c;
+    }
+  }
+}
+
+//   MODE 0 (JVP): out = act'(.) gamma rstd (t - m1 - xhat m2)          MODE 1 (VJP): out = rstd (t act'(.) gamma - m1 - xhat m2)
+//   (m1, m2) = group means of (u, xhat u);   out = result + acc * out
+template <int MODE>
+__global__ void __launch_bounds__(512) gn16_apply_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta_, int HW, int C, int G, int silu,
+                                                    const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
+                                                    long p_stride, const float* __restrict__ part, int chunks,
+                                                    __half* __restrict__ out, float acc) {
+  extern __shared__ float s_m[];                                   // [G][2] group means of this image
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int cpg = C / G;
+  for (int i = tid; i < 2 * G; i += blockDim.x) {
+    double s = 0.0;
+    const float* q = part + ((long)b * chunks * G + (i >> 1)) * 2 + (i & 1);
+    for (int k = 0; k < chunks; ++k) s += (double)q[(long)k * G * 2];
+    s_m[i] = (float)(s / ((double)HW * cpg));
+  }
+  __syncthreads();
+  const int CV = Cblk / 4;
+  if (tid >= CV * lanes) return;
+  const int cv = tid % CV, lane = tid / CV;
+  const int c0 = blockIdx.z * Cblk + cv * 4;
+  const long ps = (long)(b / k_slot) * p_stride;
+  float mu[4], rs[4], ga[4], be[4], m1[4], m2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int g = (c0 + e) / cpg;
+    mu[e] = mean[ps + g]; rs[e] = rstd[ps + g];
+    ga[e] = gamma[c0 + e]; be[e] = beta_[c0 + e];
+    m1[e] = s_m[2 * g]; m2[e] = s_m[2 * g + 1];
+  }
+  const int p0 = chunk * ppb, p1 = min(HW, p0 + ppb);
+  const float* xq = xp + ps + (long)(p0 + lane) * C + c0;
+  const long toff = ((long)b * HW + p0 + lane) * C + c0;
+  const __half* tq = t + toff;
+  __half* oq = out + toff;
+  const long step = (long)lanes * C;
+#pragma unroll 4
+  for (int pix = p0 + lane; pix < p1; pix += lanes, xq += step, tq += step, oq += step) {
+    const float4 xv = *reinterpret_cast<const float4*>(xq);
+    const uint2 tu = *reinterpret_cast<const uint2*>(tq);
+    const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu.x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu.y));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xh = (xs[e] - mu[e]) * rs[e];
+      const float f = silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
+      o[e] = MODE == 0 ? f * rs[e] * (ts[e] - m1[e] - xh * m2[e]) : rs[e] * (ts[e] * f - m1[e] - xh * m2[e]);
+    }
+    if (acc != 0.f) {
+      const uint2 pu = *reinterpret_cast<const uint2*>(oq);
+      const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&pu.x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&pu.y));
+      o[0] += acc * q0.x; o[1] += acc * q0.y; o[2] += acc * q1.x; o[3] += acc * q1.y;
+    }
+    uint2 ou;
+    *reinterpret_cast<__half2*>(&ou.x) = __floats2half2_rn(o[0], o[1]);
+    *reinterpret_cast<__half2*>(&ou.y) = __floats2half2_rn(o[2], o[3]);
+    *reinterpret_cast<uint2*>(oq) = ou;
+  }
+}
+
+// LayerNorm linearisation, one warp per token row held in registers (NV vectors of 8 channels per lane; NV = 0: any C, the
+// row is read twice).  MODE 0 (JVP): out = gamma rstd (t - m1 - xhat m2); MODE 1 (VJP): g = t gamma; out = rstd (g - m1 - xhat m2)
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256) ln16_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                              const float* __restrict__ rstd, const float* __restrict__ gamma, long rows_p, int C,
+                                              const __half* __restrict__ t, long rows, __half* __restrict__ out, float acc,
+                                              int k_slot, long p_stride) {
+  const int lane = threadIdx.x & 31;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  for (long r = warp; r < rows; r += nw) {
+    const long rp = r % rows_p;
+    const long ps = ((r / rows_p) / k_slot) * p_stride;
+    const float* xr = xp + ps + rp * C;
+    const __half* tr = t + r * C;
+    __half* orow = out + r * C;
+    const float m = mean[ps + rp], rs = rstd[ps + rp];
+    float s1 = 0.f, s2 = 0.f;
+    if constexpr (NV > 0) {
+      float xh[NV][8], tv[NV][8];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        if (c < C) {
+          f8_load(xr + c, xh[i]);
+          h8_unpack(*reinterpret_cast<const uint4*>(tr + c), tv[i]);
+          float gq[8];
+          if (MODE == 1) f8_load(gamma + c, gq);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            xh[i][e] = (xh[i][e] - m) * rs;
+            if (MODE == 1) tv[i][e] *= gq[e];
+            s1 += tv[i][e]; s2 = fmaf(xh[i][e], tv[i][e], s2);
+          }
+        }
+      }
+      const float m1 = warp_sum(s1) * invC, m2 = warp_sum(s2) * invC;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        if (c < C) {
+          float o[8], gq[8];
+          if (MODE == 0) f8_load(gamma + c, gq);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[e] = MODE == 0 ? gq[e] * rs * (tv[i][e] - m1 - xh[i][e] * m2) : rs * (tv[i][e] - m1 - xh[i][e] * m2);
+          if (acc != 0.f) {
+            float pv[8];
+            h8_unpack(*reinterpret_cast<const uint4*>(orow + c), pv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += acc * pv[e];
+          }
+          *reinterpret_cast<uint4*>(orow + c) = h8_pack(o);
+        }
+      }
+    } else {
+      for (int c = lane * 8; c < C; c += 256) {
+        float xv[8], tv[8], gq[8];
+        f8_load(xr + c, xv);
+        h8_unpack(*reinterpret_cast<const uint4*>(tr + c), tv);
+        if (MODE == 1) f8_load(gamma + c, gq);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] - m) * rs;
+          const float u = MODE == 1 ? tv[e] * gq[e] : tv[e];
+          s1 += u; s2 = fmaf(xh, u, s2);
+        }
+      }
+      const float m1 = warp_sum(s1) * invC, m2 = warp_sum(s2) * invC;
+      for (int c = lane * 8; c < C; c += 256) {
+        float xv[8], tv[8], gq[8], o[8];
+        f8_load(xr + c, xv);
+        h8_unpack(*reinterpret_cast<const uint4*>(tr + c), tv);
+        f8_load(gamma + c, gq);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] - m) * rs;
+          o[e] = MODE == 0 ? gq[e] * rs * (tv[e] - m1 - xh * m2) : rs * (tv[e] * gq[e] - m1 - xh * m2);
+        }
+        if (acc != 0.f) {
+          float pv[8];
+          h8_unpack(*reinterpret_cast<const uint4*>(orow + c), pv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += acc * pv[e];
+        }
+        *reinterpret_cast<uint4*>(orow + c) = h8_pack(o);
+      }
+    }
+  }
+}
+
+// dst[r][c] = src[r][c] + beta * dst[r][c] over halves, 8 per access
+__global__ void copy2d16_k(__half* __restrict__ dst, long ldd, const __half* __restrict__ src, long lds, long rows, int cols8,
+                           float beta) {
+  const long total = rows * cols8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols8; const int c = int(i % cols8) * 8;
+    uint4 v = *reinterpret_cast<const uint4*>(src + r * lds + c);
+    uint4* d = reinterpret_cast<uint4*>(dst + r * ldd + c);
+    if (beta != 0.f) {
+      float a[8], o[8];
+      h8_unpack(v, a); h8_unpack(*d, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += beta * o[e];
+      v = h8_pack(a);
+    }
+    *d = v;
+  }
+}
+
+__global__ void col2im16_k(const uint4* __restrict__ col, int nb, int H, int W, int C8, int pad, int Ho, int Wo,
+                           uint4* __restrict__ gx, float beta) {
+  const long total = (long)nb * H * W * C8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C8); t /= C8;
+    const int ix = int(t % W); t /= W;
+    const int iy = int(t % H); t /= H;
+    const int b = int(t);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = iy + pad - ky;
+      if (ty < 0 || (ty & 1)) continue;
+      const int oy = ty >> 1;
+      if (oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ix + pad - kx;
+        if (tx < 0 || (tx & 1)) continue;
+        const int ox = tx >> 1;
+        if (ox >= Wo) continue;
+        float v[8];
+        h8_unpack(col[((((long)b * Ho + oy) * Wo + ox) * 9 + ky * 3 + kx) * C8 + c], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += v[e];
+      }
+    }
+    if (beta != 0.f) {
+      float o[8];
+      h8_unpack(gx[i], o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += beta * o[e];
+    }
+    gx[i] = h8_pack(a);
+  }
+}
+
+__global__ void upsample_vjp16_k(const uint4* __restrict__ gy, int nb, int H, int W, int C8, uint4* __restrict__ gx, float beta) {
+  const long total = (long)nb * H * W * C8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long t = i;
+    const int c = int(t % C8); t /= C8;
+    const int x = int(t % W); t /= W;
+    const int y = int(t % H); t /= H;
+    const int b = int(t);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float v[8];
+        h8_unpack(gy[(((long)b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C8 + c], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += v[e];
+      }
+    if (beta != 0.f) {
+      float o[8];
+      h8_unpack(gx[i], o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += beta * o[e];
+    }
+    gx[i] = h8_pack(a);
+  }
+}
+
+__global__ void to_f32_k(float* __restrict__ dst, const __half* __restrict__ src, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float v[8];
+    h8_unpack(reinterpret_cast<const uint4*>(src)[i], v);
+    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+}  // namespace
+
+size_t gn_tmp_floats(int HW, int C, int G, int nb) {
+  if (C % 4 || C % G) return 0;
+  const GnGeom16 g = gn_geom16(HW, C, G, nb);
+  if (!g.nz) return 0;
+  return (size_t)nb * g.chunks * G * 2 + 16;
+}
+
+const char* gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW, int C,
+                   int G, int silu, const __half* t, int nb, int mode, __half* out, float acc, float* tmp, int k_slot,
+                   long p_stride, cudaStream_t st) {
+  if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
+  if (k_slot < 1) k_slot = nb;
+  const GnGeom16 g = gn_geom16(HW, C, G, nb);
+  if (!g.nz) return "groupnorm: channel / group geometry not supported by the fp16-tangent kernel";
+  dim3 grid(g.chunks, nb, g.nz);
+  const size_t sh1 = (size_t)g.lanes * g.Cblk * sizeof(float2), sh2 = (size_t)G * 2 * sizeof(float);
+  if (mode == 0) {
+    gn16_sums_k<0><<<grid, g.threads, sh1, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride, tmp);
+    gn16_apply_k<0><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride,
+                                                  tmp, g.chunks, out, acc);
+  } else {
+    gn16_sums_k<1><<<grid, g.threads, sh1, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride, tmp);
+    gn16_apply_k<1><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride,
+                                                  tmp, g.chunks, out, acc);
+  }
+  return last_err();
+}
+
+const char* ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C, const __half* t,
+                   int nb, int mode, __half* out, float acc, int k_slot, long p_stride, cudaStream_t st) {
+  if (C % 8) return "layernorm: C must be a multiple of 8 for fp16 tangents";
+  if (k_slot < 1) k_slot = nb;
+  const long rows = rows_p * nb;
+  const unsigned grid = grid_for(rows * 32, 256, 8);
+  const int nv = (C + 255) / 256;
+#define PB_LN16(M_, NV_) ln16_k<M_, NV_><<<grid, 256, 0, st>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, k_slot, p_stride)
+#define PB_LN16_MODE(M_)                                                                                    \
+  do {                                                                                                      \
+    if (nv == 1) PB_LN16(M_, 1); else if (nv == 2) PB_LN16(M_, 2); else if (nv == 3) PB_LN16(M_, 3);        \
+    else if (nv <= 5) PB_LN16(M_, 5); else PB_LN16(M_, 0);                                                  \
+  } while (0)
+  if (mode == 0) PB_LN16_MODE(0); else PB_LN16_MODE(1);
+#undef PB_LN16
+#undef PB_LN16_MODE
+  return last_err();
+}
+
+const char* copy2d(__half* dst, long ldd, const __half* src, long lds, long rows, int cols, float beta, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return nullptr;
+  if (cols % 8 || ldd % 8 || lds % 8 || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15))
+    return "copy2d: fp16 slices must be multiples of 8 columns with 16-byte aligned rows";
+  copy2d16_k<<<grid_for(rows * (cols / 8), 256, 16), 256, 0, st>>>(dst, ldd, src, lds, rows, cols / 8, beta);
+  return last_err();
+}
+
+const char* col2im_s2(const __half* col, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, __half* gx, float beta,
+                      cudaStream_t st) {
+  if (C % 8) return "col2im: C must be a multiple of 8 for fp16 tangents";
+  const long total = (long)nb * H * W * (C / 8);
+  col2im16_k<<<grid_for(total, 256, 16), 256, 0, st>>>(reinterpret_cast<const uint4*>(col), nb, H, W, C / 8, pad_lo, Ho, Wo,
+                                                       reinterpret_cast<uint4*>(gx), beta);
+  return last_err();
+}
+
+const char* upsample2x_vjp(const __half* gy, int nb, int H, int W, int C, __half* gx, float beta, cudaStream_t st) {
+  if (C % 8) return "upsample_vjp: C must be a multiple of 8 for fp16 tangents";
+  const long total = (long)nb * H * W * (C / 8);
+  upsample_vjp16_k<<<grid_for(total, 256, 16), 256, 0, st>>>(reinterpret_cast<const uint4*>(gy), nb, H, W, C / 8,
+                                                             reinterpret_cast<uint4*>(gx), beta);
+  return last_err();
+}
+
+const char* to_f32(float* dst, const __half* src, size_t n, cudaStream_t st) {
+  if (n % 8 || (reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(src) & 15)) return "to_f32: n % 8 and alignment";
+  to_f32_k<<<grid_for((long)(n / 8), 256, 16), 256, 0, st>>>(dst, src, n / 8);
+  return last_err();
+}
+
+}  // namespace pb16

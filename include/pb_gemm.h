@@ -38,8 +38,8 @@ struct PbGemm {
                                          // 2: B (weights) split hi/lo, A as given
   // optional split-K scratch owned by the caller (nullptr: never split): room for the partial tiles
   float* ws; long ws_floats;
-  // element types: operands A/B fp32 (TF32 tensor cores) or fp16 (kind::f16); D/R fp32 or fp16 (fp16 needs fp16
-  // operands); bias, alpha, beta and the accumulation are always fp32
+  // element types: operands A/B fp32 (TF32 tensor cores) or fp16 (kind::f16); D/R fp32 or fp16, independently of the
+  // operand type; bias, alpha, beta and the accumulation are always fp32
   int ab_dtype, d_dtype;
 };
 

@@ -11,6 +11,12 @@
 // `round_tf32` of a producer: 0 store fp32 as is; 1 RNA-round to TF32 (the consumer is a TF32 GEMM); 2 store fp16 --
 // the output buffer then holds halves at the same element offsets and its only consumer is an fp16-operand GEMM
 // (pbk_gn_lin, pbk_ln_lin, pbk_geglu_jvp/vjp, pbk_im2col_s2, pbk_upsample2x, pbk_transpose; not together with accumulation).
+// io flags (the `round_tf32` / `io` argument of the tangent-path kernels): the low two bits are the OUTPUT mode above; bit 2 says the
+// tangent / cotangent INPUT holds halves.  The all-fp16 tangent plan of the engine passes PB_IN_F16 | PB_OUT_F16 everywhere
+// except at the ends (x_t-shaped V / W and h-shaped U cross the ABI as fp32).
+#define PB_RND_MASK 3
+#define PB_OUT_F16 2
+#define PB_IN_F16 4
 // "xp" arguments are PRIMAL tensors cached once per (x_t, t, prompt); "t"/"g" arguments carry the
 // nb tangent (JVP) or cotangent (VJP) directions packed on the batch axis.
 #pragma once
@@ -43,8 +49,9 @@ PBK pbk_event_destroy(void* ev);
 // ---- contraction ----
 PBK pbk_gemm(const PbGemm* g, pb_stream st);
 // direct 3x3/s1/p1 conv for tiny channel counts (conv_in and its transpose); w is [Cout][9][Cin]
+// io: PB_IN_F16 x holds halves, PB_OUT_F16 y holds halves (conv_in keeps its x_t-shaped side in fp32)
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout,
-                       float* y, float beta, pb_stream st);
+                       float* y, float beta, int io, pb_stream st);
 // stride-2 3x3 conv as im2col + GEMM; input row = 2*o + tap - pad_lo (pad_lo 1: SD, 0: DDPM (0,1,0,1) pad)
 PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad_lo, int Ho, int Wo, float* col, int round_tf32,
                   pb_stream st);
@@ -67,6 +74,7 @@ PBK pbk_round_tf32(float* dst, const float* src, size_t n, pb_stream st);
 extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands();
 PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st);               // n % 4 == 0
 PBK pbk_to_f16_scaled(void* dst, const float* src, size_t n, float scale, pb_stream st);
+PBK pbk_to_f32(float* dst, const void* src, size_t n, pb_stream st);              // n % 8 == 0
 
 // ---- GroupNorm (+ optional SiLU) ----
 // tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch (per-chunk partial sums, combined in a fixed order)
@@ -91,7 +99,7 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 
 // ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
 PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st);
-// round_tf32 + 4: the tangent input dh holds halves (it was written by an fp16-output GEMM)
+// round_tf32 | PB_IN_F16: the tangent input dh / gy holds halves
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
                   pb_stream st);
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
@@ -103,8 +111,9 @@ PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int round_tf32, pb_s
 PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32,
                     pb_stream st);
 // delta[b][h][i] = sum_c go[b][i][h*d + c] * o[i][h*d + c]
+// io & PB_IN_F16: go holds halves (o is primal fp32, delta fp32)
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
-                   pb_stream st);
+                   int io, pb_stream st);
 // dP[b][h][r][c] <- scale * P[h][r][c] * (dP[b][h][r][c] - (col_mode ? delta[b][h][c] : delta[b][h][r]))
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
                 int col_mode, int round_tf32, pb_stream st);
@@ -134,6 +143,9 @@ struct PbAttnLin {
   // p16: Pm, C1 and C2 hold HALVES (leading dimensions / strides in elements, rows multiples of 8) and Pm is pre-scaled by
   // p_scale (= Nc keeps softmax probabilities in fp16's normal range); the kernel divides the products by p_scale again
   int p16; float p_scale;
+  // s16 (needs p16): the S operands seg[].A / seg[].B hold halves as well (kind::f16 score products; head dim % 8 == 0) and D / D2
+  // are written as halves (ldd, sDb, ldd2, sD2b in elements); O, delta stay fp32; no residual R
+  int s16;
 };
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);

@@ -34,6 +34,10 @@ inline float opB(float x, int precise) { return precise >= 1 ? x : trunc_tf32(x)
 using h16 = _Float16;
 inline float ldx(const void* p, int dt, long i) { return dt ? (float)static_cast<const h16*>(p)[i] : static_cast<const float*>(p)[i]; }
 inline void stx(void* p, int dt, long i, float v) { if (dt) static_cast<h16*>(p)[i] = (h16)v; else static_cast<float*>(p)[i] = v; }
+inline int in16(int io) { return (io & PB_IN_F16) ? 1 : 0; }
+inline int out16(int io) { return (io & PB_RND_MASK) == PB_OUT_F16 ? 1 : 0; }
+// store: fp16 when the io flags say so, else fp32 (RNA-rounded when the low bit asks for it)
+inline void sto(void* p, int io, long i, float v) { if (out16(io)) static_cast<h16*>(p)[i] = (h16)v; else static_cast<float*>(p)[i] = mr(v, io & 1); }
 inline float sigm(float x) { return 1.f / (1.f + std::exp(-x)); }
 inline float silu_f(float x) { return x * sigm(x); }
 inline float silu_d(float x) { float s = sigm(x); return s * (1.f + x * (1.f - s)); }
@@ -51,10 +55,18 @@ PBK pbk_graph_begin(pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_end(pb_stream, void**, long*) { return "hostsim: no graphs"; }
 PBK pbk_graph_launch(void*, pb_stream) { return "hostsim: no graphs"; }
 PBK pbk_graph_destroy(void*) { return nullptr; }
-// the double models the fp32 / TF32 policy only: the engine asks and keeps every operand in fp32
-extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return 0; }
-PBK pbk_to_f16(void*, const float*, size_t, pb_stream) { return "hostsim: fp16 operands are not modelled"; }
-PBK pbk_to_f16_scaled(void*, const float*, size_t, float, pb_stream) { return "hostsim: fp16 operands are not modelled"; }
+// PB_HOSTSIM_F16=1: the double models the all-fp16 tangent plan too (halves by _Float16, round to nearest even), so that the
+// engine's fp16 sequencing / offsets are testable without a GPU; default: the fp32 / TF32 policy only
+extern "C" __attribute__((visibility("default"))) int pbk_has_f16_operands() { return std::getenv("PB_HOSTSIM_F16") != nullptr; }
+PBK pbk_to_f16_scaled(void* dst, const float* src, size_t n, float scale, pb_stream) {
+  for (size_t i = 0; i < n; ++i) static_cast<h16*>(dst)[i] = (h16)(src[i] * scale);
+  return nullptr;
+}
+PBK pbk_to_f16(void* dst, const float* src, size_t n, pb_stream st) { return pbk_to_f16_scaled(dst, src, n, 1.f, st); }
+PBK pbk_to_f32(float* dst, const void* src, size_t n, pb_stream) {
+  for (size_t i = 0; i < n; ++i) dst[i] = (float)static_cast<const h16*>(src)[i];
+  return nullptr;
+}
 // timing probes: the double has no clock; a non-null token keeps the engine's bookkeeping exercised
 PBK pbk_event_record(void** ev, pb_stream) { static int token; *ev = &token; return nullptr; }
 extern "C" __attribute__((visibility("default"))) float pbk_event_elapsed_ms(void*, void*) { return 0.f; }
@@ -64,7 +76,6 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
   const PbGemm& g = *gp;
   if (g.M <= 0 || g.N <= 0) return "gemm: empty problem";
   const int ab = g.ab_dtype, dd = g.d_dtype;
-  if (!ab && dd) return "gemm: fp16 output needs fp16 operands";
   if (g.conv) {
     const PbGemmSeg& s = g.seg[0];
     const int C = s.K, H = g.H, W = g.W;
@@ -118,7 +129,8 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
 }
 
 PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const float* w, const float* bias, int Cout, float* y,
-                       float beta, pb_stream) {
+                       float beta, int io, pb_stream) {
+  const int xi = in16(io), yo = out16(io);
 #pragma omp parallel for schedule(static)
   for (long pix = 0; pix < (long)nb * H * W; ++pix) {
     const int px = pix % W, py = (pix / W) % H; const long b = pix / ((long)W * H);
@@ -127,12 +139,12 @@ PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const floa
       for (int tap = 0; tap < 9; ++tap) {
         const int iy = py + tap / 3 - 1, ix = px + tap % 3 - 1;
         if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-        const float* xp = x + ((b * H + iy) * W + ix) * Cin;
+        const long x0 = ((b * H + iy) * W + ix) * Cin;
         const float* wp = w + ((long)co * 9 + tap) * Cin;
-        for (int ci = 0; ci < Cin; ++ci) acc += xp[ci] * wp[ci];
+        for (int ci = 0; ci < Cin; ++ci) acc += ldx(x, xi, x0 + ci) * wp[ci];
       }
-      float* p = y + pix * Cout + co;
-      *p = beta != 0.f ? acc + beta * *p : acc;
+      const long o = pix * Cout + co;
+      stx(y, yo, o, beta != 0.f ? acc + beta * ldx(y, yo, o) : acc);
     }
   }
   return nullptr;
@@ -143,9 +155,9 @@ PBK pbk_im2col_s2(const float* x, int nb, int H, int W, int C, int pad, int Ho, 
       for (int ox = 0; ox < Wo; ++ox)
         for (int tap = 0; tap < 9; ++tap) {
           const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
-          float* d = col + ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
+          const long d0 = ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
           for (int c = 0; c < C; ++c)
-            d[c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? mr(x[((b * H + iy) * W + ix) * C + c], rnd) : 0.f;
+            sto(col, rnd, d0 + c, (iy >= 0 && iy < H && ix >= 0 && ix < W) ? ldx(x, in16(rnd), ((b * H + iy) * W + ix) * C + c) : 0.f);
         }
   return nullptr;
 }
@@ -158,19 +170,18 @@ PBK pbk_col2im_s2(const float* col, int nb, int H, int W, int C, int pad, int Ho
         for (int tap = 0; tap < 9; ++tap) {
           const int iy = 2 * oy + tap / 3 - pad, ix = 2 * ox + tap % 3 - pad;
           if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-          const float* s = col + ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
+          const long s0 = ((((b * Ho + oy) * Wo + ox) * 9) + tap) * C;
           float* d = acc.data() + ((b * H + iy) * W + ix) * C;
-          for (int c = 0; c < C; ++c) d[c] += s[c];
+          for (int c = 0; c < C; ++c) d[c] += ldx(col, in16(rnd), s0 + c);
         }
-  for (size_t i = 0; i < acc.size(); ++i) gx[i] = mr(beta != 0.f ? acc[i] + beta * gx[i] : acc[i], rnd);
+  for (size_t i = 0; i < acc.size(); ++i) sto(gx, rnd, (long)i, beta != 0.f ? acc[i] + beta * ldx(gx, out16(rnd), (long)i) : acc[i]);
   return nullptr;
 }
 PBK pbk_copy2d(float* dst, long ldd, const float* src, long lds, long rows, int cols, float beta, int rnd, pb_stream) {
   for (long r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
-      float* d = dst + r * ldd + c;
-      const float v = src[r * lds + c];
-      *d = mr(beta != 0.f ? v + beta * *d : v, rnd);
+      const float v = ldx(src, in16(rnd), r * lds + c);
+      sto(dst, rnd, r * ldd + c, beta != 0.f ? v + beta * ldx(dst, out16(rnd), r * ldd + c) : v);
     }
   return nullptr;
 }
@@ -178,14 +189,13 @@ PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, lo
                   int R, int C, float beta, int rnd, pb_stream) {
   for (long b = 0; b < nb; ++b)
     for (long h = 0; h < nh; ++h) {
-      const float* s = src + b * sbs + h * shs;
-      float* d = dst + b * sbd + h * shd;
+      const long s0 = b * sbs + h * shs, d0 = b * sbd + h * shd;
       for (int r = 0; r < R; ++r)
         for (int c = 0; c < C; ++c) {
-          float v = s[(long)r * lds + c];
-          float* p = d + (long)c * ldd + r;
-          if (beta != 0.f) v += beta * *p;
-          *p = mr(v, rnd);
+          float v = ldx(src, in16(rnd), s0 + (long)r * lds + c);
+          const long o = d0 + (long)c * ldd + r;
+          if (beta != 0.f) v += beta * ldx(dst, out16(rnd), o);
+          sto(dst, rnd, o, v);
         }
     }
   return nullptr;
@@ -195,7 +205,7 @@ PBK pbk_upsample2x(const float* x, int nb, int H, int W, int C, float* y, int rn
     for (int oy = 0; oy < 2 * H; ++oy)
       for (int ox = 0; ox < 2 * W; ++ox)
         for (int c = 0; c < C; ++c)
-          y[((b * 2 * H + oy) * 2 * W + ox) * C + c] = mr(x[((b * H + oy / 2) * W + ox / 2) * C + c], rnd);
+          sto(y, rnd, ((b * 2 * H + oy) * 2 * W + ox) * C + c, ldx(x, in16(rnd), ((b * H + oy / 2) * W + ox / 2) * C + c));
   return nullptr;
 }
 PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, float beta, int rnd, pb_stream) {
@@ -205,9 +215,9 @@ PBK pbk_upsample2x_vjp(const float* gy, int nb, int H, int W, int C, float* gx, 
         for (int c = 0; c < C; ++c) {
           float a = 0.f;
           for (int dy = 0; dy < 2; ++dy)
-            for (int dx = 0; dx < 2; ++dx) a += gy[((b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C + c];
-          float* p = gx + ((b * H + y) * W + x) * C + c;
-          *p = mr(beta != 0.f ? a + beta * *p : a, rnd);
+            for (int dx = 0; dx < 2; ++dx) a += ldx(gy, in16(rnd), ((b * 2 * H + 2 * y + dy) * 2 * W + 2 * x + dx) * C + c);
+          const long o = ((b * H + y) * W + x) * C + c;
+          sto(gx, rnd, o, beta != 0.f ? a + beta * ldx(gx, out16(rnd), o) : a);
         }
   return nullptr;
 }
@@ -249,7 +259,7 @@ PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const floa
       for (int p = 0; p < HW; ++p)
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
           const float xh = (xp[(long)p * C + c] - mean[g]) * rstd[g];
-          float u = t[(b * HW + p) * C + c];
+          float u = ldx(t, in16(rnd), (b * HW + p) * C + c);
           if (mode == 1) u *= silu ? gamma[c] * silu_d(gamma[c] * xh + beta[c]) : gamma[c];
           s1 += u; s2 += (double)xh * u;
         }
@@ -258,11 +268,11 @@ PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const floa
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
           const float xh = (xp[(long)p * C + c] - mean[g]) * rstd[g];
           const float f = silu ? gamma[c] * silu_d(gamma[c] * xh + beta[c]) : gamma[c];
-          const float tv = t[(b * HW + p) * C + c];
+          const float tv = ldx(t, in16(rnd), (b * HW + p) * C + c);
           float v = mode == 0 ? f * rstd[g] * (tv - m1 - xh * m2) : rstd[g] * (tv * f - m1 - xh * m2);
-          float* o = out + (b * HW + p) * C + c;
-          if (acc != 0.f) v += acc * *o;
-          *o = mr(v, rnd);
+          const long o = (b * HW + p) * C + c;
+          if (acc != 0.f) v += acc * ldx(out, out16(rnd), o);
+          sto(out, rnd, o, v);
         }
     }
   return nullptr;
@@ -287,16 +297,18 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
     double s1 = 0, s2 = 0;
     for (int c = 0; c < C; ++c) {
       const float xh = (xp[rp * C + c] - mean[rp]) * rstd[rp];
-      const float u = mode == 1 ? t[r * C + c] * gamma[c] : t[r * C + c];
+      const float tv = ldx(t, in16(rnd), r * C + c);
+      const float u = mode == 1 ? tv * gamma[c] : tv;
       s1 += u; s2 += (double)xh * u;
     }
     const float m1 = (float)(s1 / C), m2 = (float)(s2 / C);
     for (int c = 0; c < C; ++c) {
       const float xh = (xp[rp * C + c] - mean[rp]) * rstd[rp];
-      float v = mode == 0 ? gamma[c] * rstd[rp] * (t[r * C + c] - m1 - xh * m2) : rstd[rp] * (t[r * C + c] * gamma[c] - m1 - xh * m2);
-      float* o = out + r * C + c;
-      if (acc != 0.f) v += acc * *o;
-      *o = mr(v, rnd);
+      const float tv = ldx(t, in16(rnd), r * C + c);
+      float v = mode == 0 ? gamma[c] * rstd[rp] * (tv - m1 - xh * m2) : rstd[rp] * (tv * gamma[c] - m1 - xh * m2);
+      const long o = r * C + c;
+      if (acc != 0.f) v += acc * ldx(out, out16(rnd), o);
+      sto(out, rnd, o, v);
     }
   }
   return nullptr;
@@ -311,7 +323,7 @@ PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, 
     const long rp = r % rows_p;
     for (int c = 0; c < F; ++c) {
       const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c];
-      dy[r * F + c] = mr(dh[r * 2 * F + c] * gelu_f(g) + a * gelu_d(g) * dh[r * 2 * F + F + c], rnd);
+      sto(dy, rnd, r * F + c, ldx(dh, in16(rnd), r * 2 * F + c) * gelu_f(g) + a * gelu_d(g) * ldx(dh, in16(rnd), r * 2 * F + F + c));
     }
   }
   return nullptr;
@@ -320,9 +332,9 @@ PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, 
   for (long r = 0; r < rows_p * nb; ++r) {
     const long rp = r % rows_p;
     for (int c = 0; c < F; ++c) {
-      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c], y = gy[r * F + c];
-      gh[r * 2 * F + c] = mr(y * gelu_f(g), rnd);
-      gh[r * 2 * F + F + c] = mr(y * a * gelu_d(g), rnd);
+      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c], y = ldx(gy, in16(rnd), r * F + c);
+      sto(gh, rnd, r * 2 * F + c, y * gelu_f(g));
+      sto(gh, rnd, r * 2 * F + F + c, y * a * gelu_d(g));
     }
   }
   return nullptr;
@@ -349,12 +361,12 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
   }
   return nullptr;
 }
-PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta, pb_stream) {
+PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta, int io, pb_stream) {
   for (long b = 0; b < nb; ++b)
     for (int h = 0; h < H; ++h)
       for (int i = 0; i < N; ++i) {
         double s = 0;
-        for (int c = 0; c < d; ++c) s += (double)go[(b * N + i) * ldg + h * d + c] * o[(long)i * ldo + h * d + c];
+        for (int c = 0; c < d; ++c) s += (double)ldx(go, in16(io), (b * N + i) * ldg + h * d + c) * o[(long)i * ldo + h * d + c];
         delta[(b * H + h) * N + i] = (float)s;
       }
   return nullptr;
@@ -378,7 +390,10 @@ PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
 }
 PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
   const PbAttnLin& a = *ap;
-  if (a.p16) return "hostsim: fp16 attention operands are not modelled";
+  const int p16 = a.p16 ? 1 : 0, s16 = a.s16 ? 1 : 0;      // Pm / C1 / C2 halves (Pm pre-scaled); S operands and D / D2 halves
+  if (s16 && !p16) return "attn_lin: fp16 S operands need the fp16 probability path";
+  const float inv_ps = p16 ? 1.f / a.p_scale : 1.f;
+  auto opnd = [&](float v) { return p16 ? v : trunc_tf32(v); };           // operand of an accumulating product
   for (long b = 0; b < a.nb; ++b)
     for (long h = 0; h < a.nh; ++h) {
 #pragma omp parallel for schedule(static)
@@ -388,32 +403,36 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
         for (int c = 0; c < a.Nc; ++c) {
           float s = 0.f;
           for (int sg = 0; sg < a.nseg; ++sg) {
-            const float* A = static_cast<const float*>(a.seg[sg].A) + b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
-            const float* B = static_cast<const float*>(a.seg[sg].B) + b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
-            for (int k = 0; k < a.d; ++k) s += trunc_tf32(A[k]) * trunc_tf32(B[k]);
+            const long a0 = b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
+            const long b0 = b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
+            for (int k = 0; k < a.d; ++k)
+              s += s16 ? ldx(a.seg[sg].A, 1, a0 + k) * ldx(a.seg[sg].B, 1, b0 + k)
+                       : trunc_tf32(ldx(a.seg[sg].A, 0, a0 + k)) * trunc_tf32(ldx(a.seg[sg].B, 0, b0 + k));
           }
           float dl = 0.f;
           if (a.delta && a.delta_mode == 1) dl = a.delta[(b * a.nh + h) * a.Mr + r];
           if (a.delta && a.delta_mode == 2) dl = a.delta[(b * a.nh + h) * a.Nc + c];
-          T[c] = rna(a.Pm[h * a.sPh + (long)r * a.ldp + c] * (a.alpha1 * s - dl));
+          const float t = ldx(a.Pm, p16, h * a.sPh + (long)r * a.ldp + c) * (a.alpha1 * s - dl);
+          T[c] = p16 ? (float)(h16)std::min(std::max(t, -65504.f), 65504.f) : rna(t);
           rs += T[c];
         }
+        rs *= inv_ps;
         for (int n = 0; n < a.d; ++n) {
           double acc = 0;
-          const float* C1 = a.C1 + h * a.sCh + (long)n * a.ldc;
-          for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * trunc_tf32(C1[c]);
+          const long c10 = h * a.sCh + (long)n * a.ldc;
+          for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * opnd(ldx(a.C1, p16, c10 + c));
           double e2 = 0;
+          const long o2 = b * a.sD2b + (long)r * a.ldd2 + h * a.d + n;
           if (a.C2) {
-            const float* C2 = a.C2 + b * a.sC2b + h * a.sC2h + (long)n * a.ldc2;
-            const float* Pr = a.Pm + h * a.sPh + (long)r * a.ldp;
-            for (int c = 0; c < a.Nc; ++c) e2 += (double)trunc_tf32(Pr[c]) * trunc_tf32(C2[c]);
-            if (a.D2) a.D2[b * a.sD2b + (long)r * a.ldd2 + h * a.d + n] = mr((float)e2, a.round_tf32);
+            const long c20 = b * a.sC2b + h * a.sC2h + (long)n * a.ldc2, p0 = h * a.sPh + (long)r * a.ldp;
+            for (int c = 0; c < a.Nc; ++c) e2 += (double)opnd(ldx(a.Pm, p16, p0 + c)) * opnd(ldx(a.C2, p16, c20 + c));
+            if (a.D2) stx(a.D2, s16, o2, s16 ? (float)e2 * inv_ps : mr((float)e2 * inv_ps, a.round_tf32));
             else acc += e2;
           }
-          float v = a.alpha2 * (float)acc;
+          float v = a.alpha2 * inv_ps * (float)acc;
           if (a.want_rsum && a.O) v -= (float)rs * a.O[(long)r * a.ldo + h * a.d + n];
           if (a.R) v += a.beta * a.R[b * a.sRb + (long)r * a.ldr + h * a.d + n];
-          a.D[b * a.sDb + (long)r * a.ldd + h * a.d + n] = mr(v, a.round_tf32);
+          stx(a.D, s16, b * a.sDb + (long)r * a.ldd + h * a.d + n, s16 ? v : mr(v, a.round_tf32));
         }
       }
     }

@@ -405,3 +405,65 @@ def test_orthonormalize_rank_deficient_rows_are_zero_not_noise(hostsim):
     sref = torch.linalg.svdvals(W.double()).sqrt().float()
     assert torch.allclose(s[:2], sref[:2], rtol=1e-5) and float(s[2]) == 0.0
     assert torch.allclose(V[:2] @ V[:2].T, torch.eye(2), atol=1e-5) and float(V[2].abs().max()) == 0.0
+
+
+# ---- the all-fp16 tangent plan on the host double: PB_HOSTSIM_F16 makes the double model fp16 storage, so the
+# ---- engine's fp16 sequencing (element sizes, offsets, conversions at the fp32 ends, fp16 attention copies) runs without a GPU
+@pytest.mark.parametrize("name,op,bi,fused_min", [("sd_tiny", "mid", 0, 1), ("sd_tiny", "mid", 0, 1 << 30), ("sd_tiny", "up", 1, 1),
+                                                  ("sd_tiny", "up", 3, 1 << 30), ("sd_tiny_lin", "mid", 0, 1), ("uncond_tiny", "mid", 0, 1),
+                                                  ("sd_tiny", "full", 0, 1)])
+def test_fp16_tangent_plan_operator_level(hostsim, monkeypatch, name, op, bi, fused_min):
+    monkeypatch.setenv("PB_HOSTSIM_F16", "1")
+    k = 3
+    eng, m, x, t, ctx = make_engine(hostsim, name, op, bi, k, dict(fused_min_tokens=fused_min))
+    from diffusion_pullback_b200 import _native as N
+    info = N.PbPlanInfo()
+    assert hostsim.pb_plan_summary(eng.h, C.byref(info)) == 0
+    assert info.n_gemm_f16_jvp == info.n_gemm > 0                   # the plan did switch to fp16 tangents
+    if op == "full":
+        f = lambda z: (m(z, t, ctx.expand(z.shape[0], -1, -1)) if ctx is not None else m(z, t))
+    else:
+        f = PO.make_h_fn(m, t, ctx, op, bi)
+    h = eng.set_point(x, float(t), ctx, want_h=True)
+    href = f(x)
+    assert rel(h, href) < 2e-3                                      # the primal pass is the TF32 policy, unchanged
+    torch.manual_seed(0)
+    V = PO.initial_subspace(x.numel(), k)
+    U = eng.jvp(V)
+    Uref = PO.jvp_columns(f, x, V.reshape(k, *x.shape[1:])).reshape(k, -1)
+    G = torch.randn_like(Uref)
+    W = eng.vjp(G)
+    Wref = PO.vjp_rows(f, x, G.reshape(k, *href.shape[1:]))
+    # 10-bit mantissas on 32..64-channel contractions: 1e-3..3e-3 per pass on the tiny fixtures
+    assert rel(U, Uref) < 6e-3 and rel(W, Wref) < 6e-3, (rel(U, Uref), rel(W, Wref))
+    lhs, rhs = float((U * G).sum()), float((W * V).sum())
+    assert abs(lhs - rhs) < 3e-3 * float(U.norm() * G.norm())
+    assert rel(eng.jvp(V[:1]), Uref[:1]) < 6e-3 and rel(eng.vjp(G[:2]), Wref[:2]) < 6e-3
+
+
+def test_fp16_tangent_plan_pullback_and_slots(hostsim, monkeypatch):
+    monkeypatch.setenv("PB_HOSTSIM_F16", "1")
+    g = torch.load(os.path.join(GOLDEN, "sd_tiny_mid.pt"))
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, g["k"], dict(fused_min_tokens=1))
+    eng.set_point(x, float(t), ctx)
+    u, s, vT, info = eng.pullback(g["v0"], g["iters"], g["iters"], 0.0)
+    rep = PO.parity_report(s, vT, g["s"], g["vT"])
+    assert rep["s_rel_max"] < 5e-3 and rep["subspace"] > 0.999, rep
+    # problem slots: two problems batched against one at a time, same fp16 plan
+    k, P = 2, 2
+    eng1, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, k, dict(fused_min_tokens=1))
+    engP, _, _, _, _ = make_engine(hostsim, "sd_tiny", "mid", 0, P * k, dict(fused_min_tokens=1))
+    engP.set_slots(P)
+    gen = torch.Generator().manual_seed(3)
+    xs = [x, torch.randn(x.shape, generator=gen)]
+    ts = [float(t), 412.0]
+    torch.manual_seed(0)
+    V0 = torch.cat([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0)
+    singles = []
+    for p in range(P):
+        eng1.set_point(xs[p], ts[p], ctx)
+        singles.append(eng1.jvp(V0[p * k:(p + 1) * k]))
+        engP.set_point(xs[p], ts[p], ctx, slot=p)
+    U = engP.jvp(V0)
+    for p in range(P):
+        assert rel(U[p * k:(p + 1) * k], singles[p]) < 1e-6

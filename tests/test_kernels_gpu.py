@@ -311,7 +311,7 @@ def test_attn_delta():
         Cc = H * d
         go, o = torch.randn(nb, Ntok, Cc, device="cuda"), torch.randn(Ntok, Cc, device="cuda")
         delta = torch.empty(nb, H, Ntok, device="cuda")
-        _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Cc), _p(o), C.c_long(Cc), nb, Ntok, H, d, _p(delta), _st()))
+        _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Cc), _p(o), C.c_long(Cc), nb, Ntok, H, d, _p(delta), 0, _st()))
         ref = (go.double() * o.double()[None]).view(nb, Ntok, H, d).sum(-1).permute(0, 2, 1)
         assert rel(delta, ref) < 1e-5
 
@@ -401,11 +401,11 @@ def test_data_movement():
     fwd, bwd = torch.empty(32, 9, 4, device="cuda"), torch.empty(4, 9, 32, device="cuda")
     _ok(N.leaf("pbk_pack_conv3x3")(_p(w), 32, 4, _p(fwd), _p(bwd), 0, _st()))
     yo = torch.empty(nb, H, W, 32, device="cuda")
-    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, 4, _p(fwd), _p(b), 32, _p(yo), C.c_float(0), _st()))
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, 4, _p(fwd), _p(b), 32, _p(yo), C.c_float(0), 0, _st()))
     assert rel(yo, F.conv2d(xi.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)) < 1e-5
     go = torch.randn(nb, H, W, 32, device="cuda")
     gi = torch.empty(nb, H, W, 4, device="cuda")
-    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, 32, _p(bwd), None, 4, _p(gi), C.c_float(0), _st()))
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, 32, _p(bwd), None, 4, _p(gi), C.c_float(0), 0, _st()))
     assert rel(gi, F.conv_transpose2d(go.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)) < 1e-5
 
 
@@ -420,13 +420,13 @@ def test_thin_convs_blocked(nb, H, W, Cin, Cout):
     _ok(N.leaf("pbk_pack_conv3x3")(_p(w), Cout, Cin, _p(fwd), _p(bwd), 0, _st()))
     y0 = torch.randn(nb, H, W, Cout, device="cuda")
     yo = y0.clone()
-    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, Cin, _p(fwd), _p(b), Cout, _p(yo), C.c_float(0.5), _st()))
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, Cin, _p(fwd), _p(b), Cout, _p(yo), C.c_float(0.5), 0, _st()))
     ref = F.conv2d(xi.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1) + 0.5 * y0
     assert rel(yo, ref) < 1e-5
     go = torch.randn(nb, H, W, Cout, device="cuda")
     g0 = torch.randn(nb, H, W, Cin, device="cuda")
     gi = g0.clone()
-    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, Cout, _p(bwd), None, Cin, _p(gi), C.c_float(1.0), _st()))
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, Cout, _p(bwd), None, Cin, _p(gi), C.c_float(1.0), 0, _st()))
     ref = F.conv_transpose2d(go.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1) + g0
     assert rel(gi, ref) < 1e-5
 
@@ -608,3 +608,229 @@ def test_attn_lin_fused(Mr, Nc, d, nb, nh, nseg, mode, c2):
         rs = Tr.sum(-1)                                               # [nb, nh, Mr]
         ref = ref - (rs.permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
     assert rel(D, ref) < 2e-4, rel(D, ref)                            # a few T elements round the other way (fp32 vs fp64 S)
+
+
+# ---- the all-fp16 tangent plan: kernels that read and write halves (io = PB_IN_F16 | PB_OUT_F16 = 6) ----
+IO16 = 6
+
+
+@pytest.mark.parametrize("nb,HW,Cc,G", [(5, 4096, 320, 32), (5, 64, 1280, 32), (2, 1024, 640, 32), (3, 256, 2560, 32), (2, 100, 64, 32),
+                                       (1, 4096, 32, 32), (3, 1024, 1920, 32), (2, 256, 960, 32)])
+def test_fp16_groupnorm_lin(nb, HW, Cc, G):
+    """pbk_gn_lin over fp16 tangents (gn16_sums_k + gn16_apply_k): JVP and VJP, with and without accumulation, against torch
+    autograd on the same half-rounded tangent; result correct to fp16 rounding of the output."""
+    torch.manual_seed(5)
+    x = torch.randn(1, HW, Cc, device="cuda") * 1.5 + 0.3
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    mean, rstd = torch.empty(G, device="cuda"), torch.empty(G, device="cuda")
+    nfl = N.raw().pbk_gn_tmp_floats
+    nfl.restype = C.c_size_t
+    tmp = torch.empty(max(nfl(HW, Cc, G, nb), nfl(HW, Cc, G, 1)), device="cuda")
+    _ok(N.leaf("pbk_gn_stats")(_p(x), 1, HW, Cc, G, C.c_float(1e-5), _p(mean), _p(rstd), _p(tmp), _st()))
+    for silu in (1, 0):
+        def f(z):
+            o = F.group_norm(z.permute(0, 2, 1), G, gamma, beta, 1e-5).permute(0, 2, 1)
+            return F.silu(o) if silu else o
+        t16 = torch.randn(nb, HW, Cc, device="cuda").half()
+        t = t16.float()
+        for mode in (0, 1):
+            if mode == 0:
+                ref = torch.cat([torch.func.jvp(f, (x,), (t[i:i + 1],))[1] for i in range(nb)])
+            else:
+                ref = torch.cat([torch.func.vjp(f, x)[1](t[i:i + 1])[0] for i in range(nb)])
+            out = torch.full((nb, HW, Cc), float("nan"), device="cuda", dtype=torch.float16)
+            _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t16), nb, mode, _p(out),
+                                     C.c_float(0), IO16, _p(tmp), _st()))
+            assert rel(out.float(), ref) < 6e-4, (silu, mode, rel(out.float(), ref))
+            prev = torch.randn(nb, HW, Cc, device="cuda").half()
+            out = prev.clone()
+            _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t16), nb, mode, _p(out),
+                                     C.c_float(1.0), IO16, _p(tmp), _st()))
+            assert rel(out.float(), ref + prev.float()) < 6e-4
+
+
+@pytest.mark.parametrize("rows,Cc", [(200, 320), (77, 640), (64, 1280), (130, 64), (50, 2560), (33, 96)])
+def test_fp16_layernorm_geglu(rows, Cc):
+    torch.manual_seed(4)
+    nb = 3
+    x = torch.randn(rows, Cc, device="cuda") + 0.3
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    y, mean, rstd = torch.empty_like(x), torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    _ok(N.leaf("pbk_ln_fwd")(_p(x), C.c_long(rows), Cc, _p(gamma), _p(beta), C.c_float(1e-5), _p(y), _p(mean), _p(rstd), 0, _st()))
+    f = lambda z: F.layer_norm(z, (Cc,), gamma, beta, 1e-5)
+    t16 = torch.randn(nb, rows, Cc, device="cuda").half()
+    for mode in (0, 1):
+        if mode == 0:
+            ref = torch.stack([torch.func.jvp(f, (x,), (t16[i].float(),))[1] for i in range(nb)])
+        else:
+            ref = torch.stack([torch.func.vjp(f, x)[1](t16[i].float())[0] for i in range(nb)])
+        prev = torch.randn(nb, rows, Cc, device="cuda").half()
+        for acc in (0.0, 1.0):
+            out = prev.clone()
+            _ok(N.leaf("pbk_ln_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), C.c_long(rows), Cc, _p(t16), nb, mode, _p(out), C.c_float(acc),
+                                     IO16, _st()))
+            assert rel(out.float(), ref + acc * prev.float()) < 6e-4
+    Fd = 4 * Cc
+    h = torch.randn(rows, 2 * Fd, device="cuda")
+    g = lambda z: z[..., :Fd] * F.gelu(z[..., Fd:])
+    dh = torch.randn(nb, rows, 2 * Fd, device="cuda").half()
+    dy = torch.empty(nb, rows, Fd, device="cuda", dtype=torch.float16)
+    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), IO16, _st()))
+    assert rel(dy.float(), torch.stack([torch.func.jvp(g, (h,), (dh[i].float(),))[1] for i in range(nb)])) < 6e-4
+    gy = torch.randn(nb, rows, Fd, device="cuda").half()
+    gh = torch.empty(nb, rows, 2 * Fd, device="cuda", dtype=torch.float16)
+    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), IO16, _st()))
+    assert rel(gh.float(), torch.stack([torch.func.vjp(g, h)[1](gy[i].float())[0] for i in range(nb)])) < 6e-4
+
+
+def test_fp16_data_movement():
+    torch.manual_seed(5)
+    nb, H, W, Cc = 2, 8, 8, 64
+    x = torch.randn(nb, H, W, Cc, device="cuda").half()
+    y = torch.empty(nb, 2 * H, 2 * W, Cc, device="cuda", dtype=torch.float16)
+    _ok(N.leaf("pbk_upsample2x")(_p(x), nb, H, W, Cc, _p(y), IO16, _st()))
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(y.float(), ref)
+    g0 = torch.randn(nb, H, W, Cc, device="cuda").half()
+    gx = g0.clone()
+    yy = torch.randn_like(y)
+    _ok(N.leaf("pbk_upsample2x_vjp")(_p(yy), nb, H, W, Cc, _p(gx), C.c_float(1.0), IO16, _st()))
+    refv = yy.float().view(nb, H, 2, W, 2, Cc).sum((2, 4)) + g0.float()
+    assert rel(gx.float(), refv) < 6e-4
+    for pad in (1, 0):
+        Ho = Wo = H // 2
+        col = torch.empty(nb, Ho, Wo, 9, Cc, device="cuda", dtype=torch.float16)
+        _ok(N.leaf("pbk_im2col_s2")(_p(x), nb, H, W, Cc, pad, Ho, Wo, _p(col), IO16, _st()))
+        xp = x.float().permute(0, 3, 1, 2)
+        xp = F.pad(xp, (1, 1, 1, 1)) if pad else F.pad(xp, (0, 1, 0, 1))
+        ref = F.unfold(xp, 3, stride=2).view(nb, Cc, 9, Ho, Wo).permute(0, 3, 4, 2, 1)
+        assert torch.equal(col.float(), ref.contiguous())
+        g = torch.randn(nb, Ho, Wo, 9, Cc, device="cuda").half()
+        gx = torch.empty(nb, H, W, Cc, device="cuda", dtype=torch.float16)
+        _ok(N.leaf("pbk_col2im_s2")(_p(g), nb, H, W, Cc, pad, Ho, Wo, _p(gx), C.c_float(0), IO16, _st()))
+        fold = F.fold(g.float().permute(0, 4, 3, 1, 2).reshape(nb, Cc * 9, Ho * Wo), (H + 2 * pad if pad else H + 1,) * 2, 3, stride=2)
+        fold = fold[:, :, 1:-1, 1:-1] if pad else fold[:, :, :-1, :-1]
+        assert rel(gx.float(), fold.permute(0, 2, 3, 1)) < 6e-4
+    # accumulating channel-slice copy (concat split / residual fan-in) over halves
+    src = torch.randn(50, 96, device="cuda").half()
+    d0 = torch.randn(50, 64, device="cuda").half()
+    dst = d0.clone()
+    _ok(N.leaf("pbk_copy2d")(_p(dst), C.c_long(64), C.c_void_p(src.data_ptr() + 32 * 2), C.c_long(96), C.c_long(50), 64, C.c_float(1.0), IO16, _st()))
+    assert rel(dst.float(), d0.float() + src[:, 32:].float()) < 6e-4
+    # transposes at the fp32 <-> fp16 ends and between halves (dV^T per head)
+    s32 = torch.randn(3, 100, 48, device="cuda")
+    for io, sdt, ddt in ((2, torch.float32, torch.float16), (4, torch.float16, torch.float32), (6, torch.float16, torch.float16)):
+        src = s32.to(sdt)
+        dst = torch.zeros(3, 48, 104, device="cuda", dtype=ddt)
+        _ok(N.leaf("pbk_transpose")(_p(dst), C.c_long(104), C.c_long(48 * 104), C.c_long(0), _p(src), C.c_long(48), C.c_long(100 * 48),
+                                    C.c_long(0), 3, 1, 100, 48, C.c_float(0), io, _st()))
+        assert torch.equal(dst[:, :, :100].float(), src.transpose(1, 2).to(ddt).float())
+    # fp16 -> fp32 staging copy
+    hsrc = torch.randn(4096, device="cuda").half()
+    f32 = torch.empty(4096, device="cuda")
+    _ok(N.leaf("pbk_to_f32")(_p(f32), _p(hsrc), C.c_size_t(4096), _st()))
+    assert torch.equal(f32, hsrc.float())
+    # attn_delta over an fp16 cotangent
+    nbd, Ntok, Hh, d = 3, 200, 4, 40
+    go = torch.randn(nbd, Ntok, Hh * d, device="cuda").half(); o = torch.randn(Ntok, Hh * d, device="cuda")
+    delta = torch.empty(nbd, Hh, Ntok, device="cuda")
+    _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Hh * d), _p(o), C.c_long(Hh * d), nbd, Ntok, Hh, d, _p(delta), 4, _st()))
+    assert rel(delta, (go.double() * o.double()[None]).view(nbd, Ntok, Hh, d).sum(-1).permute(0, 2, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("nb,H,W,Cin,Cout", [(5, 64, 64, 4, 320), (2, 19, 23, 3, 128), (3, 16, 16, 4, 32), (2, 8, 8, 4, 1280)])
+def test_fp16_thin_convs(nb, H, W, Cin, Cout):
+    """conv_in in the all-fp16 plan: fp32 x_t-shaped tangent in -> fp16 out (io 2); its transpose fp16 in -> fp32 out (io 4)."""
+    torch.manual_seed(11)
+    xi = torch.randn(nb, H, W, Cin, device="cuda")
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda") / 6
+    fwd, bwd = torch.empty(Cout, 9, Cin, device="cuda"), torch.empty(Cin, 9, Cout, device="cuda")
+    _ok(N.leaf("pbk_pack_conv3x3")(_p(w), Cout, Cin, _p(fwd), _p(bwd), 0, _st()))
+    yo = torch.empty(nb, H, W, Cout, device="cuda", dtype=torch.float16)
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(xi), nb, H, W, Cin, _p(fwd), None, Cout, _p(yo), C.c_float(0), 2, _st()))
+    assert rel(yo.float(), F.conv2d(xi.permute(0, 3, 1, 2), w, None, padding=1).permute(0, 2, 3, 1)) < 6e-4
+    go = torch.randn(nb, H, W, Cout, device="cuda").half()
+    gi = torch.empty(nb, H, W, Cin, device="cuda")
+    _ok(N.leaf("pbk_conv3x3_direct")(_p(go), nb, H, W, Cout, _p(bwd), None, Cin, _p(gi), C.c_float(0), 4, _st()))
+    assert rel(gi, F.conv_transpose2d(go.float().permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)) < 1e-5
+
+
+def test_gemm_tf32_operands_fp16_output():
+    """fp32 (TF32) operands with an fp16 result: the last products of the materialised attention path in the all-fp16 plan."""
+    torch.manual_seed(2)
+    M, Nn, K = 300, 200, 96
+    A, B = torch.randn(M, K, device="cuda"), torch.randn(Nn, K, device="cuda")
+    R = torch.randn(M, Nn, device="cuda").half()
+    D = torch.full((M, Nn), float("nan"), device="cuda", dtype=torch.float16)
+    gemm(A, B, D, M=M, N_=Nn, K=K, lda=K, ldb=K, ldd=Nn, R=R, ldr=Nn, alpha=0.5, beta=1.0, ab_dtype=0, d_dtype=1)
+    ref = 0.5 * (tf32_trunc(A).double() @ tf32_trunc(B).double().T) + R.double()
+    assert rel(D, ref) < 6e-4
+
+
+@pytest.mark.parametrize("case", ["jvp", "vjp_a", "vjp_b", "cross"])
+@pytest.mark.parametrize("Mr,Nc,d,nb,nh", [(256, 256, 40, 2, 2), (1024, 1024, 80, 2, 3), (384, 512, 64, 2, 2), (4096, 4096, 40, 1, 2),
+                                           (300, 77, 40, 3, 2), (520, 264, 16, 2, 1), (256, 128, 96, 1, 2), (128, 192, 48, 2, 2)])
+def test_attn_lin_all_fp16(Mr, Nc, d, nb, nh, case):
+    """PbAttnLin with p16 = s16 = 1 (the all-fp16 tangent plan): fp16 score operands (kind::f16 over the head dim, incl. the
+    3-of-4-MMA last block of head dim 40 and the 32-byte tail of head dim 80), scaled fp16 probabilities, fp16 C1 / C2, fp16
+    outputs; in the roles the engine uses (JVP: two segments + folded P.C2 + row-sum term; VJP-A: row deltas; VJP-B: column
+    deltas + separate D2; cross-attention: one segment + row sums) against fp64 on the same half-rounded operands."""
+    torch.manual_seed(7)
+    Cc = nh * d
+    ldp = (Nc + 7) // 8 * 8
+    scale = 2.0 ** round(0.5 * math.log2(Nc))
+    hf = lambda *s: torch.randn(*s, device="cuda").half()
+    A0, B0 = hf(nb, Mr, Cc), hf(Nc, Cc)
+    A1, B1 = hf(Mr, Cc), hf(nb, Nc, Cc)
+    Pm = torch.softmax(torch.randn(nh, Mr, ldp, device="cuda") * 2, -1).contiguous()
+    Pm[..., Nc:] = 0
+    P16 = (Pm * scale).half().contiguous()
+    C1 = hf(nh, d, ldp)
+    C2 = hf(nb, nh, d, ldp)
+    O = torch.randn(Mr, Cc, device="cuda")
+    nseg = 2 if case == "jvp" else 1
+    mode = {"jvp": 0, "cross": 0, "vjp_a": 1, "vjp_b": 2}[case]
+    c2 = {"jvp": 1, "cross": 0, "vjp_a": 0, "vjp_b": 2}[case]
+    delta = torch.randn(nb, nh, Mr if mode == 1 else Nc, device="cuda") if mode else None
+    D = torch.full((nb, Mr, Cc), float("nan"), device="cuda", dtype=torch.float16)
+    D2 = torch.full((nb, Mr, Cc), float("nan"), device="cuda", dtype=torch.float16)
+    a = N.PbAttnLin()
+    a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, nb, nh, nseg
+    s0 = a.seg[0]
+    s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = A0.data_ptr(), Cc, Mr * Cc, d, B0.data_ptr(), Cc, 0, d
+    s1 = a.seg[1]
+    s1.A, s1.lda, s1.sAb, s1.sAh, s1.B, s1.ldb, s1.sBb, s1.sBh = A1.data_ptr(), Cc, 0, d, B1.data_ptr(), Cc, Nc * Cc, d
+    a.alpha1, a.alpha2, a.beta = d ** -0.5, 0.7, 0.0
+    a.Pm, a.ldp, a.sPh = P16.data_ptr(), ldp, Mr * ldp
+    a.delta, a.delta_mode = (delta.data_ptr() if mode else None), mode
+    a.want_rsum, a.O, a.ldo = int(mode == 0), O.data_ptr(), Cc
+    a.C1, a.ldc, a.sCh = C1.data_ptr(), ldp, d * ldp
+    a.D, a.ldd, a.sDb, a.round_tf32 = D.data_ptr(), Cc, Mr * Cc, 1
+    a.p16, a.p_scale, a.s16 = 1, scale, 1
+    if c2:
+        a.C2, a.ldc2, a.sC2h, a.sC2b = C2.data_ptr(), ldp, d * ldp, nh * d * ldp
+    if c2 == 2:
+        a.D2, a.ldd2, a.sD2b = D2.data_ptr(), Cc, Mr * Cc
+    _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+    S = torch.einsum("bihd,jhd->bhij", A0.double().view(nb, Mr, nh, d), B0.double().view(Nc, nh, d))
+    if nseg == 2:
+        S = S + torch.einsum("ihd,bjhd->bhij", A1.double().view(Mr, nh, d), B1.double().view(nb, Nc, nh, d))
+    S = S * d ** -0.5
+    if mode == 1:
+        S = S - delta.double()[..., :, None]
+    if mode == 2:
+        S = S - delta.double()[..., None, :]
+    Ps = P16.double()[None, :, :, :Nc]
+    Tr = (Ps * S).float().half().double()
+    acc = torch.einsum("bhij,hnj->bihn", Tr, C1.double()[..., :Nc]).reshape(nb, Mr, Cc) / scale
+    if c2:
+        e2 = torch.einsum("hij,bhnj->bihn", P16.double()[..., :Nc], C2.double()[..., :Nc]).reshape(nb, Mr, Cc) / scale
+        if c2 == 1:
+            acc = acc + e2
+        else:
+            assert rel(D2.float(), e2) < 6e-4, rel(D2.float(), e2)
+    ref = 0.7 * acc
+    if mode == 0:
+        rs = Tr.sum(-1) / scale
+        ref = ref - (rs.permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
+    assert rel(D.float(), ref) < 8e-4, rel(D.float(), ref)
