@@ -254,7 +254,12 @@ def run_ours(args, wl):
     unet = SY.SyntheticUNet(model_name, upto=(op, bi), device=dev)
     cfg = PB.unet_config(unet)
     size, ctx_len = unet.config["sample_size"], unet.config["ctx_len"]
-    S = max(1, args.slots)                                   # problems per step (batched through pb_set_slots when > 1)
+    # problems per step, batched through pb_set_slots when > 1.  Default: as many queued problems as fit one handle (k_max = 64
+    # columns), at most 5 -- the metric counts problems x iterations per second, the reference's own driver loops
+    # over independent problems (main.py:71-76), and one problem at a time is reported beside it (`slots1`)
+    S = max(1, args.slots) if args.slots else max(1, min(5, 64 // k))
+    if args.shard == "tangent":
+        S = 1
     if S > 1 and (args.shard == "tangent" or S * k > 64):
         raise SystemExit("bench.py: --slots needs problem sharding and slots * pca_rank <= 64")
     eng = PB.PullbackEngine(cfg, size, size, op, bi, k, ctx_len, dev)
@@ -330,6 +335,28 @@ def run_ours(args, wl):
     nprob = K if tangent else world * K * S                   # problems solved by the whole job
     value = nprob * iters / secs
 
+    # ---- one problem at a time (the reference's granularity) beside the batched number ----
+    slots1 = None
+    if S > 1:
+        n1 = max(2, min(K, 4))
+        for i in range(2):
+            eng.set_point(xd[i], tval, ctxd); eng.pullback(v0d[i], iters, iters, 0.0)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(n1):
+            eng.set_point(xd[i], tval, ctxd)
+            eng.pullback(v0d[i], iters, iters, 0.0)
+        f1.record()
+        barrier()
+        ms1 = f0.elapsed_time(f1)
+        if world > 1:
+            tm = torch.tensor([ms1], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms1 = float(tm)
+        slots1 = {"value": world * n1 * iters / (ms1 / 1e3), "unit": UNIT, "steps": n1, "ms_per_problem": ms1 / n1,
+                  "note": "one problem per pb_pullback call on the same GPU(s), device-timed"}
+
     # ---- e2e: the C-ABI host entry with pinned host buffers, H2D / D2H inside the timed region ----
     xh = [x.contiguous().pin_memory() for x in xs]
     v0h = [v.pin_memory() for v in v0s]
@@ -376,15 +403,22 @@ def run_ours(args, wl):
     # ---- per-kernel timing: two eagerly launched iterations with an event pair around every contraction launch ----
     prof, prof_iters = None, 2
     if rank == 0:
-        eng.set_point(xd[0], tval, ctxd)
+        pe = engS if S > 1 else eng                          # probe the configuration `value` was measured on
+        if S > 1:
+            for p in range(S):
+                pe.set_point(xd[p], tval, ctxd, slot=p)
+            pv0 = torch.cat(v0d[:S], 0)
+        else:
+            pe.set_point(xd[0], tval, ctxd)
+            pv0 = v0d[0]
         torch.cuda.synchronize()
-        eng.profile_begin()
+        pe.profile_begin()
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
-        eng.pullback(v0d[0], prof_iters, prof_iters, 0.0)
+        pe.pullback(pv0, prof_iters, prof_iters, 0.0)
         pe1.record()
         torch.cuda.synchronize()
-        prof = eng.profile_read()
+        prof = pe.profile_read()
         prof["_eager_ms_per_iter"] = pe0.elapsed_time(pe1) / prof_iters
 
     if rank == 0:
@@ -414,16 +448,17 @@ def run_ours(args, wl):
             if tj:
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "f16/tf32 operands, f32 accumulate", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if tangent else "weak", "vs_baseline": None, "dtype": "f16 tangents and operands, f32 accumulate (primal pass tf32)", "data": "synthetic",
                 "config": {"workload": wl, "model": model_name + " (random-init)", "latent": [cfg["in_channels"], size, size], "op": op,
                            "block_idx": bi, "pca_rank": k, "power_iters": iters, "t": tval, "problems_per_rank": K * S, "slots": S,
                            "parallelism": (f"tangent-sharded x{world} (k columns of one problem split over the ranks, one all-gather of W per iteration)"
                                            if tangent else f"problem-sharded x{world}") +
-                                          (f"; {S} problems per step batched through pb_set_slots (value and e2e; the kernel probes time one problem per call)" if S > 1 else ""), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
+                                          (f"; {S} problems per step batched through pb_set_slots (value, e2e and the kernel probes); `slots1` = one problem per call" if S > 1 else ""), "l2": "working set per iteration (>= 2.8 GB of weights + activations) exceeds the 126 MB L2",
                            "column_iters_per_s": value * k},
                 "clocks": clocks,
                 "e2e": {"value": (world if not tangent else 1) * K * S * iters / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
+                "slots1": slots1,
                 "roofline": {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"] if dom else None,
                              "peak": peak_burst, "unit": "TFLOP/s",
                              "frac": (kernels[dom]["achieved_tflops"] / peak_burst) if dom else None,
@@ -470,9 +505,10 @@ def main():
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU leg (torch eager autograd, 1 iteration)")
-    ap.add_argument("--slots", type=int, default=1,
+    ap.add_argument("--slots", type=int, default=0,
                     help="problem slots (pb_set_slots): each step solves this many independent problems as ONE tangent batch "
-                         "(throughput mode; default 1 = one problem per step, the reference's granularity)")
+                         "(0 = default: min(5, 64 // pca_rank); 1 = one problem per step, the reference's granularity, which the "
+                         "default run also reports as `slots1`)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu (the reference arm) or cuda (torch eager autograd on this box's GPU, SURVEY s.8d-ii)")
     ap.add_argument("--shard", default="problem", choices=["problem", "tangent"],

@@ -69,7 +69,7 @@ class PbAttnLin(C.Structure):
                 ("ldr", C.c_long), ("sRb", C.c_long), ("round_tf32", C.c_int),
                 ("C2", C.c_void_p), ("ldc2", C.c_long), ("sC2h", C.c_long), ("sC2b", C.c_long),
                 ("D2", C.c_void_p), ("ldd2", C.c_long), ("sD2b", C.c_long), ("p16", C.c_int), ("p_scale", C.c_float),
-                ("s16", C.c_int)]
+                ("s16", C.c_int), ("k_slot", C.c_int), ("p_stride", C.c_long)]
 
 
 _lib = None

@@ -62,6 +62,9 @@ struct alignas(64) Params {
   CUtensorMap mapAt[2], mapBt[2];      // the compact tail k-block (8 or 16 floats), if any
   CUtensorMap mapC, mapC2, mapP;
   int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2];
+  // problem slots: tangent b belongs to problem b / k_slot; a segment operand with a_slot / b_slot set is PRIMAL and its batch
+  // coordinate is the problem index, as are the batch coordinates of the P and C1 maps (ps_mul = 1) and the O pointer
+  int k_slot, a_slot[2], b_slot[2], ps_mul; long o_stride;
   uint32_t a_bytes, b_bytes, c_bytes, p_bytes;   // bytes per barrier phase
   int nseg, d, dpad;                   // accumulator width dpad = d rounded up to 16
   int kfull, tail;                     // S contraction: kfull 128-byte k-blocks + a tail of `tail` 32-byte k-steps (0, 1, 2)
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
   const int r0 = blockIdx.x * TM;
   // tangents fastest: the nb CTAs that share one head's P rows run back to back, so P comes from L2 for all but the first
   const int bat_b = blockIdx.y % p.nb, bat_h = blockIdx.y / p.nb;
+  const int bat_s = bat_b / p.k_slot;          // problem slot of this tangent (0 with one problem)
   const int nj = (p.Nc + TNc - 1) / TNc;
 
   if (threadIdx.x == 0) {
@@ -186,16 +190,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       mbar_arrive_expect_tx(a_full, p.a_bytes);
       for (int s = 0; s < nseg; ++s) {
         uint8_t* dst = sA + s * a_seg_bytes;
+        const int ab = p.a_slot[s] ? bat_s : bat_b * p.a_bmul[s];
         for (int kb = 0; kb < kfull; ++kb)
-          tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BKe, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
-        if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BKe, r0, bat_h * p.a_hmul[s], bat_b * p.a_bmul[s]);
+          tma_load_4d(dst + kb * TM * 128, &p.mapA[s], a_full, kb * BKe, r0, bat_h * p.a_hmul[s], ab);
+        if (tail) tma_load_4d(dst + a_tail_off, &p.mapAt[s], a_full, kfull * BKe, r0, bat_h * p.a_hmul[s], ab);
       }
       // Every ring is refilled as soon as ITS consumer releases a stage: the S-operand rings are released by the score
       // MMAs, the P/T and C1 rings two steps later by the accumulate MMAs, so one thread polls the three "empty" barriers
       // instead of blocking on them in a fixed order (a blocked P wait would hold back the B tiles the score warp needs).
       Ring rp{0, 0}, rb{0, 0}, rc{0, 0};
       int mp = 0, mb = 0, mc = 0;
-      const int bh[2] = {bat_h * p.b_hmul[0], bat_h * p.b_hmul[1]}, bb[2] = {bat_b * p.b_bmul[0], bat_b * p.b_bmul[1]};
+      const int bh[2] = {bat_h * p.b_hmul[0], bat_h * p.b_hmul[1]};
+      const int bb[2] = {p.b_slot[0] ? bat_s : bat_b * p.b_bmul[0], p.b_slot[1] ? bat_s : bat_b * p.b_bmul[1]};
+      const int ps = bat_s * p.ps_mul;
       long long t0 = clock64();
       unsigned spins = 0;
       while (mp < nj || mb < nj || mc < nj) {
@@ -217,12 +224,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         }
         if (mp < nj && mbar_try_wait(&pt_empty[rp.idx], rp.ph ^ 1)) {
           mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
-          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TNc, r0, bat_h, 0);
+          tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TNc, r0, bat_h, ps);
           rp.next(NPT); ++mp; any = true;
         }
         if (mc < nj && mbar_try_wait(&c_empty[rc.idx], rc.ph ^ 1)) {
           mbar_arrive_expect_tx(&c_full[rc.idx], p.c_bytes);
-          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TNc, 0, bat_h, 0);
+          tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TNc, 0, bat_h, ps);
           rc.next(NC1); ++mc; any = true;
         }
         if (any) { spins = 0; }
@@ -467,7 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
         doff = (long)bat_b * p.sDb + rr * p.ldd + bat_h * p.d;
         dptr = p.D + doff;
         if (p.R) rptr = p.R + (long)bat_b * p.sRb + rr * p.ldr + bat_h * p.d;
-        if (p.want_rsum && p.O) optr = p.O + rr * p.ldo + bat_h * p.d;
+        if (p.want_rsum && p.O) optr = p.O + bat_s * p.o_stride + rr * p.ldo + bat_h * p.d;
         alpha = p.alpha2 * p.inv_pscale; tm = tm_acc;
       } else {
         doff = (long)bat_b * p.sD2b + rr * p.ldd2 + bat_h * p.d;
@@ -554,6 +561,12 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.D = a.D; p.ldd = a.ldd; p.sDb = a.sDb; p.R = a.R; p.ldr = a.ldr; p.sRb = a.sRb; p.round_tf32 = a.round_tf32;
   p.has_c2 = a.C2 ? 1 : 0; p.sep_acc2 = a.D2 ? 1 : 0; p.D2 = a.D2; p.ldd2 = a.ldd2; p.sD2b = a.sD2b;
   p.inv_pscale = p16 ? 1.f / a.p_scale : 1.f;
+  // problem slots: nslots problems of k_slot tangents each; primal operands are strided by p_stride bytes per problem
+  const int k_slot = (a.k_slot > 0 && a.k_slot < a.nb) ? a.k_slot : a.nb;
+  const int nslots = a.nb / k_slot;
+  if (a.nb % k_slot) return "attn_lin: the tangent batch must be a whole number of problem slots";
+  if (nslots > 1 && (a.p_stride <= 0 || a.p_stride % 16)) return "attn_lin: p_stride must be a positive multiple of 16 bytes";
+  p.k_slot = k_slot; p.ps_mul = nslots > 1 ? 1 : 0; p.o_stride = nslots > 1 ? a.p_stride / 4 : 0;
   const int dq = s16 ? 8 : 4;                   // elements per 16 bytes of D / D2
   if ((a.ldd % dq) || (a.R && a.ldr % 4) || (a.O && a.ldo % 4) || (a.ldp % cq) || (a.ldc % cq) || (a.D2 && a.ldd2 % dq) ||
       ((reinterpret_cast<uintptr_t>(a.D) | reinterpret_cast<uintptr_t>(a.R) | reinterpret_cast<uintptr_t>(a.O) |
@@ -567,19 +580,23 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.c_tile_bytes = p.dpad * 128;
   uint32_t abytes = 0, bbytes = 0;
   for (int s = 0; s < a.nseg; ++s) {
-    const PbGemmSeg& sg = a.seg[s];
+    PbGemmSeg sg = a.seg[s];
     uint32_t ab = 0, bb = 0;
+    // a primal (batch-broadcast) operand with several problem slots: its batch dimension is the problem index
+    int nbA = a.nb, nbB = a.nb;
+    if (nslots > 1 && sg.sAb == 0) { sg.sAb = a.p_stride / ses; nbA = nslots; p.a_slot[s] = 1; }
+    if (nslots > 1 && sg.sBb == 0) { sg.sBb = a.p_stride / ses; nbB = nslots; p.b_slot[s] = 1; }
     if (p.kfull) {
-      if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, p.bk, TM, 128,
+      if (const char* e = pbgemm::encode_plainx(&p.mapA[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, nbA, p.bk, TM, 128,
                                                 &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, p.bk, TNh, 128,
+      if (const char* e = pbgemm::encode_plainx(&p.mapB[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, p.bk, TNh, 128,
                                                 &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab * p.kfull; bbytes += bb * p.kfull;
     }
     if (p.tail) {
-      if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, a.nb, tail_el, TM,
+      if (const char* e = pbgemm::encode_plainx(&p.mapAt[s], sg.A, s16, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, nbA, tail_el, TM,
                                                 tail_span, &p.a_hmul[s], &p.a_bmul[s], &ab)) return e;
-      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, a.nb, tail_el, TNh,
+      if (const char* e = pbgemm::encode_plainx(&p.mapBt[s], sg.B, s16, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, tail_el, TNh,
                                                 tail_span, &p.b_hmul[s], &p.b_bmul[s], &bb)) return e;
       abytes += ab; bbytes += bb;
     }
@@ -587,8 +604,8 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   p.a_bytes = abytes; p.b_bytes = bbytes;
   {
     // C1: [nh][d][ldc], K-major over the score columns; box = [one step of columns = 128 bytes] x [d rows]
-    uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), 1};
-    uint64_t stb[3] = {uint64_t(a.ldc) * ces, uint64_t(a.sCh) * ces, uint64_t(a.sCh) * ces * a.nh};
+    uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), uint64_t(nslots)};
+    uint64_t stb[3] = {uint64_t(a.ldc) * ces, uint64_t(a.sCh) * ces, nslots > 1 ? uint64_t(a.p_stride) : uint64_t(a.sCh) * ces * a.nh};
     uint32_t box[4] = {uint32_t(TNh), uint32_t(a.d), 1, 1};
     if (const char* e = pbgemm::encode4x(&p.mapC, a.C1, p16, dims, stb, box, 128)) return e;
     p.c_bytes = uint32_t(a.d) * 128;
@@ -604,7 +621,8 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   {
     // Pm: [nh][Mr][ldp]; box = [one step of columns = 128 bytes] x [128 rows]
     int hm, bm; uint32_t pb;
-    if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, p16, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, 0, 1, TNh, TM, 128, &hm, &bm, &pb)) return e;
+    if (const char* e = pbgemm::encode_plainx(&p.mapP, a.Pm, p16, a.Mr, a.Nc, a.ldp, a.sPh, a.nh, nslots > 1 ? a.p_stride / ces : 0, nslots,
+                                              TNh, TM, 128, &hm, &bm, &pb)) return e;
     p.p_bytes = pb;
   }
   // ring depths from the shared-memory budget: B and C2 rings of 3 stages, C1 ring of 5 (4 when tight), every remaining

@@ -142,6 +142,10 @@ struct pb_handle {
     return reinterpret_cast<float*>(work + off);
   }
   bool is16(int v) const { return vals[v].h16; }
+  // problem slots handled INSIDE a kernel (all-fp16 plan): images per problem and the primal stride between problems
+  // (the fp32 plan runs those ops once per slot on one problem's images: k_slot = 0 there)
+  int ks(int nb) const { return slots > 1 && t16 ? nb / slots : 0; }
+  long pstride_f() const { return slots > 1 && t16 ? (long)(cache_stride / 4) : 0; }
   // io flags of a tangent-path kernel reading the tangent of val `vin` and writing the tangent of val `vout` (pb_kernels.h)
   int io(int vin, int vout) const { return (vin >= 0 && is16(vin) ? PB_IN_F16 : 0) | (vout >= 0 && is16(vout) ? PB_OUT_F16 : rnd); }
   float* CP(size_t off) const { return reinterpret_cast<float*>(cache + slot * cache_stride + off); }
@@ -507,7 +511,8 @@ const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
   return probed(h, PB_PROBE_GEMM, flops, st, [&] { return pbk_gemm(&g, st); });
 }
 // fused attention linearisation: S (nseg products over the head dim) + T . C1 per (tangent, head)
-const char* attn_lin_call(pb_handle* h, const PbAttnLin& a, pb_stream st) {
+const char* attn_lin_call(pb_handle* h, PbAttnLin& a, pb_stream st) {
+  if (h->slots > 1 && h->t16) { a.k_slot = a.nb / h->slots; a.p_stride = (long)h->cache_stride; }   // every problem in one launch
   const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1 + (a.C2 ? 1 : 0)) * a.nb * a.nh;
   if (h->profiling) {
     char b[160];
@@ -741,7 +746,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     // the value operand of the score product as the fused kernel reads it: halves in the all-fp16 plan (X16: [N][3C] / [Nk][2C])
     const float* Vs = t16 ? el(h->CP(o.X16_off), o.cross ? C : 2 * C, 2) : V;
     float* gx = h->T(o.x); float* delta = h->WP(h->w_delta);
-    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, t16 ? PB_IN_F16 : 0, st));   // delta = rowsum(Obar o O)
+    CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, t16 ? PB_IN_F16 : 0, h->ks(nb), h->pstride_f(), st));   // delta = rowsum(Obar o O)
     const long ldx = o.cross ? C : 3 * C;
     PbAttnLin a{};
     // Qbar = scale * [P o (Obar V^T - delta_row)] K   (cross-attention: the only cotangent -- text keys / values are constants)
@@ -806,7 +811,7 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
   float* gSt = h->WP(h->w_s2); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
   const long sSt = (long)hd * Nk * ldq;
-  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, 0, st));
+  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, 0, 0, 0, st));
   {                                                                                // dP^T = V gO^T
     PbGemm g = plain_gemm(V, ldkv, Nk, gO, C, N, d, gSt, ldq);
     g.seg[0].sAh = d; g.seg[0].sBb = (long)N * C; g.seg[0].sBh = d;
@@ -911,7 +916,12 @@ int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h
 
 // ops that read primal quantities (normalisation statistics, activation arguments, attention probabilities): with several
 // problem slots they run once per slot; everything else (weight GEMMs, data movement) takes all slots in one launch
-bool per_slot_op(int kind) { return kind == OP_GN || kind == OP_LN || kind == OP_GEGLU || kind == OP_ATTN; }
+// ... except in the all-fp16 plan, whose kernels index the primal tensors per image (b / k_slot): there only the
+// materialised attention path (few tokens) still runs slot by slot
+bool per_slot_op(const pb_handle* h, const Op& o) {
+  if (h->t16) return o.kind == OP_ATTN && !(use_fused(h, o) || use_fused_cross(h, o));
+  return o.kind == OP_GN || o.kind == OP_LN || o.kind == OP_GEGLU || o.kind == OP_ATTN;
+}
 
 int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_stream st) {
   {
@@ -928,13 +938,13 @@ int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_strea
       case OP_GN: {
         const Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->io(o.x, o.y), h->WP(h->w_gn), st));
+                      o.silu, h->T(o.x), nb, 0, h->T(o.y), 0.f, h->io(o.x, o.y), h->WP(h->w_gn), h->ks(nb), h->pstride_f(), st));
         break;
       }
       case OP_LN: {
         const Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.x), nb, 0, h->T(o.y), 0.f,
-                      h->io(o.x, o.y), st));
+                      h->io(o.x, o.y), h->ks(nb), h->pstride_f(), st));
         break;
       }
       case OP_GEMM:
@@ -954,7 +964,8 @@ int jvp_op(pb_handle* h, const Op& o, const float* V, int nb, float* U, pb_strea
         CK(pbk_upsample2x(h->T(o.x), nb, o.H, o.W, h->vals[o.x].C, h->T(o.y), h->io(o.x, o.y), st));
         break;
       case OP_GEGLU:
-        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->io(o.x, o.y), st));
+        CK(pbk_geglu_jvp(h->P(o.x), h->vals[o.x].rows, h->T(o.x), nb, h->vals[o.y].C, h->T(o.y), h->io(o.x, o.y), h->ks(nb),
+                         h->pstride_f(), st));
         break;
       case OP_ATTN:
         if (int e = run_attn_jvp(h, o, nb, st)) return e;
@@ -976,7 +987,7 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
   h->rnd = h->rnd_t; h->pass_vjp = false; h->k_slot = nb / h->slots;
   SlotGuard guard{h};
   for (const Op& o : h->ops) {
-    if (h->slots > 1 && per_slot_op(o.kind)) {
+    if (h->slots > 1 && per_slot_op(h, o)) {
       for (int p = 0; p < h->slots; ++p) {
         h->slot = p;
         if (int e = jvp_op(h, o, V, h->k_slot, U, st)) return e;
@@ -1001,7 +1012,8 @@ int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_st
         break;
       case OP_GEGLU:
         if (h->vals[o.x].ginit) return fail(h, PB_ESTATE, "internal: GEGLU input has several consumers");
-        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->io(o.y, o.x), st));
+        CK(pbk_geglu_vjp(h->P(o.x), h->vals[o.x].rows, h->T(o.y), nb, h->vals[o.y].C, h->T(o.x), h->io(o.y, o.x), h->ks(nb),
+                         h->pstride_f(), st));
         h->vals[o.x].ginit = true;
         break;
       case OP_UPSAMPLE: {
@@ -1030,14 +1042,14 @@ int vjp_op(pb_handle* h, const Op& o, const float* U, int nb, float* Wout, pb_st
       case OP_LN: {
         Val& v = h->vals[o.x];
         CK(pbk_ln_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), v.rows, v.C, h->T(o.y), nb, 1, h->T(o.x),
-                      v.ginit ? 1.f : 0.f, h->io(o.y, o.x), st));
+                      v.ginit ? 1.f : 0.f, h->io(o.y, o.x), h->ks(nb), h->pstride_f(), st));
         v.ginit = true;
         break;
       }
       case OP_GN: {
         Val& v = h->vals[o.x];
         CK(pbk_gn_lin(h->P(o.x), h->CP(o.mean_off), h->CP(o.rstd_off), h->Wf(o.gamma), h->Wf(o.beta), (int)v.rows, v.C, o.groups,
-                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, h->io(o.y, o.x), h->WP(h->w_gn), st));
+                      o.silu, h->T(o.y), nb, 1, h->T(o.x), v.ginit ? 1.f : 0.f, h->io(o.y, o.x), h->WP(h->w_gn), h->ks(nb), h->pstride_f(), st));
         v.ginit = true;
         break;
       }
@@ -1067,7 +1079,7 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
   for (size_t i = h->ops.size(); i-- > 0;) {
     const Op& o = h->ops[i];
     if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
-    if (h->slots > 1 && per_slot_op(o.kind)) {
+    if (h->slots > 1 && per_slot_op(h, o)) {
       const bool had = h->vals[o.x].ginit;               // every slot sees the bookkeeping state the op started from
       for (int p = 0; p < h->slots; ++p) {
         h->slot = p;

@@ -730,28 +730,19 @@ __global__ void geglu_fwd_k(const float* __restrict__ h, long rows, int F, float
     *reinterpret_cast<float4*>(y + r * F + c) = maybe_round4(o, rnd);
   }
 }
-// IN16: the tangent dh holds halves (written by an fp16-output GEMM); rnd 2: dy is stored as halves
+// IN16: the tangent dh / gy holds halves; rnd 2: the result is stored as halves.  Problem slots: tangent image r / rows_p
+// belongs to problem (r / rows_p) / k_slot, whose primal tensor starts p_stride floats after the previous problem's.
 template <bool IN16>
 __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ dh, long rows, int F,
-                            float* __restrict__ dy, int rnd) {
+                            float* __restrict__ dy, int rnd, int k_slot, long p_stride) {
   const int F4 = F / 4;
   const long total = rows * F4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / F4; const int c = int(i % F4) * 4;
-    const long rp = r % rows_p;
-    const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
-    const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
-    float4 da, dg;
-    if constexpr (IN16) {
-      const __half* dhh = reinterpret_cast<const __half*>(dh);
-      const uint2 ua = *reinterpret_cast<const uint2*>(dhh + r * 2 * F + c), ug = *reinterpret_cast<const uint2*>(dhh + r * 2 * F + F + c);
-      const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&ua.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&ua.y));
-      const float2 g0 = __half22float2(*reinterpret_cast<const __half2*>(&ug.x)), g1 = __half22float2(*reinterpret_cast<const __half2*>(&ug.y));
-      da = make_float4(a0.x, a0.y, a1.x, a1.y); dg = make_float4(g0.x, g0.y, g1.x, g1.y);
-    } else {
-      da = *reinterpret_cast<const float4*>(dh + r * 2 * F + c);
-      dg = *reinterpret_cast<const float4*>(dh + r * 2 * F + F + c);
-    }
+    const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
+    const float4 a = *reinterpret_cast<const float4*>(hr + c);
+    const float4 g = *reinterpret_cast<const float4*>(hr + F + c);
+    const float4 da = load_in4(dh, r * 2 * F + c, IN16), dg = load_in4(dh, r * 2 * F + F + c, IN16);
     float4 o = make_float4(da.x * gelu_f(g.x) + a.x * gelu_d(g.x) * dg.x, da.y * gelu_f(g.y) + a.y * gelu_d(g.y) * dg.y,
                            da.z * gelu_f(g.z) + a.z * gelu_d(g.z) * dg.z, da.w * gelu_f(g.w) + a.w * gelu_d(g.w) * dg.w);
     store_out4(dy, r * F + c, o, rnd);
@@ -759,14 +750,14 @@ __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const flo
 }
 template <bool IN16>
 __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ gy, long rows, int F,
-                            float* __restrict__ gh, int rnd) {
+                            float* __restrict__ gh, int rnd, int k_slot, long p_stride) {
   const int F4 = F / 4;
   const long total = rows * F4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / F4; const int c = int(i % F4) * 4;
-    const long rp = r % rows_p;
-    const float4 a = *reinterpret_cast<const float4*>(hp + rp * 2 * F + c);
-    const float4 g = *reinterpret_cast<const float4*>(hp + rp * 2 * F + F + c);
+    const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
+    const float4 a = *reinterpret_cast<const float4*>(hr + c);
+    const float4 g = *reinterpret_cast<const float4*>(hr + F + c);
     const float4 y = load_in4(gy, r * F + c, IN16);
     float4 ga = make_float4(y.x * gelu_f(g.x), y.y * gelu_f(g.y), y.z * gelu_f(g.z), y.w * gelu_f(g.w));
     float4 gg = make_float4(y.x * a.x * gelu_d(g.x), y.y * a.y * gelu_d(g.y), y.z * a.z * gelu_d(g.z),
@@ -878,7 +869,7 @@ __global__ void softmax_lin_k(const float* __restrict__ P, long rows_p, float* _
 
 // thread per (tangent, row, head): heads are contiguous along a row, so a warp reads whole rows with 128-bit loads
 __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float* __restrict__ o, long ldo, int nb,
-                             int N, int H, int d, float* __restrict__ delta, bool go16) {
+                             int N, int H, int d, float* __restrict__ delta, bool go16, int k_slot, long p_stride) {
   const long total = (long)nb * N * H;
   const int d4 = d / 4;
   for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < total; w += (long)gridDim.x * blockDim.x) {
@@ -887,7 +878,7 @@ __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float
     const int i = int(t % N); t /= N;
     const int b = int(t);
     const long goff = ((long)b * N + i) * ldg + h * d;
-    const float4* oo = reinterpret_cast<const float4*>(o + (long)i * ldo + h * d);
+    const float4* oo = reinterpret_cast<const float4*>(o + (long)(b / k_slot) * p_stride + (long)i * ldo + h * d);
     float s = 0.f;
     for (int c = 0; c < d4; ++c) {
       const float4 a = load_in4(go, goff + 4 * c, go16), q = oo[c];
@@ -1317,11 +1308,13 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 }
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
-               float* tmp, pb_stream st) {
+               float* tmp, int k_slot, long p_stride, pb_stream st) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   if (in16(round_tf32)) {
     if (!out16(round_tf32)) return "groupnorm: fp16 input needs fp16 output";
-    return pb16::gn_lin(xp, mean, rstd, gamma, beta, HW, C, G, silu, HP(t), nb, mode, HP(out), acc, tmp, nb, 0, S(st));
+    return pb16::gn_lin(xp, mean, rstd, gamma, beta, HW, C, G, silu, HP(t), nb, mode, HP(out), acc, tmp, k_slot, p_stride, S(st));
   }
+  if (k_slot != nb) return "groupnorm: problem slots need the fp16-tangent kernels";
   if (round_tf32 == 2 && acc != 0.f) return "groupnorm: fp16 output cannot accumulate";
   if (C % 4 || C % G) return "groupnorm: C must be a multiple of 4 and of the group count";
   {
@@ -1377,11 +1370,13 @@ PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float
   return last_err();
 }
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
-               const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st) {
+               const float* t, int nb, int mode, float* out, float acc, int round_tf32, int k_slot, long p_stride, pb_stream st) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   if (in16(round_tf32)) {
     if (!out16(round_tf32)) return "layernorm: fp16 input needs fp16 output";
-    return pb16::ln_lin(xp, mean, rstd, gamma, rows_p, C, HP(t), nb, mode, HP(out), acc, nb, 0, S(st));
+    return pb16::ln_lin(xp, mean, rstd, gamma, rows_p, C, HP(t), nb, mode, HP(out), acc, k_slot, p_stride, S(st));
   }
+  if (k_slot != nb) return "layernorm: problem slots need the fp16-tangent kernels";
   CHECK_ALIGN4(C, "layernorm: C");
   if (round_tf32 == 2 && acc != 0.f) return "layernorm: fp16 output cannot accumulate";
   const long rows = rows_p * nb;
@@ -1397,20 +1392,23 @@ PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb
   return last_err();
 }
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
-                  pb_stream st) {
+                  int k_slot, long p_stride, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
-  // round_tf32 bit 2 (value 4): the tangent input dh holds halves
-  if (in16(round_tf32)) geglu_jvp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & 3);
-  else geglu_jvp_k<false><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32);
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  const unsigned grid = grid_for(rows * (F / 4), 256, 16);
+  if (in16(round_tf32)) geglu_jvp_k<true><<<grid, 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & PB_RND_MASK, k_slot, p_stride);
+  else geglu_jvp_k<false><<<grid, 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32, k_slot, p_stride);
   return last_err();
 }
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
-                  pb_stream st) {
+                  int k_slot, long p_stride, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
-  if (in16(round_tf32)) geglu_vjp_k<true><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32 & PB_RND_MASK);
-  else geglu_vjp_k<false><<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32);
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  const unsigned grid = grid_for(rows * (F / 4), 256, 16);
+  if (in16(round_tf32)) geglu_vjp_k<true><<<grid, 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32 & PB_RND_MASK, k_slot, p_stride);
+  else geglu_vjp_k<false><<<grid, 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32, k_slot, p_stride);
   return last_err();
 }
 
@@ -1429,11 +1427,12 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
   return last_err();
 }
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
-                   int io, pb_stream st) {
+                   int io, int k_slot, long p_stride, pb_stream st) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   const long total = (long)nb * H * N;
   if (d % 4 || ldg % 4 || ldo % 4 || ((reinterpret_cast<uintptr_t>(go) | reinterpret_cast<uintptr_t>(o)) & 15))
     return "attn_delta: head dim and leading dimensions must be multiples of 4 with 16-byte aligned bases";
-  attn_delta_k<<<grid_for(total, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta, in16(io));
+  attn_delta_k<<<grid_for(total, 256, 8), 256, 0, S(st)>>>(go, ldg, o, ldo, nb, N, H, d, delta, in16(io), k_slot, p_stride);
   return last_err();
 }
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,

@@ -114,15 +114,28 @@ __global__ void __launch_bounds__(512) gn16_apply_k(const float* __restrict__ xp
                                                     const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
                                                     long p_stride, const float* __restrict__ part, int chunks,
                                                     __half* __restrict__ out, float acc) {
-  extern __shared__ float s_m[];                                   // [G][2] group means of this image
+  extern __shared__ float s_m[];                                   // [G][2] group means of this image, then [rows][2 G] scratch
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
   const int cpg = C / G;
-  for (int i = tid; i < 2 * G; i += blockDim.x) {
-    double s = 0.0;
-    const float* q = part + ((long)b * chunks * G + (i >> 1)) * 2 + (i & 1);
-    for (int k = 0; k < chunks; ++k) s += (double)q[(long)k * G * 2];
-    s_m[i] = (float)(s / ((double)HW * cpg));
+  {
+    // group means of this image from the per-chunk partials: all threads load (chunks x 2 G values, independent loads in
+    // flight together -- a per-value serial loop over the chunks costs a chain of L2 latencies), fixed-order combination
+    const int nv = 2 * G, rows = max(1, (int)blockDim.x / nv);
+    float* sc = s_m + nv;                                          // [rows][nv]
+    const int i = tid % nv, r = tid / nv;
+    if (r < rows) {
+      float s = 0.f;
+      const float* q = part + (long)b * chunks * nv + i;
+      for (int k = r; k < chunks; k += rows) s += q[(long)k * nv];
+      sc[r * nv + i] = s;
+    }
+    __syncthreads();
+    if (tid < nv) {
+      double s = 0.0;
+      for (int rr = 0; rr < rows; ++rr) s += (double)sc[rr * nv + tid];
+      s_m[tid] = (float)(s / ((double)HW * cpg));
+    }
   }
   __syncthreads();
   const int CV = Cblk / 4;
@@ -372,7 +385,8 @@ const char* gn_lin(const float* xp, const float* mean, const float* rstd, const 
   const GnGeom16 g = gn_geom16(HW, C, G, nb);
   if (!g.nz) return "groupnorm: channel / group geometry not supported by the fp16-tangent kernel";
   dim3 grid(g.chunks, nb, g.nz);
-  const size_t sh1 = (size_t)g.lanes * g.Cblk * sizeof(float2), sh2 = (size_t)G * 2 * sizeof(float);
+  const size_t sh1 = (size_t)g.lanes * g.Cblk * sizeof(float2);
+  const size_t sh2 = (size_t)G * 2 * sizeof(float) * (1 + std::max(1, g.threads / (2 * G)));
   if (mode == 0) {
     gn16_sums_k<0><<<grid, g.threads, sh1, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride, tmp);
     gn16_apply_k<0><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride,

@@ -87,23 +87,26 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
 //   mode 0 (JVP): out = act'(.) * gamma * rstd * (t - mean_g(t) - xhat * mean_g(xhat * t))
 //   mode 1 (VJP): g = t * act'(.) * gamma ; out = rstd * (g - mean_g(g) - xhat * mean_g(xhat * g))
 // out = result + acc * out.  tmp: pbk_gn_tmp_floats(HW, C, G, nb) floats of scratch.
+// Problem slots (k_slot, p_stride): image b of the tangent batch belongs to problem b / k_slot, whose primal tensors (xp,
+// mean, rstd) start p_stride FLOATS after the previous problem's (one primal cache per problem, uniform stride).
+// k_slot <= 0 or >= nb: one problem (p_stride ignored).
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW,
                int C, int G, int silu, const float* t, int nb, int mode, float* out, float acc, int round_tf32,
-               float* tmp, pb_stream st);
+               float* tmp, int k_slot, long p_stride, pb_stream st);
 
 // ---- LayerNorm over the channel axis ----
 PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float* beta, float eps, float* y,
                float* mean, float* rstd, int round_tf32, pb_stream st);
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
-               const float* t, int nb, int mode, float* out, float acc, int round_tf32, pb_stream st);
+               const float* t, int nb, int mode, float* out, float acc, int round_tf32, int k_slot, long p_stride, pb_stream st);
 
 // ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
 PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st);
 // round_tf32 | PB_IN_F16: the tangent input dh / gy holds halves
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
-                  pb_stream st);
+                  int k_slot, long p_stride, pb_stream st);
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,
-                  pb_stream st);
+                  int k_slot, long p_stride, pb_stream st);
 
 // ---- softmax pieces (attention probabilities are materialised per (head, query) row) ----
 PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int round_tf32, pb_stream st);
@@ -113,7 +116,7 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
 // delta[b][h][i] = sum_c go[b][i][h*d + c] * o[i][h*d + c]
 // io & PB_IN_F16: go holds halves (o is primal fp32, delta fp32)
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
-                   int io, pb_stream st);
+                   int io, int k_slot, long p_stride, pb_stream st);          // o of problem b / k_slot: o + (b / k_slot) * p_stride
 // dP[b][h][r][c] <- scale * P[h][r][c] * (dP[b][h][r][c] - (col_mode ? delta[b][h][c] : delta[b][h][r]))
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
                 int col_mode, int round_tf32, pb_stream st);
@@ -146,6 +149,9 @@ struct PbAttnLin {
   // s16 (needs p16): the S operands seg[].A / seg[].B hold halves as well (kind::f16 score products; head dim % 8 == 0) and D / D2
   // are written as halves (ldd, sDb, ldd2, sD2b in elements); O, delta stay fp32; no residual R
   int s16;
+  // problem slots: tangent b belongs to problem b / k_slot; every PRIMAL operand (Pm, C1, O and the segment operands whose batch
+  // stride is 0) of problem s starts p_stride BYTES after problem s - 1's.  k_slot <= 0: one problem.
+  int k_slot; long p_stride;
 };
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);

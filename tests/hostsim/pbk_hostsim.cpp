@@ -251,10 +251,14 @@ PBK pbk_gn_apply(const float* x, const float* mean, const float* rstd, const flo
   return nullptr;
 }
 PBK pbk_gn_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, const float* beta, int HW, int C, int G,
-               int silu, const float* t, int nb, int mode, float* out, float acc, int rnd, float*, pb_stream) {
+               int silu, const float* t, int nb, int mode, float* out, float acc, int rnd, float*, int k_slot, long p_stride,
+               pb_stream) {
   const int cpg = C / G;
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  const float *xp0 = xp, *mean0 = mean, *rstd0 = rstd;
   for (long b = 0; b < nb; ++b)
     for (int g = 0; g < G; ++g) {
+      xp = xp0 + (b / k_slot) * p_stride; mean = mean0 + (b / k_slot) * p_stride; rstd = rstd0 + (b / k_slot) * p_stride;
       double s1 = 0, s2 = 0;
       for (int p = 0; p < HW; ++p)
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -291,9 +295,12 @@ PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float
   return nullptr;
 }
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C, const float* t,
-               int nb, int mode, float* out, float acc, int rnd, pb_stream) {
+               int nb, int mode, float* out, float acc, int rnd, int k_slot, long p_stride, pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  const float *xp0 = xp, *mean0 = mean, *rstd0 = rstd;
   for (long r = 0; r < rows_p * nb; ++r) {
-    const long rp = r % rows_p;
+    const long rp = r % rows_p, ps = ((r / rows_p) / k_slot) * p_stride;
+    xp = xp0 + ps; mean = mean0 + ps; rstd = rstd0 + ps;
     double s1 = 0, s2 = 0;
     for (int c = 0; c < C; ++c) {
       const float xh = (xp[rp * C + c] - mean[rp]) * rstd[rp];
@@ -318,9 +325,12 @@ PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int rnd, pb_stream
     for (int c = 0; c < F; ++c) y[r * F + c] = mr(h[r * 2 * F + c] * gelu_f(h[r * 2 * F + F + c]), rnd);
   return nullptr;
 }
-PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int rnd, pb_stream) {
+PBK pbk_geglu_jvp(const float* hp0, long rows_p, const float* dh, int nb, int F, float* dy, int rnd, int k_slot, long p_stride,
+                  pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   for (long r = 0; r < rows_p * nb; ++r) {
     const long rp = r % rows_p;
+    const float* hp = hp0 + ((r / rows_p) / k_slot) * p_stride;
     for (int c = 0; c < F; ++c) {
       const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c];
       sto(dy, rnd, r * F + c, ldx(dh, in16(rnd), r * 2 * F + c) * gelu_f(g) + a * gelu_d(g) * ldx(dh, in16(rnd), r * 2 * F + F + c));
@@ -328,9 +338,12 @@ PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, 
   }
   return nullptr;
 }
-PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int rnd, pb_stream) {
+PBK pbk_geglu_vjp(const float* hp0, long rows_p, const float* gy, int nb, int F, float* gh, int rnd, int k_slot, long p_stride,
+                  pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   for (long r = 0; r < rows_p * nb; ++r) {
     const long rp = r % rows_p;
+    const float* hp = hp0 + ((r / rows_p) / k_slot) * p_stride;
     for (int c = 0; c < F; ++c) {
       const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c], y = ldx(gy, in16(rnd), r * F + c);
       sto(gh, rnd, r * 2 * F + c, y * gelu_f(g));
@@ -361,14 +374,18 @@ PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, lo
   }
   return nullptr;
 }
-PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta, int io, pb_stream) {
+PBK pbk_attn_delta(const float* go, long ldg, const float* o0, long ldo, int nb, int N, int H, int d, float* delta, int io, int k_slot,
+                   long p_stride, pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   for (long b = 0; b < nb; ++b)
-    for (int h = 0; h < H; ++h)
+    for (int h = 0; h < H; ++h) {
+      const float* o = o0 + (b / k_slot) * p_stride;
       for (int i = 0; i < N; ++i) {
         double s = 0;
         for (int c = 0; c < d; ++c) s += (double)ldx(go, in16(io), (b * N + i) * ldg + h * d + c) * o[(long)i * ldo + h * d + c];
         delta[(b * H + h) * N + i] = (float)s;
       }
+    }
   return nullptr;
 }
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
@@ -394,8 +411,15 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
   if (s16 && !p16) return "attn_lin: fp16 S operands need the fp16 probability path";
   const float inv_ps = p16 ? 1.f / a.p_scale : 1.f;
   auto opnd = [&](float v) { return p16 ? v : trunc_tf32(v); };           // operand of an accumulating product
+  const int k_slot = (a.k_slot > 0 && a.k_slot < a.nb) ? a.k_slot : a.nb;
+  const bool slots = a.nb / k_slot > 1;
   for (long b = 0; b < a.nb; ++b)
     for (long h = 0; h < a.nh; ++h) {
+      // primal operands of this tangent's problem (byte stride p_stride per problem)
+      const long sb = slots ? (b / k_slot) * a.p_stride : 0;
+      const char* Pm = reinterpret_cast<const char*>(a.Pm) + sb;
+      const char* C1p = reinterpret_cast<const char*>(a.C1) + sb;
+      const float* Op = a.O ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(a.O) + sb) : nullptr;
 #pragma omp parallel for schedule(static)
       for (int r = 0; r < a.Mr; ++r) {
         std::vector<float> T(a.Nc);
@@ -405,14 +429,16 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
           for (int sg = 0; sg < a.nseg; ++sg) {
             const long a0 = b * a.seg[sg].sAb + h * a.seg[sg].sAh + (long)r * a.seg[sg].lda;
             const long b0 = b * a.seg[sg].sBb + h * a.seg[sg].sBh + (long)c * a.seg[sg].ldb;
+            const void* Ap = a.seg[sg].sAb == 0 ? static_cast<const void*>(static_cast<const char*>(a.seg[sg].A) + sb) : a.seg[sg].A;
+            const void* Bp = a.seg[sg].sBb == 0 ? static_cast<const void*>(static_cast<const char*>(a.seg[sg].B) + sb) : a.seg[sg].B;
             for (int k = 0; k < a.d; ++k)
-              s += s16 ? ldx(a.seg[sg].A, 1, a0 + k) * ldx(a.seg[sg].B, 1, b0 + k)
-                       : trunc_tf32(ldx(a.seg[sg].A, 0, a0 + k)) * trunc_tf32(ldx(a.seg[sg].B, 0, b0 + k));
+              s += s16 ? ldx(Ap, 1, a0 + k) * ldx(Bp, 1, b0 + k)
+                       : trunc_tf32(ldx(Ap, 0, a0 + k)) * trunc_tf32(ldx(Bp, 0, b0 + k));
           }
           float dl = 0.f;
           if (a.delta && a.delta_mode == 1) dl = a.delta[(b * a.nh + h) * a.Mr + r];
           if (a.delta && a.delta_mode == 2) dl = a.delta[(b * a.nh + h) * a.Nc + c];
-          const float t = ldx(a.Pm, p16, h * a.sPh + (long)r * a.ldp + c) * (a.alpha1 * s - dl);
+          const float t = ldx(Pm, p16, h * a.sPh + (long)r * a.ldp + c) * (a.alpha1 * s - dl);
           T[c] = p16 ? (float)(h16)std::min(std::max(t, -65504.f), 65504.f) : rna(t);
           rs += T[c];
         }
@@ -420,17 +446,17 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream) {
         for (int n = 0; n < a.d; ++n) {
           double acc = 0;
           const long c10 = h * a.sCh + (long)n * a.ldc;
-          for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * opnd(ldx(a.C1, p16, c10 + c));
+          for (int c = 0; c < a.Nc; ++c) acc += (double)T[c] * opnd(ldx(C1p, p16, c10 + c));
           double e2 = 0;
           const long o2 = b * a.sD2b + (long)r * a.ldd2 + h * a.d + n;
           if (a.C2) {
             const long c20 = b * a.sC2b + h * a.sC2h + (long)n * a.ldc2, p0 = h * a.sPh + (long)r * a.ldp;
-            for (int c = 0; c < a.Nc; ++c) e2 += (double)opnd(ldx(a.Pm, p16, p0 + c)) * opnd(ldx(a.C2, p16, c20 + c));
+            for (int c = 0; c < a.Nc; ++c) e2 += (double)opnd(ldx(Pm, p16, p0 + c)) * opnd(ldx(a.C2, p16, c20 + c));
             if (a.D2) stx(a.D2, s16, o2, s16 ? (float)e2 * inv_ps : mr((float)e2 * inv_ps, a.round_tf32));
             else acc += e2;
           }
           float v = a.alpha2 * inv_ps * (float)acc;
-          if (a.want_rsum && a.O) v -= (float)rs * a.O[(long)r * a.ldo + h * a.d + n];
+          if (a.want_rsum && Op) v -= (float)rs * Op[(long)r * a.ldo + h * a.d + n];
           if (a.R) v += a.beta * a.R[b * a.sRb + (long)r * a.ldr + h * a.d + n];
           stx(a.D, s16, b * a.sDb + (long)r * a.ldd + h * a.d + n, s16 ? v : mr(v, a.round_tf32));
         }

@@ -449,21 +449,29 @@ def test_fp16_tangent_plan_pullback_and_slots(hostsim, monkeypatch):
     u, s, vT, info = eng.pullback(g["v0"], g["iters"], g["iters"], 0.0)
     rep = PO.parity_report(s, vT, g["s"], g["vT"])
     assert rep["s_rel_max"] < 5e-3 and rep["subspace"] > 0.999, rep
-    # problem slots: two problems batched against one at a time, same fp16 plan
-    k, P = 2, 2
-    eng1, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, k, dict(fused_min_tokens=1))
-    engP, _, _, _, _ = make_engine(hostsim, "sd_tiny", "mid", 0, P * k, dict(fused_min_tokens=1))
-    engP.set_slots(P)
-    gen = torch.Generator().manual_seed(3)
-    xs = [x, torch.randn(x.shape, generator=gen)]
-    ts = [float(t), 412.0]
-    torch.manual_seed(0)
-    V0 = torch.cat([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0)
-    singles = []
-    for p in range(P):
-        eng1.set_point(xs[p], ts[p], ctx)
-        singles.append(eng1.jvp(V0[p * k:(p + 1) * k]))
-        engP.set_point(xs[p], ts[p], ctx, slot=p)
-    U = engP.jvp(V0)
-    for p in range(P):
-        assert rel(U[p * k:(p + 1) * k], singles[p]) < 1e-6
+    # problem slots: two problems batched against one at a time, same fp16 plan; the kernels index the primal cache per image
+    # (fused attention included) -- or, for the materialised attention path, the engine loops over the slots
+    for fused_min in (1, 1 << 30):
+        k, P = 2, 2
+        eng1, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "mid", 0, k, dict(fused_min_tokens=fused_min))
+        engP, _, _, _, _ = make_engine(hostsim, "sd_tiny", "mid", 0, P * k, dict(fused_min_tokens=fused_min))
+        engP.set_slots(P)
+        gen = torch.Generator().manual_seed(3)
+        xs = [x, torch.randn(x.shape, generator=gen)]
+        cs = [ctx, torch.randn(ctx.shape, generator=gen)]
+        ts = [float(t), 412.0]
+        torch.manual_seed(0)
+        V0 = torch.cat([PO.initial_subspace(x.numel(), k) for _ in range(P)], 0)
+        G = torch.randn(P * k, eng1.n_out, generator=gen)
+        singles = []
+        for p in range(P):
+            sl = slice(p * k, (p + 1) * k)
+            eng1.set_point(xs[p], ts[p], cs[p])
+            singles.append((eng1.jvp(V0[sl]), eng1.vjp(G[sl]), eng1.pullback(V0[sl], 3, 3, 0.0)))
+            engP.set_point(xs[p], ts[p], cs[p], slot=p)
+        U, W = engP.jvp(V0), engP.vjp(G)
+        u, s, vT, _ = engP.pullback(V0, 3, 3, 0.0)
+        for p in range(P):
+            sl = slice(p * k, (p + 1) * k)
+            assert rel(U[sl], singles[p][0]) < 1e-6 and rel(W[sl], singles[p][1]) < 1e-6
+            assert torch.allclose(s[sl], singles[p][2][1], rtol=1e-5) and rel(u[sl], singles[p][2][0]) < 1e-5

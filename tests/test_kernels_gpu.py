@@ -263,11 +263,11 @@ def test_groupnorm_fwd_and_lin():
         t = torch.randn(nb, HW, Cc, device="cuda")
         out = torch.empty_like(t)
         _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t), nb, 0, _p(out),
-                                 C.c_float(0), 0, _p(tmp), _st()))
+                                 C.c_float(0), 0, _p(tmp), 0, C.c_long(0), _st()))
         ref = torch.cat([torch.func.jvp(f, (x,), (t[i:i + 1],))[1] for i in range(nb)])
         assert rel(out, ref) < 2e-5
         _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t), nb, 1, _p(out),
-                                 C.c_float(0), 0, _p(tmp), _st()))
+                                 C.c_float(0), 0, _p(tmp), 0, C.c_long(0), _st()))
         ref = torch.cat([torch.func.vjp(f, x)[1](t[i:i + 1])[0] for i in range(nb)])
         assert rel(out, ref) < 2e-5
 
@@ -295,12 +295,12 @@ def test_groupnorm_lin_both_paths(nb, HW, Cc, G):
         prev = torch.randn_like(t)
         out = prev.clone()
         _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, 1, _p(t), nb, mode, _p(out),
-                                 C.c_float(1.0), 0, _p(tmp), _st()))
+                                 C.c_float(1.0), 0, _p(tmp), 0, C.c_long(0), _st()))
         assert rel(out, ref + prev) < 3e-5
         if Cc % 8 == 0:
             o16 = torch.zeros(nb, HW, Cc, device="cuda", dtype=torch.float16)
             _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, 1, _p(t), nb, mode, _p(o16),
-                                     C.c_float(0), 2, _p(tmp), _st()))
+                                     C.c_float(0), 2, _p(tmp), 0, C.c_long(0), _st()))
             assert rel(o16.float(), ref) < 1e-3
 
 
@@ -311,7 +311,7 @@ def test_attn_delta():
         Cc = H * d
         go, o = torch.randn(nb, Ntok, Cc, device="cuda"), torch.randn(Ntok, Cc, device="cuda")
         delta = torch.empty(nb, H, Ntok, device="cuda")
-        _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Cc), _p(o), C.c_long(Cc), nb, Ntok, H, d, _p(delta), 0, _st()))
+        _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Cc), _p(o), C.c_long(Cc), nb, Ntok, H, d, _p(delta), 0, 0, C.c_long(0), _st()))
         ref = (go.double() * o.double()[None]).view(nb, Ntok, H, d).sum(-1).permute(0, 2, 1)
         assert rel(delta, ref) < 1e-5
 
@@ -328,7 +328,7 @@ def test_layernorm_geglu_softmax():
     t = torch.randn(nb, rows, Cc, device="cuda")
     out = torch.empty_like(t)
     for mode in (0, 1):
-        _ok(N.leaf("pbk_ln_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), C.c_long(rows), Cc, _p(t), nb, mode, _p(out), C.c_float(0), 0, _st()))
+        _ok(N.leaf("pbk_ln_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), C.c_long(rows), Cc, _p(t), nb, mode, _p(out), C.c_float(0), 0, 0, C.c_long(0), _st()))
         if mode == 0:
             ref = torch.stack([torch.func.jvp(f, (x,), (t[i],))[1] for i in range(nb)])
         else:
@@ -343,11 +343,11 @@ def test_layernorm_geglu_softmax():
     assert rel(yy, g(h)) < 1e-5
     dh = torch.randn(nb, rows, 2 * Fd, device="cuda")
     dy = torch.empty(nb, rows, Fd, device="cuda")
-    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), 0, _st()))
+    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), 0, 0, C.c_long(0), _st()))
     assert rel(dy, torch.stack([torch.func.jvp(g, (h,), (dh[i],))[1] for i in range(nb)])) < 2e-5
     gy = torch.randn(nb, rows, Fd, device="cuda")
     gh = torch.empty(nb, rows, 2 * Fd, device="cuda")
-    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), 0, _st()))
+    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), 0, 0, C.c_long(0), _st()))
     assert rel(gh, torch.stack([torch.func.vjp(g, h)[1](gy[i])[0] for i in range(nb)])) < 2e-5
     # softmax + its linearisation, short (warp) and long (block) rows
     for cols in (77, 256, 4096):
@@ -640,12 +640,12 @@ def test_fp16_groupnorm_lin(nb, HW, Cc, G):
                 ref = torch.cat([torch.func.vjp(f, x)[1](t[i:i + 1])[0] for i in range(nb)])
             out = torch.full((nb, HW, Cc), float("nan"), device="cuda", dtype=torch.float16)
             _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t16), nb, mode, _p(out),
-                                     C.c_float(0), IO16, _p(tmp), _st()))
+                                     C.c_float(0), IO16, _p(tmp), 0, C.c_long(0), _st()))
             assert rel(out.float(), ref) < 6e-4, (silu, mode, rel(out.float(), ref))
             prev = torch.randn(nb, HW, Cc, device="cuda").half()
             out = prev.clone()
             _ok(N.leaf("pbk_gn_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), _p(beta), HW, Cc, G, silu, _p(t16), nb, mode, _p(out),
-                                     C.c_float(1.0), IO16, _p(tmp), _st()))
+                                     C.c_float(1.0), IO16, _p(tmp), 0, C.c_long(0), _st()))
             assert rel(out.float(), ref + prev.float()) < 6e-4
 
 
@@ -668,18 +668,18 @@ def test_fp16_layernorm_geglu(rows, Cc):
         for acc in (0.0, 1.0):
             out = prev.clone()
             _ok(N.leaf("pbk_ln_lin")(_p(x), _p(mean), _p(rstd), _p(gamma), C.c_long(rows), Cc, _p(t16), nb, mode, _p(out), C.c_float(acc),
-                                     IO16, _st()))
+                                     IO16, 0, C.c_long(0), _st()))
             assert rel(out.float(), ref + acc * prev.float()) < 6e-4
     Fd = 4 * Cc
     h = torch.randn(rows, 2 * Fd, device="cuda")
     g = lambda z: z[..., :Fd] * F.gelu(z[..., Fd:])
     dh = torch.randn(nb, rows, 2 * Fd, device="cuda").half()
     dy = torch.empty(nb, rows, Fd, device="cuda", dtype=torch.float16)
-    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), IO16, _st()))
+    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), IO16, 0, C.c_long(0), _st()))
     assert rel(dy.float(), torch.stack([torch.func.jvp(g, (h,), (dh[i].float(),))[1] for i in range(nb)])) < 6e-4
     gy = torch.randn(nb, rows, Fd, device="cuda").half()
     gh = torch.empty(nb, rows, 2 * Fd, device="cuda", dtype=torch.float16)
-    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), IO16, _st()))
+    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), IO16, 0, C.c_long(0), _st()))
     assert rel(gh.float(), torch.stack([torch.func.vjp(g, h)[1](gy[i].float())[0] for i in range(nb)])) < 6e-4
 
 
@@ -734,7 +734,7 @@ def test_fp16_data_movement():
     nbd, Ntok, Hh, d = 3, 200, 4, 40
     go = torch.randn(nbd, Ntok, Hh * d, device="cuda").half(); o = torch.randn(Ntok, Hh * d, device="cuda")
     delta = torch.empty(nbd, Hh, Ntok, device="cuda")
-    _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Hh * d), _p(o), C.c_long(Hh * d), nbd, Ntok, Hh, d, _p(delta), 4, _st()))
+    _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Hh * d), _p(o), C.c_long(Hh * d), nbd, Ntok, Hh, d, _p(delta), 4, 0, C.c_long(0), _st()))
     assert rel(delta, (go.double() * o.double()[None]).view(nbd, Ntok, Hh, d).sum(-1).permute(0, 2, 1)) < 1e-5
 
 
@@ -834,3 +834,98 @@ def test_attn_lin_all_fp16(Mr, Nc, d, nb, nh, case):
         rs = Tr.sum(-1) / scale
         ref = ref - (rs.permute(0, 2, 1)[..., None] * O.double().view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
     assert rel(D.float(), ref) < 8e-4, rel(D.float(), ref)
+
+
+def test_fp16_kernels_problem_slots():
+    """k_slot / p_stride: image b reads the primal tensors of problem b / k_slot (one primal cache per problem at a uniform
+    stride): one launch over two problems == two launches over one problem each, bitwise, for the GroupNorm / LayerNorm / GEGLU
+    linearisations, attn_delta and the fused attention kernel."""
+    torch.manual_seed(21)
+    k, P, HW, Cc, G = 2, 2, 256, 320, 32
+    nb = k * P
+    nfl = N.raw().pbk_gn_tmp_floats
+    nfl.restype = C.c_size_t
+    tmp = torch.empty(nfl(HW, Cc, G, nb) + 64, device="cuda")
+    gamma, beta = torch.randn(Cc, device="cuda"), torch.randn(Cc, device="cuda")
+    # one buffer holds both problems' primal tensors at stride `ps` floats: [x | mean | rstd] per problem
+    ps = HW * Cc + 2 * HW + 64
+    prim = torch.randn(P, ps, device="cuda")
+    prim[:, HW * Cc + HW:HW * Cc + 2 * HW] = prim[:, HW * Cc + HW:HW * Cc + 2 * HW].abs() + 0.5     # rstd > 0
+    xp = lambda s: C.c_void_p(prim[s].data_ptr())
+    mp = lambda s: C.c_void_p(prim[s].data_ptr() + 4 * HW * Cc)
+    rp = lambda s: C.c_void_p(prim[s].data_ptr() + 4 * (HW * Cc + HW))
+    t16 = torch.randn(nb, HW, Cc, device="cuda").half()
+    for fn in ("gn", "ln"):
+        for mode in (0, 1):
+            both = torch.empty_like(t16); sep = torch.empty_like(t16)
+            if fn == "gn":
+                call = lambda s0, tt, n, oo, ks, st_: _ok(N.leaf("pbk_gn_lin")(xp(s0), mp(s0), rp(s0), _p(gamma), _p(beta), HW, Cc, G, 1, _p(tt), n, mode,
+                                                                            _p(oo), C.c_float(0), IO16, _p(tmp), ks, C.c_long(st_), _st()))
+            else:
+                call = lambda s0, tt, n, oo, ks, st_: _ok(N.leaf("pbk_ln_lin")(xp(s0), mp(s0), rp(s0), _p(gamma), C.c_long(HW), Cc, _p(tt), n, mode, _p(oo),
+                                                                            C.c_float(0), IO16, ks, C.c_long(st_), _st()))
+            call(0, t16, nb, both, k, ps)
+            for s0 in range(P):
+                call(s0, t16[s0 * k:(s0 + 1) * k], k, sep[s0 * k:(s0 + 1) * k], 0, 0)
+            assert torch.equal(both, sep), (fn, mode)
+    # GEGLU
+    Fd = 256
+    psg = HW * 2 * Fd + 32
+    hp = torch.randn(P, psg, device="cuda")
+    dh = torch.randn(nb, HW, 2 * Fd, device="cuda").half()
+    both = torch.empty(nb, HW, Fd, device="cuda", dtype=torch.float16); sep = torch.empty_like(both)
+    _ok(N.leaf("pbk_geglu_jvp")(_p(hp), C.c_long(HW), _p(dh), nb, Fd, _p(both), IO16, k, C.c_long(psg), _st()))
+    for s0 in range(P):
+        _ok(N.leaf("pbk_geglu_jvp")(_p(hp[s0]), C.c_long(HW), _p(dh[s0 * k:(s0 + 1) * k]), k, Fd, _p(sep[s0 * k:(s0 + 1) * k]), IO16, 0, C.c_long(0), _st()))
+    assert torch.equal(both, sep)
+    gy = torch.randn(nb, HW, Fd, device="cuda").half()
+    both = torch.empty(nb, HW, 2 * Fd, device="cuda", dtype=torch.float16); sep = torch.empty_like(both)
+    _ok(N.leaf("pbk_geglu_vjp")(_p(hp), C.c_long(HW), _p(gy), nb, Fd, _p(both), IO16, k, C.c_long(psg), _st()))
+    for s0 in range(P):
+        _ok(N.leaf("pbk_geglu_vjp")(_p(hp[s0]), C.c_long(HW), _p(gy[s0 * k:(s0 + 1) * k]), k, Fd, _p(sep[s0 * k:(s0 + 1) * k]), IO16, 0, C.c_long(0), _st()))
+    assert torch.equal(both, sep)
+    # fused attention, JVP role: primal operands (X16 = [N][3C] halves, P16, Vt16, O) per problem at a byte stride
+    Mr = Nc = 256; d = 40; nh = 2; Ch = nh * d
+    def blob():
+        return dict(X=torch.randn(Mr, 3 * Ch, device="cuda").half(), P=(torch.softmax(torch.randn(nh, Mr, Nc, device="cuda") * 2, -1) * 16).half(),
+                    Vt=torch.randn(nh, d, Nc, device="cuda").half(), O=torch.randn(Mr, Ch, device="cuda"))
+    blobs = [blob() for _ in range(P)]
+    sizes = {kk: v.numel() * v.element_size() for kk, v in blobs[0].items()}
+    offs, top = {}, 0
+    for kk in ("X", "P", "Vt", "O"):
+        offs[kk] = top; top += (sizes[kk] + 255) // 256 * 256
+    cache = torch.zeros(P, top, device="cuda", dtype=torch.uint8)
+    for s0 in range(P):
+        for kk in offs:
+            cache[s0, offs[kk]:offs[kk] + sizes[kk]] = blobs[s0][kk].view(torch.uint8).reshape(-1)
+    dqkv = torch.randn(nb, Mr, 3 * Ch, device="cuda").half()
+    dVt = torch.randn(nb, nh, d, Nc, device="cuda").half()
+    def run(s0, n, tq, tv, out, ks, stride):
+        base = cache[s0].data_ptr()
+        a = N.PbAttnLin()
+        a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, n, nh, 2
+        q0 = a.seg[0]; q1 = a.seg[1]
+        q0.A, q0.lda, q0.sAb, q0.sAh, q0.B, q0.ldb, q0.sBb, q0.sBh = tq.data_ptr(), 3 * Ch, Mr * 3 * Ch, d, base + offs["X"] + 2 * Ch, 3 * Ch, 0, d
+        q1.A, q1.lda, q1.sAb, q1.sAh, q1.B, q1.ldb, q1.sBb, q1.sBh = base + offs["X"], 3 * Ch, 0, d, tq.data_ptr() + 2 * Ch, 3 * Ch, Mr * 3 * Ch, d
+        a.alpha1, a.alpha2 = d ** -0.5, 1.0
+        a.Pm, a.ldp, a.sPh = base + offs["P"], Nc, Mr * Nc
+        a.want_rsum, a.O, a.ldo = 1, base + offs["O"], Ch
+        a.C1, a.ldc, a.sCh = base + offs["Vt"], Nc, d * Nc
+        a.C2, a.ldc2, a.sC2h, a.sC2b = tv.data_ptr(), Nc, d * Nc, nh * d * Nc
+        a.D, a.ldd, a.sDb = out.data_ptr(), Ch, Mr * Ch
+        a.p16, a.p_scale, a.s16, a.k_slot, a.p_stride = 1, 16.0, 1, ks, stride
+        _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+    both = torch.empty(nb, Mr, Ch, device="cuda", dtype=torch.float16); sep = torch.empty_like(both)
+    run(0, nb, dqkv, dVt, both, k, top)
+    for s0 in range(P):
+        run(s0, k, dqkv[s0 * k:(s0 + 1) * k], dVt[s0 * k:(s0 + 1) * k], sep[s0 * k:(s0 + 1) * k], 0, 0)
+    assert torch.equal(both, sep)
+    # attn_delta
+    go = torch.randn(nb, Mr, Ch, device="cuda").half()
+    both = torch.empty(nb, nh, Mr, device="cuda"); sep = torch.empty_like(both)
+    obase = cache[0].data_ptr() + offs["O"]
+    _ok(N.leaf("pbk_attn_delta")(_p(go), C.c_long(Ch), C.c_void_p(obase), C.c_long(Ch), nb, Mr, nh, d, _p(both), 4, k, C.c_long(top // 4), _st()))
+    for s0 in range(P):
+        _ok(N.leaf("pbk_attn_delta")(_p(go[s0 * k:(s0 + 1) * k]), C.c_long(Ch), C.c_void_p(cache[s0].data_ptr() + offs["O"]), C.c_long(Ch), k, Mr, nh, d,
+                                     _p(sep[s0 * k:(s0 + 1) * k]), 4, 0, C.c_long(0), _st()))
+    assert torch.equal(both, sep)

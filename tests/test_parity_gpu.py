@@ -446,3 +446,26 @@ def test_engine_on_second_device_while_current_is_first():
         assert s.device == torch.device(dev) and torch.cuda.current_device() == 0
         outs.append(s.cpu())
     assert torch.allclose(outs[0], outs[1], rtol=1e-6)
+
+
+def test_problem_slots_full_size_vs_golden():
+    """The bench default (problem slots) at full size: the golden SD-v1.5 mid-block problem (k = 5, 50 iterations, minted by the
+    verbatim reference) solved in slot 1 of a 3-slot batch next to two other problems, per-problem parity 1e-3 / 0.999."""
+    g = torch.load(os.path.join(GOLDEN, "sd15_mid_k5_i50.pt"))
+    name, k, iters, P = "sd15", g["k"], g["iters"], 3
+    unet = SY.SyntheticUNet(name, upto=("mid", 0), device=DEV)
+    x, t, ctx = SY.synthetic_inputs(name)
+    eng = PB.PullbackEngine(PB.unet_config(unet), 64, 64, "mid", 0, P * k, ctx.shape[1], DEV)
+    eng.bind(unet.state_dict())
+    eng.set_slots(P)
+    gen = torch.Generator().manual_seed(11)
+    xs = [torch.randn(x.shape, generator=gen), x, torch.randn(x.shape, generator=gen)]
+    ts = [250.0, float(t), 900.0]
+    V0 = torch.cat([PO.initial_subspace(x.numel(), k, generator=gen), g["v0"], PO.initial_subspace(x.numel(), k, generator=gen)], 0)
+    for p in range(P):
+        eng.set_point(xs[p], ts[p], ctx, slot=p)
+    u, s, vT, info = eng.pullback(V0, iters, iters, 0.0)
+    sl = slice(k, 2 * k)
+    rep = PO.parity_report(s[sl], vT[sl], g["s"], g["vT"], u[sl].T.cpu(), g["u"])
+    print("slots full size", {kk: rep[kk] for kk in ("s_rel_max", "subspace", "cos_min_gapped", "u_subspace")})
+    assert rep["s_rel_max"] < 1e-3 and rep["subspace"] > 0.999 and rep["cos_min_gapped"] > 0.99 and rep["u_subspace"] > 0.999, rep
