@@ -42,6 +42,10 @@ const char* encode_plainx(CUtensorMap* m, const void* base, int f16, int rows, i
                           int nb, int box_cols, int box_rows, int swizzle_bytes, int* hmul, int* bmul, uint32_t* bytes);
 }
 
+namespace pbattn16 {   // pb_attn16_sm100.cu: the column-batched kernel of the all-fp16 plan
+const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled);
+}
+
 namespace pbattn {
 using namespace pbtc;
 
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
       unsigned spins = 0;
       while (mp < nj || mb < nj || mc < nj) {
         bool any = false;
-        if (mb < nj && mbar_try_wait(&b_empty[rb.idx], rb.ph ^ 1) && (!has_c2 || mbar_try_wait(&c2_empty[rb.idx], rb.ph ^ 1))) {
+        if (mb < nj && mbar_test_wait(&b_empty[rb.idx], rb.ph ^ 1) && (!has_c2 || mbar_test_wait(&c2_empty[rb.idx], rb.ph ^ 1))) {
           const int c0 = mb * TNc, st = rb.idx;
           mbar_arrive_expect_tx(&b_full[st], p.b_bytes);
 #pragma unroll
@@ -222,12 +226,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
           }
           rb.next(NB); ++mb; any = true;
         }
-        if (mp < nj && mbar_try_wait(&pt_empty[rp.idx], rp.ph ^ 1)) {
+        if (mp < nj && mbar_test_wait(&pt_empty[rp.idx], rp.ph ^ 1)) {
           mbar_arrive_expect_tx(&p_full[rp.idx], p.p_bytes);
           tma_load_4d(sPT + rp.idx * PT_BYTES, &p.mapP, &p_full[rp.idx], mp * TNc, r0, bat_h, ps);
           rp.next(NPT); ++mp; any = true;
         }
-        if (mc < nj && mbar_try_wait(&c_empty[rc.idx], rc.ph ^ 1)) {
+        if (mc < nj && mbar_test_wait(&c_empty[rc.idx], rc.ph ^ 1)) {
           mbar_arrive_expect_tx(&c_full[rc.idx], p.c_bytes);
           tma_load_4d(sC + rc.idx * p.c_tile_bytes, &p.mapC, &c_full[rc.idx], mc * TNc, 0, bat_h, ps);
           rc.next(NC1); ++mc; any = true;
@@ -534,6 +538,13 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
   if (a.nseg < 1 || a.nseg > 2) return "attn_lin: 1 or 2 segments";
   if ((long)a.nb * a.nh > 65535) return "attn_lin: batch too large";
   if (a.D2 && !a.C2) return "attn_lin: D2 needs C2";
+  {
+    // all-fp16 plan, head dim <= 64, the engine's four roles: the column-batched kernel (P and the primal tiles loaded once per
+    // group of tangent columns); everything else: the per-column kernel below
+    bool handled = false;
+    if (const char* e = pbattn16::launch(a, static_cast<cudaStream_t>(st), &handled)) return e;
+    if (handled) return nullptr;
+  }
   const int s16 = a.s16 ? 1 : 0;                // the S operands (segments) and the outputs D / D2 hold halves too
   if (s16 && !a.p16) return "attn_lin: fp16 S operands need the fp16 probability path";
   if (s16 && a.R) return "attn_lin: no residual with fp16 outputs";

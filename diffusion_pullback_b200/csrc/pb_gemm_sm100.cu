@@ -487,6 +487,7 @@ static EncodeFn get_encode() {
 }
 
 // 4-D tiled tensor map over fp32 (f16 = 0) or fp16 (f16 = 1) elements; strides in bytes; swizzle 128, 64 or 32 bytes
+int g_tmap_promo256 = 0;   // set around an encode call: 256-byte L2 promotion (streams whose next box continues the same rows)
 const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t dims[4], const uint64_t strides_bytes[3],
                      const uint32_t box[4], int swizzle_bytes) {
   EncodeFn fn = get_encode();
@@ -500,7 +501,7 @@ const char* encode4x(CUtensorMap* m, const void* base, int f16, const uint64_t d
   CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd,
                   gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  g_tmap_promo256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[256];
     snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u",

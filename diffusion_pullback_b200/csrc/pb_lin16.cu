@@ -25,14 +25,17 @@ struct GnGeom16 { int nz, Cblk, CV, lanes, threads, chunks, ppb; };
 GnGeom16 gn_geom16(int HW, int C, int G, int nb) {
   GnGeom16 g;
   const int cpg = C / G;
+  // blocks of <= 256 threads, 4 resident per SM (<= 64 registers): these kernels are latency-bound on small tensors, so
+  // occupancy and a single wave matter more than per-block efficiency (ncu r2c: 480-thread blocks at 76 registers ran ONE
+  // block per SM in 2.9 waves, 23 % of the warp slots active)
   g.nz = 1;
-  while ((C / g.nz) / 4 > 512 && g.nz < G) g.nz *= 2;
-  if (G % g.nz || ((C / g.nz) % cpg) || (C / g.nz) / 4 > 512) { g.nz = 0; return g; }   // unsupported geometry
+  while ((C / g.nz) / 4 > 256 && g.nz < G) g.nz *= 2;
+  if (G % g.nz || ((C / g.nz) % cpg) || (C / g.nz) / 4 > 256) { g.nz = 0; return g; }   // unsupported geometry
   g.Cblk = C / g.nz;
   g.CV = g.Cblk / 4;                                               // channel quads per pixel row of the slab
-  g.lanes = std::max(1, std::min(std::min(512 / g.CV, 6144 / g.Cblk), 16));   // pixel lanes; smem = lanes * Cblk * 8 bytes <= 48 KB
+  g.lanes = std::max(1, std::min(std::min(256 / g.CV, 6144 / g.Cblk), 16));   // pixel lanes; smem = lanes * Cblk * 8 bytes <= 48 KB
   g.threads = (g.CV * g.lanes + 31) / 32 * 32;
-  const int target = std::max(1, (kSMs * 3 + nb * g.nz - 1) / (nb * g.nz));
+  const int target = std::max(1, (kSMs * 4 + nb * g.nz - 1) / (nb * g.nz));
   const int maxchunks = (HW + g.lanes - 1) / g.lanes;
   g.chunks = std::max(1, std::min(maxchunks, target));
   g.ppb = (HW + g.chunks - 1) / g.chunks;
@@ -43,7 +46,7 @@ GnGeom16 gn_geom16(int HW, int C, int G, int nb) {
 
 // MODE 0 (JVP): u = t ; MODE 1 (VJP): u = t * act'(gamma xhat + beta) * gamma.   part[b][chunk][g] = (sum u, sum xhat u)
 template <int MODE>
-__global__ void __launch_bounds__(512) gn16_sums_k(const float* __restrict__ xp, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, 4) gn16_sums_k(const float* __restrict__ xp, const float* __restrict__ mean,
                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta_, int HW, int C, int G, int silu,
                                                    const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(512) gn16_sums_k(const float* __restrict__ xp,
 //   MODE 0 (JVP): out = act'(.) gamma rstd (t - m1 - xhat m2)          MODE 1 (VJP): out = rstd (t act'(.) gamma - m1 - xhat m2)
 //   (m1, m2) = group means of (u, xhat u);   out = result + acc * out
 template <int MODE>
-__global__ void __launch_bounds__(512) gn16_apply_k(const float* __restrict__ xp, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, 4) gn16_apply_k(const float* __restrict__ xp, const float* __restrict__ mean,
                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta_, int HW, int C, int G, int silu,
                                                     const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,

@@ -48,16 +48,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe of a phase: try_wait may suspend the thread for a hardware time-out before it reports "not yet", which is
+// what a loop polling SEVERAL barriers must not do (the ready ring would wait behind the blocked probe of another).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap, never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
+  bool said = false;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("pb_tc: mbarrier timeout block (%d,%d,%d) thread %d\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
+    const long long dt = clock64() - t0;
+    if (dt > 2000000000LL && !said) {      // report every stuck waiter first (barrier = shared-memory address), trap a little later
+      said = true;
+      if ((threadIdx.x & 31) == 0)
+        printf("pb_tc: mbarrier timeout block (%d,%d,%d) warp %d barrier 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x >> 5, smem_u32(bar), parity);
     }
+    if (dt > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
