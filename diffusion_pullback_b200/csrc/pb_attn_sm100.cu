@@ -30,6 +30,10 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cstring>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "pb_host_util.h"
 #include "pb_kernels.h"
@@ -172,6 +176,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_lin_kernel(const __grid_cons
     for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); }
     for (int i = 0; i < MAX_NPT; ++i) { mbar_init(&p_full[i], 1); mbar_init(&pt_empty[i], 1); mbar_init(&t_full[i], 4); mbar_init(&p_used[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.Nc < TNc) {
+    // fewer score columns than one step: the TMA box of a B tile is only Nc rows, the rows below keep whatever the previous
+    // kernel left in shared memory, and 0 (the zero-filled P columns) times a NaN bit pattern is NaN -- zero the ring once
+    uint4* z = reinterpret_cast<uint4*>(sB);
+    const int n16 = NB * b_stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += NTHREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(TMEM_COLS)
@@ -531,8 +543,8 @@ PBK pbk_attn_lin_supported(int d, int Mr, int Nc) {
   return nullptr;
 }
 
+static const char* pbk_attn_lin_v1(const PbAttnLin* ap, pb_stream st);
 PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
-  using namespace pbattn;
   const PbAttnLin& a = *ap;
   if (const char* e = pbk_attn_lin_supported(a.d, a.Mr, a.Nc)) return e;
   if (a.nseg < 1 || a.nseg > 2) return "attn_lin: 1 or 2 segments";
@@ -543,8 +555,57 @@ PBK pbk_attn_lin(const PbAttnLin* ap, pb_stream st) {
     // group of tangent columns); everything else: the per-column kernel below
     bool handled = false;
     if (const char* e = pbattn16::launch(a, static_cast<cudaStream_t>(st), &handled)) return e;
+    static const bool cmp = getenv("PB_ATTN_CMP") != nullptr;      // debugging: run the per-column kernel too and compare D / D2
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (handled && cmp) cudaStreamIsCapturing(static_cast<cudaStream_t>(st), &cs);
+    if (handled && cmp && cs == cudaStreamCaptureStatusNone) {
+      static bool inside = false;
+      if (!inside) {
+        inside = true;
+        cudaStream_t s_ = static_cast<cudaStream_t>(st);
+        cudaStreamSynchronize(s_);
+        const size_t n1 = (size_t)a.nb * a.sDb, n2 = a.D2 ? (size_t)a.nb * a.sD2b : 0;
+        std::vector<__half> v2(n1), v2b(n2), v1(n1), v1b(n2);
+        cudaMemcpy(v2.data(), a.D, n1 * 2, cudaMemcpyDeviceToHost);
+        if (n2) cudaMemcpy(v2b.data(), a.D2, n2 * 2, cudaMemcpyDeviceToHost);
+        setenv("PB_ATTN_V1_ONCE", "1", 1);
+        PbAttnLin a1 = a;
+        const char* e1 = pbk_attn_lin_v1(&a1, st);
+        cudaStreamSynchronize(s_);
+        cudaMemcpy(v1.data(), a.D, n1 * 2, cudaMemcpyDeviceToHost);
+        if (n2) cudaMemcpy(v1b.data(), a.D2, n2 * 2, cudaMemcpyDeviceToHost);
+        auto diff = [&](const std::vector<__half>& x, const std::vector<__half>& y, long ld, long sb, const char* nm) {
+          double num = 0, den = 0; long bad = 0, firstbad = -1;
+          for (int b = 0; b < a.nb; ++b)
+            for (long r = 0; r < a.Mr; ++r)
+              for (int c = 0; c < a.nh * a.d; ++c) {
+                const long i = b * sb + r * ld + c;
+                const float p_ = __half2float(x[i]), q_ = __half2float(y[i]);
+                if (!(p_ == p_) || fabsf(p_ - q_) > 1e-2f * (fabsf(q_) + 1e-3f)) { if (firstbad < 0) firstbad = i; ++bad; }
+                num += (double)(p_ - q_) * (p_ - q_); den += (double)q_ * q_;
+              }
+          fprintf(stderr, "pb_attn cmp %s: Mr %d Nc %d d %d nb %d nh %d nseg %d c2 %d dm %d rsum %d k_slot %d | rel %.3e bad %ld first %ld (b %ld r %ld c %ld) %s\n", nm,
+                  a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg, a.C2 ? (a.D2 ? 2 : 1) : 0, a.delta ? a.delta_mode : 0, a.want_rsum, a.k_slot,
+                  den > 0 ? sqrt(num / den) : -1.0, bad, firstbad, firstbad < 0 ? -1 : firstbad / sb, firstbad < 0 ? -1 : (firstbad % sb) / ld,
+                  firstbad < 0 ? -1 : (firstbad % sb) % ld, e1 ? e1 : "");
+        };
+        diff(v2, v1, a.ldd, a.sDb, "D ");
+        if (n2) diff(v2b, v1b, a.ldd2, a.sD2b, "D2");
+        inside = false;
+        return nullptr;
+      }
+    }
+    static const bool sync_after = getenv("PB_ATTN_SYNC") != nullptr;
+    if (handled && sync_after) cudaStreamSynchronize(static_cast<cudaStream_t>(st));
     if (handled) return nullptr;
   }
+  return pbk_attn_lin_v1(ap, st);
+}
+
+// the per-column kernel of this file
+static const char* pbk_attn_lin_v1(const PbAttnLin* ap, pb_stream st) {
+  using namespace pbattn;
+  const PbAttnLin& a = *ap;
   const int s16 = a.s16 ? 1 : 0;                // the S operands (segments) and the outputs D / D2 hold halves too
   if (s16 && !a.p16) return "attn_lin: fp16 S operands need the fp16 probability path";
   if (s16 && a.R) return "attn_lin: no residual with fp16 outputs";

@@ -17,76 +17,7 @@ a_ = ap.parse_args()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def build(Mr, Nc, d, nb, nh, case):
-    Cc = nh * d
-    ldp = (Nc + 7) // 8 * 8
-    scale = 2.0 ** round(0.5 * math.log2(Nc))
-    hf = lambda *s: (torch.randn(*s, device="cuda") * 0.5).half()
-    t = dict(A0=hf(nb, Mr, Cc), B0=hf(Nc, Cc), A1=hf(Mr, Cc), B1=hf(nb, Nc, Cc), C1=hf(nh, d, ldp), C2=hf(nb, nh, d, ldp),
-             O=torch.randn(Mr, Cc, device="cuda"))
-    P16 = torch.empty(nh, Mr, ldp, device="cuda", dtype=torch.float16)
-    for h in range(nh):                                          # head by head: the fp32 softmax of 4096^2 x 8 is 0.5 GB
-        Ph = torch.softmax(torch.randn(Mr, ldp, device="cuda") * 2, -1)
-        Ph[:, Nc:] = 0
-        P16[h] = (Ph * scale).half()
-    t["P16"] = P16
-    nseg = 2 if case == "jvp" else 1
-    mode = {"jvp": 0, "cross": 0, "vjp_a": 1, "vjp_b": 2}[case]
-    c2 = {"jvp": 1, "cross": 0, "vjp_a": 0, "vjp_b": 2}[case]
-    t["delta"] = torch.randn(nb, nh, Mr if mode == 1 else Nc, device="cuda") if mode else None
-    t["D"] = torch.zeros(nb, Mr, Cc, device="cuda", dtype=torch.float16)
-    t["D2"] = torch.zeros(nb, Mr, Cc, device="cuda", dtype=torch.float16)
-    a = N.PbAttnLin()
-    a.Mr, a.Nc, a.d, a.nb, a.nh, a.nseg = Mr, Nc, d, nb, nh, nseg
-    s0 = a.seg[0]
-    if case == "vjp_b":      # A primal (V rows), B per tangent (Obar)
-        s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = t["A1"].data_ptr(), Cc, 0, d, t["B1"].data_ptr(), Cc, Nc * Cc, d
-    else:
-        s0.A, s0.lda, s0.sAb, s0.sAh, s0.B, s0.ldb, s0.sBb, s0.sBh = t["A0"].data_ptr(), Cc, Mr * Cc, d, t["B0"].data_ptr(), Cc, 0, d
-    s1 = a.seg[1]
-    s1.A, s1.lda, s1.sAb, s1.sAh, s1.B, s1.ldb, s1.sBb, s1.sBh = t["A1"].data_ptr(), Cc, 0, d, t["B1"].data_ptr(), Cc, Nc * Cc, d
-    a.alpha1, a.alpha2, a.beta = d ** -0.5, 0.7, 0.0
-    a.Pm, a.ldp, a.sPh = P16.data_ptr(), ldp, Mr * ldp
-    a.delta, a.delta_mode = (t["delta"].data_ptr() if mode else None), mode
-    a.want_rsum, a.O, a.ldo = int(mode == 0), t["O"].data_ptr(), Cc
-    a.C1, a.ldc, a.sCh = t["C1"].data_ptr(), ldp, d * ldp
-    a.D, a.ldd, a.sDb, a.round_tf32 = t["D"].data_ptr(), Cc, Mr * Cc, 1
-    a.p16, a.p_scale, a.s16 = 1, scale, 1
-    if c2:
-        a.C2, a.ldc2, a.sC2h, a.sC2b = t["C2"].data_ptr(), ldp, d * ldp, nh * d * ldp
-    if c2 == 2:
-        a.D2, a.ldd2, a.sD2b = t["D2"].data_ptr(), Cc, Mr * Cc
-    nprod = nseg + 1 + (1 if c2 else 0)                          # contractions with the score matrix, 2 Mr Nc d flops each
-    return a, t, nprod, scale
-
-
-def reference(t, Mr, Nc, d, nb, nh, case, scale):
-    Cc = nh * d
-    dd = lambda x: x.double()
-    if case == "vjp_b":
-        S = torch.einsum("ihd,bjhd->bhij", dd(t["A1"]).view(Mr, nh, d), dd(t["B1"]).view(nb, Nc, nh, d))
-    else:
-        S = torch.einsum("bihd,jhd->bhij", dd(t["A0"]).view(nb, Mr, nh, d), dd(t["B0"]).view(Nc, nh, d))
-    if case == "jvp":
-        S = S + torch.einsum("ihd,bjhd->bhij", dd(t["A1"]).view(Mr, nh, d), dd(t["B1"]).view(nb, Nc, nh, d))
-    S = S * d ** -0.5
-    if case == "vjp_a":
-        S = S - dd(t["delta"])[..., :, None]
-    if case == "vjp_b":
-        S = S - dd(t["delta"])[..., None, :]
-    Ps = dd(t["P16"])[None, :, :, :Nc]
-    Tr = (Ps * S).float().half().double()
-    acc = torch.einsum("bhij,hnj->bihn", Tr, dd(t["C1"])[..., :Nc]).reshape(nb, Mr, Cc) / scale
-    e2 = None
-    if case in ("jvp", "vjp_b"):
-        e2 = torch.einsum("hij,bhnj->bihn", dd(t["P16"])[..., :Nc], dd(t["C2"])[..., :Nc]).reshape(nb, Mr, Cc) / scale
-        if case == "jvp":
-            acc = acc + e2
-    ref = 0.7 * acc
-    if case in ("jvp", "cross"):
-        rs = Tr.sum(-1) / scale
-        ref = ref - (rs.permute(0, 2, 1)[..., None] * dd(t["O"]).view(Mr, nh, d)[None]).reshape(nb, Mr, Cc)
-    return ref, (e2 if case == "vjp_b" else None)
+from tests.attn_cases import build, reference
 
 
 rel = lambda x, y: float((x.double() - y.double()).norm() / y.double().norm())
@@ -99,6 +30,10 @@ if a_.shapes.startswith("one:"):
     c_ = a_.shapes[4:]
     n_ = int(os.environ.get("BENCH_N", "4096"))
     shapes += [(n_, 77 if c_ == "cross" else n_, int(os.environ.get("BENCH_D", "40")), int(os.environ.get("BENCH_NH", "8")), c_)]
+if a_.shapes == "qkv":
+    shapes += [(1024, 1024, 16, 4, "jvp_qkv"), (1024, 1024, 40, 2, "jvp_qkv"), (512, 512, 64, 2, "jvp_qkv")]
+if a_.shapes == "d16":
+    shapes += [(1024, 1024, 16, 4, c) for c in ("jvp", "vjp_a", "vjp_b", "cross")] + [(1024, 1024, 32, 4, c) for c in ("jvp", "vjp_a", "vjp_b")]
 if a_.shapes == "small":
     shapes += [(512, 512, 40, 2, c) for c in ("jvp", "vjp_a", "vjp_b", "cross")] + [(384, 320, 64, 2, c) for c in ("jvp", "vjp_a", "vjp_b")]
 res = []

@@ -929,3 +929,22 @@ def test_fp16_kernels_problem_slots():
         _ok(N.leaf("pbk_attn_delta")(_p(go[s0 * k:(s0 + 1) * k]), C.c_long(Ch), C.c_void_p(cache[s0].data_ptr() + offs["O"]), C.c_long(Ch), k, Mr, nh, d,
                                      _p(sep[s0 * k:(s0 + 1) * k]), 4, 0, C.c_long(0), _st()))
     assert torch.equal(both, sep)
+
+
+@pytest.mark.parametrize("Mr,Nc,d,nh,nb,case", [
+    (1024, 1024, 16, 4, 3, "jvp_qkv"), (1024, 1024, 40, 2, 5, "jvp_qkv"), (512, 512, 64, 2, 5, "jvp_qkv"),
+    (1024, 1024, 16, 4, 3, "vjp_b"), (1024, 1024, 40, 2, 5, "vjp_b"), (512, 576, 64, 2, 4, "vjp_b"),
+    (1024, 1024, 40, 2, 5, "vjp_a"), (1024, 77, 40, 2, 5, "cross"), (1024, 1024, 32, 4, 7, "jvp"),
+    (2048, 2048, 40, 8, 5, "vjp_b"), (2048, 2048, 40, 8, 5, "jvp_qkv")])
+def test_attn_lin_engine_roles(Mr, Nc, d, nh, nb, case):
+    """The fused attention linearisation in the operand layouts of the engine (tests/attn_cases.py), through the column-batched
+    kernel (pb_attn16_sm100.cu): column groups of 5 / 3 + 2 / 4 + 3 tangents, the VJP-B role with a primal A and a per-tangent B
+    operand, and 2048-token launches of 256 CTAs (more than one wave: S / T / per-column rings walked by two warps each)."""
+    from tests.attn_cases import build, reference
+    torch.manual_seed(3)
+    a, t, _, scale = build(Mr, Nc, d, nb, nh, case)
+    _ok(N.leaf("pbk_attn_lin")(C.byref(a), _st()))
+    ref, e2 = reference(t, Mr, Nc, d, nb, nh, case, scale)
+    assert rel(t["D"].float(), ref) < 8e-4, rel(t["D"].float(), ref)
+    if e2 is not None:
+        assert rel(t["D2"].float(), e2) < 6e-4, rel(t["D2"].float(), e2)
