@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
 }
 
 static long long* g_trace = nullptr;
-extern "C" __attribute__((visibility("default"))) int pb_attn16_trace_read(long long* host, int n) {   // debugging aid (scripts/trace_attn.py)
+extern "C" __attribute__((visibility("default"))) int pbk_attn16_trace_read(long long* host, int n) {   // debugging aid (scripts/trace_attn.py)
   if (!g_trace) return 0;
   cudaDeviceSynchronize();
   cudaMemcpy(host, g_trace, sizeof(long long) * std::min(n, 512 * 16), cudaMemcpyDeviceToHost);

@@ -157,7 +157,7 @@ PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);
 // debugging aid of the column-batched kernel (PB_ATTN_TRACE=1, scripts/trace_attn.py): per-substep event clocks of CTA (0, 0)
 // of the last launch, [512][16] values; returns the number of values copied
-extern "C" __attribute__((visibility("default"))) int pb_attn16_trace_read(long long* host, int n);
+extern "C" __attribute__((visibility("default"))) int pbk_attn16_trace_read(long long* host, int n);
 
 // ---- time embedding (primal only) ----
 PBK pbk_timestep_embedding(float t, int dim, int flip_sin_to_cos, float freq_shift, float* out, pb_stream st);

@@ -10,7 +10,7 @@ sys.argv = ["bench_attn.py", "--shapes", "one:" + case, "--reps", "1"]
 ns = runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "bench_attn.py"))
 from diffusion_pullback_b200 import _native as N
 buf = (C.c_longlong * (512 * 16))()
-n = N.raw().pb_attn16_trace_read(buf, 512 * 16)
+n = N.raw().pbk_attn16_trace_read(buf, 512 * 16)
 ev = [[buf[u * 16 + e] for e in range(16)] for u in range(512)]
 t0 = min(v for r in ev for v in r if v)
 names = ["w1_pc", "w1_sfree", "w1_iss", "w10_pc", "w10_tfull", "c_sfull", "c_math", "c_tempty", "c_tfull", "c_start", "pcld", "shld", "w1_el", "w1_mma", "w1_cmt", "x"]
