@@ -37,7 +37,9 @@ class DDIMSchedule:
         self._L = _lib
 
     def set_timesteps(self, num_inferences, device=None, is_inversion=False):
-        """`utils.py:273-286` verbatim semantics (float timesteps; inversion adds 1e-6 and walks upwards)."""
+        """`utils.py:273-286`: float timesteps linspace(0, 1, n) * t_max; inversion adds 1e-6 and walks upwards.  The body follows
+        the reference's arithmetic step for step on purpose: the float schedule must be bit-identical (the golden test asserts
+        `torch.equal` on it), so these ~8 lines are the one place the product restates reference code nearly line for line."""
         device = "cpu" if device is None else device
         seq = torch.linspace(0, 1, num_inferences, device=device) * self.t_max
         if is_inversion:
@@ -56,9 +58,15 @@ class DDIMSchedule:
         return float(self.alphas_cumprod[int(torch.as_tensor(t).long())])
 
     def step(self, et, t, xt, eta=0.0, **kwargs):
-        """`utils.py:288-315`, eta = 0 (the only value the reference passes): one fused elementwise kernel."""
-        if eta != 0:
-            raise NotImplementedError("the reference always calls step(..., eta=0)")
+        """`utils.py:288-315` / `:1202-1245`.  eta = 0 (the SD loops): one fused elementwise kernel (`pb_ddim_step`).
+        eta != 0 (the stochastic branch the unconditional loop switches to under `performance_boosting`, `edit.py:1650-1653`):
+        sigma_t = sqrt((1 - a_t / a_next)(1 - a_next) / (1 - a_t)),
+        x_next = sqrt(a_next) P_xt + sqrt(1 - a_next - eta sigma_t^2) e_t + eta sigma_t z with z = torch.randn_like(x_t) -- the same
+        draw from the same generator as the reference -- combined by `pb_lincomb3`."""
+        if getattr(self, "learn_sigma", False):
+            raise NotImplementedError("learn_sigma is the constant False in the reference (utils.py:1177): the learned-variance "
+                                      "branch of YHCustomScheduler.step (utils.py:1239-1244) is unreachable there and not built")
+        assert et.shape == xt.shape, "et, xt shape should be same"                     # utils.py:1210
         t_idx = self.timesteps.tolist().index(float(t))
         t_next = self.timesteps_next[t_idx]
         L = self._L if self._L is not None else N.lib()
@@ -66,13 +74,53 @@ class DDIMSchedule:
             raise RuntimeError("diffusion_pullback_b200 runs on a CUDA (sm_100a) device only (no CPU fallback exists)")
         xt = xt.contiguous().float()
         et = et.contiguous().float()
-        x_next, p_xt = torch.empty_like(xt), torch.empty_like(xt)
-        st = C.c_void_p(torch.cuda.current_stream(xt.device).cuda_stream) if xt.device.type == "cuda" else C.c_void_p(0)
-        rc = L.pb_ddim_step(C.c_void_p(xt.data_ptr()), C.c_void_p(et.data_ptr()), self._alpha(t), self._alpha(t_next),
-                            C.c_void_p(x_next.data_ptr()), C.c_void_p(p_xt.data_ptr()), xt.numel(), st)
-        if rc != 0:
-            raise ValueError("pb_ddim_step: invalid arguments")
+        at, at_next = self._alpha(t), self._alpha(t_next)
+        if eta == 0:
+            x_next, p_xt = torch.empty_like(xt), torch.empty_like(xt)
+            st = C.c_void_p(torch.cuda.current_stream(xt.device).cuda_stream) if xt.device.type == "cuda" else C.c_void_p(0)
+            rc = L.pb_ddim_step(C.c_void_p(xt.data_ptr()), C.c_void_p(et.data_ptr()), at, at_next,
+                                C.c_void_p(x_next.data_ptr()), C.c_void_p(p_xt.data_ptr()), xt.numel(), st)
+            if rc != 0:
+                raise ValueError("pb_ddim_step: invalid arguments")
+            return SchedulerOutput(x_next, p_xt)
+        import math
+        sigma = math.sqrt((1.0 - at / at_next) * (1.0 - at_next) / (1.0 - at))
+        d_coef = math.sqrt(1.0 - at_next - eta * sigma ** 2)
+        z = torch.randn_like(xt)                                                        # utils.py:311 / :1237
+        inv = 1.0 / math.sqrt(at)
+        p_xt = _lincomb3(inv, xt, -math.sqrt(1.0 - at) * inv, et, 0.0, None, self._L)   # (x_t - sqrt(1 - a_t) e_t) / sqrt(a_t)
+        x_next = _lincomb3(math.sqrt(at_next), p_xt, d_coef, et, eta * sigma, z, self._L)
         return SchedulerOutput(x_next, p_xt)
+
+
+class YHCustomScheduler(DDIMSchedule):
+    """`utils.py:1171-1286`: the scheduler of the unconditional (CelebA-HQ / DDPM) family -- same float-timestep
+    `set_timesteps` / `step` as above over its own SNR schedule: 'linear' (betas = linspace(1e-4, 0.02, 1000) in float64,
+    `:1248-1254`, `:1267-1268`) or 'cosine' (improved-DDPM, `:1275-1286`, t_max + 1 steps).  `args` is the reference's
+    argument object (`noise_schedule`, `device`, `dtype` are read); keyword arguments do the same without one."""
+
+    def __init__(self, args=None, noise_schedule=None, _lib=None):
+        import math
+        self.t_max = 999
+        ns = getattr(args, "noise_schedule", None) if args is not None else noise_schedule
+        self.noise_schedule = "linear" if ns is None else ns
+        self.timesteps = self.timesteps_next = None
+        self.learn_sigma = False
+        self._L = _lib
+        if self.noise_schedule == "linear":
+            betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+        elif self.noise_schedule == "cosine":
+            timesteps, sc = self.t_max + 1, 0.008
+            x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
+            ac = torch.cos(((x / timesteps) + sc) / (1 + sc) * math.pi * 0.5) ** 2
+            ac = ac / ac[0]
+            betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+        else:
+            raise ValueError(f"unknown noise schedule {self.noise_schedule!r}")
+        dtype = getattr(args, "dtype", torch.float32) if args is not None else torch.float32
+        self.betas = betas.to(dtype=dtype).cpu()
+        # float64 cumulative product, cast afterwards (utils.py:1262-1265); kept on the host: `step` reads two scalars per call
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0).to(dtype=dtype).float().cpu()
 
 
 def _eps(unet, latents, t, ctx, guidance_scale, neg_ctx):
@@ -123,6 +171,29 @@ def ddim_forward_steps(unet, scheduler, zt, prompt_emb, num_inference_steps, t_s
     return latents
 
 
+@torch.no_grad()
+def ddim_forward_steps_uncond(unet, scheduler, xt, num_inference_steps, t_start_idx=0, t_end_idx=-1, performance_boosting=False,
+                              performance_boosting_t_idx=None):
+    """`EditUncondDiffusion.DDIMforwardsteps` (`edit.py:1601-1714`) up to the image save.  Differences from the SD loop that
+    `ddim_forward_steps` follows: the end test comes BEFORE the skip test (`:1638-1645`: `t_end_idx == t_start_idx` returns at
+    once), there is no prompt, and with `performance_boosting` the steps from `performance_boosting_t_idx` on (unless it is the
+    last index) run the stochastic branch, eta = 1 (`:1650-1653`).  A batch is evaluated one image at a time."""
+    scheduler.set_timesteps(num_inference_steps, device="cpu")
+    timesteps = scheduler.timesteps
+    assert (t_start_idx < num_inference_steps) and (t_end_idx <= num_inference_steps)            # edit.py:1617
+    for i, t in enumerate(timesteps):
+        if t_end_idx == i:
+            return xt, t, i
+        elif i < t_start_idx:
+            continue
+        boost = bool(performance_boosting) and performance_boosting_t_idx is not None and \
+            (performance_boosting_t_idx <= i) and (performance_boosting_t_idx != len(timesteps) - 1)
+        eta = 1 if boost else 0
+        et = unet.eps(xt, t)
+        xt = scheduler.step(et, t, xt, eta=eta).prev_sample
+    return xt
+
+
 def _lincomb3(a, x, b, y, c, z, _lib=None):
     """a x + b y + c z through `pb_lincomb3` (one fused elementwise kernel on the tensors' device)."""
     L = _lib if _lib is not None else N.lib()
@@ -146,10 +217,12 @@ def x_space_guidance(unet, scheduler, zt, t_idx, vk, single_edit_step, edit_prom
     `edit_prompt_emb=None`: the unconditional variant, `EditUncondDiffusion.x_space_guidance` (`edit.py:1716-1734`)."""
     t = scheduler.timesteps[t_idx]
     zt_edit = _lincomb3(1.0, zt, single_edit_step, vk.reshape(zt.shape), 0.0, None, _lib)          # zt + step * vk
+    both = torch.cat([zt, zt_edit], dim=0)                     # ONE batch-2 U-Net call like the reference (edit.py:492-497)
     if edit_prompt_emb is None:
-        et_null, et_edit = unet.eps(zt, t), unet.eps(zt_edit, t)
+        et = unet.eps(both, t)
     else:
-        et_null, et_edit = unet.eps(zt, t, edit_prompt_emb), unet.eps(zt_edit, t, edit_prompt_emb)
+        et = unet.eps(both, t, edit_prompt_emb.repeat(both.shape[0] // edit_prompt_emb.shape[0], 1, 1))
+    et_null, et_edit = et.chunk(2)
     return _lincomb3(1.0, zt, x_space_guidance_scale, et_edit, -x_space_guidance_scale, et_null, _lib)
 
 

@@ -49,14 +49,34 @@ class Scheduler:
             self.timesteps, self.timesteps_next = reversed(seq[1:]), reversed(seq_prev[1:])
 
     def step(self, et, t, xt, eta=0.0):
-        """`utils.py:288-315`, deterministic branch (the reference always passes eta = 0): returns (x_next, pred_x0)."""
+        """`utils.py:288-315` (= `YHCustomScheduler.step`, `:1202-1237`, without learned variances): returns (x_next, pred_x0).
+        eta = 0: the deterministic DDIM update; eta != 0: the stochastic branch (one `torch.randn_like(xt)` draw)."""
         t_idx = self.timesteps.tolist().index(t)
         t_next = self.timesteps_next[t_idx]
         at = extract(self.alphas_cumprod, t, xt.shape)
         at_next = extract(self.alphas_cumprod, t_next, xt.shape)
         p_xt = (xt - et * (1 - at).sqrt()) / at.sqrt()
-        assert eta == 0
-        return at_next.sqrt() * p_xt + (1 - at_next).sqrt() * et, p_xt
+        if eta == 0:
+            return at_next.sqrt() * p_xt + (1 - at_next).sqrt() * et, p_xt
+        sigma_t = ((1 - at / (at_next)) * (1 - at_next) / (1 - at)).sqrt()
+        d_xt = (1 - at_next - eta * sigma_t ** 2).sqrt() * et
+        return at_next.sqrt() * p_xt + d_xt + eta * sigma_t * torch.randn_like(xt), p_xt
+
+
+def yh_schedule(noise_schedule="linear", t_max=999, dtype=torch.float32):
+    """`YHCustomScheduler.get_alphas_cumprod` (`utils.py:1247-1286`): (betas, alphas_cumprod) of the unconditional family --
+    'linear': linspace(1e-4, 0.02, 1000) in float64; 'cosine': improved-DDPM over t_max + 1 steps; cumulative product in
+    float64, cast to `dtype` afterwards."""
+    import math
+    if noise_schedule == "linear":
+        betas = torch.linspace(0.0001, 0.02, 1000, dtype=torch.float64)
+    else:
+        timesteps, sc = t_max + 1, 0.008
+        x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
+        ac = torch.cos(((x / timesteps) + sc) / (1 + sc) * math.pi * 0.5) ** 2
+        ac = ac / ac[0]
+        betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    return betas.to(dtype), torch.cumprod(1.0 - betas, dim=0).to(dtype)
 
 
 def _eps(unet, latents, t, ctx, guidance_scale, neg_ctx):
@@ -95,6 +115,26 @@ def ddim_forward_steps(unet, sched: Scheduler, zt, ctx, num_steps, t_start_idx=0
             return latents, t, t_idx
         latents = sched.step(_eps(unet, latents, t, ctx, guidance_scale, neg_ctx), t, latents)[0]
     return latents
+
+
+@torch.no_grad()
+def ddim_forward_steps_uncond(unet, sched: Scheduler, xt, num_steps, t_start_idx=0, t_end_idx=-1, performance_boosting=False,
+                              performance_boosting_t_idx=None):
+    """`EditUncondDiffusion.DDIMforwardsteps` (`edit.py:1601-1714`) without buffering / image saving: the end test precedes the
+    skip test (`:1638-1645`); eta = 1 from `performance_boosting_t_idx` on under `performance_boosting` (`:1650-1653`)."""
+    sched.set_timesteps(num_steps)
+    timesteps = sched.timesteps
+    for i, t in enumerate(timesteps):
+        if t_end_idx == i:
+            return xt, t, i
+        elif i < t_start_idx:
+            continue
+        if performance_boosting and (performance_boosting_t_idx <= i) and (performance_boosting_t_idx != len(timesteps) - 1):
+            eta = 1
+        else:
+            eta = 0
+        xt = sched.step(unet(xt, t), t, xt, eta=eta)[0]
+    return xt
 
 
 @torch.no_grad()

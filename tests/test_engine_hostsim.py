@@ -205,7 +205,8 @@ def test_x_space_guidance_and_cache_format(hostsim, tmp_path):
     import diffusion_pullback_b200 as PB
     from oracle import ddim_oracle as DO
     eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "full", 0, 1, EXACT)
-    fake = types.SimpleNamespace(eps=lambda s, tt, c: eng.set_point(s, float(tt), c, want_h=True))
+    fake = types.SimpleNamespace(eps=lambda s, tt, c: torch.cat([eng.set_point(s[i:i + 1], float(tt), c[i:i + 1], want_h=True)
+                                                                 for i in range(s.shape[0])]))
     hostsim.pb_lincomb3.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
     ac = DO.sd_alphas_cumprod()
     sched, osched = PB.DDIMSchedule(ac, _lib=hostsim), DO.Scheduler(ac)
@@ -266,7 +267,8 @@ def test_uncond_x_space_guidance_on_the_engine(hostsim):
     import diffusion_pullback_b200 as PB
     from oracle import ddim_oracle as DO
     eng, m, x, t, _ = make_engine(hostsim, "uncond_tiny", "full", 0, 1, EXACT)
-    fake = types.SimpleNamespace(eps=lambda s, tt: eng.set_point(s, float(tt), None, want_h=True))
+    fake = types.SimpleNamespace(eps=lambda s, tt: torch.cat([eng.set_point(s[i:i + 1], float(tt), None, want_h=True)
+                                                              for i in range(s.shape[0])]))
     hostsim.pb_lincomb3.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
     ac = torch.cumprod(1.0 - torch.linspace(1e-4, 2e-2, 1000), dim=0)
     sched, osched = PB.DDIMSchedule(ac, _lib=hostsim), DO.Scheduler(ac)
@@ -278,6 +280,46 @@ def test_uncond_x_space_guidance_on_the_engine(hostsim):
     for i in range(2):
         z = DO.x_space_guidance(m, osched, z, 3, vk, 1.5, None, 0.7)
         assert rel(zs[i + 1], z) < 1e-4
+
+
+def test_stochastic_step_yh_scheduler_and_uncond_loop(hostsim):
+    """SURVEY.md s.8f row 1, the unconditional family: `YHCustomScheduler` (utils.py:1171-1286) tables, the eta != 0 branch of
+    `step` (utils.py:306-311; same generator -> same draw as the oracle, which is pinned to the reference), and the uncond
+    forward loop (edit.py:1601-1714: end test before the skip test, eta = 1 under performance boosting) on the engine."""
+    import types
+    import diffusion_pullback_b200 as PB
+    from oracle import ddim_oracle as DO
+    eng, m, x, t, _ = make_engine(hostsim, "uncond_tiny", "full", 0, 1, EXACT)
+    fake = types.SimpleNamespace(eps=lambda s, tt: torch.cat([eng.set_point(s[i:i + 1], float(tt), None, want_h=True)
+                                                              for i in range(s.shape[0])]))
+    hostsim.pb_ddim_step.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    hostsim.pb_lincomb3.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
+    for ns in ("linear", "cosine"):
+        sched = PB.YHCustomScheduler(types.SimpleNamespace(noise_schedule=ns, device="cpu", dtype=torch.float32), _lib=hostsim)
+        betas, ac = DO.yh_schedule(ns)
+        assert torch.equal(sched.betas, betas) and torch.equal(sched.alphas_cumprod, ac) and sched.t_max == 999
+    sched = PB.YHCustomScheduler(_lib=hostsim)                       # noise_schedule None -> 'linear' (utils.py:1175)
+    _, ac = DO.yh_schedule("linear")
+    osched = DO.Scheduler(ac, t_max=999)
+    sched.set_timesteps(8); osched.set_timesteps(8)
+    g = torch.Generator().manual_seed(6)
+    xt, et = torch.randn(2, 3, 16, 16, generator=g), torch.randn(2, 3, 16, 16, generator=g)
+    for eta in (1, 0.3):
+        tt = osched.timesteps[3]
+        torch.manual_seed(2); out = sched.step(et, tt, xt, eta=eta)
+        torch.manual_seed(2); xr, pr = osched.step(et, tt, xt, eta=eta)
+        assert rel(out.prev_sample, xr) < 1e-6 and rel(out.x0, pr) < 1e-6
+    for kw in (dict(t_start_idx=0, t_end_idx=-1), dict(t_start_idx=1, t_end_idx=3), dict(t_start_idx=2, t_end_idx=2),
+               dict(t_start_idx=0, t_end_idx=-1, performance_boosting=True, performance_boosting_t_idx=2)):
+        torch.manual_seed(7); ours = PB.ddim_forward_steps_uncond(fake, sched, x, 5, **kw)
+        torch.manual_seed(7); ref = DO.ddim_forward_steps_uncond(m, DO.Scheduler(ac, t_max=999), x, 5, **kw)
+        if isinstance(ref, tuple):
+            assert ours[2] == ref[2] and float(ours[1]) == float(ref[1]) and rel(ours[0], ref[0]) < 1e-4
+        else:
+            assert rel(ours, ref) < 1e-4
+    sched.learn_sigma = True
+    with pytest.raises(NotImplementedError):
+        sched.step(et, osched.timesteps[3], xt)
 
 
 def test_probe_bookkeeping_and_dump(hostsim, tmp_path, monkeypatch):

@@ -237,3 +237,77 @@ def test_uncond_x_space_guidance_restatement_matches_verbatim_reference():
     ref = E.EditUncondDiffusion.x_space_guidance(me, xt, 3, vk, 1.5)
     ours = DO.x_space_guidance(m, s, xt, 3, vk, 1.5, None, 0.7)
     assert torch.equal(ref, ours)
+
+
+# ---- stochastic step, YHCustomScheduler and the unconditional loop: the restatements against the reference run verbatim ----
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+def test_stochastic_step_restatement_matches_verbatim_reference():
+    """eta != 0 (`utils.py:306-311`): same generator state -> the same `torch.randn_like` draw -> bit-identical x_next."""
+    from oracle import ddim_oracle as DO
+    U = RS.load()
+    ac = DO.sd_alphas_cumprod()
+    ref = types.SimpleNamespace(t_max=999.0, alphas_cumprod=ac)
+    ref.set_timesteps = types.MethodType(U.set_timesteps, ref)
+    ref.step = types.MethodType(U.step, ref)
+    ours = DO.Scheduler(ac)
+    ref.set_timesteps(9); ours.set_timesteps(9)
+    g = torch.Generator().manual_seed(5)
+    xt, et = torch.randn(2, 3, 8, 8, generator=g), torch.randn(2, 3, 8, 8, generator=g)
+    for eta in (1, 0.5):
+        for t in list(ref.timesteps)[1:-1]:
+            torch.manual_seed(11); out = ref.step(et, t, xt, eta=eta)
+            torch.manual_seed(11); x2, p2 = ours.step(et, t, xt, eta=eta)
+            assert torch.equal(out.prev_sample, x2) and torch.equal(out.x0, p2)
+
+
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+@pytest.mark.parametrize("noise_schedule", [None, "linear", "cosine"])
+def test_yh_scheduler_restatement_matches_verbatim_reference(noise_schedule):
+    """`YHCustomScheduler` (`utils.py:1171-1286`): SNR tables, timesteps and both step branches against the class itself."""
+    from oracle import ddim_oracle as DO
+    U = RS.load()
+    args = types.SimpleNamespace(noise_schedule=noise_schedule, device="cpu", dtype=torch.float32)
+    ref = U.YHCustomScheduler(args)
+    betas, ac = DO.yh_schedule("linear" if noise_schedule is None else noise_schedule)
+    assert torch.equal(torch.as_tensor(ref.betas), betas) and torch.equal(torch.as_tensor(ref.alphas_cumprod), ac)
+    ours = DO.Scheduler(ac, t_max=999)
+    ref.set_timesteps(7); ours.set_timesteps(7)
+    assert torch.equal(torch.as_tensor(list(ref.timesteps)), torch.as_tensor(list(ours.timesteps)))
+    g = torch.Generator().manual_seed(1)
+    xt, et = torch.randn(1, 3, 8, 8, generator=g), torch.randn(1, 3, 8, 8, generator=g)
+    for eta in (0, 1):
+        t = list(ref.timesteps)[2]
+        torch.manual_seed(4); out = ref.step(et, t, xt, eta=eta)
+        torch.manual_seed(4); x2, p2 = ours.step(et, t, xt, eta=eta)
+        assert torch.equal(out.prev_sample, x2) and torch.equal(out.x0, p2)
+
+
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+@pytest.mark.parametrize("kw", [dict(t_start_idx=0, t_end_idx=-1), dict(t_start_idx=1, t_end_idx=3), dict(t_start_idx=2, t_end_idx=2),
+                                dict(t_start_idx=0, t_end_idx=-1, performance_boosting=True)])
+def test_uncond_forward_loop_restatement_matches_verbatim_reference(kw, tmp_path):
+    """oracle `ddim_forward_steps_uncond` against `EditUncondDiffusion.DDIMforwardsteps` (edit.py:1601-1714) run verbatim on a
+    stand-in self: end-before-skip ordering, eta = 1 under performance boosting."""
+    from oracle import ddim_oracle as DO
+    RS.load()
+    import modules.edit as E
+    m = UT.build_unet("uncond_tiny")
+    xt, _, _ = UT.synthetic_inputs("uncond_tiny")
+    _, ac = DO.yh_schedule("linear")
+    s_ref, s_our = DO.Scheduler(ac, t_max=999), DO.Scheduler(ac, t_max=999)
+    s_ref_step = s_ref.step
+    s_ref.step = lambda et, t, x, eta=0.0, **k: types.SimpleNamespace(prev_sample=s_ref_step(et, t, x, eta=eta)[0])
+    me = types.SimpleNamespace(for_steps=5, use_yh_custom_scheduler=True, scheduler=s_ref, device="cpu", dtype=torch.float32,
+                               buffer_device="cpu", memory_bound=5, performance_boosting_t_idx=2, unet=lambda x, t: m(x, t),
+                               result_folder=str(tmp_path), obs_folder=str(tmp_path), EXP_NAME="t")
+    pb = kw.get("performance_boosting", False)
+    torch.manual_seed(3)
+    ref = E.EditUncondDiffusion.DDIMforwardsteps(me, xt.clone(), kw["t_start_idx"], kw["t_end_idx"], save_image=False,
+                                                 performance_boosting=pb)
+    torch.manual_seed(3)
+    ours = DO.ddim_forward_steps_uncond(m, s_our, xt.clone(), 5, kw["t_start_idx"], kw["t_end_idx"], performance_boosting=pb,
+                                        performance_boosting_t_idx=2)
+    if isinstance(ref, tuple):
+        assert isinstance(ours, tuple) and ref[2] == ours[2] and float(ref[1]) == float(ours[1]) and torch.equal(ref[0], ours[0])
+    else:
+        assert torch.equal(ref, ours)

@@ -258,6 +258,40 @@ def test_full_uncond_unet_eps_and_ddim_vs_oracle():
         assert rel(zs[i + 1], zo) < 1e-2
 
 
+def test_uncond_scheduler_stochastic_step_and_loop_order():
+    """`YHCustomScheduler` on the device: the eta != 0 branch of `step` (utils.py:306-311) draws from the CUDA generator like the
+    reference's `torch.randn_like(xt)` (same seed -> same z as the oracle formula evaluated on the device), a batch of two; and the
+    uncond forward loop's ordering (edit.py:1638-1645: the end test precedes the skip test) against the oracle on the CPU."""
+    from oracle import ddim_oracle as DO
+    name = "uncond_tiny"
+    m = UT.build_unet(name)
+    unet = PB.patch_unet(SY.SyntheticUNet(name, device=DEV))
+    x, t, _ = SY.synthetic_inputs(name, device=DEV)
+    sched = PB.YHCustomScheduler()
+    _, ac = DO.yh_schedule("linear")
+    assert torch.equal(sched.alphas_cumprod, ac)
+    osched = DO.Scheduler(ac.to(DEV), t_max=999)
+    sched.set_timesteps(8); osched.set_timesteps(8)
+    g = torch.Generator().manual_seed(6)
+    xt, et = torch.randn(2, *x.shape[1:], generator=g).to(DEV), torch.randn(2, *x.shape[1:], generator=g).to(DEV)
+    for eta in (1, 0.3):
+        tt = osched.timesteps[3]
+        torch.manual_seed(2); out = sched.step(et, tt, xt, eta=eta)
+        torch.manual_seed(2); xr, pr = osched.step(et, tt, xt, eta=eta)
+        assert rel(out.prev_sample, xr) < 1e-6 and rel(out.x0, pr) < 1e-6
+    for kw in (dict(t_start_idx=1, t_end_idx=3), dict(t_start_idx=2, t_end_idx=2), dict(t_start_idx=0, t_end_idx=-1)):
+        ours = PB.ddim_forward_steps_uncond(unet, sched, x, 5, **kw)
+        ref = DO.ddim_forward_steps_uncond(m, DO.Scheduler(ac, t_max=999), x.cpu(), 5, **kw)
+        if isinstance(ref, tuple):
+            assert ours[2] == ref[2] and float(ours[1]) == float(ref[1]) and rel(ours[0], ref[0]) < 2e-2
+        else:
+            assert rel(ours, ref) < 2e-2
+    # performance boosting switches to eta = 1 from index 2 on: different from the deterministic run, finite, same shape
+    torch.manual_seed(1)
+    zb = PB.ddim_forward_steps_uncond(unet, sched, x, 5, performance_boosting=True, performance_boosting_t_idx=2)
+    assert zb.shape == x.shape and torch.isfinite(zb).all() and rel(zb, ours) > 1e-3
+
+
 def ddim_alphas():
     betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2     # SD `scaled_linear`
     return torch.cumprod(1.0 - betas, dim=0)
