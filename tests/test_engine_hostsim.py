@@ -239,6 +239,19 @@ def test_x_space_guidance_and_cache_format(hostsim, tmp_path):
     u2, s2, v2 = PB.load_or_compute_local_basis(types.SimpleNamespace(local_encoder_pullback_zt=pullback), x, t, ctx, d, name, "mid", 0, 5)
     assert len(calls) == 1 and s2 is None and torch.equal(u1, u2) and torch.equal(v1, v2)           # cache hit: no recompute
     assert torch.equal(torch.load(sp), s1)
+    # the two pictures of a fresh computation (edit.py:249-263): the spectrum plot next to the tensors, the PCA view of vT
+    assert os.path.getsize(os.path.join(d, f"eigenvalue_spectrum-{name}.png")) > 500
+    name2 = PB.local_basis_name("Examples", 1, 0.7, "a photo", "mid", 0, 0)
+    n_in = x[0].numel()
+    pb2 = lambda sample, timestep, encoder_hidden_states, op, block_idx, pca_rank, **kw: (
+        torch.randn(12, pca_rank), torch.rand(pca_rank), torch.randn(pca_rank, n_in))
+    PB.load_or_compute_local_basis(types.SimpleNamespace(local_encoder_pullback_zt=pb2), x, t, ctx, d, name2, "mid", 0, 5,
+                                   obs_folder=str(tmp_path / "obs"))
+    from PIL import Image
+    im = Image.open(tmp_path / "obs" / f"vT-{name2}.png")
+    assert im.size[0] >= 5 * x.shape[-1] and im.mode == "RGB"
+    vis = PB.visualize_vT(torch.randn(3, n_in), tuple(x.shape[1:]))
+    assert vis.shape == (3, 3, *x.shape[2:]) and float(vis.min()) == 0.0 and float(vis.max()) == 1.0
 
 
 def test_full_uncond_unet_eps_matches_oracle(hostsim):

@@ -258,6 +258,32 @@ def test_full_uncond_unet_eps_and_ddim_vs_oracle():
         assert rel(zs[i + 1], zo) < 1e-2
 
 
+def test_local_basis_cache_round_trip_on_the_device(tmp_path):
+    """SURVEY.md s.8f row 3 on the GPU (edit.py:218-268): a fresh computation through the patched U-Net writes u- / s- / vT-<name>.pt
+    (+ the spectrum plot and the PCA picture of vT), a second call re-uses the files without running the pullback, the loaded
+    tensors are the saved ones normalised, and the files load on the CPU like an unmodified reference run would read them."""
+    unet = PB.patch_unet(SY.SyntheticUNet("sd_small", upto=("mid", 0), device=DEV))
+    x, t, ctx = SY.synthetic_inputs("sd_small", device=DEV)
+    name = PB.local_basis_name("Examples", 0, 0.7, "a photo", "mid", 0, 0)
+    d = PB.local_basis_dir("Examples", 100, 3, root=str(tmp_path))
+    torch.manual_seed(0)
+    u1, s1, v1 = PB.load_or_compute_local_basis(unet, x, t, ctx, d, name, "mid", 0, 3, min_iter=2, max_iter=4, obs_folder=str(tmp_path / "obs"))
+    up, sp, vp = PB.local_basis_paths(d, name)
+    assert all(os.path.exists(p) for p in (up, sp, vp))
+    assert os.path.exists(os.path.join(d, f"eigenvalue_spectrum-{name}.png")) and os.path.exists(tmp_path / "obs" / f"vT-{name}.png")
+    assert u1.device.type == "cuda" and v1.shape == (3, x[0].numel()) and s1.shape == (3,)
+    assert torch.allclose(u1.norm(dim=0), torch.ones(3, device=DEV), atol=1e-5) and torch.allclose(v1.norm(dim=1), torch.ones(3, device=DEV), atol=1e-5)
+    calls = []
+    orig = unet.local_encoder_pullback_zt
+    unet.local_encoder_pullback_zt = lambda **kw: calls.append(kw) or orig(**kw)
+    u2, s2, v2 = PB.load_or_compute_local_basis(unet, x, t, ctx, d, name, "mid", 0, 3)
+    assert not calls and s2 is None and torch.equal(u1, u2) and torch.equal(v1, v2)
+    su, ss, sv = (torch.load(p, map_location="cpu") for p in (up, sp, vp))
+    assert su.shape == (u1.shape[0], 3) and sv.shape == v1.shape and torch.equal(ss.cpu(), s1.cpu())
+    un, vn = PB.normalize_basis(su, sv)
+    assert torch.allclose(un, u1.cpu(), atol=1e-6) and torch.allclose(vn, v1.cpu(), atol=1e-6)
+
+
 def test_uncond_scheduler_stochastic_step_and_loop_order():
     """`YHCustomScheduler` on the device: the eta != 0 branch of `step` (utils.py:306-311) draws from the CUDA generator like the
     reference's `torch.randn_like(xt)` (same seed -> same z as the oracle formula evaluated on the device), a batch of two; and the
