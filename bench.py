@@ -238,6 +238,78 @@ def run_reference(args, wl):
     emit(line)
 
 
+def run_secondary(dev, rank, world):
+    """BASELINE.json configs[3] -- SD-v1.5 mid-block, pca_rank 16, 50 power iterations, 10 edit timesteps -- on the `world` GPUs of
+    this job through the MIXED schedule of sharding.plan_rounds: full rounds of one problem per GPU, the left-over problems split
+    over groups of GPUs by tangent columns (SURVEY.md s.8e secondary partitioning; one all-gather of the W rows per iteration
+    inside a group), one closing all-gather of (s, vT).  With one GPU: the ten problems one after the other -- the denominator
+    of the scaling the driver computes from the per-N records.  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    import diffusion_pullback_b200 as PB
+    from diffusion_pullback_b200 import synthetic as SY
+    from diffusion_pullback_b200.sharding import gather_results, make_round_groups, plan_rounds, solve_rounds
+    model_name, op, bi, k, iters, nprob = "sd15", "mid", 0, 16, 50, 10
+    unet = SY.SyntheticUNet(model_name, upto=(op, bi), device=dev)
+    cfg = PB.unet_config(unet)
+    size, ctx_len = unet.config["sample_size"], unet.config["ctx_len"]
+    eng = PB.PullbackEngine(cfg, size, size, op, bi, k, ctx_len, dev)
+    eng.bind(unet.state_dict())
+    unet._sd = None
+    torch.cuda.empty_cache()
+    _, _, ctx = SY.synthetic_inputs(model_name)
+    ctxd = ctx.to(dev)
+    # ten edit timesteps of one image (0.95 T ... 0.5 T) with the latent each of them is reached at (synthetic)
+    ts = [999.0 * (0.95 - 0.05 * i) for i in range(nprob)]
+    xs = [torch.randn(1, cfg["in_channels"], size, size, generator=torch.Generator().manual_seed(4321 + i)).to(dev) for i in range(nprob)]
+    v0 = {}
+
+    def v0_of(i):
+        if i not in v0:
+            q, _ = torch.linalg.qr(torch.randn(eng.n_in, k, generator=torch.Generator().manual_seed(99 + i)))
+            v0[i] = q.T.contiguous().to(dev)
+        return v0[i]
+
+    plan = plan_rounds(nprob, world)
+    groups = make_round_groups(plan) if world > 1 else {}
+    for i in range(nprob):
+        v0_of(i)
+    # warm-up: every code path this rank will take (graph capture of the iteration, of the stand-alone jvp / vjp at the group's
+    # column count), two iterations each
+    warm = [[(idx, ranks) for idx, ranks in rnd if rank in ranks][:1] for rnd in plan]
+    seen = set()
+    for rnd in warm:
+        for idx, ranks in rnd:
+            if len(ranks) in seen:
+                continue
+            seen.add(len(ranks))
+            solve_rounds(eng, [[(idx, ranks)]], groups, rank, lambda i: eng.set_point(xs[i], ts[i], ctxd), v0_of, 2, 2, 0.0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    local = solve_rounds(eng, plan, groups, rank, lambda i: eng.set_point(xs[i], ts[i], ctxd), v0_of, iters, iters, 0.0)
+    allr = gather_results(local, nprob, k, eng.n_in, dev) if world > 1 else {i: (s_, v_) for i, s_, v_ in local}
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm)
+    assert sorted(allr) == list(range(nprob))
+    del eng
+    torch.cuda.empty_cache()
+    return {"workload": "sd15_mid_k16_i50 x 10 edit timesteps (BASELINE.json configs[3])", "value": nprob * iters / (ms / 1e3), "unit": UNIT,
+            "seconds": ms / 1e3, "n_gpus": world, "problems": nprob, "pca_rank": k, "power_iters": iters,
+            "schedule": [[[idx, list(ranks)] for idx, ranks in rnd] for rnd in plan],
+            "collectives": "one all-gather of the W rows (k x n_in fp32 = 1.0 MB) per iteration inside a tangent group (NCCL), "
+                           "one all-gather of (s, vT) of the ten problems at the end",
+            "sigma_max_first_problem": float(allr[0][0][0])}
+
+
 def run_ours(args, wl):
     import torch.distributed as dist
     import diffusion_pullback_b200 as PB
@@ -421,6 +493,12 @@ def run_ours(args, wl):
         prof = pe.profile_read()
         prof["_eager_ms_per_iter"] = pe0.elapsed_time(pe1) / prof_iters
 
+    secondary = None
+    if wl == "sd15_mid_k5_i50" and not tangent and not args.no_secondary:
+        del eng, engS
+        torch.cuda.empty_cache()
+        secondary = run_secondary(dev, rank, world)
+
     if rank == 0:
         pk_all = peaks()
         peak_tf, peak_burst, peak_hbm, peak_src = pk_all["sustained"], pk_all["burst"], pk_all["hbm"], pk_all["source"]
@@ -472,6 +550,8 @@ def run_ours(args, wl):
                                      "half of the bf16 peak used as denominator), fp32 accumulation; step_* = algorithmic "
                                      "flops of one whole step (50 x 2 k F_tan + primal, BASELINE.md s.3) / device time of the step; traffic = "
                                      "DRAM bytes per launch (ncu, profiles/); peak = " + peak_src}}
+        if secondary is not None:
+            line["secondary"] = secondary
         if world == 1 and not args.no_ref_gpu:
             # the reference algorithm on THIS GPU (torch eager autograd), one iteration at the workload's rank: the anchor of the
             # north star's ">= 20x the reference's single-GPU wall clock" (A100-equivalent taken as r = 1)
@@ -504,6 +584,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sd15_mid_k5_i50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the `secondary` record (BASELINE configs[3]: rank 16, 10 timesteps, mixed schedule)")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-on-this-GPU leg (torch eager autograd, 1 iteration)")
     ap.add_argument("--slots", type=int, default=0,
                     help="problem slots (pb_set_slots): each step solves this many independent problems as ONE tangent batch "

@@ -513,7 +513,10 @@ const char* gemm_call(pb_handle* h, PbGemm& g, pb_stream st) {
 // fused attention linearisation: S (nseg products over the head dim) + T . C1 per (tangent, head)
 const char* attn_lin_call(pb_handle* h, PbAttnLin& a, pb_stream st) {
   if (h->slots > 1 && h->t16) { a.k_slot = a.nb / h->slots; a.p_stride = (long)h->cache_stride; }   // every problem in one launch
-  const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * (a.nseg + 1 + (a.C2 ? 1 : 0)) * a.nb * a.nh;
+  // algorithmic products only: the score product of the VJP-B launch (column deltas) recomputes, transposed, the O-bar V^T of
+  // the VJP-A launch -- work of this implementation, not of the algorithm -- and is not counted
+  const int nprod = (a.delta && a.delta_mode == 2 ? 0 : a.nseg) + 1 + (a.C2 ? 1 : 0);
+  const double flops = 2.0 * a.Mr * a.Nc * (double)a.d * nprod * a.nb * a.nh;
   if (h->profiling) {
     char b[160];
     snprintf(b, sizeof b, "attn Mr=%d Nc=%d d=%d nseg=%d c2=%d nb=%d nh=%d", a.Mr, a.Nc, a.d, a.nseg, a.C2 ? 1 : 0, a.nb, a.nh);

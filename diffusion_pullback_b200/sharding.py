@@ -115,3 +115,51 @@ def pullback_tangent_sharded(eng, V0, min_iter: int, max_iter: int, tol: float, 
     info = N.PbIterInfo()
     info.iters_done, info.converged, info.last_dist = done, int(converged), last
     return u, s, V, info
+
+
+def plan_rounds(n_problems: int, world: int):
+    """Mixed partitioning of P problems over N ranks (both partitionings in one schedule): full rounds of one
+    problem per rank, then the P mod N left-over problems each split over N // (P mod N) ranks by tangent columns, so that no
+    GPU idles through a whole round.  Returns a list of rounds, each a list of (problem index, tuple of ranks).
+    10 problems on 8 GPUs: [[(0, (0,)), ..., (7, (7,))], [(8, (0, 1, 2, 3)), (9, (4, 5, 6, 7))]]."""
+    rounds, p = [], 0
+    while n_problems - p >= world:
+        rounds.append([(p + r, (r,)) for r in range(world)])
+        p += world
+    left = n_problems - p
+    if left > 0:
+        g = world // left
+        rounds.append([(p + j, tuple(range(j * g, (j + 1) * g))) for j in range(left)])
+    return rounds
+
+
+def make_round_groups(plan):
+    """torch.distributed groups of the multi-rank entries of a `plan_rounds` schedule ({ranks: group}); collective: every rank
+    calls it with the same plan."""
+    groups = {}
+    for rnd in plan:
+        for _, ranks in rnd:
+            if len(ranks) > 1 and ranks not in groups:
+                groups[ranks] = dist.new_group(list(ranks))
+    return groups
+
+
+@torch.no_grad()
+def solve_rounds(eng, plan, groups, rank: int, set_point, v0_of, min_iter: int, max_iter: int, tol: float):
+    """Run a `plan_rounds` schedule on this rank: `set_point(i)` sets problem i on `eng`, `v0_of(i)` is its start subspace
+    [k, n_in] (identical on every rank of a group).  Returns [(problem index, s, vT)] for the problems this rank solved or
+    co-solved as the FIRST rank of its group (so that a later `gather_results` sees each problem once)."""
+    out = []
+    for rnd in plan:
+        for idx, ranks in rnd:
+            if rank not in ranks:
+                continue
+            set_point(idx)
+            if len(ranks) == 1:
+                u, s, vT, info = eng.pullback(v0_of(idx), min_iter, max_iter, tol)
+                out.append((idx, s, vT))
+            else:
+                u, s, vT, info = pullback_tangent_sharded(eng, v0_of(idx), min_iter, max_iter, tol, groups[ranks])
+                if rank == ranks[0]:
+                    out.append((idx, s, vT))
+    return out
