@@ -645,6 +645,12 @@ bool use_fused_cross(const pb_handle* h, const Op& o) {
 // element offset into a tangent buffer that holds floats (es = 4) or halves (es = 2)
 inline float* el(const void* p, long n, int es) { return reinterpret_cast<float*>(const_cast<char*>(static_cast<const char*>(p)) + n * es); }
 
+// problem slots inside the materialised attention path (all-fp16 plan): the primal operands of its GEMMs (batch stride 0: K, V,
+// P, their transposes) are indexed by the tangent's problem, b / k_slot, so one launch covers every slot
+inline void slot_gemm(const pb_handle* h, PbGemm& g) {
+  if (h->slots > 1 && h->t16 && g.nb > 1) { g.k_slot = g.nb / h->slots; g.p_stride = (long)h->cache_stride; }
+}
+
 int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   const int hd = o.heads, d = o.d, C = hd * d, N = o.Nq, Nk = o.Nk, ldk = o.ldk;
   float* P = h->CP(o.P_off); float* Vt = h->CP(o.Vt_off);
@@ -706,7 +712,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(dx, C, N, kv, 2 * C, Nk, d, dS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   } else {
     const float* qkv = h->P(o.x); const float* dqkv = dx;
     PbGemm g = plain_gemm(dqkv, 3 * C, N, qkv + C, 3 * C, Nk, d, dS, ldk);       // dQ K^T
@@ -715,9 +721,9 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     g.seg[1].A = qkv; g.seg[1].lda = 3 * C; g.seg[1].sAb = 0; g.seg[1].sAh = d;
     g.seg[1].B = dqkv + C; g.seg[1].ldb = 3 * C; g.seg[1].sBb = (long)N * 3 * C; g.seg[1].sBh = d; g.seg[1].K = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd; g.alpha = o.scale;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
-  CK(pbk_softmax_lin(P, (long)hd * N, dS, nb, Nk, ldk, h->rnd, st));
+  CK(pbk_softmax_lin(P, (long)hd * N, dS, nb, Nk, ldk, h->rnd, h->ks(nb), h->pstride_f(), st));
   PbGemm g = plain_gemm(dS, ldk, N, Vt, ldk, d, Nk, h->T(o.y), C);                // dP V
   g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
   g.sDb = (long)N * C; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = h->rnd;
@@ -730,7 +736,7 @@ int run_attn_jvp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     g.seg[1].A = P; g.seg[1].lda = ldk; g.seg[1].sAb = 0; g.seg[1].sAh = (long)N * ldk;
     g.seg[1].B = dVt; g.seg[1].ldb = ldk; g.seg[1].sBb = (long)C * ldk; g.seg[1].sBh = (long)d * ldk; g.seg[1].K = Nk;
   }
-  g.precise = h->prec_a; CK(gemm_call(h, g, st));
+  g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   return PB_OK;
 }
 
@@ -797,16 +803,16 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
     PbGemm g = plain_gemm(gO, C, N, V, ldkv, Nk, d, gS, ldk);
     g.seg[0].sAb = (long)N * C; g.seg[0].sAh = d; g.seg[0].sBh = d;
     g.sDb = sS; g.sDh = (long)N * ldk; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
-  CK(pbk_softmax_lin(P, (long)hd * N, gS, nb, Nk, ldk, h->rnd, st));              // gS = P o (dP - rowsum(P o dP))
+  CK(pbk_softmax_lin(P, (long)hd * N, gS, nb, Nk, ldk, h->rnd, h->ks(nb), h->pstride_f(), st));              // gS = P o (dP - rowsum(P o dP))
   const long ldx = o.cross ? C : 3 * C;
   float* gx = h->T(o.x);
   {                                                                                // gQ = scale gS K
     PbGemm g = plain_gemm(gS, ldk, N, Kt, ldk, d, Nk, gx, ldx);
     g.seg[0].sAb = sS; g.seg[0].sAh = (long)N * ldk; g.seg[0].sBh = (long)d * ldk;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
   h->vals[o.x].ginit = true;
   if (o.cross) return PB_OK;
@@ -814,26 +820,26 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   float* Pt = h->CP(o.Pt_off); float* Qt = h->CP(o.Qt_off);
   float* gSt = h->WP(h->w_s2); float* delta = h->WP(h->w_delta); float* gOt = h->WP(h->w_s3);
   const long sSt = (long)hd * Nk * ldq;
-  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, 0, 0, 0, st));
+  CK(pbk_attn_delta(gO, C, h->P(o.y), C, nb, N, hd, d, delta, 0, h->ks(nb), h->pstride_f(), st));
   {                                                                                // dP^T = V gO^T
     PbGemm g = plain_gemm(V, ldkv, Nk, gO, C, N, d, gSt, ldq);
     g.seg[0].sAh = d; g.seg[0].sBb = (long)N * C; g.seg[0].sBh = d;
     g.sDb = sSt; g.sDh = (long)Nk * ldq; g.nb = nb; g.nh = hd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
-  CK(pbk_attn_ds(Pt, gSt, delta, 1.f, nb, hd, Nk, N, ldq, 1, h->rnd, st));        // gS^T = P^T o (dP^T - delta_i)
+  CK(pbk_attn_ds(Pt, gSt, delta, 1.f, nb, hd, Nk, N, ldq, 1, h->rnd, h->ks(nb), h->pstride_f(), st));        // gS^T = P^T o (dP^T - delta_i)
   {                                                                                // gK = scale gS^T Q
     PbGemm g = plain_gemm(gSt, ldq, Nk, Qt, ldq, d, N, el(gx, C, es), ldx);
     g.seg[0].sAb = sSt; g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBh = (long)d * ldq;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.alpha = o.scale; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
   CK(pbk_transpose(gOt, ldq, (long)C * ldq, (long)d * ldq, gO, C, (long)N * C, d, nb, hd, N, d, 0.f, h->rnd, st));
   {                                                                                // gV = P^T gO
     PbGemm g = plain_gemm(Pt, ldq, Nk, gOt, ldq, d, N, el(gx, 2 * C, es), ldx);
     g.seg[0].sAh = (long)Nk * ldq; g.seg[0].sBb = (long)C * ldq; g.seg[0].sBh = (long)d * ldq;
     g.sDb = (long)N * ldx; g.sDh = d; g.nb = nb; g.nh = hd; g.round_tf32 = t16 ? 0 : h->rnd; g.d_dtype = dd;
-    g.precise = h->prec_a; CK(gemm_call(h, g, st));
+    g.precise = h->prec_a; slot_gemm(h, g); CK(gemm_call(h, g, st));
   }
   return PB_OK;
 }
@@ -919,10 +925,10 @@ int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h
 
 // ops that read primal quantities (normalisation statistics, activation arguments, attention probabilities): with several
 // problem slots they run once per slot; everything else (weight GEMMs, data movement) takes all slots in one launch
-// ... except in the all-fp16 plan, whose kernels index the primal tensors per image (b / k_slot): there only the
-// materialised attention path (few tokens) still runs slot by slot
+// ... except in the all-fp16 plan, whose kernels index the primal tensors per image (b / k_slot), the GEMMs of the
+// materialised attention path included (PbGemm::k_slot)
 bool per_slot_op(const pb_handle* h, const Op& o) {
-  if (h->t16) return o.kind == OP_ATTN && !(use_fused(h, o) || use_fused_cross(h, o));
+  if (h->t16) return false;                  // every kernel of the all-fp16 plan indexes the primal tensors per image (b / k_slot)
   return o.kind == OP_GN || o.kind == OP_LN || o.kind == OP_GEGLU || o.kind == OP_ATTN;
 }
 

@@ -53,6 +53,7 @@ struct alignas(64) Params {
   int kblocks[2];                      // ceil(K_seg / 32)
   uint32_t tx_bytes[2];                // bytes one stage's A+B boxes deliver (boxes are clamped to the tensor)
   int a_bmul[2], a_hmul[2], b_bmul[2], b_hmul[2], d_bmul, d_hmul;
+  int a_bdiv[2], b_bdiv[2];            // problem slots: a primal operand's batch coordinate is bat_b / bdiv (0: bat_b * bmul)
   int nseg, taps, conv_ctot;
   int M, N, nb, nh;
   int conv, H, W, bw, bh, bb, tiles_w, tiles_h;
@@ -277,8 +278,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             // filter as a (channel, tap, out-channel) tensor: a k-block running past the channel count is zero-filled
             tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, tap, t.n0, 0);
           } else {
-            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.m0, t.bat_h * p.a_hmul[s], t.bat_b * p.a_bmul[s]);
-            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, t.n0, t.bat_h * p.b_hmul[s], t.bat_b * p.b_bmul[s]);
+            const int ca = p.a_bdiv[s] ? t.bat_b / p.a_bdiv[s] : t.bat_b * p.a_bmul[s];
+            const int cb = p.b_bdiv[s] ? t.bat_b / p.b_bdiv[s] : t.bat_b * p.b_bmul[s];
+            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.m0, t.bat_h * p.a_hmul[s], ca);
+            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, t.n0, t.bat_h * p.b_hmul[s], cb);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -647,10 +650,18 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       p.tx_bytes[s] = uint32_t(p.bw * p.bh * p.bb + brow) * 128;
     } else {
       uint32_t abytes, bbytes;
-      err = encode_plainx(&p.mapA[s], sg.A, ab16, g.M, sg.K, sg.lda, sg.sAh, g.nh, sg.sAb, g.nb, KB, BM, 128, &p.a_hmul[s],
+      // problem slots: a primal (batch-broadcast) operand gets the problem index as its batch axis
+      const int kslot = (g.k_slot > 0 && g.k_slot < g.nb) ? g.k_slot : 0;
+      const int nslots = kslot ? g.nb / kslot : 1;
+      if (kslot && (g.nb % kslot || g.p_stride <= 0 || g.p_stride % 16)) return "gemm: problem slots need nb % k_slot == 0 and a positive p_stride multiple of 16 bytes";
+      long sAb = sg.sAb, sBb = sg.sBb;
+      int nbA = g.nb, nbB = g.nb;
+      if (nslots > 1 && sAb == 0) { sAb = g.p_stride / (long)aes; nbA = nslots; p.a_bdiv[s] = kslot; }
+      if (nslots > 1 && sBb == 0) { sBb = g.p_stride / (long)aes; nbB = nslots; p.b_bdiv[s] = kslot; }
+      err = encode_plainx(&p.mapA[s], sg.A, ab16, g.M, sg.K, sg.lda, sg.sAh, g.nh, sAb, nbA, KB, BM, 128, &p.a_hmul[s],
                           &p.a_bmul[s], &abytes);
       if (err) return err;
-      err = encode_plainx(&p.mapB[s], sg.B, ab16, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sg.sBb, g.nb, KB, BN, 128, &p.b_hmul[s],
+      err = encode_plainx(&p.mapB[s], sg.B, ab16, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sBb, nbB, KB, BN, 128, &p.b_hmul[s],
                           &p.b_bmul[s], &bbytes);
       if (err) return err;
       p.tx_bytes[s] = abytes + bbytes;

@@ -817,14 +817,14 @@ __global__ void softmax_fwd_k(float* __restrict__ Sm, long rows, int cols, long 
 
 template <int NT>
 __global__ void softmax_lin_k(const float* __restrict__ P, long rows_p, float* __restrict__ dS, long rows, int cols,
-                              long ld, int rnd) {
+                              long ld, int rnd, int k_slot, long p_stride) {
   __shared__ float sh[8];
   const int tid = NT == 32 ? (threadIdx.x & 31) : threadIdx.x;
   const long row0 = NT == 32 ? (blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5)) : blockIdx.x;
   const long rstep = NT == 32 ? (long)gridDim.x * (blockDim.x >> 5) : gridDim.x;
   const int cols4 = (cols + 3) / 4;               // ld % 4 == 0 and ld >= cols, so float4 loads stay in the row
   for (long r = row0; r < rows; r += rstep) {
-    const float4* pp = reinterpret_cast<const float4*>(P + (r % rows_p) * ld);
+    const float4* pp = reinterpret_cast<const float4*>(P + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * ld);
     float4* dp = reinterpret_cast<float4*>(dS + r * ld);
     float4 pc[4], dc[4];
     float dot = 0.f;
@@ -888,7 +888,7 @@ __global__ void attn_delta_k(const float* __restrict__ go, long ldg, const float
   }
 }
 __global__ void attn_ds_k(const float* __restrict__ P, float* __restrict__ dP, const float* __restrict__ delta,
-                          float scale, int nb, int H, int rows, int cols, long ld, int col_mode, int rnd) {
+                          float scale, int nb, int H, int rows, int cols, long ld, int col_mode, int rnd, int k_slot, long p_stride4) {
   const long ld4 = ld / 4;
   const long per_b = (long)H * rows * ld4;
   const long total = (long)nb * per_b;
@@ -898,7 +898,7 @@ __global__ void attn_ds_k(const float* __restrict__ P, float* __restrict__ dP, c
     const long rr = i / ld4;                  // (b*H + h)*rows + r
     const int r = int(rr % rows);
     const long bh = rr / rows;
-    const float4 p = reinterpret_cast<const float4*>(P)[i % per_b];
+    const float4 p = reinterpret_cast<const float4*>(P)[((i / per_b) / k_slot) * p_stride4 + i % per_b];
     float4 v = reinterpret_cast<float4*>(dP)[i];
     const float* dl = delta + bh * ndelta;
     float d0, d1, d2, d3;
@@ -1418,12 +1418,14 @@ PBK pbk_softmax_fwd(float* Sm, long rows, int cols, long ld, int round_tf32, pb_
   else softmax_fwd_k<256><<<(unsigned)std::min<long>(rows, kSMs * 16), 256, 0, S(st)>>>(Sm, rows, cols, ld, round_tf32);
   return last_err();
 }
-PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32,
-                    pb_stream st) {
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32, int k_slot,
+                    long p_stride, pb_stream st) {
   CHECK_ALIGN4(ld, "softmax_lin: ld");
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  if (p_stride % 4) return "softmax_lin: p_stride must be a multiple of 4 floats";
   const long rows = rows_p * nb;
-  if (cols <= 512) softmax_lin_k<32><<<grid_for(rows, 8, 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32);
-  else softmax_lin_k<256><<<(unsigned)std::min<long>(rows, kSMs * 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32);
+  if (cols <= 512) softmax_lin_k<32><<<grid_for(rows, 8, 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32, k_slot, p_stride);
+  else softmax_lin_k<256><<<(unsigned)std::min<long>(rows, kSMs * 16), 256, 0, S(st)>>>(P, rows_p, dS, rows, cols, ld, round_tf32, k_slot, p_stride);
   return last_err();
 }
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
@@ -1436,10 +1438,12 @@ PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, 
   return last_err();
 }
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
-                int col_mode, int round_tf32, pb_stream st) {
+                int col_mode, int round_tf32, int k_slot, long p_stride, pb_stream st) {
   CHECK_ALIGN4(ld, "attn_ds: ld");
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
+  if (p_stride % 4) return "attn_ds: p_stride must be a multiple of 4 floats";
   const long total = (long)nb * H * rows * (ld / 4);
-  attn_ds_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(P, dP, delta, scale, nb, H, rows, cols, ld, col_mode, round_tf32);
+  attn_ds_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(P, dP, delta, scale, nb, H, rows, cols, ld, col_mode, round_tf32, k_slot, p_stride / 4);
   return last_err();
 }
 

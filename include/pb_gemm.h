@@ -41,6 +41,9 @@ struct PbGemm {
   // element types: operands A/B fp32 (TF32 tensor cores) or fp16 (kind::f16); D/R fp32 or fp16, independently of the
   // operand type; bias, alpha, beta and the accumulation are always fp32
   int ab_dtype, d_dtype;
+  // problem slots (plain mode): batch index b belongs to problem b / k_slot; an operand whose batch stride (sAb / sBb) is 0 is
+  // PRIMAL and the copy of problem s starts p_stride BYTES after problem s - 1's.  k_slot <= 0 or >= nb: one problem.
+  int k_slot; long p_stride;
 };
 
 static inline PbGemm pb_gemm_init() {

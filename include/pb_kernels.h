@@ -111,15 +111,16 @@ PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, 
 // ---- softmax pieces (attention probabilities are materialised per (head, query) row) ----
 PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int round_tf32, pb_stream st);
 // dS <- P * (dS - rowsum(P * dS)); P has rows_p rows and is broadcast over the nb tangents
-PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32,
-                    pb_stream st);
+// problem slots (k_slot, p_stride in FLOATS): tangent b reads the P of problem b / k_slot; k_slot <= 0: one problem
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int round_tf32, int k_slot,
+                    long p_stride, pb_stream st);
 // delta[b][h][i] = sum_c go[b][i][h*d + c] * o[i][h*d + c]
 // io & PB_IN_F16: go holds halves (o is primal fp32, delta fp32)
 PBK pbk_attn_delta(const float* go, long ldg, const float* o, long ldo, int nb, int N, int H, int d, float* delta,
                    int io, int k_slot, long p_stride, pb_stream st);          // o of problem b / k_slot: o + (b / k_slot) * p_stride
 // dP[b][h][r][c] <- scale * P[h][r][c] * (dP[b][h][r][c] - (col_mode ? delta[b][h][c] : delta[b][h][r]))
 PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
-                int col_mode, int round_tf32, pb_stream st);
+                int col_mode, int round_tf32, int k_slot, long p_stride, pb_stream st);
 
 // ---- fused attention linearisation (no N x N tangent in HBM); implemented in pb_attn_sm100.cu ----
 // Per (b, h), rows r in [0, Mr), score columns c in [0, Nc), head dim d (head h occupies columns [h*d, (h+1)*d) of A/B/D/R/O):

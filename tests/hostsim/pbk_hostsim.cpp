@@ -103,6 +103,8 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
       }
     return nullptr;
   }
+  const long kslot = (g.k_slot > 0 && g.k_slot < g.nb) ? g.k_slot : g.nb;
+  const long pstride = kslot < g.nb ? g.p_stride : 0;
   for (int b = 0; b < g.nb; ++b)
     for (int h = 0; h < g.nh; ++h) {
 #pragma omp parallel for collapse(2) schedule(static)
@@ -111,8 +113,10 @@ PBK pbk_gemm(const PbGemm* gp, pb_stream) {
           double acc = 0.0;
           for (int si = 0; si < g.nseg; ++si) {
             const PbGemmSeg& s = g.seg[si];
-            const long a0 = b * s.sAb + h * s.sAh + (long)m * s.lda;
-            const long w0 = b * s.sBb + h * s.sBh + (long)n * s.ldb;
+            // problem slots: a primal (batch-broadcast) operand of problem b / k_slot starts p_stride bytes further on
+            const long es = ab ? 2 : 4;
+            const long a0 = (s.sAb == 0 ? (b / kslot) * (pstride / es) : b * s.sAb) + h * s.sAh + (long)m * s.lda;
+            const long w0 = (s.sBb == 0 ? (b / kslot) * (pstride / es) : b * s.sBb) + h * s.sBh + (long)n * s.ldb;
             float part = 0.f;
             for (int k = 0; k < s.K; ++k)
               part += ab ? ldx(s.A, 1, a0 + k) * ldx(s.B, 1, w0 + k)
@@ -364,9 +368,10 @@ PBK pbk_softmax_fwd(float* S, long rows, int cols, long ld, int rnd, pb_stream) 
   }
   return nullptr;
 }
-PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int rnd, pb_stream) {
+PBK pbk_softmax_lin(const float* P, long rows_p, float* dS, int nb, int cols, long ld, int rnd, int k_slot, long p_stride, pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   for (long r = 0; r < rows_p * nb; ++r) {
-    const float* p = P + (r % rows_p) * ld;
+    const float* p = P + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * ld;
     float* d = dS + r * ld;
     double dot = 0;
     for (int c = 0; c < cols; ++c) dot += (double)p[c] * d[c];
@@ -388,13 +393,15 @@ PBK pbk_attn_delta(const float* go, long ldg, const float* o0, long ldo, int nb,
     }
   return nullptr;
 }
-PBK pbk_attn_ds(const float* P, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
-                int col_mode, int rnd, pb_stream) {
+PBK pbk_attn_ds(const float* P0, float* dP, const float* delta, float scale, int nb, int H, int rows, int cols, long ld,
+                int col_mode, int rnd, int k_slot, long p_stride, pb_stream) {
+  if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   for (long b = 0; b < nb; ++b)
     for (int h = 0; h < H; ++h)
       for (int r = 0; r < rows; ++r)
         for (int c = 0; c < cols; ++c) {
           const long bh = b * H + h;
+          const float* P = P0 + (b / k_slot) * p_stride;
           const float dl = col_mode ? delta[bh * cols + c] : delta[bh * rows + r];
           float* p = dP + (bh * rows + r) * ld + c;
           *p = mr(scale * P[((long)h * rows + r) * ld + c] * (*p - dl), rnd);

@@ -359,7 +359,7 @@ def test_layernorm_geglu_softmax():
         assert rel(P[:, :cols], sm(S[:, :cols])) < 1e-5
         dS = torch.randn(nb, rows, ld, device="cuda")
         ref = torch.stack([torch.func.jvp(sm, (S[:, :cols],), (dS[i, :, :cols],))[1] for i in range(nb)])
-        _ok(N.leaf("pbk_softmax_lin")(_p(P), C.c_long(rows), _p(dS), nb, cols, C.c_long(ld), 0, _st()))
+        _ok(N.leaf("pbk_softmax_lin")(_p(P), C.c_long(rows), _p(dS), nb, cols, C.c_long(ld), 0, 0, C.c_long(0), _st()))
         assert rel(dS[..., :cols], ref) < 2e-5
 
 

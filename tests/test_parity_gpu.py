@@ -297,12 +297,12 @@ def test_uncond_scheduler_stochastic_step_and_loop_order():
     _, ac = DO.yh_schedule("linear")
     assert torch.equal(sched.alphas_cumprod, ac)
     osched = DO.Scheduler(ac.to(DEV), t_max=999)
-    sched.set_timesteps(8); osched.set_timesteps(8)
+    sched.set_timesteps(8); osched.set_timesteps(8, device=DEV)        # the oracle gathers from its table with the timestep tensor
     g = torch.Generator().manual_seed(6)
     xt, et = torch.randn(2, *x.shape[1:], generator=g).to(DEV), torch.randn(2, *x.shape[1:], generator=g).to(DEV)
     for eta in (1, 0.3):
         tt = osched.timesteps[3]
-        torch.manual_seed(2); out = sched.step(et, tt, xt, eta=eta)
+        torch.manual_seed(2); out = sched.step(et, tt.cpu(), xt, eta=eta)
         torch.manual_seed(2); xr, pr = osched.step(et, tt, xt, eta=eta)
         assert rel(out.prev_sample, xr) < 1e-6 and rel(out.x0, pr) < 1e-6
     for kw in (dict(t_start_idx=1, t_end_idx=3), dict(t_start_idx=2, t_end_idx=2), dict(t_start_idx=0, t_end_idx=-1)):
