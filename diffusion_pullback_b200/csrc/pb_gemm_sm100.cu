@@ -257,33 +257,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // The whole warp walks the loop and one ELECTED lane issues: inside an `if (lane == 0)` region the compiler cannot prove
+    // the TMA operands warp-uniform and wraps every UTMALDG in an ELECT / R2UR.BROADCAST waterfall (47 broadcasts in this
+    // kernel's SASS), which made a k-block's two loads cost more issue time than its MMAs take to execute.
+    {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const Tile t = decode_item<BN>(p, item);
         const int kb_begin = t.partial ? t.split * p.kb_per_split : 0;
         const int kb_end = t.partial ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+        int tap = kb_begin / kb_tap;
+        int kbt = kb_begin - tap * kb_tap;                     // k-block inside the tap, advanced without division
         for (int it = kb_begin; it < kb_end; ++it) {
-          const int tap = it / kb_tap;
-          int kb = it - tap * kb_tap;
-          const int s = kb < p.kblocks[0] ? 0 : 1;
-          if (s) kb -= p.kblocks[0];
+          const int s = kbt < p.kblocks[0] ? 0 : 1;
+          const int kb = s ? kbt - p.kblocks[0] : kbt;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
-          if (p.conv) {
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.cx0 + dx, t.cy0 + dy, t.cb0);
-            // filter as a (channel, tap, out-channel) tensor: a k-block running past the channel count is zero-filled
-            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, tap, t.n0, 0);
-          } else {
-            const int ca = p.a_bdiv[s] ? t.bat_b / p.a_bdiv[s] : t.bat_b * p.a_bmul[s];
-            const int cb = p.b_bdiv[s] ? t.bat_b / p.b_bdiv[s] : t.bat_b * p.b_bmul[s];
-            tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.m0, t.bat_h * p.a_hmul[s], ca);
-            tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, t.n0, t.bat_h * p.b_hmul[s], cb);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
+            if (p.conv) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.cx0 + dx, t.cy0 + dy, t.cb0);
+              // filter as a (channel, tap, out-channel) tensor: a k-block running past the channel count is zero-filled
+              tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, tap, t.n0, 0);
+            } else {
+              const int ca = p.a_bdiv[s] ? t.bat_b / p.a_bdiv[s] : t.bat_b * p.a_bmul[s];
+              const int cb = p.b_bdiv[s] ? t.bat_b / p.b_bdiv[s] : t.bat_b * p.b_bmul[s];
+              tma_load_4d(sa, &p.mapA[s], &full_bar[stage], kb * KB_ELEMS, t.m0, t.bat_h * p.a_hmul[s], ca);
+              tma_load_4d(sb, &p.mapB[s], &full_bar[stage], kb * KB_ELEMS, t.n0, t.bat_h * p.b_hmul[s], cb);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++kbt == kb_tap) { kbt = 0; ++tap; }
         }
       }
     }
@@ -334,7 +341,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     // =========================== epilogue ===========================
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // tile row
-    const bool t0 = (threadIdx.x == 64);      // the thread that drives the staging TMA traffic
+    // warp 2 drives the staging TMA traffic through ONE ELECTED lane (elect.sync names the same leader for the same member
+    // mask every time, so the bulk async-groups are committed and waited on by one thread); an `if (threadIdx.x == 64)` region
+    // made every UTMASTG / UTMALDG of the epilogue an ELECT / R2UR.BROADCAST waterfall -- ten per 128 x 160 tile, which is what
+    // paced the short-K linears
+    const bool w0 = (warp == 2);
     uint32_t gch = 0;                         // chunks pushed through the staging ring so far (this CTA)
     uint32_t r_par = 0;                       // bit b: parity of the next residual load into staging buffer b
     constexpr int TAILQ = D16 ? 7 : 3;        // TMA stores clip the inner dimension in 16-byte units
@@ -364,8 +375,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       long d_off, r_off;
       const bool row_ok = tile_row(p, t, r, &d_off, &r_off);
 
-      if (t0 && has_r)
-        for (int c = 0; c < min(3, ntma); ++c) prefetch_r(c, gch + c);
+      if (w0 && has_r) {
+        if (elect_one())
+          for (int c = 0; c < min(3, ntma); ++c) prefetch_r(c, gch + c);
+        __syncwarp();
+      }
       mbar_wait(&tmem_full_bar[as], (li >> 1) & 1);
       tcgen05_fence_after();
 
@@ -388,11 +402,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           else stage_chunk<D16>(sbuf, r, v, alpha, beta, bias, nc, p.N, full, has_r, rnd);
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
-          if (t0) {
-            tma_store_4d(dmap, sbuf, dcol0 + c * EPI_W, c1, c2, c3);
-            bulk_commit();
-            bulk_wait_read<1>();              // every store but the newest has left its staging buffer
-            if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
+          if (w0) {
+            if (elect_one()) {
+              tma_store_4d(dmap, sbuf, dcol0 + c * EPI_W, c1, c2, c3);
+              bulk_commit();
+              bulk_wait_read<1>();            // every store but the newest has left its staging buffer
+              if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
+            }
+            __syncwarp();
           }
           ++gch;
         } else if (row_ok) {
@@ -413,7 +430,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
     // the staging buffers must have been read before the CTA exits; the global writes themselves complete with the kernel
     // (every consumer of D or of the split-K scratch is a later kernel in the stream)
-    if (t0) bulk_wait_read<0>();
+    if (w0) {
+      if (elect_one()) bulk_wait_read<0>();
+      __syncwarp();
+    }
     tcgen05_fence_before();
   }
   __syncthreads();
