@@ -406,7 +406,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
             if (elect_one()) {
               tma_store_4d(dmap, sbuf, dcol0 + c * EPI_W, c1, c2, c3);
               bulk_commit();
-              bulk_wait_read<1>();            // every store but the newest has left its staging buffer
+              // the next chunk stages into the buffer of the store issued NBUF - 1 chunks ago: three stores may still be
+              // reading their buffers; with a residual the buffer of the PREVIOUS store is refilled right here, so only the
+              // newest may be pending (one pending store made the short-K linears epilogue-bound: five serialised
+              // store round trips per 128 x 160 tile)
+              if (has_r) bulk_wait_read<1>(); else bulk_wait_read<NBUF - 1>();
               if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
             }
             __syncwarp();
