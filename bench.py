@@ -337,10 +337,20 @@ def run_ours(args, wl):
     eng = PB.PullbackEngine(cfg, size, size, op, bi, k, ctx_len, dev)
     eng.bind(unet.state_dict())
     engS = None
-    if S > 1:
-        engS = PB.PullbackEngine(cfg, size, size, op, bi, S * k, ctx_len, dev)
-        engS.bind(unet.state_dict())
-        engS.set_slots(S)
+    while S > 1:                                             # as many slots as fit the HBM (SD-2.1-768: 12.4 GB of primal cache per slot)
+        try:
+            engS = PB.PullbackEngine(cfg, size, size, op, bi, S * k, ctx_len, dev)
+            engS.bind(unet.state_dict())
+            engS.set_slots(S)
+            if torch.cuda.mem_get_info(dev)[0] < 8 << 30:   # head-room for the e2e buffers and the probe pass
+                raise torch.OutOfMemoryError("not enough head-room")
+            break
+        except torch.OutOfMemoryError:
+            if args.slots:
+                raise SystemExit(f"bench.py: --slots {S} does not fit the device memory")
+            engS = None
+            torch.cuda.empty_cache()
+            S -= 1
     unet._sd = None                                          # packed copy lives in the engine now
     torch.cuda.empty_cache()
     _, t, ctx = SY.synthetic_inputs(model_name)

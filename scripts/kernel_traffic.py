@@ -31,7 +31,7 @@ ends = [j for j, r in enumerate(rows) if "rotate_k" in r["name"]]
 rows = rows[ends[-2] + 1: ends[-1] + 1] if len(ends) >= 2 else rows
 agg = defaultdict(lambda: [0, 0.0, 0.0])
 for r in rows:
-    key = "gemm_tc_kernel" if "gemm_tc_kernel" in r["name"] else "attn_lin_kernel" if "attn_lin_kernel" in r["name"] else "other"
+    key = "gemm_tc_kernel" if "gemm_tc_kernel" in r["name"] else "attn_lin_kernel" if ("attn_lin_kernel" in r["name"] or "attn16_kernel" in r["name"]) else "other"
     a = agg[key]
     a[0] += 1
     a[1] += r.get("dram__bytes_read.sum", 0.0) + r.get("dram__bytes_write.sum", 0.0)
