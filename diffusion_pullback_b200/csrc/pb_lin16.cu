@@ -36,8 +36,9 @@ GnGeom16 gn_geom16(int HW, int C, int G, int nb) {
   g.lanes = std::max(1, std::min(std::min(256 / g.CV, 6144 / g.Cblk), 16));   // pixel lanes; smem = lanes * Cblk * 8 bytes <= 48 KB
   g.threads = (g.CV * g.lanes + 31) / 32 * 32;
   // chunks per (image, slab) rounded DOWN so that the grid fits ONE wave of 4 resident blocks per SM: rounded up, 25 images got
-  // 24 chunks = 600 blocks for 592 slots and the 8 left-over blocks ran as a second wave (ncu r2: 102 us for a 52 us kernel)
-  const int target = std::max(1, (kSMs * 4) / (nb * g.nz));
+  // 24 chunks = 600 blocks for 592 slots and the 8 left-over blocks ran as a second wave (ncu r2: 102 us for a 52 us kernel); 3 blocks of <= 85 registers per SM
+  // since the batched-load loops (4 pixels of operands in registers before the math) do not fit 64
+  const int target = std::max(1, (kSMs * 3) / (nb * g.nz));
   const int maxchunks = (HW + g.lanes - 1) / g.lanes;
   g.chunks = std::max(1, std::min(maxchunks, target));
   g.ppb = (HW + g.chunks - 1) / g.chunks;
@@ -48,7 +49,7 @@ GnGeom16 gn_geom16(int HW, int C, int G, int nb) {
 
 // MODE 0 (JVP): u = t ; MODE 1 (VJP): u = t * act'(gamma xhat + beta) * gamma.   part[b][chunk][g] = (sum u, sum xhat u)
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) gn16_sums_k(const float* __restrict__ xp, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, 3) gn16_sums_k(const float* __restrict__ xp, const float* __restrict__ mean,
                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                    const float* __restrict__ beta_, int HW, int C, int G, int silu,
                                                    const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
@@ -74,19 +75,28 @@ __global__ void __launch_bounds__(256, 4) gn16_sums_k(const float* __restrict__ 
     const float* xq = xp + ps + (long)(p0 + lane) * C + c0;
     const __half* tq = t + ((long)b * HW + p0 + lane) * C + c0;
     const long step = (long)lanes * C;
-#pragma unroll 4
-    for (int pix = p0 + lane; pix < p1; pix += lanes, xq += step, tq += step) {
-      const float4 xv = *reinterpret_cast<const float4*>(xq);
-      const uint2 tu = *reinterpret_cast<const uint2*>(tq);
-      const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu.x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu.y));
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
+    constexpr int U = 4;                                           // pixels per trip, all loads before the math (see gn16_apply_k)
+    for (int pix = p0 + lane; pix < p1; pix += lanes * U, xq += U * step, tq += U * step) {
+      float4 xv[U]; uint2 tu[U];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float xh = (xs[e] - mu[e]) * rs[e];
-        float u = ts[e];
-        if (MODE == 1) u *= silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
-        s1[e] += u; s2[e] = fmaf(xh, u, s2[e]);
-      }
+      for (int u = 0; u < U; ++u)
+        if (pix + u * lanes < p1) {
+          xv[u] = __ldg(reinterpret_cast<const float4*>(xq + u * step));
+          tu[u] = __ldg(reinterpret_cast<const uint2*>(tq + u * step));
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pix + u * lanes < p1) {
+          const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu[u].x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu[u].y));
+          const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float xh = (xs[e] - mu[e]) * rs[e];
+            float w = ts[e];
+            if (MODE == 1) w *= silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
+            s1[e] += w; s2[e] = fmaf(xh, w, s2[e]);
+          }
+        }
     }
     float2* sp = sh2 + (long)lane * Cblk + cv * 4;
 #pragma unroll
@@ -112,8 +122,8 @@ __global__ void __launch_bounds__(256, 4) gn16_sums_k(const float* __restrict__ 
 
 //   MODE 0 (JVP): out = act'(.) gamma rstd (t - m1 - xhat m2)          MODE 1 (VJP): out = rstd (t act'(.) gamma - m1 - xhat m2)
 //   (m1, m2) = group means of (u, xhat u);   out = result + acc * out
-template <int MODE>
-__global__ void __launch_bounds__(256, 4) gn16_apply_k(const float* __restrict__ xp, const float* __restrict__ mean,
+template <int MODE, bool ACC>
+__global__ void __launch_bounds__(256, 3) gn16_apply_k(const float* __restrict__ xp, const float* __restrict__ mean,
                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                     const float* __restrict__ beta_, int HW, int C, int G, int silu,
                                                     const __half* __restrict__ t, int Cblk, int lanes, int ppb, int k_slot,
@@ -162,28 +172,40 @@ __global__ void __launch_bounds__(256, 4) gn16_apply_k(const float* __restrict__
   const __half* tq = t + toff;
   __half* oq = out + toff;
   const long step = (long)lanes * C;
-#pragma unroll 4
-  for (int pix = p0 + lane; pix < p1; pix += lanes, xq += step, tq += step, oq += step) {
-    const float4 xv = *reinterpret_cast<const float4*>(xq);
-    const uint2 tu = *reinterpret_cast<const uint2*>(tq);
-    const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu.x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu.y));
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
-    float o[4];
+  // U pixels per trip, ALL loads first: the loop body otherwise runs load -> math -> store -> next load (the store to `out` and
+  // the optional read of `out` keep the compiler from hoisting the next loads), one memory latency per pixel and thread -- ncu r2:
+  // 0.15 of the HBM peak at 31 % issue utilisation
+  constexpr int U = 4;
+  for (int pix = p0 + lane; pix < p1; pix += lanes * U, xq += U * step, tq += U * step, oq += U * step) {
+    float4 xv[U]; uint2 tu[U], pu[U];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float xh = (xs[e] - mu[e]) * rs[e];
-      const float f = silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
-      o[e] = MODE == 0 ? f * rs[e] * (ts[e] - m1[e] - xh * m2[e]) : rs[e] * (ts[e] * f - m1[e] - xh * m2[e]);
-    }
-    if (acc != 0.f) {
-      const uint2 pu = *reinterpret_cast<const uint2*>(oq);
-      const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&pu.x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&pu.y));
-      o[0] += acc * q0.x; o[1] += acc * q0.y; o[2] += acc * q1.x; o[3] += acc * q1.y;
-    }
-    uint2 ou;
-    *reinterpret_cast<__half2*>(&ou.x) = __floats2half2_rn(o[0], o[1]);
-    *reinterpret_cast<__half2*>(&ou.y) = __floats2half2_rn(o[2], o[3]);
-    *reinterpret_cast<uint2*>(oq) = ou;
+    for (int u = 0; u < U; ++u)
+      if (pix + u * lanes < p1) {
+        xv[u] = __ldg(reinterpret_cast<const float4*>(xq + u * step));
+        tu[u] = __ldg(reinterpret_cast<const uint2*>(tq + u * step));
+        if (ACC) pu[u] = *reinterpret_cast<const uint2*>(oq + u * step);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (pix + u * lanes < p1) {
+        const float2 t0 = __half22float2(*reinterpret_cast<const __half2*>(&tu[u].x)), t1 = __half22float2(*reinterpret_cast<const __half2*>(&tu[u].y));
+        const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ts[4] = {t0.x, t0.y, t1.x, t1.y};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xh = (xs[e] - mu[e]) * rs[e];
+          const float f = silu ? ga[e] * silu_d(fmaf(ga[e], xh, be[e])) : ga[e];
+          o[e] = MODE == 0 ? f * rs[e] * (ts[e] - m1[e] - xh * m2[e]) : rs[e] * (ts[e] * f - m1[e] - xh * m2[e]);
+        }
+        if (ACC) {
+          const float2 q0 = __half22float2(*reinterpret_cast<const __half2*>(&pu[u].x)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&pu[u].y));
+          o[0] += acc * q0.x; o[1] += acc * q0.y; o[2] += acc * q1.x; o[3] += acc * q1.y;
+        }
+        uint2 ou;
+        *reinterpret_cast<__half2*>(&ou.x) = __floats2half2_rn(o[0], o[1]);
+        *reinterpret_cast<__half2*>(&ou.y) = __floats2half2_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(oq + u * step) = ou;
+      }
   }
 }
 
@@ -392,15 +414,16 @@ const char* gn_lin(const float* xp, const float* mean, const float* rstd, const 
   dim3 grid(g.chunks, nb, g.nz);
   const size_t sh1 = (size_t)g.lanes * g.Cblk * sizeof(float2);
   const size_t sh2 = (size_t)G * 2 * sizeof(float) * (1 + std::max(1, g.threads / (2 * G)));
+#define PB_GN16_APPLY(M_, A_) gn16_apply_k<M_, A_><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, \
+                                                                          k_slot, p_stride, tmp, g.chunks, out, acc)
   if (mode == 0) {
     gn16_sums_k<0><<<grid, g.threads, sh1, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride, tmp);
-    gn16_apply_k<0><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride,
-                                                  tmp, g.chunks, out, acc);
+    if (acc != 0.f) PB_GN16_APPLY(0, true); else PB_GN16_APPLY(0, false);
   } else {
     gn16_sums_k<1><<<grid, g.threads, sh1, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride, tmp);
-    gn16_apply_k<1><<<grid, g.threads, sh2, st>>>(xp, mean, rstd, gamma, beta, HW, C, G, silu, t, g.Cblk, g.lanes, g.ppb, k_slot, p_stride,
-                                                  tmp, g.chunks, out, acc);
+    if (acc != 0.f) PB_GN16_APPLY(1, true); else PB_GN16_APPLY(1, false);
   }
+#undef PB_GN16_APPLY
   return last_err();
 }
 
