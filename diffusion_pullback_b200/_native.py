@@ -31,7 +31,8 @@ class PbTensorDesc(C.Structure):
 class PbSizes(C.Structure):
     _fields_ = [("packed_weight_bytes", C.c_size_t), ("primal_cache_bytes", C.c_size_t),
                 ("workspace_bytes", C.c_size_t), ("n_in", C.c_int64), ("n_out", C.c_int64),
-                ("out_channels", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32)]
+                ("out_channels", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+                ("in_channels", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("n_x", C.c_int64)]
 
 
 class PbIterInfo(C.Structure):
@@ -132,6 +133,8 @@ def _declare(L):
     L.pb_set_option.restype = C.c_int
     L.pb_plan_summary.argtypes = [vp, C.POINTER(PbPlanInfo)]
     L.pb_plan_summary.restype = C.c_int
+    L.pb_decode_from.argtypes = [vp, vp, vp, vp]
+    L.pb_decode_from.restype = C.c_int
     L.pb_ddim_step.argtypes = [vp, vp, f32, f32, vp, vp, i64, vp]
     L.pb_ddim_step.restype = C.c_int
     L.pb_lincomb3.argtypes = [vp, f32, vp, f32, vp, f32, vp, i64, vp]

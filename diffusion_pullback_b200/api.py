@@ -189,6 +189,71 @@ def _pullback_many_on(eng, samples, timesteps, ctx, k, min_iter, max_iter, conve
     return [(u[p * k:(p + 1) * k].T, s[p * k:(p + 1) * k], vT[p * k:(p + 1) * k]) for p in range(P)]
 
 
+# ---- decoder side: get_h_to_e, local_decoder_pullback_zt, inv_jac_zt ----
+def get_h_to_e(self, sample=None, timestep=None, encoder_hidden_states=None, input_h=None, op=None, block_idx=None, verbose=False):
+    """`utils.py:529-635`: the decoder half of the U-Net from a substituted mid-block feature -- every row of `input_h`
+    ([pca_rank, C, H, W] or flattened) is pushed through the up path, `conv_norm_out`, SiLU and `conv_out` on the skip connections
+    of `sample` (one latent); returns the noise predictions [pca_rank, c, H, W].  Like the reference, only ('mid', 0) is a valid
+    place to substitute h (`assert op in ['mid', 'down']`, and 'down' never substitutes)."""
+    if not (op == "mid" and block_idx == 0):
+        raise AssertionError("up block is not implemented yet" if op == "up" else f"(op, block_idx) = ({op, block_idx}) is not valid")
+    if sample.shape[0] != 1:
+        raise ValueError("get_h_to_e takes one latent (the reference repeats its skip connections pca_rank times)")
+    ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+    eng = _engine_for(self, sample, "dec", 0, 1, ctx_len)
+    input_h = input_h.reshape(-1, *eng.in_shape)
+    eng.set_point(sample, _timestep(timestep), encoder_hidden_states)
+    return torch.cat([eng.decode_from(input_h[i:i + 1]) for i in range(input_h.shape[0])], 0)
+
+
+@torch.no_grad()
+def local_decoder_pullback_zt(self, sample, timestep, encoder_hidden_states=None, op=None, block_idx=None,
+                              pca_rank=50, chunk_size=25, min_iter=10, max_iter=100, convergence_threshold=None,
+                              v0=None, return_info=False):
+    """`utils.py:818-898`: the subspace iteration on the DECODER Jacobian d eps / d h at h = get_h(sample) (tangents enter at the
+    mid-block output, the skip connections are constants).  Returns the reference's triple: `u` [numel(h), k] (directions in
+    h-space), `s` [k] (square roots of the singular values of U^T J, as the reference returns them), `vT` [k, numel(x_t)] (the
+    images of the directions in eps-space) -- "decoder jac do not return vT" (`:895-896`).  `convergence_threshold=None` is the
+    reference's default, with which its `allclose` raises once `i > min_iter`; here None runs `max_iter` iterations."""
+    if not (op == "mid" and block_idx == 0):
+        raise AssertionError("up block is not implemented yet" if op == "up" else f"(op, block_idx) = ({op, block_idx}) is not valid")
+    time_s = time.time()
+    k = int(pca_rank)
+    ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+    eng = _engine_for(self, sample, "dec", 0, k, ctx_len)
+    if v0 is None:
+        vT = torch.randn(eng.n_in, k, device=sample.device, dtype=torch.float)           # utils.py:850-852
+        vT, _ = torch.linalg.qr(vT)
+        v0 = vT.T.contiguous()
+    eng.set_point(sample, _timestep(timestep), encoder_hidden_states)
+    tol = 0.0 if convergence_threshold is None else float(convergence_threshold)
+    lo = max_iter if convergence_threshold is None else min_iter
+    e_dirs, s, h_dirs, info = eng.pullback(v0, lo, max_iter, tol)
+    print(f"power method : {info.iters_done - 1}-th step convergence : ", info.last_dist)
+    print("power method runtime ==", time.time() - time_s)
+    out = (h_dirs.T, s, e_dirs)
+    if return_info:
+        return out + (dict(iters_done=info.iters_done, converged=bool(info.converged), last_dist=info.last_dist),)
+    return out
+
+
+@torch.no_grad()
+def inv_jac_zt(self, sample=None, timestep=None, encoder_hidden_states=None, op=None, block_idx=None, u=None, perturb_h=1e-1):
+    """`utils.py:1117-1160`: the x-space direction that moves h along `u`: the normalised gradient of
+    ||h + perturb_h u - get_h(x)|| at x = sample, i.e. -J^T u / ||J^T u|| -- one transpose pass of the encoder Jacobian (the
+    perturbation size drops out: the residual at x is exactly perturb_h u).  `u` is one direction in h-space (the reference raises
+    NotImplementedError for several)."""
+    if u.dim() > 1 and u.shape[-1] != 1 and u.numel() != u.shape[0]:
+        raise NotImplementedError("")
+    assert sample.size(0) == 1, "sample size should be 1"
+    ctx_len = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+    eng = _engine_for(self, sample, op, block_idx, 1, ctx_len)
+    eng.set_point(sample, _timestep(timestep), encoder_hidden_states)
+    w = eng.vjp(u.reshape(1, -1).to(sample.device, torch.float32))
+    vT = -w
+    return vT / vT.norm(dim=1, keepdim=True)
+
+
 def patch_unet(unet):
     """The monkey-patch of `utils.py:103-104` (uncond) / `:326`, `:333` (Stable Diffusion)."""
     if hasattr(unet, "up_blocks") and unet_config(unet)["kind"] == 0:
@@ -196,6 +261,9 @@ def patch_unet(unet):
         unet.local_encoder_pullback_zt = types.MethodType(local_encoder_pullback_zt, unet)
         unet.local_encoder_pullback_many = types.MethodType(local_encoder_pullback_many, unet)
         unet.eps = types.MethodType(eps, unet)
+        unet.get_h_to_e = types.MethodType(get_h_to_e, unet)                               # utils.py:327
+        unet.local_decoder_pullback_zt = types.MethodType(local_decoder_pullback_zt, unet)  # utils.py:334 (commented out there)
+        unet.inv_jac_zt = types.MethodType(inv_jac_zt, unet)                               # utils.py:329
     else:
         unet.get_h = types.MethodType(get_h_uncond, unet)
         unet.local_encoder_pullback_xt = types.MethodType(local_encoder_pullback_xt, unet)

@@ -96,7 +96,12 @@ struct pb_handle {
   size_t w_splitk = 0, n_splitk = 0;
   char* packed = nullptr; char* cache = nullptr; char* work = nullptr;
   int in_val = -1, out_val = -1;
+  // decoder side (PB_OP_DEC): tangents enter at value dec_val (the mid-block output), produced by op dec_op; the values of the
+  // encoder half that later ops read (skip connections) carry zero tangents
+  int dec_val = -1, dec_op = -1, dec_H = 0, dec_W = 0;
+  std::vector<int> dec_zero;
   long n_in = 0, n_out = 0;
+  long n_x = 0;                             // numel(x_t) (= n_in except on the decoder side)
   // numerics policy (DESIGN.md "precision"): producers RNA-round GEMM operands to TF32 (rnd_*); GEMMs run one TF32
   // pass (0), error-compensated 3xTF32 (1) or split-weight 2xTF32 (2)
   int rnd_p = 1, rnd_t = 1, rnd_w = 1;      // primal activations / tangents / packed weights
@@ -410,10 +415,12 @@ struct Planner {
              : attn_block(x, c.heads[L - 1], H, W, "mid_block.attentions.0");
     if (x < 0) return false;
     x = resnet(x, Cm, H, W, "mid_block.resnets.1"); if (x < 0) return false;
-    if (h->op == PB_OP_UP || h->op == PB_OP_FULL) {
+    if (h->op == PB_OP_DEC) { h->dec_val = x; h->dec_op = (int)h->ops.size() - 1; h->dec_H = H; h->dec_W = W; }
+    const bool full = h->op == PB_OP_FULL || h->op == PB_OP_DEC;
+    if (h->op == PB_OP_UP || full) {
       // get_h_uncond stops at the mid block (utils.py:158-163); the unconditional up path exists for the full forward only
       if (!cond && h->op == PB_OP_UP) { error = "(op, block_idx) is not valid: get_h_uncond supports ('mid', 0) only"; return false; }
-      const int last_up = h->op == PB_OP_FULL ? L - 1 : h->block_idx;
+      const int last_up = full ? L - 1 : h->block_idx;
       for (int i = 0; i <= last_up; ++i) {
         const std::string bp = "up_blocks." + std::to_string(i);
         const int out_ch = c.block_out_channels[L - 1 - i];
@@ -431,7 +438,7 @@ struct Planner {
         if (i != L - 1) { x = upsample(x, H, W, bp + ".upsamplers.0"); if (x < 0) return false; H *= 2; W *= 2; }
       }
     }
-    if (h->op == PB_OP_FULL) {
+    if (full) {
       // eps head: GroupNorm -> SiLU -> Conv3x3(C0 -> in_channels), the thin direct conv (few output channels)
       int a = gn(x, "conv_norm_out", c.norm_eps, 1); if (a < 0) return false;
       int y = val((long)H * W, c.in_channels);
@@ -444,6 +451,15 @@ struct Planner {
     { Op& o = push(OP_OUT); o.x = x; o.H = H; o.W = W; }
     h->out_val = x;
     h->sizes.out_channels = h->vals[x].C; h->sizes.out_h = H; h->sizes.out_w = W;
+    if (h->dec_val >= 0) {
+      // values of the encoder half (and x_t itself) read by ops of the decoder half: their tangents are zero
+      std::vector<int> producer(h->vals.size(), -1);
+      for (size_t i = 0; i < h->ops.size(); ++i) if (h->ops[i].y >= 0) producer[h->ops[i].y] = (int)i;
+      std::vector<char> seen(h->vals.size(), 0);
+      for (size_t i = h->dec_op + 1; i < h->ops.size(); ++i)
+        for (int v : {h->ops[i].x, h->ops[i].x2, h->ops[i].res})
+          if (v >= 0 && v != h->dec_val && producer[v] <= h->dec_op && !seen[v]) { seen[v] = 1; h->dec_zero.push_back(v); }
+    }
     return true;
   }
 };
@@ -844,25 +860,30 @@ int run_attn_vjp(pb_handle* h, const Op& o, int nb, pb_stream st) {
   return PB_OK;
 }
 
-int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h_out, pb_stream st) {
+// first > 0 (pb_decode_from): the ops [first, end) only, on the time embedding / text projection / skip connections the last
+// pb_set_point cached
+int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h_out, pb_stream st, size_t first = 0) {
   h->rnd = h->rnd_p;
   const pb_unet_cfg& c = h->cfg;
   const int c0 = c.block_out_channels[0], ted = 4 * c0;
   auto W = [&](const char* name, WKind kind, int n) { return h->Wf(h->windex.at(std::string(name) + "#" + std::to_string((int)kind) + "#" + std::to_string(n))); };
-  CK(pbk_timestep_embedding(t, c0, c.flip_sin_to_cos, c.freq_shift, h->CP(h->c_sin), st));
-  CK(pbk_gemv(W("time_embedding.linear_1.weight", WK_RAW, 1), h->CP(h->c_sin), W("time_embedding.linear_1.bias", WK_VEC, 1), ted, c0,
-              0, 1, h->CP(h->c_e1), st));
-  CK(pbk_gemv(W("time_embedding.linear_2.weight", WK_RAW, 1), h->CP(h->c_e1), W("time_embedding.linear_2.bias", WK_VEC, 1), ted, ted,
-              0, 0, h->CP(h->c_temb), st));
   const float* ctx_r = nullptr;
-  if (c.kind == PB_UNET_COND) {
-    if (!ctx) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
-    const size_t nctx = (size_t)h->ctx_len * c.cross_attention_dim;
-    if (h->rnd) CK(pbk_round_tf32(h->CP(h->c_ctx), ctx, nctx, st));
-    else CK(pbk_copy(h->CP(h->c_ctx), ctx, nctx * 4, st));
-    ctx_r = h->CP(h->c_ctx);
+  if (first == 0) {
+    CK(pbk_timestep_embedding(t, c0, c.flip_sin_to_cos, c.freq_shift, h->CP(h->c_sin), st));
+    CK(pbk_gemv(W("time_embedding.linear_1.weight", WK_RAW, 1), h->CP(h->c_sin), W("time_embedding.linear_1.bias", WK_VEC, 1), ted, c0,
+                0, 1, h->CP(h->c_e1), st));
+    CK(pbk_gemv(W("time_embedding.linear_2.weight", WK_RAW, 1), h->CP(h->c_e1), W("time_embedding.linear_2.bias", WK_VEC, 1), ted, ted,
+                0, 0, h->CP(h->c_temb), st));
+    if (c.kind == PB_UNET_COND) {
+      if (!ctx) return fail(h, PB_EINVAL, "encoder_hidden_states is required for a conditional U-Net");
+      const size_t nctx = (size_t)h->ctx_len * c.cross_attention_dim;
+      if (h->rnd) CK(pbk_round_tf32(h->CP(h->c_ctx), ctx, nctx, st));
+      else CK(pbk_copy(h->CP(h->c_ctx), ctx, nctx * 4, st));
+    }
   }
-  for (const Op& o : h->ops) {
+  if (c.kind == PB_UNET_COND) ctx_r = h->CP(h->c_ctx);
+  for (size_t oi = first; oi < h->ops.size(); ++oi) {
+    const Op& o = h->ops[oi];
     switch (o.kind) {
       case OP_IN: {
         const Val& v = h->vals[o.y];
@@ -995,7 +1016,21 @@ struct SlotGuard { pb_handle* h; ~SlotGuard() { h->slot = 0; } };
 int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
   h->rnd = h->rnd_t; h->pass_vjp = false; h->k_slot = nb / h->slots;
   SlotGuard guard{h};
-  for (const Op& o : h->ops) {
+  size_t first = 0;
+  if (h->dec_val >= 0) {
+    // decoder side: V is h-shaped and enters at the mid-block output; the skip connections carry zero tangents (re-zeroed every
+    // time: the transpose pass accumulates cotangents into the same buffers)
+    for (int v : h->dec_zero) {
+      const Val& a = h->vals[v];
+      CK(pbk_memset0(h->T(v), (size_t)nb * a.rows * a.C * (h->is16(v) ? 2 : 4), st));
+    }
+    const Val& v = h->vals[h->dec_val];
+    CK(pbk_transpose(h->T(h->dec_val), v.C, v.rows * v.C, 0, V, v.rows, v.rows * v.C, 0, nb, 1, v.C, (int)v.rows, 0.f,
+                     h->is16(h->dec_val) ? PB_OUT_F16 : h->rnd, st));
+    first = (size_t)h->dec_op + 1;
+  }
+  for (size_t oi = first; oi < h->ops.size(); ++oi) {
+    const Op& o = h->ops[oi];
     if (h->slots > 1 && per_slot_op(h, o)) {
       for (int p = 0; p < h->slots; ++p) {
         h->slot = p;
@@ -1085,7 +1120,8 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
   h->alias.resize(h->vals.size());
   for (size_t i = 0; i < h->alias.size(); ++i) h->alias[i] = (int)i;
   struct Unalias { pb_handle* h; ~Unalias() { h->alias.clear(); } } unalias{h};       // the JVP / primal see every val's own buffer
-  for (size_t i = h->ops.size(); i-- > 0;) {
+  const size_t stop = h->dec_val >= 0 ? (size_t)h->dec_op + 1 : 0;        // decoder side: the walk ends at the mid-block output
+  for (size_t i = h->ops.size(); i-- > stop;) {
     const Op& o = h->ops[i];
     if (o.y >= 0 && !h->vals[o.y].ginit) return fail(h, PB_ESTATE, "internal: cotangent consumed before it was produced");
     if (h->slots > 1 && per_slot_op(h, o)) {
@@ -1097,6 +1133,12 @@ int run_vjp(pb_handle* h, const float* U, int nb, float* Wout, pb_stream st) {
       }
       h->slot = 0;
     } else if (int e = vjp_op(h, o, U, nb, Wout, st)) return e;
+  }
+  if (h->dec_val >= 0) {
+    const Val& v = h->vals[h->dec_val];
+    if (!v.ginit) return fail(h, PB_ESTATE, "internal: the decoder half never reads h");
+    CK(pbk_transpose(Wout, v.rows, v.rows * v.C, 0, h->T(h->dec_val), v.C, v.rows * v.C, 0, nb, 1, (int)v.rows, v.C, 0.f,
+                     h->is16(h->dec_val) ? PB_IN_F16 : 0, st));
   }
   return PB_OK;
 }
@@ -1315,10 +1357,14 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
     if (h->cfg.kind != PB_UNET_COND || block_idx < 0 || block_idx >= h->cfg.n_levels) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   } else if (op == PB_OP_FULL) {
     if (block_idx != 0) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
+  } else if (op == PB_OP_DEC) {
+    // get_h_to_e asserts op in ['mid', 'down'] and substitutes h after the mid block only (utils.py:544, :603-606)
+    if (block_idx != 0 || h->cfg.kind != PB_UNET_COND) return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   } else return fail(h, PB_EINVAL, "(op, block_idx) is not valid");
   if (h->cfg.kind == PB_UNET_COND && ctx_len < 1) return fail(h, PB_EINVAL, "ctx_len must be >= 1 for a conditional U-Net");
   h->H = height; h->W = width; h->op = op; h->block_idx = block_idx; h->kmax = k_max; h->ctx_len = ctx_len;
   h->vals.clear(); h->ops.clear(); h->wspecs.clear(); h->windex.clear();
+  h->dec_val = h->dec_op = -1; h->dec_zero.clear();
   h->cache_top = h->work_top = h->packed_top = 0;
   h->n_s1 = h->n_s2 = h->n_s3 = h->n_delta = h->n_gn = 0; h->n_cvt = 0;
   h->sizes = pb_sizes{};
@@ -1328,7 +1374,8 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->c_sin = p.cache_alloc(c0); h->c_e1 = p.cache_alloc(4 * c0); h->c_temb = p.cache_alloc(4 * c0);
   h->c_ctx = p.cache_alloc((size_t)std::max(1, ctx_len) * std::max(1, h->cfg.cross_attention_dim));
   if (!p.build()) return fail(h, PB_EINVAL, p.error);
-  h->n_in = (long)h->cfg.in_channels * height * width;
+  h->n_x = (long)h->cfg.in_channels * height * width;
+  h->n_in = h->dec_val >= 0 ? h->vals[h->dec_val].rows * h->vals[h->dec_val].C : h->n_x;
   h->n_out = h->vals[h->out_val].rows * h->vals[h->out_val].C;
   decide_t16(h);
   const size_t K = k_max;
@@ -1338,11 +1385,14 @@ PB_API int pb_plan(pb_handle* h, int32_t height, int32_t width, int32_t op, int3
   h->w_U = p.work_alloc(K * h->n_out);
   h->w_G = p.work_alloc(2 * K * K); h->w_M = p.work_alloc(2 * K * K); h->w_R = p.work_alloc(K * K);
   h->w_sv = p.work_alloc(K); h->w_met = p.work_alloc(4 + 2 * K);      // (dist^2, not-close count) per problem slot
-  h->w_x = p.work_alloc((size_t)h->n_in);
+  h->w_x = p.work_alloc((size_t)h->n_x);
   h->n_splitk = kSplitFloats; h->w_splitk = p.work_alloc(kSplitFloats);
   h->w_cvt = p.work_alloc(h->t16 ? h->n_cvt * K : 0);
   h->sizes.packed_weight_bytes = h->packed_top; h->sizes.primal_cache_bytes = h->cache_top; h->sizes.workspace_bytes = h->work_top;
-  h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out;
+  h->sizes.n_in = h->n_in; h->sizes.n_out = h->n_out; h->sizes.n_x = h->n_x;
+  if (h->dec_val >= 0) {
+    h->sizes.in_channels = h->vals[h->dec_val].C; h->sizes.in_h = h->dec_H; h->sizes.in_w = h->dec_W;
+  } else { h->sizes.in_channels = h->cfg.in_channels; h->sizes.in_h = height; h->sizes.in_w = width; }
   if (sizes) *sizes = h->sizes;
   h->planned = true;
   return PB_OK;
@@ -1453,6 +1503,23 @@ PB_API int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx,
   h->slot_point[slot] = 1;
   h->point = std::all_of(h->slot_point.begin(), h->slot_point.end(), [](char c) { return c != 0; });
   return PB_OK;
+}
+
+// Decoder side (PB_OP_DEC), the NONLINEAR map: replaces the cached mid-block output by `h_in` ([C][H][W] like get_h returns it) and
+// re-runs the decoder half on the skip connections of the last pb_set_point: eps_out = get_h_to_e(x_t, t, ctx, input_h = h_in)
+// (utils.py:529-635).  The linearisation point moves to h_in with it.
+PB_API int pb_decode_from(pb_handle* h, const float* h_in, float* eps_out, void* stream) {
+  if (int e = check_ready(h, 1, true)) return e;
+  if (h->dec_val < 0) return fail(h, PB_ESTATE, "pb_decode_from needs a plan with op = PB_OP_DEC");
+  if (h->slots > 1) return fail(h, PB_ESTATE, "pb_decode_from does not take problem slots");
+  if (!h_in) return fail(h, PB_EINVAL, "null pointer");
+  drop_graph(h);
+  h->rnd = h->rnd_p;
+  const Val& v = h->vals[h->dec_val];
+  // [C][rows] -> [rows][C], rounded like the kernel that normally writes this value (its consumers are GEMM operands)
+  if (const char* e = pbk_transpose(h->P(h->dec_val), v.C, 0, 0, h_in, v.rows, 0, 0, 1, 1, v.C, (int)v.rows, 0.f, h->rnd, stream))
+    return fail(h, PB_ECUDA, e);
+  return run_primal(h, nullptr, 0.f, nullptr, eps_out, stream, (size_t)h->dec_op + 1);
 }
 
 PB_API int pb_jvp(pb_handle* h, const float* V, int32_t k, float* U, void* stream) {

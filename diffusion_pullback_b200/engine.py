@@ -12,7 +12,7 @@ import torch
 
 from . import _native as N
 
-PB_OP = {"mid": 0, "up": 1, "full": 2}          # "full": the whole conditional U-Net, x_t -> eps (block_idx 0)
+PB_OP = {"mid": 0, "up": 1, "full": 2, "dec": 3}   # "full": the whole U-Net, x_t -> eps; "dec": the decoder side h -> eps (block_idx 0)
 _ERRORS = {-1: ValueError, -2: RuntimeError, -3: RuntimeError, -4: KeyError}
 
 
@@ -76,8 +76,9 @@ class PullbackEngine:
         self.sizes = N.PbSizes()
         self._ck(self.L.pb_plan(self.h, height, width, PB_OP[op], int(block_idx), int(k_max), int(ctx_len), C.byref(self.sizes)))
         self.k_max, self.height, self.width, self.ctx_len = int(k_max), height, width, int(ctx_len)
-        self.n_in, self.n_out = int(self.sizes.n_in), int(self.sizes.n_out)
+        self.n_in, self.n_out, self.n_x = int(self.sizes.n_in), int(self.sizes.n_out), int(self.sizes.n_x)
         self.h_shape = (int(self.sizes.out_channels), int(self.sizes.out_h), int(self.sizes.out_w))
+        self.in_shape = (int(self.sizes.in_channels), int(self.sizes.in_h), int(self.sizes.in_w))
         z = lambda n: torch.zeros(max(int(n), 16), dtype=torch.uint8, device=self.device)
         self.packed, self.cache, self.work = z(self.sizes.packed_weight_bytes), z(self.sizes.primal_cache_bytes), z(self.sizes.workspace_bytes)
         self.stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
@@ -189,7 +190,7 @@ class PullbackEngine:
         if slot:
             self._ck(self.L.pb_select_slot(self.h, int(slot)))
         x = self._f32(x, (-1,))
-        assert x.numel() == self.n_in, "x_t shape does not match the planned geometry"
+        assert x.numel() == self.n_x, "x_t shape does not match the planned geometry"
         if ctx is not None:
             ctx = self._f32(ctx, (-1,))
             assert ctx.numel() == self.ctx_len * self.cfg["cross_attention_dim"], "encoder_hidden_states shape mismatch"
@@ -200,6 +201,17 @@ class PullbackEngine:
         self._exit()
         self._keep = (x, ctx)
         return h_out
+
+    def decode_from(self, h_in, want_eps=True):
+        """Decoder side (op='dec'): replace the cached mid-block output by `h_in` [1, C, H, W] and re-run the decoder half on the
+        skip connections of the last `set_point` (`get_h_to_e`, utils.py:529-635); returns eps [1, c, H, W]."""
+        h_in = self._f32(h_in, (-1,))
+        assert h_in.numel() == self.n_in, "h shape does not match the planned geometry"
+        eps = torch.empty((1,) + self.h_shape, device=self.device) if want_eps else None
+        self._enter()
+        self._ck(self.L.pb_decode_from(self.h, self._p(h_in), self._p(eps), self._st()))
+        self._exit()
+        return eps
 
     def jvp(self, V):
         V = self._f32(V, (-1, self.n_in))

@@ -34,7 +34,11 @@ enum pb_unet_kind {
   PB_UNET_UNCOND = 1  /* diffusers UNet2DModel (DDPM CelebA-HQ ...): get_h_uncond, utils.py:114-163   */
 };
 enum pb_op { PB_OP_MID = 0, PB_OP_UP = 1,   /* `op='down'` raises in the reference  */
-             PB_OP_FULL = 2 };               /* the whole U-Net: x_t -> eps (up path, conv_norm_out, SiLU, conv_out); block_idx 0 */
+             PB_OP_FULL = 2,                 /* the whole U-Net: x_t -> eps (up path, conv_norm_out, SiLU, conv_out); block_idx 0 */
+             PB_OP_DEC = 3 };                /* decoder side (get_h_to_e, utils.py:529-635): the map h -> eps with h the mid-block output and
+                                                the skip connections of x_t held fixed; block_idx 0.  n_in = numel(h), n_out = numel(x_t):
+                                                pb_jvp / pb_vjp / pb_pullback then act on J_dec = d eps / d h (local_decoder_pullback_zt,
+                                                utils.py:818-898); pb_set_point takes x_t as before (h_out receives eps) */
 
 #define PB_MAX_LEVELS 8
 
@@ -68,8 +72,10 @@ typedef struct pb_sizes {
   size_t packed_weight_bytes;                /* both conv/linear layouts, TF32-rounded */
   size_t primal_cache_bytes;                 /* linearisation cache for one (x_t, t, prompt) */
   size_t workspace_bytes;                    /* k_max tangents/cotangents + scratch */
-  int64_t n_in, n_out;                       /* numel(x_t), numel(h) */
+  int64_t n_in, n_out;                       /* numel(x_t), numel(h); decoder side (PB_OP_DEC): numel(h), numel(eps) */
   int32_t out_channels, out_h, out_w;
+  int32_t in_channels, in_h, in_w;           /* shape of the tangent input: x_t, or h on the decoder side */
+  int64_t n_x;                               /* numel(x_t) -- what pb_set_point reads, whatever the op */
 } pb_sizes;
 
 typedef struct pb_iter_info {
@@ -94,6 +100,10 @@ int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n, void* 
  * cache.  `primal_cache` / `workspace` are the caller's regions.  Optionally returns h (NCHW) in h_out. */
 int pb_set_point(pb_handle* h, const float* x, float t, const float* ctx, void* primal_cache, void* workspace,
                  float* h_out, void* stream);
+/* Decoder side (op = PB_OP_DEC) only, the nonlinear map get_h_to_e (utils.py:529-635): replaces the mid-block output cached by the
+ * last pb_set_point by h_in ([C][H][W] as get_h returns it) and re-runs the decoder half on the same skip connections; eps_out
+ * (optional) receives the noise prediction [in_channels][H][W].  The linearisation point of pb_jvp / pb_vjp moves to h_in. */
+int pb_decode_from(pb_handle* h, const float* h_in, float* eps_out, void* stream);
 
 /* Problem slots (throughput mode; the reference solves its problems one process after another, scripts of SURVEY.md s.3.1):
  * `slots` independent problems (x_t, t, ctx) share the handle's weights and run their tangent columns as ONE batch, so the

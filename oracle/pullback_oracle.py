@@ -176,3 +176,83 @@ def parity_report(s, vT, s_ref, vT_ref, u=None, u_ref=None):
         rep["u_cos"] = [float(c) for c in cu]
         rep["u_subspace"] = float((B.T @ A).pow(2).sum() / k)
     return rep
+
+
+# ------------------------------------------------------------------------------------
+# decoder side
+# ------------------------------------------------------------------------------------
+def get_h_to_e(unet, sample, timestep, encoder_hidden_states=None, input_h=None, op=None, block_idx=None):
+    """Follows `src/utils/utils.py:529-635`: the forward up to the mid block on `sample` (one latent), then the mid-block
+    output is REPLACED by the rows of `input_h` ([pca_rank, C, H, W]) with the skip connections and the prompt repeated
+    pca_rank times, then up blocks, conv_norm_out, SiLU, conv_out.  Only ('mid', 0) substitutes (the reference asserts
+    `op in ['mid', 'down']` and has no substitution for 'down')."""
+    assert op in ("mid", "down"), "up block is not implemented yet"
+    k = input_h.size(0)
+    t = timestep
+    if not torch.is_tensor(t):
+        t = torch.tensor([t], dtype=torch.float64 if isinstance(t, float) else torch.int64, device=sample.device)
+    elif t.dim() == 0:
+        t = t[None].to(sample.device)
+    t = t.expand(sample.shape[0])
+    emb = unet.time_embedding(unet.time_proj(t).to(dtype=unet.dtype))
+    x = unet.conv_in(sample)
+    skips = (x,)
+    for blk in unet.down_blocks:
+        if getattr(blk, "has_cross_attention", False):
+            x, res = blk(hidden_states=x, temb=emb, encoder_hidden_states=encoder_hidden_states)
+        else:
+            x, res = blk(hidden_states=x, temb=emb)
+        skips += res
+    x = unet.mid_block(x, emb, encoder_hidden_states=encoder_hidden_states)
+    if op == "mid" and block_idx == 0:
+        x = input_h.view(k, *x.shape[1:])
+        skips = tuple(s.repeat(k, 1, 1, 1) for s in skips)
+        encoder_hidden_states = encoder_hidden_states.repeat(k, 1, 1)
+    for blk in unet.up_blocks:
+        n = len(blk.resnets)
+        res, skips = skips[-n:], skips[:-n]
+        if getattr(blk, "has_cross_attention", False):
+            x = blk(hidden_states=x, temb=emb, res_hidden_states_tuple=res, encoder_hidden_states=encoder_hidden_states)
+        else:
+            x = blk(hidden_states=x, temb=emb, res_hidden_states_tuple=res, upsample_size=None)
+    if unet.conv_norm_out:
+        x = unet.conv_act(unet.conv_norm_out(x))
+    return unet.conv_out(x)
+
+
+def local_decoder_pullback_zt(unet, sample, timestep, encoder_hidden_states=None, op=None, block_idx=None, pca_rank=50,
+                              min_iter=10, max_iter=100, convergence_threshold=None, v0=None):
+    """Follows `src/utils/utils.py:818-898`: the same subspace iteration on g(h) = get_h_to_e(h) at h = get_h(sample):
+    U = J_dec V by forward-mode JVPs, W = U^T J_dec by one reverse pass per row, SVD of W.  Returns the reference's triple
+    (v.T [numel(h), k], sqrt(s), u [k, numel(x)]) -- it returns the h-space directions first (`:895-896`).  With
+    `convergence_threshold=None` (the reference's default, whose `allclose(atol=None)` raises) all `max_iter` iterations run."""
+    h = get_h(unet, sample, timestep, encoder_hidden_states, op=op, block_idx=block_idx)
+    g = lambda hh: get_h_to_e(unet, sample, timestep, encoder_hidden_states, input_h=hh, op=op, block_idx=block_idx)
+    n_h = h[0].numel()
+    if v0 is None:
+        vT = torch.randn(n_h, pca_rank, device=sample.device, dtype=torch.float)
+        vT, _ = torch.linalg.qr(vT)
+        v = vT.T
+    else:
+        v = v0
+    v = v.reshape(-1, *h.shape[1:])
+    s = u = None
+    for i in range(max_iter):
+        v_prev = v.detach().clone()
+        u = torch.cat([torch.func.jvp(g, (h,), (vi[None],))[1].detach() for vi in v], 0)                 # [k, c, H, W]
+        w = torch.autograd.functional.jacobian(lambda hh: (u * g(hh)).flatten(1).sum(1), h).reshape(-1, n_h)
+        _, s, vv = torch.linalg.svd(w, full_matrices=False)
+        v = vv.view(-1, *h.shape[1:])
+        if convergence_threshold is not None and torch.allclose(v_prev, v, atol=convergence_threshold) and i > min_iter:
+            break
+    return v.reshape(-1, n_h).T.detach(), s.sqrt().detach(), u.reshape(u.shape[0], -1).detach()
+
+
+def inv_jac_zt(unet, sample, timestep, encoder_hidden_states=None, op=None, block_idx=None, u=None, perturb_h=1e-1):
+    """Follows `src/utils/utils.py:1117-1160`: the normalised gradient of ||h + perturb_h u - get_h(x)|| at x = sample."""
+    h = get_h(unet, sample, timestep, encoder_hidden_states, op=op, block_idx=block_idx)
+    perturbed_h = (h + perturb_h * u.view(-1, *h.shape[1:])).detach()
+    jacx = lambda x: (perturbed_h - get_h(unet, x, timestep, encoder_hidden_states, op=op, block_idx=block_idx)).view(1, -1).norm(dim=-1)
+    jac = torch.autograd.functional.jacobian(jacx, sample)
+    vT = jac.view(1, -1)
+    return vT / vT.norm(dim=1, keepdim=True)

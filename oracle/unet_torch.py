@@ -627,6 +627,7 @@ class UNet2DConditionModel(nn.Module):
                 self.up_blocks.append(blk)
             # diffusers 0.11.0 UNet2DConditionModel tail: GroupNorm -> SiLU -> Conv3x3(C0 -> out_channels = in_channels)
             self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, boc[0], eps=cfg.norm_eps)
+            self.conv_act = nn.SiLU()                                   # diffusers' attribute name (read by get_h_to_e, utils.py:631)
             self.conv_out = nn.Conv2d(boc[0], cfg.in_channels, 3, padding=1)
 
     def forward(self, sample, timestep, encoder_hidden_states=None):

@@ -23,7 +23,7 @@ def hostsim():
 
 
 def make_engine(L, name, op, bi, k, opts=None):
-    m = UT.build_unet(name, build_up=(op in ("up", "full")))
+    m = UT.build_unet(name, build_up=(op in ("up", "full", "dec")))
     x, t, ctx = UT.synthetic_inputs(name)
     eng = PullbackEngine(unet_config(m), x.shape[2], x.shape[3], op, bi, k, ctx.shape[1] if ctx is not None else 0, "cpu", _lib=L)
     for kk, v in (opts or {}).items():
@@ -333,6 +333,50 @@ def test_stochastic_step_yh_scheduler_and_uncond_loop(hostsim):
     sched.learn_sigma = True
     with pytest.raises(NotImplementedError):
         sched.step(et, osched.timesteps[3], xt)
+
+
+@pytest.mark.parametrize("f16", [0, 1])
+def test_decoder_side_operator_and_pullback(hostsim, monkeypatch, f16):
+    """SURVEY.md s.8f row 4 on the engine (op = PB_OP_DEC): eps from pb_set_point, the nonlinear decoder from a substituted h
+    (pb_decode_from = get_h_to_e), one JVP / VJP of J_dec = d eps / d h against torch autograd of the oracle restatement (pinned to
+    the reference's get_h_to_e), the adjoint identity, and the subspace iteration against the restated local_decoder_pullback_zt --
+    in the exact fp32 policy and in the all-fp16 tangent plan."""
+    if f16:
+        monkeypatch.setenv("PB_HOSTSIM_F16", "1")
+    k = 3
+    eng, m, x, t, ctx = make_engine(hostsim, "sd_tiny", "dec", 0, k, None if f16 else EXACT)
+    tol = 1.2e-2 if f16 else 3e-5                                   # fp16 storage on a 32-channel fixture: few terms per sum (DESIGN.md s.5)
+    h = PO.get_h(m, x, t, ctx, op="mid", block_idx=0)
+    assert eng.n_in == h[0].numel() and eng.n_out == x[0].numel() == eng.n_x and eng.in_shape == tuple(h.shape[1:])
+    eps = eng.set_point(x, float(t), ctx, want_h=True)
+    assert rel(eps, m(x, t, encoder_hidden_states=ctx)) < (5e-3 if f16 else 1e-5)
+    g = lambda hh: PO.get_h_to_e(m, x, t, ctx, input_h=hh, op="mid", block_idx=0)
+    torch.manual_seed(0)
+    V = PO.initial_subspace(eng.n_in, k)
+    U = eng.jvp(V)
+    Uref = torch.cat([torch.func.jvp(g, (h,), (v.view_as(h),))[1] for v in V], 0).reshape(k, -1)
+    assert rel(U, Uref) < tol
+    G = torch.randn_like(Uref)
+    W = eng.vjp(G)
+    Wref = torch.autograd.functional.jacobian(lambda hh: (G.view(k, *x.shape[1:]) * g(hh)).flatten(1).sum(1), h).reshape(k, -1)
+    assert rel(W, Wref) < tol
+    lhs, rhs = float((U * G).sum()), float((W * V).sum())
+    assert abs(lhs - rhs) < (2e-3 if f16 else 1e-4) * float(U.norm() * G.norm())
+    U2 = eng.jvp(V)                                                  # the skip tangents are re-zeroed after a transpose pass
+    assert torch.equal(U, U2)
+    # subspace iteration on J_dec
+    u, s, vT, info = eng.pullback(V, 3, 3, 0.0)
+    uo, so, vo = PO.local_decoder_pullback_zt(m, x, t, ctx, op="mid", block_idx=0, pca_rank=k, min_iter=3, max_iter=3, v0=V)
+    assert torch.allclose(s, so, rtol=5e-3 if f16 else 2e-4)
+    assert rel(vT.abs(), uo.T.abs()) < (3e-2 if f16 else 2e-3)       # h-space directions (the reference returns them first)
+    # the nonlinear decoder from another h, then back
+    h2 = 0.7 * h + 0.05
+    e2 = eng.decode_from(h2)
+    assert rel(e2, g(h2)) < (5e-3 if f16 else 1e-5)
+    e1 = eng.decode_from(h)
+    assert rel(e1, eps) < (5e-3 if f16 else 1e-6)
+    with pytest.raises(Exception):
+        make_engine(hostsim, "sd_tiny", "dec", 1, k)
 
 
 def test_probe_bookkeeping_and_dump(hostsim, tmp_path, monkeypatch):

@@ -311,3 +311,44 @@ def test_uncond_forward_loop_restatement_matches_verbatim_reference(kw, tmp_path
         assert isinstance(ours, tuple) and ref[2] == ours[2] and float(ref[1]) == float(ours[1]) and torch.equal(ref[0], ours[0])
     else:
         assert torch.equal(ref, ours)
+
+
+# ---- decoder side: the restatements against the reference's own functions run verbatim ----
+@pytest.mark.skipif(not RS.available(), reason="reference sources not on this machine")
+def test_decoder_side_restatements_match_verbatim_reference():
+    """`get_h_to_e` (utils.py:529-635), `local_decoder_pullback_zt` (:818-898) and `inv_jac_zt` (:1117-1160) bound onto the oracle
+    U-Net exactly like utils.py:327-334 and run verbatim; the reference iteration is given an explicit threshold (its default
+    `None` makes `torch.allclose` raise once i > min_iter) and a chunk size equal to the rank (its `v.chunk(k // chunk_size)`)."""
+    U = RS.load()
+    m = UT.build_unet("sd_tiny")
+    x, t, ctx = UT.synthetic_inputs("sd_tiny")
+    m.after_res = m.after_sa = False                                   # read by get_h_to_e (utils.py:540)
+    m.get_h = types.MethodType(U.get_h, m)
+    m.get_h_to_e = types.MethodType(U.get_h_to_e, m)
+    h = PO.get_h(m, x, t, ctx, op="mid", block_idx=0)
+    hs = torch.cat([h, 0.5 * h + 0.1, -h], 0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = m.get_h_to_e(sample=x, timestep=t, encoder_hidden_states=ctx, input_h=hs, op="mid", block_idx=0)
+    ours = PO.get_h_to_e(m, x, t, ctx, input_h=hs, op="mid", block_idx=0)
+    assert torch.equal(ref, ours)
+    # substituting the true h reproduces the full forward
+    assert torch.allclose(ours[:1], m(x, t, encoder_hidden_states=ctx), atol=1e-5, rtol=1e-4)
+    k = 2
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ur, sr, vr = U.local_decoder_pullback_zt(m, x, t, ctx, op="mid", block_idx=0, pca_rank=k, chunk_size=k, min_iter=1, max_iter=3,
+                                                 convergence_threshold=0.0)
+    torch.manual_seed(0)
+    uo, so, vo = PO.local_decoder_pullback_zt(m, x, t, ctx, op="mid", block_idx=0, pca_rank=k, min_iter=1, max_iter=3, convergence_threshold=0.0)
+    assert ur.shape == uo.shape == (h[0].numel(), k) and vr.shape == vo.shape == (k, x[0].numel())
+    assert torch.allclose(sr, so, rtol=1e-4) and torch.allclose(ur.abs(), uo.abs(), atol=1e-4) and torch.allclose(vr.abs(), vo.abs(), atol=1e-4, rtol=1e-3)
+    # inv_jac_zt
+    m.inv_jac_zt = types.MethodType(U.inv_jac_zt, m)
+    ud = torch.randn(h[0].numel(), generator=torch.Generator().manual_seed(3))
+    with contextlib.redirect_stdout(io.StringIO()):
+        vref = m.inv_jac_zt(sample=x, timestep=t, encoder_hidden_states=ctx, op="mid", block_idx=0, u=ud)
+    vour = PO.inv_jac_zt(m, x, t, ctx, op="mid", block_idx=0, u=ud)
+    assert torch.allclose(vref, vour, atol=1e-6)
+    # ... which is -J^T u normalised
+    w = torch.autograd.functional.vjp(lambda z: PO.get_h(m, z, t, ctx, op="mid", block_idx=0), x, ud.view_as(h))[1].reshape(1, -1)
+    assert torch.allclose(vour, -w / w.norm(), atol=1e-5)

@@ -258,6 +258,41 @@ def test_full_uncond_unet_eps_and_ddim_vs_oracle():
         assert rel(zs[i + 1], zo) < 1e-2
 
 
+def test_decoder_side_on_the_device():
+    """SURVEY.md s.8f row 4 through the patched U-Net on the GPU (sd_small): `get_h_to_e` from substituted mid-block features,
+    `local_decoder_pullback_zt` (the subspace iteration on d eps / d h; returns h-space directions, sqrt singular values, eps-space
+    images) and `inv_jac_zt` (= -J^T u normalised), against the oracle restatements that tests/test_oracle.py pins to the
+    reference's own functions.  Tolerances: 5e-3 on the nonlinear forward, 1e-2 on one direction, 2e-3 on the singular values
+    (sd_small: 64-256 channels, 2 iterations)."""
+    name = "sd_small"
+    m = UT.build_unet(name)
+    unet = PB.patch_unet(SY.SyntheticUNet(name, device=DEV))
+    x, t, ctx = SY.synthetic_inputs(name)
+    xd, cd = x.to(DEV), ctx.to(DEV)
+    h = PO.get_h(m, x, t, ctx, op="mid", block_idx=0)
+    hs = torch.cat([h, 0.8 * h + 0.05], 0)
+    e = unet.get_h_to_e(sample=xd, timestep=t, encoder_hidden_states=cd, input_h=hs.to(DEV), op="mid", block_idx=0)
+    eref = PO.get_h_to_e(m, x, t, ctx, input_h=hs, op="mid", block_idx=0)
+    assert e.shape == eref.shape and rel(e, eref) < 5e-3
+    with pytest.raises(AssertionError):
+        unet.get_h_to_e(sample=xd, timestep=t, encoder_hidden_states=cd, input_h=hs.to(DEV), op="up", block_idx=0)
+    k = 2
+    torch.manual_seed(0)
+    v0 = PO.initial_subspace(h[0].numel(), k)
+    u, s, vT, info = unet.local_decoder_pullback_zt(xd, t, cd, op="mid", block_idx=0, pca_rank=k, min_iter=2, max_iter=2,
+                                                    v0=v0.to(DEV), return_info=True)
+    uo, so, vo = PO.local_decoder_pullback_zt(m, x, t, ctx, op="mid", block_idx=0, pca_rank=k, min_iter=2, max_iter=2, v0=v0)
+    assert u.shape == uo.shape == (h[0].numel(), k) and vT.shape == vo.shape == (k, x[0].numel()) and info["iters_done"] == 2
+    assert torch.allclose(s.cpu(), so, rtol=2e-3), (s, so)
+    ov = (uo.T @ u.cpu()).pow(2).sum() / k                           # subspace overlap of the h-space directions
+    assert float(ov) > 0.999
+    assert rel(vT.cpu().abs(), vo.abs()) < 2e-2
+    ud = torch.randn(h[0].numel(), generator=torch.Generator().manual_seed(3))
+    vi = unet.inv_jac_zt(sample=xd, timestep=t, encoder_hidden_states=cd, op="mid", block_idx=0, u=ud.to(DEV))
+    vref = PO.inv_jac_zt(m, x, t, ctx, op="mid", block_idx=0, u=ud)
+    assert vi.shape == vref.shape and rel(vi, vref) < 1e-2 and abs(float(vi.norm()) - 1.0) < 1e-5
+
+
 def test_local_basis_cache_round_trip_on_the_device(tmp_path):
     """SURVEY.md s.8f row 3 on the GPU (edit.py:218-268): a fresh computation through the patched U-Net writes u- / s- / vT-<name>.pt
     (+ the spectrum plot and the PCA picture of vT), a second call re-uses the files without running the pullback, the loaded
