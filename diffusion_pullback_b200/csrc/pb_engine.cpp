@@ -1558,12 +1558,15 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
   const size_t vbytes = (size_t)kt * h->n_in * 4;
   CK(pbk_copy(Vb, V0, vbytes, stream));
   // One iteration (utils.py:758-799): Vprev = Vb -> U = J Vprev -> W = U^T J -> (s, Va) = svd(W); then Vb <- Va.
+  // the iteration (and the CUDA graph captured from it) works on handle-owned buffers; the caller's u / s receive one copy at the
+  // end, so a caller that hands over fresh output tensors for every problem re-uses the graph instead of re-capturing it
+  float* ui = h->WP(h->w_U); float* si = h->WP(h->w_sv);
   auto iteration = [&]() -> int {
-    if (int e = run_jvp(h, Vb, kt, u, stream)) return e;
-    if (int e = run_vjp(h, u, kt, Wm, stream)) return e;
+    if (int e = run_jvp(h, Vb, kt, ui, stream)) return e;
+    if (int e = run_vjp(h, ui, kt, Wm, stream)) return e;
     for (int p = 0; p < P; ++p) {
       const size_t o = (size_t)p * k * h->n_in;
-      if (int e = run_ortho(h, Wm + o, Vb + o, k, tol, Va + o, s + (size_t)p * k, met + 2 * p, stream)) return e;
+      if (int e = run_ortho(h, Wm + o, Vb + o, k, tol, Va + o, si + (size_t)p * k, met + 2 * p, stream)) return e;
     }
     return PB_OK;
   };
@@ -1572,7 +1575,7 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
   for (int i = 0; i < max_iter; ++i) {
     bool replayed = false;
     if (h->use_graph && !h->profiling) {
-      if (h->graph && (h->graph_k != k || h->graph_tol != tol || h->graph_u != u || h->graph_s != s)) drop_graph(h);
+      if (h->graph && (h->graph_k != k || h->graph_tol != tol)) drop_graph(h);
       if (!h->graph && h->warm) {     // the first iteration ever runs eagerly (one-time kernel attribute setup)
         const char* e = pbk_graph_begin(stream);
         if (!e) {
@@ -1583,7 +1586,7 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
           h->launches = before;
           if (rc) { drop_graph(h); return rc; }
           if (e2) { drop_graph(h); return fail(h, PB_ECUDA, std::string("graph capture: ") + e2); }
-          h->graph_k = k; h->graph_tol = tol; h->graph_u = u; h->graph_s = s;
+          h->graph_k = k; h->graph_tol = tol;
           h->graph_nodes = nodes;
         } else {
           h->use_graph = 0;            // backend without graph support: launch directly
@@ -1610,6 +1613,8 @@ PB_API int pb_pullback(pb_handle* h, const float* V0, int32_t k, int32_t min_ite
     CK(pbk_copy(Vb, Va, vbytes, stream));
   }
   CK(pbk_copy(vT, Va, vbytes, stream));
+  if (u != ui) CK(pbk_copy(u, ui, (size_t)kt * h->n_out * 4, stream));
+  if (s != si) CK(pbk_copy(s, si, (size_t)kt * 4, stream));
   if (info) { info->iters_done = done; info->converged = converged; info->last_dist = std::sqrt(host_met[0]); }
   return PB_OK;
 }
