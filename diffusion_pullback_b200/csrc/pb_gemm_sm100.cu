@@ -59,6 +59,7 @@ struct alignas(64) Params {
   int conv, H, W, bw, bh, bb, tiles_w, tiles_h;
   CUtensorMap mapW;                    // split-K scratch as a [tile][split][128][BN] tensor
   int raster_b, mt, nt, items;
+  int pair;                            // CTA-pair kernel: tiles 2j and 2j + 1 are the two 128-row halves of pair-item j
   int full_tiles;                      // tiles [0, full_tiles) are whole items; every later tile is `splits` partial items
   int splits, kb_per_split;            // partial item s covers flat k-blocks [s*kb_per_split, (s+1)*kb_per_split)
   float* ws;
@@ -71,10 +72,10 @@ struct alignas(64) Params {
 
 using namespace pbtc;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 4;   // a CTA of a pair stages half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFF = STAGING_OFF + NBUF * EPI_BYTES;
@@ -93,6 +94,21 @@ __device__ __forceinline__ Tile decode_tile(const Params& p, int tile) {
   t.m0 = t.bat_b = t.bat_h = t.cx0 = t.cy0 = t.cb0 = t.split = t.partial = 0;
   t.tile_id = tile;
   int v = tile;
+  if (p.pair) {
+    // CTA-pair kernel (conv mode, or plain mode with nb = nh = 1): tiles 2j and 2j + 1 share the column tile and are row
+    // tiles 2m', 2m' + 1; a row tile past the end (odd count) lies outside the tensor: zero-filled loads, clipped stores
+    const int rank = v & 1; v >>= 1;
+    t.n0 = (v % p.nt) * BN;
+    int m = 2 * (v / p.nt) + rank;
+    if (p.conv) {
+      const int tw = m % p.tiles_w; m /= p.tiles_w;
+      const int th = m % p.tiles_h; m /= p.tiles_h;
+      t.cx0 = tw * p.bw; t.cy0 = th * p.bh; t.cb0 = m * p.bb;
+    } else {
+      t.m0 = m * BM;
+    }
+    return t;
+  }
   if (p.raster_b) {
     // tangent index fastest: the nb tiles that read the same broadcast A tile (attention probabilities) run at the same
     // time on neighbouring SMs, so A comes from HBM once and from L2 nb - 1 times
@@ -119,8 +135,14 @@ __device__ __forceinline__ Tile decode_tile(const Params& p, int tile) {
 template <int BN>
 __device__ __forceinline__ Tile decode_item(const Params& p, int item) {
   if (item < p.full_tiles) return decode_tile<BN>(p, item);
-  const int j = item - p.full_tiles;
-  Tile t = decode_tile<BN>(p, p.full_tiles + j / p.splits);
+  int j = item - p.full_tiles;
+  Tile t;
+  if (p.pair) {                        // items 2i, 2i + 1: the same split of the two tiles of a pair
+    const int rank = j & 1; j >>= 1;
+    t = decode_tile<BN>(p, p.full_tiles + 2 * (j / p.splits) + rank);
+  } else {
+    t = decode_tile<BN>(p, p.full_tiles + j / p.splits);
+  }
   t.split = j % p.splits;
   t.partial = 1;
   return t;
@@ -207,13 +229,25 @@ __device__ __forceinline__ void stage_chunk(uint8_t* buf, int r, const uint32_t 
   }
 }
 
-template <int BN, int STAGES, bool AB16, bool D16>
+// PAIR: the CTA-pair variant (fp16 operands).  The two CTAs of a cluster, on the two SMs of a TPC, own row tiles 2m' and
+// 2m' + 1 of the same column tile and run them as ONE 256 x BN tcgen05.mma.cta_group::2 issued by the leader (cluster
+// rank 0): each CTA stages its own 128 rows of A and HALF of the B tile, so a k-block costs a CTA 16 KB + BN * 64 B of
+// shared-memory writes and as many reads instead of 16 KB + BN * 128 B -- the one-CTA 128 x 160 tile needs 230 B per clock
+// of shared-memory bandwidth (36 KB written by TMA + 36 KB read by the tensor core per 320-clock k-block) against the 128 B
+// per clock an SM has, which is what held the big convolutions at half the tensor peak.  Protocol: both producers load
+// into their own stage s and signal the LEADER's full barrier (one expect_tx of both CTAs' bytes); the leader's commits
+// arrive on the empty / accumulator-full barriers of BOTH CTAs (multicast); the epilogue warps of both CTAs release an
+// accumulator stage on the leader's barrier (8 arrivals).  Epilogue, staging, residual and split-K paths are per CTA and
+// unchanged.
+template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
+  static_assert(!PAIR || AB16, "the CTA-pair variant takes fp16 operands");
   using OutT = typename std::conditional<D16, __half, float>::type;
   constexpr int KB_ELEMS = AB16 ? BK16 : BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, PAIR>;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   uint8_t* staging = smem + S::STAGING_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -236,19 +270,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], PAIR ? 8 : 4); }
     for (int i = 0; i < NBUF; ++i) mbar_init(&r_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_base_smem)),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {        // collective over the pair: warp 1 of both CTAs, the same shared-memory offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_base_smem)),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_base_smem)),
+                   "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -262,6 +305,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     // kernel's SASS), which made a k-block's two loads cost more issue time than its MMAs take to execute.
     {
       int stage = 0; uint32_t phase = 0;
+      const uint32_t full_leader = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0u;   // the leader's full barriers
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
         const Tile t = decode_item<BN>(p, item);
         const int kb_begin = t.partial ? t.split * p.kb_per_split : 0;
@@ -274,7 +318,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          if (elect_one()) {
+          if constexpr (PAIR) {
+            const uint32_t fb = full_leader + uint32_t(stage) * 8u;
+            const int nb0 = t.n0 + int(cta_rank) * (BN / 2);
+            if (elect_one()) {
+              // the leader expects both CTAs' bytes; a peer load that lands first only drives the count negative
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * p.tx_bytes[0]);
+              if (p.conv) {
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                tma_load_4d_2sm(sa, &p.mapA[0], fb, kb * KB_ELEMS, t.cx0 + dx, t.cy0 + dy, t.cb0);
+                tma_load_4d_2sm(sb, &p.mapB[0], fb, kb * KB_ELEMS, tap, nb0, 0);
+              } else {
+                tma_load_4d_2sm(sa, &p.mapA[0], fb, kb * KB_ELEMS, t.m0, 0, 0);
+                tma_load_4d_2sm(sb, &p.mapB[0], fb, kb * KB_ELEMS, nb0, 0, 0);
+              }
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[stage], p.tx_bytes[s]);
             if (p.conv) {
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -294,20 +353,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && cta_rank == 0) {
     // =========================== MMA issuer ===========================
-    // the whole warp walks the loop; one elected lane issues (see elect_one)
+    // the whole warp walks the loop; one elected lane issues (see elect_one); of a CTA pair only the leader's
     {
-      // instruction descriptor: fp32 accumulate; A/B format tf32 (2) or f16 (0); N >> 3, M >> 4
+      // instruction descriptor: fp32 accumulate; A/B format tf32 (2) or f16 (0); N >> 3, M >> 4 (256 rows over a pair)
       constexpr uint32_t idesc = (1u << 4) | (AB16 ? 0u : (2u << 7) | (2u << 10)) | (uint32_t(BN >> 3) << 17) |
-                                 (uint32_t(BM >> 4) << 24);
+                                 (uint32_t((PAIR ? 2 * BM : BM) >> 4) << 24);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t smem_u = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
       int stage = 0; uint32_t phase = 0;
       int li = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
         const bool partial = item >= p.full_tiles;
-        const int kb_begin = partial ? ((item - p.full_tiles) % p.splits) * p.kb_per_split : 0;
+        const int kb_begin = partial ? (((item - p.full_tiles) >> (PAIR ? 1 : 0)) % p.splits) * p.kb_per_split : 0;
         const int kb_end = partial ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
         const int as = li & 1;
         mbar_wait(&tmem_empty_bar[as], ((li >> 1) & 1) ^ 1);
@@ -323,21 +382,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // advance 8 tf32 / 16 halves = 32 bytes along K inside the swizzle row: +2 in the 16-byte address field
-              if constexpr (AB16)
+              if constexpr (PAIR)
+                mma_f16_2sm(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
+              else if constexpr (AB16)
                 mma_f16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
               else
                 mma_tf32(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, ((kb - kb_begin) | k) ? 1u : 0u);
             }
-            tcgen05_commit(&empty_bar[stage]);
+            if constexpr (PAIR) tcgen05_commit_2sm(&empty_bar[stage]); else tcgen05_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) tcgen05_commit(&tmem_full_bar[as]);
+        if (elect_one()) {
+          if constexpr (PAIR) tcgen05_commit_2sm(&tmem_full_bar[as]); else tcgen05_commit(&tmem_full_bar[as]);
+        }
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // =========================== epilogue ===========================
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // tile row
@@ -346,6 +409,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     // made every UTMASTG / UTMALDG of the epilogue an ELECT / R2UR.BROADCAST waterfall -- ten per 128 x 160 tile, which is what
     // paced the short-K linears
     const bool w0 = (warp == 2);
+    const uint32_t tmem_empty_leader = PAIR ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0u;
     uint32_t gch = 0;                         // chunks pushed through the staging ring so far (this CTA)
     uint32_t r_par = 0;                       // bit b: parity of the next residual load into staging buffer b
     constexpr int TAILQ = D16 ? 7 : 3;        // TMA stores clip the inner dimension in 16-byte units
@@ -391,7 +455,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         if (c == nchunks - 1) {
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + uint32_t(as) * 8u);
+            else mbar_arrive(&tmem_empty_bar[as]);
+          }
         }
         const bool full = (nc + EPI_W <= p.N);
         if (c < ntma) {
@@ -441,9 +508,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     tcgen05_fence_before();
   }
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // no CTA leaves while its peer may still signal its barriers / read its tiles
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -567,14 +638,25 @@ static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
 static int sm_count() { return pbhost::sm_count(); }
 
-template <int BN, int STAGES, bool AB16, bool D16>
+template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false>
 static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
-  using S = Smem<BN, STAGES>;
+  using S = Smem<BN, STAGES, PAIR>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(2 * BN <= 512 && BN <= ACC_STRIDE, "two accumulator stages must fit TMEM");
-  if (const char* err = pbhost::optin_smem(gemm_tc_kernel<BN, STAGES, AB16, D16>, S::TOTAL)) return err;
-  gemm_tc_kernel<BN, STAGES, AB16, D16><<<grid, NTHREADS, S::TOTAL, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  if (const char* err = pbhost::optin_smem(gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR>, S::TOTAL)) return err;
+  cudaError_t e;
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR>, p);
+  } else {
+    gemm_tc_kernel<BN, STAGES, AB16, D16><<<grid, NTHREADS, S::TOTAL, st>>>(p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return cudaGetErrorString(e);
   if (p.splits > 1) {
     const int ntail = (p.items - p.full_tiles) / p.splits;
@@ -584,6 +666,38 @@ static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
     e = cudaGetLastError();
   }
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// CTA-pair kernels: 256 x 160 (6 stages of 26 KB) and 256 x 256 (5 stages of 32 KB)
+template <bool D16>
+static const char* launch_pair(int BN, const Params& p, int grid, cudaStream_t st) {
+  if (BN == 160) return launch_t<160, 6, true, D16, true>(p, grid, st);
+  if (BN == 256) return launch_t<256, 5, true, D16, true>(p, grid, st);
+  return "gemm: unsupported pair tile width";
+}
+
+// co-resident CTA pairs of the pair kernel on the current device (74 on a B200), cached per device
+static int pair_clusters() {
+  static int n[pbhost::kMaxDevices] = {};
+  const int dev = pbhost::current_device();
+  if (dev < 0 || dev >= pbhost::kMaxDevices) return 0;
+  if (!n[dev]) {
+    using S = Smem<256, 5, true>;
+    auto* fn = gemm_tc_kernel<256, 5, true, true, true>;
+    n[dev] = -1;
+    if (pbhost::optin_smem(fn, S::TOTAL) == nullptr) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * sm_count()); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = S::TOTAL;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int c = 0;
+      if (cudaOccupancyMaxActiveClusters(&c, fn, &cfg) == cudaSuccess && c > 0) n[dev] = c;
+      else (void)cudaGetLastError();
+    }
+  }
+  return n[dev] > 0 ? n[dev] : 0;
 }
 
 template <bool AB16, bool D16>
@@ -599,10 +713,12 @@ static const char* launch_bn(int BN, const Params& p, int grid, cudaStream_t st)
 // tuning hooks (scripts/bench_gemm.py): force a tile width (0 = heuristic), split policy (0 off, 1 heuristic,
 // >1 forced split count), allow BN = 160
 static int g_force_bn = 0, g_split = 1, g_use160 = 1, g_split_min_kb = 24;
+static int g_pair = getenv("PB_GEMM_PAIR") ? atoi(getenv("PB_GEMM_PAIR")) : 1;   // CTA-pair kernels (A/B switch)
 extern "C" __attribute__((visibility("default"))) void pb_gemm_tune(int force_bn, int split, int use160) {
   g_force_bn = force_bn; g_split = split; g_use160 = use160;
 }
 extern "C" __attribute__((visibility("default"))) void pb_gemm_tune_split_min_kb(int kb) { g_split_min_kb = kb; }
+extern "C" __attribute__((visibility("default"))) void pb_gemm_tune_pair(int on) { g_pair = on; }
 
 // Returns nullptr on success, else a static error string.  Stream-ordered, no host sync.
 const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
@@ -646,6 +762,18 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   else if (g.N <= 128 || g.N % 128 == 0) BN = 128;
   else if (g.N % 128 <= 64 && mt * nz * ((g.N + 63) / 64) <= 2L * nsm) BN = 64;
   if (g_force_bn) BN = g_force_bn;
+  // CTA-pair kernel (256-row tiles over two SMs, see gemm_tc_kernel): fp16 weight GEMMs and convolutions with at least one
+  // full wave of tiles; attention products (batched B, two segments) and the small-M layers keep the one-CTA kernel
+  int pair = 0;
+  int nsm_eff = nsm;
+  if (g_pair && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
+      (g.N % 256 == 0 || g.N % 160 == 0) && (!g_force_bn || g_force_bn == 160 || g_force_bn == 256)) {
+    const int ncl = pair_clusters();
+    const int pbn = g_force_bn ? g_force_bn : (g.N % 256 == 0 ? 256 : 160);
+    const long ptiles = ((mt + 1) / 2) * 2 * ((g.N + pbn - 1) / pbn);
+    if (ncl > 0 && g.N % pbn == 0 && ptiles >= 2L * ncl) { pair = 1; BN = pbn; nsm_eff = 2 * ncl; mt = ((mt + 1) / 2) * 2; }
+  }
+  p.pair = pair;
   const long nt = (g.N + BN - 1) / BN;
 
   int ktot = 0;
@@ -667,7 +795,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       // packed filter [N][9][C] as a (C, tap, N) tensor
       uint64_t bd[4] = {uint64_t(sg.K), 9, uint64_t(g.N), 1};
       uint64_t bs[3] = {uint64_t(sg.K) * aes, uint64_t(sg.ldb) * aes, uint64_t(sg.ldb) * aes};
-      const uint32_t brow = (uint32_t)std::min(BN, g.N);
+      const uint32_t brow = (uint32_t)std::min(pair ? BN / 2 : BN, g.N);
       uint32_t bbox[4] = {uint32_t(KB), 1, brow, 1};
       err = encode4x(&p.mapB[s], sg.B, ab16, bd, bs, bbox, 128);
       if (err) return err;
@@ -685,8 +813,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       err = encode_plainx(&p.mapA[s], sg.A, ab16, g.M, sg.K, sg.lda, sg.sAh, g.nh, sAb, nbA, KB, BM, 128, &p.a_hmul[s],
                           &p.a_bmul[s], &abytes);
       if (err) return err;
-      err = encode_plainx(&p.mapB[s], sg.B, ab16, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sBb, nbB, KB, BN, 128, &p.b_hmul[s],
-                          &p.b_bmul[s], &bbytes);
+      err = encode_plainx(&p.mapB[s], sg.B, ab16, g.N, sg.K, sg.ldb, sg.sBh, g.nh, sBb, nbB, KB, pair ? BN / 2 : BN, 128,
+                          &p.b_hmul[s], &p.b_bmul[s], &bbytes);
       if (err) return err;
       p.tx_bytes[s] = abytes + bbytes;
     }
@@ -734,7 +862,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   long full = tiles, tail = 0;
   static const int env_min_kb = getenv("PB_SPLIT_MIN_KB") ? atoi(getenv("PB_SPLIT_MIN_KB")) : 0;     // A/B switch
   if (g_split && g.ws && ktot >= (env_min_kb ? env_min_kb : g_split_min_kb)) {
-    tail = tiles % nsm;
+    tail = tiles % nsm_eff;
     // split count of the tail wave: minimise (rounds the tail items need) x (k-blocks per item); a tail of 80 tiles is
     // better cut in 5 (3 rounds of 1/5) than run whole on 80 of the 148 SMs
     int s = 1;
@@ -744,7 +872,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       for (int c = 1; c <= smax; ++c) {
         const long kb = (ktot + c - 1) / c;
         // in k-block times: rounds x (k-blocks + pipeline fill and partial-tile store) + the reduce pass over c partials
-        const long cost = c == 1 ? kb : ((tail * c + nsm - 1) / nsm) * (kb + 6) + tail * c / 16;
+        const long cost = c == 1 ? kb : ((tail * c + nsm_eff - 1) / nsm_eff) * (kb + 6) + tail * c / 16;
         if (cost < best) { best = cost; s = c; }
       }
     }
@@ -767,7 +895,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   }
   p.full_tiles = (int)full;
   p.items = (int)(full + tail * p.splits);
-  const int grid = (int)std::min<long>(p.items, nsm);
+  const int grid = (int)std::min<long>(p.items, nsm_eff);
+  if (pair) return d16 ? launch_pair<true>(BN, p, grid, st) : launch_pair<false>(BN, p, grid, st);
   if (ab16) return d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
   return d16 ? launch_bn<false, true>(BN, p, grid, st) : launch_bn<false, false>(BN, p, grid, st);
 }

@@ -59,6 +59,7 @@ extern "C" {
 #endif
 void pb_gemm_tune(int force_bn, int split, int use160);
 void pb_gemm_tune_split_min_kb(int kb);
+void pb_gemm_tune_pair(int on);          // CTA-pair (cta_group::2) kernels on / off (default on; env PB_GEMM_PAIR)
 #ifdef __cplusplus
 }
 #endif

@@ -132,6 +132,60 @@ def test_gemm_f16_conv3x3(nb, H, W, Ci, Co):
     assert rel(y, ref) < 6e-4
 
 
+def _pair(on):
+    N.raw().pb_gemm_tune_pair(int(on))
+
+
+@pytest.mark.parametrize("out16", [True, False])
+@pytest.mark.parametrize("M,Nn,K,res", [(20480, 320, 320, True), (19000, 320, 320, False), (19001, 640, 640, True),
+                                        (12800, 1280, 320, False), (9500, 960, 328, True), (9600, 2560, 72, False),
+                                        (128 * 75, 1280, 1280, True), (128 * 149, 160, 2560, False)])
+def test_gemm_f16_cta_pair_plain(M, Nn, K, res, out16):
+    """CTA-pair kernel (tcgen05.mma.cta_group::2, 256-row tiles over two SMs) against fp64 and, without split-K, bitwise
+    against the one-CTA kernel (same k order); odd row-tile counts exercise the phantom half of the last pair."""
+    torch.manual_seed(M + Nn + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.randn(M, Kp, device="cuda").half()
+    B = (torch.randn(Nn, Kp, device="cuda") / math.sqrt(K)).half()
+    odt = torch.float16 if out16 else torch.float32
+    bias = torch.randn(Nn, device="cuda")
+    R = torch.randn(M, Nn, device="cuda").to(odt) if res else None
+    outs = []
+    for on, splitk in ((1, True), (1, False), (0, False)):
+        _pair(on)
+        D = torch.full((M, Nn), float("nan"), device="cuda", dtype=odt)
+        gemm16(A, B, D, M=M, N_=Nn, K=K, lda=Kp, ldb=Kp, ldd=Nn, out16=out16, bias=bias, R=R, ldr=Nn, alpha=0.5,
+               beta=2.0 if res else 0.0, splitk=splitk)
+        outs.append(D)
+    _pair(1)
+    ref = 0.5 * (A[:, :K].double() @ B[:, :K].double().T) + bias.double() + (2.0 * R.double() if res else 0.0)
+    for D in outs:
+        assert rel(D, ref) < (6e-4 if out16 else 1e-5)
+    assert torch.equal(outs[1], outs[2])
+
+
+@pytest.mark.parametrize("nb,H,W,Ci,Co", [(5, 64, 64, 320, 320), (25, 16, 16, 640, 1280), (7, 32, 32, 64, 640), (3, 48, 40, 96, 160),
+                                          (25, 32, 32, 320, 640)])
+def test_gemm_f16_cta_pair_conv3x3(nb, H, W, Ci, Co):
+    torch.manual_seed(3)
+    x = torch.randn(nb, H, W, Ci, device="cuda").half()
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda") / math.sqrt(9 * Ci)).half()
+    fwd = w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci).contiguous()
+    R = torch.randn(nb, H, W, Co, device="cuda").half()
+    outs = []
+    for on, splitk in ((1, True), (1, False), (0, False)):
+        _pair(on)
+        y = torch.zeros(nb, H, W, Co, device="cuda", dtype=torch.float16)
+        gemm16(x, fwd, y, M=nb * H * W, N_=Co, K=Ci, lda=Ci, ldb=9 * Ci, ldd=Co, nb=nb, conv=1, H=H, W=W, R=R, ldr=Co, beta=1.0,
+               splitk=splitk)
+        outs.append(y)
+    _pair(1)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), None, padding=1).permute(0, 2, 3, 1) + R.double()
+    for y in outs:
+        assert rel(y, ref) < 6e-4
+    assert torch.equal(outs[1], outs[2])
+
+
 def test_gemm_f16_attention_batched():
     """Head-strided fp16 operands, fp32 scores out, then probabilities x V^T with a broadcast A (raster_b path)."""
     torch.manual_seed(1)
