@@ -40,7 +40,7 @@ namespace pbgemm {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // k-block of the fp32 / TF32 path: 32 fp32 = 128 bytes = one swizzle row
 constexpr int BK16 = 64;               // k-block of the fp16 path: 64 halves = 128 bytes
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;              // warps: 0 TMA producer, 1 MMA issuer, 2-5 / 6-9 epilogue groups
 constexpr int EPI_W = 32;              // epilogue chunk: 32 columns = one 128-byte staging row
 constexpr int NBUF = 4;                // staging buffers
 constexpr int EPI_BYTES = BM * EPI_W * 4;
@@ -68,6 +68,7 @@ struct alignas(64) Params {
   long ldd, sDb, sDh, ldr, sRb, sRh;
   float alpha, beta;
   int round_tf32;
+  long long* trace;                    // PB_GEMM_TRACE: per-item clocks of CTA 0 ([item][8]: producer begin / end, MMA begin / end, epilogue begin / end)
 };
 
 using namespace pbtc;
@@ -253,8 +254,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint64_t* r_bar = tmem_empty_bar + 2;              // [NBUF]
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(r_bar + NBUF);
+  uint64_t* r_bar = tmem_empty_bar + 2;              // [2 * NBUF]: residual barriers of the two epilogue groups
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(r_bar + 2 * NBUF);
+  constexpr int NG = D16 ? 2 : 1;                    // epilogue groups (see the epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -270,8 +272,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], PAIR ? 8 : 4); }
-    for (int i = 0; i < NBUF; ++i) mbar_init(&r_bar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], (PAIR ? 8 : 4) * NG); }
+    for (int i = 0; i < 2 * NBUF; ++i) mbar_init(&r_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -310,6 +312,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         const Tile t = decode_item<BN>(p, item);
         const int kb_begin = t.partial ? t.split * p.kb_per_split : 0;
         const int kb_end = t.partial ? min(total_kb, kb_begin + p.kb_per_split) : total_kb;
+        const int tli = (item - blockIdx.x) / gridDim.x;
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tli < 64) p.trace[tli * 8 + 0] = clock64();
         int tap = kb_begin / kb_tap;
         int kbt = kb_begin - tap * kb_tap;                     // k-block inside the tap, advanced without division
         for (int it = kb_begin; it < kb_end; ++it) {
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
           if (++kbt == kb_tap) { kbt = 0; ++tap; }
         }
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tli < 64) p.trace[tli * 8 + 1] = clock64();
       }
     }
   } else if (warp == 1 && cta_rank == 0) {
@@ -372,6 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(&tmem_empty_bar[as], ((li >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_u + uint32_t(as * ACC_STRIDE);
+        if (p.trace && blockIdx.x == 0 && lane == 0 && li < 64) p.trace[li * 8 + 2] = clock64();
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
@@ -398,20 +404,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           if constexpr (PAIR) tcgen05_commit_2sm(&tmem_full_bar[as]); else tcgen05_commit(&tmem_full_bar[as]);
         }
         __syncwarp();
+        if (p.trace && blockIdx.x == 0 && lane == 0 && li < 64) p.trace[li * 8 + 3] = clock64();
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && ((warp - 2) >> 2) < NG) {
     // =========================== epilogue ===========================
+    // fp16-output kernels run TWO epilogue groups of four warps (warps 2-5 and 6-9; a warp may touch the TMEM lane quarter
+    // warp % 4): group g takes the 32-column chunks c = g, g + 2, ... of every tile.  One group needs ~1300 clocks per chunk
+    // (TMEM load -> convert -> staging -> proxy fence -> group barrier -> TMA store), 6400 per 128 x 160 tile, which is what
+    // paced every GEMM with fewer than ~12 k-blocks per tile (per-item clocks of PB_GEMM_TRACE).  Each group owns half of the
+    // staging area, its own named barrier, residual barriers and bulk async-groups.
+    const int eg = (warp - 2) >> 2;           // epilogue group
     const int q = warp & 3;                   // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;              // tile row
-    // warp 2 drives the staging TMA traffic through ONE ELECTED lane (elect.sync names the same leader for the same member
-    // mask every time, so the bulk async-groups are committed and waited on by one thread); an `if (threadIdx.x == 64)` region
-    // made every UTMASTG / UTMALDG of the epilogue an ELECT / R2UR.BROADCAST waterfall -- ten per 128 x 160 tile, which is what
-    // paced the short-K linears
-    const bool w0 = (warp == 2);
+    // the group's first warp drives its staging TMA traffic through ONE ELECTED lane (elect.sync names the same leader for the
+    // same member mask every time, so the bulk async-groups are committed and waited on by one thread); an
+    // `if (threadIdx.x == 64)` region made every UTMASTG / UTMALDG of the epilogue an ELECT / R2UR.BROADCAST waterfall
+    const bool w0 = ((warp - 2) & 3) == 0;
+    const int bar_id = 1 + eg;
     const uint32_t tmem_empty_leader = PAIR ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0u;
-    uint32_t gch = 0;                         // chunks pushed through the staging ring so far (this CTA)
+    // staging geometry: fp32-output kernels 4 x 16 KB (one group); fp16-output kernels 4 x 8 KB per group for output tiles
+    // (64-byte rows) and 2 x 16 KB per group for the fp32 partial tiles of split items
+    uint8_t* gstaging = staging + eg * (NBUF * EPI_BYTES / NG);
+    uint64_t* gr_bar = r_bar + eg * NBUF;
+    uint32_t gch = 0;                         // chunks this group pushed through its staging ring so far
     uint32_t r_par = 0;                       // bit b: parity of the next residual load into staging buffer b
+    int cur_partial = 0;
     constexpr int TAILQ = D16 ? 7 : 3;        // TMA stores clip the inner dimension in 16-byte units
     int li = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++li) {
@@ -431,28 +449,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int rc1 = c1, rc2 = c2, rc3 = c3;
       int dcol0 = t.n0;
       if (t.partial) { c1 = ((t.tile_id - p.full_tiles) * p.splits + t.split) * BM; c2 = c3 = 0; dcol0 = 0; }
-      auto prefetch_r = [&](int c, uint32_t g) {   // residual chunk c of this tile -> staging buffer g % NBUF
+      if (D16 && t.partial && !cur_partial) {
+        // the 16 KB partial-tile buffers overlay the 8 KB output buffers: the group's pending stores must have been read
+        cur_partial = 1;
+        if (w0) {
+          if (elect_one()) bulk_wait_read<0>();
+          __syncwarp();
+        }
+        named_bar_sync(bar_id, 128);
+      }
+      const uint32_t nbuf = (D16 && t.partial) ? 2u : uint32_t(NBUF);
+      const uint32_t bufsz = (D16 && !t.partial) ? uint32_t(EPI_BYTES / 2) : uint32_t(EPI_BYTES);
+      auto prefetch_r = [&](int c, uint32_t g) {   // residual chunk c of this tile -> staging buffer g % NBUF of the group
         const uint32_t b = g % NBUF;
-        mbar_arrive_expect_tx(&r_bar[b], p.r_bytes);
-        tma_load_4d(staging + b * EPI_BYTES, &p.mapR, &r_bar[b], t.n0 + c * EPI_W, rc1, rc2, rc3);
+        mbar_arrive_expect_tx(&gr_bar[b], p.r_bytes);
+        tma_load_4d(gstaging + b * bufsz, &p.mapR, &gr_bar[b], t.n0 + c * EPI_W, rc1, rc2, rc3);
       };
       long d_off, r_off;
       const bool row_ok = tile_row(p, t, r, &d_off, &r_off);
 
       if (w0 && has_r) {
         if (elect_one())
-          for (int c = 0; c < min(3, ntma); ++c) prefetch_r(c, gch + c);
+          for (int j = 0; j < 3 && eg + NG * j < ntma; ++j) prefetch_r(eg + NG * j, gch + j);
         __syncwarp();
       }
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && li < 64) p.trace[li * 8 + 6] = clock64();
       mbar_wait(&tmem_full_bar[as], (li >> 1) & 1);
       tcgen05_fence_after();
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && li < 64) p.trace[li * 8 + 4] = clock64();
+      if (eg >= nchunks) {                        // no chunk of this tile for the group: release the accumulator at once
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + uint32_t(as) * 8u);
+          else mbar_arrive(&tmem_empty_bar[as]);
+        }
+      }
 
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = eg; c < nchunks; c += NG) {
         const int nc = t.n0 + c * EPI_W;
         uint32_t v[32];
         tmem_ld32(acc + uint32_t(c * EPI_W), v);
-        if (c == nchunks - 1) {
+        if (c + NG >= nchunks) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -462,23 +501,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         }
         const bool full = (nc + EPI_W <= p.N);
         if (c < ntma) {
-          const uint32_t b = gch % NBUF;
-          uint8_t* sbuf = staging + b * EPI_BYTES;
-          if (has_r) { mbar_wait(&r_bar[b], (r_par >> b) & 1u); r_par ^= 1u << b; }
+          const uint32_t b = gch % nbuf;
+          uint8_t* sbuf = gstaging + b * bufsz;
+          if (has_r) { mbar_wait(&gr_bar[b], (r_par >> b) & 1u); r_par ^= 1u << b; }
           if (t.partial) stage_chunk<false>(sbuf, r, v, alpha, beta, bias, nc, p.N, full, has_r, rnd);
           else stage_chunk<D16>(sbuf, r, v, alpha, beta, bias, nc, p.N, full, has_r, rnd);
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          // the NEXT chunk stages into the buffer of the store issued nbuf - 1 chunks before it: the store thread waits for
+          // that store's reads BEFORE the group barrier, so that every warp leaving the barrier knows the buffer is free (a
+          // wait after the barrier told only the store thread; with two 16 KB buffers the other warps overwrote a partial
+          // tile the previous store was still reading).  With a residual the buffer's next user is the TMA residual load
+          // issued below by the store thread itself, and the warps wait for its barrier.
+          if (w0 && !has_r) {
+            if (elect_one()) {
+              if (nbuf == 2u) bulk_wait_read<0>(); else bulk_wait_read<NBUF - 2>();
+            }
+            __syncwarp();
+          }
+          named_bar_sync(bar_id, 128);
           if (w0) {
             if (elect_one()) {
               tma_store_4d(dmap, sbuf, dcol0 + c * EPI_W, c1, c2, c3);
               bulk_commit();
-              // the next chunk stages into the buffer of the store issued NBUF - 1 chunks ago: three stores may still be
-              // reading their buffers; with a residual the buffer of the PREVIOUS store is refilled right here, so only the
-              // newest may be pending (one pending store made the short-K linears epilogue-bound: five serialised
-              // store round trips per 128 x 160 tile)
-              if (has_r) bulk_wait_read<1>(); else bulk_wait_read<NBUF - 1>();
-              if (has_r && c + 3 < ntma) prefetch_r(c + 3, gch + 3);
+              // with a residual the buffer of the PREVIOUS store is refilled right here: only the newest store may be pending
+              if (has_r) {
+                bulk_wait_read<1>();
+                if (c + 3 * NG < ntma) prefetch_r(c + 3 * NG, gch + 3);
+              }
             }
             __syncwarp();
           }
@@ -766,7 +815,10 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   // full wave of tiles; attention products (batched B, two segments) and the small-M layers keep the one-CTA kernel
   int pair = 0;
   int nsm_eff = nsm;
-  if (g_pair && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
+  // (tiles of fewer than 8 k-blocks -- the K = 320 linears -- are bound by their epilogue and the A stream from DRAM, where
+  // the pair kernel measured 0.85-1.0 of the one-CTA kernel; from 10 k-blocks on it is 1.1-1.6x)
+  const int kb_tile = (g.conv ? 9 : 1) * ((g.seg[0].K + KB - 1) / KB);
+  if (g_pair && (kb_tile >= 8 || g_pair > 1) && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
       (g.N % 256 == 0 || g.N % 160 == 0) && (!g_force_bn || g_force_bn == 160 || g_force_bn == 256)) {
     const int ncl = pair_clusters();
     const int pbn = g_force_bn ? g_force_bn : (g.N % 256 == 0 ? 256 : 160);
@@ -895,8 +947,30 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   }
   p.full_tiles = (int)full;
   p.items = (int)(full + tail * p.splits);
+  static const int env_trace = getenv("PB_GEMM_TRACE") ? atoi(getenv("PB_GEMM_TRACE")) : 0;
+  static long long* trace_buf = nullptr;
+  if (env_trace) {
+    if (!trace_buf) cudaMalloc(&trace_buf, 64 * 8 * sizeof(long long));
+    cudaMemsetAsync(trace_buf, 0, 64 * 8 * sizeof(long long), st);
+    p.trace = trace_buf;
+  }
   const int grid = (int)std::min<long>(p.items, nsm_eff);
-  if (pair) return d16 ? launch_pair<true>(BN, p, grid, st) : launch_pair<false>(BN, p, grid, st);
-  if (ab16) return d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
-  return d16 ? launch_bn<false, true>(BN, p, grid, st) : launch_bn<false, false>(BN, p, grid, st);
+  const char* lerr;
+  if (pair) lerr = d16 ? launch_pair<true>(BN, p, grid, st) : launch_pair<false>(BN, p, grid, st);
+  else if (ab16) lerr = d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
+  else lerr = d16 ? launch_bn<false, true>(BN, p, grid, st) : launch_bn<false, false>(BN, p, grid, st);
+  if (env_trace && !lerr) {          // debugging aid: synchronous dump of CTA 0's per-item clocks
+    static int dumps = 0;
+    long long h[64 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, trace_buf, sizeof h, cudaMemcpyDeviceToHost);
+    if (dumps++ < env_trace) {
+      fprintf(stderr, "GEMMTRACE M=%d N=%d kb=%d BN=%d pair=%d items=%d grid=%d\n", g.M, g.N, ktot, BN, pair, p.items, grid);
+      const long long t0 = h[0];
+      for (int i = 0; i < 64 && h[i * 8 + 2]; ++i)
+        fprintf(stderr, "  item %2d  prod %7lld..%7lld  mma %7lld..%7lld  epi wait %7lld start %7lld\n", i, h[i * 8] - t0,
+                h[i * 8 + 1] - t0, h[i * 8 + 2] - t0, h[i * 8 + 3] - t0, h[i * 8 + 6] - t0, h[i * 8 + 4] - t0);
+    }
+  }
+  return lerr;
 }
