@@ -59,14 +59,15 @@ template <> struct KCfg<3> { static constexpr int SP0 = 128, N0 = 4, SP1 = 0, N1
 
 struct alignas(64) Params {
   CUtensorMap mapA[2][2], mapB[2][2];  // [segment][k-chunk]
-  CUtensorMap mapC, mapC2, mapP;
+  CUtensorMap mapC[2], mapC2[2], mapP; // C tiles per cluster rank (a CTA of a pair holds half of the rows)
   int a_pc[2], b_pc[2];                // operand is per tangent column (else primal: shared by the columns of the CTA)
   int a_hmul[2], b_hmul[2], a_bmul[2], b_bmul[2], a_smul[2], b_smul[2];   // head / tangent / slot coordinate multipliers
   int a_tile0[2], b_idx[2];            // first resident A tile of the segment; tile index of its B inside a stage
   int nA, nbsh, nbpc;                  // resident A tiles (at kc_max); shared / per-column B tiles per stage
-  uint32_t a_bytes[2], sh_bytes, pc_bytes;
+  uint32_t a_bytes[2], sh_bytes[2], pc_bytes[2];   // stage bytes per cluster rank
   int pc_cnt;                          // consumers that release a per-column stage (score warp, accumulate warp)
-  int ctile, accw, accw_tot;           // bytes of a C tile (accw rows); accumulator columns per tangent (x2 with D2)
+  int ctile, accw, accw_tot;           // bytes of a C tile (clr rows); accumulator columns per tangent (x2 with D2)
+  int clr;                             // rows of a C tile a CTA holds: accw, or accw / 2 in a CTA pair
   int ns, nsh, npc, nt;                // ring depths: S (TMEM), shared stage, per-column stage, T
   int k_slot, nslots, ngrp, kc_base, kc_rem, kc_max, ps_mul;
   int d, Mr, Nc, nh;
@@ -86,6 +87,9 @@ __host__ __device__ constexpr uint32_t desc_hi(int span) {
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) { return (uint64_t(hi) << 32) | lo; }
 
+// peer handshakes of the CTA-pair variant: remote arrive with the default semantics and a plain wait, as CUTLASS' ClusterBarrier
+#define PEER_ARRIVE mbar_arrive_cluster
+#define PEER_WAIT mbar_wait
 #define TR(u_, e_) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (u_) < 512) p.trace[(u_) * 16 + (e_)] = clock64(); } while (0)
 
 struct Ring {
@@ -115,13 +119,34 @@ __device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
   return r;
 }
 
+template <bool PAIR>
+__device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if constexpr (PAIR) mma_f16_2sm(d, a, b, idesc, acc); else mma_f16(d, a, b, idesc, acc);
+}
+template <bool PAIR>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  if constexpr (PAIR) tcgen05_commit_2sm(bar); else tcgen05_commit(bar);
+}
+
 // NSEG score segments, KCFG k-chunk layout, C2M: 0 no second product, 1 folded into Acc, 2 separate accumulator / output,
 // DM delta mode: 0 none, 1 per row, 2 per column
-template <int NSEG, int KCFG, int C2M, int DM>
+// PAIR: two CTAs of a cluster (row tiles 2i, 2i + 1 of the same head / slot / column group, on the two SMs of a TPC) run every
+// product as ONE tcgen05.mma.cta_group::2 of 256 rows issued by the leader (cluster rank 0).  A one-CTA MMA of these shapes
+// costs 67-72 clocks (N = 48 / 64, A from shared memory: ~38 clocks per instruction on top of the math), a pair MMA 41-43 for
+// both SMs' work (scripts/mma_rate.cu); with 14 MMAs per substep the one-CTA kernel sits at its instruction roofline.  Each
+// CTA keeps its own rows (A tiles, P, T, accumulators, epilogue) and HALF of every B operand (32 of the 64 K / dK rows of a
+// step, half of the C tile rows).  Protocol: the peer CTA runs the same warp programs with the same local barriers; where the
+// leader's issuing warp would issue, the peer's twin has done the same waits on ITS barriers and arrives on a leader
+// barrier (peer_s / peer_c2 / peer_t, indexed like the ring stage the product uses), which the leader waits for as well; the
+// leader's commits arrive on the barriers of both CTAs (multicast), so the peer's rings advance exactly as the leader's.
+template <int NSEG, int KCFG, int C2M, int DM, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_constant__ Params p) {
   using KF = KCfg<KCFG>;
   constexpr int SP0 = KF::SP0, N0 = KF::N0, SP1 = KF::SP1, N1 = KF::N1;
-  constexpr int A_TILE = TM * (SP0 + SP1), B_TILE = TN * (SP0 + SP1);
+  constexpr int BROWS = PAIR ? TN / 2 : TN;                 // rows of a score-operand B tile this CTA holds
+  constexpr int A_TILE = TM * (SP0 + SP1), B_TILE = BROWS * (SP0 + SP1);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   constexpr bool HAS_C2 = C2M != 0, SEP = C2M == 2;
   constexpr int LAG = HAS_C2 ? 2 : 0;          // the T . C1 product of substep u is issued with the P . C2 product of u + LAG
 
@@ -149,7 +174,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
   uint64_t* t_full = s_free + MAX_NS;           // [MAX_NT]
   uint64_t* t_empty = t_full + MAX_NT;
   uint64_t* acc_zeroed = t_empty + MAX_NT;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_zeroed + 1);
+  uint64_t* peer_a = acc_zeroed + 1;            // CTA pair, on the leader: the peer's A tiles landed
+  uint64_t* peer_z = peer_a + 1;                // the peer's accumulators are zeroed (its 8 compute warps)
+  uint64_t* peer_s = peer_z + 1;                // [MAX_NS]  the peer is ready for the score product into this S stage
+  uint64_t* peer_c2 = peer_s + MAX_NS;          // [MAX_NPC] ... for the P . C2 product of this per-column stage
+  uint64_t* peer_t = peer_c2 + MAX_NPC;         // [MAX_NT]  ... for the T . C1 product of this T stage
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(peer_t + MAX_NT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * TM;
@@ -167,33 +197,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     for (int i = 0; i < MAX_NSH; ++i) { mbar_init(&sh_full[i], 1); mbar_init(&sh_empty[i], 12); }
     for (int i = 0; i < MAX_NPC; ++i) { mbar_init(&pc_full[i], 1); mbar_init(&pc_empty[i], max(p.pc_cnt, 1)); }
     for (int i = 0; i < MAX_NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4); }
-    for (int i = 0; i < MAX_NT; ++i) { mbar_init(&t_full[i], 4); mbar_init(&t_empty[i], 1); }
+    for (int i = 0; i < MAX_NT; ++i) { mbar_init(&t_full[i], 4); mbar_init(&t_empty[i], 1); mbar_init(&peer_t[i], 1); }
+    mbar_init(peer_a, 1); mbar_init(peer_z, 8);
+    for (int i = 0; i < MAX_NS; ++i) mbar_init(&peer_s[i], 1);
+    for (int i = 0; i < MAX_NPC; ++i) mbar_init(&peer_c2[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
     // rows d .. accw-1 of every C tile stage are outside the TMA box: zero them once; with want_rsum row d of the C1 stages is
     // ones, so that accumulator column d collects rowsum(T).  (A row of equal 16-byte chunks is swizzle-invariant.)
-    const int xrows = p.accw - p.d;
+    // (a CTA of a pair holds rows rank * clr .. of the tile: its constant rows start where the TMA box ends)
+    const int lr = p.clr;
+    const int first = min(lr, max(0, p.d - int(rank) * lr));
+    const int xrows = lr - first;
     const int per_stage = xrows * 8;                                   // 16-byte chunks
     const int n1 = NSH * per_stage, n2 = HAS_C2 ? NPC * per_stage : 0;
     const uint32_t one2 = 0x3C003C00u;
-    for (int i = threadIdx.x; i < n1 + n2; i += NTHREADS) {
+    for (int i = threadIdx.x; per_stage > 0 && i < n1 + n2; i += NTHREADS) {
       const bool c1 = i < n1;
       const int k = c1 ? i : i - n1;
       const int stg = k / per_stage, rem = k % per_stage;
-      uint8_t* base = (c1 ? sC1 : sC2) + stg * p.ctile + p.d * 128 + rem * 16;
-      const uint32_t v = (c1 && p.want_rsum && rem < 8) ? one2 : 0u;
+      uint8_t* base = (c1 ? sC1 : sC2) + stg * p.ctile + first * 128 + rem * 16;
+      const uint32_t v = (c1 && p.want_rsum && int(rank) * lr + first + (rem >> 3) == p.d) ? one2 : 0u;
       *reinterpret_cast<uint4*>(base) = make_uint4(v, v, v, v);
     }
     fence_proxy_async_smem();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // both CTAs' barriers are initialised before either signals the other's
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
@@ -227,7 +270,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
       for (int s = 0; s < NSEG; ++s) {
         hb[s] = bat_h * p.b_hmul[s]; sb[s] = slot * p.b_smul[s]; ob[s] = uint32_t(p.b_idx[s]) * B_TILE; shb[s] = !p.b_pc[s];
       }
-      const uint32_t sh_bytes = p.sh_bytes, ctile = p.ctile, shB = uint32_t(p.nbsh) * B_TILE;
+      const uint32_t sh_bytes = p.sh_bytes[rank], ctile = p.ctile, shB = uint32_t(p.nbsh) * B_TILE;
+      const int brow = int(rank) * BROWS, crow = int(rank) * p.clr;
       for (int msh = 0; msh < nj; ++msh) {
         mbar_wait(&sh_empty[rsh.idx], rsh.ph ^ 1);
         const int st = rsh.idx;
@@ -239,10 +283,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
           for (int s = 0; s < NSEG; ++s)
             if (shb[s]) {
               uint8_t* dst = sBsh + st * shB + ob[s];
-              tma_load_4d(dst, &p.mapB[s][0], &sh_full[st], 0, msh * TN, hb[s], sb[s]);
-              if (N1) tma_load_4d(dst + TN * SP0, &p.mapB[s][1], &sh_full[st], SP0 / 2, msh * TN, hb[s], sb[s]);
+              tma_load_4d(dst, &p.mapB[s][0], &sh_full[st], 0, msh * TN + brow, hb[s], sb[s]);
+              if (N1) tma_load_4d(dst + BROWS * SP0, &p.mapB[s][1], &sh_full[st], SP0 / 2, msh * TN + brow, hb[s], sb[s]);
             }
-          tma_load_4d(sC1 + st * ctile, &p.mapC, &sh_full[st], msh * TN, 0, bat_h, ps);
+          tma_load_4d(sC1 + st * ctile, &p.mapC[rank], &sh_full[st], msh * TN, crow, bat_h, ps);
         }
         __syncwarp();
         rsh.next(NSH);
@@ -257,7 +301,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
       for (int s = 0; s < NSEG; ++s) {
         hb[s] = bat_h * p.b_hmul[s]; bm[s] = p.b_bmul[s]; ob[s] = uint32_t(p.b_idx[s]) * B_TILE; pcb[s] = p.b_pc[s] != 0;
       }
-      const uint32_t pc_bytes = p.pc_bytes, ctile = p.ctile, pcB = uint32_t(p.nbpc) * B_TILE;
+      const uint32_t pc_bytes = p.pc_bytes[rank], ctile = p.ctile, pcB = uint32_t(p.nbpc) * B_TILE;
+      const int brow = int(rank) * BROWS, crow = int(rank) * p.clr;
       int pj = 0, pcol = 0;
       for (int mpc = 0; mpc < nu; ++mpc) {
         mbar_wait(&pc_empty[rpc.idx], rpc.ph ^ 1);
@@ -270,10 +315,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
             if (pcb[s]) {
               uint8_t* dst = sBpc + st * pcB + ob[s];
               const int bc = (b0 + pcol) * bm[s];
-              tma_load_4d(dst, &p.mapB[s][0], &pc_full[st], 0, pj * TN, hb[s], bc);
-              if (N1) tma_load_4d(dst + TN * SP0, &p.mapB[s][1], &pc_full[st], SP0 / 2, pj * TN, hb[s], bc);
+              tma_load_4d(dst, &p.mapB[s][0], &pc_full[st], 0, pj * TN + brow, hb[s], bc);
+              if (N1) tma_load_4d(dst + BROWS * SP0, &p.mapB[s][1], &pc_full[st], SP0 / 2, pj * TN + brow, hb[s], bc);
             }
-          if (HAS_C2) tma_load_4d(sC2 + st * ctile, &p.mapC2, &pc_full[st], pj * TN, 0, bat_h, b0 + pcol);
+          if (HAS_C2) tma_load_4d(sC2 + st * ctile, &p.mapC2[rank], &pc_full[st], pj * TN, crow, bat_h, b0 + pcol);
         }
         __syncwarp();
         rpc.next(NPC);
@@ -287,7 +332,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     // whole CTA while the tensor pipe was 27 % busy; everything loop-invariant is hoisted and a descriptor is one 32-bit add
     // away: desc = {lo + offset16, HI(span)} -- only the 14-bit address field of the low word ever changes.
     const int w = warp == 1 ? 0 : 1;
-    const uint32_t idesc_s = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_s = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t((PAIR ? 2 * TM : TM) >> 4) << 24);
+    const uint32_t peer_s_l = PAIR ? mapa_u32(smem_u32(peer_s), 0) : 0u, peer_a_l = PAIR ? mapa_u32(smem_u32(peer_a), 0) : 0u;
     constexpr uint32_t HI0 = desc_hi(SP0), HI1 = desc_hi(SP1 ? SP1 : 32);
     const uint32_t uA = smem_u32(sA), uBsh = smem_u32(sBsh), uBpc = smem_u32(sBpc);
     uint32_t a_lo[NSEG], a_cs[NSEG], b_lo[NSEG], b_st[NSEG], b_sel[NSEG];
@@ -304,6 +350,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     int j = w / KC, c = w % KC;
     int jr = 0, jdone = -1, jw = -1;          // step rsh points at / last step released by a commit / last step waited for
     mbar_wait(a_full, 0);
+    if constexpr (PAIR) {
+      if (leader) PEER_WAIT(peer_a, 0);
+      else if (w == 0 && lane == 0) PEER_ARRIVE(peer_a_l);
+    }
     for (int u = w; u < nu; u += 2) {
       while (jr < j) {                         // steps this warp had no substep in are released by a plain arrive
         if (jdone != jr) { mbar_wait(&sh_full[rsh.idx], rsh.ph); if (lane == 0) mbar_arrive(&sh_empty[rsh.idx]); }
@@ -316,23 +366,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
       if (lane == 0) TR(u, 1);
       if (wait_pc) mbar_wait(&pc_full[rpc.idx], rpc.ph);
       if (lane == 0) TR(u, 0);
+      if constexpr (PAIR) {                    // the peer's twin has done the same waits on its own barriers
+        if (leader) PEER_WAIT(&peer_s[rs.idx], rs.ph);
+        else if (lane == 0) PEER_ARRIVE(peer_s_l + uint32_t(rs.idx) * 8u);
+      }
       tcgen05_fence_after();
       const bool last = c + 2 >= KC;           // this warp's last substep of step j
-      if (elect_one()) {
+      if (leader && elect_one()) {
         const uint32_t d_s = tmem_base + rs.idx * TN;
 #pragma unroll
         for (int s = 0; s < NSEG; ++s) {
           const uint32_t al = a_lo[s] + uint32_t(c) * a_cs[s];
           const uint32_t bl = b_lo[s] + uint32_t(b_sel[s] ? rpc.idx : rsh.idx) * b_st[s];
 #pragma unroll
-          for (int k = 0; k < N0; ++k) mma_f16(d_s, mk_desc(al + 2 * k, HI0), mk_desc(bl + 2 * k, HI0), idesc_s, (s | k) ? 1u : 0u);
+          for (int k = 0; k < N0; ++k) mma<PAIR>(d_s, mk_desc(al + 2 * k, HI0), mk_desc(bl + 2 * k, HI0), idesc_s, (s | k) ? 1u : 0u);
 #pragma unroll
           for (int k = 0; k < N1; ++k)
-            mma_f16(d_s, mk_desc(al + (TM * SP0 >> 4) + 2 * k, HI1), mk_desc(bl + (TN * SP0 >> 4) + 2 * k, HI1), idesc_s, 1u);
+            mma<PAIR>(d_s, mk_desc(al + (TM * SP0 >> 4) + 2 * k, HI1), mk_desc(bl + (BROWS * SP0 >> 4) + 2 * k, HI1), idesc_s, 1u);
         }
-        if (wait_pc) tcgen05_commit(&pc_empty[rpc.idx]);
-        tcgen05_commit(&s_full[rs.idx]);
-        if (last) tcgen05_commit(&sh_empty[rsh.idx]);
+        if (wait_pc) commit<PAIR>(&pc_empty[rpc.idx]);
+        commit<PAIR>(&s_full[rs.idx]);
+        if (last) commit<PAIR>(&sh_empty[rsh.idx]);
       }
       __syncwarp();
       if (lane == 0) TR(u, 2);
@@ -352,7 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     // zeroed by the compute warps up front (acc_zeroed) and every product accumulates, so the two warps need no ordering
     // between them ("first write" vs "accumulate" on the same columns).
     const int w = warp == 10 ? 0 : 1;
-    const uint32_t idesc_a = (1u << 4) | (uint32_t(p.accw >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    const uint32_t idesc_a = (1u << 4) | (uint32_t(p.accw >> 3) << 17) | (uint32_t((PAIR ? 2 * TM : TM) >> 4) << 24);
+    const uint32_t peer_c2_l = PAIR ? mapa_u32(smem_u32(peer_c2), 0) : 0u, peer_t_l = PAIR ? mapa_u32(smem_u32(peer_t), 0) : 0u;
     constexpr uint32_t HI = desc_hi(128);
     const uint32_t u_acc = tmem_base + NS * TN;
     const uint32_t lC1 = desc_lo(smem_u32(sC1)), lC2 = desc_lo(smem_u32(sC2)), lP = desc_lo(smem_u32(sP)), lT = desc_lo(smem_u32(sT));
@@ -362,6 +417,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     int jp = w / KC, cp = w % KC, jrp = 0, jwp = -1;              // P . C2 cursor and its view of the shared-stage ring
     int ja = w / KC, ca = w % KC, jra = 0, jwa = -1, jdone = -1;  // T . C1 cursor (this one releases the shared stages)
     mbar_wait(acc_zeroed, 0);
+    if constexpr (PAIR) {
+      if (leader) PEER_WAIT(peer_z, 0);
+    }
     tcgen05_fence_after();
     for (int u = w; u < nu + LAG; u += 2) {
       if (u >= LAG) {                             // steps the T . C1 cursor skips are released first: the P . C2 product below
@@ -375,14 +433,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
         if (jwp != jp) { mbar_wait(&sh_full[rshp.idx], rshp.ph); jwp = jp; }
         mbar_wait(&pc_full[rpc.idx], rpc.ph);
         if (lane == 0) TR(u, 3);
+        if constexpr (PAIR) {
+          if (leader) PEER_WAIT(&peer_c2[rpc.idx], rpc.ph);
+          else if (lane == 0) PEER_ARRIVE(peer_c2_l + uint32_t(rpc.idx) * 8u);
+        }
         tcgen05_fence_after();
         const uint32_t al = lP + uint32_t(rshp.idx) * (PT_BYTES >> 4);
         const uint32_t bl = lC2 + uint32_t(rpc.idx) * ct16;
         const uint32_t tacc = u_acc + uint32_t(cp) * accw_tot + acc2_off;
-        if (elect_one()) {
+        if (leader && elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16(tacc, mk_desc(al + 2 * k, HI), mk_desc(bl + 2 * k, HI), idesc_a, 1u);
-          tcgen05_commit(&pc_empty[rpc.idx]);
+          for (int k = 0; k < 4; ++k) mma<PAIR>(tacc, mk_desc(al + 2 * k, HI), mk_desc(bl + 2 * k, HI), idesc_a, 1u);
+          commit<PAIR>(&pc_empty[rpc.idx]);
         }
         __syncwarp();
         rpc.next2(NPC);
@@ -393,16 +455,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
         if (jwa != ja) { mbar_wait(&sh_full[rsha.idx], rsha.ph); jwa = ja; }
         mbar_wait(&t_full[rt.idx], rt.ph);
         if (lane == 0) TR(u - LAG, 4);
+        if constexpr (PAIR) {
+          if (leader) PEER_WAIT(&peer_t[rt.idx], rt.ph);
+          else if (lane == 0) PEER_ARRIVE(peer_t_l + uint32_t(rt.idx) * 8u);
+        }
         tcgen05_fence_after();
         const uint32_t al = lT + uint32_t(rt.idx) * (PT_BYTES >> 4);
         const uint32_t bl = lC1 + uint32_t(rsha.idx) * ct16;
         const uint32_t tacc = u_acc + uint32_t(ca) * accw_tot;
         const bool last = ca + 2 >= KC;
-        if (elect_one()) {
+        if (leader && elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) mma_f16(tacc, mk_desc(al + 2 * k, HI), mk_desc(bl + 2 * k, HI), idesc_a, 1u);
-          tcgen05_commit(&t_empty[rt.idx]);
-          if (last) tcgen05_commit(&sh_empty[rsha.idx]);
+          for (int k = 0; k < 4; ++k) mma<PAIR>(tacc, mk_desc(al + 2 * k, HI), mk_desc(bl + 2 * k, HI), idesc_a, 1u);
+          commit<PAIR>(&t_empty[rt.idx]);
+          if (last) commit<PAIR>(&sh_empty[rsha.idx]);
         }
         __syncwarp();
         if (last) jdone = ja;
@@ -415,7 +481,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
       if (jdone != jra) { mbar_wait(&sh_full[rsha.idx], rsha.ph); if (lane == 0) mbar_arrive(&sh_empty[rsha.idx]); }
       rsha.next(NSH); ++jra;
     }
-    if (elect_one()) tcgen05_commit(acc_full);
+    if (leader && elect_one()) commit<PAIR>(acc_full);
     __syncwarp();
   } else {
     // =========================== compute warps ===========================
@@ -436,7 +502,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_zeroed);
+      if (lane == 0) {
+        mbar_arrive(acc_zeroed);
+        if (PAIR && !leader) mbar_arrive_cluster(mapa_u32(smem_u32(peer_z), 0));
+      }
     }
     uint4 pv[8];
     Ring rsh{0, 0}, rs{grp, 0}, rt{grp, 0};
@@ -587,9 +656,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn16_kernel(const __grid_consta
     tcgen05_fence_before();
   }
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers or read its tiles
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -619,7 +692,16 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
   if (!(a.p_scale > 0.f)) return "attn_lin: p_scale must be positive";
   const int kcfg = a.d <= 16 ? 0 : a.d <= 32 ? 1 : a.d <= 48 ? 2 : 3;
   const int sp0 = kcfg == 0 ? 32 : kcfg == 3 ? 128 : 64, sp1 = kcfg == 2 ? 32 : 0;
-  const int a_tile = TM * (sp0 + sp1), b_tile = TN * (sp0 + sp1);
+  // CTA pairs (see the kernel): an even number of row tiles, and a C tile whose second half still starts inside the d rows
+  // OPT-IN (PB_ATTN_PAIR=1): correct (the GPU tests pass with it on) but not faster -- 4096-token JVP 1.78 ms against 1.66 ms
+  // one-CTA, although its MMAs cost 586 instead of 971 clocks per substep: the dependency loop s_free -> score MMA -> compute
+  // -> T . C1 -> s_free (two S stages per parity class, TMEM is full) already takes ~890 clocks per substep in the one-CTA
+  // kernel, and every product of the pair adds a cross-CTA handshake to it
+  static const int pair_env = getenv("PB_ATTN_PAIR") ? atoi(getenv("PB_ATTN_PAIR")) : 0;
+  const int accw0 = (a.d + (a.want_rsum ? 1 : 0) + 15) / 16 * 16;
+  const bool pair = pair_env && ((a.Mr + TM - 1) / TM) % 2 == 0 && a.d > accw0 / 2 && a.Nc % 8 == 0;
+  const int brows = pair ? TN / 2 : TN;
+  const int a_tile = TM * (sp0 + sp1), b_tile = brows * (sp0 + sp1);
 
   Params p;
   memset(&p, 0, sizeof p);
@@ -640,11 +722,12 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
     return "attn_lin: D/D2/O/P/C2 must be 16-byte aligned with rows that are multiples of 16 bytes";
   p.accw = (a.d + (p.want_rsum ? 1 : 0) + 15) / 16 * 16;
   p.accw_tot = p.accw * (c2m == 2 ? 2 : 1);
-  p.ctile = p.accw * 128;
+  p.clr = pair ? p.accw / 2 : p.accw;
+  p.ctile = p.clr * 128;
 
   // operands: per tangent column (batch stride != 0) or primal
   int nA_fixed = 0, nA_pc = 0;
-  uint32_t sh_b = 0, pc_b = 0;
+  uint32_t sh_b = 0, pc_b = 0;                                          // stage bytes common to both ranks (C tiles added below)
   for (int s = 0; s < a.nseg; ++s) {
     p.a_pc[s] = a.seg[s].sAb != 0 ? 1 : 0;
     p.b_pc[s] = a.seg[s].sBb != 0 ? 1 : 0;
@@ -661,12 +744,12 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
     const int el0 = sp0 / 2, el1 = sp1 / 2;
     if (const char* e = pbgemm::encode_plainx(&p.mapA[s][0], sg.A, 1, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, nbA, el0, TM, sp0, &hm, &bm, &t)) return e;
     ab += t; p.a_hmul[s] = hm; p.a_bmul[s] = p.a_pc[s] ? bm : 0; if (!p.a_pc[s]) p.a_smul[s] = bm;
-    if (const char* e = pbgemm::encode_plainx(&p.mapB[s][0], sg.B, 1, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, el0, TN, sp0, &hm, &bm, &t)) return e;
+    if (const char* e = pbgemm::encode_plainx(&p.mapB[s][0], sg.B, 1, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, el0, brows, sp0, &hm, &bm, &t)) return e;
     bb += t; p.b_hmul[s] = hm; p.b_bmul[s] = p.b_pc[s] ? bm : 0; if (!p.b_pc[s]) p.b_smul[s] = bm;
     if (sp1) {
       if (const char* e = pbgemm::encode_plainx(&p.mapA[s][1], sg.A, 1, a.Mr, a.d, sg.lda, sg.sAh, a.nh, sg.sAb, nbA, el1, TM, sp1, &hm, &bm, &t)) return e;
       ab += t;
-      if (const char* e = pbgemm::encode_plainx(&p.mapB[s][1], sg.B, 1, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, el1, TN, sp1, &hm, &bm, &t)) return e;
+      if (const char* e = pbgemm::encode_plainx(&p.mapB[s][1], sg.B, 1, a.Nc, a.d, sg.ldb, sg.sBh, a.nh, sg.sBb, nbB, el1, brows, sp1, &hm, &bm, &t)) return e;
       bb += t;
     }
     p.a_bytes[s] = ab;
@@ -676,16 +759,22 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
     // C1: [nh][d][ldc], K-major over the score columns; box = [64 columns = 128 bytes] x [d rows]
     uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), uint64_t(nslots)};
     uint64_t stb[3] = {uint64_t(a.ldc) * 2, uint64_t(a.sCh) * 2, nslots > 1 ? uint64_t(a.p_stride) : uint64_t(a.sCh) * 2 * a.nh};
-    uint32_t box[4] = {uint32_t(TN), uint32_t(a.d), 1, 1};
-    if (const char* e = pbgemm::encode4x(&p.mapC, a.C1, 1, dims, stb, box, 128)) return e;
-    sh_b += uint32_t(a.d) * 128;
+    for (int rk = 0; rk < (pair ? 2 : 1); ++rk) {                      // rank rk holds rows rk * clr .. of the tile
+      const int rows = std::min(p.clr, a.d - rk * p.clr);
+      uint32_t box[4] = {uint32_t(TN), uint32_t(rows), 1, 1};
+      if (const char* e = pbgemm::encode4x(&p.mapC[rk], a.C1, 1, dims, stb, box, 128)) return e;
+      p.sh_bytes[rk] = uint32_t(rows) * 128;
+    }
   }
   if (a.C2) {
     uint64_t dims[4] = {uint64_t(a.Nc), uint64_t(a.d), uint64_t(a.nh), uint64_t(a.nb)};
     uint64_t stb[3] = {uint64_t(a.ldc2) * 2, uint64_t(a.nh > 1 ? a.sC2h : a.ldc2) * 2, uint64_t(a.nb > 1 ? a.sC2b : a.ldc2) * 2};
-    uint32_t box[4] = {uint32_t(TN), uint32_t(a.d), 1, 1};
-    if (const char* e = pbgemm::encode4x(&p.mapC2, a.C2, 1, dims, stb, box, 128)) return e;
-    pc_b += uint32_t(a.d) * 128;
+    for (int rk = 0; rk < (pair ? 2 : 1); ++rk) {
+      const int rows = std::min(p.clr, a.d - rk * p.clr);
+      uint32_t box[4] = {uint32_t(TN), uint32_t(rows), 1, 1};
+      if (const char* e = pbgemm::encode4x(&p.mapC2[rk], a.C2, 1, dims, stb, box, 128)) return e;
+      p.pc_bytes[rk] = uint32_t(rows) * 128;
+    }
   }
   {
     int hm, bm; uint32_t pb;
@@ -696,7 +785,7 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
                                               TN, TM, 128, &hm, &bm, &pb)) return e;
     sh_b += pb;
   }
-  p.sh_bytes = sh_b; p.pc_bytes = pc_b;
+  for (int rk = 0; rk < 2; ++rk) { p.sh_bytes[rk] += sh_b; p.pc_bytes[rk] += pc_b; }
   p.pc_cnt = (p.nbpc > 0 ? 1 : 0) + (a.C2 ? 1 : 0);
   const bool has_pc = p.pc_cnt > 0;
 
@@ -748,17 +837,30 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
     if (!g_trace) cudaMalloc(&g_trace, sizeof(long long) * 512 * 16);
     cudaMemsetAsync(g_trace, 0, sizeof(long long) * 512 * 16, st);
     p.trace = g_trace;
-    fprintf(stderr, "pb_attn16: role %d kc %d ngrp %d ns %d nsh %d npc %d nt %d smem %d\n", role, kc, ngrp, ns, nsh, npc, nt, smem);
+    fprintf(stderr, "pb_attn16: pair %d role %d kc %d ngrp %d ns %d nsh %d npc %d nt %d smem %d\n", int(pair), role, kc, ngrp, ns, nsh, npc, nt, smem);
   }
   void (*kern)(Params) = nullptr;
-#define PB_A16_ROLE(KCFG_)                                                      \
-  kern = role == 0 ? attn16_kernel<2, KCFG_, 1, 0> : role == 1 ? attn16_kernel<1, KCFG_, 0, 0> \
-       : role == 2 ? attn16_kernel<1, KCFG_, 0, 1> : attn16_kernel<1, KCFG_, 2, 2>;
+#define PB_A16_ROLE2(KCFG_, PAIR_)                                                                            \
+  kern = role == 0 ? attn16_kernel<2, KCFG_, 1, 0, PAIR_> : role == 1 ? attn16_kernel<1, KCFG_, 0, 0, PAIR_> \
+       : role == 2 ? attn16_kernel<1, KCFG_, 0, 1, PAIR_> : attn16_kernel<1, KCFG_, 2, 2, PAIR_>;
+#define PB_A16_ROLE(KCFG_) if (pair) { PB_A16_ROLE2(KCFG_, true) } else { PB_A16_ROLE2(KCFG_, false) }
   if (kcfg == 0) { PB_A16_ROLE(0) } else if (kcfg == 1) { PB_A16_ROLE(1) } else if (kcfg == 2) { PB_A16_ROLE(2) } else { PB_A16_ROLE(3) }
 #undef PB_A16_ROLE
+#undef PB_A16_ROLE2
   if (const char* err = pbhost::optin_smem(kern, 227 * 1024)) return err;
-  kern<<<grid, NTHREADS, smem, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+  } else {
+    kern<<<grid, NTHREADS, smem, st>>>(p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) return cudaGetErrorString(e);
   *handled = true;
   return nullptr;

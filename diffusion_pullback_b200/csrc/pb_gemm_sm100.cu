@@ -815,15 +815,16 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   // full wave of tiles; attention products (batched B, two segments) and the small-M layers keep the one-CTA kernel
   int pair = 0;
   int nsm_eff = nsm;
-  // (tiles of fewer than 8 k-blocks -- the K = 320 linears -- are bound by their epilogue and the A stream from DRAM, where
-  // the pair kernel measured 0.85-1.0 of the one-CTA kernel; from 10 k-blocks on it is 1.1-1.6x)
-  const int kb_tile = (g.conv ? 9 : 1) * ((g.seg[0].K + KB - 1) / KB);
-  if (g_pair && (kb_tile >= 8 || g_pair > 1) && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
+  if (g_pair && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
       (g.N % 256 == 0 || g.N % 160 == 0) && (!g_force_bn || g_force_bn == 160 || g_force_bn == 256)) {
     const int ncl = pair_clusters();
     const int pbn = g_force_bn ? g_force_bn : (g.N % 256 == 0 ? 256 : 160);
     const long ptiles = ((mt + 1) / 2) * 2 * ((g.N + pbn - 1) / pbn);
-    if (ncl > 0 && g.N % pbn == 0 && ptiles >= 2L * ncl) { pair = 1; BN = pbn; nsm_eff = 2 * ncl; mt = ((mt + 1) / 2) * 2; }
+    // at least one full wave of tiles; the deep-K small-M layers (8 x 8 convolutions: 70 tiles of 180 k-blocks, all cut along
+    // K) gain from the pair MMA as well (62 -> 49 us), the short ones do not
+    static const long pair_min_env = getenv("PB_GEMM_PAIR_MIN") ? atol(getenv("PB_GEMM_PAIR_MIN")) : 0;
+    const long pair_min = pair_min_env ? pair_min_env : (kb_tile >= 64 ? 48 : 2L * ncl);
+    if (ncl > 0 && g.N % pbn == 0 && ptiles >= pair_min) { pair = 1; BN = pbn; nsm_eff = 2 * ncl; mt = ((mt + 1) / 2) * 2; }
   }
   p.pair = pair;
   const long nt = (g.N + BN - 1) / BN;

@@ -77,6 +77,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (dt > 4000000000LL) __trap();
   }
 }
+// wait on a barrier of THIS CTA that a peer CTA of the cluster arrives on (acquire at cluster scope); bounded like mbar_wait
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = clock64();
+  bool said = false;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    const long long dt = clock64() - t0;
+    if (dt > 2000000000LL && !said) {
+      said = true;
+      if ((threadIdx.x & 31) == 0)
+        printf("pb_tc: cluster mbarrier timeout block (%d,%d,%d) warp %d barrier 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x >> 5, smem_u32(bar), parity);
+    }
+    if (dt > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2, int c3) {
   asm volatile(
@@ -133,7 +160,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope), the form CUTLASS' ClusterBarrier::arrive uses: a `.release.cluster` arrive
+  // measured ~1000 clocks per call (three per substep made the pair attention kernel 1.7x slower than the one-CTA kernel)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA tile load of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count on the barrier at the
 // shared::cluster address `bar_cluster` (the leader CTA's)
