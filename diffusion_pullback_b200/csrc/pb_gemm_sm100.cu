@@ -815,6 +815,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   // full wave of tiles; attention products (batched B, two segments) and the small-M layers keep the one-CTA kernel
   int pair = 0;
   int nsm_eff = nsm;
+  const int kb_tile = (g.conv ? 9 : 1) * ((g.seg[0].K + KB - 1) / KB);   // k-blocks per tile
   if (g_pair && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
       (g.N % 256 == 0 || g.N % 160 == 0) && (!g_force_bn || g_force_bn == 160 || g_force_bn == 256)) {
     const int ncl = pair_clusters();

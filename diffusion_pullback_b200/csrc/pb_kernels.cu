@@ -960,9 +960,12 @@ __global__ void pack_conv3x3_k(const float* __restrict__ w, int Co, int Ci, floa
 }
 
 
-// conv_in and its transpose, register / shared-memory blocked (the two "thin" kernels above are the generic fallback).
-// thin-in: each thread owns TWO output channels (its 2 x 9 x CIN filter taps stay in registers) and walks a strip of
-// pixels; the CIN inputs of a tap are one broadcast load per warp.  w: [Cout][9][CIN].
+// conv_in and its transpose, register blocked over a STRIP of 8 pixels of an image row (the two "thin" kernels above are the
+// generic fallback).  Both are 1.2 GFMA at 25 x 64 x 64 pixels, 33 us of fp32 FMA issue; one pixel per loop iteration with the
+// filter re-read from shared memory per input (thin-out) or 64-bit index arithmetic per pixel (thin-in) ran them at 430-500 us.
+// thin-in: each thread owns TWO output channels (its 2 x 9 x CIN filter taps stay in registers); the 3 x 10 input patch of a
+// strip is 30 broadcast loads per thread, 576 FMAs.  w: [Cout][9][CIN].
+constexpr int THIN_PW = 8;
 template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __restrict__ x, int nb, int H, int W,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
@@ -975,36 +978,66 @@ __global__ void __launch_bounds__(256) conv3x3_thin_in_reg_k(const float* __rest
 #pragma unroll
     for (int i = 0; i < 9 * CIN; ++i) wr[e][i] = w[(long)(2 * cp + e) * 9 * CIN + i];
   const float b0 = bias ? bias[2 * cp] : 0.f, b1 = bias ? bias[2 * cp + 1] : 0.f;
-  const long total = (long)nb * H * W;
-  for (long pix = blockIdx.x; pix < total; pix += gridDim.x) {
-    const int px = int(pix % W), py = int((pix / W) % H);
-    float a0 = b0, a1 = b1;
+  const int spr = (W + THIN_PW - 1) / THIN_PW;                // strips per image row
+  const int total = nb * H * spr;
+  for (int sidx = blockIdx.x; sidx < total; sidx += gridDim.x) {
+    const int sx = sidx % spr, row = sidx / spr;              // row = b * H + py
+    const int py = row % H, px0 = sx * THIN_PW;
+    float a0[THIN_PW], a1[THIN_PW];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
-      const long xo = (pix + (long)dy * W + dx) * CIN;
+    for (int q = 0; q < THIN_PW; ++q) { a0[q] = b0; a1[q] = b1; }
 #pragma unroll
-      for (int ci = 0; ci < CIN; ++ci) {
-        const float xv = load_in1(x, xo + ci, x16);
-        a0 = fmaf(xv, wr[0][tap * CIN + ci], a0);
-        a1 = fmaf(xv, wr[1][tap * CIN + ci], a1);
+    for (int dy = -1; dy <= 1; ++dy) {
+      if (py + dy < 0 || py + dy >= H) continue;
+      const long rbase = (long)(row + dy) * W;
+      float xv[THIN_PW + 2][CIN];
+#pragma unroll
+      for (int i = 0; i < THIN_PW + 2; ++i) {
+        const int xx = px0 - 1 + i;
+        const bool ok = xx >= 0 && xx < W;
+        if (CIN == 4) {
+          const float4 v = ok ? load_in4(x, (rbase + xx) * 4, x16) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xv[i][0] = v.x; xv[i][1] = v.y; xv[i][2] = v.z; xv[i][CIN - 1] = v.w;
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) xv[i][ci] = ok ? load_in1(x, (rbase + xx) * CIN + ci, x16) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int tap = (dy + 1) * 3 + dx;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float w0 = wr[0][tap * CIN + ci], w1 = wr[1][tap * CIN + ci];
+#pragma unroll
+          for (int q = 0; q < THIN_PW; ++q) {
+            a0[q] = fmaf(xv[q + dx][ci], w0, a0[q]);
+            a1[q] = fmaf(xv[q + dx][ci], w1, a1[q]);
+          }
+        }
       }
     }
-    const long yo = pix * Cout + 2 * cp;
-    if (y16) {
-      __half2* yp = reinterpret_cast<__half2*>(HP(y) + yo);
-      if (beta != 0.f) { const float2 o = __half22float2(*yp); a0 += beta * o.x; a1 += beta * o.y; }
-      *yp = __floats2half2_rn(a0, a1);
-    } else {
-      float2* yp = reinterpret_cast<float2*>(y + yo);
-      if (beta != 0.f) { const float2 o = *yp; a0 += beta * o.x; a1 += beta * o.y; }
-      *yp = make_float2(a0, a1);
+#pragma unroll
+    for (int q = 0; q < THIN_PW; ++q) {
+      if (px0 + q >= W) break;
+      const long yo = ((long)row * W + px0 + q) * Cout + 2 * cp;
+      float o0 = a0[q], o1 = a1[q];
+      if (y16) {
+        __half2* yp = reinterpret_cast<__half2*>(HP(y) + yo);
+        if (beta != 0.f) { const float2 o = __half22float2(*yp); o0 += beta * o.x; o1 += beta * o.y; }
+        *yp = __floats2half2_rn(o0, o1);
+      } else {
+        float2* yp = reinterpret_cast<float2*>(y + yo);
+        if (beta != 0.f) { const float2 o = *yp; o0 += beta * o.x; o1 += beta * o.y; }
+        *yp = make_float2(o0, o1);
+      }
     }
   }
 }
-// thin-out: the whole filter ([COUT <= 4][9][Cin], 46 KB for SD) sits in shared memory; one warp per output pixel,
-// lanes split the input channels in float4 quads, four warp reductions per pixel.
+// thin-out: the whole filter ([COUT <= 4][9][Cin], 46 KB for SD) sits in shared memory; one warp per strip of 8 pixels,
+// lanes split the input channels in float4 quads: a filter quad read from shared memory serves the 8 pixels (32 FMAs per
+// LDS.128), and the 8 x COUT partial sums are reduced across the warp by one 31-shuffle transpose-reduction that leaves
+// lane l with output (pixel l / 4, channel l % 4) -- one coalesced store.
 template <int COUT>
 __global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __restrict__ x, int nb, int H, int W, int Cin,
                                                                const float* __restrict__ w, const float* __restrict__ bias,
@@ -1014,37 +1047,61 @@ __global__ void __launch_bounds__(256) conv3x3_thin_out_smem_k(const float* __re
   for (int i = threadIdx.x; i < COUT * 9 * C4; i += blockDim.x) wsm[i] = reinterpret_cast<const float4*>(w)[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  const long total = (long)nb * H * W;
-  for (long pix = warp; pix < total; pix += nwarps) {
-    const int px = int(pix % W), py = int((pix / W) % H);
-    float acc[COUT];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int spr = (W + THIN_PW - 1) / THIN_PW;
+  const int total = nb * H * spr;
+  for (int sidx = warp; sidx < total; sidx += nwarps) {
+    const int sx = sidx % spr, row = sidx / spr;
+    const int py = row % H, px0 = sx * THIN_PW;
+    float acc[32];                                             // [pixel][4]
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int c4 = lane; c4 < C4; c4 += 32) {
+#pragma unroll 1
+      for (int dy = -1; dy <= 1; ++dy) {
+        if (py + dy < 0 || py + dy >= H) continue;
+        const long rbase = (long)(row + dy) * W;
+        float4 xv[THIN_PW + 2];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-      if (py + dy < 0 || py + dy >= H || px + dx < 0 || px + dx >= W) continue;
-      const long xo = (pix + (long)dy * W + dx) * Cin;
-      for (int c4 = lane; c4 < C4; c4 += 32) {
-        const float4 xv = load_in4(x, xo + 4 * c4, x16);
+        for (int i = 0; i < THIN_PW + 2; ++i) {
+          const int xx = px0 - 1 + i;
+          xv[i] = (xx >= 0 && xx < W) ? load_in4(x, (rbase + xx) * Cin + 4 * c4, x16) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) {
-          const float4 wv = wsm[(co * 9 + tap) * C4 + c4];
-          acc[co] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[co]))));
+        for (int dx = 0; dx < 3; ++dx) {
+          const int tap = (dy + 1) * 3 + dx;
+#pragma unroll
+          for (int co = 0; co < COUT; ++co) {
+            const float4 wv = wsm[(co * 9 + tap) * C4 + c4];
+#pragma unroll
+            for (int q = 0; q < THIN_PW; ++q) {
+              const float4 v = xv[q + dx];
+              acc[q * 4 + co] = fmaf(v.x, wv.x, fmaf(v.y, wv.y, fmaf(v.z, wv.z, fmaf(v.w, wv.w, acc[q * 4 + co]))));
+            }
+          }
         }
       }
     }
+    // transpose-reduction: after the step of stride s a lane keeps the half of its values whose index has bit s equal to its
+    // own lane bit and adds the partner's; lane l ends with the warp total of value l
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-      float v = warp_sum(acc[co]);
-      if (lane == 0) {
-        if (bias) v += bias[co];
-        const long yo = pix * COUT + co;
-        if (beta != 0.f) v += beta * load_in1(y, yo, y16);
-        if (y16) HP(y)[yo] = __float2half_rn(v); else y[yo] = v;
+    for (int s = 16; s >= 1; s >>= 1) {
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const float mine = up ? acc[i + s] : acc[i];
+        const float other = up ? acc[i] : acc[i + s];
+        acc[i] = mine + __shfl_xor_sync(0xffffffffu, other, s);
       }
+    }
+    const int q = lane >> 2, co = lane & 3;
+    if (co < COUT && px0 + q < W) {
+      float v = acc[0];
+      if (bias) v += bias[co];
+      const long yo = ((long)row * W + px0 + q) * COUT + co;
+      if (beta != 0.f) v += beta * load_in1(y, yo, y16);
+      if (y16) HP(y)[yo] = __float2half_rn(v); else y[yo] = v;
     }
   }
 }
@@ -1139,14 +1196,16 @@ PBK pbk_conv3x3_direct(const float* x, int nb, int H, int W, int Cin, const floa
   if ((Cin == 3 || Cin == 4) && Cout % 2 == 0 && Cout >= 64) {                  // conv_in
     const int gy = (Cout / 2 + 255) / 256;
     const int bx = std::min(256, ((Cout / 2 + 31) / 32) * 32);
-    dim3 grid((unsigned)std::min<long>(pix, (long)kSMs * 8 / ((Cout / 2 + bx - 1) / bx)), (Cout / 2 + bx - 1) / bx);
+    const long strips = (long)nb * H * ((W + THIN_PW - 1) / THIN_PW);
+    dim3 grid((unsigned)std::min<long>(strips, (long)kSMs * 8 / ((Cout / 2 + bx - 1) / bx)), (Cout / 2 + bx - 1) / bx);
     (void)gy;
     if (Cin == 4) conv3x3_thin_in_reg_k<4><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta, x16, y16);
     else conv3x3_thin_in_reg_k<3><<<grid, bx, 0, S(st)>>>(x, nb, H, W, w, bias, Cout, y, beta, x16, y16);
   } else if ((Cout == 3 || Cout == 4) && Cin % 4 == 0 && (size_t)Cout * 9 * Cin * 4 <= 96 * 1024 &&
              (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {   // its transpose
     const int shmem = Cout * 9 * Cin * 4;
-    const unsigned blocks = (unsigned)std::min<long>((pix + 7) / 8, (long)kSMs * 2);
+    const long strips = (long)nb * H * ((W + THIN_PW - 1) / THIN_PW);
+    const unsigned blocks = (unsigned)std::min<long>((strips + 7) / 8, (long)kSMs * 4);
     if (Cout == 4) {
       if (const char* err = pbhost::optin_smem(conv3x3_thin_out_smem_k<4>, 96 * 1024)) return err;
       conv3x3_thin_out_smem_k<4><<<blocks, 256, shmem, S(st)>>>(x, nb, H, W, Cin, w, bias, y, beta, x16, y16);
