@@ -112,6 +112,43 @@ __global__ void transpose_k(float* __restrict__ dst, long ldd, long sbd, long sh
   }
 }
 
+// fp16 -> fp16 transpose of narrow per-head matrices (C = head dim, a multiple of 8, <= 128): src_(b,h) [R][lds] halves ->
+// dst_(b,h) [C][ldd] halves.  A block moves a tile of 64 rows: 16-byte loads along C, 16-byte stores of 8 consecutive rows
+// along R (the generic kernel above moves 32 x 32 tiles one element per thread: 64-byte segments, and two column blocks of which
+// the second is 80 % empty at C = 40 -- 0.75 TB/s).  blockIdx.y = b * nh + h
+constexpr int TH_ROWS = 64;
+__global__ void __launch_bounds__(256) transpose_heads16_k(__half* __restrict__ dst, long ldd, long sbd, long shd,
+                                                           const __half* __restrict__ src, long lds, long sbs, long shs,
+                                                           int nh, int R, int C) {
+  extern __shared__ __half th_tile[];                          // [TH_ROWS][C + 2]
+  const int P = C + 2;
+  const int b = blockIdx.y / nh, h = blockIdx.y % nh;
+  const int r0 = blockIdx.x * TH_ROWS;
+  const __half* sp = src + (long)b * sbs + (long)h * shs;
+  __half* dp = dst + (long)b * sbd + (long)h * shd;
+  const int c8 = C >> 3;
+  for (int i = threadIdx.x; i < TH_ROWS * c8; i += blockDim.x) {
+    const int r = i / c8, cc = (i % c8) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < R) v = *reinterpret_cast<const uint4*>(sp + (long)(r0 + r) * lds + cc);
+    uint32_t* t = reinterpret_cast<uint32_t*>(th_tile + r * P + cc);      // P and cc are even: 4-byte aligned
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * (TH_ROWS / 8); i += blockDim.x) {
+    const int c = i / (TH_ROWS / 8), j = (i % (TH_ROWS / 8)) * 8;
+    __align__(16) __half e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) e[k] = th_tile[(j + k) * P + c];
+    __half* o = dp + (long)c * ldd + r0 + j;
+    if (r0 + j + 8 <= R) {
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(e);
+    } else {
+      for (int k = 0; k < 8 && r0 + j + k < R; ++k) o[k] = e[k];
+    }
+  }
+}
+
 __global__ void upsample2x_k(const float4* __restrict__ x, int nb, int H, int W, int C4, float4* __restrict__ y,
                              int rnd) {
   const long total = (long)nb * 4 * H * W * C4;
@@ -1263,6 +1300,13 @@ PBK pbk_transpose(float* dst, long ldd, long sbd, long shd, const float* src, lo
                   int nh, int R, int C, float beta, int round_tf32, pb_stream st) {
   if ((long)nb * nh > 65535 || (R + 31) / 32 > 65535) return "transpose: batch / row extent too large";
   if (out16(round_tf32) && beta != 0.f) return "transpose: fp16 output cannot accumulate";
+  if (in16(round_tf32) && out16(round_tf32) && C % 8 == 0 && C <= 128 && R >= 256 && lds % 8 == 0 && ldd % 8 == 0 && sbs % 8 == 0 &&
+      shs % 8 == 0 && sbd % 8 == 0 && shd % 8 == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0 &&
+      (R + TH_ROWS - 1) / TH_ROWS <= 65535 * 32) {              // narrow per-head matrices of the attention operands
+    dim3 grid((R + TH_ROWS - 1) / TH_ROWS, nb * nh);
+    transpose_heads16_k<<<grid, 256, TH_ROWS * (C + 2) * 2, S(st)>>>(HP(dst), ldd, sbd, shd, HP(src), lds, sbs, shs, nh, R, C);
+    return last_err();
+  }
   dim3 grid((C + 31) / 32, (R + 31) / 32, nb * nh), block(32, 8);
   transpose_k<<<grid, block, 0, S(st)>>>(dst, ldd, sbd, shd, src, lds, sbs, shs, nh, R, C, beta, round_tf32 & PB_RND_MASK,
                                          in16(round_tf32) ? 1 : 0);

@@ -779,6 +779,17 @@ def test_fp16_data_movement():
         _ok(N.leaf("pbk_transpose")(_p(dst), C.c_long(104), C.c_long(48 * 104), C.c_long(0), _p(src), C.c_long(48), C.c_long(100 * 48),
                                     C.c_long(0), 3, 1, 100, 48, C.c_float(0), io, _st()))
         assert torch.equal(dst[:, :, :100].float(), src.transpose(1, 2).to(ddt).float())
+    # per-head transposes between halves, the engine's layouts (dV^T out of the fused qkv tangent, Obar^T): the 64-row tile kernel
+    for nb_, nh_, R_, d_, lds_ in ((3, 4, 1000, 40, 3 * 160), (2, 5, 4096, 64, 320), (2, 2, 300, 80, 160)):
+        src = torch.randn(nb_, R_, lds_, device="cuda").half()
+        ldd_ = (R_ + 7) // 8 * 8 + 8
+        dst = torch.zeros(nb_, nh_, d_, ldd_, device="cuda", dtype=torch.float16)
+        off = lds_ - nh_ * d_                                   # heads start at a column offset (the v third of qkv)
+        _ok(N.leaf("pbk_transpose")(_p(dst), C.c_long(ldd_), C.c_long(nh_ * d_ * ldd_), C.c_long(d_ * ldd_),
+                                    C.c_void_p(src.data_ptr() + 2 * off), C.c_long(lds_), C.c_long(R_ * lds_), C.c_long(d_), nb_, nh_, R_, d_,
+                                    C.c_float(0), 6, _st()))
+        ref = src[:, :, off:].view(nb_, R_, nh_, d_).permute(0, 2, 3, 1)
+        assert torch.equal(dst[..., :R_], ref) and (dst[..., R_:] == 0).all()
     # fp16 -> fp32 staging copy
     hsrc = torch.randn(4096, device="cuda").half()
     f32 = torch.empty(4096, device="cuda")
