@@ -1,6 +1,6 @@
 """fp16-operand GEMM shapes of the batched iteration (5 problem slots x k = 5, SD-1.5 mid-block), one-CTA kernel against the
 CTA-pair kernel (tcgen05.mma.cta_group::2): CUDA events over 20 launches, operands rotated through > 126 MB (GPU box).
-  python scripts/bench_gemm16.py [nb]
+  python scripts/bench_gemm16.py [nb [shape indices [0 | 1: one kernel only]]]
 """
 import ctypes as C
 import sys
@@ -47,7 +47,7 @@ for conv, H, W, K, Nn, res in shapes:
         gs.append(g)
     out = []
     ref = None
-    for on in (0, 1):
+    for on in ((0, 1) if len(sys.argv) < 4 else (int(sys.argv[3]),)):
         pair(on)
         for g in gs:
             err = f(C.byref(g), st)
@@ -67,5 +67,7 @@ for conv, H, W, K, Nn, res in shapes:
             else:
                 assert (D[0].float() - ref.float()).abs().max() <= 1e-2 * ref.float().abs().max(), "pair kernel differs"
     pair(1)
+    if len(out) == 1:
+        out = out * 2
     print(f"{'conv3x3' if conv else 'linear '} M={M:6d} N={Nn:5d} K={K:5d} res={res}:  {out[0]:8.1f} us {flops / out[0] / 1e6:7.1f} | "
           f"{out[1]:8.1f} us {flops / out[1] / 1e6:7.1f}   x{out[0] / out[1]:.2f}")

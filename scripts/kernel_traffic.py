@@ -28,7 +28,9 @@ for r in csv.DictReader(lines):
     launch[i][r["Metric Name"]] = v * scale
 rows = [launch[i] for i in order]
 ends = [j for j, r in enumerate(rows) if "rotate_k" in r["name"]]
-rows = rows[ends[-2] + 1: ends[-1] + 1] if len(ends) >= 2 else rows
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 2      # iterations in the pass; with P problem slots P rotate_k launches close each
+per = max(1, len(ends) // iters)
+rows = rows[ends[-per - 1] + 1: ends[-1] + 1] if len(ends) > per else rows
 agg = defaultdict(lambda: [0, 0.0, 0.0])
 for r in rows:
     key = "gemm_tc_kernel" if "gemm_tc_kernel" in r["name"] else "attn_lin_kernel" if ("attn_lin_kernel" in r["name"] or "attn16_kernel" in r["name"]) else "other"
