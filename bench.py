@@ -521,7 +521,13 @@ def run_ours(args, wl):
             if kn:
                 kernels[name] = {"launches_per_iter": kn / prof_iters, "ms_per_iter": kms / prof_iters,
                                  "avg_launch_us": 1e3 * kms / kn, "achieved_tflops": kfl / kms / 1e9,
-                                 "share_of_eager_iter": kms / prof_iters / prof["_eager_ms_per_iter"]}
+                                 "share_of_eager_iter": kms / prof_iters / prof["_eager_ms_per_iter"],
+                                 "frac": kfl / kms / 1e9 / pk_all["burst"]}
+        if "attn_lin_kernel" in kernels:
+            # what bounds it is the tcgen05 instruction rate at its small MMA shapes, not the tensor-pipe math rate: a JVP substep is
+            # 6 MMAs of N = 64 and 8 of N = 48 = 971 clocks back to back for 384 clocks of peak-rate math (scripts/mma_rate.cu)
+            kernels["attn_lin_kernel"]["instruction_roofline_frac_of_peak"] = 384.0 / 971.0
+            kernels["attn_lin_kernel"]["instruction_roofline_source"] = "profiles/r3h_mma_rate.txt (one-CTA M = 128 MMAs, A from shared memory)"
         dom = max(kernels, key=lambda n: kernels[n]["ms_per_iter"]) if kernels else None
         # the GEMM launches by operand type, each against its own tensor-pipe peak (kind::tf32 = half the 16-bit rate)
         for name, pk in (("gemm_tc_kernel[kind::f16]", peak_burst), ("gemm_tc_kernel[kind::tf32]", pk_all["tf32_burst"])):
