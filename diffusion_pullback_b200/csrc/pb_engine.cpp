@@ -928,7 +928,8 @@ int run_primal(pb_handle* h, const float* x, float t, const float* ctx, float* h
         CK(pbk_upsample2x(h->P(o.x), 1, o.H, o.W, h->vals[o.x].C, h->P(o.y), h->rnd, st));
         break;
       case OP_GEGLU:
-        CK(pbk_geglu_fwd(h->P(o.x), h->vals[o.x].rows, h->vals[o.y].C, h->P(o.y), h->rnd, st));
+        // the cached ff1 output [a | g] becomes the linearisation factors [gelu(g) | a gelu'(g)] in the same pass
+        CK(pbk_geglu_fwd(h->P(o.x), h->vals[o.x].rows, h->vals[o.y].C, h->P(o.y), h->rnd, 1, st));
         break;
       case OP_ATTN:
         if (int e = run_attn_primal(h, o, ctx_r, st)) return e;

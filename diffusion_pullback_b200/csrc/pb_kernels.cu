@@ -756,15 +756,22 @@ __global__ void ln_lin_k(const float* __restrict__ xp, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // GEGLU
 // ------------------------------------------------------------------------------------------------
-__global__ void geglu_fwd_k(const float* __restrict__ h, long rows, int F, float* __restrict__ y, int rnd) {
+// prepare: [a | g] -> [gelu(g) | a gelu'(g)] in place, the factors of the linearisation (read by geglu_jvp_k / geglu_vjp_k)
+__global__ void geglu_fwd_k(float* __restrict__ h, long rows, int F, float* __restrict__ y, int rnd, int prepare) {
   const int F4 = F / 4;
   const long total = rows * F4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / F4; const int c = int(i % F4) * 4;
     const float4 a = *reinterpret_cast<const float4*>(h + r * 2 * F + c);
     const float4 g = *reinterpret_cast<const float4*>(h + r * 2 * F + F + c);
-    float4 o = make_float4(a.x * gelu_f(g.x), a.y * gelu_f(g.y), a.z * gelu_f(g.z), a.w * gelu_f(g.w));
+    const float4 gf = make_float4(gelu_f(g.x), gelu_f(g.y), gelu_f(g.z), gelu_f(g.w));
+    float4 o = make_float4(a.x * gf.x, a.y * gf.y, a.z * gf.z, a.w * gf.w);
     *reinterpret_cast<float4*>(y + r * F + c) = maybe_round4(o, rnd);
+    if (prepare) {
+      *reinterpret_cast<float4*>(h + r * 2 * F + c) = gf;
+      *reinterpret_cast<float4*>(h + r * 2 * F + F + c) =
+          make_float4(a.x * gelu_d(g.x), a.y * gelu_d(g.y), a.z * gelu_d(g.z), a.w * gelu_d(g.w));
+    }
   }
 }
 // IN16: the tangent dh / gy holds halves; rnd 2: the result is stored as halves.  Problem slots: tangent image r / rows_p
@@ -777,11 +784,10 @@ __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const flo
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / F4; const int c = int(i % F4) * 4;
     const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
-    const float4 a = *reinterpret_cast<const float4*>(hr + c);
-    const float4 g = *reinterpret_cast<const float4*>(hr + F + c);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(hr + c));          // gelu(g)
+    const float4 g2 = __ldg(reinterpret_cast<const float4*>(hr + F + c));      // a gelu'(g)
     const float4 da = load_in4(dh, r * 2 * F + c, IN16), dg = load_in4(dh, r * 2 * F + F + c, IN16);
-    float4 o = make_float4(da.x * gelu_f(g.x) + a.x * gelu_d(g.x) * dg.x, da.y * gelu_f(g.y) + a.y * gelu_d(g.y) * dg.y,
-                           da.z * gelu_f(g.z) + a.z * gelu_d(g.z) * dg.z, da.w * gelu_f(g.w) + a.w * gelu_d(g.w) * dg.w);
+    float4 o = make_float4(da.x * g1.x + g2.x * dg.x, da.y * g1.y + g2.y * dg.y, da.z * g1.z + g2.z * dg.z, da.w * g1.w + g2.w * dg.w);
     store_out4(dy, r * F + c, o, rnd);
   }
 }
@@ -793,12 +799,11 @@ __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const flo
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / F4; const int c = int(i % F4) * 4;
     const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
-    const float4 a = *reinterpret_cast<const float4*>(hr + c);
-    const float4 g = *reinterpret_cast<const float4*>(hr + F + c);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(hr + c));
+    const float4 g2 = __ldg(reinterpret_cast<const float4*>(hr + F + c));
     const float4 y = load_in4(gy, r * F + c, IN16);
-    float4 ga = make_float4(y.x * gelu_f(g.x), y.y * gelu_f(g.y), y.z * gelu_f(g.z), y.w * gelu_f(g.w));
-    float4 gg = make_float4(y.x * a.x * gelu_d(g.x), y.y * a.y * gelu_d(g.y), y.z * a.z * gelu_d(g.z),
-                            y.w * a.w * gelu_d(g.w));
+    float4 ga = make_float4(y.x * g1.x, y.y * g1.y, y.z * g1.z, y.w * g1.w);
+    float4 gg = make_float4(y.x * g2.x, y.y * g2.y, y.z * g2.z, y.w * g2.w);
     store_out4(gh, r * 2 * F + c, ga, rnd);
     store_out4(gh, r * 2 * F + F + c, gg, rnd);
   }
@@ -1489,9 +1494,9 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 }
 
 // ---- GEGLU ----
-PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st) {
+PBK pbk_geglu_fwd(float* h, long rows, int F, float* y, int round_tf32, int prepare, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
-  geglu_fwd_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(h, rows, F, y, round_tf32);
+  geglu_fwd_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(h, rows, F, y, round_tf32, prepare);
   return last_err();
 }
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,

@@ -101,8 +101,10 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
                const float* t, int nb, int mode, float* out, float acc, int round_tf32, int k_slot, long p_stride, pb_stream st);
 
 // ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
-PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int round_tf32, pb_stream st);
-// round_tf32 | PB_IN_F16: the tangent input dh / gy holds halves
+// prepare != 0: h = [a | g] is then overwritten IN PLACE with the linearisation factors [gelu(g) | a gelu'(g)], the form
+// pbk_geglu_jvp / _vjp read (no erf / exp per element and iteration: the two linearisation kernels were ALU-bound on them)
+PBK pbk_geglu_fwd(float* h, long rows, int F, float* y, int round_tf32, int prepare, pb_stream st);
+// hp: the PREPARED cache [gelu(g) | a gelu'(g)] of pbk_geglu_fwd;  round_tf32 | PB_IN_F16: the tangent input dh / gy holds halves
 PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, float* dy, int round_tf32,
                   int k_slot, long p_stride, pb_stream st);
 PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, float* gh, int round_tf32,

@@ -324,9 +324,13 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
   }
   return nullptr;
 }
-PBK pbk_geglu_fwd(const float* h, long rows, int F, float* y, int rnd, pb_stream) {
+PBK pbk_geglu_fwd(float* h, long rows, int F, float* y, int rnd, int prepare, pb_stream) {
   for (long r = 0; r < rows; ++r)
-    for (int c = 0; c < F; ++c) y[r * F + c] = mr(h[r * 2 * F + c] * gelu_f(h[r * 2 * F + F + c]), rnd);
+    for (int c = 0; c < F; ++c) {
+      const float a = h[r * 2 * F + c], g = h[r * 2 * F + F + c];
+      y[r * F + c] = mr(a * gelu_f(g), rnd);
+      if (prepare) { h[r * 2 * F + c] = gelu_f(g); h[r * 2 * F + F + c] = a * gelu_d(g); }
+    }
   return nullptr;
 }
 PBK pbk_geglu_jvp(const float* hp0, long rows_p, const float* dh, int nb, int F, float* dy, int rnd, int k_slot, long p_stride,
@@ -336,8 +340,8 @@ PBK pbk_geglu_jvp(const float* hp0, long rows_p, const float* dh, int nb, int F,
     const long rp = r % rows_p;
     const float* hp = hp0 + ((r / rows_p) / k_slot) * p_stride;
     for (int c = 0; c < F; ++c) {
-      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c];
-      sto(dy, rnd, r * F + c, ldx(dh, in16(rnd), r * 2 * F + c) * gelu_f(g) + a * gelu_d(g) * ldx(dh, in16(rnd), r * 2 * F + F + c));
+      const float g1 = hp[rp * 2 * F + c], g2 = hp[rp * 2 * F + F + c];      // prepared cache: gelu(g), a gelu'(g)
+      sto(dy, rnd, r * F + c, ldx(dh, in16(rnd), r * 2 * F + c) * g1 + g2 * ldx(dh, in16(rnd), r * 2 * F + F + c));
     }
   }
   return nullptr;
@@ -349,9 +353,9 @@ PBK pbk_geglu_vjp(const float* hp0, long rows_p, const float* gy, int nb, int F,
     const long rp = r % rows_p;
     const float* hp = hp0 + ((r / rows_p) / k_slot) * p_stride;
     for (int c = 0; c < F; ++c) {
-      const float a = hp[rp * 2 * F + c], g = hp[rp * 2 * F + F + c], y = ldx(gy, in16(rnd), r * F + c);
-      sto(gh, rnd, r * 2 * F + c, y * gelu_f(g));
-      sto(gh, rnd, r * 2 * F + F + c, y * a * gelu_d(g));
+      const float g1 = hp[rp * 2 * F + c], g2 = hp[rp * 2 * F + F + c], y = ldx(gy, in16(rnd), r * F + c);
+      sto(gh, rnd, r * 2 * F + c, y * g1);
+      sto(gh, rnd, r * 2 * F + F + c, y * g2);
     }
   }
   return nullptr;

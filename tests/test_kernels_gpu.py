@@ -393,15 +393,18 @@ def test_layernorm_geglu_softmax():
     h = torch.randn(rows, 2 * Fd, device="cuda")
     g = lambda z: z[..., :Fd] * F.gelu(z[..., Fd:])
     yy = torch.empty(rows, Fd, device="cuda")
-    _ok(N.leaf("pbk_geglu_fwd")(_p(h), C.c_long(rows), Fd, _p(yy), 0, _st()))
+    _ok(N.leaf("pbk_geglu_fwd")(_p(h), C.c_long(rows), Fd, _p(yy), 0, 0, _st()))
     assert rel(yy, g(h)) < 1e-5
+    hprep = h.clone()                               # prepared cache [gelu(g) | a gelu'(g)], written in place by the primal kernel
+    _ok(N.leaf("pbk_geglu_fwd")(_p(hprep), C.c_long(rows), Fd, _p(yy), 0, 1, _st()))
+    assert rel(yy, g(h)) < 1e-5 and rel(hprep[:, :Fd], F.gelu(h[:, Fd:])) < 1e-5
     dh = torch.randn(nb, rows, 2 * Fd, device="cuda")
     dy = torch.empty(nb, rows, Fd, device="cuda")
-    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), 0, 0, C.c_long(0), _st()))
+    _ok(N.leaf("pbk_geglu_jvp")(_p(hprep), C.c_long(rows), _p(dh), nb, Fd, _p(dy), 0, 0, C.c_long(0), _st()))
     assert rel(dy, torch.stack([torch.func.jvp(g, (h,), (dh[i],))[1] for i in range(nb)])) < 2e-5
     gy = torch.randn(nb, rows, Fd, device="cuda")
     gh = torch.empty(nb, rows, 2 * Fd, device="cuda")
-    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), 0, 0, C.c_long(0), _st()))
+    _ok(N.leaf("pbk_geglu_vjp")(_p(hprep), C.c_long(rows), _p(gy), nb, Fd, _p(gh), 0, 0, C.c_long(0), _st()))
     assert rel(gh, torch.stack([torch.func.vjp(g, h)[1](gy[i])[0] for i in range(nb)])) < 2e-5
     # softmax + its linearisation, short (warp) and long (block) rows
     for cols in (77, 256, 4096):
@@ -727,13 +730,15 @@ def test_fp16_layernorm_geglu(rows, Cc):
     Fd = 4 * Cc
     h = torch.randn(rows, 2 * Fd, device="cuda")
     g = lambda z: z[..., :Fd] * F.gelu(z[..., Fd:])
+    hprep, ytmp = h.clone(), torch.empty(rows, Fd, device="cuda")
+    _ok(N.leaf("pbk_geglu_fwd")(_p(hprep), C.c_long(rows), Fd, _p(ytmp), 0, 1, _st()))
     dh = torch.randn(nb, rows, 2 * Fd, device="cuda").half()
     dy = torch.empty(nb, rows, Fd, device="cuda", dtype=torch.float16)
-    _ok(N.leaf("pbk_geglu_jvp")(_p(h), C.c_long(rows), _p(dh), nb, Fd, _p(dy), IO16, 0, C.c_long(0), _st()))
+    _ok(N.leaf("pbk_geglu_jvp")(_p(hprep), C.c_long(rows), _p(dh), nb, Fd, _p(dy), IO16, 0, C.c_long(0), _st()))
     assert rel(dy.float(), torch.stack([torch.func.jvp(g, (h,), (dh[i].float(),))[1] for i in range(nb)])) < 6e-4
     gy = torch.randn(nb, rows, Fd, device="cuda").half()
     gh = torch.empty(nb, rows, 2 * Fd, device="cuda", dtype=torch.float16)
-    _ok(N.leaf("pbk_geglu_vjp")(_p(h), C.c_long(rows), _p(gy), nb, Fd, _p(gh), IO16, 0, C.c_long(0), _st()))
+    _ok(N.leaf("pbk_geglu_vjp")(_p(hprep), C.c_long(rows), _p(gy), nb, Fd, _p(gh), IO16, 0, C.c_long(0), _st()))
     assert rel(gh.float(), torch.stack([torch.func.vjp(g, h)[1](gy[i].float())[0] for i in range(nb)])) < 6e-4
 
 
