@@ -779,33 +779,35 @@ __global__ void geglu_fwd_k(float* __restrict__ h, long rows, int F, float* __re
 template <bool IN16>
 __global__ void geglu_jvp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ dh, long rows, int F,
                             float* __restrict__ dy, int rnd, int k_slot, long p_stride) {
-  const int F4 = F / 4;
-  const long total = rows * F4;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / F4; const int c = int(i % F4) * 4;
-    const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
+  // 32-bit index arithmetic (the launcher checks rows * F / 4 < 2^31): four 64-bit divisions per float4 cost more instructions than
+  // the whole linearisation
+  const unsigned F4 = F / 4, total = unsigned(rows) * F4, rp32 = unsigned(rows_p);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / F4; const int c = int(i - r * F4) * 4;
+    const unsigned img = r / rp32;
+    const float* hr = hp + (long)(img / unsigned(k_slot)) * p_stride + (long)(r - img * rp32) * 2 * F;
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(hr + c));          // gelu(g)
     const float4 g2 = __ldg(reinterpret_cast<const float4*>(hr + F + c));      // a gelu'(g)
-    const float4 da = load_in4(dh, r * 2 * F + c, IN16), dg = load_in4(dh, r * 2 * F + F + c, IN16);
+    const float4 da = load_in4(dh, (long)r * 2 * F + c, IN16), dg = load_in4(dh, (long)r * 2 * F + F + c, IN16);
     float4 o = make_float4(da.x * g1.x + g2.x * dg.x, da.y * g1.y + g2.y * dg.y, da.z * g1.z + g2.z * dg.z, da.w * g1.w + g2.w * dg.w);
-    store_out4(dy, r * F + c, o, rnd);
+    store_out4(dy, (long)r * F + c, o, rnd);
   }
 }
 template <bool IN16>
 __global__ void geglu_vjp_k(const float* __restrict__ hp, long rows_p, const float* __restrict__ gy, long rows, int F,
                             float* __restrict__ gh, int rnd, int k_slot, long p_stride) {
-  const int F4 = F / 4;
-  const long total = rows * F4;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / F4; const int c = int(i % F4) * 4;
-    const float* hr = hp + ((r / rows_p) / k_slot) * p_stride + (r % rows_p) * 2 * F;
+  const unsigned F4 = F / 4, total = unsigned(rows) * F4, rp32 = unsigned(rows_p);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned r = i / F4; const int c = int(i - r * F4) * 4;
+    const unsigned img = r / rp32;
+    const float* hr = hp + (long)(img / unsigned(k_slot)) * p_stride + (long)(r - img * rp32) * 2 * F;
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(hr + c));
     const float4 g2 = __ldg(reinterpret_cast<const float4*>(hr + F + c));
-    const float4 y = load_in4(gy, r * F + c, IN16);
+    const float4 y = load_in4(gy, (long)r * F + c, IN16);
     float4 ga = make_float4(y.x * g1.x, y.y * g1.y, y.z * g1.z, y.w * g1.w);
     float4 gg = make_float4(y.x * g2.x, y.y * g2.y, y.z * g2.z, y.w * g2.w);
-    store_out4(gh, r * 2 * F + c, ga, rnd);
-    store_out4(gh, r * 2 * F + F + c, gg, rnd);
+    store_out4(gh, (long)r * 2 * F + c, ga, rnd);
+    store_out4(gh, (long)r * 2 * F + F + c, gg, rnd);
   }
 }
 
@@ -1503,6 +1505,7 @@ PBK pbk_geglu_jvp(const float* hp, long rows_p, const float* dh, int nb, int F, 
                   int k_slot, long p_stride, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
+  if (rows * (F / 4) >= (1L << 31)) return "geglu: tensor too large for 32-bit indexing";
   if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   const unsigned grid = grid_for(rows * (F / 4), 256, 16);
   if (in16(round_tf32)) geglu_jvp_k<true><<<grid, 256, 0, S(st)>>>(hp, rows_p, dh, rows, F, dy, round_tf32 & PB_RND_MASK, k_slot, p_stride);
@@ -1513,6 +1516,7 @@ PBK pbk_geglu_vjp(const float* hp, long rows_p, const float* gy, int nb, int F, 
                   int k_slot, long p_stride, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   const long rows = rows_p * nb;
+  if (rows * (F / 4) >= (1L << 31)) return "geglu: tensor too large for 32-bit indexing";
   if (k_slot < 1 || k_slot >= nb) { k_slot = nb; p_stride = 0; }
   const unsigned grid = grid_for(rows * (F / 4), 256, 16);
   if (in16(round_tf32)) geglu_vjp_k<true><<<grid, 256, 0, S(st)>>>(hp, rows_p, gy, rows, F, gh, round_tf32 & PB_RND_MASK, k_slot, p_stride);

@@ -220,9 +220,12 @@ __global__ void __launch_bounds__(256) ln16_k(const float* __restrict__ xp, cons
   const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const long nw = ((long)gridDim.x * blockDim.x) >> 5;
   const float invC = 1.f / (float)C;
+  // (32-bit row arithmetic: the launcher checks rows < 2^31; two 64-bit divisions per token were a third of this kernel's instructions)
+  const unsigned rp32 = unsigned(rows_p);
   for (long r = warp; r < rows; r += nw) {
-    const long rp = r % rows_p;
-    const long ps = ((r / rows_p) / k_slot) * p_stride;
+    const unsigned img = unsigned(r) / rp32;
+    const long rp = unsigned(r) - img * rp32;
+    const long ps = long(img / unsigned(k_slot)) * p_stride;
     const float* xr = xp + ps + rp * C;
     const __half* tr = t + r * C;
     __half* orow = out + r * C;
@@ -305,8 +308,11 @@ __global__ void __launch_bounds__(256) ln16_k(const float* __restrict__ xp, cons
 __global__ void copy2d16_k(__half* __restrict__ dst, long ldd, const __half* __restrict__ src, long lds, long rows, int cols8,
                            float beta) {
   const long total = rows * cols8;
+  const bool small = total < (1L << 31);                       // 32-bit index arithmetic where it fits (a 64-bit division per access otherwise)
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / cols8; const int c = int(i % cols8) * 8;
+    long r; int c;
+    if (small) { const unsigned q = unsigned(i) / unsigned(cols8); r = q; c = int(unsigned(i) - q * unsigned(cols8)) * 8; }
+    else { r = i / cols8; c = int(i % cols8) * 8; }
     uint4 v = *reinterpret_cast<const uint4*>(src + r * lds + c);
     uint4* d = reinterpret_cast<uint4*>(dst + r * ldd + c);
     if (beta != 0.f) {
@@ -432,6 +438,7 @@ const char* ln_lin(const float* xp, const float* mean, const float* rstd, const 
   if (C % 8) return "layernorm: C must be a multiple of 8 for fp16 tangents";
   if (k_slot < 1) k_slot = nb;
   const long rows = rows_p * nb;
+  if (rows >= (1L << 31)) return "layernorm: too many rows for 32-bit indexing";
   const unsigned grid = grid_for(rows * 32, 256, 8);
   const int nv = (C + 255) / 256;
 #define PB_LN16(M_, NV_) ln16_k<M_, NV_><<<grid, 256, 0, st>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, k_slot, p_stride)
