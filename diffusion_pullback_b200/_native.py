@@ -59,7 +59,8 @@ class PbGemm(C.Structure):
                 ("nb", C.c_int), ("nh", C.c_int), ("conv", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("round_tf32", C.c_int), ("precise", C.c_int),
                 ("ws", C.c_void_p), ("ws_floats", C.c_long), ("ab_dtype", C.c_int), ("d_dtype", C.c_int),
-                ("k_slot", C.c_int), ("p_stride", C.c_long)]
+                ("k_slot", C.c_int), ("p_stride", C.c_long),
+                ("gg", C.c_void_p), ("gg_F", C.c_int), ("gg_rows_p", C.c_long), ("gg_k_slot", C.c_int), ("gg_p_stride", C.c_long)]
 
 
 class PbAttnLin(C.Structure):

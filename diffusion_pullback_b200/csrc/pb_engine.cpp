@@ -54,6 +54,7 @@ struct WSpec {
   int out, in;                      // total rows, columns (conv: Co, Ci)
   size_t fwd_off, bwd_off;          // bytes in the packed region
   size_t fwd16_off = 0, bwd16_off = 0;   // fp16 copies of the two GEMM layouts (0: none)
+  size_t fwd16g_off = 0;                 // ff1 of a GEGLU block: fp16 forward copy with the a / gate rows interleaved (PbGemm::gg; 0: none)
 };
 
 enum OpKind { OP_IN, OP_CONV_DIRECT, OP_GN, OP_LN, OP_GEMM, OP_CONCAT, OP_IM2COL, OP_UPSAMPLE, OP_GEGLU, OP_ATTN, OP_OUT };
@@ -108,6 +109,8 @@ struct pb_handle {
   int prec_p = 0, prec_t = 0, prec_a = 0;   // primal GEMMs / tangent weight GEMMs / tangent attention GEMMs
   int rnd = 1;                              // rounding flag of the pass being interpreted
   int fused_min_tokens = 512;               // self-attention layers with >= this many tokens use the fused kernel
+  int fuse_geglu = 1;                       // JVP of ff1 with the GEGLU linearisation in the GEMM epilogue (all-fp16 plan, device backend)
+  int fuse_geglu_min_k = 0;                 // ... for layers with at least this many input channels
   int f16 = -1;                             // fp16 tangents + fp16-operand GEMMs on the tangent passes: -1 = if the backend has them
   bool t16 = false;                         // the plan stores every tangent / cotangent as halves (decided by pb_plan: f16 and an eligible geometry)
   size_t w_cvt = 0, n_cvt = 0;              // fp32 staging of an fp16 tangent for the materialised attention path (floats per tangent)
@@ -328,6 +331,14 @@ struct Planner {
     int t2 = linear(o2, {tb + ".attn2.to_out.0.weight"}, {tb + ".attn2.to_out.0.bias"}, C, t1);
     int l3 = ln(t2, tb + ".norm3");
     int f1 = linear(l3, {tb + ".ff.net.0.proj.weight"}, {tb + ".ff.net.0.proj.bias"}, 8 * C);
+    {
+      // the JVP of ff1 can run with the GEGLU linearisation in its epilogue (the 8C-wide tangent never reaches HBM): it takes a
+      // copy of the fp16 forward weight with the a / gate rows interleaved
+      WSpec& ws = h->wspecs[h->ops.back().w];
+      if (ws.fwd16_off && !ws.fwd16g_off && (4 * C) % 128 == 0 && pbk_gemm_geglu_supported()) {
+        ws.fwd16g_off = h->packed_top; h->packed_top = align_up(h->packed_top + (size_t)8 * C * C * 2);
+      }
+    }
     int gg = val(h->vals[f1].rows, 4 * C);
     { Op& o = push(OP_GEGLU); o.x = f1; o.y = gg; }
     int t3 = linear(gg, {tb + ".ff.net.2.weight"}, {tb + ".ff.net.2.bias"}, C, t2);
@@ -564,6 +575,29 @@ int run_gemm_fwd(pb_handle* h, const Op& o, int nb, bool primal, pb_stream st) {
     g.seg[0].B = h->Wf16(o.w); g.ab_dtype = PB_GEMM_F16; g.d_dtype = PB_GEMM_F16; g.round_tf32 = 0;
   }
   CK(gemm_call(h, g, st));
+  return PB_OK;
+}
+// JVP of ff1 + GEGLU in one launch: d(a gelu(g)) = da gelu(g) + dg a gelu'(g) combined in the GEMM epilogue from the factor cache
+bool can_fuse_geglu(const pb_handle* h, const Op& o, const Op* next) {
+  static const int env_mink = getenv("PB_FUSE_GEGLU_MINK") ? atoi(getenv("PB_FUSE_GEGLU_MINK")) : -1;   // A/B switch
+  const int mink = env_mink >= 0 ? env_mink : h->fuse_geglu_min_k;
+  return h->fuse_geglu && h->t16 && next && o.kind == OP_GEMM && next->kind == OP_GEGLU && next->x == o.y && !o.conv && o.res < 0 &&
+         h->wspecs[o.w].fwd16g_off != 0 && h->vals[o.x].C >= mink;
+}
+int run_gemm_geglu_jvp(pb_handle* h, const Op& o, const Op& ge, int nb, pb_stream st) {
+  const Val& vx = h->vals[o.x]; const Val& vy = h->vals[o.y]; const Val& vo = h->vals[ge.y];
+  PbGemm g = plain_gemm(h->T(o.x), vx.C, vx.rows * nb, reinterpret_cast<const float*>(h->packed + h->wspecs[o.w].fwd16g_off), vx.C, vy.C, vx.C,
+                        h->T(ge.y), vo.C);
+  g.ab_dtype = PB_GEMM_F16; g.d_dtype = PB_GEMM_F16; g.round_tf32 = 0;
+  g.gg = h->P(o.y); g.gg_F = vo.C; g.gg_rows_p = vy.rows; g.gg_k_slot = h->ks(nb); g.gg_p_stride = h->pstride_f();
+  const double flops = 2.0 * g.M * g.N * vx.C;
+  h->probe_f16 = 1;
+  if (h->profiling) {
+    char b[160];
+    snprintf(b, sizeof b, "gemm+geglu M=%d N=%d K=%d nseg=1 nb=1 nh=1 conv=0 HW=0x0 res=0 ab16=1 d16=1", g.M, g.N, vx.C);
+    h->probe_label = b;
+  }
+  CK(probed(h, PB_PROBE_GEMM, flops, st, [&] { return pbk_gemm(&g, st); }));   // no split-K scratch: the epilogue is not a plain sum
   return PB_OK;
 }
 // gx (+)= gy (*) W^T ; gres (+)= gy
@@ -1032,6 +1066,11 @@ int run_jvp(pb_handle* h, const float* V, int nb, float* U, pb_stream st) {
   }
   for (size_t oi = first; oi < h->ops.size(); ++oi) {
     const Op& o = h->ops[oi];
+    if (can_fuse_geglu(h, o, oi + 1 < h->ops.size() ? &h->ops[oi + 1] : nullptr)) {
+      if (int e = run_gemm_geglu_jvp(h, o, h->ops[oi + 1], nb, st)) return e;
+      ++oi;                                     // the GEGLU op ran in the GEMM's epilogue
+      continue;
+    }
     if (h->slots > 1 && per_slot_op(h, o)) {
       for (int p = 0; p < h->slots; ++p) {
         h->slot = p;
@@ -1330,7 +1369,7 @@ PB_API int pb_set_option(pb_handle* h, const char* name, int value) {
   struct { const char* n; int* p; bool rebind; } opts[] = {
       {"round_primal", &h->rnd_p, false}, {"round_tangent", &h->rnd_t, false}, {"round_weights", &h->rnd_w, true},
       {"precise_primal", &h->prec_p, false}, {"precise_tangent", &h->prec_t, false}, {"precise_attn", &h->prec_a, false},
-      {"fused_min_tokens", &h->fused_min_tokens, false}};
+      {"fused_min_tokens", &h->fused_min_tokens, false}, {"fuse_geglu", &h->fuse_geglu, false}};
   if (!strcmp(name, "f16_operands")) {          // changes the plan (fp16 weight copies, operand dtypes): plan again
     if (value && !pbk_has_f16_operands()) return fail(h, PB_EINVAL, "this backend has no fp16-operand GEMMs");
     h->f16 = value ? 1 : 0; h->planned = h->bound = h->point = false; drop_graph(h);
@@ -1458,6 +1497,7 @@ PB_API int pb_bind_weights(pb_handle* h, const pb_tensor_desc* table, int32_t n,
       const size_t n = (size_t)s.out * s.in * ((s.kind == WK_CONV3 || s.kind == WK_CONV3_S2) ? 9 : 1);
       CK(pbk_to_f16(h->packed + s.fwd16_off, reinterpret_cast<const float*>(h->packed + s.fwd_off), n, stream));
       CK(pbk_to_f16(h->packed + s.bwd16_off, reinterpret_cast<const float*>(h->packed + s.bwd_off), n, stream));
+      if (s.fwd16g_off) CK(pbk_interleave_rows16(h->packed + s.fwd16g_off, h->packed + s.fwd16_off, s.out / 2, s.in, stream));
     }
   }
   h->bound = true;

@@ -68,6 +68,7 @@ struct alignas(64) Params {
   long ldd, sDb, sDh, ldr, sRb, sRh;
   float alpha, beta;
   int round_tf32;
+  const float* gg; int gg_F; unsigned gg_rows_p, gg_k_slot; long gg_p_stride;   // GEGLU tangent epilogue (PbGemm::gg)
   long long* trace;                    // PB_GEMM_TRACE: per-item clocks of CTA 0 ([item][8]: producer begin / end, MMA begin / end, epilogue begin / end)
 };
 
@@ -240,9 +241,14 @@ __device__ __forceinline__ void stage_chunk(uint8_t* buf, int r, const uint32_t 
 // arrive on the empty / accumulator-full barriers of BOTH CTAs (multicast); the epilogue warps of both CTAs release an
 // accumulator stage on the leader's barrier (8 arrivals).  Epilogue, staging, residual and split-K paths are per CTA and
 // unchanged.
-template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false>
+// GEGLU (pair kernel, BN = 256, fp16 out): the tangent of ff1 never reaches HBM.  The weight rows are interleaved in blocks of 64
+// ([32 a rows | the 32 matching gate rows]), so accumulator chunk 2i holds da and chunk 2i + 1 holds dg of output columns
+// n0 / 2 + 32 i ..; an epilogue group combines its chunk PAIRS with the cached factors, out = da * gelu(g) + dg * a gelu'(g)
+// (two 128-byte global reads per row and pair), and stores 32 output columns through the usual staging + TMA path.
+template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false, bool GEGLU = false>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ Params p) {
   static_assert(!PAIR || AB16, "the CTA-pair variant takes fp16 operands");
+  static_assert(!GEGLU || (PAIR && D16 && BN % 64 == 0), "the GEGLU epilogue belongs to the fp16 pair kernel");
   using OutT = typename std::conditional<D16, __half, float>::type;
   constexpr int KB_ELEMS = AB16 ? BK16 : BK;
   extern __shared__ uint8_t smem_raw[];
@@ -473,6 +479,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           for (int j = 0; j < 3 && eg + NG * j < ntma; ++j) prefetch_r(eg + NG * j, gch + j);
         __syncwarp();
       }
+      // GEGLU epilogue: factor-row pointers of the four rows whose pieces this lane fetches (row 8 it + lane / 4 of the warp's 32), and
+      // the pieces of the group's first two half-steps issued ahead of the accumulator wait
+      const float* gptr[4] = {nullptr, nullptr, nullptr, nullptr}; bool gok[4] = {false, false, false, false};
+      float4 gpre1[2][4], gpre2[2][4];
+      if constexpr (GEGLU) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const unsigned m = unsigned(t.m0 + q * 32 + it * 8 + (lane >> 2));
+          const unsigned img = m / p.gg_rows_p;
+          gptr[it] = p.gg + (long)(img / p.gg_k_slot) * p.gg_p_stride + (long)(m - img * p.gg_rows_p) * 2 * p.gg_F;
+          gok[it] = int(m) < p.M;
+        }
+#pragma unroll
+        for (int s0 = 0; s0 < 2; ++s0) {
+          const int fn = (t.n0 >> 1) + 32 * eg + s0 * 16 + 4 * (lane & 3);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            gpre1[s0][it] = gok[it] ? __ldg(reinterpret_cast<const float4*>(gptr[it] + fn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gpre2[s0][it] = gok[it] ? __ldg(reinterpret_cast<const float4*>(gptr[it] + p.gg_F + fn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
       if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && li < 64) p.trace[li * 8 + 6] = clock64();
       mbar_wait(&tmem_full_bar[as], (li >> 1) & 1);
       tcgen05_fence_after();
@@ -486,6 +514,95 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         }
       }
 
+      if constexpr (GEGLU) {
+        // half-steps s = (pair, 16-column half) of this group.  The factors of a half-step (64 bytes per row and operand) are
+        // loaded COALESCED -- lane l fetches 16-byte piece l % 4 of row 8 it + l / 4 of its warp's 32 rows, four trips per operand --
+        // TWO half-steps ahead into registers (the first two were issued before the accumulator wait; carrying them over from the
+        // CTA's previous tile instead spilled 256 bytes per thread and was slower), pass through a per-warp
+        // scratch tile in the staging area (swizzled like the output rows: conflict-free both ways) and come back as the
+        // thread's own row.  One row per thread straight from global memory made every LDG.128 a 32-sector request with
+        // ~4000 clocks of latency: 552 us for the 102400 x 2560 x 320 launch against 307 us of the two separate kernels.
+        constexpr int NPAIR = BN / 64, NSTEP = 2 * (NPAIR / NG);
+        static_assert(NPAIR % NG == 0, "pairs split evenly over the epilogue groups");
+        uint8_t* scr1 = gstaging + 2 * (EPI_BYTES / 2);               // buffers 2, 3 of the group: factor scratch (G1, G2)
+        uint8_t* scr2 = gstaging + 3 * (EPI_BYTES / 2);
+        const uint32_t swz = uint32_t((r >> 1) & 3);
+        float4 pf1[3][4], pf2[3][4];                                  // pieces in flight: [step % 3][trip]
+#pragma unroll
+        for (int it = 0; it < 4; ++it) { pf1[0][it] = gpre1[0][it]; pf2[0][it] = gpre2[0][it]; pf1[1][it] = gpre1[1][it]; pf2[1][it] = gpre2[1][it]; }
+#pragma unroll
+        for (int s = 0; s < NSTEP; ++s) {
+          const int i = eg + NG * (s >> 1), hh = s & 1, cur = s % 3;
+          const int f0 = (t.n0 >> 1) + 32 * i;                        // first output column of the pair
+          if (s + 2 < NSTEP) {
+            const int fn = (t.n0 >> 1) + 32 * (eg + NG * ((s + 2) >> 1)) + ((s + 2) & 1) * 16 + 4 * (lane & 3);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              pf1[(s + 2) % 3][it] = gok[it] ? __ldg(reinterpret_cast<const float4*>(gptr[it] + fn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              pf2[(s + 2) % 3][it] = gok[it] ? __ldg(reinterpret_cast<const float4*>(gptr[it] + p.gg_F + fn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          // pieces of this half-step -> scratch rows of this warp -> the thread's own row
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = q * 32 + it * 8 + (lane >> 2);
+            const uint32_t off = uint32_t(row * 64) + ((uint32_t(lane & 3) ^ uint32_t((row >> 1) & 3)) << 4);
+            *reinterpret_cast<float4*>(scr1 + off) = pf1[cur][it];
+            *reinterpret_cast<float4*>(scr2 + off) = pf2[cur][it];
+          }
+          __syncwarp();
+          float4 a4[4], c4[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            a4[qq] = *reinterpret_cast<const float4*>(scr1 + r * 64 + ((uint32_t(qq) ^ swz) << 4));
+            c4[qq] = *reinterpret_cast<const float4*>(scr2 + r * 64 + ((uint32_t(qq) ^ swz) << 4));
+          }
+          __syncwarp();
+          const uint32_t ob = gch & 1u;                               // output buffers 0, 1 of the group
+          uint8_t* sbuf = gstaging + ob * uint32_t(EPI_BYTES / 2);
+          uint8_t* srow = sbuf + r * 64;
+          uint32_t va[16], vg[16];
+          tmem_ld16(acc + uint32_t((2 * i) * EPI_W + hh * 16), va);
+          tmem_ld16(acc + uint32_t((2 * i + 1) * EPI_W + hh * 16), vg);
+          if (s == NSTEP - 1) {                                       // the group's last read of this accumulator stage
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + uint32_t(as) * 8u);
+          }
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {                            // 8 columns = one 16-byte piece of the staging row
+            const float4 a0 = a4[2 * qq], a1 = a4[2 * qq + 1], c0 = c4[2 * qq], c1 = c4[2 * qq + 1];
+            const float w1[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float w2[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              o[e] = fmaf(__uint_as_float(va[8 * qq + e]), w1[e], __uint_as_float(vg[8 * qq + e]) * w2[e]);
+            uint4 ov;
+            __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(o[2 * e], o[2 * e + 1]);
+            *reinterpret_cast<uint4*>(srow + ((uint32_t(hh * 2 + qq) ^ swz) << 4)) = ov;
+          }
+          if (hh == 1) {
+            fence_proxy_async_smem();
+            if (w0) {                                                 // two output buffers: the previous pair's store must have been read
+              if (elect_one()) bulk_wait_read<0>();
+              __syncwarp();
+            }
+            named_bar_sync(bar_id, 128);
+            if (w0) {
+              if (elect_one()) {
+                tma_store_4d(&p.mapD, sbuf, f0, t.m0, 0, 0);
+                bulk_commit();
+              }
+              __syncwarp();
+            }
+            ++gch;
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = eg; c < nchunks; c += NG) {
         const int nc = t.n0 + c * EPI_W;
@@ -687,12 +804,12 @@ static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
 static int sm_count() { return pbhost::sm_count(); }
 
-template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false>
+template <int BN, int STAGES, bool AB16, bool D16, bool PAIR = false, bool GEGLU = false>
 static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
   using S = Smem<BN, STAGES, PAIR>;
   static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
   static_assert(2 * BN <= 512 && BN <= ACC_STRIDE, "two accumulator stages must fit TMEM");
-  if (const char* err = pbhost::optin_smem(gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR>, S::TOTAL)) return err;
+  if (const char* err = pbhost::optin_smem(gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR, GEGLU>, S::TOTAL)) return err;
   cudaError_t e;
   if constexpr (PAIR) {
     cudaLaunchConfig_t cfg = {};
@@ -701,7 +818,7 @@ static const char* launch_t(const Params& p, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR>, p);
+    e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AB16, D16, PAIR, GEGLU>, p);
   } else {
     gemm_tc_kernel<BN, STAGES, AB16, D16><<<grid, NTHREADS, S::TOTAL, st>>>(p);
     e = cudaGetLastError();
@@ -784,6 +901,14 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   p.D = g.D; p.R = g.R; p.bias = g.bias;
   p.ldd = g.ldd; p.sDb = g.sDb; p.sDh = g.sDh; p.ldr = g.ldr; p.sRb = g.sRb; p.sRh = g.sRh;
   p.alpha = g.alpha; p.beta = g.R ? g.beta : 0.f; p.round_tf32 = g.round_tf32;
+  const bool geglu = g.gg != nullptr;
+  if (geglu) {
+    if (!ab16 || !d16 || g.nseg != 1 || g.conv || g.nb != 1 || g.nh != 1 || g.R || g.bias || g.alpha != 1.f || g.N != 2 * g.gg_F ||
+        g.gg_F % 128 || g.gg_rows_p <= 0 || (reinterpret_cast<uintptr_t>(g.gg) & 15) || (g.gg_p_stride % 4))
+      return "gemm: the GEGLU epilogue takes an fp16 plain GEMM (nb = nh = 1, no residual / bias, alpha = 1) with N = 2 F, F % 128 == 0";
+    p.gg = g.gg; p.gg_F = g.gg_F; p.gg_rows_p = unsigned(g.gg_rows_p);
+    p.gg_k_slot = g.gg_k_slot > 0 ? unsigned(g.gg_k_slot) : 0x7fffffffu; p.gg_p_stride = g.gg_k_slot > 0 ? g.gg_p_stride : 0;
+  }
   if ((g.ldd % dq) || (g.R && (g.ldr % dq)) || (reinterpret_cast<uintptr_t>(g.D) & 15) ||
       (g.R && (reinterpret_cast<uintptr_t>(g.R) & 15)) || (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)))
     return "gemm: D/R/bias must be 16-byte aligned with a leading dimension that is a multiple of 16 bytes";
@@ -816,6 +941,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   int pair = 0;
   int nsm_eff = nsm;
   const int kb_tile = (g.conv ? 9 : 1) * ((g.seg[0].K + KB - 1) / KB);   // k-blocks per tile
+  if (geglu && (!g_pair || pair_clusters() <= 0)) return "gemm: the GEGLU epilogue needs the CTA-pair kernel";
   if (g_pair && ab16 && g.nseg == 1 && (g.conv || (g.nb == 1 && g.nh == 1)) && g.N >= EPI_W &&
       (g.N % 256 == 0 || g.N % 160 == 0) && (!g_force_bn || g_force_bn == 160 || g_force_bn == 256)) {
     const int ncl = pair_clusters();
@@ -825,7 +951,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
     // K) gain from the pair MMA as well (62 -> 49 us), the short ones do not
     static const long pair_min_env = getenv("PB_GEMM_PAIR_MIN") ? atol(getenv("PB_GEMM_PAIR_MIN")) : 0;
     const long pair_min = pair_min_env ? pair_min_env : (kb_tile >= 64 ? 48 : 2L * ncl);
-    if (ncl > 0 && g.N % pbn == 0 && ptiles >= pair_min) { pair = 1; BN = pbn; nsm_eff = 2 * ncl; mt = ((mt + 1) / 2) * 2; }
+    if (geglu && (pbn != 256 || g_force_bn)) return "gemm: the GEGLU epilogue needs 256-column tiles";
+    if (ncl > 0 && g.N % pbn == 0 && (ptiles >= pair_min || geglu)) { pair = 1; BN = pbn; nsm_eff = 2 * ncl; mt = ((mt + 1) / 2) * 2; }
   }
   p.pair = pair;
   const long nt = (g.N + BN - 1) / BN;
@@ -895,8 +1022,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
       p.r_bytes = uint32_t(p.bw * p.bh * p.bb) * EPI_W * des;
     } else {
       int hm, bm;
-      err = encode_plainx(&p.mapD, g.D, d16, g.M, g.N, g.ldd, g.sDh, g.nh, g.sDb, g.nb, EPI_W, BM, swz, &p.d_hmul, &p.d_bmul,
-                          &p.r_bytes);
+      err = encode_plainx(&p.mapD, g.D, d16, g.M, geglu ? g.gg_F : g.N, g.ldd, g.sDh, g.nh, g.sDb, g.nb, EPI_W, BM, swz, &p.d_hmul,
+                          &p.d_bmul, &p.r_bytes);
       if (err) return err;
       if ((g.nh > 1 && !p.d_hmul) || (g.nb > 1 && !p.d_bmul)) return "gemm: D needs a stride for every batch dimension";
       if (g.R) {
@@ -915,7 +1042,7 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   // when the K loop is deep enough for the saving to outweigh the reduction pass
   long full = tiles, tail = 0;
   static const int env_min_kb = getenv("PB_SPLIT_MIN_KB") ? atoi(getenv("PB_SPLIT_MIN_KB")) : 0;     // A/B switch
-  if (g_split && g.ws && ktot >= (env_min_kb ? env_min_kb : g_split_min_kb)) {
+  if (g_split && g.ws && !geglu && ktot >= (env_min_kb ? env_min_kb : g_split_min_kb)) {
     tail = tiles % nsm_eff;
     // split count of the tail wave: minimise (rounds the tail items need) x (k-blocks per item); a tail of 80 tiles is
     // better cut in 5 (3 rounds of 1/5) than run whole on 80 of the 148 SMs
@@ -958,7 +1085,8 @@ const char* pb_gemm_launch(const PbGemm& g, cudaStream_t st) {
   }
   const int grid = (int)std::min<long>(p.items, nsm_eff);
   const char* lerr;
-  if (pair) lerr = d16 ? launch_pair<true>(BN, p, grid, st) : launch_pair<false>(BN, p, grid, st);
+  if (geglu) lerr = pair ? launch_t<256, 5, true, true, true, true>(p, grid, st) : "gemm: the GEGLU epilogue needs the CTA-pair kernel";
+  else if (pair) lerr = d16 ? launch_pair<true>(BN, p, grid, st) : launch_pair<false>(BN, p, grid, st);
   else if (ab16) lerr = d16 ? launch_bn<true, true>(BN, p, grid, st) : launch_bn<true, false>(BN, p, grid, st);
   else lerr = d16 ? launch_bn<false, true>(BN, p, grid, st) : launch_bn<false, false>(BN, p, grid, st);
   if (env_trace && !lerr) {          // debugging aid: synchronous dump of CTA 0's per-item clocks

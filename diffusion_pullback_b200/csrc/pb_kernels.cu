@@ -756,6 +756,16 @@ __global__ void ln_lin_k(const float* __restrict__ xp, const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // GEGLU
 // ------------------------------------------------------------------------------------------------
+// ff1 weight [2 F][cols] halves -> blocks of 64 rows [32 rows of the a half | the 32 matching rows of the gate half] (PbGemm::gg)
+__global__ void interleave_rows16_k(uint4* __restrict__ dst, const uint4* __restrict__ src, int F, int c8) {
+  const long total = 2L * F * c8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int row = int(i / c8), c = int(i % c8);
+    const int j = row >> 6, e = row & 63;
+    const int srow = e < 32 ? 32 * j + e : F + 32 * j + (e - 32);
+    dst[i] = src[(long)srow * c8 + c];
+  }
+}
 // prepare: [a | g] -> [gelu(g) | a gelu'(g)] in place, the factors of the linearisation (read by geglu_jvp_k / geglu_vjp_k)
 __global__ void geglu_fwd_k(float* __restrict__ h, long rows, int F, float* __restrict__ y, int rnd, int prepare) {
   const int F4 = F / 4;
@@ -1496,6 +1506,14 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 }
 
 // ---- GEGLU ----
+extern "C" __attribute__((visibility("default"))) int pbk_gemm_geglu_supported() { return 1; }
+PBK pbk_interleave_rows16(void* dst, const void* src, int F, int cols, pb_stream st) {
+  if (F % 32 || cols % 8 || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15))
+    return "interleave_rows16: F % 32 == 0, cols % 8 == 0 and 16-byte aligned matrices";
+  const long total = 2L * F * (cols / 8);
+  interleave_rows16_k<<<grid_for(total, 256, 16), 256, 0, S(st)>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src), F, cols / 8);
+  return last_err();
+}
 PBK pbk_geglu_fwd(float* h, long rows, int F, float* y, int round_tf32, int prepare, pb_stream st) {
   CHECK_ALIGN4(F, "geglu: F");
   geglu_fwd_k<<<grid_for(rows * (F / 4), 256, 16), 256, 0, S(st)>>>(h, rows, F, y, round_tf32, prepare);

@@ -44,6 +44,13 @@ struct PbGemm {
   // problem slots (plain mode): batch index b belongs to problem b / k_slot; an operand whose batch stride (sAb / sBb) is 0 is
   // PRIMAL and the copy of problem s starts p_stride BYTES after problem s - 1's.  k_slot <= 0 or >= nb: one problem.
   int k_slot; long p_stride;
+  // GEGLU tangent epilogue (JVP of ff1 fused with the GEGLU linearisation; nullptr: off).  B holds the 2 F weight rows INTERLEAVED in
+  // blocks of 64 ([32 rows of the a half | the 32 matching rows of the gate half], pbk_interleave_rows16), N = 2 F, and
+  //   D[m][f] = acc_a[m][f] * G1[m'][f] + acc_g[m][f] * G2[m'][f],   f < F,  D is [M][ldd >= F] halves,
+  // with [G1 | G2] = gg[m'] the prepared factor cache [gelu(g) | a gelu'(g)] of pbk_geglu_fwd ([gg_rows_p][2 F] floats per
+  // problem; m' = m % gg_rows_p, problem = (m / gg_rows_p) / gg_k_slot at gg_p_stride floats).  fp16 operands and output, plain
+  // mode, nb = nh = 1, no residual / bias, alpha = 1, F % 128 == 0; pbk_gemm_geglu_supported() tells whether the backend has it.
+  const float* gg; int gg_F; long gg_rows_p; int gg_k_slot; long gg_p_stride;
 };
 
 static inline PbGemm pb_gemm_init() {

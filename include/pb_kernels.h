@@ -100,6 +100,10 @@ PBK pbk_ln_fwd(const float* x, long rows, int C, const float* gamma, const float
 PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const float* gamma, long rows_p, int C,
                const float* t, int nb, int mode, float* out, float acc, int round_tf32, int k_slot, long p_stride, pb_stream st);
 
+// the GEMM's GEGLU tangent epilogue (PbGemm::gg) exists in this backend; the interleaved copy of the ff1 weight it takes:
+// dst rows [64 j, 64 j + 32) = src rows [32 j, ...), dst rows [64 j + 32, 64 j + 64) = src rows [F + 32 j, ...); halves, F % 32 == 0
+extern "C" __attribute__((visibility("default"))) int pbk_gemm_geglu_supported();
+PBK pbk_interleave_rows16(void* dst, const void* src, int F, int cols, pb_stream st);
 // ---- GEGLU: y = h[:, :F] * gelu_erf(h[:, F:]) ----
 // prepare != 0: h = [a | g] is then overwritten IN PLACE with the linearisation factors [gelu(g) | a gelu'(g)], the form
 // pbk_geglu_jvp / _vjp read (no erf / exp per element and iteration: the two linearisation kernels were ALU-bound on them)

@@ -186,6 +186,43 @@ def test_gemm_f16_cta_pair_conv3x3(nb, H, W, Ci, Co):
     assert torch.equal(outs[1], outs[2])
 
 
+@pytest.mark.parametrize("P,k,rows_p,Cc", [(1, 3, 1024, 320), (2, 2, 700, 640), (3, 1, 256, 160 * 8)])
+def test_gemm_geglu_tangent_epilogue(P, k, rows_p, Cc):
+    """ff1 tangent GEMM with the GEGLU linearisation in its epilogue (PbGemm::gg: interleaved weight rows, factor cache per problem)
+    against the two separate kernels (GEMM -> pbk_geglu_jvp) and fp64."""
+    torch.manual_seed(P + k + Cc)
+    Fd = 4 * Cc if Cc <= 640 else 1280
+    nb = P * k
+    M = nb * rows_p
+    w = (torch.randn(2 * Fd, Cc, device="cuda") / math.sqrt(Cc)).half()
+    wi = torch.empty_like(w)
+    _ok(N.leaf("pbk_interleave_rows16")(_p(wi), _p(w), Fd, Cc, _st()))
+    ref_i = torch.stack([w[:Fd].view(Fd // 32, 32, Cc), w[Fd:].view(Fd // 32, 32, Cc)], 1).reshape(2 * Fd, Cc)
+    assert torch.equal(wi, ref_i)
+    ps = rows_p * 2 * Fd + 64                                        # floats between the problems' factor caches
+    hp = torch.randn(P, ps, device="cuda")
+    dx = torch.randn(M, Cc, device="cuda").half()
+    # separate path
+    dh = torch.empty(M, 2 * Fd, device="cuda", dtype=torch.float16)
+    gemm16(dx, w, dh, M=M, N_=2 * Fd, K=Cc, lda=Cc, ldb=Cc, ldd=2 * Fd)
+    sep = torch.empty(M, Fd, device="cuda", dtype=torch.float16)
+    _ok(N.leaf("pbk_geglu_jvp")(_p(hp), C.c_long(rows_p), _p(dh), nb, Fd, _p(sep), 2 | 4, k if P > 1 else 0, C.c_long(ps if P > 1 else 0), _st()))
+    # fused
+    g = N.PbGemm()
+    g.M, g.N, g.nseg = M, 2 * Fd, 1
+    sg = g.seg[0]
+    sg.A, sg.lda, sg.B, sg.ldb, sg.K = dx.data_ptr(), Cc, wi.data_ptr(), Cc, Cc
+    out = torch.full((M, Fd), float("nan"), device="cuda", dtype=torch.float16)
+    g.D, g.ldd, g.alpha, g.nb, g.nh, g.ab_dtype, g.d_dtype = out.data_ptr(), Fd, 1.0, 1, 1, 1, 1
+    g.gg, g.gg_F, g.gg_rows_p, g.gg_k_slot, g.gg_p_stride = hp.data_ptr(), Fd, rows_p, (k if P > 1 else 0), (ps if P > 1 else 0)
+    _ok(N.leaf("pbk_gemm")(C.byref(g), _st()))
+    fac = hp[:, :rows_p * 2 * Fd].view(P, 1, rows_p, 2 * Fd).expand(P, k, rows_p, 2 * Fd).reshape(M, 2 * Fd).double()
+    acc = dx.double() @ w.double().T
+    ref = acc[:, :Fd] * fac[:, :Fd] + acc[:, Fd:] * fac[:, Fd:]
+    assert rel(out, ref) < 6e-4
+    assert rel(out.float(), sep.float()) < 1e-3                     # the separate path rounds dh to halves in between
+
+
 def test_gemm_f16_attention_batched():
     """Head-strided fp16 operands, fp32 scores out, then probabilities x V^T with a broadcast A (raster_b path)."""
     torch.manual_seed(1)
