@@ -806,7 +806,8 @@ const char* launch(const PbAttnLin& a, cudaStream_t st, bool* handled) {
     static const bool ns4 = getenv("PB_ATTN_NS4") != nullptr;
     int s = std::min(MAX_NS, (TMEM_COLS - k * p.accw_tot) / TN) & ~1;
     if (s < (ns4 ? 4 : 2)) continue;
-    const int pc0 = has_pc ? 4 : 0;
+    static const int pc0_env = getenv("PB_ATTN_PC0") ? atoi(getenv("PB_ATTN_PC0")) : 4;      // A/B switch: per-column ring depth the search starts from
+    const int pc0 = has_pc ? std::max(2, pc0_env & ~1) : 0;
     // the accumulate warp releases a shared stage LAG = 2 substeps after the P . C2 product of the same substep, and that
     // product may already need the stage NSH steps on: kc_min * (NSH - 1) >= LAG + 1 or the ring dead-locks
     const int kmin = k_slot / g;

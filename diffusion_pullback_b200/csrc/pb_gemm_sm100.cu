@@ -7,8 +7,12 @@
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (the whole warp walks the loop, one elected lane issues; kind::tf32
 //                 or kind::f16, fp32 accumulators in TMEM, two accumulator stages so the epilogue of item i overlaps the
 //                 main loop of item i + 1)
-//   warps 2..5  : epilogue: tcgen05.ld 32x32b -> alpha / bias / residual / RNA rounding -> 128B-swizzled smem staging
+//   warps 2..5  : epilogue group 0: tcgen05.ld 32x32b -> alpha / bias / residual / RNA rounding -> 128B-swizzled smem staging
 //                 -> TMA tensor store (the residual tile arrives by TMA into the same staging buffer, 3 chunks ahead)
+//   warps 6..9  : epilogue group 1 (fp16-output kernels): the groups take alternate 32-column chunks of every tile
+// CTA-pair variant (PAIR, fp16 operands): the two CTAs of a cluster run tiles 2j, 2j + 1 as ONE 256-row
+// tcgen05.mma.cta_group::2 issued by the leader; each CTA stages its 128 rows of A and half of the B tile (see the kernel).
+// GEGLU variant of the pair kernel: the GEGLU linearisation of the ff1 tangent in the epilogue (PbGemm::gg).
 // smem: STAGES x (A 16 KB + B BN*128 B) operand ring with full/empty mbarriers (MMA completion by tcgen05.commit)
 // + 4 x 16 KB staging buffers.
 // Scheduling: output tiles are dealt round-robin to the CTAs.  The tiles of the last, partial wave (all tiles when there
