@@ -304,6 +304,82 @@ __global__ void __launch_bounds__(256) ln16_k(const float* __restrict__ xp, cons
   }
 }
 
+// LayerNorm linearisation for C = 64 NV4 exactly (C = 320: NV4 = 5, C = 640: NV4 = 10): HALF a warp per token, NV4 vectors of FOUR
+// channels per lane.  The eight-channel vectors of ln16_k leave 8 of 40 lane-vectors at C = 320 to a second, 25 %-occupied pass;
+// here every lane is busy and a warp keeps two tokens in flight.  Same arithmetic and summation tree per token as ln16_k up to the
+// order of the partial sums.
+template <int MODE, int NV4>
+__global__ void __launch_bounds__(256) ln16h_k(const float* __restrict__ xp, const float* __restrict__ mean,
+                                               const float* __restrict__ rstd, const float* __restrict__ gamma, long rows_p,
+                                               const __half* __restrict__ t, long rows, __half* __restrict__ out, float acc,
+                                               int k_slot, long p_stride) {
+  constexpr int C = 64 * NV4;
+  const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+  const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long nw = ((long)gridDim.x * blockDim.x) >> 5;
+  const float invC = 1.f / (float)C;
+  const unsigned rp32 = unsigned(rows_p);
+  for (long r0 = 2 * warp; r0 < rows; r0 += 2 * nw) {
+    const long r = r0 + half;
+    const bool ok = r < rows;
+    const unsigned img = ok ? unsigned(r) / rp32 : 0u;
+    const long rp = ok ? long(unsigned(r) - img * rp32) : 0;
+    const long ps = long(img / unsigned(k_slot)) * p_stride;
+    const float* xr = xp + ps + rp * C;
+    const __half* tr = t + (ok ? r : 0) * C;
+    __half* orow = out + (ok ? r : 0) * C;
+    const float m = mean[ps + rp], rs = rstd[ps + rp];
+    float xh[NV4][4], tv[NV4][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int c = (hl + 16 * i) * 4;
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const uint2 tu = ok ? *reinterpret_cast<const uint2*>(tr + c) : make_uint2(0u, 0u);
+      const float2 ta = __half22float2(*reinterpret_cast<const __half2*>(&tu.x)), tb = __half22float2(*reinterpret_cast<const __half2*>(&tu.y));
+      xh[i][0] = (xv.x - m) * rs; xh[i][1] = (xv.y - m) * rs; xh[i][2] = (xv.z - m) * rs; xh[i][3] = (xv.w - m) * rs;
+      tv[i][0] = ta.x; tv[i][1] = ta.y; tv[i][2] = tb.x; tv[i][3] = tb.y;
+      if (MODE == 1) {
+        const float4 gq = *reinterpret_cast<const float4*>(gamma + c);
+        tv[i][0] *= gq.x; tv[i][1] *= gq.y; tv[i][2] *= gq.z; tv[i][3] *= gq.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s1 += tv[i][e]; s2 = fmaf(xh[i][e], tv[i][e], s2); }
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {                       // over the 16 lanes of the token
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * invC, m2 = s2 * invC;
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int c = (hl + 16 * i) * 4;
+        float o[4];
+        if (MODE == 0) {
+          const float4 gq = *reinterpret_cast<const float4*>(gamma + c);
+          const float g4[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = g4[e] * rs * (tv[i][e] - m1 - xh[i][e] * m2);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = rs * (tv[i][e] - m1 - xh[i][e] * m2);
+        }
+        if (acc != 0.f) {
+          const uint2 pu = *reinterpret_cast<const uint2*>(orow + c);
+          const float2 pa = __half22float2(*reinterpret_cast<const __half2*>(&pu.x)), pb = __half22float2(*reinterpret_cast<const __half2*>(&pu.y));
+          o[0] += acc * pa.x; o[1] += acc * pa.y; o[2] += acc * pb.x; o[3] += acc * pb.y;
+        }
+        uint2 ou;
+        *reinterpret_cast<__half2*>(&ou.x) = __floats2half2_rn(o[0], o[1]);
+        *reinterpret_cast<__half2*>(&ou.y) = __floats2half2_rn(o[2], o[3]);
+        *reinterpret_cast<uint2*>(orow + c) = ou;
+      }
+    }
+  }
+}
+
 // dst[r][c] = src[r][c] + beta * dst[r][c] over halves, 8 per access
 __global__ void copy2d16_k(__half* __restrict__ dst, long ldd, const __half* __restrict__ src, long lds, long rows, int cols8,
                            float beta) {
@@ -439,6 +515,15 @@ const char* ln_lin(const float* xp, const float* mean, const float* rstd, const 
   if (k_slot < 1) k_slot = nb;
   const long rows = rows_p * nb;
   if (rows >= (1L << 31)) return "layernorm: too many rows for 32-bit indexing";
+  static const bool no_half = getenv("PB_LN_HALFWARP") && atoi(getenv("PB_LN_HALFWARP")) == 0;     // A/B switch
+  if (!no_half && (C == 320 || C == 640)) {                  // half a warp per token (see ln16h_k)
+    const unsigned gridh = grid_for((rows + 1) / 2 * 32, 256, 8);
+#define PB_LN16H(M_, NV4_) ln16h_k<M_, NV4_><<<gridh, 256, 0, st>>>(xp, mean, rstd, gamma, rows_p, t, rows, out, acc, k_slot, p_stride)
+    if (C == 320) { if (mode == 0) PB_LN16H(0, 5); else PB_LN16H(1, 5); }
+    else { if (mode == 0) PB_LN16H(0, 10); else PB_LN16H(1, 10); }
+#undef PB_LN16H
+    return last_err();
+  }
   const unsigned grid = grid_for(rows * 32, 256, 8);
   const int nv = (C + 255) / 256;
 #define PB_LN16(M_, NV_) ln16_k<M_, NV_><<<grid, 256, 0, st>>>(xp, mean, rstd, gamma, rows_p, C, t, rows, out, acc, k_slot, p_stride)
