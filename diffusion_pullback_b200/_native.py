@@ -87,7 +87,18 @@ def raw() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -m diffusion_pullback_b200.build` "
                 "(there is no CPU or PyTorch fallback for the pullback hot path)")
         _raw = C.CDLL(LIB_PATH)
+        check_struct_layout(_raw)
     return _raw
+
+
+def check_struct_layout(L) -> None:
+    """The ctypes mirrors of PbGemm / PbAttnLin must have the size the library was compiled with (a field added on one side only
+    would make the C side read past the Python struct)."""
+    gb, ab = C.c_int(0), C.c_int(0)
+    L.pbk_struct_sizes(C.byref(gb), C.byref(ab))
+    if (gb.value, ab.value) != (C.sizeof(PbGemm), C.sizeof(PbAttnLin)):
+        raise RuntimeError(f"descriptor layout mismatch: library PbGemm / PbAttnLin = {gb.value} / {ab.value} bytes, "
+                           f"ctypes mirrors = {C.sizeof(PbGemm)} / {C.sizeof(PbAttnLin)}; rebuild the library or update _native.py")
 
 
 def lib() -> C.CDLL:

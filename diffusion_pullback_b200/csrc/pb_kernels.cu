@@ -1507,6 +1507,10 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 
 // ---- GEGLU ----
 extern "C" __attribute__((visibility("default"))) int pbk_gemm_geglu_supported() { return 1; }
+extern "C" __attribute__((visibility("default"))) void pbk_struct_sizes(int* gemm_bytes, int* attn_lin_bytes) {
+  if (gemm_bytes) *gemm_bytes = (int)sizeof(PbGemm);
+  if (attn_lin_bytes) *attn_lin_bytes = (int)sizeof(PbAttnLin);
+}
 PBK pbk_interleave_rows16(void* dst, const void* src, int F, int cols, pb_stream st) {
   if (F % 32 || cols % 8 || ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15))
     return "interleave_rows16: F % 32 == 0, cols % 8 == 0 and 16-byte aligned matrices";

@@ -162,6 +162,9 @@ struct PbAttnLin {
 };
 PBK pbk_attn_lin_supported(int d, int Mr, int Nc);    // nullptr if pbk_attn_lin handles this geometry
 PBK pbk_attn_lin(const PbAttnLin* a, pb_stream st);
+// sizeof(PbGemm) / sizeof(PbAttnLin) as this library was compiled: a binding that mirrors the two descriptors (ctypes in
+// diffusion_pullback_b200/_native.py) checks its layout against them at load time instead of passing a short struct
+extern "C" __attribute__((visibility("default"))) void pbk_struct_sizes(int* gemm_bytes, int* attn_lin_bytes);
 // debugging aid of the column-batched kernel (PB_ATTN_TRACE=1, scripts/trace_attn.py): per-substep event clocks of CTA (0, 0)
 // of the last launch, [512][16] values; returns the number of values copied
 extern "C" __attribute__((visibility("default"))) int pbk_attn16_trace_read(long long* host, int n);

@@ -326,6 +326,10 @@ PBK pbk_ln_lin(const float* xp, const float* mean, const float* rstd, const floa
 }
 // the GEGLU tangent epilogue of the GEMM is a device-backend fusion: the engine keeps the two separate ops on this double
 extern "C" __attribute__((visibility("default"))) int pbk_gemm_geglu_supported() { return 0; }
+extern "C" __attribute__((visibility("default"))) void pbk_struct_sizes(int* gemm_bytes, int* attn_lin_bytes) {
+  if (gemm_bytes) *gemm_bytes = (int)sizeof(PbGemm);
+  if (attn_lin_bytes) *attn_lin_bytes = (int)sizeof(PbAttnLin);
+}
 PBK pbk_interleave_rows16(void*, const void*, int, int, pb_stream) { return "interleave_rows16: not in the host double"; }
 PBK pbk_geglu_fwd(float* h, long rows, int F, float* y, int rnd, int prepare, pb_stream) {
   for (long r = 0; r < rows; ++r)

@@ -101,3 +101,21 @@ def test_plan_of_the_headline_workload_host_only():
         assert info.n_attn_p16 == 8                                           # all of them with fp16 probabilities and score operands
     finally:
         L.pb_destroy(h)
+
+
+def test_ctypes_descriptor_mirrors_match_the_library():
+    """PbGemm / PbAttnLin as mirrored in _native.py have the size the product library (and the host double) were compiled with:
+    a field added on one side only would make the C side read past the Python struct."""
+    from diffusion_pullback_b200 import _native as N
+    from diffusion_pullback_b200.build import build
+    from tests.hostsim.build import build as build_hostsim
+    for path in (build(), build_hostsim()):
+        N.check_struct_layout(C.CDLL(path))
+    short = type("Short", (C.Structure,), {"_fields_": N.PbGemm._fields_[:-1]})
+    saved = N.PbGemm
+    try:
+        N.PbGemm = short                                       # a mirror that lags the header is refused
+        with pytest.raises(RuntimeError):
+            N.check_struct_layout(C.CDLL(build()))
+    finally:
+        N.PbGemm = saved
